@@ -1,0 +1,92 @@
+"""Synthetic planning problems (no dataset files exist offline).
+
+Restates the obstacle / start-goal distributions of the reference's dataset generators so that
+benchmarks and parity tests run on inputs of the same shape as ``data/random_{2d,3d}``:
+
+* 3D: ``env_configs/random_3d.yml`` + ``generate_random_world_env_3d_raw.py:15-87``
+  (world 50^3, 6-9 boxes with sides 8-19, 6-9 balls with radius 8-11, integer coordinates,
+  clearance 2, start/goal integer points with squared distance > 50^2 outside inflated obstacles).
+* gamma_RRT* : ``datasets_3d/planning_problem_utils_3d.py:77-97`` (Monte-Carlo free volume).
+
+The reference validates start/goal pairs with A* (offline labelling, out of scope); here a pair is
+only required to be collision-free, so a problem may be infeasible -- planners then return all-inf.
+"""
+import math
+
+import numpy as np
+
+XYZ_MAX_3D = (50, 50, 50)
+
+
+def make_env_3d(seed):
+    """Returns an ``env_dict`` in the reference's json schema (rrt_env_3d.py:1-11)."""
+    rs = np.random.RandomState(seed)
+    xmax, ymax, zmax = XYZ_MAX_3D
+    n_boxes = rs.randint(6, 10)
+    n_balls = rs.randint(6, 10)
+    boxes, balls = [], []
+    while len(boxes) < n_boxes:
+        x, y, z = rs.randint(0, xmax), rs.randint(0, ymax), rs.randint(0, zmax)
+        w, h, d = rs.randint(8, 20), rs.randint(8, 20), rs.randint(8, 20)
+        if x < xmax - w and y < ymax - h and z < zmax - d:
+            boxes.append([int(x), int(y), int(z), int(w), int(h), int(d)])
+    while len(balls) < n_balls:
+        x, y, z = rs.randint(0, xmax), rs.randint(0, ymax), rs.randint(0, zmax)
+        r = rs.randint(8, 12)
+        if r < x < xmax - r and r < y < ymax - r and r < z < zmax - r:
+            balls.append([int(x), int(y), int(z), int(r)])
+    clearance = 2
+    box_a = np.asarray(boxes, dtype=np.float64)
+    ball_a = np.asarray(balls, dtype=np.float64)
+
+    def blocked(p):
+        in_box = np.any(np.all((box_a[:, :3] - clearance <= p) & (p <= box_a[:, :3] + box_a[:, 3:] + clearance), axis=1))
+        in_ball = np.any(((ball_a[:, :3] - p) ** 2).sum(axis=1) <= (ball_a[:, 3] + clearance) ** 2)
+        return bool(in_box or in_ball)
+
+    min_d2 = 50 ** 2
+    for attempt in range(100000):
+        if attempt == 2000:
+            min_d2 = 30 ** 2  # very cluttered worlds: relax, still a long query
+        sg = rs.randint(low=clearance, high=np.array(XYZ_MAX_3D) - clearance, size=(2, 3))
+        if ((sg[0] - sg[1]) ** 2).sum() > min_d2 and not blocked(sg[0]) and not blocked(sg[1]):
+            break
+    else:
+        raise RuntimeError("could not place start/goal")
+    return {
+        "env_dims": list(XYZ_MAX_3D),
+        "box_obstacles": boxes,
+        "ball_obstacles": balls,
+        "start": [sg[0].tolist()],
+        "goal": [sg[1].tolist()],
+    }
+
+
+def gamma_rrt_star_3d(env_dict, seed, n_points=100000):
+    """search_radius as compute_gamma_rrt_star_3d does it, with a private RandomState."""
+    rs = np.random.RandomState(seed)
+    dims = env_dict["env_dims"]  # (height, width, depth) -> y, x, z ranges (rrt_env_3d.py:6-9)
+    pts = np.stack([rs.uniform(0, dims[1], n_points), rs.uniform(0, dims[0], n_points),
+                    rs.uniform(0, dims[2], n_points)], axis=1)
+    box = np.asarray(env_dict["box_obstacles"], dtype=np.float64).reshape(-1, 6)
+    ball = np.asarray(env_dict["ball_obstacles"], dtype=np.float64).reshape(-1, 4)
+    inside = np.zeros(n_points, dtype=bool)
+    for b in box:
+        inside |= np.all((b[:3] <= pts) & (pts <= b[:3] + b[3:]), axis=1)
+    for b in ball:
+        inside |= ((pts - b[:3]) ** 2).sum(axis=1) < b[3] ** 2
+    free_vol = dims[0] * dims[1] * dims[2] * (1 - inside.mean())
+    return math.ceil((2 * (1 + 1. / 3)) ** (1. / 3) * (free_vol / (4. / 3. * np.pi)) ** (1. / 3))
+
+
+def make_problem_3d(env_idx, base_seed=100):
+    """A ``problem`` dict with the keys get_random_3d_problem_input returns
+    (planning_problem_utils_3d.py:62-75), minus the reference's own ``Env`` object (callers
+    wrap ``env_dict`` with whichever Env class they use)."""
+    env_dict = make_env_3d(base_seed + env_idx)
+    return {
+        "x_start": tuple(env_dict["start"][0]),
+        "x_goal": tuple(env_dict["goal"][0]),
+        "env_dict": env_dict,
+        "search_radius": gamma_rrt_star_3d(env_dict, base_seed + env_idx),
+    }
