@@ -1,0 +1,156 @@
+/*
+ * nirrt_b200.h -- C ABI of libnirrt_b200.so (sm_100a), the drop-in boundary of the NIRRT* hot path.
+ *
+ * The reference (tedhuang96/nirrt_star) has no native boundary: its hot path is Python/numpy
+ * (SURVEY.md section 8b).  This header is the boundary a maintainer binds with ctypes (see
+ * INTEGRATION.md); each entry point names the reference interface it replaces.  Plain pointers and
+ * sizes only, no torch types.  All `host` pointers are caller-owned host memory (pinned memory makes
+ * the copies asynchronous); `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *
+ * Conventions: every function returns 0 on success or a negative code; nirrt_last_error() returns a
+ * description for the calling thread.  A batch handle must not be used from two threads at once.
+ * Entry points whose name ends in _sync wait for the stream; the others only enqueue work.
+ */
+#ifndef NIRRT_B200_H
+#define NIRRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIRRT_OK 0
+#define NIRRT_ERR_INVALID -1      /* bad argument */
+#define NIRRT_ERR_CUDA -2         /* CUDA runtime error (message in nirrt_last_error) */
+#define NIRRT_ERR_CAPACITY -3     /* a device-side buffer overflowed (near candidates, solutions, vertices) */
+#define NIRRT_ERR_NO_DEVICE -4    /* no CUDA device / wrong architecture */
+
+#define NIRRT_MAX_OBSTACLES 32    /* per obstacle type and problem */
+
+/* planner families (path_planning_classes_3d/{rrt_star,irrt_star,nirrt_star_png}_3d.py) */
+#define NIRRT_VARIANT_RRT_STAR 0
+#define NIRRT_VARIANT_IRRT_STAR 1
+#define NIRRT_VARIANT_NIRRT_STAR 2
+/* loop drivers: planning() body (rrt_star_3d.py:36-55) / planning_random (rrt_star_3d.py:200-270,
+ * irrt_star_3d.py:245-331) */
+#define NIRRT_MODE_PLANNING 0
+#define NIRRT_MODE_PLANNING_RANDOM 1
+
+const char *nirrt_last_error(void);
+int nirrt_version(void);
+/* number of visible CUDA devices with compute capability 10.x; <= 0 means the library cannot run */
+int nirrt_device_count(void);
+
+typedef struct nirrt_batch nirrt_batch;
+
+typedef struct nirrt_batch_desc {
+    int dim;            /* 3 (2D worlds use nirrt2_* entry points) */
+    int n_envs;         /* E: independent planning problems advanced in lock step */
+    int capacity;       /* vertices per problem = 1 + iter_max (rrt_base_3d.py:25) */
+    int record_capacity;/* per-problem path_len_list rows (>= iter_max + iter_after_initial + 2) */
+    int near_capacity;  /* per-problem Near candidate buffer (entries); 0 = default 2048 */
+    int device;         /* CUDA device ordinal */
+} nirrt_batch_desc;
+
+/* Allocates the flat HBM state for E problems: SoA vertex coordinates (scan layout), 32-byte
+ * vertex records {x,y,z,parent} (cost-walk layout), obstacle tables, MT19937 streams. */
+int nirrt_batch_create(const nirrt_batch_desc *desc, nirrt_batch **out);
+int nirrt_batch_destroy(nirrt_batch *b);
+
+/* Problem upload == the arguments of RRTStar3D.__init__ / get_path_planner
+ * (rrt_star_3d.py:10-30,272-285) + Utils.__init__ (rrt_utils_3d.py:6-19), for all E problems.
+ *   start, goal      [E][3]
+ *   step_len, search_radius, clearance   [E]
+ *   range            [E][6]  x0 x1 y0 y1 z0 z1   (Env.x_range..., rrt_env_3d.py:6-9)
+ *   n_balls,n_boxes  [E]     each <= NIRRT_MAX_OBSTACLES
+ *   balls            [E][NIRRT_MAX_OBSTACLES][4]  x y z r
+ *   ball_r2          [E][NIRRT_MAX_OBSTACLES]     (r+clearance)**2 evaluated by numpy's scalar power
+ *                    (collision_check_utils_3d.py:21,31-37; libm pow is not x*x, so the host passes it)
+ *   boxes            [E][NIRRT_MAX_OBSTACLES][6]  x y z w h d
+ *   near_table       [capacity+2]  t[n] = (math.log(n)/n)**(1/3.)  (rrt_star_3d.py:134; libm on host)
+ *   rot_c            [E][9] IRRTStar3D.RotationToWorldFrame (irrt_star_3d.py:159-173, numpy SVD on host);
+ *                    may be NULL for RRT*.
+ * Resets every tree to the single start vertex. */
+int nirrt_batch_set_problems(nirrt_batch *b, const double *start, const double *goal,
+                             const double *step_len, const double *search_radius, const double *clearance,
+                             const double *range, const int *n_balls, const double *balls,
+                             const double *ball_r2, const int *n_boxes, const double *boxes,
+                             const double *near_table, const double *rot_c, void *stream);
+
+/* np.random.seed(s) state of each problem: key [E][624], pos [E] (np.random.get_state()[1:3]) */
+int nirrt_batch_set_rng(nirrt_batch *b, const uint32_t *key, const int *pos, void *stream);
+int nirrt_batch_get_rng_sync(nirrt_batch *b, uint32_t *key, int *pos, void *stream);
+
+/* NIRRT* knobs (nirrt_star_png_3d.py:39-45): pc_sample_rate, pc_update_cost_ratio, applied to all */
+int nirrt_batch_set_guidance(nirrt_batch *b, double pc_sample_rate, double pc_update_cost_ratio);
+/* path_point_cloud_pred of one problem (nirrt_star_png_3d.py:172): points [n][3] f64 host */
+int nirrt_batch_set_cloud(nirrt_batch *b, int env, const double *points, int n, void *stream);
+
+/* Tree snapshot in the reference's own layout: vertices [count][capacity][3] f64 (AoS),
+ * parents [count][capacity] int64, n [count]  (RRTBase3D.vertices / vertex_parents / num_vertices,
+ * rrt_base_3d.py:25-28) for problems env_begin .. env_begin+count-1. */
+int nirrt_batch_load_trees(nirrt_batch *b, int env_begin, int count, const int *n,
+                           const double *vertices, const int64_t *parents, void *stream);
+int nirrt_batch_read_trees_sync(nirrt_batch *b, int env_begin, int count, int *n,
+                                double *vertices, int64_t *parents, void *stream);
+
+/* Starts a driver: variant/mode select the loop (see defines); iter_max = phase-1 cap,
+ * iter_after_initial = phase-2 length (planning_random); for NIRRT_MODE_PLANNING only iter_max is
+ * used.  Resets per-problem phase machines and record counters (not the trees). */
+int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter_max, int iter_after_initial, void *stream);
+
+/* Enqueues `iters` lock-step iterations of the loop body on every problem that is still running
+ * (Sample -> Nearest scan -> Steer + collision -> Near scan -> ChooseParent/Rewire/goal work).
+ * Problems that finished their driver idle.  No host synchronisation. */
+int nirrt_batch_run(nirrt_batch *b, int iters, void *stream);
+
+/* Waits for the stream; returns the number of problems whose driver has not finished in *running
+ * and the number waiting for a guidance cloud in *need_cloud.  Returns NIRRT_ERR_CAPACITY if any
+ * problem overflowed a device buffer. */
+int nirrt_batch_status_sync(nirrt_batch *b, int *running, int *need_cloud, void *stream);
+/* per problem: state[E] (0 done, 1 phase 1, 2 phase 2, 3 waiting for cloud), n_records[E], n_vertices[E] */
+int nirrt_batch_env_state_sync(nirrt_batch *b, int *state, int *n_records, int *n_vertices, void *stream);
+
+/* Raw per-iteration records [count][record_capacity] f64 + lengths [count].  RRT* family: path
+ * length after each iteration; IRRT* family: c_best at the top of each iteration plus the final
+ * refresh -- path_len_list is records[1:]. */
+int nirrt_batch_read_records_sync(nirrt_batch *b, int env_begin, int count, double *records, int *n_records, void *stream);
+
+/* path_solutions of one problem (irrt_star_3d.py:29): returns count, fills out[<=cap] */
+int nirrt_batch_read_solutions_sync(nirrt_batch *b, int env, int64_t *out, int cap, void *stream);
+/* RRTStar3D.search_goal_parent (rrt_star_3d.py:101-117) / find_best_path_solution
+ * (irrt_star_3d.py:80-93) for every problem: goal_parent[E] (-1 = None), cost[E] */
+int nirrt_batch_goal_parent_sync(nirrt_batch *b, int64_t *goal_parent, double *cost, void *stream);
+
+/* Per-iteration trace of the LAST executed iteration of every problem (parity tests):
+ * nearest[E], new_index[E] (-1: steer edge collided), near_count[E], near [E][near_stride] int32 */
+int nirrt_batch_read_trace_sync(nirrt_batch *b, int *nearest, int *new_index, int *near_count,
+                                int *near, int near_stride, double *x_rand, void *stream);
+
+/* ---- stand-alone batched predicates over a problem's obstacle table --------------------------
+ * Utils.is_collision(start,end) for m edges: edges [m][2][3] f64 host -> out [m] u8
+ * (rrt_utils_3d.py:22-36 -> collision_check_utils_3d.py:151-216) */
+int nirrt_collide_edges_sync(nirrt_batch *b, int env, const double *edges, int64_t m, uint8_t *out, void *stream);
+/* kind 0: Utils.is_inside_obs (rrt_utils_3d.py:39-51); kind 1: Utils.is_valid (:68-86);
+ * points [m][3] -> out [m] u8 */
+int nirrt_points_check_sync(nirrt_batch *b, int env, int kind, const double *points, int64_t m, uint8_t *out, void *stream);
+/* RRTBase3D.nearest_neighbor (rrt_base_3d.py:100-113) for m queries against problem env's tree */
+int nirrt_nearest_sync(nirrt_batch *b, int env, const double *queries, int64_t m, int64_t *out, void *stream);
+/* np.where(np.linalg.norm(q - vertices, axis=-1) <= r)[0] (rrt_star_3d.py:135-137), ascending;
+ * returns the count (may exceed cap; only cap entries are written) */
+int64_t nirrt_within_sync(nirrt_batch *b, int env, const double *q, double r, int64_t *out, int64_t cap, void *stream);
+/* RRTBase3D.cost (rrt_base_3d.py:60-67) for m vertex indices */
+int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int64_t m, double *out, void *stream);
+
+/* Device-resident benchmark hooks: bytes scanned per Nearest+Near pass and launch counters. */
+int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *reserved);
+/* Times `reps` back-to-back launches of ONE scan kernel (0 = Nearest, 1 = Near) on the batch's
+ * current trees with CUDA events on `stream`; returns average milliseconds per launch in *ms and
+ * the vertex-coordinate bytes one launch reads in *bytes. */
+int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, float *ms, int64_t *bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIRRT_B200_H */

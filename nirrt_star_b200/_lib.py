@@ -1,0 +1,106 @@
+"""ctypes binding of libnirrt_b200.so (include/nirrt_b200.h).  No fallback: if the library is
+missing or no sm_100 device is visible, every compute entry point raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_i64p = C.POINTER(C.c_int64)
+c_u32p = C.POINTER(C.c_uint32)
+c_u8p = C.POINTER(C.c_uint8)
+c_fp = C.POINTER(C.c_float)
+
+MAX_OBSTACLES = 32
+
+
+class NirrtError(RuntimeError):
+    pass
+
+
+class BatchDesc(C.Structure):
+    _fields_ = [("dim", C.c_int), ("n_envs", C.c_int), ("capacity", C.c_int), ("record_capacity", C.c_int),
+                ("near_capacity", C.c_int), ("device", C.c_int)]
+
+
+def lib():
+    """Loads (building if sources are newer and nvcc exists) the C-ABI library."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path) or _build.needs_build():
+        try:
+            _build.build()
+        except Exception as exc:  # pragma: no cover - build environment problem
+            if not os.path.exists(path):
+                raise NirrtError(f"libnirrt_b200.so is missing and could not be built: {exc}") from exc
+    L = C.CDLL(path)
+    V = C.c_void_p
+    L.nirrt_last_error.restype = C.c_char_p
+    L.nirrt_batch_create.argtypes = [C.POINTER(BatchDesc), C.POINTER(V)]
+    L.nirrt_batch_destroy.argtypes = [V]
+    L.nirrt_batch_set_problems.argtypes = [V, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp, V]
+    L.nirrt_batch_set_rng.argtypes = [V, c_u32p, c_ip, V]
+    L.nirrt_batch_get_rng_sync.argtypes = [V, c_u32p, c_ip, V]
+    L.nirrt_batch_set_guidance.argtypes = [V, C.c_double, C.c_double]
+    L.nirrt_batch_set_cloud.argtypes = [V, C.c_int, c_dp, C.c_int, V]
+    L.nirrt_batch_load_trees.argtypes = [V, C.c_int, C.c_int, c_ip, c_dp, c_i64p, V]
+    L.nirrt_batch_read_trees_sync.argtypes = [V, C.c_int, C.c_int, c_ip, c_dp, c_i64p, V]
+    L.nirrt_batch_begin.argtypes = [V, C.c_int, C.c_int, C.c_int, C.c_int, V]
+    L.nirrt_batch_run.argtypes = [V, C.c_int, V]
+    L.nirrt_batch_status_sync.argtypes = [V, c_ip, c_ip, V]
+    L.nirrt_batch_env_state_sync.argtypes = [V, c_ip, c_ip, c_ip, V]
+    L.nirrt_batch_read_records_sync.argtypes = [V, C.c_int, C.c_int, c_dp, c_ip, V]
+    L.nirrt_batch_read_solutions_sync.argtypes = [V, C.c_int, c_i64p, C.c_int, V]
+    L.nirrt_batch_goal_parent_sync.argtypes = [V, c_i64p, c_dp, V]
+    L.nirrt_batch_read_trace_sync.argtypes = [V, c_ip, c_ip, c_ip, c_ip, C.c_int, c_dp, V]
+    L.nirrt_collide_edges_sync.argtypes = [V, C.c_int, c_dp, C.c_int64, c_u8p, V]
+    L.nirrt_points_check_sync.argtypes = [V, C.c_int, C.c_int, c_dp, C.c_int64, c_u8p, V]
+    L.nirrt_nearest_sync.argtypes = [V, C.c_int, c_dp, C.c_int64, c_i64p, V]
+    L.nirrt_within_sync.restype = C.c_int64
+    L.nirrt_within_sync.argtypes = [V, C.c_int, c_dp, C.c_double, c_i64p, C.c_int64, V]
+    L.nirrt_costs_sync.argtypes = [V, C.c_int, c_i64p, C.c_int64, c_dp, V]
+    L.nirrt_batch_counters.argtypes = [V, c_i64p, c_i64p]
+    L.nirrt_batch_time_scan_sync.argtypes = [V, C.c_int, C.c_int, c_fp, c_i64p, V]
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise NirrtError(f"libnirrt_b200 error {rc}: {lib().nirrt_last_error().decode()}")
+    return rc
+
+
+def require_device():
+    n = lib().nirrt_device_count()
+    if n <= 0:
+        raise NirrtError("no sm_100 (B200) CUDA device visible: nirrt_star_b200 has no CPU fallback")
+    return n
+
+
+def dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def i64p(a):
+    return a.ctypes.data_as(c_i64p)
+
+
+def u8p(a):
+    return a.ctypes.data_as(c_u8p)
+
+
+def f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a if shape is None else a.reshape(shape)

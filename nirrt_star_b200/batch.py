@@ -1,0 +1,274 @@
+"""Host-side driver of the lock-step batched 3D planner (C ABI: include/nirrt_b200.h).
+
+``BatchPlanner3D`` owns one ``nirrt_batch`` handle: E independent planning problems whose trees
+live in HBM and advance one loop body per iteration.  It mirrors, for a whole batch, what one
+``RRTStar3D`` / ``IRRTStar3D`` / ``NIRRTStarPNG3D`` object does in the reference
+(path_planning_classes_3d/*.py); the single-problem drop-in classes are thin views over a batch
+of one (nirrt_star_b200/dropin/path_planning_classes_3d).
+
+Host responsibilities (all one-off, per problem): evaluating the three libm-dependent constants
+the reference computes with CPython/numpy -- the Near radius table (math.log / **), numpy's scalar
+``r ** 2`` of each ball, and the informed-sampling rotation (numpy SVD) -- so the device only
+executes IEEE-exact arithmetic.  Everything per-iteration runs in CUDA.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import MAX_OBSTACLES, NirrtError, check, dp, f64, i64p, ip, u8p
+
+VARIANT_RRT_STAR, VARIANT_IRRT_STAR, VARIANT_NIRRT_STAR = 0, 1, 2
+MODE_PLANNING, MODE_PLANNING_RANDOM = 0, 1
+ST_DONE, ST_PHASE1, ST_PHASE2, ST_WAIT_CLOUD = 0, 1, 2, 3
+
+
+def near_radius_table(capacity, dim=3):
+    """t[n] = (math.log(n)/n)**(1/3.) -- the n-dependent factor of find_near_neighbors' radius
+    (rrt_star_3d.py:134), evaluated with CPython's libm exactly as the reference does."""
+    t = np.zeros(capacity + 2, dtype=np.float64)
+    if dim == 3:
+        for n in range(1, capacity + 2):
+            t[n] = (math.log(n) / n) ** (1 / 3.)
+    else:
+        for n in range(1, capacity + 2):
+            t[n] = math.sqrt(math.log(n) / n)
+    return t
+
+
+def rotation_to_world_frame_3d(x_start, x_goal):
+    """IRRTStar3D.RotationToWorldFrame (irrt_star_3d.py:159-173): one numpy SVD per problem."""
+    x_start = np.array(x_start).astype(np.float64)
+    x_goal = np.array(x_goal).astype(np.float64)
+    dx, dy, dz = x_goal - x_start
+    length = math.hypot(dx, dy, dz)
+    a1 = (x_goal - x_start) / length
+    U, _, V = np.linalg.svd(np.outer(a1, [1, 0, 0]))
+    return U @ np.diag([1, 1, np.linalg.det(U) * np.linalg.det(V)]) @ V.T
+
+
+def seed_state(seed):
+    """(key[624] uint32, pos) of ``np.random.seed(seed)``."""
+    st = np.random.RandomState(seed).get_state()
+    return st[1].astype(np.uint32), int(st[2])
+
+
+class BatchPlanner3D:
+    def __init__(self, problems, iter_max, step_len=10, clearance=2, seeds=None, rng_states=None,
+                 record_capacity=None, near_capacity=0, device=0, stream=None):
+        _lib.require_device()
+        self.L = _lib.lib()
+        self.E = len(problems)
+        if self.E < 1:
+            raise ValueError("at least one problem required")
+        self.iter_max = int(iter_max)
+        self.capacity = 1 + self.iter_max
+        self.record_capacity = int(record_capacity) if record_capacity else self.capacity + 8
+        self.stream = C.c_void_p(stream) if stream else None
+        self.variant = VARIANT_RRT_STAR
+        self.mode = MODE_PLANNING
+        desc = _lib.BatchDesc(3, self.E, self.capacity, self.record_capacity, int(near_capacity), int(device))
+        h = C.c_void_p()
+        check(self.L.nirrt_batch_create(C.byref(desc), C.byref(h)))
+        self.h = h
+        self._upload_problems(problems, step_len, clearance)
+        if rng_states is None:
+            if seeds is None:
+                seeds = list(range(self.E))
+            rng_states = [seed_state(s) for s in seeds]
+        self.set_rng(rng_states)
+
+    # ------------------------------------------------------------------ setup
+    def _upload_problems(self, problems, step_len, clearance):
+        E = self.E
+        start = np.zeros((E, 3)); goal = np.zeros((E, 3)); rng6 = np.zeros((E, 6))
+        sl = np.zeros(E); sr = np.zeros(E); cl = np.zeros(E)
+        nb = np.zeros(E, dtype=np.int32); nx = np.zeros(E, dtype=np.int32)
+        balls = np.zeros((E, MAX_OBSTACLES, 4)); r2 = np.zeros((E, MAX_OBSTACLES)); boxes = np.zeros((E, MAX_OBSTACLES, 6))
+        rot = np.zeros((E, 9))
+        step_len = np.broadcast_to(np.asarray(step_len, dtype=np.float64), (E,))
+        clearance = np.broadcast_to(np.asarray(clearance, dtype=np.float64), (E,))
+        for e, p in enumerate(problems):
+            ed = p["env_dict"]
+            start[e] = np.array(p["x_start"]).astype(np.float64)
+            goal[e] = np.array(p["x_goal"]).astype(np.float64)
+            h, w, d = ed["env_dims"]                      # rrt_env_3d.py:6-9
+            rng6[e] = [0, w, 0, h, 0, d]
+            sl[e], sr[e], cl[e] = step_len[e], float(p["search_radius"]), clearance[e]
+            b = np.asarray(ed["ball_obstacles"], dtype=np.float64).reshape(-1, 4)
+            x = np.asarray(ed["box_obstacles"], dtype=np.float64).reshape(-1, 6)
+            if len(b) > MAX_OBSTACLES or len(x) > MAX_OBSTACLES:
+                raise ValueError(f"problem {e}: more than {MAX_OBSTACLES} obstacles of one type")
+            nb[e], nx[e] = len(b), len(x)
+            balls[e, :len(b)] = b
+            boxes[e, :len(x)] = x
+            # numpy *scalar* power, as check_collision_line_single_ball evaluates r ** 2
+            # (collision_check_utils_3d.py:21,31-37)
+            for k in range(len(b)):
+                r2[e, k] = float((b[k, 3] + clearance[e]) ** 2)
+            if np.any(start[e] != goal[e]):
+                rot[e] = rotation_to_world_frame_3d(start[e], goal[e]).reshape(9)
+            else:
+                rot[e] = np.eye(3).reshape(9)
+        self.start, self.goal = start, goal
+        table = near_radius_table(self.capacity, 3)
+        check(self.L.nirrt_batch_set_problems(self.h, dp(start), dp(goal), dp(sl), dp(sr), dp(cl), dp(rng6),
+                                              ip(nb), dp(balls), dp(r2), ip(nx), dp(boxes), dp(table), dp(rot),
+                                              self.stream))
+
+    def set_rng(self, rng_states):
+        key = np.zeros((self.E, 624), dtype=np.uint32); pos = np.zeros(self.E, dtype=np.int32)
+        for e, (k, p) in enumerate(rng_states):
+            key[e] = k; pos[e] = p
+        check(self.L.nirrt_batch_set_rng(self.h, key.ctypes.data_as(_lib.c_u32p), ip(pos), self.stream))
+
+    def get_rng(self):
+        key = np.zeros((self.E, 624), dtype=np.uint32); pos = np.zeros(self.E, dtype=np.int32)
+        check(self.L.nirrt_batch_get_rng_sync(self.h, key.ctypes.data_as(_lib.c_u32p), ip(pos), self.stream))
+        return [(key[e].copy(), int(pos[e])) for e in range(self.E)]
+
+    def set_guidance(self, pc_sample_rate, pc_update_cost_ratio):
+        check(self.L.nirrt_batch_set_guidance(self.h, float(pc_sample_rate), float(pc_update_cost_ratio)))
+
+    def set_cloud(self, env, points):
+        pts = f64(points).reshape(-1, 3)
+        check(self.L.nirrt_batch_set_cloud(self.h, int(env), dp(pts), len(pts), self.stream))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nirrt_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ trees
+    def load_trees(self, vertices, parents, n, env_begin=0):
+        """vertices [count][capacity][3] f64, parents [count][capacity] int64, n [count]."""
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        v = f64(vertices); p = np.ascontiguousarray(parents, dtype=np.int64)
+        assert v.shape == (len(n), self.capacity, 3) and p.shape == (len(n), self.capacity)
+        check(self.L.nirrt_batch_load_trees(self.h, int(env_begin), len(n), ip(n), dp(v), i64p(p), self.stream))
+
+    def read_trees(self, env_begin=0, count=None, out=None):
+        count = self.E - env_begin if count is None else count
+        if out is None:
+            v = np.zeros((count, self.capacity, 3)); p = np.zeros((count, self.capacity), dtype=np.int64)
+        else:
+            v, p = out
+        n = np.zeros(count, dtype=np.int32)
+        check(self.L.nirrt_batch_read_trees_sync(self.h, int(env_begin), count, ip(n), dp(v), i64p(p), self.stream))
+        return v, p, n
+
+    # ------------------------------------------------------------------ drivers
+    def begin(self, variant, mode, iter_max=None, iter_after_initial=0):
+        self.variant, self.mode = int(variant), int(mode)
+        im = self.iter_max if iter_max is None else int(iter_max)
+        check(self.L.nirrt_batch_begin(self.h, self.variant, self.mode, im, int(iter_after_initial), self.stream))
+
+    def run(self, iters):
+        check(self.L.nirrt_batch_run(self.h, int(iters), self.stream))
+
+    def status(self):
+        running = C.c_int(0); need = C.c_int(0)
+        check(self.L.nirrt_batch_status_sync(self.h, C.byref(running), C.byref(need), self.stream))
+        return running.value, need.value
+
+    def env_state(self):
+        st = np.zeros(self.E, dtype=np.int32); nr = np.zeros(self.E, dtype=np.int32); nv = np.zeros(self.E, dtype=np.int32)
+        check(self.L.nirrt_batch_env_state_sync(self.h, ip(st), ip(nr), ip(nv), self.stream))
+        return st, nr, nv
+
+    def run_to_completion(self, chunk=256, cloud_callback=None):
+        """Runs until every problem's driver finished.  ``cloud_callback(batch, env_indices)`` is
+        invoked for problems that paused for a guidance-cloud update (NIRRT*)."""
+        while True:
+            self.run(chunk)
+            running, need = self.status()
+            if need:
+                if cloud_callback is None:
+                    raise NirrtError("a problem requested a guidance cloud but no cloud_callback was given")
+                st, _, _ = self.env_state()
+                cloud_callback(self, np.nonzero(st == ST_WAIT_CLOUD)[0])
+                continue
+            if running == 0:
+                return
+
+    def records(self, env_begin=0, count=None):
+        count = self.E - env_begin if count is None else count
+        rec = np.zeros((count, self.record_capacity)); n = np.zeros(count, dtype=np.int32)
+        check(self.L.nirrt_batch_read_records_sync(self.h, int(env_begin), count, dp(rec), ip(n), self.stream))
+        return [rec[k, :n[k]].copy() for k in range(count)]
+
+    def path_len_lists(self):
+        """path_len_list of every problem exactly as planning_random returns it: the RRT* family
+        records after each iteration; the IRRT* family drops the pre-loop entry
+        (irrt_star_3d.py:285)."""
+        recs = self.records()
+        if self.variant == VARIANT_RRT_STAR:
+            return [list(r) for r in recs]
+        return [list(r[1:]) for r in recs]
+
+    def solutions(self, env):
+        n = check(self.L.nirrt_batch_read_solutions_sync(self.h, int(env), None, 0, self.stream))
+        out = np.zeros(max(n, 1), dtype=np.int64)
+        check(self.L.nirrt_batch_read_solutions_sync(self.h, int(env), i64p(out), len(out), self.stream))
+        return out[:n]
+
+    def goal_parents(self):
+        gp = np.zeros(self.E, dtype=np.int64); cost = np.zeros(self.E)
+        check(self.L.nirrt_batch_goal_parent_sync(self.h, i64p(gp), dp(cost), self.stream))
+        return gp, cost
+
+    def trace(self, near_stride=2048):
+        E = self.E
+        nearest = np.zeros(E, dtype=np.int32); new = np.zeros(E, dtype=np.int32); cnt = np.zeros(E, dtype=np.int32)
+        near = np.zeros((E, near_stride), dtype=np.int32); xr = np.zeros((E, 3))
+        check(self.L.nirrt_batch_read_trace_sync(self.h, ip(nearest), ip(new), ip(cnt), ip(near), near_stride, dp(xr), self.stream))
+        return nearest, new, cnt, near, xr
+
+    # ------------------------------------------------------------------ stand-alone predicates
+    def collide_edges(self, env, edges):
+        e = f64(edges).reshape(-1, 6)
+        out = np.zeros(len(e), dtype=np.uint8)
+        check(self.L.nirrt_collide_edges_sync(self.h, int(env), dp(e), len(e), u8p(out), self.stream))
+        return out.astype(bool)
+
+    def points_inside_obs(self, env, pts):
+        p = f64(pts).reshape(-1, 3); out = np.zeros(len(p), dtype=np.uint8)
+        check(self.L.nirrt_points_check_sync(self.h, int(env), 0, dp(p), len(p), u8p(out), self.stream))
+        return out.astype(bool)
+
+    def points_valid(self, env, pts):
+        p = f64(pts).reshape(-1, 3); out = np.zeros(len(p), dtype=np.uint8)
+        check(self.L.nirrt_points_check_sync(self.h, int(env), 1, dp(p), len(p), u8p(out), self.stream))
+        return out.astype(bool)
+
+    def nearest(self, env, queries):
+        q = f64(queries).reshape(-1, 3); out = np.zeros(len(q), dtype=np.int64)
+        check(self.L.nirrt_nearest_sync(self.h, int(env), dp(q), len(q), i64p(out), self.stream))
+        return out
+
+    def within(self, env, q, r, cap=2048):
+        q = f64(q).reshape(3); out = np.zeros(cap, dtype=np.int64)
+        m = check(self.L.nirrt_within_sync(self.h, int(env), dp(q), float(r), i64p(out), cap, self.stream))
+        return out[:min(m, cap)]
+
+    def costs(self, env, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int64); out = np.zeros(len(idx))
+        check(self.L.nirrt_costs_sync(self.h, int(env), i64p(idx), len(idx), dp(out), self.stream))
+        return out
+
+    def kernel_launches(self):
+        n = C.c_int64(0)
+        check(self.L.nirrt_batch_counters(self.h, C.byref(n), None))
+        return n.value
+
+    def time_scan(self, which, reps=20):
+        ms = C.c_float(0); nbytes = C.c_int64(0)
+        check(self.L.nirrt_batch_time_scan_sync(self.h, int(which), int(reps), C.byref(ms), C.byref(nbytes), self.stream))
+        return ms.value, nbytes.value

@@ -1,0 +1,56 @@
+"""Builds libnirrt_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libnirrt_b200.so")
+
+# -fmad=false: planner arithmetic must round every operation (explicit intrinsics already do;
+# this keeps the compiler from contracting anything that slips through).
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--shared", "-Xcompiler", "-fPIC"]
+UNITS = [("planner3d.cu", ["-fmad=false"])]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; libnirrt_b200.so cannot be built")
+    return exe
+
+
+def sources():
+    out = []
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h"))]
+    out.append(os.path.join(os.path.dirname(HERE), "include", "nirrt_b200.h"))
+    return out
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    for name, extra in UNITS:
+        obj = os.path.join(CSRC, name.replace(".cu", ".o"))
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+               "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, name), "-o", obj] + extra
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    subprocess.check_call([_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,1483 @@
+// planner3d.cu -- lock-step batched RRT*/IRRT*/NIRRT* loop body for 3D worlds on sm_100a, and the
+// C ABI over it (include/nirrt_b200.h).
+//
+// One "iteration" advances every running planning problem (env) by one loop body of the reference
+// (rrt_star_3d.py:37-55 == irrt_star_3d.py:50-71) with five kernels:
+//
+//   k_top      1 CTA / env   driver phase machine, c_best refresh (IRRT*), MT19937 sampling
+//   k_nearest  (chunks x E)  HBM-bound argmin scan over the env's SoA vertex coordinates
+//   k_steer    1 warp / env  argmin finish, Steer, steer-edge collision, vertex insert, Near radius
+//   k_near     (chunks x E)  HBM-bound radius scan, sparse append of candidate indices
+//   k_expand   1 CTA / env   sort candidates, edge collision filter, cost walks, ChooseParent,
+//                            sequential Rewire, goal bookkeeping, per-iteration record
+//
+// HBM layout per env (flat, capacity-strided):
+//   vx[], vy[], vz[]   f64 SoA      -- what the two scans stream (24 B / vertex / scan)
+//   nodes[]            {x,y,z,parent} 32 B records -- one sector per hop of a cost walk
+// All index-deciding arithmetic is IEEE-exact float64 in the reference's operand order
+// (exact_math.cuh, geometry3d.cuh); there is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <limits.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nirrt_b200.h"
+#include "exact_math.cuh"
+#include "geometry3d.cuh"
+#include "mt19937.cuh"
+
+using namespace nirrt;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                                \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(NIRRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+extern "C" const char *nirrt_last_error(void) { return g_err.c_str(); }
+extern "C" int nirrt_version(void) { return 100; }
+extern "C" int nirrt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side state
+
+struct __align__(32) Node {
+    double x, y, z;
+    long long parent;
+};
+
+enum { ST_DONE = 0, ST_PHASE1 = 1, ST_PHASE2 = 2, ST_WAIT_CLOUD = 3 };
+enum { ERR_NEAR_OVERFLOW = 1, ERR_SOL_OVERFLOW = 2, ERR_VERTEX_OVERFLOW = 4, ERR_EMPTY_CLOUD = 8,
+       ERR_PATH_DEPTH = 16, ERR_RECORD_OVERFLOW = 32, ERR_GOAL_OVERFLOW = 64 };
+
+struct EnvCtl {
+    // problem
+    double start[3], goal[3];
+    double step_len, search_radius;
+    double c_min, center[3], C[9];
+    double T_goal;  // rownorm(goal - v) <= step_len  <=>  sq <= T_goal
+    // tree
+    int n;
+    // driver
+    int state, saved_state, p1_done, left, budget, n_rec, resumed;
+    // iteration scratch
+    int go, skip, nearest, new_idx, inserted, cand_cnt, near_cnt;
+    double x_rand[3], x_new[3];
+    double r, T_near, curr_cost, c_best, c_update;
+    // goal bookkeeping
+    int n_sol, n_goal, tree_changed, n_pc;
+    long long last_gp;
+    double last_len;
+    int err, pad;
+};
+
+struct View {
+    int E, cap, stride, chunks, near_cap, rec_cap, sol_cap, pc_cap, path_cap;
+    int variant, mode, iter_max, iter_after;
+    double pc_rate, pc_ratio;
+    double *vx, *vy, *vz;
+    Node *nodes;
+    Geom3 *geom;
+    MtState *mt;
+    EnvCtl *ctl;
+    double *part_s;
+    int *part_i;
+    int *cand;       // [E][near_cap] unordered Near candidates of the current iteration
+    int *near_out;   // [E][near_cap] final (ordered, collision-filtered) Near list: trace
+    int *sol;        // [E][sol_cap]  path_solutions
+    int *gc_idx;     // [E][cap]      vertices within step_len of the goal (RRT* eval driver)
+    double *gc_d;    // [E][cap]      their goal distance, +inf when the goal edge collides
+    double *records; // [E][rec_cap]
+    double *pc;      // [E][pc_cap][3]
+    double *pathseg; // [E][path_cap]
+    const double *near_table;
+};
+
+__device__ __forceinline__ Node load_node(const Node *p) {
+    // L2-coherent loads: parents are rewritten by this CTA while other threads keep walking
+    const double2 a = __ldcg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
+    Node n;
+    n.x = a.x; n.y = a.y; n.z = b.x; n.parent = __double_as_longlong(b.y);
+    return n;
+}
+__device__ __forceinline__ void store_parent(Node *p, long long parent) {
+    __stcg(reinterpret_cast<long long *>(p) + 3, parent);
+}
+
+// RRTBase3D.cost (rrt_base_3d.py:60-67): leaf -> root, math.hypot per edge, summed in that order
+__device__ double cost_walk(const Node *nodes, int idx) {
+    double c = 0.0;
+    if (idx == 0) return c;
+    Node cur = load_node(nodes + idx);
+    while (idx != 0) {
+        const int par = (int)cur.parent;
+        const Node p = load_node(nodes + par);
+        c = XADD(c, hypot3(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z)));
+        idx = par;
+        cur = p;
+    }
+    return c;
+}
+
+// lexicographic (value, index) min == np.argmin's first-minimum rule
+__device__ __forceinline__ void lexmin(double &s, int &i, double os, int oi) {
+    if (os < s || (os == s && oi < i)) { s = os; i = oi; }
+}
+__device__ __forceinline__ void warp_lexmin(double &s, int &i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double os = __shfl_down_sync(0xffffffffu, s, off);
+        const int oi = __shfl_down_sync(0xffffffffu, i, off);
+        lexmin(s, i, os, oi);
+    }
+}
+// block-wide (<= 1024 threads); result valid in thread 0 and broadcast through smem to all
+__device__ void block_lexmin(double &s, int &i, double *sm_s, int *sm_i) {
+    warp_lexmin(s, i);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) { sm_s[w] = s; sm_i[w] = i; }
+    __syncthreads();
+    if (w == 0) {
+        s = l < nw ? sm_s[l] : XINF;
+        i = l < nw ? sm_i[l] : INT_MAX;
+        warp_lexmin(s, i);
+        if (l == 0) { sm_s[0] = s; sm_i[0] = i; }
+    }
+    __syncthreads();
+    s = sm_s[0]; i = sm_i[0];
+    __syncthreads();
+}
+__device__ int block_min_int(int v, int *sm_i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, off));
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) sm_i[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = l < nw ? sm_i[l] : INT_MAX;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, off));
+        if (l == 0) sm_i[0] = v;
+    }
+    __syncthreads();
+    v = sm_i[0];
+    __syncthreads();
+    return v;
+}
+
+__device__ __forceinline__ void push_record(const View &v, EnvCtl *c, int e, double val) {
+    if (c->n_rec < v.rec_cap) v.records[(size_t)e * v.rec_cap + c->n_rec] = val;
+    else c->err |= ERR_RECORD_OVERFLOW;
+    c->n_rec++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_top: driver phase machine + c_best refresh + sampling
+//   RRTBase3D.SampleFree                 rrt_base_3d.py:49-58
+//   IRRTStar3D.find_best_path_solution   irrt_star_3d.py:80-93
+//   IRRTStar3D.SampleInformedSubset      irrt_star_3d.py:117-157
+//   NIRRTStarPNG3D.generate_random_node  nirrt_star_png_3d.py:99-130
+//   planning_random record/phase rules   irrt_star_3d.py:245-331
+__device__ void sample_free(const Geom3 &g, MtStream &rng, double *out) {
+    const double x0 = XADD(g.range[0], g.clearance), x1 = XSUB(g.range[1], g.clearance);
+    const double y0 = XADD(g.range[2], g.clearance), y1 = XSUB(g.range[3], g.clearance);
+    const double z0 = XADD(g.range[4], g.clearance), z1 = XSUB(g.range[5], g.clearance);
+    do {
+        out[0] = rng.uniform(x0, x1);
+        out[1] = rng.uniform(y0, y1);
+        out[2] = rng.uniform(z0, z1);
+    } while (point_inside_obs(g, out));
+}
+
+__device__ void sample_informed(const Geom3 &g, const EnvCtl *c, MtStream &rng, double c_max, double *out) {
+    const double c2 = XSUB(XMUL(c_max, c_max), XMUL(c->c_min, c->c_min));
+    const double eps = (c2 < 0.0) ? 1e-6 : 0.0;
+    double r[3], M[9];
+    r[0] = XDIV(c_max, 2.0);
+    r[1] = r[2] = XDIV(XSQRT(XADD(c2, eps)), 2.0);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) M[3 * i + j] = XMUL(c->C[3 * i + j], r[j]);
+    const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
+    for (;;) {
+        const double rr = rng.uniform(0.0, 1.0);
+        const double th = rng.uniform(0.0, PI);
+        const double ph = rng.uniform(0.0, TWO_PI);
+        double st, ct, sp, cp;
+        cr_sincos(th, &st, &ct);
+        cr_sincos(ph, &sp, &cp);
+        const double rs = XMUL(rr, st);
+        const double xb0 = XMUL(rs, cp), xb1 = XMUL(rs, sp), xb2 = XMUL(rr, ct);
+        for (int i = 0; i < 3; i++)
+            out[i] = XADD(XFMA(M[3 * i + 2], xb2, XFMA(M[3 * i], xb0, XMUL(M[3 * i + 1], xb1))), c->center[i]);
+        if (point_valid(g, out)) break;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_top(View v) {
+    const int e = blockIdx.x;
+    EnvCtl *c = v.ctl + e;
+    __shared__ Geom3 g;
+    __shared__ double sm_s[4];
+    __shared__ int sm_i[4];
+    const int state = c->state, budget = c->budget;
+    if (state == ST_DONE || state == ST_WAIT_CLOUD || budget <= 0) {
+        if (threadIdx.x == 0) c->go = 0;
+        return;
+    }
+    for (int i = threadIdx.x; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + e)[i];
+    mt_prepare_next(v.mt + e, 160);
+    __syncthreads();
+
+    double c_best = XINF;
+    if (v.variant >= 1) {
+        const int n_sol = c->n_sol;
+        const Node *nodes = v.nodes + (size_t)e * v.stride;
+        const int *sol = v.sol + (size_t)e * v.sol_cap;
+        double bs = XINF; int bk = INT_MAX;
+        for (int k = threadIdx.x; k < n_sol; k += blockDim.x) {
+            const int idx = sol[k];
+            const Node nd = load_node(nodes + idx);
+            const double val = XADD(cost_walk(nodes, idx),
+                                    hypot3(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z)));
+            lexmin(bs, bk, val, k);
+        }
+        block_lexmin(bs, bk, sm_s, sm_i);
+        if (n_sol > 0) c_best = bs;
+    }
+    if (threadIdx.x != 0) return;
+
+    const bool fresh = !(v.variant == 2 && c->resumed);
+    if (v.variant >= 1 && fresh) {
+        c->c_best = c_best;
+        if (v.mode == NIRRT_MODE_PLANNING_RANDOM) {
+            if (c->state == ST_PHASE1) {
+                if (c_best < XINF) { c->state = ST_PHASE2; c->left = v.iter_after; }
+                else if (c->p1_done >= v.iter_max) { push_record(v, c, e, c_best); c->state = ST_DONE; c->go = 0; return; }
+            }
+            if (c->state == ST_PHASE2 && c->left <= 0) { push_record(v, c, e, c_best); c->state = ST_DONE; c->go = 0; return; }
+            push_record(v, c, e, c_best);
+        }
+    }
+    if (v.variant == 2 && fresh && c_best < XMUL(v.pc_ratio, c->c_update)) {
+        // update_point_cloud (nirrt_star_png_3d.py:113-115): the host runs PointNet++ and resumes us
+        c->c_update = c_best;
+        c->saved_state = c->state;
+        c->state = ST_WAIT_CLOUD;
+        c->resumed = 1;
+        c->go = 0;
+        return;
+    }
+    c->resumed = 0;
+
+    MtStream rng(v.mt + e);
+    double out[3];
+    bool done = false;
+    if (v.variant == 2) {
+        if (rng.next_double() < v.pc_rate) {
+            if (c->n_pc <= 0) { c->err |= ERR_EMPTY_CLOUD; c->state = ST_DONE; c->go = 0; rng.flush(); return; }
+            const long long k = rng.randint(c->n_pc);
+            const double *p = v.pc + ((size_t)e * v.pc_cap + k) * 3;
+            out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+            done = true;
+        }
+    }
+    if (!done) {
+        if (v.variant >= 1 && c_best < XINF) sample_informed(g, c, rng, c_best, out);
+        else sample_free(g, rng, out);
+    }
+    rng.flush();
+    c->x_rand[0] = out[0]; c->x_rand[1] = out[1]; c->x_rand[2] = out[2];
+    c->go = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_nearest: RRTBase3D.nearest_neighbor (rrt_base_3d.py:100-113)
+//   argmin_i sqrt((dx*dx + dy*dy) + dz*dz), first index on ties.  The square root is only taken
+//   for running-minimum candidates: s2 >= RU(best_s*best_s) implies sqrt_rn(s2) >= best_s.
+template <bool kForce>
+__global__ void __launch_bounds__(256) k_nearest(View v) {
+    const int e = blockIdx.y;
+    const EnvCtl *c = v.ctl + e;
+    if (!kForce && !c->go) return;
+    const int n = c->n;
+    const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 1) & ~1;
+    const int beg = blockIdx.x * per;
+    const int end = min(n, beg + per);
+    const double *X = v.vx + (size_t)e * v.stride, *Y = v.vy + (size_t)e * v.stride, *Z = v.vz + (size_t)e * v.stride;
+    const double qx = c->x_rand[0], qy = c->x_rand[1], qz = c->x_rand[2];
+    double best_s = XINF, T = XINF;
+    int best_i = INT_MAX;
+
+#define NEAREST_ONE(xx, yy, zz, ii)                                                   \
+    {                                                                                 \
+        const double dx = XSUB(qx, xx), dy = XSUB(qy, yy), dz = XSUB(qz, zz);         \
+        const double s2 = sq3_rows(dx, dy, dz);                                       \
+        if (s2 < T) {                                                                 \
+            const double s = XSQRT(s2);                                               \
+            if (s < best_s) { best_s = s; best_i = (ii); T = __dmul_ru(s, s); }       \
+        }                                                                             \
+    }
+    const int step = 2 * blockDim.x;
+    int i = beg + 2 * threadIdx.x;
+    for (; i + step < end; i += 2 * step) {   // two independent 16-byte loads per array in flight
+        const double2 xa = __ldg(reinterpret_cast<const double2 *>(X + i));
+        const double2 ya = __ldg(reinterpret_cast<const double2 *>(Y + i));
+        const double2 za = __ldg(reinterpret_cast<const double2 *>(Z + i));
+        const double2 xb = __ldg(reinterpret_cast<const double2 *>(X + i + step));
+        const double2 yb = __ldg(reinterpret_cast<const double2 *>(Y + i + step));
+        const double2 zb = __ldg(reinterpret_cast<const double2 *>(Z + i + step));
+        NEAREST_ONE(xa.x, ya.x, za.x, i)
+        NEAREST_ONE(xa.y, ya.y, za.y, i + 1)          // i+1 < i+step < end
+        NEAREST_ONE(xb.x, yb.x, zb.x, i + step)
+        if (i + step + 1 < end) NEAREST_ONE(xb.y, yb.y, zb.y, i + step + 1)
+    }
+    for (; i < end; i += step) {
+        const double2 xa = __ldg(reinterpret_cast<const double2 *>(X + i));
+        const double2 ya = __ldg(reinterpret_cast<const double2 *>(Y + i));
+        const double2 za = __ldg(reinterpret_cast<const double2 *>(Z + i));
+        NEAREST_ONE(xa.x, ya.x, za.x, i)
+        if (i + 1 < end) NEAREST_ONE(xa.y, ya.y, za.y, i + 1)
+    }
+#undef NEAREST_ONE
+    __shared__ double sm_s[8];
+    __shared__ int sm_i[8];
+    warp_lexmin(best_s, best_i);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sm_s[w] = best_s; sm_i[w] = best_i; }
+    __syncthreads();
+    if (w == 0) {
+        best_s = l < 8 ? sm_s[l] : XINF;
+        best_i = l < 8 ? sm_i[l] : INT_MAX;
+        warp_lexmin(best_s, best_i);
+        if (l == 0) {
+            v.part_s[(size_t)e * v.chunks + blockIdx.x] = best_s;
+            v.part_i[(size_t)e * v.chunks + blockIdx.x] = best_i;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_steer: argmin finish + new_state (rrt_star_3d.py:67-78) + steer-edge collision
+//          + duplicate guard / vertex insert (rrt_star_3d.py:40-51) + Near radius (rrt_star_3d.py:134)
+__global__ void __launch_bounds__(32) k_steer(View v) {
+    const int e = blockIdx.x;
+    EnvCtl *c = v.ctl + e;
+    if (!c->go) return;
+    const int lane = threadIdx.x;
+    double bs = XINF; int bi = INT_MAX;
+    for (int k = lane; k < v.chunks; k += 32) lexmin(bs, bi, v.part_s[(size_t)e * v.chunks + k], v.part_i[(size_t)e * v.chunks + k]);
+    warp_lexmin(bs, bi);
+    const int nearest = __shfl_sync(0xffffffffu, bi, 0);
+    Node *nodes = v.nodes + (size_t)e * v.stride;
+    const Geom3 &g = v.geom[e];
+    const Node nn = load_node(nodes + nearest);
+    const double xn[3] = {nn.x, nn.y, nn.z};
+    // every lane computes the same x_new (cheap, avoids broadcasts)
+    const double d0 = XSUB(c->x_rand[0], xn[0]), d1 = XSUB(c->x_rand[1], xn[1]), d2 = XSUB(c->x_rand[2], xn[2]);
+    double dist = hypot3(d0, d1, d2);
+    double dir[3] = {0.0, 0.0, 0.0};
+    if (dist != 0.0) { dir[0] = XDIV(d0, dist); dir[1] = XDIV(d1, dist); dir[2] = XDIV(d2, dist); }
+    if (!(dist < c->step_len)) dist = c->step_len;   // min(step_len, dist)
+    double xnew[3];
+    for (int i = 0; i < 3; i++) xnew[i] = XADD(xn[i], XMUL(dist, dir[i]));
+    const int m = g.n_balls + g.n_boxes;
+    bool hit = false;
+    for (int k = lane; k < m; k += 32) hit = hit || seg_hits_obstacle(g, k, xn, xnew);
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane != 0) return;
+    c->nearest = nearest;
+    c->cand_cnt = 0;
+    c->near_cnt = 0;
+    c->inserted = 0;
+    if (hit) { c->skip = 1; c->new_idx = -1; return; }
+    c->skip = 0;
+    int new_idx;
+    if (vecnorm3(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2])) < 1e-8) {
+        // "do not create a new node if it is actually the same point" (rrt_star_3d.py:41-45)
+        xnew[0] = xn[0]; xnew[1] = xn[1]; xnew[2] = xn[2];
+        new_idx = nearest;
+        c->curr_cost = cost_walk(nodes, nearest);
+    } else {
+        new_idx = c->n;
+        if (new_idx >= v.cap) { c->err |= ERR_VERTEX_OVERFLOW; c->skip = 1; c->new_idx = -1; return; }
+        const size_t o = (size_t)e * v.stride + new_idx;
+        v.vx[o] = xnew[0]; v.vy[o] = xnew[1]; v.vz[o] = xnew[2];
+        Node nd; nd.x = xnew[0]; nd.y = xnew[1]; nd.z = xnew[2]; nd.parent = nearest;
+        nodes[new_idx] = nd;
+        c->n = new_idx + 1;
+        c->inserted = 1;
+        c->tree_changed = 1;
+        c->curr_cost = XADD(cost_walk(nodes, nearest),
+                            hypot3(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2])));
+    }
+    c->new_idx = new_idx;
+    c->x_new[0] = xnew[0]; c->x_new[1] = xnew[1]; c->x_new[2] = xnew[2];
+    double r = XMUL(c->search_radius, v.near_table[c->n]);
+    if (c->step_len < r) r = c->step_len;            // min(gamma*(log n/n)^(1/3), step_len)
+    c->r = r;
+    c->T_near = sqrt_le_threshold(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_near: the distance part of find_near_neighbors (rrt_star_3d.py:134-137):
+//   np.where(np.linalg.norm(node_new - vertices, axis=-1) <= r)  <=>  sq <= T_near  (exact, see
+//   sqrt_le_threshold).  Matches are sparse (tens out of 1e5) and are appended unordered;
+//   k_expand sorts them back into ascending index order.
+template <bool kForce>
+__global__ void __launch_bounds__(256) k_near(View v) {
+    const int e = blockIdx.y;
+    EnvCtl *c = v.ctl + e;
+    if (!kForce && (!c->go || c->skip)) return;
+    const int n = c->n;
+    const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 1) & ~1;
+    const int beg = blockIdx.x * per;
+    const int end = min(n, beg + per);
+    const double *X = v.vx + (size_t)e * v.stride, *Y = v.vy + (size_t)e * v.stride, *Z = v.vz + (size_t)e * v.stride;
+    const double qx = c->x_new[0], qy = c->x_new[1], qz = c->x_new[2];
+    const double T = c->T_near;
+    int *cand = v.cand + (size_t)e * v.near_cap;
+
+#define NEAR_ONE(xx, yy, zz, ii)                                                      \
+    {                                                                                 \
+        const double dx = XSUB(qx, xx), dy = XSUB(qy, yy), dz = XSUB(qz, zz);         \
+        if (sq3_rows(dx, dy, dz) <= T) {                                              \
+            const int slot = atomicAdd(&c->cand_cnt, 1);                              \
+            if (slot < v.near_cap) cand[slot] = (ii);                                 \
+        }                                                                             \
+    }
+    const int step = 2 * blockDim.x;
+    int i = beg + 2 * threadIdx.x;
+    for (; i + step < end; i += 2 * step) {
+        const double2 xa = __ldg(reinterpret_cast<const double2 *>(X + i));
+        const double2 ya = __ldg(reinterpret_cast<const double2 *>(Y + i));
+        const double2 za = __ldg(reinterpret_cast<const double2 *>(Z + i));
+        const double2 xb = __ldg(reinterpret_cast<const double2 *>(X + i + step));
+        const double2 yb = __ldg(reinterpret_cast<const double2 *>(Y + i + step));
+        const double2 zb = __ldg(reinterpret_cast<const double2 *>(Z + i + step));
+        NEAR_ONE(xa.x, ya.x, za.x, i)
+        NEAR_ONE(xa.y, ya.y, za.y, i + 1)
+        NEAR_ONE(xb.x, yb.x, zb.x, i + step)
+        if (i + step + 1 < end) NEAR_ONE(xb.y, yb.y, zb.y, i + step + 1)
+    }
+    for (; i < end; i += step) {
+        const double2 xa = __ldg(reinterpret_cast<const double2 *>(X + i));
+        const double2 ya = __ldg(reinterpret_cast<const double2 *>(Y + i));
+        const double2 za = __ldg(reinterpret_cast<const double2 *>(Z + i));
+        NEAR_ONE(xa.x, ya.x, za.x, i)
+        if (i + 1 < end) NEAR_ONE(xa.y, ya.y, za.y, i + 1)
+    }
+#undef NEAR_ONE
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_expand: collision filter of find_near_neighbors (rrt_star_3d.py:141-144), choose_parent
+// (:80-90), rewire (:92-99), InGoalRegion append (irrt_star_3d.py:70-71), search_goal_parent +
+// path length record (rrt_star_3d.py:101-117,225-231), iteration accounting.
+constexpr int kExpandThreads = 128;
+constexpr int kNearSmem = 2048;
+
+__device__ void bitonic_sort_int(int *a, int n_pow2) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int x = a[i], y = a[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// RRT* eval driver: best goal parent over the incrementally maintained goal-candidate list and the
+// numpy-ordered path length (rrt_base_3d.py:69-91).  Called by all threads; result in thread 0.
+__device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nodes, double *sm_s, int *sm_i) {
+    const int ng = c->n_goal;
+    if (ng == 0) { if (threadIdx.x == 0) c->last_gp = -1; return XINF; }
+    const int *gi = v.gc_idx + (size_t)e * v.cap;
+    const double *gd = v.gc_d + (size_t)e * v.cap;
+    double bs = XINF; int bk = INT_MAX;
+    for (int k = threadIdx.x; k < ng; k += blockDim.x) {
+        const double d = gd[k];
+        const double val = (d < XINF) ? XADD(cost_walk(nodes, gi[k]), d) : XINF;
+        lexmin(bs, bk, val, k);
+    }
+    block_lexmin(bs, bk, sm_s, sm_i);
+    double len = XINF;
+    if (threadIdx.x == 0) {
+        const int gp = gi[bk];
+        c->last_gp = gp;
+        int depth = 0;
+        for (int i = gp; i != 0; i = (int)load_node(nodes + i).parent) depth++;
+        const int M = depth + 1;
+        if (M > v.path_cap) { c->err |= ERR_PATH_DEPTH; }
+        else {
+            double *seg = v.pathseg + (size_t)e * v.path_cap;
+            Node cur = load_node(nodes + gp);
+            seg[M - 1] = rownorm3(XSUB(c->goal[0], cur.x), XSUB(c->goal[1], cur.y), XSUB(c->goal[2], cur.z));
+            int idx = gp;
+            for (int j = 0; idx != 0; j++) {
+                const int par = (int)cur.parent;
+                const Node p = load_node(nodes + par);
+                seg[M - 2 - j] = rownorm3(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
+                idx = par; cur = p;
+            }
+            len = (M == 1) ? seg[0] : XADD(seg[0], pairwise_sum(seg + 1, M - 1));
+        }
+    }
+    return len;
+}
+
+__global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
+    const int e = blockIdx.x;
+    EnvCtl *c = v.ctl + e;
+    if (!c->go) return;
+    __shared__ Geom3 g;
+    __shared__ int s_cand[kNearSmem];
+    __shared__ int s_near[kNearSmem];
+    __shared__ double s_d[kNearSmem];
+    __shared__ double sm_s[4];
+    __shared__ int sm_i[4];
+    __shared__ int s_m;
+    __shared__ double s_cnew;
+    Node *nodes = v.nodes + (size_t)e * v.stride;
+    const int tid = threadIdx.x;
+
+    if (!c->skip) {
+        for (int i = tid; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
+            reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + e)[i];
+        int cnt = c->cand_cnt;
+        if (cnt > v.near_cap || cnt > kNearSmem) {
+            if (tid == 0) c->err |= ERR_NEAR_OVERFLOW;
+            cnt = min(min(cnt, v.near_cap), kNearSmem);
+        }
+        int p2 = 1;
+        while (p2 < cnt) p2 <<= 1;
+        const int *cand = v.cand + (size_t)e * v.near_cap;
+        for (int i = tid; i < p2; i += blockDim.x) s_cand[i] = i < cnt ? cand[i] : INT_MAX;
+        if (tid == 0) s_m = 0;
+        __syncthreads();
+        bitonic_sort_int(s_cand, p2);
+
+        const double xnew[3] = {c->x_new[0], c->x_new[1], c->x_new[2]};
+        const int new_idx = c->new_idx;
+        // collision filter + ordered compaction (tiles of blockDim candidates, ascending)
+        for (int base = 0; base < cnt; base += blockDim.x) {
+            const int k = base + tid;
+            bool keep = false;
+            int idx = -1;
+            double d = 0.0;
+            if (k < cnt) {
+                idx = s_cand[k];
+                const Node nd = load_node(nodes + idx);
+                const double p1[3] = {nd.x, nd.y, nd.z};
+                keep = (idx != new_idx) && !seg_collides(g, xnew, p1);
+                d = rownorm3(XSUB(xnew[0], p1[0]), XSUB(xnew[1], p1[1]), XSUB(xnew[2], p1[2]));
+            }
+            // block-ordered positions: warp ballots + warp-count prefix through smem
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int w = tid >> 5, l = tid & 31;
+            __shared__ int s_wcnt[kExpandThreads / 32];
+            if (l == 0) s_wcnt[w] = __popc(bal);
+            __syncthreads();
+            int off = s_m;
+            for (int q = 0; q < w; q++) off += s_wcnt[q];
+            if (keep) {
+                const int pos = off + __popc(bal & ((1u << l) - 1u));
+                s_near[pos] = idx;
+                s_d[pos] = d;
+            }
+            __syncthreads();
+            if (tid == 0) { int t = 0; for (int q = 0; q < kExpandThreads / 32; q++) t += s_wcnt[q]; s_m += t; }
+            __syncthreads();
+        }
+        const int m = s_m;
+        int *near_out = v.near_out + (size_t)e * v.near_cap;
+        for (int k = tid; k < m; k += blockDim.x) near_out[k] = s_near[k];
+        if (tid == 0) c->near_cnt = m;
+
+        if (m > 0) {
+            // ---- choose_parent
+            double bs = XINF; int bk = INT_MAX;
+            for (int k = tid; k < m; k += blockDim.x) lexmin(bs, bk, XADD(cost_walk(nodes, s_near[k]), s_d[k]), k);
+            block_lexmin(bs, bk, sm_s, sm_i);
+            if (tid == 0) {
+                if (bs < c->curr_cost) { store_parent(nodes + new_idx, s_near[bk]); c->tree_changed = 1; }
+                __threadfence_block();
+            }
+            __syncthreads();
+            // ---- rewire: sequential semantics, parallel walks; after each re-parenting the
+            // remaining neighbours are re-evaluated so later ones see earlier changes
+            if (tid == 0) s_cnew = cost_walk(nodes, new_idx);
+            __syncthreads();
+            const double c_new = s_cnew;
+            int start = 0;
+            while (start < m) {
+                int first = INT_MAX;
+                for (int k = start + tid; k < m; k += blockDim.x) {
+                    if (cost_walk(nodes, s_near[k]) > XADD(c_new, s_d[k])) { first = k; break; }
+                }
+                first = block_min_int(first, sm_i);
+                if (first == INT_MAX) break;
+                if (tid == 0) { store_parent(nodes + s_near[first], new_idx); c->tree_changed = 1; __threadfence_block(); }
+                __syncthreads();
+                start = first + 1;
+            }
+        }
+        // ---- goal bookkeeping
+        if (tid == 0) {
+            if (v.variant >= 1) {
+                // InGoalRegion (rrt_base_3d.py:93-95)
+                if (hypot3(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2])) < c->step_len &&
+                    !seg_collides(g, xnew, c->goal)) {
+                    if (c->n_sol < v.sol_cap) v.sol[(size_t)e * v.sol_cap + c->n_sol] = new_idx;
+                    else c->err |= ERR_SOL_OVERFLOW;
+                    c->n_sol++;
+                }
+            } else if (v.mode == NIRRT_MODE_PLANNING_RANDOM && c->inserted) {
+                const double s2 = sq3_rows(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2]));
+                if (s2 <= c->T_goal) {
+                    const int k = c->n_goal;
+                    v.gc_idx[(size_t)e * v.cap + k] = new_idx;
+                    v.gc_d[(size_t)e * v.cap + k] = seg_collides(g, xnew, c->goal) ? XINF : XSQRT(s2);
+                    c->n_goal = k + 1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- per-iteration record + phase machine (RRT* family; the IRRT* family records in k_top)
+    if (v.variant == 0 && v.mode == NIRRT_MODE_PLANNING_RANDOM) {
+        double len;
+        __syncthreads();
+        const int changed = c->tree_changed;        // uniform: every thread reads before thread 0 clears it
+        __syncthreads();
+        if (changed) {
+            len = goal_path_len(v, c, e, nodes, sm_s, sm_i);
+        } else {
+            len = c->last_len;
+        }
+        if (tid == 0) {
+            c->last_len = len;
+            c->tree_changed = 0;
+            push_record(v, c, e, len);
+            if (c->state == ST_PHASE1) {
+                c->p1_done++;
+                if (len < XINF) { c->state = ST_PHASE2; c->left = v.iter_after; if (c->left <= 0) c->state = ST_DONE; }
+                else if (c->p1_done >= v.iter_max) c->state = ST_DONE;
+            } else {
+                c->left--;
+                if (c->left <= 0) c->state = ST_DONE;
+            }
+            c->budget--;
+        }
+    } else if (tid == 0) {
+        c->budget--;
+        if (v.mode == NIRRT_MODE_PLANNING) {
+            c->p1_done++;
+            if (c->p1_done >= v.iter_max) c->state = ST_DONE;
+        } else {  // IRRT* family planning_random: counters only, phase switches happen in k_top
+            if (c->state == ST_PHASE1) c->p1_done++; else c->left--;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup / IO kernels
+
+// builds the goal-candidate list of an existing tree in ascending index order (1 CTA / env)
+__global__ void __launch_bounds__(256) k_goal_init(View v) {
+    const int e = blockIdx.x;
+    EnvCtl *c = v.ctl + e;
+    __shared__ Geom3 g;
+    __shared__ int s_wcnt[8];
+    __shared__ int s_total;
+    for (int i = threadIdx.x; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + e)[i];
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    const int n = c->n;
+    const Node *nodes = v.nodes + (size_t)e * v.stride;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool keep = false;
+        double d = 0.0;
+        if (i < n) {
+            const Node nd = load_node(nodes + i);
+            const double p[3] = {nd.x, nd.y, nd.z};
+            const double s2 = sq3_rows(XSUB(c->goal[0], p[0]), XSUB(c->goal[1], p[1]), XSUB(c->goal[2], p[2]));
+            if (s2 <= c->T_goal) { keep = true; d = seg_collides(g, p, c->goal) ? XINF : XSQRT(s2); }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) s_wcnt[w] = __popc(bal);
+        __syncthreads();
+        int off = s_total;
+        for (int q = 0; q < w; q++) off += s_wcnt[q];
+        if (keep) {
+            const int pos = off + __popc(bal & ((1u << l) - 1u));
+            v.gc_idx[(size_t)e * v.cap + pos] = i;
+            v.gc_d[(size_t)e * v.cap + pos] = d;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; q++) t += s_wcnt[q]; s_total += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { c->n_goal = s_total; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1; }
+}
+
+__global__ void k_begin(View v) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E) return;
+    EnvCtl *c = v.ctl + e;
+    c->state = ST_PHASE1; c->saved_state = ST_PHASE1;
+    c->p1_done = 0; c->left = 0; c->budget = 0; c->n_rec = 0; c->resumed = 0;
+    c->go = 0; c->skip = 0; c->nearest = 0; c->new_idx = -1; c->inserted = 0; c->cand_cnt = 0; c->near_cnt = 0;
+    c->c_best = XINF; c->c_update = XINF;
+    c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
+    c->err = 0;
+}
+
+__global__ void k_set_budget(View v, int iters) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < v.E) v.ctl[e].budget = iters;
+}
+
+struct ProblemUpload {
+    const double *start, *goal, *step_len, *search_radius, *clearance, *range, *balls, *ball_r2, *boxes, *rot_c;
+    const int *n_balls, *n_boxes;
+};
+
+__global__ void k_set_problems(View v, ProblemUpload u) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E) return;
+    EnvCtl *c = v.ctl + e;
+    Geom3 *g = v.geom + e;
+    for (int i = 0; i < 3; i++) { c->start[i] = u.start[3 * e + i]; c->goal[i] = u.goal[3 * e + i]; }
+    c->step_len = u.step_len[e];
+    c->search_radius = u.search_radius[e];
+    c->T_goal = sqrt_le_threshold(c->step_len);
+    c->c_min = hypot3(XSUB(c->goal[0], c->start[0]), XSUB(c->goal[1], c->start[1]), XSUB(c->goal[2], c->start[2]));
+    for (int i = 0; i < 3; i++) c->center[i] = XDIV(XADD(c->start[i], c->goal[i]), 2.0);
+    for (int i = 0; i < 9; i++) c->C[i] = u.rot_c ? u.rot_c[9 * e + i] : ((i % 4) == 0 ? 1.0 : 0.0);
+    g->n_balls = u.n_balls[e]; g->n_boxes = u.n_boxes[e];
+    g->clearance = u.clearance[e];
+    for (int i = 0; i < 6; i++) g->range[i] = u.range[6 * e + i];
+    for (int k = 0; k < kMaxObs; k++) {
+        for (int i = 0; i < 4; i++) g->balls[k][i] = u.balls[((size_t)e * kMaxObs + k) * 4 + i];
+        g->ball_r2[k] = u.ball_r2[(size_t)e * kMaxObs + k];
+        for (int i = 0; i < 6; i++) g->boxes[k][i] = u.boxes[((size_t)e * kMaxObs + k) * 6 + i];
+    }
+    // tree = {start}, parent[0] = 0 (rrt_base_3d.py:25-28)
+    const size_t o = (size_t)e * v.stride;
+    v.vx[o] = c->start[0]; v.vy[o] = c->start[1]; v.vz[o] = c->start[2];
+    Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = c->start[2]; nd.parent = 0;
+    v.nodes[o] = nd;
+    c->n = 1;
+    c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
+    c->state = ST_DONE; c->budget = 0; c->go = 0; c->n_rec = 0; c->err = 0; c->resumed = 0;
+    c->c_best = XINF; c->c_update = XINF; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
+}
+
+// AoS (reference layout) <-> device layout
+__global__ void k_scatter_tree(View v, int env, int n, const double *verts /*[cap][3]*/, const long long *parents) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t o = (size_t)env * v.stride + i;
+    Node nd; nd.x = verts[3 * (size_t)i]; nd.y = verts[3 * (size_t)i + 1]; nd.z = verts[3 * (size_t)i + 2]; nd.parent = parents[i];
+    v.vx[o] = nd.x; v.vy[o] = nd.y; v.vz[o] = nd.z;
+    v.nodes[o] = nd;
+    if (i == 0) { v.ctl[env].n = n; v.ctl[env].tree_changed = 1; }
+}
+__global__ void k_gather_tree(View v, int env, double *verts, long long *parents) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.cap) return;
+    const int n = v.ctl[env].n;
+    Node nd; nd.x = nd.y = nd.z = 0.0; nd.parent = 0;
+    if (i < n) nd = v.nodes[(size_t)env * v.stride + i];
+    verts[3 * (size_t)i] = nd.x; verts[3 * (size_t)i + 1] = nd.y; verts[3 * (size_t)i + 2] = nd.z;
+    parents[i] = nd.parent;
+}
+
+// stand-alone predicates ---------------------------------------------------------------------------
+__global__ void k_collide_edges(View v, int env, const double *edges, long long m, uint8_t *out) {
+    __shared__ Geom3 g;
+    for (int i = threadIdx.x; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + env)[i];
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        double p0[3], p1[3];
+        for (int k = 0; k < 3; k++) { p0[k] = edges[6 * i + k]; p1[k] = edges[6 * i + 3 + k]; }
+        out[i] = seg_collides(g, p0, p1) ? 1 : 0;
+    }
+}
+__global__ void k_points_check(View v, int env, int kind, const double *pts, long long m, uint8_t *out) {
+    __shared__ Geom3 g;
+    for (int i = threadIdx.x; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + env)[i];
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        out[i] = (kind == 0 ? point_inside_obs(g, p) : point_valid(g, p)) ? 1 : 0;
+    }
+}
+__global__ void k_costs(View v, int env, const long long *idx, long long m, double *out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < m) out[i] = cost_walk(v.nodes + (size_t)env * v.stride, (int)idx[i]);
+}
+// goal parent of every env for the final search (rrt_star_3d.py:58; irrt_star_3d.py:74-76)
+__global__ void __launch_bounds__(kExpandThreads) k_goal_parent(View v, int use_solutions, long long *gp_out, double *cost_out) {
+    const int e = blockIdx.x;
+    EnvCtl *c = v.ctl + e;
+    __shared__ double sm_s[4];
+    __shared__ int sm_i[4];
+    const Node *nodes = v.nodes + (size_t)e * v.stride;
+    if (use_solutions) {
+        const int n_sol = min(c->n_sol, v.sol_cap);
+        const int *sol = v.sol + (size_t)e * v.sol_cap;
+        double bs = XINF; int bk = INT_MAX;
+        for (int k = threadIdx.x; k < n_sol; k += blockDim.x) {
+            const int idx = sol[k];
+            const Node nd = load_node(nodes + idx);
+            lexmin(bs, bk, XADD(cost_walk(nodes, idx), hypot3(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z))), k);
+        }
+        block_lexmin(bs, bk, sm_s, sm_i);
+        if (threadIdx.x == 0) { gp_out[e] = n_sol > 0 ? sol[bk] : -1; cost_out[e] = n_sol > 0 ? bs : XINF; }
+    } else {
+        const double len = goal_path_len(v, c, e, nodes, sm_s, sm_i);
+        if (threadIdx.x == 0) { gp_out[e] = c->last_gp; cost_out[e] = len; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: batch object
+
+struct nirrt_batch {
+    View v;
+    int device;
+    size_t stride_bytes;
+    std::vector<void *> allocs;
+    int64_t launches;
+    bool goal_lists;   // gc_idx/gc_d allocated
+    // pinned scratch for small synchronous reads
+    EnvCtl *h_ctl;
+};
+
+static int dalloc(nirrt_batch *b, void **p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(NIRRT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    b->allocs.push_back(*p);
+    return NIRRT_OK;
+}
+#define DALLOC(ptr, type, count)                                                          \
+    do { void *_p = nullptr; int _r = dalloc(b, &_p, sizeof(type) * (size_t)(count));     \
+         if (_r) { nirrt_batch_destroy(b); return _r; } ptr = (type *)_p; } while (0)
+
+static int pick_chunks(int E) {
+    const char *env = getenv("NIRRT_CHUNKS");
+    if (env && atoi(env) > 0) return atoi(env) > 64 ? 64 : atoi(env);
+    // aim for ~8 resident 256-thread CTAs on each of the 148 SMs
+    int c = (148 * 8 + E - 1) / E;
+    if (c < 1) c = 1;
+    if (c > 64) c = 64;
+    return c;
+}
+
+extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
+    if (!b) return NIRRT_OK;
+    cudaSetDevice(b->device);
+    for (void *p : b->allocs) cudaFree(p);
+    if (b->h_ctl) cudaFreeHost(b->h_ctl);
+    delete b;
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) {
+    if (!d || !out) return fail(NIRRT_ERR_INVALID, "null argument");
+    if (d->dim != 3) return fail(NIRRT_ERR_INVALID, "nirrt_batch_create: dim must be 3");
+    if (d->n_envs < 1 || d->capacity < 2) return fail(NIRRT_ERR_INVALID, "n_envs >= 1 and capacity >= 2 required");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(NIRRT_ERR_NO_DEVICE, "no CUDA device visible");
+    if (d->device < 0 || d->device >= ndev) return fail(NIRRT_ERR_INVALID, "bad device ordinal");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major != 10) return fail(NIRRT_ERR_NO_DEVICE, "libnirrt_b200 is built for sm_100a only");
+    CUDA_TRY(cudaSetDevice(d->device));
+    nirrt_batch *b = new nirrt_batch();
+    memset(&b->v, 0, sizeof(View));
+    b->device = d->device; b->launches = 0; b->goal_lists = false; b->h_ctl = nullptr;
+    View &v = b->v;
+    v.E = d->n_envs; v.cap = d->capacity;
+    v.stride = (d->capacity + 63) & ~63;
+    v.chunks = pick_chunks(v.E);
+    v.near_cap = d->near_capacity > 0 ? d->near_capacity : kNearSmem;
+    v.rec_cap = d->record_capacity > 0 ? d->record_capacity : d->capacity + 8;
+    v.sol_cap = v.rec_cap;
+    v.pc_cap = 4096; v.path_cap = 4096;
+    v.pc_rate = 0.5; v.pc_ratio = 0.9;
+    const size_t EV = (size_t)v.E * v.stride;
+    DALLOC(v.vx, double, EV); DALLOC(v.vy, double, EV); DALLOC(v.vz, double, EV);
+    DALLOC(v.nodes, Node, EV);
+    DALLOC(v.geom, Geom3, v.E); DALLOC(v.mt, MtState, v.E); DALLOC(v.ctl, EnvCtl, v.E);
+    DALLOC(v.part_s, double, (size_t)v.E * v.chunks); DALLOC(v.part_i, int, (size_t)v.E * v.chunks);
+    DALLOC(v.cand, int, (size_t)v.E * v.near_cap); DALLOC(v.near_out, int, (size_t)v.E * v.near_cap);
+    DALLOC(v.sol, int, (size_t)v.E * v.sol_cap);
+    DALLOC(v.records, double, (size_t)v.E * v.rec_cap);
+    DALLOC(v.pathseg, double, (size_t)v.E * v.path_cap);
+    { double *t; DALLOC(t, double, (size_t)v.cap + 2); v.near_table = t; }
+    CUDA_TRY(cudaMemset(v.ctl, 0, sizeof(EnvCtl) * v.E));
+    CUDA_TRY(cudaMemset(v.mt, 0, sizeof(MtState) * v.E));
+    CUDA_TRY(cudaMallocHost((void **)&b->h_ctl, sizeof(EnvCtl) * v.E));
+    *out = b;
+    return NIRRT_OK;
+}
+
+static int ensure_goal_lists(nirrt_batch *b) {
+    if (b->goal_lists) return NIRRT_OK;
+    View &v = b->v;
+    void *p = nullptr;
+    int r = dalloc(b, &p, sizeof(int) * (size_t)v.E * v.cap); if (r) return r; v.gc_idx = (int *)p;
+    r = dalloc(b, &p, sizeof(double) * (size_t)v.E * v.cap); if (r) return r; v.gc_d = (double *)p;
+    b->goal_lists = true;
+    return NIRRT_OK;
+}
+
+// copies a host array to a temporary device buffer on `s` (freed after the stream is drained by the caller)
+struct TempBufs {
+    std::vector<void *> ptrs;
+    ~TempBufs() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> int up(const T *host, size_t count, cudaStream_t s, T **dev) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+        if (e != cudaSuccess) return fail(NIRRT_ERR_CUDA, std::string("cudaMalloc(temp): ") + cudaGetErrorString(e));
+        ptrs.push_back(p);
+        if (count) {
+            e = cudaMemcpyAsync(p, host, sizeof(T) * count, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return fail(NIRRT_ERR_CUDA, std::string("cudaMemcpyAsync(H2D): ") + cudaGetErrorString(e));
+        }
+        *dev = (T *)p;
+        return NIRRT_OK;
+    }
+    template <typename T> int make(size_t count, T **dev) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+        if (e != cudaSuccess) return fail(NIRRT_ERR_CUDA, std::string("cudaMalloc(temp): ") + cudaGetErrorString(e));
+        ptrs.push_back(p);
+        *dev = (T *)p;
+        return NIRRT_OK;
+    }
+};
+#define TRY(expr) do { int _r = (expr); if (_r) return _r; } while (0)
+#define CHECK_LAUNCH() CUDA_TRY(cudaGetLastError())
+
+extern "C" int nirrt_batch_set_problems(nirrt_batch *b, const double *start, const double *goal,
+                                        const double *step_len, const double *search_radius, const double *clearance,
+                                        const double *range, const int *n_balls, const double *balls,
+                                        const double *ball_r2, const int *n_boxes, const double *boxes,
+                                        const double *near_table, const double *rot_c, void *stream) {
+    if (!b || !start || !goal || !step_len || !search_radius || !clearance || !range || !n_balls || !balls || !ball_r2 ||
+        !n_boxes || !boxes || !near_table)
+        return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_problems: null argument");
+    View &v = b->v;
+    for (int e = 0; e < v.E; e++)
+        if (n_balls[e] < 0 || n_balls[e] > kMaxObs || n_boxes[e] < 0 || n_boxes[e] > kMaxObs)
+            return fail(NIRRT_ERR_INVALID, "more than NIRRT_MAX_OBSTACLES obstacles of one type");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    TempBufs t;
+    ProblemUpload u;
+    double *dp; int *ip;
+    const size_t E = v.E;
+    TRY(t.up(start, 3 * E, s, &dp)); u.start = dp;
+    TRY(t.up(goal, 3 * E, s, &dp)); u.goal = dp;
+    TRY(t.up(step_len, E, s, &dp)); u.step_len = dp;
+    TRY(t.up(search_radius, E, s, &dp)); u.search_radius = dp;
+    TRY(t.up(clearance, E, s, &dp)); u.clearance = dp;
+    TRY(t.up(range, 6 * E, s, &dp)); u.range = dp;
+    TRY(t.up(balls, 4 * E * kMaxObs, s, &dp)); u.balls = dp;
+    TRY(t.up(ball_r2, E * kMaxObs, s, &dp)); u.ball_r2 = dp;
+    TRY(t.up(boxes, 6 * E * kMaxObs, s, &dp)); u.boxes = dp;
+    u.rot_c = nullptr;
+    if (rot_c) { TRY(t.up(rot_c, 9 * E, s, &dp)); u.rot_c = dp; }
+    TRY(t.up(n_balls, E, s, &ip)); u.n_balls = ip;
+    TRY(t.up(n_boxes, E, s, &ip)); u.n_boxes = ip;
+    CUDA_TRY(cudaMemcpyAsync((void *)v.near_table, near_table, sizeof(double) * ((size_t)v.cap + 2), cudaMemcpyHostToDevice, s));
+    k_set_problems<<<(v.E + 127) / 128, 128, 0, s>>>(v, u);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaStreamSynchronize(s));   // temporaries are freed on return
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_set_rng(nirrt_batch *b, const uint32_t *key, const int *pos, void *stream) {
+    if (!b || !key || !pos) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_rng: null argument");
+    View &v = b->v;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<MtState> h(v.E);
+    for (int e = 0; e < v.E; e++) {
+        memcpy(h[e].key[0], key + (size_t)e * 624, 624 * sizeof(uint32_t));
+        memset(h[e].key[1], 0, 624 * sizeof(uint32_t));
+        if (pos[e] < 0 || pos[e] > 624) return fail(NIRRT_ERR_INVALID, "rng pos out of range");
+        h[e].pos = pos[e]; h[e].cur = 0; h[e].has_next = 0; h[e].pad = 0;
+    }
+    CUDA_TRY(cudaMemcpyAsync(v.mt, h.data(), sizeof(MtState) * v.E, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_get_rng_sync(nirrt_batch *b, uint32_t *key, int *pos, void *stream) {
+    if (!b || !key || !pos) return fail(NIRRT_ERR_INVALID, "nirrt_batch_get_rng_sync: null argument");
+    View &v = b->v;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<MtState> h(v.E);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), v.mt, sizeof(MtState) * v.E, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int e = 0; e < v.E; e++) {
+        memcpy(key + (size_t)e * 624, h[e].key[h[e].cur], 624 * sizeof(uint32_t));
+        pos[e] = h[e].pos;
+    }
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_set_guidance(nirrt_batch *b, double pc_sample_rate, double pc_update_cost_ratio) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    b->v.pc_rate = pc_sample_rate; b->v.pc_ratio = pc_update_cost_ratio;
+    return NIRRT_OK;
+}
+
+__global__ void k_set_cloud_meta(View v, int env, int n) {
+    EnvCtl *c = v.ctl + env;
+    c->n_pc = n;
+    if (c->state == ST_WAIT_CLOUD) c->state = c->saved_state;
+}
+
+extern "C" int nirrt_batch_set_cloud(nirrt_batch *b, int env, const double *points, int n, void *stream) {
+    if (!b || env < 0 || env >= b->v.E || n < 0 || (n > 0 && !points)) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_cloud: bad argument");
+    View &v = b->v;
+    if (n > v.pc_cap) return fail(NIRRT_ERR_CAPACITY, "guidance cloud larger than 4096 points");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!v.pc) {
+        void *p = nullptr;
+        TRY(dalloc(b, &p, sizeof(double) * 3 * (size_t)v.E * v.pc_cap));
+        v.pc = (double *)p;
+    }
+    if (n) CUDA_TRY(cudaMemcpyAsync(v.pc + (size_t)env * v.pc_cap * 3, points, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+    k_set_cloud_meta<<<1, 1, 0, s>>>(v, env, n);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_load_trees(nirrt_batch *b, int env_begin, int count, const int *n,
+                                      const double *vertices, const int64_t *parents, void *stream) {
+    if (!b || !n || !vertices || !parents) return fail(NIRRT_ERR_INVALID, "nirrt_batch_load_trees: null argument");
+    View &v = b->v;
+    if (env_begin < 0 || count < 0 || env_begin + count > v.E) return fail(NIRRT_ERR_INVALID, "env range out of bounds");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int maxn = 0;
+    for (int k = 0; k < count; k++) {
+        if (n[k] < 1 || n[k] > v.cap) return fail(NIRRT_ERR_INVALID, "tree size out of range");
+        if (n[k] > maxn) maxn = n[k];
+    }
+    // double-buffered staging so the copy of problem k+1 overlaps the scatter of problem k
+    TempBufs t;
+    double *dv[2]; long long *dp[2];
+    cudaEvent_t ev[2];
+    for (int q = 0; q < 2; q++) {
+        TRY(t.make<double>(3 * (size_t)maxn, &dv[q])); TRY(t.make<long long>((size_t)maxn, &dp[q]));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < count; k++) {
+        const int q = k & 1;
+        if (k >= 2) CUDA_TRY(cudaEventSynchronize(ev[q]));
+        CUDA_TRY(cudaMemcpyAsync(dv[q], vertices + (size_t)k * v.cap * 3, sizeof(double) * 3 * n[k], cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(dp[q], parents + (size_t)k * v.cap, sizeof(long long) * n[k], cudaMemcpyHostToDevice, s));
+        k_scatter_tree<<<(n[k] + 255) / 256, 256, 0, s>>>(v, env_begin + k, n[k], dv[q], dp[q]);
+        CHECK_LAUNCH();
+        CUDA_TRY(cudaEventRecord(ev[q], s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int q = 0; q < 2; q++) cudaEventDestroy(ev[q]);
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_read_trees_sync(nirrt_batch *b, int env_begin, int count, int *n,
+                                           double *vertices, int64_t *parents, void *stream) {
+    if (!b || !n || !vertices || !parents) return fail(NIRRT_ERR_INVALID, "nirrt_batch_read_trees_sync: null argument");
+    View &v = b->v;
+    if (env_begin < 0 || count < 0 || env_begin + count > v.E) return fail(NIRRT_ERR_INVALID, "env range out of bounds");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(b->h_ctl, v.ctl, sizeof(EnvCtl) * v.E, cudaMemcpyDeviceToHost, s));
+    TempBufs t;
+    double *dv[2]; long long *dp[2];
+    for (int q = 0; q < 2; q++) { TRY(t.make<double>(3 * (size_t)v.cap, &dv[q])); TRY(t.make<long long>((size_t)v.cap, &dp[q])); }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int k = 0; k < count; k++) {
+        const int q = k & 1;
+        if (k >= 2) CUDA_TRY(cudaStreamSynchronize(s));   // staging buffer q is free again
+        k_gather_tree<<<(v.cap + 255) / 256, 256, 0, s>>>(v, env_begin + k, dv[q], dp[q]);
+        CHECK_LAUNCH();
+        CUDA_TRY(cudaMemcpyAsync(vertices + (size_t)k * v.cap * 3, dv[q], sizeof(double) * 3 * v.cap, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(parents + (size_t)k * v.cap, dp[q], sizeof(long long) * v.cap, cudaMemcpyDeviceToHost, s));
+        n[k] = b->h_ctl[env_begin + k].n;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter_max, int iter_after_initial, void *stream) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    if (variant < 0 || variant > 2 || mode < 0 || mode > 1 || iter_max < 0 || iter_after_initial < 0)
+        return fail(NIRRT_ERR_INVALID, "nirrt_batch_begin: bad variant/mode/iteration counts");
+    View &v = b->v;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    v.variant = variant; v.mode = mode; v.iter_max = iter_max; v.iter_after = iter_after_initial;
+    k_begin<<<(v.E + 127) / 128, 128, 0, s>>>(v);
+    CHECK_LAUNCH();
+    if (variant == 0 && mode == NIRRT_MODE_PLANNING_RANDOM) {
+        TRY(ensure_goal_lists(b));
+        k_goal_init<<<v.E, 256, 0, s>>>(v);
+        CHECK_LAUNCH();
+    }
+    return NIRRT_OK;
+}
+
+static int launch_iteration(nirrt_batch *b, cudaStream_t s) {
+    View &v = b->v;
+    k_top<<<v.E, 128, 0, s>>>(v);
+    k_nearest<false><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+    k_steer<<<v.E, 32, 0, s>>>(v);
+    k_near<false><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+    k_expand<<<v.E, kExpandThreads, 0, s>>>(v);
+    b->launches += 5;
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
+    if (!b || iters < 0) return fail(NIRRT_ERR_INVALID, "nirrt_batch_run: bad argument");
+    View &v = b->v;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
+    for (int it = 0; it < iters; it++) launch_iteration(b, s);
+    CHECK_LAUNCH();
+    return NIRRT_OK;
+}
+
+static int fetch_ctl(nirrt_batch *b, cudaStream_t s) {
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaMemcpyAsync(b->h_ctl, b->v.ctl, sizeof(EnvCtl) * b->v.E, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+static std::string err_bits(int err) {
+    std::string m;
+    if (err & ERR_NEAR_OVERFLOW) m += " near-candidate buffer overflow;";
+    if (err & ERR_SOL_OVERFLOW) m += " path_solutions overflow;";
+    if (err & ERR_VERTEX_OVERFLOW) m += " vertex capacity exceeded;";
+    if (err & ERR_EMPTY_CLOUD) m += " SamplePointCloud on an empty predicted cloud (reference raises ValueError);";
+    if (err & ERR_PATH_DEPTH) m += " path deeper than 4096 edges;";
+    if (err & ERR_RECORD_OVERFLOW) m += " record buffer overflow;";
+    if (err & ERR_GOAL_OVERFLOW) m += " goal-candidate overflow;";
+    return m;
+}
+
+extern "C" int nirrt_batch_status_sync(nirrt_batch *b, int *running, int *need_cloud, void *stream) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    TRY(fetch_ctl(b, (cudaStream_t)stream));
+    int run = 0, need = 0, err = 0, err_env = -1;
+    for (int e = 0; e < b->v.E; e++) {
+        const EnvCtl &c = b->h_ctl[e];
+        if (c.state == ST_PHASE1 || c.state == ST_PHASE2) run++;
+        if (c.state == ST_WAIT_CLOUD) need++;
+        if (c.err && !err) { err = c.err; err_env = e; }
+    }
+    if (running) *running = run;
+    if (need_cloud) *need_cloud = need;
+    if (err) return fail(NIRRT_ERR_CAPACITY, "problem " + std::to_string(err_env) + ":" + err_bits(err));
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_env_state_sync(nirrt_batch *b, int *state, int *n_records, int *n_vertices, void *stream) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    TRY(fetch_ctl(b, (cudaStream_t)stream));
+    for (int e = 0; e < b->v.E; e++) {
+        if (state) state[e] = b->h_ctl[e].state;
+        if (n_records) n_records[e] = b->h_ctl[e].n_rec;
+        if (n_vertices) n_vertices[e] = b->h_ctl[e].n;
+    }
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_read_records_sync(nirrt_batch *b, int env_begin, int count, double *records, int *n_records, void *stream) {
+    if (!b || !records || !n_records) return fail(NIRRT_ERR_INVALID, "nirrt_batch_read_records_sync: null argument");
+    View &v = b->v;
+    if (env_begin < 0 || count < 0 || env_begin + count > v.E) return fail(NIRRT_ERR_INVALID, "env range out of bounds");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaMemcpyAsync(records, v.records + (size_t)env_begin * v.rec_cap, sizeof(double) * (size_t)count * v.rec_cap, cudaMemcpyDeviceToHost, s));
+    TRY(fetch_ctl(b, s));
+    for (int k = 0; k < count; k++) n_records[k] = b->h_ctl[env_begin + k].n_rec < v.rec_cap ? b->h_ctl[env_begin + k].n_rec : v.rec_cap;
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_read_solutions_sync(nirrt_batch *b, int env, int64_t *out, int cap, void *stream) {
+    if (!b || env < 0 || env >= b->v.E) return fail(NIRRT_ERR_INVALID, "nirrt_batch_read_solutions_sync: bad argument");
+    View &v = b->v;
+    cudaStream_t s = (cudaStream_t)stream;
+    TRY(fetch_ctl(b, s));
+    int n = b->h_ctl[env].n_sol;
+    if (n > v.sol_cap) n = v.sol_cap;
+    if (out && cap > 0 && n > 0) {
+        const int m = n < cap ? n : cap;
+        std::vector<int> h(m);
+        CUDA_TRY(cudaMemcpyAsync(h.data(), v.sol + (size_t)env * v.sol_cap, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (int i = 0; i < m; i++) out[i] = h[i];
+    }
+    return n;
+}
+
+extern "C" int nirrt_batch_goal_parent_sync(nirrt_batch *b, int64_t *goal_parent, double *cost, void *stream) {
+    if (!b || !goal_parent || !cost) return fail(NIRRT_ERR_INVALID, "nirrt_batch_goal_parent_sync: null argument");
+    View &v = b->v;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    const int use_solutions = v.variant >= 1;
+    if (!use_solutions) {
+        TRY(ensure_goal_lists(b));
+        k_goal_init<<<v.E, 256, 0, s>>>(v);
+        CHECK_LAUNCH();
+    }
+    TempBufs t;
+    long long *dgp; double *dc;
+    TRY(t.make<long long>(v.E, &dgp)); TRY(t.make<double>(v.E, &dc));
+    k_goal_parent<<<v.E, kExpandThreads, 0, s>>>(v, use_solutions, dgp, dc);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(goal_parent, dgp, sizeof(long long) * v.E, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(cost, dc, sizeof(double) * v.E, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_read_trace_sync(nirrt_batch *b, int *nearest, int *new_index, int *near_count,
+                                           int *near, int near_stride, double *x_rand, void *stream) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    View &v = b->v;
+    cudaStream_t s = (cudaStream_t)stream;
+    TRY(fetch_ctl(b, s));
+    std::vector<int> h;
+    if (near && near_stride > 0) {
+        h.resize((size_t)v.E * v.near_cap);
+        CUDA_TRY(cudaMemcpyAsync(h.data(), v.near_out, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    for (int e = 0; e < v.E; e++) {
+        const EnvCtl &c = b->h_ctl[e];
+        if (nearest) nearest[e] = c.nearest;
+        if (new_index) new_index[e] = c.new_idx;
+        if (near_count) near_count[e] = c.near_cnt;
+        if (x_rand) for (int i = 0; i < 3; i++) x_rand[3 * e + i] = c.x_rand[i];
+        if (near && near_stride > 0) {
+            const int m = c.near_cnt < near_stride ? c.near_cnt : near_stride;
+            for (int k = 0; k < m; k++) near[(size_t)e * near_stride + k] = h[(size_t)e * v.near_cap + k];
+        }
+    }
+    return NIRRT_OK;
+}
+
+// ---- stand-alone predicates --------------------------------------------------------------------
+extern "C" int nirrt_collide_edges_sync(nirrt_batch *b, int env, const double *edges, int64_t m, uint8_t *out, void *stream) {
+    if (!b || env < 0 || env >= b->v.E || m < 0 || (m > 0 && (!edges || !out))) return fail(NIRRT_ERR_INVALID, "nirrt_collide_edges_sync: bad argument");
+    if (m == 0) return NIRRT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    TempBufs t;
+    double *de; uint8_t *dout;
+    TRY(t.up(edges, 6 * (size_t)m, s, &de)); TRY(t.make<uint8_t>((size_t)m, &dout));
+    const int blocks = (int)((m + 255) / 256 < 148 * 8 ? (m + 255) / 256 : 148 * 8);
+    k_collide_edges<<<blocks, 256, 0, s>>>(b->v, env, de, m, dout);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)m, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_points_check_sync(nirrt_batch *b, int env, int kind, const double *points, int64_t m, uint8_t *out, void *stream) {
+    if (!b || env < 0 || env >= b->v.E || m < 0 || kind < 0 || kind > 1 || (m > 0 && (!points || !out)))
+        return fail(NIRRT_ERR_INVALID, "nirrt_points_check_sync: bad argument");
+    if (m == 0) return NIRRT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    TempBufs t;
+    double *dp; uint8_t *dout;
+    TRY(t.up(points, 3 * (size_t)m, s, &dp)); TRY(t.make<uint8_t>((size_t)m, &dout));
+    const int blocks = (int)((m + 255) / 256 < 148 * 8 ? (m + 255) / 256 : 148 * 8);
+    k_points_check<<<blocks, 256, 0, s>>>(b->v, env, kind, dp, m, dout);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)m, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+// single-env views for the stand-alone scans: reuse the batch kernels on a 1-env grid
+__global__ void k_set_query(View v, int env, const double *q, int which, double r) {
+    EnvCtl *c = v.ctl + env;
+    if (which == 0) { c->x_rand[0] = q[0]; c->x_rand[1] = q[1]; c->x_rand[2] = q[2]; }
+    else { c->x_new[0] = q[0]; c->x_new[1] = q[1]; c->x_new[2] = q[2]; c->T_near = sqrt_le_threshold(r); c->cand_cnt = 0; }
+}
+__global__ void k_finish_nearest(View v, int env, long long *out) {
+    double bs = XINF; int bi = INT_MAX;
+    for (int k = threadIdx.x; k < v.chunks; k += 32) lexmin(bs, bi, v.part_s[(size_t)env * v.chunks + k], v.part_i[(size_t)env * v.chunks + k]);
+    warp_lexmin(bs, bi);
+    if (threadIdx.x == 0) *out = bi;
+}
+
+static View single_env_view(const View &v, int env) {
+    View w = v;   // shift every per-env array so that blockIdx.y == 0 addresses `env`
+    w.vx += (size_t)env * v.stride; w.vy += (size_t)env * v.stride; w.vz += (size_t)env * v.stride;
+    w.nodes += (size_t)env * v.stride;
+    w.geom += env; w.mt += env; w.ctl += env;
+    w.part_s += (size_t)env * v.chunks; w.part_i += (size_t)env * v.chunks;
+    w.cand += (size_t)env * v.near_cap; w.near_out += (size_t)env * v.near_cap;
+    w.E = 1;
+    return w;
+}
+
+extern "C" int nirrt_nearest_sync(nirrt_batch *b, int env, const double *queries, int64_t m, int64_t *out, void *stream) {
+    if (!b || env < 0 || env >= b->v.E || m < 0 || (m > 0 && (!queries || !out))) return fail(NIRRT_ERR_INVALID, "nirrt_nearest_sync: bad argument");
+    if (m == 0) return NIRRT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    TempBufs t;
+    double *dq; long long *dout;
+    TRY(t.up(queries, 3 * (size_t)m, s, &dq)); TRY(t.make<long long>((size_t)m, &dout));
+    View w = single_env_view(b->v, env);
+    for (int64_t k = 0; k < m; k++) {
+        k_set_query<<<1, 1, 0, s>>>(w, 0, dq + 3 * k, 0, 0.0);
+        k_nearest<true><<<dim3(w.chunks, 1), 256, 0, s>>>(w);
+        k_finish_nearest<<<1, 32, 0, s>>>(w, 0, dout + k);
+    }
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out, dout, sizeof(long long) * m, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int64_t nirrt_within_sync(nirrt_batch *b, int env, const double *q, double r, int64_t *out, int64_t cap, void *stream) {
+    if (!b || env < 0 || env >= b->v.E || !q || r < 0 || (cap > 0 && !out)) return fail(NIRRT_ERR_INVALID, "nirrt_within_sync: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    TempBufs t;
+    double *dq;
+    TRY(t.up(q, 3, s, &dq));
+    View w = single_env_view(b->v, env);
+    k_set_query<<<1, 1, 0, s>>>(w, 0, dq, 1, r);
+    k_near<true><<<dim3(w.chunks, 1), 256, 0, s>>>(w);
+    CHECK_LAUNCH();
+    TRY(fetch_ctl(b, s));
+    const int cnt = b->h_ctl[env].cand_cnt;
+    if (cnt > b->v.near_cap) return fail(NIRRT_ERR_CAPACITY, "nirrt_within_sync: more matches than near_capacity");
+    std::vector<int> h(cnt > 0 ? cnt : 1);
+    if (cnt > 0) {
+        CUDA_TRY(cudaMemcpyAsync(h.data(), b->v.cand + (size_t)env * b->v.near_cap, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        std::vector<int> sorted(h.begin(), h.begin() + cnt);
+        // marshalling only: the device appends matches unordered, callers expect ascending order
+        for (int i = 1; i < cnt; i++) { int x = sorted[i], j = i - 1; while (j >= 0 && sorted[j] > x) { sorted[j + 1] = sorted[j]; j--; } sorted[j + 1] = x; }
+        for (int i = 0; i < cnt && i < cap; i++) out[i] = sorted[i];
+    }
+    return cnt;
+}
+
+extern "C" int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int64_t m, double *out, void *stream) {
+    if (!b || env < 0 || env >= b->v.E || m < 0 || (m > 0 && (!idx || !out))) return fail(NIRRT_ERR_INVALID, "nirrt_costs_sync: bad argument");
+    if (m == 0) return NIRRT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    TRY(fetch_ctl(b, s));
+    for (int64_t i = 0; i < m; i++)
+        if (idx[i] < 0 || idx[i] >= b->h_ctl[env].n) return fail(NIRRT_ERR_INVALID, "vertex index out of range");
+    TempBufs t;
+    long long *di; double *dout;
+    TRY(t.up((const long long *)idx, (size_t)m, s, &di)); TRY(t.make<double>((size_t)m, &dout));
+    k_costs<<<(int)((m + 127) / 128), 128, 0, s>>>(b->v, env, di, m, dout);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *reserved) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    if (kernel_launches) *kernel_launches = b->launches;
+    if (reserved) *reserved = 0;
+    return NIRRT_OK;
+}
+
+__global__ void k_reset_cand(View v) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < v.E) v.ctl[e].cand_cnt = 0;
+}
+
+extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, float *ms, int64_t *bytes, void *stream) {
+    if (!b || reps < 1 || !ms || which < 0 || which > 1) return fail(NIRRT_ERR_INVALID, "nirrt_batch_time_scan_sync: bad argument");
+    View &v = b->v;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    TRY(fetch_ctl(b, s));
+    int64_t total = 0;
+    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * 24;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    float acc = 0.f;
+    for (int r = 0; r < reps; r++) {
+        if (which == 1) k_reset_cand<<<(v.E + 127) / 128, 128, 0, s>>>(v);
+        CUDA_TRY(cudaEventRecord(e0, s));
+        if (which == 0) k_nearest<true><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+        else k_near<true><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+        CUDA_TRY(cudaEventRecord(e1, s));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+        acc += t;
+    }
+    k_reset_cand<<<(v.E + 127) / 128, 128, 0, s>>>(v);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms = acc / reps;
+    if (bytes) *bytes = total;
+    return NIRRT_OK;
+}

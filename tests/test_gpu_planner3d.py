@@ -1,0 +1,196 @@
+"""GPU parity tests of the 3D planner path: CUDA (through the C ABI) vs the CPU oracle and vs the
+committed reference golden traces.  Bit-exact for indices and (RRT*) coordinates."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from nirrt_star_b200.synthetic import make_problem_3d
+
+pytestmark = pytest.mark.gpu
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "planner3d_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def B():
+    from nirrt_star_b200 import batch
+    return batch
+
+
+def _oracle(problem, iter_max, seed):
+    from oracle.planner_oracle import Oracle3D
+    return Oracle3D(problem, iter_max, seed=seed)
+
+
+def test_predicates_match_oracle(B):
+    problems = [make_problem_3d(i) for i in range(3)]
+    bp = B.BatchPlanner3D(problems, 50, seeds=[0, 1, 2])
+    rng = np.random.default_rng(0)
+    for e, pr in enumerate(problems):
+        o = _oracle(pr, 50, 0)
+        a = rng.uniform(-2, 52, (50000, 3)); d = rng.normal(size=(50000, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+        b = a + d * rng.uniform(0, 12, (50000, 1))
+        b[:300] = a[:300]
+        edges = np.stack([a, b], 1)
+        assert np.array_equal(bp.collide_edges(e, edges), o.collide_edges(edges))
+        pts = rng.uniform(-3, 53, (50000, 3)); pts[:2000] = np.round(pts[:2000])
+        assert np.array_equal(bp.points_inside_obs(e, pts), o.points_inside_obs(pts))
+        assert np.array_equal(bp.points_valid(e, pts), o.points_valid(pts))
+    # empty inputs are accepted
+    assert bp.collide_edges(0, np.zeros((0, 2, 3))).shape == (0,)
+
+
+def _grow_oracle(problem, iters, seed):
+    o = _oracle(problem, iters, seed)
+    o.run(iters, 0, 0)
+    return o
+
+
+def test_nearest_within_costs_on_loaded_tree(B):
+    pr = make_problem_3d(4)
+    iters = 3000
+    o = _grow_oracle(pr, iters, 3)
+    v, p = o.tree()
+    n = len(v)
+    bp = B.BatchPlanner3D([pr], iters, seeds=[3])
+    V = np.zeros((1, bp.capacity, 3)); P = np.zeros((1, bp.capacity), dtype=np.int64)
+    V[0, :n] = v; P[0, :n] = p
+    bp.load_trees(V, P, [n])
+    v2, p2, n2 = bp.read_trees()
+    assert n2[0] == n and np.array_equal(v2[0, :n], v) and np.array_equal(p2[0, :n], p)
+    assert not v2[0, n:].any() and not p2[0, n:].any()
+    rng = np.random.default_rng(1)
+    q = rng.uniform(0, 50, (64, 3))
+    q[:8] = v[rng.integers(0, n, 8)]                       # exact hits
+    assert np.array_equal(bp.nearest(0, q), o.nearest(q))
+    for k in range(16):
+        r = float(rng.uniform(0.5, 10))
+        assert np.array_equal(bp.within(0, q[k], r), o.within(q[k], r))
+    # radius exactly equal to an existing distance (the <= boundary)
+    d = np.linalg.norm(q[20] - v, axis=-1)
+    r = float(np.sort(d)[5])
+    assert np.array_equal(bp.within(0, q[20], r), o.within(q[20], r))
+    idx = rng.integers(0, n, 200)
+    want = np.array([o.cost(i) for i in idx])
+    assert np.array_equal(bp.costs(0, idx), want)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_per_iteration_trace_matches_oracle(B, variant):
+    """One iteration at a time: nearest index, new index, Near list and sample must be identical."""
+    E, iters = 6, 400
+    problems = [make_problem_3d(10 + i) for i in range(E)]
+    seeds = [100 + i for i in range(E)]
+    bp = B.BatchPlanner3D(problems, iters, seeds=seeds)
+    bp.begin(variant, B.MODE_PLANNING, iters)
+    oracles = [_oracle(pr, iters, s) for pr, s in zip(problems, seeds)]
+    for it in range(iters):
+        bp.run(1)
+        nearest, new, cnt, near, xr = bp.trace()
+        for e, o in enumerate(oracles):
+            r = o.run(1, variant, 0, trace=True)
+            assert nearest[e] == r["nearest"][0], (it, e)
+            assert new[e] == r["new"][0], (it, e)
+            if r["new"][0] >= 0:
+                assert cnt[e] == r["near_cnt"][0], (it, e)
+                assert np.array_equal(near[e, :cnt[e]], r["near"]), (it, e)
+    running, need = bp.status()
+    assert running == 0 and need == 0
+    v, p, n = bp.read_trees()
+    for e, o in enumerate(oracles):
+        ov, op = o.tree()
+        assert n[e] == len(ov)
+        assert np.array_equal(p[e, :n[e]], op)
+        assert np.array_equal(v[e, :n[e]], ov)              # same op sequence on both sides -> bit exact
+        if variant == 1:
+            assert np.array_equal(bp.solutions(e), o.solutions())
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_planning_random_matches_oracle(B, variant):
+    E, iter_max, iter_after = 8, 1500, 250
+    problems = [make_problem_3d(30 + i) for i in range(E)]
+    seeds = [7 + 3 * i for i in range(E)]
+    bp = B.BatchPlanner3D(problems, iter_max, seeds=seeds, record_capacity=iter_max + iter_after + 8)
+    bp.begin(variant, B.MODE_PLANNING_RANDOM, iter_max, iter_after)
+    bp.run_to_completion(chunk=128)
+    lists = bp.path_len_lists()
+    v, p, n = bp.read_trees()
+    for e in range(E):
+        o = _oracle(problems[e], iter_max, seeds[e])
+        want = np.array(o.planning_random(iter_after, variant))
+        got = np.array(lists[e])
+        assert len(got) == len(want), (e, len(got), len(want))
+        assert np.array_equal(np.isinf(got), np.isinf(want))
+        f = np.isfinite(want)
+        assert np.allclose(got[f], want[f], rtol=1e-12, atol=0)
+        ov, op = o.tree()
+        assert n[e] == len(ov) and np.array_equal(p[e, :n[e]], op) and np.array_equal(v[e, :n[e]], ov)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_matches_reference_golden(B, path):
+    """CUDA path vs traces recorded from the REFERENCE's own classes (tests/golden)."""
+    g = np.load(path)
+    kind, mode = str(g["kind"]), str(g["mode"])
+    variant = {"rrt": 0, "irrt": 1}[kind]
+    iter_max, iter_after = int(g["iter_max"]), int(g["iter_after"])
+    pr = make_problem_3d(int(g["env_idx"]))
+    bp = B.BatchPlanner3D([pr], iter_max, seeds=[int(g["seed"])], record_capacity=iter_max + iter_after + 8)
+    if mode == "planning":
+        bp.begin(variant, B.MODE_PLANNING, iter_max)
+    else:
+        bp.begin(variant, B.MODE_PLANNING_RANDOM, iter_max, iter_after)
+    bp.run_to_completion(chunk=200)
+    v, p, n = bp.read_trees()
+    assert n[0] == int(g["num_vertices"])
+    assert np.array_equal(p[0, :n[0]], g["parents"])
+    if variant == 0:
+        assert np.array_equal(v[0, :n[0]], g["vertices"])
+    else:
+        assert np.allclose(v[0, :n[0]], g["vertices"], rtol=0, atol=1e-12)
+        assert np.array_equal(bp.solutions(0), g["solutions"])
+    if mode == "random":
+        got = np.array(bp.path_len_lists()[0]); want = g["path_len_list"]
+        assert len(got) == len(want)
+        assert np.array_equal(np.isinf(got), np.isinf(want))
+        f = np.isfinite(want)
+        assert np.allclose(got[f], want[f], rtol=1e-5, atol=0)
+    else:
+        gp, cost = bp.goal_parents()
+        if len(g["path"]):
+            # extract_path(goal_parent)[-2] is the goal parent vertex
+            assert np.array_equal(v[0, gp[0]], g["path"][-2])
+        else:
+            assert gp[0] == -1
+
+
+def test_large_tree_window_matches_oracle(B):
+    """Steady-state window on a big tree (the benchmark regime, scaled to what the oracle grows in
+    seconds): grow on the GPU, continue on both sides from the same snapshot + RNG state."""
+    E, grow, window = 4, 20000, 200
+    problems = [make_problem_3d(50 + i) for i in range(E)]
+    seeds = [900 + i for i in range(E)]
+    cap_iters = grow + window
+    bp = B.BatchPlanner3D(problems, cap_iters, seeds=seeds)
+    bp.begin(0, B.MODE_PLANNING, cap_iters)
+    bp.run(grow)
+    v, p, n = bp.read_trees()
+    states = bp.get_rng()
+    assert n.min() > grow // 4
+    from oracle.planner_oracle import Oracle3D
+    oracles = []
+    for e in range(E):
+        o = Oracle3D(problems[e], cap_iters, rng_state=states[e])
+        o.load_tree(v[e, :n[e]], p[e, :n[e]])
+        oracles.append(o)
+    bp.run(window)
+    v2, p2, n2 = bp.read_trees()
+    for e, o in enumerate(oracles):
+        o.run(window, 0, 0)
+        ov, op = o.tree()
+        assert n2[e] == len(ov)
+        assert np.array_equal(p2[e, :n2[e]], op)
+        assert np.array_equal(v2[e, :n2[e]], ov)
