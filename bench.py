@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- RRT* iterations/s at 100k-node trees on random_3d worlds (BASELINE.json metric).
+
+A "step" is ONE lock-step iteration of the RRT* loop body (Sample, Nearest scan, Steer + collision,
+Near scan, ChooseParent, Rewire -- rrt_star_3d.py:36-55 of the reference) over a batch of E
+independent planning problems per GPU whose trees already hold `--nodes` vertices.  Workload at
+N=1: BASELINE.json configs[4] scaled to one GPU (4096 envs / 8 GPUs = 512 envs per GPU, 100k-node
+trees); more GPUs shard more problems (weak scaling), with one NCCL gather of per-problem results.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+  python bench.py --impl reference ...                          CPU arm: numpy port of the reference
+                                                                loop body on all host cores
+
+Prints ONE JSON line (see the keys below).  Trees are grown to size by the CUDA planner itself
+before the timed region (parity-tested path); inputs are larger than L2 (E x n x 24 B per scan =
+1.2 GB at the default size), so no L2 flush is needed between steps.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RRT* iters/sec at 100k nodes (random_3d)"
+UNIT = "env-iters/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=512, help="planning problems per GPU")
+    ap.add_argument("--nodes", type=int, default=100000, help="tree size at the start of the timed window")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample length per core")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="wrap the timed core region in cudaProfilerStart/Stop (ncu --profile-from-start off)")
+    ap.add_argument("--core-only", action="store_true", help="skip roofline/eval/e2e/cpu legs (profiling runs)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (numpy port of the reference loop body; oracle/ is test infrastructure -- this is one of
+# the two places allowed to execute it)
+
+def _cpu_worker_snapshot(args):
+    """Times the numpy port for ~seconds on a tree snapshot; returns (iters, elapsed)."""
+    path, env_idx, seconds = args
+    from nirrt_star_b200.synthetic import make_problem_3d
+    from oracle.numpy_port import RRTStar3DPort
+    d = np.load(path)
+    pr = make_problem_3d(env_idx)
+    rs = np.random.RandomState(0)
+    rs.set_state(("MT19937", d["key"], int(d["pos"]), 0, 0.0))
+    n = int(d["n"])
+    port = RRTStar3DPort(pr, n + 20000, rng=rs)
+    port.load_tree(d["v"][:n], d["p"][:n])
+    port.run(3)
+    t0 = time.perf_counter(); it = 0
+    while time.perf_counter() - t0 < seconds:
+        port.iterate(); it += 1
+    return it, time.perf_counter() - t0
+
+
+def cpu_baseline_from_snapshot(bp, v, p, n, rng_states, env_base, seconds):
+    cores = os.cpu_count() or 1
+    workers = min(cores, bp.E)
+    tmp = tempfile.mkdtemp(prefix="nirrt_cpu_")
+    jobs = []
+    for k in range(workers):
+        path = os.path.join(tmp, f"env{k}.npz")
+        np.savez(path, v=v[k], p=p[k], n=n[k], key=rng_states[k][0], pos=rng_states[k][1])
+        jobs.append((path, env_base + k, seconds))
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker_snapshot, jobs)
+    wall = time.perf_counter() - t0
+    rate = sum(it / el for it, el in res)
+    return {"value": rate, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": f"{workers} problems (one per host core) x ~{seconds:.0f} s of the numpy port of the reference "
+                      f"loop body, continuing from the same {int(n[0])}-vertex GPU-grown trees and RNG states; "
+                      f"{sum(it for it, _ in res)} iterations in {wall:.0f} s wall",
+            "per_core": rate / workers}
+
+
+def _ref_worker(conn, env_idx, seed, nodes):
+    """--impl reference worker: grows its own tree with the C oracle (untimed), then executes
+    `count` numpy-port iterations per request."""
+    from nirrt_star_b200.synthetic import make_problem_3d
+    from oracle.numpy_port import RRTStar3DPort
+    from oracle.planner_oracle import Oracle3D
+    pr = make_problem_3d(env_idx)
+    cap_iters = int(nodes * 1.6) + 50000
+    o = Oracle3D(pr, cap_iters, seed=seed)
+    while o.num_vertices < nodes:
+        o.run(min(2000, max(1, nodes - o.num_vertices)), 0, 0)
+    v, p = o.tree()
+    key, pos = o.rng_state()
+    rs = np.random.RandomState(0)
+    rs.set_state(("MT19937", key, pos, 0, 0.0))
+    port = RRTStar3DPort(pr, len(v) + 200000, rng=rs)
+    port.load_tree(v, p)
+    del o
+    t0 = time.perf_counter(); port.run(5); rate = 5 / (time.perf_counter() - t0)
+    conn.send(("ready", rate, port.num_vertices))
+    while True:
+        msg = conn.recv()
+        if msg == "stop":
+            break
+        t0 = time.perf_counter()
+        port.run(msg)
+        conn.send(time.perf_counter() - t0)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    procs, conns = [], []
+    for k in range(cores):
+        a, b = ctx.Pipe()
+        pr = ctx.Process(target=_ref_worker, args=(b, k, 1000 + k, args.nodes), daemon=True)
+        pr.start(); procs.append(pr); conns.append(a)
+    rates = []
+    for c in conns:
+        tag, rate, n = c.recv(); rates.append(rate)
+    # bounded sample: iterations per worker per step so that the whole run takes ~2 minutes
+    per_step = max(1, int(120.0 * min(rates) / max(1, args.steps + args.warmup)))
+
+    def step():
+        for c in conns:
+            c.send(per_step)
+        for c in conns:
+            c.recv()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    for c in conns:
+        c.send("stop")
+    value = cores * per_step * args.steps / el
+    sample = (f"{cores} processes (one per host core), each a {args.nodes}-vertex RRT* tree grown by the C oracle; "
+              f"one step = {per_step} numpy-port iteration(s) per process")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"rrt_star 3D random_3d, {args.nodes}-node trees, CPU numpy port of the reference loop body",
+                      "nodes": args.nodes, "iters_per_step_per_process": per_step},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nirrt_star_b200 import batch as B
+    from nirrt_star_b200.synthetic import make_problem_3d
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    E, nodes, K, W = args.envs, args.nodes, args.steps, args.warmup
+    env_base = rank * E
+    problems = [make_problem_3d(env_base + i) for i in range(E)]
+    seeds = [5000 + env_base + i for i in range(E)]
+    slack = W + 3 * K + 4096
+    bp = B.BatchPlanner3D(problems, nodes + slack, seeds=seeds, device=local, record_capacity=K + W + 64)
+
+    # ---- untimed: grow every tree to exactly `nodes` vertices with the CUDA planner itself
+    t_grow0 = time.perf_counter()
+    bp.begin(B.VARIANT_RRT_STAR, B.MODE_PLANNING, 1 << 30)
+    bp.set_vertex_limit(nodes)
+    while True:
+        bp.run(4000)
+        _, _, nv = bp.env_state()
+        if nv.min() >= nodes:
+            break
+    bp.set_vertex_limit(0)
+    grow_s = time.perf_counter() - t_grow0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # snapshot (host, pinned) for the e2e leg and the CPU baseline
+    snap = None
+    if not args.no_e2e or (rank == 0 and not args.no_cpu_baseline):
+        v_pin = torch.empty((E, bp.capacity, 3), dtype=torch.float64, pin_memory=True)
+        p_pin = torch.empty((E, bp.capacity), dtype=torch.int64, pin_memory=True)
+        v_np, p_np = v_pin.numpy(), p_pin.numpy()
+        _, _, n_np = bp.read_trees(out=(v_np, p_np))
+        snap = (v_np, p_np, n_np, bp.get_rng())
+
+    # ---- timed: core variant (planning() loop body)
+    def timed_region(variant_mode):
+        bp.begin(B.VARIANT_RRT_STAR, variant_mode, 1 << 30, 1 << 30)
+        bp.run(W)
+        _, _, n0 = bp.env_state()
+        barrier()
+        sampler = ClockSampler(local); sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = bp.kernel_launches()
+        if args.profile_range:
+            torch.cuda.profiler.start()
+        ev0.record()
+        bp.run(K)
+        ev1.record()
+        if args.profile_range:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        barrier()
+        clocks = sampler.stop()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        _, _, n1 = bp.env_state()
+        return ms, clocks, bp.kernel_launches() - launches0, n0, n1
+
+    ms_core, clocks, launches, n0, n1 = timed_region(B.MODE_PLANNING)
+    value = world * E * K / (ms_core / 1e3)
+    if args.core_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_core / K, "core_only": True}))
+        return
+
+    # ---- roofline attribution: same steps with an event bracket around every launch
+    prof_iters = min(K, 200)
+    prof = bp.run_profiled(prof_iters)
+    _, _, n2 = bp.env_state()
+    scan_bytes = float(0.5 * (n1.astype(np.float64).sum() + n2.astype(np.float64).sum()) * 24.0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    t_near_ms = prof["nearest"] / prof_iters
+    achieved = scan_bytes / (t_near_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_nearest_dram_bytes_per_launch")
+    except Exception:
+        pass
+    step_ms = sum(prof.values()) / prof_iters
+    roofline = {"bound": "hbm", "kernel": "k_nearest (Nearest argmin scan, f64 SoA)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": scan_bytes,
+                "near_scan": {"achieved": scan_bytes / (prof["near"] / prof_iters * 1e-3) / 1e9,
+                              "frac": scan_bytes / (prof["near"] / prof_iters * 1e-3) / 1e9 / peak},
+                "kernel_ms_per_step": {k: v / prof_iters for k, v in prof.items()},
+                "kernel_share_of_step": {k: v / prof_iters / step_ms for k, v in prof.items()}}
+
+    # ---- eval variant (planning_random body: + search_goal_parent / path length every iteration)
+    ms_eval, _, _, _, _ = timed_region(B.MODE_PLANNING_RANDOM)
+    value_eval = world * E * K / (ms_eval / 1e3)
+
+    # ---- e2e through the C ABI with host buffers: snapshot H2D + K iterations + results D2H
+    e2e = None
+    if not args.no_e2e:
+        v_np, p_np, n_np, rng_states = snap
+        out_v = torch.empty((E, bp.capacity, 3), dtype=torch.float64, pin_memory=True).numpy()
+        out_p = torch.empty((E, bp.capacity), dtype=torch.int64, pin_memory=True).numpy()
+        reps = 2
+        best = None
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            bp.load_trees(v_np, p_np, n_np)                      # H2D: trees (reference layout)
+            bp.set_rng(rng_states)                               # H2D: RNG streams
+            bp.begin(B.VARIANT_RRT_STAR, B.MODE_PLANNING, 1 << 30)
+            bp.run(K)
+            bp.read_trees(out=(out_v, out_p))                    # D2H: vertices / parents / num_vertices
+            gp, cost = bp.goal_parents()                         # D2H: goal parent + path cost per problem
+            barrier()
+            el = time.perf_counter() - t0
+            best = el if best is None else min(best, el)
+        if world > 1:
+            t = torch.tensor([best], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item())
+        h2d = float((n_np.astype(np.float64) * 32).sum() + E * 625 * 4)
+        d2h = float(E * bp.capacity * 32 + E * 16)
+        e2e = {"value": world * E * K / best, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+               "seconds": best,
+               "what": "nirrt_batch_load_trees + set_rng (pinned host -> HBM) + K iterations + read_trees + goal_parents (HBM -> pinned host)"}
+
+    # ---- the one collective: gather per-problem results on every rank (NCCL all_gather)
+    gp, cost = bp.goal_parents()
+    _, _, nv = bp.env_state()
+    summary = torch.tensor(np.stack([cost, nv.astype(np.float64)], 1), device="cuda")
+    if world > 1:
+        gathered = [torch.empty_like(summary) for _ in range(world)]
+        dist.all_gather(gathered, summary)
+        summary = torch.cat(gathered)
+    solved = int(torch.isfinite(summary[:, 0]).sum().item())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v_np, p_np, n_np, rng_states = snap
+        cpu = cpu_baseline_from_snapshot(bp, v_np, p_np, n_np, rng_states, env_base, args.cpu_seconds)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms_core / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"rrt_star 3D random_3d (BASELINE configs[4] per-GPU shard): {E} problems/GPU in lock step, "
+                                      f"{nodes}-node trees, planning() loop body",
+                          "envs_per_gpu": E, "nodes_at_window_start": int(n0.min()), "nodes_at_window_end": int(n1.max()),
+                          "l2": "inputs larger than L2 (%.2f GB scanned per kernel launch)" % (scan_bytes / 1e9),
+                          "tree_growth": "grown 1 -> %d vertices by the same CUDA planner, untimed (%.0f s)" % (nodes, grow_s),
+                          "timing": "CUDA events on the launch stream, barrier + synchronize both sides, max over ranks"},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+               "eval_variant": {"value": value_eval, "unit": UNIT, "ms_per_step": ms_eval / K,
+                                "what": "planning_random loop body (adds goal-parent search + path length per iteration)"},
+               "problems_with_solution": solved, "problems_total": world * E}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

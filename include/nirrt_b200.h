@@ -105,6 +105,13 @@ int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter_max, int i
  * Problems that finished their driver idle.  No host synchronisation. */
 int nirrt_batch_run(nirrt_batch *b, int iters, void *stream);
 
+/* Benchmark pre-growth: while limit > 0, problems whose tree already holds `limit` vertices idle
+ * (they neither sample nor consume iterations), so a batch can be grown to a common size. */
+int nirrt_batch_set_vertex_limit(nirrt_batch *b, int limit);
+/* nirrt_batch_run with a CUDA-event bracket around every kernel launch; ms5 receives the summed
+ * device milliseconds of {top, nearest scan, steer, near scan, expand} over `iters` iterations. */
+int nirrt_batch_run_profiled_sync(nirrt_batch *b, int iters, float *ms5, void *stream);
+
 /* Waits for the stream; returns the number of problems whose driver has not finished in *running
  * and the number waiting for a guidance cloud in *need_cloud.  Returns NIRRT_ERR_CAPACITY if any
  * problem overflowed a device buffer. */

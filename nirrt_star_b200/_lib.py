@@ -66,6 +66,8 @@ def lib():
     L.nirrt_within_sync.restype = C.c_int64
     L.nirrt_within_sync.argtypes = [V, C.c_int, c_dp, C.c_double, c_i64p, C.c_int64, V]
     L.nirrt_costs_sync.argtypes = [V, C.c_int, c_i64p, C.c_int64, c_dp, V]
+    L.nirrt_batch_set_vertex_limit.argtypes = [V, C.c_int]
+    L.nirrt_batch_run_profiled_sync.argtypes = [V, C.c_int, c_fp, V]
     L.nirrt_batch_counters.argtypes = [V, c_i64p, c_i64p]
     L.nirrt_batch_time_scan_sync.argtypes = [V, C.c_int, C.c_int, c_fp, c_i64p, V]
     _LIB = L

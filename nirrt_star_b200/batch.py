@@ -173,6 +173,15 @@ class BatchPlanner3D:
     def run(self, iters):
         check(self.L.nirrt_batch_run(self.h, int(iters), self.stream))
 
+    def set_vertex_limit(self, limit):
+        check(self.L.nirrt_batch_set_vertex_limit(self.h, int(limit)))
+
+    def run_profiled(self, iters):
+        """Like run(), synchronous, returning summed device ms of the five kernels."""
+        ms = (C.c_float * 5)()
+        check(self.L.nirrt_batch_run_profiled_sync(self.h, int(iters), ms, self.stream))
+        return dict(zip(("top", "nearest", "steer", "near", "expand"), [float(x) for x in ms]))
+
     def status(self):
         running = C.c_int(0); need = C.c_int(0)
         check(self.L.nirrt_batch_status_sync(self.h, C.byref(running), C.byref(need), self.stream))

@@ -91,6 +91,7 @@ struct EnvCtl {
 struct View {
     int E, cap, stride, chunks, near_cap, rec_cap, sol_cap, pc_cap, path_cap;
     int variant, mode, iter_max, iter_after;
+    int n_limit;     // > 0: problems whose tree reached n_limit vertices idle (benchmark pre-growth)
     double pc_rate, pc_ratio;
     double *vx, *vy, *vz;
     Node *nodes;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
     __shared__ double sm_s[4];
     __shared__ int sm_i[4];
     const int state = c->state, budget = c->budget;
-    if (state == ST_DONE || state == ST_WAIT_CLOUD || budget <= 0) {
+    if (state == ST_DONE || state == ST_WAIT_CLOUD || budget <= 0 || (v.n_limit > 0 && c->n >= v.n_limit)) {
         if (threadIdx.x == 0) c->go = 0;
         return;
     }
@@ -1191,6 +1192,50 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
     for (int it = 0; it < iters; it++) launch_iteration(b, s);
     CHECK_LAUNCH();
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_set_vertex_limit(nirrt_batch *b, int limit) {
+    if (!b || limit < 0) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_vertex_limit: bad argument");
+    b->v.n_limit = limit;
+    return NIRRT_OK;
+}
+
+// Same work as nirrt_batch_run, with a CUDA-event bracket around every launch: returns the summed
+// device time of each of the five kernels over `iters` iterations (roofline attribution).
+extern "C" int nirrt_batch_run_profiled_sync(nirrt_batch *b, int iters, float *ms5, void *stream) {
+    if (!b || iters < 1 || !ms5) return fail(NIRRT_ERR_INVALID, "nirrt_batch_run_profiled_sync: bad argument");
+    View &v = b->v;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<cudaEvent_t> ev((size_t)iters * 6);
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
+    for (int it = 0; it < iters; it++) {
+        cudaEvent_t *e = ev.data() + (size_t)it * 6;
+        cudaEventRecord(e[0], s);
+        k_top<<<v.E, 128, 0, s>>>(v);
+        cudaEventRecord(e[1], s);
+        k_nearest<false><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+        cudaEventRecord(e[2], s);
+        k_steer<<<v.E, 32, 0, s>>>(v);
+        cudaEventRecord(e[3], s);
+        k_near<false><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+        cudaEventRecord(e[4], s);
+        k_expand<<<v.E, kExpandThreads, 0, s>>>(v);
+        cudaEventRecord(e[5], s);
+    }
+    b->launches += 5LL * iters;
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int k = 0; k < 5; k++) ms5[k] = 0.f;
+    for (int it = 0; it < iters; it++)
+        for (int k = 0; k < 5; k++) {
+            float t = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&t, ev[(size_t)it * 6 + k], ev[(size_t)it * 6 + k + 1]));
+            ms5[k] += t;
+        }
+    for (auto &e : ev) cudaEventDestroy(e);
     return NIRRT_OK;
 }
 
