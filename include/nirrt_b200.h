@@ -100,6 +100,11 @@ int nirrt_batch_read_trees_sync(nirrt_batch *b, int env_begin, int count, int *n
  * used.  Resets per-problem phase machines and record counters (not the trees). */
 int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter_max, int iter_after_initial, void *stream);
 
+/* planning_block_gap(path_len_threshold) (rrt_star_2d.py:159-196, irrt_star_3d.py:193-243): call after
+ * nirrt_batch_begin(..., NIRRT_MODE_PLANNING_RANDOM, iter_max, 0); phase 1 then ends as soon as the
+ * recorded value is < stop_below instead of < inf.  nirrt_batch_begin resets it to +inf. */
+int nirrt_batch_set_stop_threshold(nirrt_batch *b, double stop_below);
+
 /* Enqueues `iters` lock-step iterations of the loop body on every problem that is still running
  * (Sample -> Nearest scan -> Steer + collision -> Near scan -> ChooseParent/Rewire/goal work).
  * Problems that finished their driver idle.  No host synchronisation. */

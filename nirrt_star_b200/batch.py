@@ -173,6 +173,9 @@ class BatchPlanner3D:
     def run(self, iters):
         check(self.L.nirrt_batch_run(self.h, int(iters), self.stream))
 
+    def set_stop_threshold(self, stop_below):
+        check(self.L.nirrt_batch_set_stop_threshold(self.h, float(stop_below)))
+
     def set_vertex_limit(self, limit):
         check(self.L.nirrt_batch_set_vertex_limit(self.h, int(limit)))
 

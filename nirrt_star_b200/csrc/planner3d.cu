@@ -91,6 +91,7 @@ struct EnvCtl {
 struct View {
     int E, cap, stride, chunks, near_cap, rec_cap, sol_cap, pc_cap, path_cap;
     int variant, mode, iter_max, iter_after;
+    double stop_below; // phase 1 ends when the recorded value drops below this (+inf: planning_random; finite: planning_block_gap)
     int n_limit;     // > 0: problems whose tree reached n_limit vertices idle (benchmark pre-growth)
     double pc_rate, pc_ratio;
     double *vx, *vy, *vz;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
         c->c_best = c_best;
         if (v.mode == NIRRT_MODE_PLANNING_RANDOM) {
             if (c->state == ST_PHASE1) {
-                if (c_best < XINF) { c->state = ST_PHASE2; c->left = v.iter_after; }
+                if (c_best < v.stop_below) { c->state = ST_PHASE2; c->left = v.iter_after; }
                 else if (c->p1_done >= v.iter_max) { push_record(v, c, e, c_best); c->state = ST_DONE; c->go = 0; return; }
             }
             if (c->state == ST_PHASE2 && c->left <= 0) { push_record(v, c, e, c_best); c->state = ST_DONE; c->go = 0; return; }
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
             push_record(v, c, e, len);
             if (c->state == ST_PHASE1) {
                 c->p1_done++;
-                if (len < XINF) { c->state = ST_PHASE2; c->left = v.iter_after; if (c->left <= 0) c->state = ST_DONE; }
+                if (len < v.stop_below) { c->state = ST_PHASE2; c->left = v.iter_after; if (c->left <= 0) c->state = ST_DONE; }
                 else if (c->p1_done >= v.iter_max) c->state = ST_DONE;
             } else {
                 c->left--;
@@ -940,7 +941,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     v.rec_cap = d->record_capacity > 0 ? d->record_capacity : d->capacity + 8;
     v.sol_cap = v.rec_cap;
     v.pc_cap = 4096; v.path_cap = 4096;
-    v.pc_rate = 0.5; v.pc_ratio = 0.9;
+    v.pc_rate = 0.5; v.pc_ratio = 0.9; v.stop_below = (double)INFINITY;
     const size_t EV = (size_t)v.E * v.stride;
     DALLOC(v.vx, double, EV); DALLOC(v.vy, double, EV); DALLOC(v.vz, double, EV);
     DALLOC(v.nodes, Node, EV);
@@ -1163,6 +1164,7 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     v.variant = variant; v.mode = mode; v.iter_max = iter_max; v.iter_after = iter_after_initial;
+    v.stop_below = (double)INFINITY;
     k_begin<<<(v.E + 127) / 128, 128, 0, s>>>(v);
     CHECK_LAUNCH();
     if (variant == 0 && mode == NIRRT_MODE_PLANNING_RANDOM) {
@@ -1192,6 +1194,12 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
     for (int it = 0; it < iters; it++) launch_iteration(b, s);
     CHECK_LAUNCH();
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_set_stop_threshold(nirrt_batch *b, double stop_below) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    b->v.stop_below = stop_below;
     return NIRRT_OK;
 }
 

@@ -62,6 +62,7 @@ def run_case(kind, env_idx, seed, iter_max, mode, iter_after=0):
             plist = np.zeros(0)
         else:
             plist = np.array(pl.planning_random(iter_after), dtype=np.float64)
+    next_random = np.random.random()   # pins how far the reference advanced the global stream
     n = pl.num_vertices
     k = len(tr["nearest"])
     near_cnt = np.full(k, -1, dtype=np.int64)   # -1: steer edge collided (find_near not called)
@@ -77,7 +78,7 @@ def run_case(kind, env_idx, seed, iter_max, mode, iter_after=0):
                         nearest=np.array(tr["nearest"], dtype=np.int64), rand=np.array(tr["rand"]),
                         near_cnt=near_cnt, near=near_flat, vertices=pl.vertices[:n].copy(),
                         parents=pl.vertex_parents[:n].astype(np.int64), num_vertices=n,
-                        path_len_list=plist, solutions=sols, path=path)
+                        path_len_list=plist, solutions=sols, path=path, next_random=next_random)
     print(name, "iters", k, "n", n, "finite", int(np.isfinite(plist).sum()) if len(plist) else "-")
 
 
