@@ -90,3 +90,84 @@ def make_problem_3d(env_idx, base_seed=100):
         "env_dict": env_dict,
         "search_radius": gamma_rrt_star_3d(env_dict, base_seed + env_idx),
     }
+
+
+# ---------------------------------------------------------------------------------------------
+# Synthetic PointNet++ checkpoint (the trained weights are a Google-Drive download, absent offline)
+
+POINTNET2_SA = [  # npoint, radii, nsamples, in_channel, mlps            (pointnet2.py:11-14)
+    (1024, (0.05, 0.1), (16, 32), 6, ((16, 16, 32), (32, 32, 64))),
+    (256, (0.1, 0.2), (16, 32), 96, ((64, 64, 128), (64, 96, 128))),
+    (64, (0.2, 0.4), (16, 32), 256, ((128, 196, 256), (128, 196, 256))),
+    (16, (0.4, 0.8), (16, 32), 512, ((256, 256, 512), (256, 384, 512))),
+]
+POINTNET2_FP = [  # name, in_channel, mlp                                  (pointnet2.py:15-18)
+    ("fp4", 1536, (256, 256)), ("fp3", 512, (256, 256)), ("fp2", 352, (256, 128)), ("fp1", 128, (128, 128, 128)),
+]
+# conv2.bias[1] shift that makes ~half of a uniform cloud "path" for the seed-0 checkpoint
+# (SURVEY.md 8c item 4); measured once with tests/golden/make_golden_pointnet2.py --calibrate
+POINTNET2_BIAS_SHIFT = {0: 0.84}
+
+
+def make_pointnet2_state(seed=0, num_classes=2):
+    """A ``model_state_dict`` with exactly the reference's 240 keys and shapes
+    (pointnet_pointnet2/models/pointnet2.py:8-22), He-uniform weights, non-trivial BatchNorm
+    statistics so that BN folding is exercised.  numpy arrays, generated from ``seed`` only."""
+    rs = np.random.RandomState(1000 + seed)
+    sd = {}
+
+    def conv(prefix, cin, cout, kdims):
+        b = math.sqrt(6.0 / cin)
+        sd[prefix + ".weight"] = rs.uniform(-b, b, (cout, cin) + (1,) * kdims).astype(np.float32)
+        sd[prefix + ".bias"] = rs.uniform(-0.1, 0.1, cout).astype(np.float32)
+
+    def bn(prefix, c):
+        sd[prefix + ".weight"] = rs.uniform(0.7, 1.3, c).astype(np.float32)
+        sd[prefix + ".bias"] = rs.uniform(-0.2, 0.2, c).astype(np.float32)
+        sd[prefix + ".running_mean"] = (0.2 * rs.standard_normal(c)).astype(np.float32)
+        sd[prefix + ".running_var"] = rs.uniform(0.6, 1.6, c).astype(np.float32)
+        sd[prefix + ".num_batches_tracked"] = np.array(0, dtype=np.int64)
+
+    for li, (_, _, _, cin, mlps) in enumerate(POINTNET2_SA, start=1):
+        for si, mlp in enumerate(mlps):
+            last = cin + 3
+            for j, cout in enumerate(mlp):
+                conv(f"sa{li}.conv_blocks.{si}.{j}", last, cout, 2)
+                bn(f"sa{li}.bn_blocks.{si}.{j}", cout)
+                last = cout
+    for name, cin, mlp in POINTNET2_FP:
+        last = cin
+        for j, cout in enumerate(mlp):
+            conv(f"{name}.mlp_convs.{j}", last, cout, 1)
+            bn(f"{name}.mlp_bns.{j}", cout)
+            last = cout
+    conv("conv1", 128, 128, 1)
+    bn("bn1", 128)
+    conv("conv2", 128, num_classes, 1)
+    sd["conv2.bias"][1] += np.float32(POINTNET2_BIAS_SHIFT.get(seed, 0.0))
+    return sd
+
+
+def make_cloud_3d(env_idx, n_points=2048, base_seed=100):
+    """(pc f32 (n,3), start_mask f32 (n,), goal_mask f32 (n,)) : uniform free-space samples of a
+    synthetic random_3d world plus the start/goal neighbourhood masks the planners feed the
+    network (datasets/point_cloud_mask_utils.py:20-31, nirrt_star_png_3d.py:157-166)."""
+    pr = make_problem_3d(env_idx, base_seed)
+    rs = np.random.RandomState(7000 + env_idx)
+    ed = pr["env_dict"]
+    box = np.asarray(ed["box_obstacles"], dtype=np.float64).reshape(-1, 6)
+    ball = np.asarray(ed["ball_obstacles"], dtype=np.float64).reshape(-1, 4)
+    pts = np.zeros((0, 3))
+    while len(pts) < n_points:
+        p = rs.uniform(0, 50, (4 * n_points, 3))
+        inside = np.zeros(len(p), dtype=bool)
+        for b in box:
+            inside |= np.all((b[:3] - 2 <= p) & (p <= b[:3] + b[3:] + 2), axis=1)
+        for b in ball:
+            inside |= ((p - b[:3]) ** 2).sum(axis=1) <= (b[3] + 2) ** 2
+        pts = np.concatenate([pts, p[~inside]])
+    pc = pts[:n_points].astype(np.float32)
+    r = 10.0
+    sm = (np.linalg.norm(pc - np.array(pr["x_start"], dtype=np.float32), axis=1) < r).astype(np.float32)
+    gm = (np.linalg.norm(pc - np.array(pr["x_goal"], dtype=np.float32), axis=1) < r).astype(np.float32)
+    return pc, sm, gm
