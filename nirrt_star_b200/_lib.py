@@ -23,6 +23,11 @@ class NirrtError(RuntimeError):
     pass
 
 
+class Pn2Layer(C.Structure):
+    _fields_ = [("weight", c_fp), ("bias", c_fp), ("bn_weight", c_fp), ("bn_bias", c_fp), ("bn_mean", c_fp),
+                ("bn_var", c_fp), ("c_in", C.c_int), ("c_out", C.c_int)]
+
+
 class BatchDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("n_envs", C.c_int), ("capacity", C.c_int), ("record_capacity", C.c_int),
                 ("near_capacity", C.c_int), ("device", C.c_int)]
@@ -71,6 +76,20 @@ def lib():
     L.nirrt_batch_run_profiled_sync.argtypes = [V, C.c_int, c_fp, V]
     L.nirrt_batch_counters.argtypes = [V, c_i64p, c_i64p]
     L.nirrt_batch_time_scan_sync.argtypes = [V, C.c_int, C.c_int, c_fp, c_i64p, V]
+    # PointNet++ (include/nirrt_pointnet2.h)
+    c_i32p = C.POINTER(C.c_int32)
+    c_u16p = C.POINTER(C.c_uint16)
+    L.nirrt_pn2_create.argtypes = [C.POINTER(Pn2Layer), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(V)]
+    L.nirrt_pn2_destroy.argtypes = [V]
+    L.nirrt_pn2_classify_sync.argtypes = [V, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_i32p, c_i64p, c_fp, c_fp, V]
+    L.nirrt_pn2_classify_device.argtypes = [V, C.c_int, C.c_int, V, V, V, V, V, V, V, V]
+    L.nirrt_pn2_read_buffer_sync.restype = C.c_int64
+    L.nirrt_pn2_read_buffer_sync.argtypes = [V, C.c_char_p, V, C.c_int64, V]
+    L.nirrt_pn2_set_profiling.argtypes = [V, C.c_int]
+    L.nirrt_pn2_last_stage_ms.argtypes = [V, c_fp]
+    L.nirrt_pn2_launch_count.restype = C.c_int64
+    L.nirrt_pn2_launch_count.argtypes = [V]
+    L.nirrt_gemm_f16_sync.argtypes = [c_u16p, c_u16p, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_u16p, V]
     _LIB = L
     return L
 
@@ -86,6 +105,10 @@ def require_device():
     if n <= 0:
         raise NirrtError("no sm_100 (B200) CUDA device visible: nirrt_star_b200 has no CPU fallback")
     return n
+
+
+def fp(a):
+    return a.ctypes.data_as(c_fp)
 
 
 def dp(a):

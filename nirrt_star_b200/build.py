@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "libnirrt_b200.so")
 # this keeps the compiler from contracting anything that slips through).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
-UNITS = [("planner3d.cu", ["-fmad=false"])]
+UNITS = [("planner3d.cu", ["-fmad=false"]), ("pointnet2.cu", [])]
 
 
 def _nvcc():
@@ -26,6 +26,7 @@ def sources():
     for root, _, files in os.walk(CSRC):
         out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h"))]
     out.append(os.path.join(os.path.dirname(HERE), "include", "nirrt_b200.h"))
+    out.append(os.path.join(os.path.dirname(HERE), "include", "nirrt_pointnet2.h"))
     return out
 
 

@@ -33,8 +33,10 @@ using namespace nirrt;
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
+#include "errors.h"
 static thread_local std::string g_err;
-static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+int nirrt_set_error(int code, const std::string &msg) { g_err = msg; return code; }
+static int fail(int code, const std::string &msg) { return nirrt_set_error(code, msg); }
 #define CUDA_TRY(expr)                                                                                \
     do {                                                                                              \
         cudaError_t _e = (expr);                                                                      \

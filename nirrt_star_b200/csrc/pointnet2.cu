@@ -1,0 +1,824 @@
+// pointnet2.cu -- PointNet++ (MSG semantic segmentation) guidance-state inference for batches of
+// point clouds on sm_100a, and the C ABI over it (include/nirrt_pointnet2.h).
+//
+// Stages of one forward (reference: pointnet_pointnet2/models/pointnet2.py:24-42):
+//   k_prep         pc_normalize + [xyz, start, goal, free] feature build   (pointnet2_wrapper.py:46-59)
+//   per SA level:  k_fps          farthest point sampling, 1 CTA / cloud    (pointnet2_utils.py:65-86)
+//                  k_ball_query   both radii, 1 warp / centroid             (pointnet2_utils.py:89-109)
+//                  k_group*       gather neighbours -> fp16 GEMM operand    (pointnet2_utils.py:246-253)
+//                  umma::k_gemm   3 x (conv1x1 + BN + ReLU) on tcgen05, max over K fused into the last
+//   per FP level:  k_interp       3-NN inverse-distance interpolation + skip concat (:298-311)
+//                  umma::k_gemm   conv1d + BN + ReLU chain
+//   head:          umma::k_gemm (conv1+bn1+relu), k_head (conv2, log_softmax, argmax, softmax[:,1])
+//
+// Everything between the input cloud and the per-point outputs stays in HBM/L2; activations and
+// weights are fp16 (K-major rows), accumulation fp32 in TMEM, coordinates enter the first
+// convolution of each SA level as an fp16 hi+lo pair so that no position information is lost.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nirrt_b200.h"
+#include "../../include/nirrt_pointnet2.h"
+#include "errors.h"
+#include "umma_gemm.cuh"
+
+static int pfail(int code, const std::string &msg) { return nirrt_set_error(code, msg); }
+#define PCUDA(expr)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return pfail(NIRRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+#define PTRY(expr) do { int _r = (expr); if (_r) return _r; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// k_prep: pc_normalize (pointnet2_utils.py:13-18) in numpy's float32 operation order -- column sums
+// accumulate row by row (np.mean over axis 0), norm = sqrt((x*x + y*y) + z*z), divide by the max --
+// and the 6-channel network input [x, y, z, start, goal, free] (pointnet2_wrapper.py:51-59).
+__global__ void __launch_bounds__(256) k_prep(const float *pc, int dim, const float *sm, const float *gm, int N,
+                                              float *xyz0, float *in6) {
+    const int b = blockIdx.x;
+    const float *P = pc + (size_t)b * N * dim;
+    __shared__ float s_c[3];
+    __shared__ float s_red[8];
+    if (threadIdx.x < 3) {
+        float s = 0.f;
+        if ((int)threadIdx.x < dim)
+            for (int i = 0; i < N; i++) s = __fadd_rn(s, P[(size_t)i * dim + threadIdx.x]);
+        s_c[threadIdx.x] = __fdiv_rn(s, (float)N);
+    }
+    __syncthreads();
+    const float cx = s_c[0], cy = s_c[1], cz = s_c[2];
+    float mx = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float x = __fsub_rn(P[(size_t)i * dim], cx), y = __fsub_rn(P[(size_t)i * dim + 1], cy);
+        const float z = dim > 2 ? __fsub_rn(P[(size_t)i * dim + 2], cz) : 0.f;
+        const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+        mx = fmaxf(mx, __fsqrt_rn(n2));
+    }
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = s_red[0];
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, s_red[w]);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float x = __fdiv_rn(__fsub_rn(P[(size_t)i * dim], cx), mx);
+        const float y = __fdiv_rn(__fsub_rn(P[(size_t)i * dim + 1], cy), mx);
+        const float z = dim > 2 ? __fdiv_rn(__fsub_rn(P[(size_t)i * dim + 2], cz), mx) : __fdiv_rn(0.f, mx);
+        const size_t o = (size_t)b * N + i;
+        xyz0[o * 3] = x; xyz0[o * 3 + 1] = y; xyz0[o * 3 + 2] = z;
+        const float s = sm[o], g = gm[o];
+        float *f = in6 + o * 6;
+        f[0] = x; f[1] = y; f[2] = z; f[3] = s; f[4] = g;
+        f[5] = (__fadd_rn(s, g) != 0.f) ? 0.f : 1.f;      // 1 - (start+goal).astype(bool)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fps: farthest_point_sample (pointnet2_utils.py:65-86).  One CTA per cloud, the cloud's running
+// min-distance lives in registers (PPT points per thread), one barrier per selected point.
+// dist = (dx*dx + dy*dy) + dz*dz in fp32 without contraction; argmax ties -> lowest index.
+template <int PPT>
+__global__ void __launch_bounds__(256) k_fps(const float *xyz, int N, int npoint, const int *start, int level,
+                                             int *fidx, float *new_xyz) {
+    extern __shared__ float s_xyz[];          // [N][3]
+    __shared__ float s_d[2][8];
+    __shared__ int s_i[2][8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *X = xyz + (size_t)b * N * 3;
+    for (int i = tid; i < N * 3; i += 256) s_xyz[i] = X[i];
+    __syncthreads();
+    float px[PPT], py[PPT], pz[PPT], dist[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        const int i = tid + j * 256;
+        const bool in = i < N;
+        px[j] = in ? s_xyz[i * 3] : 0.f; py[j] = in ? s_xyz[i * 3 + 1] : 0.f; pz[j] = in ? s_xyz[i * 3 + 2] : 0.f;
+        dist[j] = in ? 1e10f : -1.f;           // padding lanes can never win the argmax
+    }
+    int far = start[b * 4 + level];
+    for (int it = 0; it < npoint; it++) {
+        const float cx = s_xyz[far * 3], cy = s_xyz[far * 3 + 1], cz = s_xyz[far * 3 + 2];
+        if (tid == 0) {
+            fidx[(size_t)b * npoint + it] = far;
+            float *o = new_xyz + ((size_t)b * npoint + it) * 3;
+            o[0] = cx; o[1] = cy; o[2] = cz;
+        }
+        float bd = -2.f; int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < PPT; j++) {
+            const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(py[j], cy), dz = __fsub_rn(pz[j], cz);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d < dist[j]) dist[j] = d;
+            if (dist[j] > bd) { bd = dist[j]; bi = tid + j * 256; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        const int slot = it & 1;
+        if (lane == 0) { s_d[slot][warp] = bd; s_i[slot][warp] = bi; }
+        __syncthreads();
+        bd = s_d[slot][0]; bi = s_i[slot][0];
+#pragma unroll
+        for (int w = 1; w < 8; w++) {
+            const float od = s_d[slot][w]; const int oi = s_i[slot][w];
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        far = bi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_ball_query: query_ball_point (pointnet2_utils.py:89-109) for both radii of an SA level.
+// One warp per centroid scans the cloud in index order (32 points per step, ballot + prefix
+// popcount), keeps the first K members of each ball and pads with the first member.  Distances use
+// the reference's expansion -2*a.b + |a|^2 + |b|^2 (square_distance, :39-41).
+__global__ void __launch_bounds__(256) k_ball_query(const float *xyz, int N, const float *new_xyz, int S,
+                                                    float r0sq, int K0, float r1sq, int K1, int *g0, int *g1) {
+    extern __shared__ float s_pts[];          // x[N] y[N] z[N] sq[N]
+    float *sx = s_pts, *sy = sx + N, *sz = sy + N, *sq = sz + N;
+    const int b = blockIdx.y;
+    const float *X = xyz + (size_t)b * N * 3;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float x = X[i * 3], y = X[i * 3 + 1], z = X[i * 3 + 2];
+        sx[i] = x; sy[i] = y; sz[i] = z;
+        sq[i] = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= S) return;
+    const float *c = new_xyz + ((size_t)b * S + s) * 3;
+    const float cx = c[0], cy = c[1], cz = c[2];
+    const float cs = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
+    int *o0 = g0 + ((size_t)b * S + s) * K0, *o1 = g1 + ((size_t)b * S + s) * K1;
+    int cnt0 = 0, cnt1 = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < N && (cnt0 < K0 || cnt1 < K1); base += 32) {
+        const int i = base + lane;
+        bool m0 = false, m1 = false;
+        if (i < N) {
+            const float dot = __fmaf_rn(cz, sz[i], __fmaf_rn(cy, sy[i], __fmul_rn(cx, sx[i])));
+            float d = __fmul_rn(-2.f, dot);
+            d = __fadd_rn(d, cs);
+            d = __fadd_rn(d, sq[i]);
+            m0 = !(d > r0sq); m1 = !(d > r1sq);
+        }
+        const unsigned b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
+        if (m0) { const int pos = cnt0 + __popc(b0 & lt); if (pos < K0) o0[pos] = i; }
+        if (m1) { const int pos = cnt1 + __popc(b1 & lt); if (pos < K1) o1[pos] = i; }
+        cnt0 += __popc(b0); cnt1 += __popc(b1);
+    }
+    __syncwarp();
+    // pad with the first member (group_first); an empty ball cannot occur: the centroid is a member
+    if (cnt0 < K0) { const int f = cnt0 > 0 ? o0[0] : 0; for (int p = cnt0 + lane; p < K0; p += 32) o0[p] = f; }
+    if (cnt1 < K1) { const int f = cnt1 > 0 ? o1[0] : 0; for (int p = cnt1 + lane; p < K1; p += 32) o1[p] = f; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// grouping (pointnet2_utils.py:246-253): rows of the first convolution's operand,
+// [features of neighbour, xyz(neighbour) - xyz(centroid)], features first.  Coordinates are
+// written as an fp16 hi part plus an fp16 lo (residual) part; the weight matrix repeats the
+// corresponding columns, so the tensor cores see coordinates with ~22 significant bits.
+__device__ __forceinline__ void split_half(float x, __half &hi, __half &lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(__fsub_rn(x, __half2float(hi)));
+}
+
+// sa1: in6 f32 [B][N][6] -> rows of 16 halves:
+//   [x y z start goal free | rx ry rz | x_lo y_lo z_lo | rx_lo ry_lo rz_lo | 0]
+__global__ void __launch_bounds__(256) k_group_sa1(const float *in6, const float *xyz, int N, const float *new_xyz, int S,
+                                                   const int *gidx, int K, int B, __half *out) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * S * K;
+    if (r >= total) return;
+    const size_t bs = r / K;
+    const int b = (int)(bs / S);
+    const int i = gidx[r];
+    const float *f = in6 + ((size_t)b * N + i) * 6;
+    const float *c = new_xyz + bs * 3;
+    __half h[16];
+    __half lo;
+    float v[9];
+    for (int k = 0; k < 6; k++) v[k] = f[k];
+    for (int k = 0; k < 3; k++) v[6 + k] = __fsub_rn(f[k], c[k]);
+    for (int k = 0; k < 3; k++) { split_half(v[k], h[k], lo); h[9 + k] = lo; }
+    for (int k = 3; k < 6; k++) h[k] = __float2half_rn(v[k]);
+    for (int k = 6; k < 9; k++) { split_half(v[k], h[k], lo); h[6 + k] = lo; }
+    h[15] = __float2half_rn(0.f);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + r * 16);
+    dst[0] = *reinterpret_cast<uint4 *>(h);
+    dst[1] = *reinterpret_cast<uint4 *>(h + 8);
+}
+
+// sa2..sa4: feat fp16 [B][N][C] (C % 8 == 0) -> rows of Kpad halves:
+//   [feat(C) | rx ry rz | rx_lo ry_lo rz_lo | 0...]; one thread per 16-byte chunk
+__global__ void __launch_bounds__(256) k_group(const __half *feat, int C, const float *xyz, int N, const float *new_xyz,
+                                               int S, const int *gidx, int K, int B, int Kpad, __half *out) {
+    const int CH = Kpad >> 3, FC = C >> 3;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * S * K * CH;
+    if (t >= total) return;
+    const size_t r = t / CH;
+    const int ch = (int)(t - r * CH);
+    const size_t bs = r / K;
+    const int b = (int)(bs / S);
+    const int i = gidx[r];
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ch < FC) {
+        val = *reinterpret_cast<const uint4 *>(feat + ((size_t)b * N + i) * C + ch * 8);
+    } else if (ch == FC) {
+        const float *p = xyz + ((size_t)b * N + i) * 3;
+        const float *c = new_xyz + bs * 3;
+        __half h[8];
+        for (int k = 0; k < 3; k++) split_half(__fsub_rn(p[k], c[k]), h[k], h[3 + k]);
+        h[6] = h[7] = __float2half_rn(0.f);
+        val = *reinterpret_cast<uint4 *>(h);
+    }
+    *reinterpret_cast<uint4 *>(out + r * Kpad + ch * 8) = val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_interp: PointNetFeaturePropagation's interpolation (pointnet2_utils.py:298-311): the three
+// nearest of the S coarse points by expansion distance, weights 1/(d+1e-8) normalised, weighted sum
+// of their features, concatenated after the skip features: row = [points1(C1) | interpolated(C2)].
+// One warp per fine point.
+struct Top3 { float d[3]; int i[3]; };
+__device__ __forceinline__ void top3_insert(Top3 &t, float d, int i) {
+    if (d < t.d[2]) {
+        if (d < t.d[1]) {
+            t.d[2] = t.d[1]; t.i[2] = t.i[1];
+            if (d < t.d[0]) { t.d[1] = t.d[0]; t.i[1] = t.i[0]; t.d[0] = d; t.i[0] = i; }
+            else { t.d[1] = d; t.i[1] = i; }
+        } else { t.d[2] = d; t.i[2] = i; }
+    }
+}
+__global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const float *xyz2, int S, const __half *feat1, int C1,
+                                                const __half *feat2, int C2, int B, __half *out) {
+    const int lane = threadIdx.x & 31;
+    const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (p >= (size_t)B * N) return;
+    const int b = (int)(p / N);
+    const float *a = xyz1 + p * 3;
+    const float ax = a[0], ay = a[1], az = a[2];
+    const float as = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+    const float *Q = xyz2 + (size_t)b * S * 3;
+    Top3 t;
+    t.d[0] = t.d[1] = t.d[2] = INFINITY; t.i[0] = t.i[1] = t.i[2] = 0x7fffffff;
+    for (int s = lane; s < S; s += 32) {
+        const float qx = Q[s * 3], qy = Q[s * 3 + 1], qz = Q[s * 3 + 2];
+        const float qs = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz));
+        const float dot = __fmaf_rn(az, qz, __fmaf_rn(ay, qy, __fmul_rn(ax, qx)));
+        float d = __fmul_rn(-2.f, dot);
+        d = __fadd_rn(d, as);
+        d = __fadd_rn(d, qs);
+        top3_insert(t, d, s);
+    }
+    float nd[3]; int ni[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float bd = t.d[0]; int bi = t.i[0];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        nd[r] = bd; ni[r] = bi;
+        if (t.i[0] == bi) { t.d[0] = t.d[1]; t.i[0] = t.i[1]; t.d[1] = t.d[2]; t.i[1] = t.i[2]; t.d[2] = INFINITY; t.i[2] = 0x7fffffff; }
+    }
+    const float r0 = __fdiv_rn(1.f, __fadd_rn(nd[0], 1e-8f)), r1 = __fdiv_rn(1.f, __fadd_rn(nd[1], 1e-8f)),
+                r2 = __fdiv_rn(1.f, __fadd_rn(nd[2], 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+    __half *o = out + p * (size_t)(C1 + C2);
+    if (C1 > 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(feat1 + p * (size_t)C1);
+        uint4 *dst = reinterpret_cast<uint4 *>(o);
+        for (int k = lane; k < (C1 >> 3); k += 32) dst[k] = src[k];
+    }
+    const __half2 *f0 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + ni[0]) * C2);
+    const __half2 *f1 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + ni[1]) * C2);
+    const __half2 *f2 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + ni[2]) * C2);
+    __half2 *oi = reinterpret_cast<__half2 *>(o + C1);
+    for (int k = lane; k < (C2 >> 1); k += 32) {
+        const float2 a0 = __half22float2(f0[k]), a1 = __half22float2(f1[k]), a2 = __half22float2(f2[k]);
+        const float x = __fadd_rn(__fadd_rn(__fmul_rn(a0.x, w0), __fmul_rn(a1.x, w1)), __fmul_rn(a2.x, w2));
+        const float y = __fadd_rn(__fadd_rn(__fmul_rn(a0.y, w0), __fmul_rn(a1.y, w1)), __fmul_rn(a2.y, w2));
+        oi[k] = __floats2half2_rn(fminf(x, 65504.f), fminf(y, 65504.f));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_head: conv2 (128 -> 2) + log_softmax + argmax + softmax[:,1] (pointnet2.py:39-41,
+// pointnet2_wrapper.py:61-62).  fp32 weights; one thread per point.
+__global__ void __launch_bounds__(128) k_head(const __half *x, const float *w2, const float *b2, size_t total,
+                                              long long *pred, float *score, float *logp) {
+    __shared__ float s_w[2 * 128 + 2];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_w[i] = w2[i];
+    if (threadIdx.x < 2) s_w[256 + threadIdx.x] = b2[threadIdx.x];
+    __syncthreads();
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const uint4 *row = reinterpret_cast<const uint4 *>(x + p * 128);
+    float z0 = 0.f, z1 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 16; k++) {
+        const uint4 v = row[k];
+        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 f = __half22float2(h[j]);
+            const int c = k * 8 + j * 2;
+            z0 = fmaf(f.x, s_w[c], z0); z0 = fmaf(f.y, s_w[c + 1], z0);
+            z1 = fmaf(f.x, s_w[128 + c], z1); z1 = fmaf(f.y, s_w[128 + c + 1], z1);
+        }
+    }
+    z0 += s_w[256]; z1 += s_w[257];
+    const float m = fmaxf(z0, z1);
+    const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
+    const float l0 = z0 - lse, l1 = z1 - lse;
+    if (logp) { logp[p * 2] = l0; logp[p * 2 + 1] = l1; }
+    pred[p] = (l1 > l0) ? 1 : 0;                      // np.argmax: first maximum
+    const float e0 = expf(l0), e1 = expf(l1);
+    score[p] = e1 / (e0 + e1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int load_encode() {
+    if (g_encode) return NIRRT_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+        return pfail(NIRRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    g_encode = (PFN_encodeTiled)fn;
+    return NIRRT_OK;
+}
+
+// tensor map of a row-major fp16 matrix [rows][cols] with a {64, box_rows} box and 128-byte swizzle
+static int make_tmap(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    PTRY(load_encode());
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)umma::kBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return pfail(NIRRT_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return NIRRT_OK;
+}
+
+static bool g_gemm_attr = false;
+static int gemm_attr() {
+    if (g_gemm_attr) return NIRRT_OK;
+    PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCUDA(cudaFuncSetAttribute(k_ball_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    g_gemm_attr = true;
+    return NIRRT_OK;
+}
+
+static int pick_bn(int N) { return N <= 256 ? N : N / 2; }
+
+struct Conv {
+    int K = 0, N = 0, BN = 0;      // padded dims (multiples of 16)
+    __half *w = nullptr;           // [N][K]
+    float *b = nullptr;            // [N]
+    CUtensorMap tmW;
+};
+
+static int launch_gemm(const Conv &c, const __half *A, int M, int mode, __half *out, int ldo, int col_off, int group,
+                       cudaStream_t s) {
+    PTRY(gemm_attr());
+    CUtensorMap tmA;
+    PTRY(make_tmap(&tmA, A, (uint64_t)M, (uint64_t)c.K, umma::kBM));
+    umma::GemmArgs g;
+    g.M = M; g.N = c.N; g.K = c.K; g.BN = c.BN;
+    const int nkb = (c.K + umma::kBK - 1) / umma::kBK;
+    g.stages = nkb < umma::kMaxStages ? nkb : umma::kMaxStages;
+    g.ldo = ldo; g.col_off = col_off; g.group = group; g.bias = c.b; g.out = out;
+    const umma::SmemLayout L = umma::smem_layout(g.BN, g.stages);
+    const dim3 grid((M + umma::kBM - 1) / umma::kBM, (c.N + c.BN - 1) / c.BN);
+    const size_t smem = (size_t)L.total + 1024;
+    if (mode == umma::MODE_STORE) umma::k_gemm<umma::MODE_STORE><<<grid, umma::kThreads, smem, s>>>(tmA, c.tmW, g);
+    else umma::k_gemm<umma::MODE_POOL><<<grid, umma::kThreads, smem, s>>>(tmA, c.tmW, g);
+    PCUDA(cudaGetLastError());
+    return NIRRT_OK;
+}
+
+static const int kNp[5] = {0, 1024, 256, 64, 16};            // npoint of sa1..sa4 (pointnet2.py:11-14)
+static const int kC[5] = {6, 96, 256, 512, 1024};            // channels of l0..l4 features
+static const double kRad[4][2] = {{0.05, 0.1}, {0.1, 0.2}, {0.2, 0.4}, {0.4, 0.8}};
+static const int kK[2] = {16, 32};
+static const int kUpC[4] = {256, 256, 128, 128};             // outputs of fp4, fp3, fp2, fp1
+
+struct nirrt_pn2 {
+    int N0 = 0, maxB = 0, device = 0;
+    int n[5];
+    Conv conv[34];
+    float *w2 = nullptr, *b2 = nullptr;
+    float *xyz[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *in6 = nullptr;
+    __half *feat[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int *fidx[4] = {nullptr, nullptr, nullptr, nullptr};
+    int *grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    __half *bufA = nullptr, *bufB = nullptr;
+    __half *up[4] = {nullptr, nullptr, nullptr, nullptr};     // outputs of fp4 (level 3) .. fp1 (level 0)
+    // staging for the host-pointer entry point
+    float *d_pc = nullptr, *d_sm = nullptr, *d_gm = nullptr, *d_score = nullptr, *d_logp = nullptr;
+    int *d_fps = nullptr;
+    long long *d_pred = nullptr;
+    std::vector<void *> allocs;
+    int lastB = 0;
+    int64_t launches = 0;
+    bool profiling = false;
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+template <typename T>
+static int palloc(nirrt_pn2 *h, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
+    if (e != cudaSuccess) return pfail(NIRRT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return NIRRT_OK;
+}
+
+static int round16(int x) { return (x + 15) & ~15; }
+
+// folds BatchNorm into the convolution, remaps/pads the input channels and uploads fp16 rows
+//   remap: for each padded input column k the source column (or -1 for zero)
+static int upload_conv(nirrt_pn2 *h, Conv &c, const nirrt_pn2_layer &L, const std::vector<int> &remap) {
+    c.K = (int)remap.size();
+    c.N = round16(L.c_out);
+    c.BN = pick_bn(c.N);
+    std::vector<__half> w((size_t)c.N * c.K, __float2half(0.f));
+    std::vector<float> b((size_t)c.N, 0.f);
+    for (int n = 0; n < L.c_out; n++) {
+        float s = 1.f, shift = L.bias[n];
+        if (L.bn_weight) {
+            s = L.bn_weight[n] / sqrtf(L.bn_var[n] + 1e-5f);
+            shift = (L.bias[n] - L.bn_mean[n]) * s + L.bn_bias[n];
+        }
+        b[n] = shift;
+        for (int k = 0; k < c.K; k++)
+            if (remap[k] >= 0) w[(size_t)n * c.K + k] = __float2half_rn(L.weight[(size_t)n * L.c_in + remap[k]] * s);
+    }
+    PTRY(palloc(h, &c.w, w.size()));
+    PTRY(palloc(h, &c.b, b.size()));
+    PCUDA(cudaMemcpy(c.w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    PCUDA(cudaMemcpy(c.b, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+    PTRY(make_tmap(&c.tmW, c.w, (uint64_t)c.N, (uint64_t)c.K, (uint32_t)c.BN));
+    return NIRRT_OK;
+}
+
+static std::vector<int> identity_remap(int c_in) {
+    std::vector<int> r(round16(c_in), -1);
+    for (int k = 0; k < c_in; k++) r[k] = k;
+    return r;
+}
+
+extern "C" int nirrt_pn2_destroy(nirrt_pn2 *h) {
+    if (!h) return NIRRT_OK;
+    cudaSetDevice(h->device);
+    for (void *p : h->allocs) cudaFree(p);
+    for (int i = 0; i < 2; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int n_points, int max_batch, int device,
+                                nirrt_pn2 **out) {
+    if (!layers || !out) return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_create: null argument");
+    if (n_layers != NIRRT_PN2_NUM_LAYERS) return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_create: expected 35 layers");
+    if (n_points < 1024 || n_points > 4096) return pfail(NIRRT_ERR_INVALID, "n_points must be in [1024, 4096] (sa1 samples 1024 points)");
+    if (max_batch < 1) return pfail(NIRRT_ERR_INVALID, "max_batch >= 1 required");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pfail(NIRRT_ERR_NO_DEVICE, "no CUDA device visible");
+    if (device < 0 || device >= ndev) return pfail(NIRRT_ERR_INVALID, "bad device ordinal");
+    cudaDeviceProp prop;
+    PCUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return pfail(NIRRT_ERR_NO_DEVICE, "libnirrt_b200 is built for sm_100a only");
+    PCUDA(cudaSetDevice(device));
+    // expected channel plan
+    static const int sa_mlp[4][2][3] = {{{16, 16, 32}, {32, 32, 64}}, {{64, 64, 128}, {64, 96, 128}},
+                                        {{128, 196, 256}, {128, 196, 256}}, {{256, 256, 512}, {256, 384, 512}}};
+    nirrt_pn2 *h = new nirrt_pn2();
+    h->N0 = n_points; h->maxB = max_batch; h->device = device;
+    h->n[0] = n_points;
+    for (int l = 1; l <= 4; l++) h->n[l] = kNp[l];
+#define FAILC(msg) do { nirrt_pn2_destroy(h); return pfail(NIRRT_ERR_INVALID, msg); } while (0)
+#define TRYC(expr) do { int _r = (expr); if (_r) { nirrt_pn2_destroy(h); return _r; } } while (0)
+    int li = 0;
+    for (int l = 1; l <= 4; l++)
+        for (int sc = 0; sc < 2; sc++) {
+            int last = kC[l - 1] + 3;
+            for (int j = 0; j < 3; j++, li++) {
+                const nirrt_pn2_layer &L = layers[li];
+                if (L.c_in != last || L.c_out != sa_mlp[l - 1][sc][j] || !L.weight || !L.bias || !L.bn_weight || !L.bn_bias || !L.bn_mean || !L.bn_var)
+                    FAILC("nirrt_pn2_create: SA layer " + std::to_string(li) + " has unexpected shape");
+                std::vector<int> remap;
+                if (j == 0) {
+                    const int C = kC[l - 1];
+                    if (l == 1) {
+                        remap.assign(16, -1);
+                        for (int k = 0; k < 9; k++) remap[k] = k;
+                        for (int k = 0; k < 3; k++) { remap[9 + k] = k; remap[12 + k] = 6 + k; }
+                    } else {
+                        remap.assign(round16(C + 6), -1);
+                        for (int k = 0; k < C + 3; k++) remap[k] = k;
+                        for (int k = 0; k < 3; k++) remap[C + 3 + k] = C + k;
+                    }
+                } else remap = identity_remap(last);
+                TRYC(upload_conv(h, h->conv[li], L, remap));
+                last = L.c_out;
+            }
+        }
+    static const int fp_in[4] = {1536, 512, 352, 128};
+    static const int fp_mlp[4][3] = {{256, 256, 0}, {256, 256, 0}, {256, 128, 0}, {128, 128, 128}};
+    for (int f = 0; f < 4; f++) {
+        int last = fp_in[f];
+        for (int j = 0; j < 3 && fp_mlp[f][j]; j++, li++) {
+            const nirrt_pn2_layer &L = layers[li];
+            if (L.c_in != last || L.c_out != fp_mlp[f][j] || !L.weight || !L.bias || !L.bn_weight)
+                FAILC("nirrt_pn2_create: FP layer " + std::to_string(li) + " has unexpected shape");
+            TRYC(upload_conv(h, h->conv[li], L, identity_remap(last)));
+            last = L.c_out;
+        }
+    }
+    if (layers[33].c_in != 128 || layers[33].c_out != 128 || !layers[33].bn_weight) FAILC("nirrt_pn2_create: conv1 has unexpected shape");
+    TRYC(upload_conv(h, h->conv[33], layers[33], identity_remap(128)));
+    if (layers[34].c_in != 128 || layers[34].c_out != 2) FAILC("nirrt_pn2_create: conv2 must be 128 -> 2 (num_classes = 2)");
+    TRYC(palloc(h, &h->w2, 256)); TRYC(palloc(h, &h->b2, 2));
+    if (cudaMemcpy(h->w2, layers[34].weight, 256 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->b2, layers[34].bias, 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        FAILC("nirrt_pn2_create: weight upload failed");
+    // activations
+    const size_t B = (size_t)max_batch;
+    for (int l = 0; l <= 4; l++) TRYC(palloc(h, &h->xyz[l], B * h->n[l] * 3));
+    TRYC(palloc(h, &h->in6, B * h->N0 * 6));
+    for (int l = 1; l <= 4; l++) {
+        TRYC(palloc(h, &h->feat[l], B * h->n[l] * kC[l]));
+        TRYC(palloc(h, &h->fidx[l - 1], B * h->n[l]));
+        for (int sc = 0; sc < 2; sc++) TRYC(palloc(h, &h->grp[(l - 1) * 2 + sc], B * h->n[l] * kK[sc]));
+    }
+    size_t per_cloud = 1024 * 32 * 32;                     // sa1 scale 1: 32768 rows x 32 channels
+    const size_t cand[] = {(size_t)256 * 32 * 112, (size_t)64 * 32 * 272, (size_t)16 * 32 * 528, (size_t)64 * 1536,
+                           (size_t)256 * 512, (size_t)1024 * 352, (size_t)h->N0 * 128};
+    for (size_t c : cand) if (c > per_cloud) per_cloud = c;
+    TRYC(palloc(h, &h->bufA, B * per_cloud + 4096));
+    TRYC(palloc(h, &h->bufB, B * per_cloud + 4096));
+    for (int f = 0; f < 4; f++) TRYC(palloc(h, &h->up[f], B * h->n[3 - f] * kUpC[f]));
+    TRYC(palloc(h, &h->d_pc, B * h->N0 * 3)); TRYC(palloc(h, &h->d_sm, B * h->N0)); TRYC(palloc(h, &h->d_gm, B * h->N0));
+    TRYC(palloc(h, &h->d_fps, B * 4)); TRYC(palloc(h, &h->d_pred, B * h->N0)); TRYC(palloc(h, &h->d_score, B * h->N0));
+    TRYC(palloc(h, &h->d_logp, B * h->N0 * 2));
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreate(&h->ev[i]) != cudaSuccess) FAILC("cudaEventCreate failed");
+    if (gemm_attr()) { nirrt_pn2_destroy(h); return NIRRT_ERR_CUDA; }
+#undef FAILC
+#undef TRYC
+    *out = h;
+    return NIRRT_OK;
+}
+
+struct StageTimer {
+    nirrt_pn2 *h; cudaStream_t s; int stage;
+    StageTimer(nirrt_pn2 *h_, cudaStream_t s_, int st) : h(h_), s(s_), stage(st) { if (h->profiling) cudaEventRecord(h->ev[0], s); }
+    ~StageTimer() {
+        if (!h->profiling) return;
+        cudaEventRecord(h->ev[1], s);
+        cudaEventSynchronize(h->ev[1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+        h->stage_ms[stage] += ms;
+    }
+};
+
+static int fps_launch(nirrt_pn2 *h, int B, int l, const int *start, cudaStream_t s) {
+    const int N = h->n[l - 1], np = h->n[l];
+    const size_t smem = (size_t)N * 3 * sizeof(float);
+    const int ppt = (N + 255) / 256;
+    if (ppt <= 1) k_fps<1><<<B, 256, smem, s>>>(h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]);
+    else if (ppt <= 4) k_fps<4><<<B, 256, smem, s>>>(h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]);
+    else if (ppt <= 8) k_fps<8><<<B, 256, smem, s>>>(h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]);
+    else k_fps<16><<<B, 256, smem, s>>>(h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]);
+    PCUDA(cudaGetLastError());
+    h->launches++;
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const float *pc, const float *start_mask,
+                                         const float *goal_mask, const int32_t *fps_start, int64_t *path_pred,
+                                         float *path_score, float *logp, void *stream) {
+    if (!h || !pc || !start_mask || !goal_mask || !fps_start || !path_pred || !path_score)
+        return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_classify_device: null argument");
+    if (batch < 1 || batch > h->maxB) return pfail(NIRRT_ERR_INVALID, "batch out of range (1..max_batch)");
+    if (dim != 2 && dim != 3) return pfail(NIRRT_ERR_INVALID, "dim must be 2 or 3");
+    PCUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = batch;
+    h->lastB = B;
+    if (h->profiling) for (int i = 0; i < 8; i++) h->stage_ms[i] = 0.f;
+    {
+        StageTimer t(h, s, 0);
+        k_prep<<<B, 256, 0, s>>>(pc, dim, start_mask, goal_mask, h->N0, h->xyz[0], h->in6);
+        PCUDA(cudaGetLastError());
+        h->launches++;
+    }
+    int li = 0;
+    for (int l = 1; l <= 4; l++) {
+        const int N = h->n[l - 1], S = h->n[l];
+        { StageTimer t(h, s, 1); PTRY(fps_launch(h, B, l, fps_start, s)); }
+        {
+            StageTimer t(h, s, 2);
+            const float r0 = (float)(kRad[l - 1][0] * kRad[l - 1][0]), r1 = (float)(kRad[l - 1][1] * kRad[l - 1][1]);
+            k_ball_query<<<dim3((S + 7) / 8, B), 256, (size_t)N * 4 * sizeof(float), s>>>(
+                h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
+            PCUDA(cudaGetLastError());
+            h->launches++;
+        }
+        for (int sc = 0; sc < 2; sc++) {
+            const int K = kK[sc];
+            const int rows = B * S * K;
+            const Conv &c0 = h->conv[li], &c1 = h->conv[li + 1], &c2 = h->conv[li + 2];
+            {
+                StageTimer t(h, s, 3);
+                if (l == 1) {
+                    k_group_sa1<<<(rows + 255) / 256, 256, 0, s>>>(h->in6, h->xyz[0], N, h->xyz[1], S, h->grp[sc], K, B, h->bufA);
+                } else {
+                    const size_t total = (size_t)rows * (c0.K >> 3);
+                    k_group<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->feat[l - 1], kC[l - 1], h->xyz[l - 1], N, h->xyz[l], S,
+                                                                            h->grp[(l - 1) * 2 + sc], K, B, c0.K, h->bufA);
+                }
+                PCUDA(cudaGetLastError());
+                h->launches++;
+            }
+            {
+                StageTimer t(h, s, 4);
+                PTRY(launch_gemm(c0, h->bufA, rows, umma::MODE_STORE, h->bufB, c0.N, 0, 0, s));
+                PTRY(launch_gemm(c1, h->bufB, rows, umma::MODE_STORE, h->bufA, c1.N, 0, 0, s));
+                // scale 0 channels first, then scale 1 (torch.cat(new_points_list, dim=1)); the last
+                // layer widths (32|64, 128|128, 256|256, 512|512) need no padding
+                const int off = sc == 0 ? 0 : h->conv[li - 1].N;
+                PTRY(launch_gemm(c2, h->bufA, rows, umma::MODE_POOL, h->feat[l], kC[l], off, K, s));
+                h->launches += 3;
+            }
+            li += 3;
+        }
+    }
+    // feature propagation: fp4 (l3 <- l4), fp3, fp2, fp1 (l0 <- l1, no skip features)
+    const __half *upf = h->feat[4];
+    int upC = kC[4];
+    for (int f = 0; f < 4; f++) {
+        const int lo = 3 - f;
+        const int N = h->n[lo], S = h->n[lo + 1];
+        const int C1 = lo == 0 ? 0 : kC[lo];
+        const int rows = B * N;
+        {
+            StageTimer t(h, s, 5);
+            k_interp<<<(rows + 7) / 8, 256, 0, s>>>(h->xyz[lo], N, h->xyz[lo + 1], S, C1 ? h->feat[lo] : nullptr, C1, upf, upC, B, h->bufA);
+            PCUDA(cudaGetLastError());
+            h->launches++;
+        }
+        {
+            StageTimer t(h, s, 6);
+            const int nl = f == 3 ? 3 : 2;
+            const __half *in = h->bufA;
+            __half *pp[2] = {h->bufB, h->bufA};
+            for (int j = 0; j < nl; j++, li++) {
+                const Conv &c = h->conv[li];
+                __half *o = (j == nl - 1) ? h->up[f] : pp[j & 1];
+                PTRY(launch_gemm(c, in, rows, umma::MODE_STORE, o, c.N, 0, 0, s));
+                h->launches++;
+                in = o;
+            }
+        }
+        upf = h->up[f];
+        upC = kUpC[f];
+    }
+    {
+        StageTimer t(h, s, 6);
+        PTRY(launch_gemm(h->conv[33], h->up[3], B * h->N0, umma::MODE_STORE, h->bufA, 128, 0, 0, s));
+        h->launches++;
+    }
+    {
+        StageTimer t(h, s, 7);
+        const size_t total = (size_t)B * h->N0;
+        k_head<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(h->bufA, h->w2, h->b2, total, (long long *)path_pred, path_score, logp);
+        PCUDA(cudaGetLastError());
+        h->launches++;
+    }
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_pn2_classify_sync(nirrt_pn2 *h, int batch, int dim, const float *pc, const float *start_mask,
+                                       const float *goal_mask, const int32_t *fps_start, int64_t *path_pred,
+                                       float *path_score, float *logp, void *stream) {
+    if (!h || !pc || !start_mask || !goal_mask || !fps_start || !path_pred || !path_score)
+        return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_classify_sync: null argument");
+    if (batch < 1 || batch > h->maxB) return pfail(NIRRT_ERR_INVALID, "batch out of range (1..max_batch)");
+    if (dim != 2 && dim != 3) return pfail(NIRRT_ERR_INVALID, "dim must be 2 or 3");
+    PCUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t BN = (size_t)batch * h->N0;
+    PCUDA(cudaMemcpyAsync(h->d_pc, pc, BN * dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    PCUDA(cudaMemcpyAsync(h->d_sm, start_mask, BN * sizeof(float), cudaMemcpyHostToDevice, s));
+    PCUDA(cudaMemcpyAsync(h->d_gm, goal_mask, BN * sizeof(float), cudaMemcpyHostToDevice, s));
+    PCUDA(cudaMemcpyAsync(h->d_fps, fps_start, (size_t)batch * 4 * sizeof(int), cudaMemcpyHostToDevice, s));
+    PTRY(nirrt_pn2_classify_device(h, batch, dim, h->d_pc, h->d_sm, h->d_gm, h->d_fps, (int64_t *)h->d_pred, h->d_score,
+                                   h->d_logp, s));
+    PCUDA(cudaMemcpyAsync(path_pred, h->d_pred, BN * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    PCUDA(cudaMemcpyAsync(path_score, h->d_score, BN * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (logp) PCUDA(cudaMemcpyAsync(logp, h->d_logp, BN * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PCUDA(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int64_t nirrt_pn2_read_buffer_sync(nirrt_pn2 *h, const char *name, void *out, int64_t bytes, void *stream) {
+    if (!h || !name) return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_read_buffer_sync: null argument");
+    const size_t B = (size_t)(h->lastB > 0 ? h->lastB : 1);
+    const void *src = nullptr;
+    size_t size = 0;
+    const std::string nm(name);
+    if (nm == "xyz0") { src = h->xyz[0]; size = B * h->N0 * 3 * sizeof(float); }
+    else if (nm.size() == 4 && nm.compare(0, 3, "fps") == 0 && nm[3] >= '0' && nm[3] <= '3') {
+        const int l = nm[3] - '0'; src = h->fidx[l]; size = B * h->n[l + 1] * sizeof(int);
+    } else if (nm.size() == 6 && nm.compare(0, 5, "group") == 0 && nm[5] >= '0' && nm[5] <= '7') {
+        const int g = nm[5] - '0'; src = h->grp[g]; size = B * h->n[g / 2 + 1] * kK[g & 1] * sizeof(int);
+    } else if (nm.size() == 5 && nm.compare(0, 4, "feat") == 0 && nm[4] >= '1' && nm[4] <= '4') {
+        const int l = nm[4] - '0'; src = h->feat[l]; size = B * h->n[l] * kC[l] * sizeof(__half);
+    } else if (nm.size() == 3 && nm.compare(0, 2, "up") == 0 && nm[2] >= '0' && nm[2] <= '3') {
+        const int lo = nm[2] - '0'; const int f = 3 - lo; src = h->up[f]; size = B * h->n[lo] * kUpC[f] * sizeof(__half);
+    } else return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_read_buffer_sync: unknown buffer name");
+    cudaStream_t s = (cudaStream_t)stream;
+    PCUDA(cudaSetDevice(h->device));
+    if (out && bytes > 0) {
+        const size_t m = (size_t)bytes < size ? (size_t)bytes : size;
+        PCUDA(cudaMemcpyAsync(out, src, m, cudaMemcpyDeviceToHost, s));
+        PCUDA(cudaStreamSynchronize(s));
+    }
+    return (int64_t)size;
+}
+
+extern "C" int nirrt_pn2_set_profiling(nirrt_pn2 *h, int enabled) {
+    if (!h) return pfail(NIRRT_ERR_INVALID, "null handle");
+    h->profiling = enabled != 0;
+    return NIRRT_OK;
+}
+extern "C" int nirrt_pn2_last_stage_ms(nirrt_pn2 *h, float *ms8) {
+    if (!h || !ms8) return pfail(NIRRT_ERR_INVALID, "null argument");
+    for (int i = 0; i < 8; i++) ms8[i] = h->stage_ms[i];
+    return NIRRT_OK;
+}
+extern "C" int64_t nirrt_pn2_launch_count(nirrt_pn2 *h) { return h ? h->launches : 0; }
+
+extern "C" int nirrt_gemm_f16_sync(const uint16_t *A, const uint16_t *W, const float *bias, int m, int n, int k, int mode,
+                                   int group, uint16_t *out, void *stream) {
+    if (!A || !W || !bias || !out) return pfail(NIRRT_ERR_INVALID, "nirrt_gemm_f16_sync: null argument");
+    if (m < 1 || n < 16 || k < 16 || (n & 15) || (k & 15)) return pfail(NIRRT_ERR_INVALID, "n and k must be positive multiples of 16");
+    if (mode != 0 && mode != 1) return pfail(NIRRT_ERR_INVALID, "mode must be 0 or 1");
+    if (mode == 1 && ((group != 16 && group != 32) || m % group)) return pfail(NIRRT_ERR_INVALID, "group must be 16 or 32 and divide m");
+    cudaStream_t s = (cudaStream_t)stream;
+    __half *dA = nullptr, *dW = nullptr, *dO = nullptr;
+    float *dB = nullptr;
+    const size_t orow = mode == 0 ? (size_t)m : (size_t)(m / group);
+    int rc = NIRRT_OK;
+    auto cleanup = [&]() { cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dB); };
+#define GT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return pfail(NIRRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+    GT(cudaMalloc(&dA, (size_t)m * k * 2)); GT(cudaMalloc(&dW, (size_t)n * k * 2)); GT(cudaMalloc(&dO, orow * n * 2)); GT(cudaMalloc(&dB, (size_t)n * 4));
+    GT(cudaMemcpyAsync(dA, A, (size_t)m * k * 2, cudaMemcpyHostToDevice, s));
+    GT(cudaMemcpyAsync(dW, W, (size_t)n * k * 2, cudaMemcpyHostToDevice, s));
+    GT(cudaMemcpyAsync(dB, bias, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    GT(cudaMemsetAsync(dO, 0, orow * n * 2, s));
+    Conv c;
+    c.K = k; c.N = n; c.BN = pick_bn(n); c.w = dW; c.b = dB;
+    if (c.BN & 15) c.BN = 256;
+    rc = make_tmap(&c.tmW, dW, (uint64_t)n, (uint64_t)k, (uint32_t)c.BN);
+    if (!rc) rc = launch_gemm(c, dA, m, mode, dO, n, 0, group, s);
+    if (rc) { cleanup(); return rc; }
+    GT(cudaMemcpyAsync(out, dO, orow * n * 2, cudaMemcpyDeviceToHost, s));
+    GT(cudaStreamSynchronize(s));
+#undef GT
+    cleanup();
+    return NIRRT_OK;
+}

@@ -1,0 +1,130 @@
+"""GPU parity tests of the PointNet++ path: CUDA (through the C ABI) vs the torch-fp32 oracle and
+vs fixtures recorded from the reference's own PNGWrapper (tests/golden/pointnet2_*.npz).
+
+Tolerances: FPS indices exact given identical start indices; ball-query groups exact
+outside a |d^2 - r^2| < 4e-6 band; log-probabilities <= 2e-2 abs (fp16 tensor-core operands, fp32
+accumulation); path_pred identical except where |score - 0.5| < 0.05."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from nirrt_star_b200.synthetic import make_cloud_3d, make_pointnet2_state
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pointnet2_*.npz")))
+LOGP_TOL = 2e-2
+RADII = ((0.05, 0.1), (0.1, 0.2), (0.2, 0.4), (0.4, 0.8))
+NP = (2048, 1024, 256, 64, 16)
+CH = (6, 96, 256, 512, 1024)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from nirrt_star_b200.pointnet2 import PointNet2Engine
+    eng = PointNet2Engine(make_pointnet2_state(0), n_points=2048, max_batch=8)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("m,n,k,mode,group", [
+    (128, 16, 16, 0, 16), (128, 32, 64, 0, 16), (256, 64, 112, 0, 16), (384, 208, 272, 0, 16),
+    (100, 128, 128, 0, 16), (512, 256, 528, 0, 16), (256, 384, 256, 0, 16), (256, 512, 384, 0, 16),
+    (256, 32, 16, 1, 16), (256, 64, 32, 1, 32), (512, 512, 256, 1, 32), (2048, 128, 96, 1, 16),
+])
+def test_tensor_core_gemm_matches_fp32(m, n, k, mode, group):
+    from nirrt_star_b200.pointnet2 import gemm_f16
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    A = rng.standard_normal((m, k)).astype(np.float16)
+    W = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float16)
+    bias = rng.standard_normal(n).astype(np.float32) * 0.1
+    got = gemm_f16(A, W, bias, mode, group).astype(np.float32)
+    ref = A.astype(np.float32) @ W.astype(np.float32).T
+    if mode == 0:
+        want = np.maximum(ref + bias, 0)
+    else:
+        want = np.maximum(ref.reshape(m // group, group, n).max(axis=1) + bias, 0)
+    assert got.shape == want.shape
+    err = np.abs(got - want).max()
+    assert err <= 4e-3 * max(1.0, np.abs(want).max()), err      # fp16 output rounding
+
+
+def _ball_band_ok(got, want, sqd, r, K, N):
+    """groups equal, or differ only at members whose expansion distance is within 4e-6 of r^2"""
+    if np.array_equal(got, want):
+        return True
+    r2 = np.float32(r ** 2)
+    for s in np.nonzero((got != want).any(axis=1))[0]:
+        amb = set(np.nonzero(np.abs(sqd[s] - r2) < 4e-6)[0].tolist())
+        if not amb:
+            return False
+        if (set(got[s].tolist()) ^ set(want[s].tolist())) - amb:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_forward_matches_reference_golden(engine, path):
+    from oracle import pointnet2_oracle as O
+    g = np.load(path)
+    pc, sm, gm, fs = g["pc"], g["start_mask"], g["goal_mask"], g["fps_start"]
+    pred, score, logp = engine.classify(pc, sm, gm, fps_start=fs, return_logp=True)
+    # normalisation is bit-exact
+    pc3 = pc if pc.shape[1] == 3 else np.concatenate([pc, np.zeros((len(pc), 1), np.float32)], 1)
+    assert np.array_equal(engine.read_buffer("xyz0", np.float32, (1, 2048, 3))[0], O.pc_normalize(pc3))
+    # FPS: exact
+    for l in range(4):
+        got = engine.read_buffer(f"fps{l}", np.int32, (1, NP[l + 1]))[0]
+        assert np.array_equal(got, g[f"fps{l}"].astype(np.int32)), f"fps level {l}"
+    # ball query: exact outside the rounding band of the expansion distance
+    tr = {}
+    sd = make_pointnet2_state(int(g["ckpt_seed"]))
+    O.classify_path_points(sd, pc, sm, gm, fs, trace=tr)
+    for i in range(8):
+        K = (16, 32)[i & 1]
+        got = engine.read_buffer(f"group{i}", np.int32, (1, NP[i // 2 + 1], K))[0]
+        assert _ball_band_ok(got, g[f"group{i}"].astype(np.int32), tr["sqd"][i][0], RADII[i // 2][i & 1], K, NP[i // 2]), f"group {i}"
+    # network outputs
+    assert np.abs(logp[0] - g["logp"]).max() <= LOGP_TOL, np.abs(logp[0] - g["logp"]).max()
+    assert np.abs(score[0] - g["score"]).max() <= LOGP_TOL
+    flip = pred[0] != g["pred"]
+    assert not np.any(flip & (np.abs(g["score"] - 0.5) >= 0.05))
+    assert pred.dtype == np.int64 and score.dtype == np.float32
+
+
+def test_features_track_the_fp16_emulation(engine):
+    """Layer by layer against the oracle's fp16-operand emulation (tight: same rounding points)."""
+    from oracle import pointnet2_oracle as O
+    g = np.load(GOLD[-1])
+    sd = make_pointnet2_state(int(g["ckpt_seed"]))
+    tr = {}
+    _, _, want = O.classify_path_points(sd, g["pc"], g["start_mask"], g["goal_mask"], g["fps_start"], emulate="fp16", trace=tr)
+    _, _, logp = engine.classify(g["pc"], g["start_mask"], g["goal_mask"], fps_start=g["fps_start"], return_logp=True)
+    for l in range(1, 5):
+        got = engine.read_buffer(f"feat{l}", np.float16, (1, NP[l], CH[l]))[0].astype(np.float32)
+        ref = tr["feats"][l - 1][0]
+        assert np.abs(got - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max()), (l, np.abs(got - ref).max())
+    assert np.abs(logp[0] - want).max() <= 5e-3
+
+
+def test_batch_equals_singles_and_is_deterministic(engine):
+    clouds = [make_cloud_3d(i) for i in range(5)]
+    pc = np.stack([c[0] for c in clouds]); sm = np.stack([c[1] for c in clouds]); gm = np.stack([c[2] for c in clouds])
+    fs = np.array([[7 * i % 2048, 5 * i % 1024, 3 * i % 256, i % 64] for i in range(5)], dtype=np.int32)
+    pred, score, logp = engine.classify(pc, sm, gm, fps_start=fs, return_logp=True)
+    pred2, score2, logp2 = engine.classify(pc, sm, gm, fps_start=fs, return_logp=True)
+    assert np.array_equal(logp, logp2) and np.array_equal(pred, pred2)
+    for i in (0, 3, 4):
+        p1, s1, l1 = engine.classify(pc[i], sm[i], gm[i], fps_start=fs[i], return_logp=True)
+        assert np.array_equal(l1[0], logp[i])
+        assert np.array_equal(p1[0], pred[i]) and np.array_equal(s1[0], score[i])
+
+
+def test_bad_arguments_raise(engine):
+    from nirrt_star_b200._lib import NirrtError
+    pc, sm, gm = make_cloud_3d(0)
+    with pytest.raises(ValueError):
+        engine.classify(pc[:1000], sm[:1000], gm[:1000])
+    with pytest.raises(NirrtError):
+        engine.classify(np.stack([pc] * 9), np.stack([sm] * 9), np.stack([gm] * 9), fps_start=np.zeros((9, 4), np.int32))
