@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap the timed core region in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--core-only", action="store_true", help="skip roofline/eval/e2e/cpu legs (profiling runs)")
+    ap.add_argument("--clouds", type=int, default=256, help="PointNet++ leg: clouds per batch per GPU (2048 points each)")
+    ap.add_argument("--pn2-steps", type=int, default=20, help="PointNet++ leg: timed forwards")
+    ap.add_argument("--no-pointnet2", action="store_true")
+    ap.add_argument("--pointnet2-only", action="store_true", help="run only the PointNet++ leg (profiling runs)")
     return ap.parse_args()
 
 
@@ -225,6 +229,114 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# PointNet++ leg: clouds/s at 2048 points (second half of BASELINE.json's metric)
+
+PN2_GMAC_SA = 1.040e9      # MACs per 2048-point cloud in the SA MLPs
+PN2_GMAC_ALL = 1.380e9     # whole network
+
+
+def _pn2_cpu_baseline(seconds):
+    """The torch-fp32 oracle (== the reference's forward, see oracle/pointnet2_oracle.py) on all host
+    cores, batch 1 as the reference's planner calls it."""
+    import torch
+    from nirrt_star_b200.synthetic import make_cloud_3d, make_pointnet2_state
+    from oracle import pointnet2_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in make_pointnet2_state(0).items()}
+    pc, sm, gm = make_cloud_3d(0)
+    O.classify_path_points(sd, pc, sm, gm, [0, 0, 0, 0])
+    t0 = time.perf_counter(); n = 0
+    while time.perf_counter() - t0 < seconds:
+        O.classify_path_points(sd, pc, sm, gm, [n % 2048, n % 1024, n % 256, n % 64]); n += 1
+    el = time.perf_counter() - t0
+    return {"value": n / el, "unit": "clouds/s", "cores": cores, "kind": "port",
+            "sample": f"{n} single-cloud forwards of the torch-fp32 oracle (the reference's forward restated) in {el:.1f} s, "
+                      f"torch.set_num_threads({cores})"}
+
+
+def bench_pointnet2(args, world, rank, local, peaks, cpu=True):
+    import torch
+    import torch.distributed as dist
+    from nirrt_star_b200.pointnet2 import PointNet2Engine
+    from nirrt_star_b200.synthetic import make_cloud_3d, make_pointnet2_state
+    Bc, N, K, W = args.clouds, 2048, args.pn2_steps, 3
+    eng = PointNet2Engine(make_pointnet2_state(0), n_points=N, max_batch=Bc, device=local)
+    base = [make_cloud_3d(i) for i in range(16)]
+    rs = np.random.RandomState(rank)
+    pc = np.stack([base[i % 16][0] + rs.uniform(-0.01, 0.01, (N, 3)).astype(np.float32) for i in range(Bc)])
+    sm = np.stack([base[i % 16][1] for i in range(Bc)]); gm = np.stack([base[i % 16][2] for i in range(Bc)])
+    fs = np.stack([rs.randint(0, n, Bc) for n in (2048, 1024, 256, 64)], 1).astype(np.int32)
+    d_pc, d_sm, d_gm = (torch.from_numpy(a).cuda() for a in (pc, sm, gm))
+    d_fs = torch.from_numpy(fs).cuda()
+    d_pred = torch.empty((Bc, N), dtype=torch.int64, device="cuda")
+    d_score = torch.empty((Bc, N), dtype=torch.float32, device="cuda")
+
+    def fwd():
+        eng.classify_device(Bc, 3, d_pc.data_ptr(), d_sm.data_ptr(), d_gm.data_ptr(), d_fs.data_ptr(),
+                            d_pred.data_ptr(), d_score.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        fwd()
+    barrier()
+    l0 = eng.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_range:
+        torch.cuda.profiler.start()
+    ev0.record()
+    for _ in range(K):
+        fwd()
+    ev1.record()
+    barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches() - l0
+    # end to end through the host-buffer entry point (pinned host -> HBM -> pinned host inside)
+    pin = [torch.from_numpy(a).pin_memory().numpy() for a in (pc, sm, gm)]
+    eng.classify(pin[0], pin[1], pin[2], fps_start=fs)
+    barrier()
+    t0 = time.perf_counter()
+    reps = max(2, K // 4)
+    for _ in range(reps):
+        eng.classify(pin[0], pin[1], pin[2], fps_start=fs)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / reps
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0].item()), float(t[1].item())
+    # stage attribution (event bracket + sync around each stage group)
+    eng.set_profiling(True)
+    fwd(); torch.cuda.synchronize()
+    stages = eng.stage_ms()
+    eng.set_profiling(False)
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    sa_tflops = 2 * PN2_GMAC_SA * Bc / (stages["sa_mlp"] * 1e-3) / 1e12
+    out = {"metric": "PointNet++ clouds/sec @2048pts", "value": world * Bc * K / (ms / 1e3), "unit": "clouds/s",
+           "ms_per_step": ms / K, "steps": K, "warmup": W, "dtype": "f16 operands, f32 accumulate",
+           "config": {"workload": f"pointnet2 MSG sem-seg forward (classify_path_points), {Bc} clouds x {N} points per GPU "
+                                  "(BASELINE configs[2] batch), synthetic checkpoint", "clouds_per_gpu": Bc, "n_points": N},
+           "e2e": {"value": world * Bc / e2e_s, "unit": "clouds/s", "h2d_bytes_per_step": float(pc.nbytes + sm.nbytes + gm.nbytes + fs.nbytes),
+                   "d2h_bytes_per_step": float(Bc * N * 12), "what": "nirrt_pn2_classify_sync with pinned host buffers"},
+           "gpu_launches": int(launches), "stage_ms": stages,
+           "roofline": {"bound": "tensor", "kernel": "umma::k_gemm (24 SA-MLP launches, tcgen05 kind::f16)", "achieved": sa_tflops,
+                        "peak": peak, "unit": "TFLOP/s", "frac": sa_tflops / peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (of measured)" if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s (of fallback)",
+                        "algorithmic_flops_per_step": 2 * PN2_GMAC_SA * Bc}}
+    if cpu and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = _pn2_cpu_baseline(min(10.0, args.cpu_seconds))
+    eng.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 
 def main():
@@ -246,6 +358,17 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if args.pointnet2_only:
+        pn2 = bench_pointnet2(args, world, rank, local, peaks, cpu=False)
+        if rank == 0:
+            print(json.dumps(pn2), flush=True)
+        return
 
     E, nodes, K, W = args.envs, args.nodes, args.steps, args.warmup
     env_base = rank * E
@@ -320,11 +443,6 @@ def main():
     prof = bp.run_profiled(prof_iters)
     _, _, n2 = bp.env_state()
     scan_bytes = float(0.5 * (n1.astype(np.float64).sum() + n2.astype(np.float64).sum()) * 24.0)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     t_near_ms = prof["nearest"] / prof_iters
     achieved = scan_bytes / (t_near_ms * 1e-3) / 1e9
@@ -392,6 +510,11 @@ def main():
         v_np, p_np, n_np, rng_states = snap
         cpu = cpu_baseline_from_snapshot(bp, v_np, p_np, n_np, rng_states, env_base, args.cpu_seconds)
 
+    pn2 = None
+    if not args.no_pointnet2:
+        bp.close()
+        pn2 = bench_pointnet2(args, world, rank, local, peaks)
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms_core / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -405,7 +528,7 @@ def main():
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "eval_variant": {"value": value_eval, "unit": UNIT, "ms_per_step": ms_eval / K,
                                 "what": "planning_random loop body (adds goal-parent search + path length per iteration)"},
-               "problems_with_solution": solved, "problems_total": world * E}
+               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
