@@ -32,6 +32,7 @@ extern "C" {
 #define NIRRT_VARIANT_RRT_STAR 0
 #define NIRRT_VARIANT_IRRT_STAR 1
 #define NIRRT_VARIANT_NIRRT_STAR 2
+#define NIRRT_VARIANT_NRRT_STAR 3   /* RRT* driver + fixed guidance cloud (nrrt_star_png_3d.py:52-56) */
 /* loop drivers: planning() body (rrt_star_3d.py:36-55) / planning_random (rrt_star_3d.py:200-270,
  * irrt_star_3d.py:245-331) */
 #define NIRRT_MODE_PLANNING 0
@@ -124,6 +125,10 @@ int nirrt_batch_status_sync(nirrt_batch *b, int *running, int *need_cloud, void 
 /* per problem: state[E] (0 done, 1 phase 1, 2 phase 2, 3 waiting for cloud), n_records[E], n_vertices[E] */
 int nirrt_batch_env_state_sync(nirrt_batch *b, int *state, int *n_records, int *n_vertices, void *stream);
 
+/* c_best as refreshed at the top of the last iteration (irrt_star_3d.py:253-254) and c_min = |goal - start|
+ * of every problem: the arguments of NIRRTStarPNG3D.update_point_cloud(cmax, cmin) (nirrt_star_png_3d.py:113-115) */
+int nirrt_batch_read_cbest_sync(nirrt_batch *b, double *c_best, double *c_min, void *stream);
+
 /* Raw per-iteration records [count][record_capacity] f64 + lengths [count].  RRT* family: path
  * length after each iteration; IRRT* family: c_best at the top of each iteration plus the final
  * refresh -- path_len_list is records[1:]. */
@@ -154,6 +159,11 @@ int nirrt_nearest_sync(nirrt_batch *b, int env, const double *queries, int64_t m
 int64_t nirrt_within_sync(nirrt_batch *b, int env, const double *q, double r, int64_t *out, int64_t cap, void *stream);
 /* RRTBase3D.cost (rrt_base_3d.py:60-67) for m vertex indices */
 int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int64_t m, double *out, void *stream);
+
+/* Farthest-point down-sampling of an f64 point set [n][3] (n <= 16384) to npoint indices, starting at
+ * `start`: open3d's PointCloud.farthest_point_down_sample as the guidance-cloud generators call it
+ * (datasets_3d/point_cloud_mask_utils_3d.py:49-52,196-199; datasets/point_cloud_mask_utils.py:69-72,170-173) */
+int nirrt_fps_f64_sync(const double *points, int64_t n, int npoint, int start, int64_t *out_idx, void *stream);
 
 /* Device-resident benchmark hooks: bytes scanned per Nearest+Near pass and launch counters. */
 int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *reserved);

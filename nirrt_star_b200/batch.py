@@ -19,7 +19,8 @@ import numpy as np
 from . import _lib
 from ._lib import MAX_OBSTACLES, NirrtError, check, dp, f64, i64p, ip, u8p
 
-VARIANT_RRT_STAR, VARIANT_IRRT_STAR, VARIANT_NIRRT_STAR = 0, 1, 2
+VARIANT_RRT_STAR, VARIANT_IRRT_STAR, VARIANT_NIRRT_STAR, VARIANT_NRRT_STAR = 0, 1, 2, 3
+INFORMED = (VARIANT_IRRT_STAR, VARIANT_NIRRT_STAR)
 MODE_PLANNING, MODE_PLANNING_RANDOM = 0, 1
 ST_DONE, ST_PHASE1, ST_PHASE2, ST_WAIT_CLOUD = 0, 1, 2, 3
 
@@ -221,7 +222,7 @@ class BatchPlanner3D:
         records after each iteration; the IRRT* family drops the pre-loop entry
         (irrt_star_3d.py:285)."""
         recs = self.records()
-        if self.variant == VARIANT_RRT_STAR:
+        if self.variant not in INFORMED:
             return [list(r) for r in recs]
         return [list(r[1:]) for r in recs]
 
@@ -230,6 +231,12 @@ class BatchPlanner3D:
         out = np.zeros(max(n, 1), dtype=np.int64)
         check(self.L.nirrt_batch_read_solutions_sync(self.h, int(env), i64p(out), len(out), self.stream))
         return out[:n]
+
+    def c_best(self):
+        """(c_best[E], c_min[E]) as of the top of the last executed iteration."""
+        cb = np.zeros(self.E); cm = np.zeros(self.E)
+        check(self.L.nirrt_batch_read_cbest_sync(self.h, dp(cb), dp(cm), self.stream))
+        return cb, cm
 
     def goal_parents(self):
         gp = np.zeros(self.E, dtype=np.int64); cost = np.zeros(self.E)
@@ -284,3 +291,14 @@ class BatchPlanner3D:
         ms = C.c_float(0); nbytes = C.c_int64(0)
         check(self.L.nirrt_batch_time_scan_sync(self.h, int(which), int(reps), C.byref(ms), C.byref(nbytes), self.stream))
         return ms.value, nbytes.value
+
+
+def fps_f64(points, npoint, start=0, stream=None):
+    """Indices of the farthest-point down-sampling of an (n,3) f64 point set (open3d semantics:
+    start index 0, squared distances in f64, first argmax)."""
+    _lib.require_device()
+    pts = f64(points).reshape(-1, 3)
+    out = np.zeros(int(npoint), dtype=np.int64)
+    check(_lib.lib().nirrt_fps_f64_sync(dp(pts), len(pts), int(npoint), int(start), i64p(out),
+                                        C.c_void_p(stream) if stream else None))
+    return out

@@ -114,6 +114,11 @@ struct View {
     const double *near_table;
 };
 
+// planner families: 0 RRT*, 1 IRRT*, 2 NIRRT* (informed + guidance cloud with updates),
+// 3 NRRT* (RRT* driver + a fixed guidance cloud, nrrt_star_png_3d.py:52-56)
+__host__ __device__ __forceinline__ bool fam_informed(int variant) { return variant == 1 || variant == 2; }
+__host__ __device__ __forceinline__ bool fam_cloud(int variant) { return variant == 2 || variant == 3; }
+
 __device__ __forceinline__ Node load_node(const Node *p) {
     // L2-coherent loads: parents are rewritten by this CTA while other threads keep walking
     const double2 a = __ldcg(reinterpret_cast<const double2 *>(p));
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
     __syncthreads();
 
     double c_best = XINF;
-    if (v.variant >= 1) {
+    if (fam_informed(v.variant)) {
         const int n_sol = c->n_sol;
         const Node *nodes = v.nodes + (size_t)e * v.stride;
         const int *sol = v.sol + (size_t)e * v.sol_cap;
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
     if (threadIdx.x != 0) return;
 
     const bool fresh = !(v.variant == 2 && c->resumed);
-    if (v.variant >= 1 && fresh) {
+    if (fam_informed(v.variant) && fresh) {
         c->c_best = c_best;
         if (v.mode == NIRRT_MODE_PLANNING_RANDOM) {
             if (c->state == ST_PHASE1) {
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
     MtStream rng(v.mt + e);
     double out[3];
     bool done = false;
-    if (v.variant == 2) {
+    if (fam_cloud(v.variant)) {
         if (rng.next_double() < v.pc_rate) {
             if (c->n_pc <= 0) { c->err |= ERR_EMPTY_CLOUD; c->state = ST_DONE; c->go = 0; rng.flush(); return; }
             const long long k = rng.randint(c->n_pc);
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
         }
     }
     if (!done) {
-        if (v.variant >= 1 && c_best < XINF) sample_informed(g, c, rng, c_best, out);
+        if (fam_informed(v.variant) && c_best < XINF) sample_informed(g, c, rng, c_best, out);
         else sample_free(g, rng, out);
     }
     rng.flush();
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
         }
         // ---- goal bookkeeping
         if (tid == 0) {
-            if (v.variant >= 1) {
+            if (fam_informed(v.variant)) {
                 // InGoalRegion (rrt_base_3d.py:93-95)
                 if (hypot3(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2])) < c->step_len &&
                     !seg_collides(g, xnew, c->goal)) {
@@ -676,7 +681,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
     }
 
     // ---- per-iteration record + phase machine (RRT* family; the IRRT* family records in k_top)
-    if (v.variant == 0 && v.mode == NIRRT_MODE_PLANNING_RANDOM) {
+    if (!fam_informed(v.variant) && v.mode == NIRRT_MODE_PLANNING_RANDOM) {
         double len;
         __syncthreads();
         const int changed = c->tree_changed;        // uniform: every thread reads before thread 0 clears it
@@ -1160,7 +1165,7 @@ extern "C" int nirrt_batch_read_trees_sync(nirrt_batch *b, int env_begin, int co
 
 extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter_max, int iter_after_initial, void *stream) {
     if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
-    if (variant < 0 || variant > 2 || mode < 0 || mode > 1 || iter_max < 0 || iter_after_initial < 0)
+    if (variant < 0 || variant > 3 || mode < 0 || mode > 1 || iter_max < 0 || iter_after_initial < 0)
         return fail(NIRRT_ERR_INVALID, "nirrt_batch_begin: bad variant/mode/iteration counts");
     View &v = b->v;
     CUDA_TRY(cudaSetDevice(b->device));
@@ -1169,7 +1174,7 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
     v.stop_below = (double)INFINITY;
     k_begin<<<(v.E + 127) / 128, 128, 0, s>>>(v);
     CHECK_LAUNCH();
-    if (variant == 0 && mode == NIRRT_MODE_PLANNING_RANDOM) {
+    if (!fam_informed(variant) && mode == NIRRT_MODE_PLANNING_RANDOM) {
         TRY(ensure_goal_lists(b));
         k_goal_init<<<v.E, 256, 0, s>>>(v);
         CHECK_LAUNCH();
@@ -1295,6 +1300,16 @@ extern "C" int nirrt_batch_env_state_sync(nirrt_batch *b, int *state, int *n_rec
     return NIRRT_OK;
 }
 
+extern "C" int nirrt_batch_read_cbest_sync(nirrt_batch *b, double *c_best, double *c_min, void *stream) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    TRY(fetch_ctl(b, (cudaStream_t)stream));
+    for (int e = 0; e < b->v.E; e++) {
+        if (c_best) c_best[e] = b->h_ctl[e].c_best;
+        if (c_min) c_min[e] = b->h_ctl[e].c_min;
+    }
+    return NIRRT_OK;
+}
+
 extern "C" int nirrt_batch_read_records_sync(nirrt_batch *b, int env_begin, int count, double *records, int *n_records, void *stream) {
     if (!b || !records || !n_records) return fail(NIRRT_ERR_INVALID, "nirrt_batch_read_records_sync: null argument");
     View &v = b->v;
@@ -1329,7 +1344,7 @@ extern "C" int nirrt_batch_goal_parent_sync(nirrt_batch *b, int64_t *goal_parent
     View &v = b->v;
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(b->device));
-    const int use_solutions = v.variant >= 1;
+    const int use_solutions = fam_informed(v.variant) ? 1 : 0;
     if (!use_solutions) {
         TRY(ensure_goal_lists(b));
         k_goal_init<<<v.E, 256, 0, s>>>(v);
@@ -1534,5 +1549,71 @@ extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, f
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *ms = acc / reps;
     if (bytes) *bytes = total;
+    return NIRRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Farthest-point down-sampling of a float64 point set (guidance-cloud generation, SURVEY row f1:
+// open3d PointCloud.farthest_point_down_sample as called by point_cloud_mask_utils_3d.py:49-52,
+// 196-199): start at `start`, running minimum of the squared distance (dx*dx + dy*dy) + dz*dz in
+// f64, next = first argmax.  One CTA; distances live in registers, the selected point's
+// coordinates are re-read from L2 each step.
+constexpr int kFpsThreads = 1024, kFpsPPT = 16;
+__global__ void __launch_bounds__(kFpsThreads) k_fps_f64(const double *pts, int n, int npoint, int start, long long *out) {
+    __shared__ double s_d[2][32];
+    __shared__ int s_i[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double px[kFpsPPT], py[kFpsPPT], pz[kFpsPPT], dist[kFpsPPT];
+#pragma unroll
+    for (int j = 0; j < kFpsPPT; j++) {
+        const int i = tid + j * kFpsThreads;
+        const bool in = i < n;
+        px[j] = in ? pts[3 * (size_t)i] : 0.0; py[j] = in ? pts[3 * (size_t)i + 1] : 0.0; pz[j] = in ? pts[3 * (size_t)i + 2] : 0.0;
+        dist[j] = in ? XINF : -1.0;
+    }
+    int far = start;
+    for (int it = 0; it < npoint; it++) {
+        if (tid == 0) out[it] = far;
+        const double cx = __ldg(pts + 3 * (size_t)far), cy = __ldg(pts + 3 * (size_t)far + 1), cz = __ldg(pts + 3 * (size_t)far + 2);
+        double bd = -2.0; int bi = INT_MAX;
+#pragma unroll
+        for (int j = 0; j < kFpsPPT; j++) {
+            const double d = sq3_rows(XSUB(px[j], cx), XSUB(py[j], cy), XSUB(pz[j], cz));
+            if (d < dist[j]) dist[j] = d;
+            if (dist[j] > bd) { bd = dist[j]; bi = tid + j * kFpsThreads; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        const int slot = it & 1;
+        if (lane == 0) { s_d[slot][warp] = bd; s_i[slot][warp] = bi; }
+        __syncthreads();
+        bd = s_d[slot][lane]; bi = s_i[slot][lane];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        far = bi;
+    }
+}
+
+extern "C" int nirrt_fps_f64_sync(const double *points, int64_t n, int npoint, int start, int64_t *out_idx, void *stream) {
+    if (!points || !out_idx || n < 1 || npoint < 1 || npoint > n || start < 0 || start >= n)
+        return fail(NIRRT_ERR_INVALID, "nirrt_fps_f64_sync: bad argument");
+    if (n > (int64_t)kFpsThreads * kFpsPPT) return fail(NIRRT_ERR_CAPACITY, "nirrt_fps_f64_sync: at most 16384 points");
+    if (nirrt_device_count() <= 0) return fail(NIRRT_ERR_NO_DEVICE, "no sm_100 device");
+    cudaStream_t s = (cudaStream_t)stream;
+    TempBufs t;
+    double *dp; long long *dout;
+    TRY(t.up(points, 3 * (size_t)n, s, &dp)); TRY(t.make<long long>((size_t)npoint, &dout));
+    k_fps_f64<<<1, kFpsThreads, 0, s>>>(dp, (int)n, npoint, start, dout);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out_idx, dout, sizeof(long long) * npoint, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return NIRRT_OK;
 }

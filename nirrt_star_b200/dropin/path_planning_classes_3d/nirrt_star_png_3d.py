@@ -1,0 +1,90 @@
+"""NIRRTStarPNG3D drop-in (reference: path_planning_classes_3d/nirrt_star_png_3d.py).  The loop body
+(including the point-cloud / informed / free sampling switch, nirrt_star_png_3d.py:99-130) runs on
+the device; when c_best drops below pc_update_cost_ratio * c_update the device pauses the problem,
+``update_point_cloud`` runs here (cloud sampling on the shared numpy stream, CUDA filters + FPS,
+PointNet++ through ``png_wrapper``) and the new predicted cloud is uploaded."""
+import numpy as np
+
+from nirrt_star_b200 import batch as _B
+from path_planning_utils_3d.rrt_env_3d import Env
+from path_planning_classes_3d.rrt_base_3d import RRTBase3D
+from path_planning_classes_3d.irrt_star_3d import IRRTStar3D
+from path_planning_classes_3d.rrt_visualizer_3d import NIRRTStarVisualizer3D
+from datasets.point_cloud_mask_utils import get_point_cloud_mask_around_points
+from datasets_3d.point_cloud_mask_utils_3d import generate_rectangle_point_cloud_3d, \
+    ellipsoid_point_cloud_sampling_3d
+
+
+class NIRRTStarPNG3D(IRRTStar3D):
+    _variant = _B.VARIANT_NIRRT_STAR
+
+    def __init__(self, x_start, x_goal, step_len, search_radius, iter_max, env_dict, png_wrapper, clearance,
+                 pc_n_points, pc_over_sample_scale, pc_sample_rate, pc_update_cost_ratio):
+        RRTBase3D.__init__(self, x_start, x_goal, step_len, search_radius, iter_max, Env(env_dict), clearance,
+                           "NIRRT*-PNG 3D")
+        self.png_wrapper = png_wrapper
+        self.pc_n_points = pc_n_points
+        self.pc_over_sample_scale = pc_over_sample_scale
+        self.pc_sample_rate = pc_sample_rate
+        self.pc_neighbor_radius = self.step_len
+        self.pc_update_cost_ratio = pc_update_cost_ratio
+        self.path_solutions = []
+        self.path_point_cloud_pred = None
+        self.visualizer = NIRRTStarVisualizer3D(self.x_start, self.x_goal, self.env)
+
+    # ---- engine hooks --------------------------------------------------------------------------
+    def _upload_cloud(self, eng):
+        pc = self.path_point_cloud_pred
+        eng.set_cloud(0, np.zeros((0, 3)) if pc is None else pc)
+
+    def _prepare(self, eng):
+        # init_pc() (nirrt_star_png_3d.py:50-54) consumes the numpy stream before the loop starts
+        eng.set_guidance(self.pc_sample_rate, self.pc_update_cost_ratio)
+        self.init_pc()
+        st = np.random.get_state()
+        eng.set_rng([(st[1], st[2])])
+        self._upload_cloud(eng)
+
+    def _cloud_callback(self):
+        def cb(eng, env_indices):
+            key, pos = eng.get_rng()[0]
+            np.random.set_state(("MT19937", key, pos, 0, 0.0))
+            c_best, c_min = eng.c_best()
+            self.update_point_cloud(float(c_best[0]), float(c_min[0]))
+            st = np.random.get_state()
+            eng.set_rng([(st[1], st[2])])
+            self._upload_cloud(eng)
+        return cb
+
+    # ---- reference methods ---------------------------------------------------------------------
+    def init_pc(self):
+        self.update_point_cloud(cmax=np.inf, cmin=None)
+
+    def SamplePointCloud(self):
+        return self.path_point_cloud_pred[np.random.randint(0, len(self.path_point_cloud_pred))]
+
+    def _sample_cloud(self, cmax, cmin):
+        if cmax < np.inf:
+            return ellipsoid_point_cloud_sampling_3d(self.x_start, self.x_goal, cmax / cmin, self.env, self.pc_n_points,
+                                                     n_raw_samples=self.pc_n_points * self.pc_over_sample_scale)
+        return generate_rectangle_point_cloud_3d(self.env, self.pc_n_points, over_sample_scale=self.pc_over_sample_scale)
+
+    def update_point_cloud(self, cmax, cmin):
+        """nirrt_star_png_3d.py:132-173"""
+        if self.pc_sample_rate == 0:
+            self.path_point_cloud_pred = None
+            self.visualizer.set_path_point_cloud_pred(self.path_point_cloud_pred)
+            return
+        pc = self._sample_cloud(cmax, cmin)
+        start_mask = get_point_cloud_mask_around_points(pc, self.x_start[np.newaxis, :], self.pc_neighbor_radius)
+        goal_mask = get_point_cloud_mask_around_points(pc, self.x_goal[np.newaxis, :], self.pc_neighbor_radius)
+        path_pred, path_score = self.png_wrapper.classify_path_points(
+            pc.astype(np.float32), start_mask.astype(np.float32), goal_mask.astype(np.float32))
+        self.path_point_cloud_pred = pc[path_pred.nonzero()[0]]
+        self.visualizer.set_path_point_cloud_pred(self.path_point_cloud_pred)
+
+
+def get_path_planner(args, problem, neural_wrapper):
+    return NIRRTStarPNG3D(problem['x_start'], problem['x_goal'], args.step_len, problem['search_radius'],
+                          args.iter_max, problem['env_dict'], neural_wrapper, args.clearance, args.pc_n_points,
+                          args.pc_over_sample_scale, args.pc_sample_rate, args.pc_update_cost_ratio)

@@ -28,7 +28,7 @@ class RRTStar3D(RRTBase3D):
         eng.run_to_completion(chunk=min(512, max(1, self.iter_max)), cloud_callback=self._cloud_callback())
         gp, _ = eng.goal_parents()
         self._finish_engine()
-        if self._variant != _B.VARIANT_RRT_STAR:
+        if self._variant in _B.INFORMED:
             self.path_solutions = [int(i) for i in eng.solutions(0)]
         self.path = self.extract_path(int(gp[0])) if gp[0] >= 0 else []
         if visualize:
@@ -42,7 +42,7 @@ class RRTStar3D(RRTBase3D):
             eng.set_stop_threshold(stop_below)
         eng.run_to_completion(chunk=min(512, max(1, self.iter_max)), cloud_callback=self._cloud_callback())
         self._finish_engine()
-        if self._variant != _B.VARIANT_RRT_STAR:
+        if self._variant in _B.INFORMED:
             self.path_solutions = [int(i) for i in eng.solutions(0)]
         return eng.path_len_lists()[0]
 

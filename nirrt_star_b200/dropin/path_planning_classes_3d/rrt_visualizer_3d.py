@@ -3,9 +3,9 @@ can be constructed cheaply (rrt_star_3d.py:30) and that refuse to draw."""
 
 
 class _NoVisualizer:
-    def __init__(self, x_start, x_goal, env):
+    def __init__(self, x_start, x_goal, env, path_point_cloud_pred=None):
         self.x_start, self.x_goal, self.env = x_start, x_goal, env
-        self.path_point_cloud_pred = None
+        self.path_point_cloud_pred = path_point_cloud_pred
 
     def set_path_point_cloud_pred(self, pc):
         self.path_point_cloud_pred = pc

@@ -1,0 +1,110 @@
+"""NIRRT*-PNG / NRRT*-PNG 3D drop-in classes vs fixtures recorded from the reference's own classes
+(tests/golden/make_golden_neural_planner.py).  The network is replaced on both sides by recorded
+predictions, so this pins: the device loop body with the cloud / informed / free sampler switch, the
+cloud-update trigger (c_best < ratio * c_update) and its pause/resume, the shared numpy stream
+hand-over, and the guidance-cloud generation (uniform / ellipsoid draws, CUDA obstacle filters,
+CUDA farthest-point down-sampling) -- every cloud must hash identically to the reference's."""
+import glob
+import hashlib
+import os
+import random
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "neural3d_*.npz")))
+
+
+class ReplayWrapper:
+    def __init__(self, g):
+        self.g, self.k = g, 0
+
+    def classify_path_points(self, pc, start_mask, goal_mask):
+        g, k = self.g, self.k
+        assert k < int(g["n_calls"]), "more cloud updates than the reference made"
+        assert pc.dtype == np.float32 and len(pc) == int(g["call_n"][k])
+        assert hashlib.sha1(np.ascontiguousarray(pc).tobytes()).hexdigest() == str(g["call_pc_sha1"][k]), f"cloud {k} differs"
+        assert hashlib.sha1(start_mask.tobytes() + goal_mask.tobytes()).hexdigest() == str(g["call_mask_sha1"][k])
+        pred = np.unpackbits(g["call_pred"][k])[:len(pc)].astype(np.int64)
+        self.k += 1
+        return pred, pred.astype(np.float32)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def dropin():
+    from nirrt_star_b200 import dropin
+    dropin.install()
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_neural_planner_matches_reference_golden(path):
+    import importlib
+    from nirrt_star_b200.synthetic import make_problem_3d
+    g = np.load(path)
+    kind, mode = str(g["kind"]), str(g["mode"])
+    mod = importlib.import_module("path_planning_classes_3d." + {"nirrt": "nirrt_star_png_3d", "nrrt": "nrrt_star_png_3d"}[kind])
+    problem = make_problem_3d(int(g["env_idx"]))
+    args = types.SimpleNamespace(step_len=10, iter_max=int(g["iter_max"]), clearance=2, pc_n_points=2048,
+                                 pc_over_sample_scale=5, pc_sample_rate=float(g["pc_sample_rate"]),
+                                 pc_update_cost_ratio=float(g["ratio"]))
+    seed = int(g["seed"])
+    np.random.seed(seed); random.seed(seed)
+    w = ReplayWrapper(g)
+    planner = mod.get_path_planner(args, problem, w)
+    if mode == "planning":
+        planner.planning(False)
+        if len(g["path"]):
+            assert np.allclose(planner.path, g["path"], rtol=0, atol=1e-12)
+        else:
+            assert len(planner.path) == 0
+    else:
+        lst = planner.planning_random(int(g["iter_after"]))
+        want = g["path_len_list"]
+        assert len(lst) == len(want)
+        assert np.array_equal(np.isinf(lst), np.isinf(want))
+        f = np.isfinite(want)
+        assert np.allclose(np.array(lst)[f], want[f], rtol=1e-5, atol=0)
+    assert w.k == int(g["n_calls"])
+    n = planner.num_vertices
+    assert n == int(g["num_vertices"])
+    assert np.array_equal(planner.vertex_parents[:n], g["parents"])
+    assert np.allclose(planner.vertices[:n], g["vertices"], rtol=0, atol=1e-12)
+    if kind == "nirrt":
+        assert list(planner.path_solutions) == list(g["solutions"])
+    assert np.random.random() == float(g["next_random"])
+
+
+def test_fps_f64_matches_numpy():
+    from nirrt_star_b200.batch import fps_f64
+    rs = np.random.RandomState(3)
+    for n, m in ((5000, 2048), (9000, 2048), (300, 300), (16384, 100)):
+        pts = rs.uniform(0, 50, (n, 3))
+        dist = np.full(n, np.inf); far = 0; want = []
+        for _ in range(m):
+            want.append(far)
+            dist = np.minimum(dist, ((pts - pts[far]) ** 2).sum(axis=1))
+            far = int(np.argmax(dist))
+        assert np.array_equal(fps_f64(pts, m), np.array(want))
+
+
+def test_nirrt_with_the_cuda_network_end_to_end(tmp_path):
+    """NIRRTStarPNG3D + the sm_100a PNGWrapper (synthetic checkpoint): runs, returns a valid path."""
+    import torch
+    from nirrt_star_b200.synthetic import make_pointnet2_state, make_problem_3d
+    from path_planning_classes_3d.nirrt_star_png_3d import get_path_planner
+    from wrapper_3d.pointnet_pointnet2.pointnet2_wrapper import PNGWrapper
+    d = tmp_path / "results/model_training/pointnet2_3d/checkpoints"
+    d.mkdir(parents=True)
+    torch.save({"model_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in make_pointnet2_state(0).items()}},
+               str(d / "best_pointnet2_3d.pth"))
+    w = PNGWrapper(root_dir=str(tmp_path), device="cuda")
+    problem = make_problem_3d(0)
+    args = types.SimpleNamespace(step_len=10, iter_max=2000, clearance=2, pc_n_points=2048, pc_over_sample_scale=5,
+                                 pc_sample_rate=0.5, pc_update_cost_ratio=0.9)
+    np.random.seed(1); torch.manual_seed(1)
+    planner = get_path_planner(args, problem, w)
+    lst = planner.planning_random(200)
+    assert np.isfinite(lst[-1]) and len(planner.path_point_cloud_pred) > 0
+    assert all(b <= a + 1e-9 for a, b in zip(lst[-200:], lst[-199:]))      # best cost never increases

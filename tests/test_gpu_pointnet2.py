@@ -128,3 +128,34 @@ def test_bad_arguments_raise(engine):
         engine.classify(pc[:1000], sm[:1000], gm[:1000])
     with pytest.raises(NirrtError):
         engine.classify(np.stack([pc] * 9), np.stack([sm] * 9), np.stack([gm] * 9), fps_start=np.zeros((9, 4), np.int32))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_dropin_wrapper_matches_reference_golden(path, tmp_path):
+    """wrapper{,_3d}.pointnet_pointnet2.pointnet2_wrapper.PNGWrapper: checkpoint file in, same
+    outputs as the reference's wrapper, torch's global CPU generator advanced identically."""
+    import importlib
+    import torch
+    from nirrt_star_b200 import dropin
+    dropin.install()
+    g = np.load(path)
+    dim = int(g["dim"])
+    d = tmp_path / f"results/model_training/pointnet2_{dim}d/checkpoints"
+    d.mkdir(parents=True)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in make_pointnet2_state(int(g["ckpt_seed"])).items()}
+    torch.save({"model_state_dict": sd}, str(d / f"best_pointnet2_{dim}d.pth"))
+    mod = importlib.import_module(("wrapper_3d" if dim == 3 else "wrapper") + ".pointnet_pointnet2.pointnet2_wrapper")
+    w = mod.PNGWrapper(root_dir=str(tmp_path), device="cuda")
+    torch.manual_seed(int(g["seed"]))
+    pred, score = w.classify_path_points(g["pc"], g["start_mask"], g["goal_mask"])
+    assert pred.shape == (2048,) and pred.dtype == np.int64 and score.dtype == np.float32
+    assert np.abs(score - g["score"]).max() <= LOGP_TOL
+    assert not np.any((pred != g["pred"]) & (np.abs(g["score"] - 0.5) >= 0.05))
+    # the reference would have drawn exactly four randint()s from the global torch generator
+    torch.manual_seed(int(g["seed"]))
+    for n in (2048, 1024, 256, 64):
+        torch.randint(0, n, (1,))
+    expect_next = torch.rand(1)
+    torch.manual_seed(int(g["seed"]))
+    w.classify_path_points(g["pc"], g["start_mask"], g["goal_mask"])
+    assert torch.equal(torch.rand(1), expect_next)
