@@ -946,7 +946,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     v.chunks = pick_chunks(v.E);
     v.near_cap = d->near_capacity > 0 ? d->near_capacity : kNearSmem;
     v.rec_cap = d->record_capacity > 0 ? d->record_capacity : d->capacity + 8;
-    v.sol_cap = v.rec_cap;
+    v.sol_cap = v.rec_cap > v.cap + 8 ? v.rec_cap : v.cap + 8;   // at most one append per iteration
     v.pc_cap = 4096; v.path_cap = 4096;
     v.pc_rate = 0.5; v.pc_ratio = 0.9; v.stop_below = (double)INFINITY;
     const size_t EV = (size_t)v.E * v.stride;
