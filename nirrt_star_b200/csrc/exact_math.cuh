@@ -173,9 +173,9 @@ NIRRT_HD dd_t dd_cos_coef(int i) {
     dd_t r; r.hi = t[i][0]; r.lo = t[i][1]; return r;
 }
 
-// Correctly-rounded (error < 2^-100) sin and cos for 0 <= |x| < ~1e5, double-double Taylor series
+// sin and cos as double-doubles (error < 2^-100) for 0 <= |x| < ~1e5: Taylor series in double-double
 // after an exact four-term reduction by pi/2.  Same operation sequence as the oracle's cr_sincos.
-NIRRT_HD void cr_sincos(double x, double *s_out, double *c_out) {
+NIRRT_HD void dd_sincos(double x, dd_t *s_out, dd_t *c_out) {
     double k = rint(XMUL(x, 0x1.45f306dc9c883p-1));
     dd_t r, t, m;
     t = two_prod(k, dd_pio2(0));
@@ -193,12 +193,67 @@ NIRRT_HD void cr_sincos(double x, double *s_out, double *c_out) {
     dd_t sn = dd_add(r, dd_mul(dd_mul(r2, ps), r));
     m.hi = 1.0; m.lo = 0.0;
     dd_t cs = dd_add(m, dd_mul(r2, pc));
+    dd_t ns, nc;
+    ns.hi = -sn.hi; ns.lo = -sn.lo; nc.hi = -cs.hi; nc.lo = -cs.lo;
     int q = ((int)k) & 3;
-    if (q == 0) { *s_out = sn.hi; *c_out = cs.hi; }
-    else if (q == 1) { *s_out = cs.hi; *c_out = -sn.hi; }
-    else if (q == 2) { *s_out = -sn.hi; *c_out = -cs.hi; }
-    else { *s_out = -cs.hi; *c_out = sn.hi; }
+    if (q == 0) { *s_out = sn; *c_out = cs; }
+    else if (q == 1) { *s_out = cs; *c_out = ns; }
+    else if (q == 2) { *s_out = ns; *c_out = nc; }
+    else { *s_out = nc; *c_out = sn; }
 }
+// Correctly-rounded sin and cos (np.sin / np.cos / math.sin / math.cos up to glibc's own ~0.13 %
+// last-bit misroundings).
+NIRRT_HD void cr_sincos(double x, double *s_out, double *c_out) {
+    dd_t s, c;
+    dd_sincos(x, &s, &c);
+    *s_out = s.hi; *c_out = c.hi;
+}
+
+// Correctly-rounded atan2 (math.atan2 up to glibc's last-bit misroundings): one Newton step in
+// double-double on a <= 2-ulp seed, theta = t0 + (y cos t0 - x sin t0) / (x cos t0 + y sin t0).
+NIRRT_HD double cr_atan2(double y, double x) {
+    if (y == 0.0 && x == 0.0) return 0.0;          // atan2(+0, +0); the planners never produce -0 here
+    const double t0 = atan2(y, x);
+    dd_t s, c;
+    dd_sincos(t0, &s, &c);
+    dd_t a = two_prod(y, c.hi); a.lo = XADD(a.lo, XMUL(y, c.lo));
+    dd_t b = two_prod(x, s.hi); b.lo = XADD(b.lo, XMUL(x, s.lo));
+    b.hi = -b.hi; b.lo = -b.lo;
+    const dd_t num = dd_add(a, b);
+    const double den = XADD(XMUL(x, c.hi), XMUL(y, s.hi));
+    return XADD(t0, XDIV(XADD(num.hi, num.lo), den));
+}
+
+// np.hypot(x, y) == glibc 2.35+ hypot (sysdeps/ieee754/dbl-64/e_hypot.c, the non-FMA kernel that
+// x86-64 builds use; pinned against libm on 2e7 samples in tests/test_host_math.py).  Not correctly
+// rounded, hence restated operation by operation.  Planner coordinates are far from the
+// overflow / underflow scaling branches, which fall back to the plain formula here.
+NIRRT_HD double np_hypot(double x, double y) {
+    x = fabs(x); y = fabs(y);
+    const double ax = x < y ? y : x, ay = x < y ? x : y;
+    if (!(ax <= 0x1p+511) || (ay != 0.0 && ay < 0x1p-459)) return XSQRT(XADD(XMUL(ax, ax), XMUL(ay, ay)));
+    if (ay <= XMUL(ax, 0x1p-54)) return XADD(ax, ay);
+    double t1, t2;
+    double h = XSQRT(XADD(XMUL(ax, ax), XMUL(ay, ay)));
+    if (h <= XMUL(2.0, ay)) {
+        const double delta = XSUB(h, ay);
+        t1 = XMUL(ax, XSUB(XMUL(2.0, delta), ax));
+        t2 = XMUL(XSUB(delta, XMUL(2.0, XSUB(ax, ay))), delta);
+    } else {
+        const double delta = XSUB(h, ax);
+        t1 = XMUL(XMUL(2.0, delta), XSUB(ax, XMUL(2.0, ay)));
+        t2 = XADD(XMUL(XSUB(XMUL(4.0, delta), ay), ay), XMUL(delta, delta));
+    }
+    h = XSUB(h, XDIV(XADD(t1, t2), XMUL(2.0, h)));
+    return h;
+}
+// 2D twins of the norms above (probed against numpy 2.3 in this image):
+//   vecnorm2 == np.linalg.norm(vec2) (1-D, BLAS ddot)          collision_check_utils.py:50,55,76; rrt_star_2d.py:41
+//   rownorm2 == np.linalg.norm(v, axis=1) on (n,2)             rrt_base_2d.py:85
+//   dot2     == np.dot(vec2, vec2)                             collision_check_utils.py:53
+NIRRT_HD double vecnorm2(double dx, double dy) { return XSQRT(XFMA(dy, dy, XMUL(dx, dx))); }
+NIRRT_HD double rownorm2(double dx, double dy) { return XSQRT(XADD(XMUL(dx, dx), XMUL(dy, dy))); }
+NIRRT_HD double dot2(double a0, double a1, double b0, double b1) { return XFMA(a1, b1, XMUL(a0, b0)); }
 
 // numpy pairwise summation of a contiguous f64 vector (np.add.reduce inner loop, PW_BLOCKSIZE 128)
 #if defined(__CUDACC__)

@@ -171,3 +171,57 @@ def make_cloud_3d(env_idx, n_points=2048, base_seed=100):
     sm = (np.linalg.norm(pc - np.array(pr["x_start"], dtype=np.float32), axis=1) < r).astype(np.float32)
     gm = (np.linalg.norm(pc - np.array(pr["x_goal"], dtype=np.float32), axis=1) < r).astype(np.float32)
     return pc, sm, gm
+
+
+# ---------------------------------------------------------------------------------------------
+# Synthetic random_2d worlds (env_configs/random_2d.yml + generate_random_world_env_2d.py:14-47)
+
+IMG_2D = (224, 224)
+
+
+def rasterize_2d(rects, circles, hw=IMG_2D):
+    """binary_mask (1 = free) of the world image the reference draws with cv2.rectangle/circle
+    (filled, inclusive pixel extents); the drawing itself is restated with numpy."""
+    h, w = hw
+    yy, xx = np.mgrid[0:h, 0:w]
+    occ = np.zeros((h, w), dtype=bool)
+    for x, y, rw, rh in rects:
+        occ |= (xx >= x) & (xx <= x + rw) & (yy >= y) & (yy <= y + rh)
+    for x, y, r in circles:
+        occ |= (xx - x) ** 2 + (yy - y) ** 2 <= r * r
+    return (~occ).astype(float)
+
+
+def make_env_2d(seed):
+    import random as _r
+    rnd = _r.Random(seed)
+    h, w = IMG_2D
+    n_rect, n_circ = rnd.randint(8, 12), rnd.randint(8, 12)
+    rects = [[rnd.randint(0, w), rnd.randint(0, h), rnd.randint(16, 24), rnd.randint(16, 24)] for _ in range(n_rect)]
+    circles = [[rnd.randint(0, w), rnd.randint(0, h), rnd.randint(16, 24)] for _ in range(n_circ)]
+    mask = rasterize_2d(rects, circles)
+    c = 3
+
+    def window_free(p):
+        x, y = p
+        if x - c < 0 or y - c < 0 or x + c >= w or y + c >= h:
+            return False
+        return bool(mask[y - c:y + c + 1, x - c:x + c + 1].all())
+
+    for _ in range(100000):
+        s = (rnd.randint(0, w - 1), rnd.randint(0, h - 1)); g = (rnd.randint(0, w - 1), rnd.randint(0, h - 1))
+        if abs(s[0] - g[0]) >= 50 and abs(s[1] - g[1]) >= 50 and window_free(s) and window_free(g):
+            break
+    else:
+        raise RuntimeError("could not place start/goal")
+    return {"env_dims": [h, w], "rectangle_obstacles": rects, "circle_obstacles": circles,
+            "start": [list(s)], "goal": [list(g)]}, mask
+
+
+def make_problem_2d(env_idx, base_seed=100):
+    """A 2D ``problem`` dict with the keys get_random_2d_problem_input returns
+    (planning_problem_utils_2d.py:145-162), minus the reference's ``Env`` object."""
+    env_dict, mask = make_env_2d(base_seed + env_idx)
+    gamma = math.ceil((2 * (1 + 1. / 2)) ** (1. / 2) * (mask.sum() / np.pi) ** (1. / 2))   # compute_gamma_rrt_star
+    return {"x_start": tuple(env_dict["start"][0]), "x_goal": tuple(env_dict["goal"][0]), "env_dict": env_dict,
+            "binary_mask": mask, "search_radius": gamma}

@@ -4,6 +4,7 @@
 #include <cstring>
 #include "../nirrt_star_b200/csrc/exact_math.cuh"
 #include "../nirrt_star_b200/csrc/geometry3d.cuh"
+#include "../nirrt_star_b200/csrc/geometry2d.cuh"
 
 using namespace nirrt;
 
@@ -29,4 +30,23 @@ void hh_collide(long m, const double *edges, unsigned char *out) {
 }
 void hh_inside(long m, const double *p, unsigned char *out) { for (long i = 0; i < m; i++) out[i] = point_inside_obs(g, p + 3 * i); }
 void hh_valid(long m, const double *p, unsigned char *out) { for (long i = 0; i < m; i++) out[i] = point_valid(g, p + 3 * i); }
+
+// ---- 2D
+double hh_np_hypot(double a, double b) { return np_hypot(a, b); }
+double hh_cr_atan2(double y, double x) { return cr_atan2(y, x); }
+double hh_vecnorm2(double a, double b) { return vecnorm2(a, b); }
+double hh_rownorm2(double a, double b) { return rownorm2(a, b); }
+static Geom2 g2;
+void hh_set_geom2(int nc, const double *circles, int nr, const double *rects, double cl, const double *range4) {
+    memset(&g2, 0, sizeof(g2));
+    g2.n_circles = nc; g2.n_rects = nr; g2.clearance = cl;
+    memcpy(g2.range, range4, 32);
+    for (int k = 0; k < nc; k++) memcpy(g2.circles[k], circles + 3 * k, 24);
+    for (int k = 0; k < nr; k++) memcpy(g2.rects[k], rects + 4 * k, 32);
+}
+void hh_collide2(long m, const double *edges, unsigned char *out) {
+    for (long i = 0; i < m; i++) out[i] = seg_collides(g2, edges + 4 * i, edges + 4 * i + 2);
+}
+void hh_inside2(long m, const double *p, unsigned char *out) { for (long i = 0; i < m; i++) out[i] = point_inside_obs(g2, p + 2 * i); }
+void hh_valid2(long m, const double *p, unsigned char *out) { for (long i = 0; i < m; i++) out[i] = point_valid(g2, p + 2 * i); }
 }

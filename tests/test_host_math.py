@@ -101,3 +101,66 @@ def test_geometry_matches_oracle(hh, env_idx):
     assert np.array_equal(out.astype(bool), o.points_inside_obs(pts))
     hh.hh_valid(len(pts), dpp(pts), out.ctypes.data_as(C.POINTER(C.c_uint8)))
     assert np.array_equal(out.astype(bool), o.points_valid(pts))
+
+
+# ---------------------------------------------------------------------------------------------- 2D
+def test_np_hypot_is_glibc_hypot(hh):
+    hh.hh_np_hypot.restype = C.c_double; hh.hh_np_hypot.argtypes = [C.c_double] * 2
+    rng = np.random.default_rng(5)
+    for scale in (224.0, 10.0, 1e-3, 1e6):
+        w = rng.uniform(-scale, scale, (100000, 2))
+        w[:2000, 1] *= 1e-9; w[2000:2500, 1] = 0.0; w[2500:3000] = np.round(w[2500:3000])
+        want = np.hypot(w[:, 0], w[:, 1])
+        got = np.array([hh.hh_np_hypot(a, b) for a, b in w])
+        assert np.array_equal(got, want)
+
+
+def test_cr_atan2_is_correctly_rounded(hh):
+    hh.hh_cr_atan2.restype = C.c_double; hh.hh_cr_atan2.argtypes = [C.c_double] * 2
+    rng = np.random.default_rng(6)
+    w = rng.uniform(-224, 224, (40000, 2))
+    w[:100, 0] = 0.0; w[100:200, 1] = 0.0
+    mism = 0
+    for y, x in w:
+        got = hh.hh_cr_atan2(y, x)
+        ref = math.atan2(y, x)
+        assert abs(got - ref) <= 4.5e-16 * max(1.0, abs(ref))     # never more than one ulp from libm
+        mism += got != ref
+    assert mism < 0.01 * len(w)                                   # libm misrounds a fraction of a percent
+    assert hh.hh_cr_atan2(0.0, 0.0) == 0.0 and hh.hh_cr_atan2(0.0, -1.0) == math.pi
+    # exactness against an independent high-precision evaluation (decimal-free: long double on x86 has 64 bits,
+    # enough to decide the rounding of almost every sample)
+    ld = np.arctan2(w[:2000, 0].astype(np.longdouble), w[:2000, 1].astype(np.longdouble))
+    got = np.array([hh.hh_cr_atan2(y, x) for y, x in w[:2000]])
+    assert (got != ld.astype(np.float64)).sum() <= 2              # only double-rounding coincidences may differ
+
+
+def test_norms2_match_numpy(hh):
+    for f in ("hh_vecnorm2", "hh_rownorm2"):
+        getattr(hh, f).restype = C.c_double; getattr(hh, f).argtypes = [C.c_double] * 2
+    rng = np.random.default_rng(7)
+    w = rng.uniform(-224, 224, (20000, 2))
+    rows = np.linalg.norm(w, axis=1)
+    for i, (a, b) in enumerate(w):
+        assert hh.hh_rownorm2(a, b) == rows[i]
+        assert hh.hh_vecnorm2(a, b) == float(np.linalg.norm(w[i]))
+
+
+@pytest.mark.parametrize("env_idx", [0, 1, 2])
+def test_geometry2d_matches_reference_golden(hh, env_idx):
+    from nirrt_star_b200.synthetic import make_problem_2d
+    g = np.load(os.path.join(HERE, "golden", f"geom2d_e{env_idx}.npz"))
+    ed = make_problem_2d(env_idx)["env_dict"]
+    circles = np.ascontiguousarray(ed["circle_obstacles"], dtype=np.float64)
+    rects = np.ascontiguousarray(ed["rectangle_obstacles"], dtype=np.float64)
+    dpp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rng4 = np.array([0, ed["env_dims"][1], 0, ed["env_dims"][0]], dtype=np.float64)
+    hh.hh_set_geom2(len(circles), dpp(circles), len(rects), dpp(rects), C.c_double(3.0), dpp(rng4))
+    u8 = lambda a: a.ctypes.data_as(C.POINTER(C.c_ubyte))
+    edges = np.ascontiguousarray(g["edges"]); pts = np.ascontiguousarray(g["pts"])
+    out = np.zeros(len(edges), dtype=np.uint8)
+    hh.hh_collide2(len(edges), dpp(edges), u8(out))
+    assert np.array_equal(out.astype(bool), g["hit"])
+    out = np.zeros(len(pts), dtype=np.uint8)
+    hh.hh_inside2(len(pts), dpp(pts), u8(out)); assert np.array_equal(out.astype(bool), g["inside"])
+    hh.hh_valid2(len(pts), dpp(pts), u8(out)); assert np.array_equal(out.astype(bool), g["valid"])
