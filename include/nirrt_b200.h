@@ -46,7 +46,8 @@ int nirrt_device_count(void);
 typedef struct nirrt_batch nirrt_batch;
 
 typedef struct nirrt_batch_desc {
-    int dim;            /* 3 (2D worlds use nirrt2_* entry points) */
+    int dim;            /* 3, or 2 (problems then come from nirrt_batch_set_problems_2d; every [..][3] array
+                           below is [..][2], edges are [m][2][2]) */
     int n_envs;         /* E: independent planning problems advanced in lock step */
     int capacity;       /* vertices per problem = 1 + iter_max (rrt_base_3d.py:25) */
     int record_capacity;/* per-problem path_len_list rows (>= iter_max + iter_after_initial + 2) */
@@ -78,6 +79,22 @@ int nirrt_batch_set_problems(nirrt_batch *b, const double *start, const double *
                              const double *range, const int *n_balls, const double *balls,
                              const double *ball_r2, const int *n_boxes, const double *boxes,
                              const double *near_table, const double *rot_c, void *stream);
+
+/* 2D problems == the arguments of RRTStar2D.__init__ / get_path_planner (rrt_star_2d.py:10-30,270-283) +
+ * Utils.__init__ (rrt_utils_2d.py:5-17):
+ *   start, goal [E][2]; step_len, search_radius, clearance [E]; range [E][4] x0 x1 y0 y1 (rrt_env.py:7-8)
+ *   circles [E][NIRRT_MAX_OBSTACLES][3] x y r; rects [E][NIRRT_MAX_OBSTACLES][4] x y w h
+ *   near_table [capacity+2]  t[n] = math.sqrt(math.log(n)/n)  (rrt_star_2d.py:133)
+ *   rot_c [E][9] IRRTStar2D.RotationToWorldFrame (irrt_star_2d.py:153-161), may be NULL for RRT*. */
+int nirrt_batch_set_problems_2d(nirrt_batch *b, const double *start, const double *goal,
+                                const double *step_len, const double *search_radius, const double *clearance,
+                                const double *range, const int *n_circles, const double *circles,
+                                const int *n_rects, const double *rects, const double *near_table,
+                                const double *rot_c, void *stream);
+/* random.seed(s) state of each problem (2D informed sampling draws its unit disc from CPython's
+ * `random`, irrt_star_2d.py:146-151): key [E][624], pos [E] (random.getstate()[1][:624], [624]) */
+int nirrt_batch_set_py_rng(nirrt_batch *b, const uint32_t *key, const int *pos, void *stream);
+int nirrt_batch_get_py_rng_sync(nirrt_batch *b, uint32_t *key, int *pos, void *stream);
 
 /* np.random.seed(s) state of each problem: key [E][624], pos [E] (np.random.get_state()[1:3]) */
 int nirrt_batch_set_rng(nirrt_batch *b, const uint32_t *key, const int *pos, void *stream);

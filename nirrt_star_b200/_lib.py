@@ -51,6 +51,9 @@ def lib():
     L.nirrt_batch_create.argtypes = [C.POINTER(BatchDesc), C.POINTER(V)]
     L.nirrt_batch_destroy.argtypes = [V]
     L.nirrt_batch_set_problems.argtypes = [V, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp, V]
+    L.nirrt_batch_set_problems_2d.argtypes = [V, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp, c_ip, c_dp, c_dp, c_dp, V]
+    L.nirrt_batch_set_py_rng.argtypes = [V, c_u32p, c_ip, V]
+    L.nirrt_batch_get_py_rng_sync.argtypes = [V, c_u32p, c_ip, V]
     L.nirrt_batch_set_rng.argtypes = [V, c_u32p, c_ip, V]
     L.nirrt_batch_get_rng_sync.argtypes = [V, c_u32p, c_ip, V]
     L.nirrt_batch_set_guidance.argtypes = [V, C.c_double, C.c_double]

@@ -55,9 +55,32 @@ def seed_state(seed):
     return st[1].astype(np.uint32), int(st[2])
 
 
+def rotation_to_world_frame_2d(x_start, x_goal):
+    """IRRTStar2D.RotationToWorldFrame (irrt_star_2d.py:153-161): one numpy SVD per problem."""
+    x_start = np.array(x_start).astype(np.float64)
+    x_goal = np.array(x_goal).astype(np.float64)
+    dx, dy = x_goal - x_start
+    L = math.hypot(dx, dy)
+    a1 = np.zeros((3, 1))
+    a1[:2, 0] = (x_goal - x_start) / L
+    e1 = np.array([[1.0], [0.0], [0.0]])
+    M = a1 @ e1.T
+    U, _, V_T = np.linalg.svd(M, True, True)
+    return U @ np.diag([1.0, 1.0, np.linalg.det(U) * np.linalg.det(V_T.T)]) @ V_T
+
+
+def py_seed_state(seed):
+    """(key[624] uint32, pos) of ``random.seed(seed)`` (CPython's MT19937)."""
+    import random
+    st = random.Random(seed).getstate()[1]
+    return np.array(st[:624], dtype=np.uint32), int(st[624])
+
+
 class BatchPlanner3D:
-    def __init__(self, problems, iter_max, step_len=10, clearance=2, seeds=None, rng_states=None,
-                 record_capacity=None, near_capacity=0, device=0, stream=None):
+    dim = 3
+
+    def __init__(self, problems, iter_max, step_len=10, clearance=None, seeds=None, rng_states=None,
+                 record_capacity=None, near_capacity=0, device=0, stream=None, py_rng_states=None):
         _lib.require_device()
         self.L = _lib.lib()
         self.E = len(problems)
@@ -69,7 +92,9 @@ class BatchPlanner3D:
         self.stream = C.c_void_p(stream) if stream else None
         self.variant = VARIANT_RRT_STAR
         self.mode = MODE_PLANNING
-        desc = _lib.BatchDesc(3, self.E, self.capacity, self.record_capacity, int(near_capacity), int(device))
+        if clearance is None:
+            clearance = 2 if self.dim == 3 else 3          # eval_planning_3d.py:76-77 / eval_planning_2d.py:80-81
+        desc = _lib.BatchDesc(self.dim, self.E, self.capacity, self.record_capacity, int(near_capacity), int(device))
         h = C.c_void_p()
         check(self.L.nirrt_batch_create(C.byref(desc), C.byref(h)))
         self.h = h
@@ -78,7 +103,11 @@ class BatchPlanner3D:
             if seeds is None:
                 seeds = list(range(self.E))
             rng_states = [seed_state(s) for s in seeds]
+            if self.dim == 2 and py_rng_states is None:
+                py_rng_states = [py_seed_state(s) for s in seeds]
         self.set_rng(rng_states)
+        if self.dim == 2 and py_rng_states is not None:
+            self.set_py_rng(py_rng_states)
 
     # ------------------------------------------------------------------ setup
     def _upload_problems(self, problems, step_len, clearance):
@@ -124,6 +153,18 @@ class BatchPlanner3D:
             key[e] = k; pos[e] = p
         check(self.L.nirrt_batch_set_rng(self.h, key.ctypes.data_as(_lib.c_u32p), ip(pos), self.stream))
 
+    def set_py_rng(self, rng_states):
+        """CPython ``random`` streams (2D informed sampling): [(key[624], pos)] per problem."""
+        key = np.zeros((self.E, 624), dtype=np.uint32); pos = np.zeros(self.E, dtype=np.int32)
+        for e, (k, p) in enumerate(rng_states):
+            key[e] = k; pos[e] = p
+        check(self.L.nirrt_batch_set_py_rng(self.h, key.ctypes.data_as(_lib.c_u32p), ip(pos), self.stream))
+
+    def get_py_rng(self):
+        key = np.zeros((self.E, 624), dtype=np.uint32); pos = np.zeros(self.E, dtype=np.int32)
+        check(self.L.nirrt_batch_get_py_rng_sync(self.h, key.ctypes.data_as(_lib.c_u32p), ip(pos), self.stream))
+        return [(key[e].copy(), int(pos[e])) for e in range(self.E)]
+
     def get_rng(self):
         key = np.zeros((self.E, 624), dtype=np.uint32); pos = np.zeros(self.E, dtype=np.int32)
         check(self.L.nirrt_batch_get_rng_sync(self.h, key.ctypes.data_as(_lib.c_u32p), ip(pos), self.stream))
@@ -133,7 +174,7 @@ class BatchPlanner3D:
         check(self.L.nirrt_batch_set_guidance(self.h, float(pc_sample_rate), float(pc_update_cost_ratio)))
 
     def set_cloud(self, env, points):
-        pts = f64(points).reshape(-1, 3)
+        pts = f64(points).reshape(-1, self.dim)
         check(self.L.nirrt_batch_set_cloud(self.h, int(env), dp(pts), len(pts), self.stream))
 
     def close(self):
@@ -152,13 +193,13 @@ class BatchPlanner3D:
         """vertices [count][capacity][3] f64, parents [count][capacity] int64, n [count]."""
         n = np.ascontiguousarray(n, dtype=np.int32)
         v = f64(vertices); p = np.ascontiguousarray(parents, dtype=np.int64)
-        assert v.shape == (len(n), self.capacity, 3) and p.shape == (len(n), self.capacity)
+        assert v.shape == (len(n), self.capacity, self.dim) and p.shape == (len(n), self.capacity)
         check(self.L.nirrt_batch_load_trees(self.h, int(env_begin), len(n), ip(n), dp(v), i64p(p), self.stream))
 
     def read_trees(self, env_begin=0, count=None, out=None):
         count = self.E - env_begin if count is None else count
         if out is None:
-            v = np.zeros((count, self.capacity, 3)); p = np.zeros((count, self.capacity), dtype=np.int64)
+            v = np.zeros((count, self.capacity, self.dim)); p = np.zeros((count, self.capacity), dtype=np.int64)
         else:
             v, p = out
         n = np.zeros(count, dtype=np.int32)
@@ -246,34 +287,34 @@ class BatchPlanner3D:
     def trace(self, near_stride=2048):
         E = self.E
         nearest = np.zeros(E, dtype=np.int32); new = np.zeros(E, dtype=np.int32); cnt = np.zeros(E, dtype=np.int32)
-        near = np.zeros((E, near_stride), dtype=np.int32); xr = np.zeros((E, 3))
+        near = np.zeros((E, near_stride), dtype=np.int32); xr = np.zeros((E, self.dim))
         check(self.L.nirrt_batch_read_trace_sync(self.h, ip(nearest), ip(new), ip(cnt), ip(near), near_stride, dp(xr), self.stream))
         return nearest, new, cnt, near, xr
 
     # ------------------------------------------------------------------ stand-alone predicates
     def collide_edges(self, env, edges):
-        e = f64(edges).reshape(-1, 6)
+        e = f64(edges).reshape(-1, 2 * self.dim)
         out = np.zeros(len(e), dtype=np.uint8)
         check(self.L.nirrt_collide_edges_sync(self.h, int(env), dp(e), len(e), u8p(out), self.stream))
         return out.astype(bool)
 
     def points_inside_obs(self, env, pts):
-        p = f64(pts).reshape(-1, 3); out = np.zeros(len(p), dtype=np.uint8)
+        p = f64(pts).reshape(-1, self.dim); out = np.zeros(len(p), dtype=np.uint8)
         check(self.L.nirrt_points_check_sync(self.h, int(env), 0, dp(p), len(p), u8p(out), self.stream))
         return out.astype(bool)
 
     def points_valid(self, env, pts):
-        p = f64(pts).reshape(-1, 3); out = np.zeros(len(p), dtype=np.uint8)
+        p = f64(pts).reshape(-1, self.dim); out = np.zeros(len(p), dtype=np.uint8)
         check(self.L.nirrt_points_check_sync(self.h, int(env), 1, dp(p), len(p), u8p(out), self.stream))
         return out.astype(bool)
 
     def nearest(self, env, queries):
-        q = f64(queries).reshape(-1, 3); out = np.zeros(len(q), dtype=np.int64)
+        q = f64(queries).reshape(-1, self.dim); out = np.zeros(len(q), dtype=np.int64)
         check(self.L.nirrt_nearest_sync(self.h, int(env), dp(q), len(q), i64p(out), self.stream))
         return out
 
     def within(self, env, q, r, cap=2048):
-        q = f64(q).reshape(3); out = np.zeros(cap, dtype=np.int64)
+        q = f64(q).reshape(self.dim); out = np.zeros(cap, dtype=np.int64)
         m = check(self.L.nirrt_within_sync(self.h, int(env), dp(q), float(r), i64p(out), cap, self.stream))
         return out[:min(m, cap)]
 
@@ -291,6 +332,42 @@ class BatchPlanner3D:
         ms = C.c_float(0); nbytes = C.c_int64(0)
         check(self.L.nirrt_batch_time_scan_sync(self.h, int(which), int(reps), C.byref(ms), C.byref(nbytes), self.stream))
         return ms.value, nbytes.value
+
+
+class BatchPlanner2D(BatchPlanner3D):
+    """E independent 2D planning problems (RRTStar2D / IRRTStar2D / N(I)RRTStarPNG2D loop bodies,
+    path_planning_classes/*.py).  ``problems[i]['env_dict']`` follows the reference's 2D json schema
+    (rrt_env.py:1-20): env_dims (height, width), circle_obstacles [x,y,r], rectangle_obstacles [x,y,w,h]."""
+    dim = 2
+
+    def _upload_problems(self, problems, step_len, clearance):
+        E = self.E
+        start = np.zeros((E, 2)); goal = np.zeros((E, 2)); rng4 = np.zeros((E, 4))
+        sl = np.zeros(E); sr = np.zeros(E); cl = np.zeros(E)
+        nc = np.zeros(E, dtype=np.int32); nr = np.zeros(E, dtype=np.int32)
+        circles = np.zeros((E, MAX_OBSTACLES, 3)); rects = np.zeros((E, MAX_OBSTACLES, 4))
+        rot = np.zeros((E, 9))
+        step_len = np.broadcast_to(np.asarray(step_len, dtype=np.float64), (E,))
+        clearance = np.broadcast_to(np.asarray(clearance, dtype=np.float64), (E,))
+        for e, p in enumerate(problems):
+            ed = p["env_dict"]
+            start[e] = np.array(p["x_start"]).astype(np.float64)
+            goal[e] = np.array(p["x_goal"]).astype(np.float64)
+            h, w = ed["env_dims"]                         # rrt_env.py:6-8
+            rng4[e] = [0, w, 0, h]
+            sl[e], sr[e], cl[e] = step_len[e], float(p["search_radius"]), clearance[e]
+            c = np.asarray(ed["circle_obstacles"], dtype=np.float64).reshape(-1, 3)
+            r = np.asarray(ed["rectangle_obstacles"], dtype=np.float64).reshape(-1, 4)
+            if len(c) > MAX_OBSTACLES or len(r) > MAX_OBSTACLES:
+                raise ValueError(f"problem {e}: more than {MAX_OBSTACLES} obstacles of one type")
+            nc[e], nr[e] = len(c), len(r)
+            circles[e, :len(c)] = c
+            rects[e, :len(r)] = r
+            rot[e] = (rotation_to_world_frame_2d(start[e], goal[e]) if np.any(start[e] != goal[e]) else np.eye(3)).reshape(9)
+        self.start, self.goal = start, goal
+        table = near_radius_table(self.capacity, 2)
+        check(self.L.nirrt_batch_set_problems_2d(self.h, dp(start), dp(goal), dp(sl), dp(sr), dp(cl), dp(rng4),
+                                                 ip(nc), dp(circles), ip(nr), dp(rects), dp(table), dp(rot), self.stream))
 
 
 def fps_f64(points, npoint, start=0, stream=None):

@@ -27,6 +27,7 @@
 #include "../../include/nirrt_b200.h"
 #include "exact_math.cuh"
 #include "geometry3d.cuh"
+#include "geometry2d.cuh"
 #include "mt19937.cuh"
 
 using namespace nirrt;
@@ -99,7 +100,10 @@ struct View {
     double *vx, *vy, *vz;
     Node *nodes;
     Geom3 *geom;
+    Geom2 *geom2;    // 2D worlds (dim == 2)
+    int dim;
     MtState *mt;
+    MtState *mt_py;  // CPython `random` stream (2D informed sampling, irrt_star_2d.py:146-151)
     EnvCtl *ctl;
     double *part_s;
     int *part_i;
@@ -131,7 +135,47 @@ __device__ __forceinline__ void store_parent(Node *p, long long parent) {
     __stcg(reinterpret_cast<long long *>(p) + 3, parent);
 }
 
-// RRTBase3D.cost (rrt_base_3d.py:60-67): leaf -> root, math.hypot per edge, summed in that order
+// ---- dimension traits: which obstacle table, and which of the reference's norms evaluates what
+template <int D> struct GeomOf;
+template <> struct GeomOf<3> {
+    typedef Geom3 type;
+    static __host__ __device__ __forceinline__ Geom3 *ptr(const View &v, int e) { return v.geom + e; }
+};
+template <> struct GeomOf<2> {
+    typedef Geom2 type;
+    static __host__ __device__ __forceinline__ Geom2 *ptr(const View &v, int e) { return v.geom2 + e; }
+};
+template <int D> __device__ __forceinline__ void stage_geom(typename GeomOf<D>::type *dst, const View &v, int e) {
+    typedef typename GeomOf<D>::type G;
+    for (int i = threadIdx.x; i < (int)(sizeof(G) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(dst)[i] = reinterpret_cast<const double *>(GeomOf<D>::ptr(v, e))[i];
+}
+// math.hypot(dx, dy[, dz]): cost() edges, Line(), steer distance (rrt_base_{2,3}d.py)
+template <int D> __device__ __forceinline__ double edge_len(double dx, double dy, double dz) {
+    return D == 3 ? hypot3(dx, dy, dz) : hypot2(dx, dy);
+}
+// squared distance used by the scans: exact decision value in 3D, pre-filter in 2D
+template <int D> __device__ __forceinline__ double scan_sq(double dx, double dy, double dz) {
+    return D == 3 ? sq3_rows(dx, dy, dz) : XADD(XMUL(dx, dx), XMUL(dy, dy));
+}
+// the vectorised distance of Near / ChooseParent / Rewire / goal scans:
+// np.linalg.norm(axis=-1) in 3D (rrt_star_3d.py:82,94,103,136), np.hypot in 2D (rrt_star_2d.py:82,94,103,135)
+template <int D> __device__ __forceinline__ double vec_dist(double dx, double dy, double dz) {
+    return D == 3 ? rownorm3(dx, dy, dz) : np_hypot(dx, dy);
+}
+// np.linalg.norm(path[1:] - path[:-1], axis=1) rows (rrt_base_{2,3}d.py get_path_len)
+template <int D> __device__ __forceinline__ double row_norm(double dx, double dy, double dz) {
+    return D == 3 ? rownorm3(dx, dy, dz) : rownorm2(dx, dy);
+}
+// 2D scans decide with np.hypot (not correctly rounded, < 1 ulp): a squared-distance pre-filter
+// with a 2^-49 relative safety band selects the few candidates that need the exact evaluation.
+__device__ __forceinline__ double hypot_band_sq(double h) {
+    return __dmul_ru(__dmul_ru(h, h), 1.0000000000000018);
+}
+
+// RRTBase{2,3}D.cost (rrt_base_3d.py:60-67, rrt_base_2d.py:54-61): leaf -> root, math.hypot per
+// edge, summed in that order
+template <int D>
 __device__ double cost_walk(const Node *nodes, int idx) {
     double c = 0.0;
     if (idx == 0) return c;
@@ -139,7 +183,7 @@ __device__ double cost_walk(const Node *nodes, int idx) {
     while (idx != 0) {
         const int par = (int)cur.parent;
         const Node p = load_node(nodes + par);
-        c = XADD(c, hypot3(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z)));
+        c = XADD(c, edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z)));
         idx = par;
         cur = p;
     }
@@ -207,7 +251,7 @@ __device__ __forceinline__ void push_record(const View &v, EnvCtl *c, int e, dou
 //   IRRTStar3D.SampleInformedSubset      irrt_star_3d.py:117-157
 //   NIRRTStarPNG3D.generate_random_node  nirrt_star_png_3d.py:99-130
 //   planning_random record/phase rules   irrt_star_3d.py:245-331
-__device__ void sample_free(const Geom3 &g, MtStream &rng, double *out) {
+__device__ void sample_free(const Geom3 &g, MtStream &rng, MtStream &, double *out) {
     const double x0 = XADD(g.range[0], g.clearance), x1 = XSUB(g.range[1], g.clearance);
     const double y0 = XADD(g.range[2], g.clearance), y1 = XSUB(g.range[3], g.clearance);
     const double z0 = XADD(g.range[4], g.clearance), z1 = XSUB(g.range[5], g.clearance);
@@ -217,8 +261,18 @@ __device__ void sample_free(const Geom3 &g, MtStream &rng, double *out) {
         out[2] = rng.uniform(z0, z1);
     } while (point_inside_obs(g, out));
 }
+// RRTBase2D.SampleFree (rrt_base_2d.py:46-52)
+__device__ void sample_free(const Geom2 &g, MtStream &rng, MtStream &, double *out) {
+    const double x0 = XADD(g.range[0], g.clearance), x1 = XSUB(g.range[1], g.clearance);
+    const double y0 = XADD(g.range[2], g.clearance), y1 = XSUB(g.range[3], g.clearance);
+    out[2] = 0.0;
+    do {
+        out[0] = rng.uniform(x0, x1);
+        out[1] = rng.uniform(y0, y1);
+    } while (point_inside_obs(g, out));
+}
 
-__device__ void sample_informed(const Geom3 &g, const EnvCtl *c, MtStream &rng, double c_max, double *out) {
+__device__ void sample_informed(const Geom3 &g, const EnvCtl *c, MtStream &rng, MtStream &, double c_max, double *out) {
     const double c2 = XSUB(XMUL(c_max, c_max), XMUL(c->c_min, c->c_min));
     const double eps = (c2 < 0.0) ? 1e-6 : 0.0;
     double r[3], M[9];
@@ -241,11 +295,33 @@ __device__ void sample_informed(const Geom3 &g, const EnvCtl *c, MtStream &rng, 
         if (point_valid(g, out)) break;
     }
 }
+// IRRTStar2D.SampleInformedSubset / SampleUnitBall (irrt_star_2d.py:121-151): the unit-disc draw
+// consumes the CPython `random` stream (py), node = (C L) x_ball + x_center evaluated as numpy's
+// dgemv does it (fma(M0, x, M1 * y) + centre, probed).
+__device__ void sample_informed(const Geom2 &g, const EnvCtl *c, MtStream &, MtStream &py, double c_max, double *out) {
+    const double c2 = XSUB(XMUL(c_max, c_max), XMUL(c->c_min, c->c_min));
+    const double eps = (c2 < 0.0) ? 1e-6 : 0.0;
+    const double r0 = XDIV(c_max, 2.0), r1 = XDIV(XSQRT(XADD(c2, eps)), 2.0);
+    const double M00 = XMUL(c->C[0], r0), M01 = XMUL(c->C[1], r1), M10 = XMUL(c->C[3], r0), M11 = XMUL(c->C[4], r1);
+    out[2] = 0.0;
+    for (;;) {
+        double x, y;
+        do {
+            x = py.uniform(-1.0, 1.0);
+            y = py.uniform(-1.0, 1.0);
+        } while (!(XADD(XMUL(x, x), XMUL(y, y)) < 1.0));
+        out[0] = XADD(XFMA(M00, x, XMUL(M01, y)), c->center[0]);
+        out[1] = XADD(XFMA(M10, x, XMUL(M11, y)), c->center[1]);
+        if (point_valid(g, out)) break;
+    }
+}
 
+template <int D>
 __global__ void __launch_bounds__(128) k_top(View v) {
+    typedef typename GeomOf<D>::type G;
     const int e = blockIdx.x;
     EnvCtl *c = v.ctl + e;
-    __shared__ Geom3 g;
+    __shared__ G g;
     __shared__ double sm_s[4];
     __shared__ int sm_i[4];
     const int state = c->state, budget = c->budget;
@@ -253,9 +329,9 @@ __global__ void __launch_bounds__(128) k_top(View v) {
         if (threadIdx.x == 0) c->go = 0;
         return;
     }
-    for (int i = threadIdx.x; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
-        reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + e)[i];
+    stage_geom<D>(&g, v, e);
     mt_prepare_next(v.mt + e, 160);
+    if (D == 2 && fam_informed(v.variant)) mt_prepare_next(v.mt_py + e, 160);
     __syncthreads();
 
     double c_best = XINF;
@@ -267,8 +343,8 @@ __global__ void __launch_bounds__(128) k_top(View v) {
         for (int k = threadIdx.x; k < n_sol; k += blockDim.x) {
             const int idx = sol[k];
             const Node nd = load_node(nodes + idx);
-            const double val = XADD(cost_walk(nodes, idx),
-                                    hypot3(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z)));
+            const double val = XADD(cost_walk<D>(nodes, idx),
+                                    edge_len<D>(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z)));
             lexmin(bs, bk, val, k);
         }
         block_lexmin(bs, bk, sm_s, sm_i);
@@ -300,6 +376,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
     c->resumed = 0;
 
     MtStream rng(v.mt + e);
+    MtStream py(D == 2 ? v.mt_py + e : v.mt + e);
     double out[3];
     bool done = false;
     if (fam_cloud(v.variant)) {
@@ -312,10 +389,11 @@ __global__ void __launch_bounds__(128) k_top(View v) {
         }
     }
     if (!done) {
-        if (fam_informed(v.variant) && c_best < XINF) sample_informed(g, c, rng, c_best, out);
-        else sample_free(g, rng, out);
+        if (fam_informed(v.variant) && c_best < XINF) sample_informed(g, c, rng, py, c_best, out);
+        else sample_free(g, rng, py, out);
     }
     rng.flush();
+    if (D == 2) py.flush();
     c->x_rand[0] = out[0]; c->x_rand[1] = out[1]; c->x_rand[2] = out[2];
     c->go = 1;
 }
@@ -324,7 +402,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
 // k_nearest: RRTBase3D.nearest_neighbor (rrt_base_3d.py:100-113)
 //   argmin_i sqrt((dx*dx + dy*dy) + dz*dz), first index on ties.  The square root is only taken
 //   for running-minimum candidates: s2 >= RU(best_s*best_s) implies sqrt_rn(s2) >= best_s.
-template <bool kForce>
+template <int D, bool kForce>
 __global__ void __launch_bounds__(256) k_nearest(View v) {
     const int e = blockIdx.y;
     const EnvCtl *c = v.ctl + e;
@@ -333,18 +411,27 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
     const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 1) & ~1;
     const int beg = blockIdx.x * per;
     const int end = min(n, beg + per);
-    const double *X = v.vx + (size_t)e * v.stride, *Y = v.vy + (size_t)e * v.stride, *Z = v.vz + (size_t)e * v.stride;
+    const double *X = v.vx + (size_t)e * v.stride, *Y = v.vy + (size_t)e * v.stride;
+    const double *Z = D == 3 ? v.vz + (size_t)e * v.stride : nullptr;
     const double qx = c->x_rand[0], qy = c->x_rand[1], qz = c->x_rand[2];
     double best_s = XINF, T = XINF;
     int best_i = INT_MAX;
 
+    // 3D: argmin of sqrt((dx*dx + dy*dy) + dz*dz); the square root is only taken for running-minimum
+    // candidates (s2 >= RU(best*best) implies sqrt_rn(s2) >= best).
+    // 2D: argmin of np.hypot(dx, dy) (rrt_base_2d.py:105-106); evaluated only inside the band.
 #define NEAREST_ONE(xx, yy, zz, ii)                                                   \
     {                                                                                 \
-        const double dx = XSUB(qx, xx), dy = XSUB(qy, yy), dz = XSUB(qz, zz);         \
-        const double s2 = sq3_rows(dx, dy, dz);                                       \
-        if (s2 < T) {                                                                 \
-            const double s = XSQRT(s2);                                               \
-            if (s < best_s) { best_s = s; best_i = (ii); T = __dmul_ru(s, s); }       \
+        const double dx = XSUB(qx, xx), dy = XSUB(qy, yy), dz = D == 3 ? XSUB(qz, zz) : 0.0; \
+        const double s2 = scan_sq<D>(dx, dy, dz);                                     \
+        if (D == 3) {                                                                 \
+            if (s2 < T) {                                                             \
+                const double s = XSQRT(s2);                                           \
+                if (s < best_s) { best_s = s; best_i = (ii); T = __dmul_ru(s, s); }   \
+            }                                                                         \
+        } else if (s2 <= T) {                                                         \
+            const double s = np_hypot(dx, dy);                                        \
+            if (s < best_s) { best_s = s; best_i = (ii); T = hypot_band_sq(s); }      \
         }                                                                             \
     }
     const int step = 2 * blockDim.x;
@@ -352,10 +439,13 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
     for (; i + step < end; i += 2 * step) {   // two independent 16-byte loads per array in flight
         const double2 xa = __ldg(reinterpret_cast<const double2 *>(X + i));
         const double2 ya = __ldg(reinterpret_cast<const double2 *>(Y + i));
-        const double2 za = __ldg(reinterpret_cast<const double2 *>(Z + i));
         const double2 xb = __ldg(reinterpret_cast<const double2 *>(X + i + step));
         const double2 yb = __ldg(reinterpret_cast<const double2 *>(Y + i + step));
-        const double2 zb = __ldg(reinterpret_cast<const double2 *>(Z + i + step));
+        double2 za = make_double2(0.0, 0.0), zb = za;
+        if (D == 3) {
+            za = __ldg(reinterpret_cast<const double2 *>(Z + i));
+            zb = __ldg(reinterpret_cast<const double2 *>(Z + i + step));
+        }
         NEAREST_ONE(xa.x, ya.x, za.x, i)
         NEAREST_ONE(xa.y, ya.y, za.y, i + 1)          // i+1 < i+step < end
         NEAREST_ONE(xb.x, yb.x, zb.x, i + step)
@@ -364,7 +454,8 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
     for (; i < end; i += step) {
         const double2 xa = __ldg(reinterpret_cast<const double2 *>(X + i));
         const double2 ya = __ldg(reinterpret_cast<const double2 *>(Y + i));
-        const double2 za = __ldg(reinterpret_cast<const double2 *>(Z + i));
+        double2 za = make_double2(0.0, 0.0);
+        if (D == 3) za = __ldg(reinterpret_cast<const double2 *>(Z + i));
         NEAREST_ONE(xa.x, ya.x, za.x, i)
         if (i + 1 < end) NEAREST_ONE(xa.y, ya.y, za.y, i + 1)
     }
@@ -387,9 +478,11 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_steer: argmin finish + new_state (rrt_star_3d.py:67-78) + steer-edge collision
-//          + duplicate guard / vertex insert (rrt_star_3d.py:40-51) + Near radius (rrt_star_3d.py:134)
+// k_steer: argmin finish + new_state (rrt_star_3d.py:67-78 / rrt_star_2d.py:67-78) + steer-edge
+//          collision + duplicate guard / vertex insert (:40-51) + Near radius (:134 / :133)
+template <int D>
 __global__ void __launch_bounds__(32) k_steer(View v) {
+    typedef typename GeomOf<D>::type G;
     const int e = blockIdx.x;
     EnvCtl *c = v.ctl + e;
     if (!c->go) return;
@@ -399,18 +492,29 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
     warp_lexmin(bs, bi);
     const int nearest = __shfl_sync(0xffffffffu, bi, 0);
     Node *nodes = v.nodes + (size_t)e * v.stride;
-    const Geom3 &g = v.geom[e];
+    const G &g = *GeomOf<D>::ptr(v, e);
     const Node nn = load_node(nodes + nearest);
     const double xn[3] = {nn.x, nn.y, nn.z};
     // every lane computes the same x_new (cheap, avoids broadcasts)
-    const double d0 = XSUB(c->x_rand[0], xn[0]), d1 = XSUB(c->x_rand[1], xn[1]), d2 = XSUB(c->x_rand[2], xn[2]);
-    double dist = hypot3(d0, d1, d2);
-    double dir[3] = {0.0, 0.0, 0.0};
-    if (dist != 0.0) { dir[0] = XDIV(d0, dist); dir[1] = XDIV(d1, dist); dir[2] = XDIV(d2, dist); }
-    if (!(dist < c->step_len)) dist = c->step_len;   // min(step_len, dist)
+    const double d0 = XSUB(c->x_rand[0], xn[0]), d1 = XSUB(c->x_rand[1], xn[1]), d2 = D == 3 ? XSUB(c->x_rand[2], xn[2]) : 0.0;
+    double dist = edge_len<D>(d0, d1, d2);
     double xnew[3];
-    for (int i = 0; i < 3; i++) xnew[i] = XADD(xn[i], XMUL(dist, dir[i]));
-    const int m = g.n_balls + g.n_boxes;
+    if (D == 3) {
+        double dir[3] = {0.0, 0.0, 0.0};
+        if (dist != 0.0) { dir[0] = XDIV(d0, dist); dir[1] = XDIV(d1, dist); dir[2] = XDIV(d2, dist); }
+        if (!(dist < c->step_len)) dist = c->step_len;   // min(step_len, dist)
+        for (int i = 0; i < 3; i++) xnew[i] = XADD(xn[i], XMUL(dist, dir[i]));
+    } else {
+        // theta = math.atan2(dy, dx); node_new = start + dist * [cos(theta), sin(theta)]
+        const double theta = cr_atan2(d1, d0);
+        if (!(dist < c->step_len)) dist = c->step_len;
+        double sn, cs;
+        cr_sincos(theta, &sn, &cs);
+        xnew[0] = XADD(xn[0], XMUL(dist, cs));
+        xnew[1] = XADD(xn[1], XMUL(dist, sn));
+        xnew[2] = 0.0;
+    }
+    const int m = n_obstacles(g);
     bool hit = false;
     for (int k = lane; k < m; k += 32) hit = hit || seg_hits_obstacle(g, k, xn, xnew);
     hit = __any_sync(0xffffffffu, hit);
@@ -422,38 +526,43 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
     if (hit) { c->skip = 1; c->new_idx = -1; return; }
     c->skip = 0;
     int new_idx;
-    if (vecnorm3(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2])) < 1e-8) {
+    const double dup = D == 3 ? vecnorm3(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2]))
+                              : vecnorm2(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]));
+    if (dup < 1e-8) {
         // "do not create a new node if it is actually the same point" (rrt_star_3d.py:41-45)
         xnew[0] = xn[0]; xnew[1] = xn[1]; xnew[2] = xn[2];
         new_idx = nearest;
-        c->curr_cost = cost_walk(nodes, nearest);
+        c->curr_cost = cost_walk<D>(nodes, nearest);
     } else {
         new_idx = c->n;
         if (new_idx >= v.cap) { c->err |= ERR_VERTEX_OVERFLOW; c->skip = 1; c->new_idx = -1; return; }
         const size_t o = (size_t)e * v.stride + new_idx;
-        v.vx[o] = xnew[0]; v.vy[o] = xnew[1]; v.vz[o] = xnew[2];
+        v.vx[o] = xnew[0]; v.vy[o] = xnew[1];
+        if (D == 3) v.vz[o] = xnew[2];
         Node nd; nd.x = xnew[0]; nd.y = xnew[1]; nd.z = xnew[2]; nd.parent = nearest;
         nodes[new_idx] = nd;
         c->n = new_idx + 1;
         c->inserted = 1;
         c->tree_changed = 1;
-        c->curr_cost = XADD(cost_walk(nodes, nearest),
-                            hypot3(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2])));
+        c->curr_cost = XADD(cost_walk<D>(nodes, nearest),
+                            edge_len<D>(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2])));
     }
     c->new_idx = new_idx;
     c->x_new[0] = xnew[0]; c->x_new[1] = xnew[1]; c->x_new[2] = xnew[2];
     double r = XMUL(c->search_radius, v.near_table[c->n]);
-    if (c->step_len < r) r = c->step_len;            // min(gamma*(log n/n)^(1/3), step_len)
+    if (c->step_len < r) r = c->step_len;            // min(gamma * f(n), step_len)
     c->r = r;
-    c->T_near = sqrt_le_threshold(r);
+    c->T_near = D == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_near: the distance part of find_near_neighbors (rrt_star_3d.py:134-137):
-//   np.where(np.linalg.norm(node_new - vertices, axis=-1) <= r)  <=>  sq <= T_near  (exact, see
-//   sqrt_le_threshold).  Matches are sparse (tens out of 1e5) and are appended unordered;
-//   k_expand sorts them back into ascending index order.
-template <bool kForce>
+// k_near: the distance part of find_near_neighbors (rrt_star_3d.py:134-137 / rrt_star_2d.py:133-136):
+//   3D  np.where(np.linalg.norm(node_new - vertices, axis=-1) <= r)  <=>  sq <= T_near (exact, see
+//       sqrt_le_threshold)
+//   2D  np.where(np.hypot(dx, dy) <= r): squared pre-filter, exact np.hypot inside the band.
+// Matches are sparse (tens out of 1e5) and are appended unordered; k_expand sorts them back into
+// ascending index order.
+template <int D, bool kForce>
 __global__ void __launch_bounds__(256) k_near(View v) {
     const int e = blockIdx.y;
     EnvCtl *c = v.ctl + e;
@@ -462,15 +571,16 @@ __global__ void __launch_bounds__(256) k_near(View v) {
     const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 1) & ~1;
     const int beg = blockIdx.x * per;
     const int end = min(n, beg + per);
-    const double *X = v.vx + (size_t)e * v.stride, *Y = v.vy + (size_t)e * v.stride, *Z = v.vz + (size_t)e * v.stride;
+    const double *X = v.vx + (size_t)e * v.stride, *Y = v.vy + (size_t)e * v.stride;
+    const double *Z = D == 3 ? v.vz + (size_t)e * v.stride : nullptr;
     const double qx = c->x_new[0], qy = c->x_new[1], qz = c->x_new[2];
-    const double T = c->T_near;
+    const double T = c->T_near, r = c->r;
     int *cand = v.cand + (size_t)e * v.near_cap;
 
 #define NEAR_ONE(xx, yy, zz, ii)                                                      \
     {                                                                                 \
-        const double dx = XSUB(qx, xx), dy = XSUB(qy, yy), dz = XSUB(qz, zz);         \
-        if (sq3_rows(dx, dy, dz) <= T) {                                              \
+        const double dx = XSUB(qx, xx), dy = XSUB(qy, yy), dz = D == 3 ? XSUB(qz, zz) : 0.0; \
+        if (scan_sq<D>(dx, dy, dz) <= T && (D == 3 || np_hypot(dx, dy) <= r)) {       \
             const int slot = atomicAdd(&c->cand_cnt, 1);                              \
             if (slot < v.near_cap) cand[slot] = (ii);                                 \
         }                                                                             \
@@ -480,10 +590,13 @@ __global__ void __launch_bounds__(256) k_near(View v) {
     for (; i + step < end; i += 2 * step) {
         const double2 xa = __ldg(reinterpret_cast<const double2 *>(X + i));
         const double2 ya = __ldg(reinterpret_cast<const double2 *>(Y + i));
-        const double2 za = __ldg(reinterpret_cast<const double2 *>(Z + i));
         const double2 xb = __ldg(reinterpret_cast<const double2 *>(X + i + step));
         const double2 yb = __ldg(reinterpret_cast<const double2 *>(Y + i + step));
-        const double2 zb = __ldg(reinterpret_cast<const double2 *>(Z + i + step));
+        double2 za = make_double2(0.0, 0.0), zb = za;
+        if (D == 3) {
+            za = __ldg(reinterpret_cast<const double2 *>(Z + i));
+            zb = __ldg(reinterpret_cast<const double2 *>(Z + i + step));
+        }
         NEAR_ONE(xa.x, ya.x, za.x, i)
         NEAR_ONE(xa.y, ya.y, za.y, i + 1)
         NEAR_ONE(xb.x, yb.x, zb.x, i + step)
@@ -492,7 +605,8 @@ __global__ void __launch_bounds__(256) k_near(View v) {
     for (; i < end; i += step) {
         const double2 xa = __ldg(reinterpret_cast<const double2 *>(X + i));
         const double2 ya = __ldg(reinterpret_cast<const double2 *>(Y + i));
-        const double2 za = __ldg(reinterpret_cast<const double2 *>(Z + i));
+        double2 za = make_double2(0.0, 0.0);
+        if (D == 3) za = __ldg(reinterpret_cast<const double2 *>(Z + i));
         NEAR_ONE(xa.x, ya.x, za.x, i)
         if (i + 1 < end) NEAR_ONE(xa.y, ya.y, za.y, i + 1)
     }
@@ -524,6 +638,7 @@ __device__ void bitonic_sort_int(int *a, int n_pow2) {
 
 // RRT* eval driver: best goal parent over the incrementally maintained goal-candidate list and the
 // numpy-ordered path length (rrt_base_3d.py:69-91).  Called by all threads; result in thread 0.
+template <int D>
 __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nodes, double *sm_s, int *sm_i) {
     const int ng = c->n_goal;
     if (ng == 0) { if (threadIdx.x == 0) c->last_gp = -1; return XINF; }
@@ -532,7 +647,7 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
     double bs = XINF; int bk = INT_MAX;
     for (int k = threadIdx.x; k < ng; k += blockDim.x) {
         const double d = gd[k];
-        const double val = (d < XINF) ? XADD(cost_walk(nodes, gi[k]), d) : XINF;
+        const double val = (d < XINF) ? XADD(cost_walk<D>(nodes, gi[k]), d) : XINF;
         lexmin(bs, bk, val, k);
     }
     block_lexmin(bs, bk, sm_s, sm_i);
@@ -547,12 +662,12 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
         else {
             double *seg = v.pathseg + (size_t)e * v.path_cap;
             Node cur = load_node(nodes + gp);
-            seg[M - 1] = rownorm3(XSUB(c->goal[0], cur.x), XSUB(c->goal[1], cur.y), XSUB(c->goal[2], cur.z));
+            seg[M - 1] = row_norm<D>(XSUB(c->goal[0], cur.x), XSUB(c->goal[1], cur.y), XSUB(c->goal[2], cur.z));
             int idx = gp;
             for (int j = 0; idx != 0; j++) {
                 const int par = (int)cur.parent;
                 const Node p = load_node(nodes + par);
-                seg[M - 2 - j] = rownorm3(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
+                seg[M - 2 - j] = row_norm<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
                 idx = par; cur = p;
             }
             len = (M == 1) ? seg[0] : XADD(seg[0], pairwise_sum(seg + 1, M - 1));
@@ -561,11 +676,13 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
     return len;
 }
 
+template <int D>
 __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
+    typedef typename GeomOf<D>::type G;
     const int e = blockIdx.x;
     EnvCtl *c = v.ctl + e;
     if (!c->go) return;
-    __shared__ Geom3 g;
+    __shared__ G g;
     __shared__ int s_cand[kNearSmem];
     __shared__ int s_near[kNearSmem];
     __shared__ double s_d[kNearSmem];
@@ -577,8 +694,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
     const int tid = threadIdx.x;
 
     if (!c->skip) {
-        for (int i = tid; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
-            reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + e)[i];
+        stage_geom<D>(&g, v, e);
         int cnt = c->cand_cnt;
         if (cnt > v.near_cap || cnt > kNearSmem) {
             if (tid == 0) c->err |= ERR_NEAR_OVERFLOW;
@@ -605,7 +721,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
                 const Node nd = load_node(nodes + idx);
                 const double p1[3] = {nd.x, nd.y, nd.z};
                 keep = (idx != new_idx) && !seg_collides(g, xnew, p1);
-                d = rownorm3(XSUB(xnew[0], p1[0]), XSUB(xnew[1], p1[1]), XSUB(xnew[2], p1[2]));
+                d = vec_dist<D>(XSUB(xnew[0], p1[0]), XSUB(xnew[1], p1[1]), XSUB(xnew[2], p1[2]));
             }
             // block-ordered positions: warp ballots + warp-count prefix through smem
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -632,7 +748,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
         if (m > 0) {
             // ---- choose_parent
             double bs = XINF; int bk = INT_MAX;
-            for (int k = tid; k < m; k += blockDim.x) lexmin(bs, bk, XADD(cost_walk(nodes, s_near[k]), s_d[k]), k);
+            for (int k = tid; k < m; k += blockDim.x) lexmin(bs, bk, XADD(cost_walk<D>(nodes, s_near[k]), s_d[k]), k);
             block_lexmin(bs, bk, sm_s, sm_i);
             if (tid == 0) {
                 if (bs < c->curr_cost) { store_parent(nodes + new_idx, s_near[bk]); c->tree_changed = 1; }
@@ -641,14 +757,14 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
             __syncthreads();
             // ---- rewire: sequential semantics, parallel walks; after each re-parenting the
             // remaining neighbours are re-evaluated so later ones see earlier changes
-            if (tid == 0) s_cnew = cost_walk(nodes, new_idx);
+            if (tid == 0) s_cnew = cost_walk<D>(nodes, new_idx);
             __syncthreads();
             const double c_new = s_cnew;
             int start = 0;
             while (start < m) {
                 int first = INT_MAX;
                 for (int k = start + tid; k < m; k += blockDim.x) {
-                    if (cost_walk(nodes, s_near[k]) > XADD(c_new, s_d[k])) { first = k; break; }
+                    if (cost_walk<D>(nodes, s_near[k]) > XADD(c_new, s_d[k])) { first = k; break; }
                 }
                 first = block_min_int(first, sm_i);
                 if (first == INT_MAX) break;
@@ -661,18 +777,20 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
         if (tid == 0) {
             if (fam_informed(v.variant)) {
                 // InGoalRegion (rrt_base_3d.py:93-95)
-                if (hypot3(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2])) < c->step_len &&
+                if (edge_len<D>(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2])) < c->step_len &&
                     !seg_collides(g, xnew, c->goal)) {
                     if (c->n_sol < v.sol_cap) v.sol[(size_t)e * v.sol_cap + c->n_sol] = new_idx;
                     else c->err |= ERR_SOL_OVERFLOW;
                     c->n_sol++;
                 }
             } else if (v.mode == NIRRT_MODE_PLANNING_RANDOM && c->inserted) {
-                const double s2 = sq3_rows(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2]));
-                if (s2 <= c->T_goal) {
+                const double gx = XSUB(c->goal[0], xnew[0]), gy = XSUB(c->goal[1], xnew[1]), gz = XSUB(c->goal[2], xnew[2]);
+                const double s2 = scan_sq<D>(gx, gy, gz);
+                // dist_to_goal <= step_len (rrt_star_3d.py:103-104 / rrt_star_2d.py:103-104)
+                if (s2 <= c->T_goal && (D == 3 || np_hypot(gx, gy) <= c->step_len)) {
                     const int k = c->n_goal;
                     v.gc_idx[(size_t)e * v.cap + k] = new_idx;
-                    v.gc_d[(size_t)e * v.cap + k] = seg_collides(g, xnew, c->goal) ? XINF : XSQRT(s2);
+                    v.gc_d[(size_t)e * v.cap + k] = seg_collides(g, xnew, c->goal) ? XINF : (D == 3 ? XSQRT(s2) : np_hypot(gx, gy));
                     c->n_goal = k + 1;
                 }
             }
@@ -687,7 +805,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
         const int changed = c->tree_changed;        // uniform: every thread reads before thread 0 clears it
         __syncthreads();
         if (changed) {
-            len = goal_path_len(v, c, e, nodes, sm_s, sm_i);
+            len = goal_path_len<D>(v, c, e, nodes, sm_s, sm_i);
         } else {
             len = c->last_len;
         }
@@ -720,14 +838,15 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
 // setup / IO kernels
 
 // builds the goal-candidate list of an existing tree in ascending index order (1 CTA / env)
+template <int D>
 __global__ void __launch_bounds__(256) k_goal_init(View v) {
+    typedef typename GeomOf<D>::type G;
     const int e = blockIdx.x;
     EnvCtl *c = v.ctl + e;
-    __shared__ Geom3 g;
+    __shared__ G g;
     __shared__ int s_wcnt[8];
     __shared__ int s_total;
-    for (int i = threadIdx.x; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
-        reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + e)[i];
+    stage_geom<D>(&g, v, e);
     if (threadIdx.x == 0) s_total = 0;
     __syncthreads();
     const int n = c->n;
@@ -739,8 +858,12 @@ __global__ void __launch_bounds__(256) k_goal_init(View v) {
         if (i < n) {
             const Node nd = load_node(nodes + i);
             const double p[3] = {nd.x, nd.y, nd.z};
-            const double s2 = sq3_rows(XSUB(c->goal[0], p[0]), XSUB(c->goal[1], p[1]), XSUB(c->goal[2], p[2]));
-            if (s2 <= c->T_goal) { keep = true; d = seg_collides(g, p, c->goal) ? XINF : XSQRT(s2); }
+            const double gx = XSUB(c->goal[0], p[0]), gy = XSUB(c->goal[1], p[1]), gz = XSUB(c->goal[2], p[2]);
+            const double s2 = scan_sq<D>(gx, gy, gz);
+            if (s2 <= c->T_goal && (D == 3 || np_hypot(gx, gy) <= c->step_len)) {
+                keep = true;
+                d = seg_collides(g, p, c->goal) ? XINF : (D == 3 ? XSQRT(s2) : np_hypot(gx, gy));
+            }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -813,53 +936,96 @@ __global__ void k_set_problems(View v, ProblemUpload u) {
     c->c_best = XINF; c->c_update = XINF; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
 }
 
-// AoS (reference layout) <-> device layout
-__global__ void k_scatter_tree(View v, int env, int n, const double *verts /*[cap][3]*/, const long long *parents) {
+struct ProblemUpload2 {
+    const double *start, *goal, *step_len, *search_radius, *clearance, *range, *circles, *rects, *rot_c;
+    const int *n_circles, *n_rects;
+};
+
+// 2D problems: RRTStar2D.__init__ arguments (rrt_star_2d.py:10-30) + Utils (rrt_utils_2d.py:5-17)
+__global__ void k_set_problems_2d(View v, ProblemUpload2 u) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E) return;
+    EnvCtl *c = v.ctl + e;
+    Geom2 *g = v.geom2 + e;
+    for (int i = 0; i < 2; i++) { c->start[i] = u.start[2 * e + i]; c->goal[i] = u.goal[2 * e + i]; }
+    c->start[2] = c->goal[2] = 0.0;
+    c->step_len = u.step_len[e];
+    c->search_radius = u.search_radius[e];
+    c->T_goal = hypot_band_sq(c->step_len);
+    c->c_min = hypot2(XSUB(c->goal[0], c->start[0]), XSUB(c->goal[1], c->start[1]));
+    for (int i = 0; i < 3; i++) c->center[i] = XDIV(XADD(c->start[i], c->goal[i]), 2.0);
+    for (int i = 0; i < 9; i++) c->C[i] = u.rot_c ? u.rot_c[9 * e + i] : ((i % 4) == 0 ? 1.0 : 0.0);
+    g->n_circles = u.n_circles[e]; g->n_rects = u.n_rects[e];
+    g->clearance = u.clearance[e];
+    for (int i = 0; i < 4; i++) g->range[i] = u.range[4 * e + i];
+    for (int k = 0; k < kMaxObs; k++) {
+        for (int i = 0; i < 3; i++) g->circles[k][i] = u.circles[((size_t)e * kMaxObs + k) * 3 + i];
+        for (int i = 0; i < 4; i++) g->rects[k][i] = u.rects[((size_t)e * kMaxObs + k) * 4 + i];
+    }
+    const size_t o = (size_t)e * v.stride;
+    v.vx[o] = c->start[0]; v.vy[o] = c->start[1];
+    Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = 0.0; nd.parent = 0;
+    v.nodes[o] = nd;
+    c->n = 1;
+    c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
+    c->state = ST_DONE; c->budget = 0; c->go = 0; c->n_rec = 0; c->err = 0; c->resumed = 0;
+    c->c_best = XINF; c->c_update = XINF; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
+}
+
+// AoS (reference layout, [cap][dim]) <-> device layout
+__global__ void k_scatter_tree(View v, int env, int n, const double *verts, const long long *parents) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int D = v.dim;
     const size_t o = (size_t)env * v.stride + i;
-    Node nd; nd.x = verts[3 * (size_t)i]; nd.y = verts[3 * (size_t)i + 1]; nd.z = verts[3 * (size_t)i + 2]; nd.parent = parents[i];
-    v.vx[o] = nd.x; v.vy[o] = nd.y; v.vz[o] = nd.z;
+    Node nd; nd.x = verts[D * (size_t)i]; nd.y = verts[D * (size_t)i + 1]; nd.z = D == 3 ? verts[D * (size_t)i + 2] : 0.0; nd.parent = parents[i];
+    v.vx[o] = nd.x; v.vy[o] = nd.y;
+    if (D == 3) v.vz[o] = nd.z;
     v.nodes[o] = nd;
     if (i == 0) { v.ctl[env].n = n; v.ctl[env].tree_changed = 1; }
 }
 __global__ void k_gather_tree(View v, int env, double *verts, long long *parents) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.cap) return;
+    const int D = v.dim;
     const int n = v.ctl[env].n;
     Node nd; nd.x = nd.y = nd.z = 0.0; nd.parent = 0;
     if (i < n) nd = v.nodes[(size_t)env * v.stride + i];
-    verts[3 * (size_t)i] = nd.x; verts[3 * (size_t)i + 1] = nd.y; verts[3 * (size_t)i + 2] = nd.z;
+    verts[D * (size_t)i] = nd.x; verts[D * (size_t)i + 1] = nd.y;
+    if (D == 3) verts[D * (size_t)i + 2] = nd.z;
     parents[i] = nd.parent;
 }
 
 // stand-alone predicates ---------------------------------------------------------------------------
+template <int D>
 __global__ void k_collide_edges(View v, int env, const double *edges, long long m, uint8_t *out) {
-    __shared__ Geom3 g;
-    for (int i = threadIdx.x; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
-        reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + env)[i];
+    __shared__ typename GeomOf<D>::type g;
+    stage_geom<D>(&g, v, env);
     __syncthreads();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-        double p0[3], p1[3];
-        for (int k = 0; k < 3; k++) { p0[k] = edges[6 * i + k]; p1[k] = edges[6 * i + 3 + k]; }
+        double p0[3] = {0.0, 0.0, 0.0}, p1[3] = {0.0, 0.0, 0.0};
+        for (int k = 0; k < D; k++) { p0[k] = edges[2 * D * i + k]; p1[k] = edges[2 * D * i + D + k]; }
         out[i] = seg_collides(g, p0, p1) ? 1 : 0;
     }
 }
+template <int D>
 __global__ void k_points_check(View v, int env, int kind, const double *pts, long long m, uint8_t *out) {
-    __shared__ Geom3 g;
-    for (int i = threadIdx.x; i < (int)(sizeof(Geom3) / sizeof(double)); i += blockDim.x)
-        reinterpret_cast<double *>(&g)[i] = reinterpret_cast<const double *>(v.geom + env)[i];
+    __shared__ typename GeomOf<D>::type g;
+    stage_geom<D>(&g, v, env);
     __syncthreads();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-        const double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        double p[3] = {0.0, 0.0, 0.0};
+        for (int k = 0; k < D; k++) p[k] = pts[D * i + k];
         out[i] = (kind == 0 ? point_inside_obs(g, p) : point_valid(g, p)) ? 1 : 0;
     }
 }
+template <int D>
 __global__ void k_costs(View v, int env, const long long *idx, long long m, double *out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < m) out[i] = cost_walk(v.nodes + (size_t)env * v.stride, (int)idx[i]);
+    if (i < m) out[i] = cost_walk<D>(v.nodes + (size_t)env * v.stride, (int)idx[i]);
 }
 // goal parent of every env for the final search (rrt_star_3d.py:58; irrt_star_3d.py:74-76)
+template <int D>
 __global__ void __launch_bounds__(kExpandThreads) k_goal_parent(View v, int use_solutions, long long *gp_out, double *cost_out) {
     const int e = blockIdx.x;
     EnvCtl *c = v.ctl + e;
@@ -873,18 +1039,30 @@ __global__ void __launch_bounds__(kExpandThreads) k_goal_parent(View v, int use_
         for (int k = threadIdx.x; k < n_sol; k += blockDim.x) {
             const int idx = sol[k];
             const Node nd = load_node(nodes + idx);
-            lexmin(bs, bk, XADD(cost_walk(nodes, idx), hypot3(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z))), k);
+            lexmin(bs, bk, XADD(cost_walk<D>(nodes, idx), edge_len<D>(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z))), k);
         }
         block_lexmin(bs, bk, sm_s, sm_i);
         if (threadIdx.x == 0) { gp_out[e] = n_sol > 0 ? sol[bk] : -1; cost_out[e] = n_sol > 0 ? bs : XINF; }
     } else {
-        const double len = goal_path_len(v, c, e, nodes, sm_s, sm_i);
+        const double len = goal_path_len<D>(v, c, e, nodes, sm_s, sm_i);
         if (threadIdx.x == 0) { gp_out[e] = c->last_gp; cost_out[e] = len; }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side: batch object
+
+// launches kernel template KERNEL<D, ...> for the batch's dimension
+#define LAUNCH_D(dim, KERNEL, grid, block, smem, stream, ...)                          \
+    do {                                                                               \
+        if ((dim) == 3) KERNEL<3><<<grid, block, smem, stream>>>(__VA_ARGS__);         \
+        else KERNEL<2><<<grid, block, smem, stream>>>(__VA_ARGS__);                    \
+    } while (0)
+#define LAUNCH_DB(dim, KERNEL, FORCE, grid, block, smem, stream, ...)                  \
+    do {                                                                               \
+        if ((dim) == 3) KERNEL<3, FORCE><<<grid, block, smem, stream>>>(__VA_ARGS__);  \
+        else KERNEL<2, FORCE><<<grid, block, smem, stream>>>(__VA_ARGS__);             \
+    } while (0)
 
 struct nirrt_batch {
     View v;
@@ -928,7 +1106,7 @@ extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
 
 extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) {
     if (!d || !out) return fail(NIRRT_ERR_INVALID, "null argument");
-    if (d->dim != 3) return fail(NIRRT_ERR_INVALID, "nirrt_batch_create: dim must be 3");
+    if (d->dim != 3 && d->dim != 2) return fail(NIRRT_ERR_INVALID, "nirrt_batch_create: dim must be 2 or 3");
     if (d->n_envs < 1 || d->capacity < 2) return fail(NIRRT_ERR_INVALID, "n_envs >= 1 and capacity >= 2 required");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(NIRRT_ERR_NO_DEVICE, "no CUDA device visible");
@@ -941,7 +1119,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     memset(&b->v, 0, sizeof(View));
     b->device = d->device; b->launches = 0; b->goal_lists = false; b->h_ctl = nullptr;
     View &v = b->v;
-    v.E = d->n_envs; v.cap = d->capacity;
+    v.E = d->n_envs; v.cap = d->capacity; v.dim = d->dim;
     v.stride = (d->capacity + 63) & ~63;
     v.chunks = pick_chunks(v.E);
     v.near_cap = d->near_capacity > 0 ? d->near_capacity : kNearSmem;
@@ -950,9 +1128,15 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     v.pc_cap = 4096; v.path_cap = 4096;
     v.pc_rate = 0.5; v.pc_ratio = 0.9; v.stop_below = (double)INFINITY;
     const size_t EV = (size_t)v.E * v.stride;
-    DALLOC(v.vx, double, EV); DALLOC(v.vy, double, EV); DALLOC(v.vz, double, EV);
+    DALLOC(v.vx, double, EV); DALLOC(v.vy, double, EV);
+    if (v.dim == 3) DALLOC(v.vz, double, EV);
     DALLOC(v.nodes, Node, EV);
-    DALLOC(v.geom, Geom3, v.E); DALLOC(v.mt, MtState, v.E); DALLOC(v.ctl, EnvCtl, v.E);
+    if (v.dim == 3) { DALLOC(v.geom, Geom3, v.E); }
+    else {
+        DALLOC(v.geom2, Geom2, v.E); DALLOC(v.mt_py, MtState, v.E);
+        CUDA_TRY(cudaMemset(v.mt_py, 0, sizeof(MtState) * v.E));
+    }
+    DALLOC(v.mt, MtState, v.E); DALLOC(v.ctl, EnvCtl, v.E);
     DALLOC(v.part_s, double, (size_t)v.E * v.chunks); DALLOC(v.part_i, int, (size_t)v.E * v.chunks);
     DALLOC(v.cand, int, (size_t)v.E * v.near_cap); DALLOC(v.near_out, int, (size_t)v.E * v.near_cap);
     DALLOC(v.sol, int, (size_t)v.E * v.sol_cap);
@@ -1013,6 +1197,7 @@ extern "C" int nirrt_batch_set_problems(nirrt_batch *b, const double *start, con
         !n_boxes || !boxes || !near_table)
         return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_problems: null argument");
     View &v = b->v;
+    if (v.dim != 3) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_problems: batch is 2D, use nirrt_batch_set_problems_2d");
     for (int e = 0; e < v.E; e++)
         if (n_balls[e] < 0 || n_balls[e] > kMaxObs || n_boxes[e] < 0 || n_boxes[e] > kMaxObs)
             return fail(NIRRT_ERR_INVALID, "more than NIRRT_MAX_OBSTACLES obstacles of one type");
@@ -1040,6 +1225,82 @@ extern "C" int nirrt_batch_set_problems(nirrt_batch *b, const double *start, con
     CHECK_LAUNCH();
     CUDA_TRY(cudaStreamSynchronize(s));   // temporaries are freed on return
     return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_set_problems_2d(nirrt_batch *b, const double *start, const double *goal,
+                                           const double *step_len, const double *search_radius, const double *clearance,
+                                           const double *range, const int *n_circles, const double *circles,
+                                           const int *n_rects, const double *rects, const double *near_table,
+                                           const double *rot_c, void *stream) {
+    if (!b || !start || !goal || !step_len || !search_radius || !clearance || !range || !n_circles || !circles ||
+        !n_rects || !rects || !near_table)
+        return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_problems_2d: null argument");
+    View &v = b->v;
+    if (v.dim != 2) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_problems_2d: batch is 3D");
+    for (int e = 0; e < v.E; e++)
+        if (n_circles[e] < 0 || n_circles[e] > kMaxObs || n_rects[e] < 0 || n_rects[e] > kMaxObs)
+            return fail(NIRRT_ERR_INVALID, "more than NIRRT_MAX_OBSTACLES obstacles of one type");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    TempBufs t;
+    ProblemUpload2 u;
+    double *dp; int *ip;
+    const size_t E = v.E;
+    TRY(t.up(start, 2 * E, s, &dp)); u.start = dp;
+    TRY(t.up(goal, 2 * E, s, &dp)); u.goal = dp;
+    TRY(t.up(step_len, E, s, &dp)); u.step_len = dp;
+    TRY(t.up(search_radius, E, s, &dp)); u.search_radius = dp;
+    TRY(t.up(clearance, E, s, &dp)); u.clearance = dp;
+    TRY(t.up(range, 4 * E, s, &dp)); u.range = dp;
+    TRY(t.up(circles, 3 * E * kMaxObs, s, &dp)); u.circles = dp;
+    TRY(t.up(rects, 4 * E * kMaxObs, s, &dp)); u.rects = dp;
+    u.rot_c = nullptr;
+    if (rot_c) { TRY(t.up(rot_c, 9 * E, s, &dp)); u.rot_c = dp; }
+    TRY(t.up(n_circles, E, s, &ip)); u.n_circles = ip;
+    TRY(t.up(n_rects, E, s, &ip)); u.n_rects = ip;
+    CUDA_TRY(cudaMemcpyAsync((void *)v.near_table, near_table, sizeof(double) * ((size_t)v.cap + 2), cudaMemcpyHostToDevice, s));
+    k_set_problems_2d<<<(v.E + 127) / 128, 128, 0, s>>>(v, u);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+static int upload_mt(nirrt_batch *b, MtState *dst, const uint32_t *key, const int *pos, cudaStream_t s) {
+    View &v = b->v;
+    std::vector<MtState> h(v.E);
+    for (int e = 0; e < v.E; e++) {
+        memcpy(h[e].key[0], key + (size_t)e * 624, 624 * sizeof(uint32_t));
+        memset(h[e].key[1], 0, 624 * sizeof(uint32_t));
+        if (pos[e] < 0 || pos[e] > 624) return fail(NIRRT_ERR_INVALID, "rng pos out of range");
+        h[e].pos = pos[e]; h[e].cur = 0; h[e].has_next = 0; h[e].pad = 0;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dst, h.data(), sizeof(MtState) * v.E, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+static int download_mt(nirrt_batch *b, const MtState *src, uint32_t *key, int *pos, cudaStream_t s) {
+    View &v = b->v;
+    std::vector<MtState> h(v.E);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), src, sizeof(MtState) * v.E, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int e = 0; e < v.E; e++) {
+        memcpy(key + (size_t)e * 624, h[e].key[h[e].cur], 624 * sizeof(uint32_t));
+        pos[e] = h[e].pos;
+    }
+    return NIRRT_OK;
+}
+// random.getstate()[1] of each problem (CPython MT19937: 624 key words + position), 2D batches only
+extern "C" int nirrt_batch_set_py_rng(nirrt_batch *b, const uint32_t *key, const int *pos, void *stream) {
+    if (!b || !key || !pos) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_py_rng: null argument");
+    if (b->v.dim != 2) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_py_rng: only 2D planners consume the CPython stream");
+    CUDA_TRY(cudaSetDevice(b->device));
+    return upload_mt(b, b->v.mt_py, key, pos, (cudaStream_t)stream);
+}
+extern "C" int nirrt_batch_get_py_rng_sync(nirrt_batch *b, uint32_t *key, int *pos, void *stream) {
+    if (!b || !key || !pos) return fail(NIRRT_ERR_INVALID, "nirrt_batch_get_py_rng_sync: null argument");
+    if (b->v.dim != 2) return fail(NIRRT_ERR_INVALID, "nirrt_batch_get_py_rng_sync: only 2D planners consume the CPython stream");
+    CUDA_TRY(cudaSetDevice(b->device));
+    return download_mt(b, b->v.mt_py, key, pos, (cudaStream_t)stream);
 }
 
 extern "C" int nirrt_batch_set_rng(nirrt_batch *b, const uint32_t *key, const int *pos, void *stream) {
@@ -1097,7 +1358,16 @@ extern "C" int nirrt_batch_set_cloud(nirrt_batch *b, int env, const double *poin
         TRY(dalloc(b, &p, sizeof(double) * 3 * (size_t)v.E * v.pc_cap));
         v.pc = (double *)p;
     }
-    if (n) CUDA_TRY(cudaMemcpyAsync(v.pc + (size_t)env * v.pc_cap * 3, points, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+    if (n) {
+        if (v.dim == 3) {
+            CUDA_TRY(cudaMemcpyAsync(v.pc + (size_t)env * v.pc_cap * 3, points, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+        } else {   // 2D clouds [n][2] are stored as [n][3] with z = 0
+            std::vector<double> tmp((size_t)n * 3, 0.0);
+            for (int i = 0; i < n; i++) { tmp[3 * (size_t)i] = points[2 * (size_t)i]; tmp[3 * (size_t)i + 1] = points[2 * (size_t)i + 1]; }
+            CUDA_TRY(cudaMemcpyAsync(v.pc + (size_t)env * v.pc_cap * 3, tmp.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+    }
     k_set_cloud_meta<<<1, 1, 0, s>>>(v, env, n);
     CHECK_LAUNCH();
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -1121,13 +1391,13 @@ extern "C" int nirrt_batch_load_trees(nirrt_batch *b, int env_begin, int count, 
     double *dv[2]; long long *dp[2];
     cudaEvent_t ev[2];
     for (int q = 0; q < 2; q++) {
-        TRY(t.make<double>(3 * (size_t)maxn, &dv[q])); TRY(t.make<long long>((size_t)maxn, &dp[q]));
+        TRY(t.make<double>(v.dim * (size_t)maxn, &dv[q])); TRY(t.make<long long>((size_t)maxn, &dp[q]));
         CUDA_TRY(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming));
     }
     for (int k = 0; k < count; k++) {
         const int q = k & 1;
         if (k >= 2) CUDA_TRY(cudaEventSynchronize(ev[q]));
-        CUDA_TRY(cudaMemcpyAsync(dv[q], vertices + (size_t)k * v.cap * 3, sizeof(double) * 3 * n[k], cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(dv[q], vertices + (size_t)k * v.cap * v.dim, sizeof(double) * v.dim * n[k], cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(dp[q], parents + (size_t)k * v.cap, sizeof(long long) * n[k], cudaMemcpyHostToDevice, s));
         k_scatter_tree<<<(n[k] + 255) / 256, 256, 0, s>>>(v, env_begin + k, n[k], dv[q], dp[q]);
         CHECK_LAUNCH();
@@ -1148,14 +1418,14 @@ extern "C" int nirrt_batch_read_trees_sync(nirrt_batch *b, int env_begin, int co
     CUDA_TRY(cudaMemcpyAsync(b->h_ctl, v.ctl, sizeof(EnvCtl) * v.E, cudaMemcpyDeviceToHost, s));
     TempBufs t;
     double *dv[2]; long long *dp[2];
-    for (int q = 0; q < 2; q++) { TRY(t.make<double>(3 * (size_t)v.cap, &dv[q])); TRY(t.make<long long>((size_t)v.cap, &dp[q])); }
+    for (int q = 0; q < 2; q++) { TRY(t.make<double>(v.dim * (size_t)v.cap, &dv[q])); TRY(t.make<long long>((size_t)v.cap, &dp[q])); }
     CUDA_TRY(cudaStreamSynchronize(s));
     for (int k = 0; k < count; k++) {
         const int q = k & 1;
         if (k >= 2) CUDA_TRY(cudaStreamSynchronize(s));   // staging buffer q is free again
         k_gather_tree<<<(v.cap + 255) / 256, 256, 0, s>>>(v, env_begin + k, dv[q], dp[q]);
         CHECK_LAUNCH();
-        CUDA_TRY(cudaMemcpyAsync(vertices + (size_t)k * v.cap * 3, dv[q], sizeof(double) * 3 * v.cap, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(vertices + (size_t)k * v.cap * v.dim, dv[q], sizeof(double) * v.dim * v.cap, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(parents + (size_t)k * v.cap, dp[q], sizeof(long long) * v.cap, cudaMemcpyDeviceToHost, s));
         n[k] = b->h_ctl[env_begin + k].n;
     }
@@ -1176,7 +1446,7 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
     CHECK_LAUNCH();
     if (!fam_informed(variant) && mode == NIRRT_MODE_PLANNING_RANDOM) {
         TRY(ensure_goal_lists(b));
-        k_goal_init<<<v.E, 256, 0, s>>>(v);
+        LAUNCH_D(v.dim, k_goal_init, v.E, 256, 0, s, v);
         CHECK_LAUNCH();
     }
     return NIRRT_OK;
@@ -1184,11 +1454,11 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
 
 static int launch_iteration(nirrt_batch *b, cudaStream_t s) {
     View &v = b->v;
-    k_top<<<v.E, 128, 0, s>>>(v);
-    k_nearest<false><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
-    k_steer<<<v.E, 32, 0, s>>>(v);
-    k_near<false><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
-    k_expand<<<v.E, kExpandThreads, 0, s>>>(v);
+    LAUNCH_D(v.dim, k_top, v.E, 128, 0, s, v);
+    LAUNCH_DB(v.dim, k_nearest, false, dim3(v.chunks, v.E), 256, 0, s, v);
+    LAUNCH_D(v.dim, k_steer, v.E, 32, 0, s, v);
+    LAUNCH_DB(v.dim, k_near, false, dim3(v.chunks, v.E), 256, 0, s, v);
+    LAUNCH_D(v.dim, k_expand, v.E, kExpandThreads, 0, s, v);
     b->launches += 5;
     return NIRRT_OK;
 }
@@ -1229,15 +1499,15 @@ extern "C" int nirrt_batch_run_profiled_sync(nirrt_batch *b, int iters, float *m
     for (int it = 0; it < iters; it++) {
         cudaEvent_t *e = ev.data() + (size_t)it * 6;
         cudaEventRecord(e[0], s);
-        k_top<<<v.E, 128, 0, s>>>(v);
+        LAUNCH_D(v.dim, k_top, v.E, 128, 0, s, v);
         cudaEventRecord(e[1], s);
-        k_nearest<false><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+        LAUNCH_DB(v.dim, k_nearest, false, dim3(v.chunks, v.E), 256, 0, s, v);
         cudaEventRecord(e[2], s);
-        k_steer<<<v.E, 32, 0, s>>>(v);
+        LAUNCH_D(v.dim, k_steer, v.E, 32, 0, s, v);
         cudaEventRecord(e[3], s);
-        k_near<false><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+        LAUNCH_DB(v.dim, k_near, false, dim3(v.chunks, v.E), 256, 0, s, v);
         cudaEventRecord(e[4], s);
-        k_expand<<<v.E, kExpandThreads, 0, s>>>(v);
+        LAUNCH_D(v.dim, k_expand, v.E, kExpandThreads, 0, s, v);
         cudaEventRecord(e[5], s);
     }
     b->launches += 5LL * iters;
@@ -1347,13 +1617,13 @@ extern "C" int nirrt_batch_goal_parent_sync(nirrt_batch *b, int64_t *goal_parent
     const int use_solutions = fam_informed(v.variant) ? 1 : 0;
     if (!use_solutions) {
         TRY(ensure_goal_lists(b));
-        k_goal_init<<<v.E, 256, 0, s>>>(v);
+        LAUNCH_D(v.dim, k_goal_init, v.E, 256, 0, s, v);
         CHECK_LAUNCH();
     }
     TempBufs t;
     long long *dgp; double *dc;
     TRY(t.make<long long>(v.E, &dgp)); TRY(t.make<double>(v.E, &dc));
-    k_goal_parent<<<v.E, kExpandThreads, 0, s>>>(v, use_solutions, dgp, dc);
+    LAUNCH_D(v.dim, k_goal_parent, v.E, kExpandThreads, 0, s, v, use_solutions, dgp, dc);
     CHECK_LAUNCH();
     CUDA_TRY(cudaMemcpyAsync(goal_parent, dgp, sizeof(long long) * v.E, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(cost, dc, sizeof(double) * v.E, cudaMemcpyDeviceToHost, s));
@@ -1378,7 +1648,7 @@ extern "C" int nirrt_batch_read_trace_sync(nirrt_batch *b, int *nearest, int *ne
         if (nearest) nearest[e] = c.nearest;
         if (new_index) new_index[e] = c.new_idx;
         if (near_count) near_count[e] = c.near_cnt;
-        if (x_rand) for (int i = 0; i < 3; i++) x_rand[3 * e + i] = c.x_rand[i];
+        if (x_rand) for (int i = 0; i < v.dim; i++) x_rand[v.dim * e + i] = c.x_rand[i];
         if (near && near_stride > 0) {
             const int m = c.near_cnt < near_stride ? c.near_cnt : near_stride;
             for (int k = 0; k < m; k++) near[(size_t)e * near_stride + k] = h[(size_t)e * v.near_cap + k];
@@ -1395,9 +1665,9 @@ extern "C" int nirrt_collide_edges_sync(nirrt_batch *b, int env, const double *e
     CUDA_TRY(cudaSetDevice(b->device));
     TempBufs t;
     double *de; uint8_t *dout;
-    TRY(t.up(edges, 6 * (size_t)m, s, &de)); TRY(t.make<uint8_t>((size_t)m, &dout));
+    TRY(t.up(edges, 2 * b->v.dim * (size_t)m, s, &de)); TRY(t.make<uint8_t>((size_t)m, &dout));
     const int blocks = (int)((m + 255) / 256 < 148 * 8 ? (m + 255) / 256 : 148 * 8);
-    k_collide_edges<<<blocks, 256, 0, s>>>(b->v, env, de, m, dout);
+    LAUNCH_D(b->v.dim, k_collide_edges, blocks, 256, 0, s, b->v, env, de, m, dout);
     CHECK_LAUNCH();
     CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)m, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -1412,9 +1682,9 @@ extern "C" int nirrt_points_check_sync(nirrt_batch *b, int env, int kind, const 
     CUDA_TRY(cudaSetDevice(b->device));
     TempBufs t;
     double *dp; uint8_t *dout;
-    TRY(t.up(points, 3 * (size_t)m, s, &dp)); TRY(t.make<uint8_t>((size_t)m, &dout));
+    TRY(t.up(points, b->v.dim * (size_t)m, s, &dp)); TRY(t.make<uint8_t>((size_t)m, &dout));
     const int blocks = (int)((m + 255) / 256 < 148 * 8 ? (m + 255) / 256 : 148 * 8);
-    k_points_check<<<blocks, 256, 0, s>>>(b->v, env, kind, dp, m, dout);
+    LAUNCH_D(b->v.dim, k_points_check, blocks, 256, 0, s, b->v, env, kind, dp, m, dout);
     CHECK_LAUNCH();
     CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)m, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -1424,8 +1694,14 @@ extern "C" int nirrt_points_check_sync(nirrt_batch *b, int env, int kind, const 
 // single-env views for the stand-alone scans: reuse the batch kernels on a 1-env grid
 __global__ void k_set_query(View v, int env, const double *q, int which, double r) {
     EnvCtl *c = v.ctl + env;
-    if (which == 0) { c->x_rand[0] = q[0]; c->x_rand[1] = q[1]; c->x_rand[2] = q[2]; }
-    else { c->x_new[0] = q[0]; c->x_new[1] = q[1]; c->x_new[2] = q[2]; c->T_near = sqrt_le_threshold(r); c->cand_cnt = 0; }
+    const double qz = v.dim == 3 ? q[2] : 0.0;
+    if (which == 0) { c->x_rand[0] = q[0]; c->x_rand[1] = q[1]; c->x_rand[2] = qz; }
+    else {
+        c->x_new[0] = q[0]; c->x_new[1] = q[1]; c->x_new[2] = qz;
+        c->r = r;
+        c->T_near = v.dim == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
+        c->cand_cnt = 0;
+    }
 }
 __global__ void k_finish_nearest(View v, int env, long long *out) {
     double bs = XINF; int bi = INT_MAX;
@@ -1436,9 +1712,13 @@ __global__ void k_finish_nearest(View v, int env, long long *out) {
 
 static View single_env_view(const View &v, int env) {
     View w = v;   // shift every per-env array so that blockIdx.y == 0 addresses `env`
-    w.vx += (size_t)env * v.stride; w.vy += (size_t)env * v.stride; w.vz += (size_t)env * v.stride;
+    w.vx += (size_t)env * v.stride; w.vy += (size_t)env * v.stride;
+    if (v.vz) w.vz += (size_t)env * v.stride;
     w.nodes += (size_t)env * v.stride;
-    w.geom += env; w.mt += env; w.ctl += env;
+    if (v.geom) w.geom += env;
+    if (v.geom2) w.geom2 += env;
+    if (v.mt_py) w.mt_py += env;
+    w.mt += env; w.ctl += env;
     w.part_s += (size_t)env * v.chunks; w.part_i += (size_t)env * v.chunks;
     w.cand += (size_t)env * v.near_cap; w.near_out += (size_t)env * v.near_cap;
     w.E = 1;
@@ -1452,11 +1732,11 @@ extern "C" int nirrt_nearest_sync(nirrt_batch *b, int env, const double *queries
     CUDA_TRY(cudaSetDevice(b->device));
     TempBufs t;
     double *dq; long long *dout;
-    TRY(t.up(queries, 3 * (size_t)m, s, &dq)); TRY(t.make<long long>((size_t)m, &dout));
+    TRY(t.up(queries, b->v.dim * (size_t)m, s, &dq)); TRY(t.make<long long>((size_t)m, &dout));
     View w = single_env_view(b->v, env);
     for (int64_t k = 0; k < m; k++) {
-        k_set_query<<<1, 1, 0, s>>>(w, 0, dq + 3 * k, 0, 0.0);
-        k_nearest<true><<<dim3(w.chunks, 1), 256, 0, s>>>(w);
+        k_set_query<<<1, 1, 0, s>>>(w, 0, dq + w.dim * k, 0, 0.0);
+        LAUNCH_DB(w.dim, k_nearest, true, dim3(w.chunks, 1), 256, 0, s, w);
         k_finish_nearest<<<1, 32, 0, s>>>(w, 0, dout + k);
     }
     CHECK_LAUNCH();
@@ -1471,10 +1751,10 @@ extern "C" int64_t nirrt_within_sync(nirrt_batch *b, int env, const double *q, d
     CUDA_TRY(cudaSetDevice(b->device));
     TempBufs t;
     double *dq;
-    TRY(t.up(q, 3, s, &dq));
+    TRY(t.up(q, (size_t)b->v.dim, s, &dq));
     View w = single_env_view(b->v, env);
     k_set_query<<<1, 1, 0, s>>>(w, 0, dq, 1, r);
-    k_near<true><<<dim3(w.chunks, 1), 256, 0, s>>>(w);
+    LAUNCH_DB(w.dim, k_near, true, dim3(w.chunks, 1), 256, 0, s, w);
     CHECK_LAUNCH();
     TRY(fetch_ctl(b, s));
     const int cnt = b->h_ctl[env].cand_cnt;
@@ -1502,7 +1782,7 @@ extern "C" int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int
     TempBufs t;
     long long *di; double *dout;
     TRY(t.up((const long long *)idx, (size_t)m, s, &di)); TRY(t.make<double>((size_t)m, &dout));
-    k_costs<<<(int)((m + 127) / 128), 128, 0, s>>>(b->v, env, di, m, dout);
+    LAUNCH_D(b->v.dim, k_costs, (int)((m + 127) / 128), 128, 0, s, b->v, env, di, m, dout);
     CHECK_LAUNCH();
     CUDA_TRY(cudaMemcpyAsync(out, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -1528,15 +1808,15 @@ extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, f
     CUDA_TRY(cudaSetDevice(b->device));
     TRY(fetch_ctl(b, s));
     int64_t total = 0;
-    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * 24;
+    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * 8 * v.dim;
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
     float acc = 0.f;
     for (int r = 0; r < reps; r++) {
         if (which == 1) k_reset_cand<<<(v.E + 127) / 128, 128, 0, s>>>(v);
         CUDA_TRY(cudaEventRecord(e0, s));
-        if (which == 0) k_nearest<true><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
-        else k_near<true><<<dim3(v.chunks, v.E), 256, 0, s>>>(v);
+        if (which == 0) LAUNCH_DB(v.dim, k_nearest, true, dim3(v.chunks, v.E), 256, 0, s, v);
+        else LAUNCH_DB(v.dim, k_near, true, dim3(v.chunks, v.E), 256, 0, s, v);
         CUDA_TRY(cudaEventRecord(e1, s));
         CUDA_TRY(cudaEventSynchronize(e1));
         float t = 0.f;
