@@ -1,9 +1,12 @@
-"""NIRRT*-PNG / NRRT*-PNG 3D drop-in classes vs fixtures recorded from the reference's own classes
+"""NIRRT*-PNG / NRRT*-PNG drop-in classes (3D and 2D) vs fixtures recorded from the reference's own classes
 (tests/golden/make_golden_neural_planner.py).  The network is replaced on both sides by recorded
 predictions, so this pins: the device loop body with the cloud / informed / free sampler switch, the
 cloud-update trigger (c_best < ratio * c_update) and its pause/resume, the shared numpy stream
 hand-over, and the guidance-cloud generation (uniform / ellipsoid draws, CUDA obstacle filters,
-CUDA farthest-point down-sampling) -- every cloud must hash identically to the reference's."""
+CUDA farthest-point down-sampling) -- every 3D cloud must hash identically to the reference's; 2D
+clouds are compared to 1e-5 because the ellipse that is sampled depends on c_best, i.e. on vertex
+coordinates that may differ from the reference in their last bit (libm steer, see
+tests/test_gpu_planner2d.py)."""
 import glob
 import hashlib
 import os
@@ -14,7 +17,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "neural3d_*.npz")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "neural[23]d_*.npz")))
 
 
 class ReplayWrapper:
@@ -25,8 +28,11 @@ class ReplayWrapper:
         g, k = self.g, self.k
         assert k < int(g["n_calls"]), "more cloud updates than the reference made"
         assert pc.dtype == np.float32 and len(pc) == int(g["call_n"][k])
-        assert hashlib.sha1(np.ascontiguousarray(pc).tobytes()).hexdigest() == str(g["call_pc_sha1"][k]), f"cloud {k} differs"
-        assert hashlib.sha1(start_mask.tobytes() + goal_mask.tobytes()).hexdigest() == str(g["call_mask_sha1"][k])
+        if int(g["dim"]) == 3:
+            assert hashlib.sha1(np.ascontiguousarray(pc).tobytes()).hexdigest() == str(g["call_pc_sha1"][k]), f"cloud {k} differs"
+            assert hashlib.sha1(start_mask.tobytes() + goal_mask.tobytes()).hexdigest() == str(g["call_mask_sha1"][k])
+        else:
+            assert np.allclose(pc, g[f"call_pc{k}"], rtol=0, atol=1e-5), f"cloud {k} differs"
         pred = np.unpackbits(g["call_pred"][k])[:len(pc)].astype(np.int64)
         self.k += 1
         return pred, pred.astype(np.float32)
@@ -41,12 +47,13 @@ def dropin():
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
 def test_neural_planner_matches_reference_golden(path):
     import importlib
-    from nirrt_star_b200.synthetic import make_problem_3d
+    from nirrt_star_b200.synthetic import make_problem_2d, make_problem_3d
     g = np.load(path)
-    kind, mode = str(g["kind"]), str(g["mode"])
-    mod = importlib.import_module("path_planning_classes_3d." + {"nirrt": "nirrt_star_png_3d", "nrrt": "nrrt_star_png_3d"}[kind])
-    problem = make_problem_3d(int(g["env_idx"]))
-    args = types.SimpleNamespace(step_len=10, iter_max=int(g["iter_max"]), clearance=2, pc_n_points=2048,
+    kind, mode, dim = str(g["kind"]), str(g["mode"]), int(g["dim"])
+    pkg = "path_planning_classes_3d." if dim == 3 else "path_planning_classes."
+    mod = importlib.import_module(pkg + {"nirrt": "nirrt_star_png_", "nrrt": "nrrt_star_png_"}[kind] + f"{dim}d")
+    problem = (make_problem_3d if dim == 3 else make_problem_2d)(int(g["env_idx"]))
+    args = types.SimpleNamespace(step_len=10, iter_max=int(g["iter_max"]), clearance=2 if dim == 3 else 3, pc_n_points=2048,
                                  pc_over_sample_scale=5, pc_sample_rate=float(g["pc_sample_rate"]),
                                  pc_update_cost_ratio=float(g["ratio"]))
     seed = int(g["seed"])
@@ -56,7 +63,7 @@ def test_neural_planner_matches_reference_golden(path):
     if mode == "planning":
         planner.planning(False)
         if len(g["path"]):
-            assert np.allclose(planner.path, g["path"], rtol=0, atol=1e-12)
+            assert np.allclose(planner.path, g["path"], rtol=0, atol=1e-12 if dim == 3 else 1e-9)
         else:
             assert len(planner.path) == 0
     else:
@@ -70,10 +77,11 @@ def test_neural_planner_matches_reference_golden(path):
     n = planner.num_vertices
     assert n == int(g["num_vertices"])
     assert np.array_equal(planner.vertex_parents[:n], g["parents"])
-    assert np.allclose(planner.vertices[:n], g["vertices"], rtol=0, atol=1e-12)
+    assert np.allclose(planner.vertices[:n], g["vertices"], rtol=0, atol=1e-12 if dim == 3 else 1e-9)
     if kind == "nirrt":
         assert list(planner.path_solutions) == list(g["solutions"])
     assert np.random.random() == float(g["next_random"])
+    assert random.random() == float(g["next_py_random"])
 
 
 def test_fps_f64_matches_numpy():
