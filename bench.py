@@ -495,15 +495,15 @@ def main():
                "seconds": best,
                "what": "nirrt_batch_load_trees + set_rng (pinned host -> HBM) + K iterations + read_trees + goal_parents (HBM -> pinned host)"}
 
-    # ---- the one collective: gather per-problem results on every rank (NCCL all_gather)
+    # ---- the one collective: gather per-problem result rows on every rank (NCCL all_gather,
+    # nirrt_star_b200/shard.py -- the same code path the gloo CPU tests exercise)
+    from nirrt_star_b200.shard import gather_lists, shard_bounds
+    assert shard_bounds(world * E, world, rank) == (env_base, env_base + E)
     gp, cost = bp.goal_parents()
     _, _, nv = bp.env_state()
-    summary = torch.tensor(np.stack([cost, nv.astype(np.float64)], 1), device="cuda")
-    if world > 1:
-        gathered = [torch.empty_like(summary) for _ in range(world)]
-        dist.all_gather(gathered, summary)
-        summary = torch.cat(gathered)
-    solved = int(torch.isfinite(summary[:, 0]).sum().item())
+    rows = gather_lists([[float(cost[i]), float(nv[i])] for i in range(E)], world * E,
+                        device=torch.device("cuda", local) if world > 1 else None)
+    solved = int(sum(1 for r in rows if np.isfinite(r[0])))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

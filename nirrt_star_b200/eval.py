@@ -1,0 +1,167 @@
+"""Batched evaluation front-end: what eval_planning_{2d,3d}.py does one problem at a time
+(eval_planning_3d.py:101-126: build planner, `planning_random(iter_after_initial)`, store
+`path_len_list`), done for a whole list of problems in lock step on the GPU and sharded over ranks.
+
+``plan_batch`` returns, for every problem, exactly the list the reference's
+``get_path_planner(args, problem, wrapper).planning_random(iter_after_initial)`` returns under the
+per-problem seeding convention of SURVEY.md 8c (`np.random.seed(s); random.seed(s);
+torch.manual_seed(s)` with ``s = seeds[i]`` right before the planner is constructed) -- the drop-in
+classes are the single-problem special case of this driver and the GPU tests compare the two.
+
+Neural planners (nrrt_star / nirrt_star): guidance clouds are generated per problem on that problem's
+own numpy stream (host, same code as the drop-in classes), classified in ONE batched PointNet++
+forward for all problems that wait for a cloud at the same lock-step iteration, and uploaded.
+"""
+import types
+
+import numpy as np
+
+from . import batch as _B
+from .shard import gather_lists, shard_bounds
+
+VARIANTS = {"rrt_star": _B.VARIANT_RRT_STAR, "irrt_star": _B.VARIANT_IRRT_STAR,
+            "nrrt_star": _B.VARIANT_NRRT_STAR, "nirrt_star": _B.VARIANT_NIRRT_STAR}
+
+
+def default_args(dim, **kw):
+    """The argparse defaults of eval_planning_{2d,3d}.py:10-31 that reach the planners."""
+    a = dict(step_len=10, iter_max=30000, clearance=3 if dim == 2 else 2, pc_n_points=2048, pc_over_sample_scale=5,
+             pc_sample_rate=0.5, pc_update_cost_ratio=0.9, iter_after_initial=5000)
+    a.update(kw)
+    return types.SimpleNamespace(**a)
+
+
+class _CloudMaker:
+    """update_point_cloud (nirrt_star_png_{2d,3d}.py:132-174) for one problem, split in two halves
+    around the network call so that the forwards of many problems can be batched."""
+
+    def __init__(self, dim, problem, args):
+        from . import dropin
+        dropin.install()
+        self.dim, self.args = dim, args
+        self.x_start = np.array(problem["x_start"]).astype(np.float64)
+        self.x_goal = np.array(problem["x_goal"]).astype(np.float64)
+        if dim == 3:
+            from path_planning_utils_3d.rrt_env_3d import Env
+            self.env = Env(problem["env_dict"])
+        else:
+            self.mask = problem["binary_mask"]
+
+    def sample(self, cmax, cmin):
+        a = self.args
+        if self.dim == 3:
+            from datasets_3d.point_cloud_mask_utils_3d import ellipsoid_point_cloud_sampling_3d, generate_rectangle_point_cloud_3d
+            if cmax < np.inf:
+                pc = ellipsoid_point_cloud_sampling_3d(self.x_start, self.x_goal, cmax / cmin, self.env, a.pc_n_points,
+                                                       n_raw_samples=a.pc_n_points * a.pc_over_sample_scale)
+            else:
+                pc = generate_rectangle_point_cloud_3d(self.env, a.pc_n_points, over_sample_scale=a.pc_over_sample_scale)
+        else:
+            from datasets.point_cloud_mask_utils import ellipsoid_point_cloud_sampling, generate_rectangle_point_cloud
+            if cmax < np.inf:
+                pc = ellipsoid_point_cloud_sampling(self.x_start, self.x_goal, cmax / cmin, self.mask, a.pc_n_points,
+                                                    n_raw_samples=a.pc_n_points * a.pc_over_sample_scale)
+            else:
+                pc = generate_rectangle_point_cloud(self.mask, a.pc_n_points, a.pc_over_sample_scale)
+        from datasets.point_cloud_mask_utils import get_point_cloud_mask_around_points
+        sm = get_point_cloud_mask_around_points(pc, self.x_start[np.newaxis, :], a.step_len)
+        gm = get_point_cloud_mask_around_points(pc, self.x_goal[np.newaxis, :], a.step_len)
+        return pc, sm.astype(np.float32), gm.astype(np.float32)
+
+
+def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, classify=None, device=0, chunk=256,
+               distributed=False, return_planner=False):
+    """path_len_list of every problem (global order on every rank when ``distributed``).
+
+    planner: 'rrt_star' | 'irrt_star' | 'nrrt_star' | 'nirrt_star'
+    state_dict: PointNet++ ``model_state_dict`` for the neural planners (the sm_100a engine is built
+        from it), or pass ``classify(list_of_(pc, start_mask, goal_mask)) -> list_of_path_pred`` to
+        supply predictions some other way (tests replay recorded ones).
+    """
+    import torch
+    args = default_args(dim) if args is None else args
+    variant = VARIANTS[planner]
+    n_total = len(problems)
+    seeds = list(range(n_total)) if seeds is None else list(seeds)
+    rank, world = 0, 1
+    if distributed:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+    b, e = shard_bounds(n_total, world, rank)
+    local, lseeds = problems[b:e], seeds[b:e]
+    lists = []
+    bp = None
+    if local:
+        E = len(local)
+        cls = _B.BatchPlanner3D if dim == 3 else _B.BatchPlanner2D
+        bp = cls(local, args.iter_max, step_len=args.step_len, clearance=args.clearance, seeds=lseeds, device=device,
+                 record_capacity=args.iter_max + args.iter_after_initial + 8)
+        neural = variant in (_B.VARIANT_NIRRT_STAR, _B.VARIANT_NRRT_STAR)
+        if neural:
+            makers = [_CloudMaker(dim, p, args) for p in local]
+            gens = [torch.Generator().manual_seed(int(s)) for s in lseeds]
+            engine = None
+            if classify is None:
+                from .pointnet2 import NPOINTS, PointNet2Engine
+                if state_dict is None:
+                    raise ValueError("neural planners need state_dict= or classify=")
+                engine = PointNet2Engine(state_dict, n_points=args.pc_n_points, max_batch=E, device=device)
+
+                def classify(items, envs):
+                    full = [k for k, it in enumerate(items) if len(it[0]) == args.pc_n_points]
+                    if len(full) != len(items):
+                        raise ValueError("a guidance cloud has fewer than pc_n_points free points")
+                    fs = np.stack([[int(torch.randint(0, n, (1,), generator=gens[env], dtype=torch.long)) for n in (args.pc_n_points,) + NPOINTS]
+                                   for env in envs]).astype(np.int32)
+                    pred, _ = engine.classify(np.stack([it[0].astype(np.float32) for it in items]),
+                                              np.stack([it[1] for it in items]), np.stack([it[2] for it in items]), fps_start=fs)
+                    return list(pred)
+            else:
+                user = classify
+
+                def classify(items, envs):
+                    return user([(it[0].astype(np.float32), it[1], it[2]) for it in items], envs)
+
+            bp.set_guidance(args.pc_sample_rate, args.pc_update_cost_ratio if variant == _B.VARIANT_NIRRT_STAR else 0.0)
+
+            def update(envs, cbest, cmin):
+                """host half of update_point_cloud for the listed problems, one batched forward"""
+                if args.pc_sample_rate == 0:          # nirrt_star_png_3d.py:137-140: no cloud, no draws
+                    for env in envs:
+                        bp.set_cloud(int(env), np.zeros((0, dim)))
+                    return
+                states = bp.get_rng()
+                items = []
+                for env in envs:
+                    np.random.set_state(("MT19937", states[env][0], states[env][1], 0, 0.0))
+                    items.append(makers[env].sample(cbest[env], cmin[env]))
+                    st = np.random.get_state()
+                    states[env] = (st[1], st[2])
+                preds = classify(items, list(envs))
+                bp.set_rng(states)
+                for env, it, pred in zip(envs, items, preds):
+                    bp.set_cloud(int(env), it[0][np.asarray(pred).nonzero()[0]])
+
+            keep = np.random.get_state()
+            if args.pc_sample_rate != 0:
+                update(list(range(E)), np.full(E, np.inf), np.full(E, np.nan))        # init_pc()
+        bp.begin(variant, _B.MODE_PLANNING_RANDOM, args.iter_max, args.iter_after_initial)
+        while True:
+            bp.run(chunk)
+            running, need = bp.status()
+            if need:
+                st, _, _ = bp.env_state()
+                cb, cm = bp.c_best()
+                update(list(np.nonzero(st == _B.ST_WAIT_CLOUD)[0]), cb, cm)
+                continue
+            if running == 0:
+                break
+        if neural:
+            np.random.set_state(keep)
+        lists = bp.path_len_lists()
+    out = gather_lists(lists, n_total, device=torch.device("cuda", device)) if distributed else lists
+    if return_planner:
+        return out, bp
+    if bp is not None:
+        bp.close()
+    return out
