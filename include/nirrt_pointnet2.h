@@ -75,6 +75,15 @@ int nirrt_pn2_last_stage_ms(nirrt_pn2 *h, float *ms8);
 /* kernel launches issued so far */
 int64_t nirrt_pn2_launch_count(nirrt_pn2 *h);
 
+/* Neural Connect graph analysis (wrapper/utils/bfs_connect_heuristic.py:5-29,32-78; used by
+ * PNGWrapper.generate_connected_path_points, pointnet2_wrapper_connect_bfs.py:76-240): over the r-disc
+ * graph on [src, dst, pc[path_mask]] (float32 norms, strict <) returns has_path (dst reachable from
+ * src), visited_mask [n] (path points in src's component) and boundary_mask [n] (visited path points
+ * with a non-path point closer than radius).  Host buffers, synchronous; n <= 4096, dim 2 or 3. */
+int nirrt_connect_analyse_sync(const float *pc, int n, int dim, const uint8_t *path_mask, const float *src,
+                               const float *dst, float radius, int *has_path, uint8_t *visited_mask,
+                               uint8_t *boundary_mask, void *stream);
+
 /* Stand-alone tensor-core GEMM (the kernel the network uses), host buffers, synchronous:
  *   A [m][k] fp16, W [n][k] fp16, bias [n] f32; k, n multiples of 16.
  *   mode 0: out [m][n]        = fp16(relu(A W^T + bias))

@@ -822,3 +822,136 @@ extern "C" int nirrt_gemm_f16_sync(const uint16_t *A, const uint16_t *W, const f
     cleanup();
     return NIRRT_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Neural Connect graph analysis (wrapper/utils/bfs_connect_heuristic.py):
+//   bfs_point_cloud            :32-78   r-disc graph over [src, dst, predicted path points], component
+//                                       of src, has_path <=> dst is in it
+//   get_boundary_mask          :5-29    visited path points with a non-path point closer than r
+// float32 arithmetic as numpy evaluates it on float32 clouds: norm = sqrt((dx*dx + dy*dy) + dz*dz).
+// One CTA: vertex coordinates in shared memory, level-synchronous frontier expansion (the visited
+// SET of an exhausted BFS is order-independent; when dst is reached the reference's caller ignores
+// the set), then the boundary test of the visited path points against all non-path points.
+constexpr int kConnMax = 4096;         // points per cloud
+__device__ __forceinline__ float norm_f32(float dx, float dy, float dz, int dim) {
+    float s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (dim == 3) s = __fadd_rn(s, __fmul_rn(dz, dz));
+    return __fsqrt_rn(s);
+}
+__global__ void __launch_bounds__(1024) k_connect(const float *pc, int n, int dim, const uint8_t *path_mask, const float *src,
+                                                  const float *dst, float radius, int *has_path, uint8_t *visited_mask,
+                                                  uint8_t *boundary_mask) {
+    extern __shared__ unsigned char s_raw[];
+    float *vx = reinterpret_cast<float *>(s_raw);            // [m] vertices: 0 = src, 1 = dst, 2.. = path points
+    float *vy = vx + (kConnMax + 2), *vz = vy + (kConnMax + 2);
+    int *vid = reinterpret_cast<int *>(vz + (kConnMax + 2)); // point index of vertex (>= 2)
+    int *fr = vid + (kConnMax + 2);                          // frontier lists, double buffered
+    int *fr2 = fr + (kConnMax + 2);
+    unsigned char *state = reinterpret_cast<unsigned char *>(fr2 + (kConnMax + 2));   // 0 unvisited, 1 visited
+    __shared__ int s_m, s_cnt[2], s_found;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_m = 2; s_cnt[0] = 1; s_cnt[1] = 0; s_found = 0; }
+    __syncthreads();
+    // compact the path points in ascending point order (order only matters for determinism of vid)
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        const bool p = i < n && path_mask[i];
+        // block-ordered append via warp ballots
+        const unsigned bal = __ballot_sync(0xffffffffu, p);
+        __shared__ int s_w[32];
+        const int w = tid >> 5, l = tid & 31;
+        if (l == 0) s_w[w] = __popc(bal);
+        __syncthreads();
+        int off = s_m;
+        for (int q = 0; q < w; q++) off += s_w[q];
+        if (p) {
+            const int pos = off + __popc(bal & ((1u << l) - 1u));
+            vx[pos] = pc[(size_t)i * dim]; vy[pos] = pc[(size_t)i * dim + 1]; vz[pos] = dim == 3 ? pc[(size_t)i * dim + 2] : 0.f;
+            vid[pos] = i;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += s_w[q]; s_m += t; }
+        __syncthreads();
+    }
+    const int m = s_m;
+    if (tid == 0) {
+        vx[0] = src[0]; vy[0] = src[1]; vz[0] = dim == 3 ? src[2] : 0.f;
+        vx[1] = dst[0]; vy[1] = dst[1]; vz[1] = dim == 3 ? dst[2] : 0.f;
+        fr[0] = 0;
+    }
+    for (int j = tid; j < m; j += blockDim.x) state[j] = j == 0 ? 1 : 0;
+    __syncthreads();
+    int *cur = fr, *nxt = fr2;
+    int level = 0;
+    while (true) {
+        const int nf = s_cnt[level & 1];
+        if (nf == 0 || s_found) break;
+        for (int j = tid; j < m; j += blockDim.x) {
+            if (state[j]) continue;
+            bool hit = false;
+            for (int k = 0; k < nf && !hit; k++) {
+                const int f = cur[k];
+                hit = norm_f32(__fsub_rn(vx[j], vx[f]), __fsub_rn(vy[j], vy[f]), __fsub_rn(vz[j], vz[f]), dim) < radius;
+            }
+            if (hit) {
+                state[j] = 1;
+                if (j == 1) s_found = 1;
+                else nxt[atomicAdd(&s_cnt[(level + 1) & 1], 1)] = j;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_cnt[level & 1] = 0;
+        __syncthreads();
+        int *t = cur; cur = nxt; nxt = t;
+        level++;
+    }
+    __syncthreads();
+    if (tid == 0) *has_path = s_found;
+    for (int i = tid; i < n; i += blockDim.x) { visited_mask[i] = 0; boundary_mask[i] = 0; }
+    __syncthreads();
+    for (int j = 2 + tid; j < m; j += blockDim.x) {
+        if (!state[j]) continue;
+        const int i = vid[j];
+        visited_mask[i] = 1;
+        bool b = false;
+        for (int u = 0; u < n && !b; u++) {
+            if (path_mask[u]) continue;
+            const float ux = pc[(size_t)u * dim], uy = pc[(size_t)u * dim + 1], uz = dim == 3 ? pc[(size_t)u * dim + 2] : 0.f;
+            b = norm_f32(__fsub_rn(vx[j], ux), __fsub_rn(vy[j], uy), __fsub_rn(vz[j], uz), dim) < radius;
+        }
+        boundary_mask[i] = b ? 1 : 0;
+    }
+}
+
+extern "C" int nirrt_connect_analyse_sync(const float *pc, int n, int dim, const uint8_t *path_mask, const float *src,
+                                          const float *dst, float radius, int *has_path, uint8_t *visited_mask,
+                                          uint8_t *boundary_mask, void *stream) {
+    if (!pc || !path_mask || !src || !dst || !has_path || !visited_mask || !boundary_mask)
+        return pfail(NIRRT_ERR_INVALID, "nirrt_connect_analyse_sync: null argument");
+    if (n < 1 || n > kConnMax || (dim != 2 && dim != 3)) return pfail(NIRRT_ERR_INVALID, "nirrt_connect_analyse_sync: 1 <= n <= 4096, dim 2 or 3");
+    if (nirrt_device_count() <= 0) return pfail(NIRRT_ERR_NO_DEVICE, "no sm_100 device");
+    cudaStream_t s = (cudaStream_t)stream;
+    float *d_pc = nullptr, *d_sd = nullptr;
+    uint8_t *d_mask = nullptr, *d_out = nullptr;
+    int *d_hp = nullptr;
+    auto cleanup = [&]() { cudaFree(d_pc); cudaFree(d_sd); cudaFree(d_mask); cudaFree(d_out); cudaFree(d_hp); };
+#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return pfail(NIRRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+    CT(cudaMalloc(&d_pc, sizeof(float) * (size_t)n * dim)); CT(cudaMalloc(&d_sd, sizeof(float) * 6));
+    CT(cudaMalloc(&d_mask, (size_t)n)); CT(cudaMalloc(&d_out, 2 * (size_t)n)); CT(cudaMalloc(&d_hp, sizeof(int)));
+    CT(cudaMemcpyAsync(d_pc, pc, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice, s));
+    CT(cudaMemcpyAsync(d_sd, src, sizeof(float) * dim, cudaMemcpyHostToDevice, s));
+    CT(cudaMemcpyAsync(d_sd + 3, dst, sizeof(float) * dim, cudaMemcpyHostToDevice, s));
+    CT(cudaMemcpyAsync(d_mask, path_mask, (size_t)n, cudaMemcpyHostToDevice, s));
+    const size_t smem = (size_t)(kConnMax + 2) * (3 * sizeof(float) + 3 * sizeof(int) + 1) + 16;
+    static bool attr = false;
+    if (!attr) { CT(cudaFuncSetAttribute(k_connect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_connect<<<1, 1024, smem, s>>>(d_pc, n, dim, d_mask, d_sd, d_sd + 3, radius, d_hp, d_out, d_out + n);
+    CT(cudaGetLastError());
+    CT(cudaMemcpyAsync(has_path, d_hp, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CT(cudaMemcpyAsync(visited_mask, d_out, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CT(cudaMemcpyAsync(boundary_mask, d_out + n, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CT(cudaStreamSynchronize(s));
+#undef CT
+    cleanup();
+    return NIRRT_OK;
+}

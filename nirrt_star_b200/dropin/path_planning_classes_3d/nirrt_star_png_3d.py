@@ -69,6 +69,14 @@ class NIRRTStarPNG3D(IRRTStar3D):
                                                      n_raw_samples=self.pc_n_points * self.pc_over_sample_scale)
         return generate_rectangle_point_cloud_3d(self.env, self.pc_n_points, over_sample_scale=self.pc_over_sample_scale)
 
+    def _predict(self, pc):
+        """one network call on start/goal neighbourhood masks; the (C) variants override this"""
+        start_mask = get_point_cloud_mask_around_points(pc, self.x_start[np.newaxis, :], self.pc_neighbor_radius)
+        goal_mask = get_point_cloud_mask_around_points(pc, self.x_goal[np.newaxis, :], self.pc_neighbor_radius)
+        path_pred, path_score = self.png_wrapper.classify_path_points(
+            pc.astype(np.float32), start_mask.astype(np.float32), goal_mask.astype(np.float32))
+        return path_pred
+
     def update_point_cloud(self, cmax, cmin):
         """nirrt_star_png_3d.py:132-173"""
         if self.pc_sample_rate == 0:
@@ -76,10 +84,7 @@ class NIRRTStarPNG3D(IRRTStar3D):
             self.visualizer.set_path_point_cloud_pred(self.path_point_cloud_pred)
             return
         pc = self._sample_cloud(cmax, cmin)
-        start_mask = get_point_cloud_mask_around_points(pc, self.x_start[np.newaxis, :], self.pc_neighbor_radius)
-        goal_mask = get_point_cloud_mask_around_points(pc, self.x_goal[np.newaxis, :], self.pc_neighbor_radius)
-        path_pred, path_score = self.png_wrapper.classify_path_points(
-            pc.astype(np.float32), start_mask.astype(np.float32), goal_mask.astype(np.float32))
+        path_pred = self._predict(pc)
         self.path_point_cloud_pred = pc[path_pred.nonzero()[0]]
         self.visualizer.set_path_point_cloud_pred(self.path_point_cloud_pred)
 

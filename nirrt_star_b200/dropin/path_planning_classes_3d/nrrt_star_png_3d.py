@@ -41,6 +41,14 @@ class NRRTStarPNG3D(RRTStar3D):
     def SamplePointCloud(self):
         return self.path_point_cloud_pred[np.random.randint(0, len(self.path_point_cloud_pred))]
 
+    def _predict(self, pc):
+        """one network call on start/goal neighbourhood masks; the (C) variants override this"""
+        start_mask = get_point_cloud_mask_around_points(pc, self.x_start[np.newaxis, :], self.pc_neighbor_radius)
+        goal_mask = get_point_cloud_mask_around_points(pc, self.x_goal[np.newaxis, :], self.pc_neighbor_radius)
+        path_pred, path_score = self.png_wrapper.classify_path_points(
+            pc.astype(np.float32), start_mask.astype(np.float32), goal_mask.astype(np.float32))
+        return path_pred
+
     def update_point_cloud(self):
         """nrrt_star_png_3d.py:74-100"""
         if self.pc_sample_rate == 0:
@@ -48,10 +56,7 @@ class NRRTStarPNG3D(RRTStar3D):
             self.visualizer.set_path_point_cloud_pred(self.path_point_cloud_pred)
             return
         pc = generate_rectangle_point_cloud_3d(self.env, self.pc_n_points, over_sample_scale=self.pc_over_sample_scale)
-        start_mask = get_point_cloud_mask_around_points(pc, self.x_start[np.newaxis, :], self.pc_neighbor_radius)
-        goal_mask = get_point_cloud_mask_around_points(pc, self.x_goal[np.newaxis, :], self.pc_neighbor_radius)
-        path_pred, path_score = self.png_wrapper.classify_path_points(
-            pc.astype(np.float32), start_mask.astype(np.float32), goal_mask.astype(np.float32))
+        path_pred = self._predict(pc)
         self.path_point_cloud_pred = pc[path_pred.nonzero()[0]]
         self.visualizer.set_path_point_cloud_pred(self.path_point_cloud_pred)
 

@@ -147,3 +147,20 @@ def gemm_f16(A, W, bias, mode=0, group=16, stream=None):
     check(L.nirrt_gemm_f16_sync(A.ctypes.data_as(u16), W.ctypes.data_as(u16), fp(bias), m, n, k, int(mode), int(group),
                                 out.ctypes.data_as(u16), C.c_void_p(stream) if stream else None))
     return out
+
+
+def connect_analyse(pc, path_mask, src, dst, radius, stream=None):
+    """(has_path, visited_mask f32 [n], boundary_mask f32 [n]) of the r-disc graph over
+    [src, dst, pc[path_mask]] -- bfs_point_cloud + get_boundary_mask of the reference's Neural Connect
+    (wrapper/utils/bfs_connect_heuristic.py) in one CUDA launch."""
+    _lib.require_device()
+    L = _lib.lib()
+    pc = np.ascontiguousarray(pc, dtype=np.float32)
+    n, dim = pc.shape
+    pm = np.ascontiguousarray(np.asarray(path_mask) != 0, dtype=np.uint8)
+    s = np.ascontiguousarray(src, dtype=np.float32).reshape(dim); d = np.ascontiguousarray(dst, dtype=np.float32).reshape(dim)
+    hp = C.c_int(0)
+    vis = np.zeros(n, dtype=np.uint8); bnd = np.zeros(n, dtype=np.uint8)
+    check(L.nirrt_connect_analyse_sync(fp(pc), n, dim, _lib.u8p(pm), fp(s), fp(d), C.c_float(float(radius)), C.byref(hp),
+                                       _lib.u8p(vis), _lib.u8p(bnd), C.c_void_p(stream) if stream else None))
+    return bool(hp.value), vis.astype(np.float32), bnd.astype(np.float32)
