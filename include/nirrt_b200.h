@@ -183,7 +183,7 @@ int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int64_t m, dou
 int nirrt_fps_f64_sync(const double *points, int64_t n, int npoint, int start, int64_t *out_idx, void *stream);
 
 /* Device-resident benchmark hooks: bytes scanned per Nearest+Near pass and launch counters. */
-int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *reserved);
+int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *scan_bytes_per_vertex);
 /* Times `reps` back-to-back launches of ONE scan kernel (0 = Nearest, 1 = Near) on the batch's
  * current trees with CUDA events on `stream`; returns average milliseconds per launch in *ms and
  * the vertex-coordinate bytes one launch reads in *bytes. */

@@ -328,6 +328,12 @@ class BatchPlanner3D:
         check(self.L.nirrt_batch_counters(self.h, C.byref(n), None))
         return n.value
 
+    def scan_bytes_per_vertex(self):
+        """bytes one Nearest / Near pass reads per vertex: 4*dim with the f32 mirror, 8*dim without"""
+        n = C.c_int64(0); b = C.c_int64(0)
+        check(self.L.nirrt_batch_counters(self.h, C.byref(n), C.byref(b)))
+        return b.value
+
     def time_scan(self, which, reps=20):
         ms = C.c_float(0); nbytes = C.c_int64(0)
         check(self.L.nirrt_batch_time_scan_sync(self.h, int(which), int(reps), C.byref(ms), C.byref(nbytes), self.stream))

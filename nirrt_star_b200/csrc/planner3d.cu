@@ -68,7 +68,7 @@ struct __align__(32) Node {
 
 enum { ST_DONE = 0, ST_PHASE1 = 1, ST_PHASE2 = 2, ST_WAIT_CLOUD = 3 };
 enum { ERR_NEAR_OVERFLOW = 1, ERR_SOL_OVERFLOW = 2, ERR_VERTEX_OVERFLOW = 4, ERR_EMPTY_CLOUD = 8,
-       ERR_PATH_DEPTH = 16, ERR_RECORD_OVERFLOW = 32, ERR_GOAL_OVERFLOW = 64 };
+       ERR_PATH_DEPTH = 16, ERR_RECORD_OVERFLOW = 32, ERR_GOAL_OVERFLOW = 64, ERR_OUT_OF_RANGE = 128 };
 
 struct EnvCtl {
     // problem
@@ -84,6 +84,10 @@ struct EnvCtl {
     int go, skip, nearest, new_idx, inserted, cand_cnt, near_cnt;
     double x_rand[3], x_new[3];
     double r, T_near, curr_cost, c_best, c_update;
+    double cnew_default;  // cost(new) if ChooseParent keeps the steer parent: the walk from x_new, leaf -> root
+    double margin;    // bound on |f32-mirror distance - f64 distance| for vertices inside the world range
+    float near_thr;   // f32 scan: a <= near_thr selects the Near candidates that get the exact f64 test
+    int fallbacks;    // Nearest chunks that had to be re-scanned in f64 (more than two candidates per thread)
     // goal bookkeeping
     int n_sol, n_goal, tree_changed, n_pc;
     long long last_gp;
@@ -93,11 +97,13 @@ struct EnvCtl {
 
 struct View {
     int E, cap, stride, chunks, near_cap, rec_cap, sol_cap, pc_cap, path_cap;
+    int env0;        // first problem of the group an iteration kernel works on (see nirrt_batch_run)
     int variant, mode, iter_max, iter_after;
     double stop_below; // phase 1 ends when the recorded value drops below this (+inf: planning_random; finite: planning_block_gap)
     int n_limit;     // > 0: problems whose tree reached n_limit vertices idle (benchmark pre-growth)
     double pc_rate, pc_ratio;
     double *vx, *vy, *vz;
+    float *fx, *fy, *fz;   // f32 mirror of the coordinates (scan layout, 4 B per coordinate); null = scan the f64 arrays
     Node *nodes;
     Geom3 *geom;
     Geom2 *geom2;    // 2D worlds (dim == 2)
@@ -188,6 +194,27 @@ __device__ double cost_walk(const Node *nodes, int idx) {
         cur = p;
     }
     return c;
+}
+
+// One walk, two sums in the reference's leaf -> root order:
+//   c   = cost(idx)                                   (0 + e1) + e2 + ...
+//   via = cost(x_new) if idx were x_new's parent      (first + e1) + e2 + ...   with first = hypot(x_new - v[idx])
+// so neither ChooseParent's winner nor the steer parent needs a second walk for node_new_cost
+// (rrt_star_3d.py:96).
+template <int D>
+__device__ __forceinline__ void cost_walk2(const Node *nodes, int idx, double first, double &c_out, double &via_out) {
+    double c = 0.0, a = first;
+    if (idx != 0) {
+        Node cur = load_node(nodes + idx);
+        while (idx != 0) {
+            const int par = (int)cur.parent;
+            const Node p = load_node(nodes + par);
+            const double e = edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
+            c = XADD(c, e); a = XADD(a, e);
+            idx = par; cur = p;
+        }
+    }
+    c_out = c; via_out = a;
 }
 
 // lexicographic (value, index) min == np.argmin's first-minimum rule
@@ -319,7 +346,7 @@ __device__ void sample_informed(const Geom2 &g, const EnvCtl *c, MtStream &, MtS
 template <int D>
 __global__ void __launch_bounds__(128) k_top(View v) {
     typedef typename GeomOf<D>::type G;
-    const int e = blockIdx.x;
+    const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
     __shared__ G g;
     __shared__ double sm_s[4];
@@ -404,7 +431,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
 //   for running-minimum candidates: s2 >= RU(best_s*best_s) implies sqrt_rn(s2) >= best_s.
 template <int D, bool kForce>
 __global__ void __launch_bounds__(256) k_nearest(View v) {
-    const int e = blockIdx.y;
+    const int e = v.env0 + blockIdx.y;
     const EnvCtl *c = v.ctl + e;
     if (!kForce && !c->go) return;
     const int n = c->n;
@@ -483,7 +510,7 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
 template <int D>
 __global__ void __launch_bounds__(32) k_steer(View v) {
     typedef typename GeomOf<D>::type G;
-    const int e = blockIdx.x;
+    const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
     if (!c->go) return;
     const int lane = threadIdx.x;
@@ -533,19 +560,24 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
         xnew[0] = xn[0]; xnew[1] = xn[1]; xnew[2] = xn[2];
         new_idx = nearest;
         c->curr_cost = cost_walk<D>(nodes, nearest);
+        c->cnew_default = c->curr_cost;
     } else {
         new_idx = c->n;
         if (new_idx >= v.cap) { c->err |= ERR_VERTEX_OVERFLOW; c->skip = 1; c->new_idx = -1; return; }
         const size_t o = (size_t)e * v.stride + new_idx;
         v.vx[o] = xnew[0]; v.vy[o] = xnew[1];
         if (D == 3) v.vz[o] = xnew[2];
+        if (v.fx) { v.fx[o] = (float)xnew[0]; v.fy[o] = (float)xnew[1]; if (D == 3) v.fz[o] = (float)xnew[2]; }
         Node nd; nd.x = xnew[0]; nd.y = xnew[1]; nd.z = xnew[2]; nd.parent = nearest;
         nodes[new_idx] = nd;
         c->n = new_idx + 1;
         c->inserted = 1;
         c->tree_changed = 1;
-        c->curr_cost = XADD(cost_walk<D>(nodes, nearest),
-                            edge_len<D>(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2])));
+        const double e0 = edge_len<D>(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2]));
+        double cn, via;
+        cost_walk2<D>(nodes, nearest, e0, cn, via);
+        c->curr_cost = XADD(cn, e0);
+        c->cnew_default = via;
     }
     c->new_idx = new_idx;
     c->x_new[0] = xnew[0]; c->x_new[1] = xnew[1]; c->x_new[2] = xnew[2];
@@ -553,6 +585,10 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
     if (c->step_len < r) r = c->step_len;            // min(gamma * f(n), step_len)
     c->r = r;
     c->T_near = D == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
+    {   // f32 pre-filter threshold: every vertex with f64 distance <= r has f32 squared distance <= near_thr
+        const double rm = r + c->margin;
+        c->near_thr = __double2float_ru(rm * rm * 1.000001);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -564,7 +600,7 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
 // ascending index order.
 template <int D, bool kForce>
 __global__ void __launch_bounds__(256) k_near(View v) {
-    const int e = blockIdx.y;
+    const int e = v.env0 + blockIdx.y;
     EnvCtl *c = v.ctl + e;
     if (!kForce && (!c->go || c->skip)) return;
     const int n = c->n;
@@ -614,11 +650,155 @@ __global__ void __launch_bounds__(256) k_near(View v) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// f32-mirror scans.  The two HBM-bound passes read a float copy of the coordinates (12 B / vertex
+// in 3D, 8 B in 2D instead of 24 / 16) and use it only as a conservative filter: for vertices
+// inside the world range the f32 distance differs from the reference's f64 value by less than
+// `margin` (EnvCtl.margin = 2^-19 * largest |range bound|; derivation in DESIGN.md section 4), so
+//   Nearest: the f64 argmin lies within 2*margin of the f32 minimum of its chunk; every thread
+//            keeps its two best f32 candidates (and the value of the third), the candidates inside
+//            the band are re-evaluated with the exact formula and reduced lexicographically
+//            (value, index) exactly like the f64 scan.  A thread whose third-best value is also
+//            inside the band (practically never) makes its CTA re-scan the chunk in f64.
+//   Near:    f32 squared distance <= near_thr is a superset of the exact set; k_expand applies the
+//            exact test to every candidate before anything else looks at it.
+// Results are therefore bit-identical to the f64 scans (same parity tests).
+template <int D>
+__device__ __forceinline__ double exact_scan_value(const View &v, int e, int i, double qx, double qy, double qz) {
+    const size_t o = (size_t)e * v.stride + i;
+    const double dx = XSUB(qx, v.vx[o]), dy = XSUB(qy, v.vy[o]), dz = D == 3 ? XSUB(qz, v.vz[o]) : 0.0;
+    return D == 3 ? XSQRT(sq3_rows(dx, dy, dz)) : np_hypot(dx, dy);
+}
+
+template <int D, bool kForce>
+__global__ void __launch_bounds__(256) k_nearest_f32(View v) {
+    const int e = v.env0 + blockIdx.y;
+    EnvCtl *c = v.ctl + e;
+    if (!kForce && !c->go) return;
+    const int n = c->n;
+    const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
+    const int beg = blockIdx.x * per;
+    const int end = min(n, beg + per);
+    const float *X = v.fx + (size_t)e * v.stride, *Y = v.fy + (size_t)e * v.stride;
+    const float *Z = D == 3 ? v.fz + (size_t)e * v.stride : nullptr;
+    const double qx = c->x_rand[0], qy = c->x_rand[1], qz = c->x_rand[2];
+    const float fqx = (float)qx, fqy = (float)qy, fqz = (float)qz;
+    float a1 = INFINITY, a2 = INFINITY, a3 = INFINITY;
+    int i1 = INT_MAX, i2 = INT_MAX;
+#define TOP3(xx, yy, zz, ii)                                                          \
+    {                                                                                 \
+        const float dx = fqx - (xx), dy = fqy - (yy);                                 \
+        float a = dx * dx + dy * dy;                                                  \
+        if (D == 3) { const float dz = fqz - (zz); a += dz * dz; }                    \
+        if (a < a3) {                                                                 \
+            if (a < a2) {                                                             \
+                a3 = a2;                                                              \
+                if (a < a1) { a2 = a1; i2 = i1; a1 = a; i1 = (ii); }                  \
+                else { a2 = a; i2 = (ii); }                                           \
+            } else a3 = a;                                                            \
+        }                                                                             \
+    }
+    const int step = 4 * blockDim.x;
+    for (int i = beg + 4 * threadIdx.x; i < end; i += step) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(X + i));
+        const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + i));
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (D == 3) z = __ldg(reinterpret_cast<const float4 *>(Z + i));
+        TOP3(x.x, y.x, z.x, i)
+        if (i + 1 < end) TOP3(x.y, y.y, z.y, i + 1)
+        if (i + 2 < end) TOP3(x.z, y.z, z.z, i + 2)
+        if (i + 3 < end) TOP3(x.w, y.w, z.w, i + 3)
+    }
+#undef TOP3
+    __shared__ float sm_f[8];
+    __shared__ double sm_s[8];
+    __shared__ int sm_i[8];
+    __shared__ int s_fallback;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    float amin = a1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, off));
+    if (threadIdx.x == 0) s_fallback = 0;
+    if (l == 0) sm_f[w] = amin;
+    __syncthreads();
+    amin = sm_f[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) amin = fminf(amin, sm_f[k]);
+    // band in the distance domain, evaluated in double: sqrt(a) <= sqrt(amin) + 2 * margin
+    const double lim = sqrt((double)amin) + 2.0 * c->margin;
+    const double band = lim * lim * 1.0000001;
+    double best_s = XINF; int best_i = INT_MAX;
+    if (beg < end) {
+        if ((double)a3 <= band) s_fallback = 1;
+        if ((double)a1 <= band) lexmin(best_s, best_i, exact_scan_value<D>(v, e, i1, qx, qy, qz), i1);
+        if ((double)a2 <= band) lexmin(best_s, best_i, exact_scan_value<D>(v, e, i2, qx, qy, qz), i2);
+    }
+    __syncthreads();
+    if (s_fallback) {      // exact f64 re-scan of this chunk (same arithmetic as k_nearest)
+        best_s = XINF; best_i = INT_MAX;
+        for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+            const double sv = exact_scan_value<D>(v, e, i, qx, qy, qz);
+            if (sv < best_s) { best_s = sv; best_i = i; }
+        }
+        if (threadIdx.x == 0) atomicAdd(&c->fallbacks, 1);
+    }
+    warp_lexmin(best_s, best_i);
+    if (l == 0) { sm_s[w] = best_s; sm_i[w] = best_i; }
+    __syncthreads();
+    if (w == 0) {
+        best_s = l < 8 ? sm_s[l] : XINF;
+        best_i = l < 8 ? sm_i[l] : INT_MAX;
+        warp_lexmin(best_s, best_i);
+        if (l == 0) {
+            v.part_s[(size_t)e * v.chunks + blockIdx.x] = best_s;
+            v.part_i[(size_t)e * v.chunks + blockIdx.x] = best_i;
+        }
+    }
+}
+
+template <int D, bool kForce>
+__global__ void __launch_bounds__(256) k_near_f32(View v) {
+    const int e = v.env0 + blockIdx.y;
+    EnvCtl *c = v.ctl + e;
+    if (!kForce && (!c->go || c->skip)) return;
+    const int n = c->n;
+    const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
+    const int beg = blockIdx.x * per;
+    const int end = min(n, beg + per);
+    const float *X = v.fx + (size_t)e * v.stride, *Y = v.fy + (size_t)e * v.stride;
+    const float *Z = D == 3 ? v.fz + (size_t)e * v.stride : nullptr;
+    const float fqx = (float)c->x_new[0], fqy = (float)c->x_new[1], fqz = (float)c->x_new[2];
+    const float thr = c->near_thr;
+    int *cand = v.cand + (size_t)e * v.near_cap;
+#define NEARF(xx, yy, zz, ii)                                                         \
+    {                                                                                 \
+        const float dx = fqx - (xx), dy = fqy - (yy);                                 \
+        float a = dx * dx + dy * dy;                                                  \
+        if (D == 3) { const float dz = fqz - (zz); a += dz * dz; }                    \
+        if (a <= thr) {                                                               \
+            const int slot = atomicAdd(&c->cand_cnt, 1);                              \
+            if (slot < v.near_cap) cand[slot] = (ii);                                 \
+        }                                                                             \
+    }
+    const int step = 4 * blockDim.x;
+    for (int i = beg + 4 * threadIdx.x; i < end; i += step) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(X + i));
+        const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + i));
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (D == 3) z = __ldg(reinterpret_cast<const float4 *>(Z + i));
+        NEARF(x.x, y.x, z.x, i)
+        if (i + 1 < end) NEARF(x.y, y.y, z.y, i + 1)
+        if (i + 2 < end) NEARF(x.z, y.z, z.z, i + 2)
+        if (i + 3 < end) NEARF(x.w, y.w, z.w, i + 3)
+    }
+#undef NEARF
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_expand: collision filter of find_near_neighbors (rrt_star_3d.py:141-144), choose_parent
 // (:80-90), rewire (:92-99), InGoalRegion append (irrt_star_3d.py:70-71), search_goal_parent +
 // path length record (rrt_star_3d.py:101-117,225-231), iteration accounting.
 constexpr int kExpandThreads = 128;
-constexpr int kNearSmem = 2048;
+constexpr int kNearSmem = 1024;
 
 __device__ void bitonic_sort_int(int *a, int n_pow2) {
     for (int k = 2; k <= n_pow2; k <<= 1) {
@@ -679,17 +859,21 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
 template <int D>
 __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
     typedef typename GeomOf<D>::type G;
-    const int e = blockIdx.x;
+    const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
     if (!c->go) return;
     __shared__ G g;
     __shared__ int s_cand[kNearSmem];
     __shared__ int s_near[kNearSmem];
     __shared__ double s_d[kNearSmem];
+    __shared__ double s_cost[kNearSmem];                // cost(near_k) before any rewiring of this iteration
+    __shared__ double s_via[kNearSmem];                 // cost(x_new) if near_k became its parent
+    __shared__ unsigned long long s_anc[kNearSmem];     // Near members on near_k's root path (see below)
+    __shared__ unsigned s_bloom[32];
+    __shared__ unsigned s_rew[kNearSmem / 32];
     __shared__ double sm_s[4];
     __shared__ int sm_i[4];
     __shared__ int s_m;
-    __shared__ double s_cnew;
     Node *nodes = v.nodes + (size_t)e * v.stride;
     const int tid = threadIdx.x;
 
@@ -720,8 +904,11 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
                 idx = s_cand[k];
                 const Node nd = load_node(nodes + idx);
                 const double p1[3] = {nd.x, nd.y, nd.z};
-                keep = (idx != new_idx) && !seg_collides(g, xnew, p1);
-                d = vec_dist<D>(XSUB(xnew[0], p1[0]), XSUB(xnew[1], p1[1]), XSUB(xnew[2], p1[2]));
+                const double ex = XSUB(xnew[0], p1[0]), ey = XSUB(xnew[1], p1[1]), ez = XSUB(xnew[2], p1[2]);
+                d = vec_dist<D>(ex, ey, ez);
+                // dist <= r exactly as the reference decides it (the scan may have over-selected)
+                const bool within = D == 3 ? (sq3_rows(ex, ey, ez) <= c->T_near) : (d <= c->r);
+                keep = within && (idx != new_idx) && !seg_collides(g, xnew, p1);
             }
             // block-ordered positions: warp ballots + warp-count prefix through smem
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -746,32 +933,82 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
         if (tid == 0) c->near_cnt = m;
 
         if (m > 0) {
-            // ---- choose_parent
+            // One parallel round of root walks serves ChooseParent, node_new_cost and Rewire.
+            // Every walk also notes which OTHER Near members (and x_new itself when it re-used an
+            // existing vertex) lie on its path: Rewire is sequential in the reference
+            // (rrt_star_3d.py:96-99), a neighbour's cost only changes when one of its ancestors was
+            // re-parented earlier in the same loop, and only then is it walked again.
+            for (int i = tid; i < 32; i += blockDim.x) s_bloom[i] = 0;
+            for (int i = tid; i < kNearSmem / 32; i += blockDim.x) s_rew[i] = 0;
+            __syncthreads();
+            for (int k = tid; k <= m; k += blockDim.x) {
+                const unsigned hsh = ((unsigned)(k < m ? s_near[k] : new_idx) * 2654435761u) >> 22;
+                atomicOr(&s_bloom[hsh >> 5], 1u << (hsh & 31));
+            }
+            __syncthreads();
             double bs = XINF; int bk = INT_MAX;
-            for (int k = tid; k < m; k += blockDim.x) lexmin(bs, bk, XADD(cost_walk<D>(nodes, s_near[k]), s_d[k]), k);
+            for (int k = tid; k < m; k += blockDim.x) {
+                int idx = s_near[k];
+                const Node nd0 = load_node(nodes + idx);
+                double cacc = 0.0;
+                double vacc = edge_len<D>(XSUB(xnew[0], nd0.x), XSUB(xnew[1], nd0.y), XSUB(xnew[2], nd0.z));
+                unsigned long long anc = 0;   // [0,30): three 10-bit positions, [30,32): count, bit 32: overflow, bit 33: through x_new
+                Node cur = nd0;
+                while (idx != 0) {
+                    const int par = (int)cur.parent;
+                    const Node p = load_node(nodes + par);
+                    const double eg = edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
+                    cacc = XADD(cacc, eg); vacc = XADD(vacc, eg);
+                    const unsigned hsh = ((unsigned)par * 2654435761u) >> 22;
+                    if ((s_bloom[hsh >> 5] >> (hsh & 31)) & 1u) {
+                        if (par == new_idx) anc |= 1ull << 33;
+                        else {
+                            int lo = 0, hi = m - 1, pos = -1;
+                            while (lo <= hi) { const int mid = (lo + hi) >> 1; const int vv = s_near[mid]; if (vv == par) { pos = mid; break; } if (vv < par) lo = mid + 1; else hi = mid - 1; }
+                            if (pos >= 0) {
+                                const int cntp = (int)((anc >> 30) & 3ull);
+                                if (cntp < 3) { anc |= (unsigned long long)pos << (10 * cntp); anc = (anc & ~(3ull << 30)) | ((unsigned long long)(cntp + 1) << 30); }
+                                else anc |= 1ull << 32;
+                            }
+                        }
+                    }
+                    idx = par; cur = p;
+                }
+                s_cost[k] = cacc; s_via[k] = vacc; s_anc[k] = anc;
+                lexmin(bs, bk, XADD(cacc, s_d[k]), k);
+            }
             block_lexmin(bs, bk, sm_s, sm_i);
             if (tid == 0) {
-                if (bs < c->curr_cost) { store_parent(nodes + new_idx, s_near[bk]); c->tree_changed = 1; }
+                // ---- choose_parent (rrt_star_3d.py:80-90)
+                double c_new = c->cnew_default;
+                bool new_moved = false;
+                if (bs < c->curr_cost) {
+                    store_parent(nodes + new_idx, s_near[bk]);
+                    c->tree_changed = 1;
+                    c_new = s_via[bk];
+                    new_moved = !c->inserted;      // an existing vertex (duplicate guard) changed its parent
+                }
+                // ---- rewire (rrt_star_3d.py:92-99): ascending index order, later neighbours see earlier re-parentings
+                bool any = false;
+                for (int k = 0; k < m; k++) {
+                    const unsigned long long anc = s_anc[k];
+                    bool dirty = (new_moved && ((anc >> 33) & 1ull)) || (any && ((anc >> 32) & 1ull));
+                    const int cntp = (int)((anc >> 30) & 3ull);
+                    for (int q = 0; q < cntp && !dirty; q++) {
+                        const int pos = (int)((anc >> (10 * q)) & 1023ull);
+                        dirty = (s_rew[pos >> 5] >> (pos & 31)) & 1u;
+                    }
+                    const double ck = dirty ? cost_walk<D>(nodes, s_near[k]) : s_cost[k];
+                    if (ck > XADD(c_new, s_d[k])) {
+                        store_parent(nodes + s_near[k], new_idx);
+                        s_rew[k >> 5] |= 1u << (k & 31);
+                        any = true;
+                        c->tree_changed = 1;
+                    }
+                }
                 __threadfence_block();
             }
             __syncthreads();
-            // ---- rewire: sequential semantics, parallel walks; after each re-parenting the
-            // remaining neighbours are re-evaluated so later ones see earlier changes
-            if (tid == 0) s_cnew = cost_walk<D>(nodes, new_idx);
-            __syncthreads();
-            const double c_new = s_cnew;
-            int start = 0;
-            while (start < m) {
-                int first = INT_MAX;
-                for (int k = start + tid; k < m; k += blockDim.x) {
-                    if (cost_walk<D>(nodes, s_near[k]) > XADD(c_new, s_d[k])) { first = k; break; }
-                }
-                first = block_min_int(first, sm_i);
-                if (first == INT_MAX) break;
-                if (tid == 0) { store_parent(nodes + s_near[first], new_idx); c->tree_changed = 1; __threadfence_block(); }
-                __syncthreads();
-                start = first + 1;
-            }
         }
         // ---- goal bookkeeping
         if (tid == 0) {
@@ -928,6 +1165,13 @@ __global__ void k_set_problems(View v, ProblemUpload u) {
     // tree = {start}, parent[0] = 0 (rrt_base_3d.py:25-28)
     const size_t o = (size_t)e * v.stride;
     v.vx[o] = c->start[0]; v.vy[o] = c->start[1]; v.vz[o] = c->start[2];
+    if (v.fx) { v.fx[o] = (float)c->start[0]; v.fy[o] = (float)c->start[1]; v.fz[o] = (float)c->start[2]; }
+    {
+        double R = 1.0;
+        for (int i = 0; i < 6; i++) R = fmax(R, fabs(g->range[i]));
+        c->margin = R * 0x1p-19;
+        c->fallbacks = 0;
+    }
     Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = c->start[2]; nd.parent = 0;
     v.nodes[o] = nd;
     c->n = 1;
@@ -964,6 +1208,13 @@ __global__ void k_set_problems_2d(View v, ProblemUpload2 u) {
     }
     const size_t o = (size_t)e * v.stride;
     v.vx[o] = c->start[0]; v.vy[o] = c->start[1];
+    if (v.fx) { v.fx[o] = (float)c->start[0]; v.fy[o] = (float)c->start[1]; }
+    {
+        double R = 1.0;
+        for (int i = 0; i < 4; i++) R = fmax(R, fabs(g->range[i]));
+        c->margin = R * 0x1p-19;
+        c->fallbacks = 0;
+    }
     Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = 0.0; nd.parent = 0;
     v.nodes[o] = nd;
     c->n = 1;
@@ -981,6 +1232,14 @@ __global__ void k_scatter_tree(View v, int env, int n, const double *verts, cons
     Node nd; nd.x = verts[D * (size_t)i]; nd.y = verts[D * (size_t)i + 1]; nd.z = D == 3 ? verts[D * (size_t)i + 2] : 0.0; nd.parent = parents[i];
     v.vx[o] = nd.x; v.vy[o] = nd.y;
     if (D == 3) v.vz[o] = nd.z;
+    if (v.fx) {
+        v.fx[o] = (float)nd.x; v.fy[o] = (float)nd.y;
+        if (D == 3) v.fz[o] = (float)nd.z;
+        const double *rg = D == 3 ? v.geom[env].range : v.geom2[env].range;
+        bool out = nd.x < rg[0] || nd.x > rg[1] || nd.y < rg[2] || nd.y > rg[3];
+        if (D == 3) out = out || nd.z < rg[4] || nd.z > rg[5];
+        if (out) atomicOr(&v.ctl[env].err, ERR_OUT_OF_RANGE);
+    }
     v.nodes[o] = nd;
     if (i == 0) { v.ctl[env].n = n; v.ctl[env].tree_changed = 1; }
 }
@@ -1071,6 +1330,13 @@ struct nirrt_batch {
     std::vector<void *> allocs;
     int64_t launches;
     bool goal_lists;   // gc_idx/gc_d allocated
+    // two-group software pipeline (nirrt_batch_run): the problems are split in two halves that run
+    // the same five-kernel sequence on two internal streams, so the latency-bound kernels of one
+    // half (k_top, k_steer, k_expand: dependent pointer chasing) overlap the HBM-bound scans of
+    // the other half
+    int groups;
+    cudaStream_t gs[2];
+    cudaEvent_t ev_fork, ev_join[2];
     // pinned scratch for small synchronous reads
     EnvCtl *h_ctl;
 };
@@ -1100,6 +1366,11 @@ extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
     cudaSetDevice(b->device);
     for (void *p : b->allocs) cudaFree(p);
     if (b->h_ctl) cudaFreeHost(b->h_ctl);
+    for (int g = 0; g < 2; g++) {
+        if (b->gs[g]) cudaStreamDestroy(b->gs[g]);
+        if (b->ev_join[g]) cudaEventDestroy(b->ev_join[g]);
+    }
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     delete b;
     return NIRRT_OK;
 }
@@ -1118,10 +1389,15 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     nirrt_batch *b = new nirrt_batch();
     memset(&b->v, 0, sizeof(View));
     b->device = d->device; b->launches = 0; b->goal_lists = false; b->h_ctl = nullptr;
+    b->groups = 1; b->gs[0] = b->gs[1] = nullptr; b->ev_fork = nullptr; b->ev_join[0] = b->ev_join[1] = nullptr;
     View &v = b->v;
     v.E = d->n_envs; v.cap = d->capacity; v.dim = d->dim;
     v.stride = (d->capacity + 63) & ~63;
-    v.chunks = pick_chunks(v.E);
+    {
+        const char *g = getenv("NIRRT_GROUPS");
+        b->groups = g ? (atoi(g) == 2 ? 2 : 1) : (d->n_envs >= 32 ? 2 : 1);
+    }
+    v.chunks = pick_chunks((v.E + b->groups - 1) / b->groups);
     v.near_cap = d->near_capacity > 0 ? d->near_capacity : kNearSmem;
     v.rec_cap = d->record_capacity > 0 ? d->record_capacity : d->capacity + 8;
     v.sol_cap = v.rec_cap > v.cap + 8 ? v.rec_cap : v.cap + 8;   // at most one append per iteration
@@ -1130,6 +1406,13 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     const size_t EV = (size_t)v.E * v.stride;
     DALLOC(v.vx, double, EV); DALLOC(v.vy, double, EV);
     if (v.dim == 3) DALLOC(v.vz, double, EV);
+    {
+        const char *mode = getenv("NIRRT_SCAN");         // "f64": scan the f64 arrays (no mirror)
+        if (!(mode && strcmp(mode, "f64") == 0)) {
+            DALLOC(v.fx, float, EV); DALLOC(v.fy, float, EV);
+            if (v.dim == 3) DALLOC(v.fz, float, EV);
+        }
+    }
     DALLOC(v.nodes, Node, EV);
     if (v.dim == 3) { DALLOC(v.geom, Geom3, v.E); }
     else {
@@ -1146,6 +1429,13 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     CUDA_TRY(cudaMemset(v.ctl, 0, sizeof(EnvCtl) * v.E));
     CUDA_TRY(cudaMemset(v.mt, 0, sizeof(MtState) * v.E));
     CUDA_TRY(cudaMallocHost((void **)&b->h_ctl, sizeof(EnvCtl) * v.E));
+    if (b->groups == 2) {
+        for (int g = 0; g < 2; g++) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&b->gs[g], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&b->ev_join[g], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    }
     *out = b;
     return NIRRT_OK;
 }
@@ -1452,13 +1742,16 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
     return NIRRT_OK;
 }
 
-static int launch_iteration(nirrt_batch *b, cudaStream_t s) {
-    View &v = b->v;
-    LAUNCH_D(v.dim, k_top, v.E, 128, 0, s, v);
-    LAUNCH_DB(v.dim, k_nearest, false, dim3(v.chunks, v.E), 256, 0, s, v);
-    LAUNCH_D(v.dim, k_steer, v.E, 32, 0, s, v);
-    LAUNCH_DB(v.dim, k_near, false, dim3(v.chunks, v.E), 256, 0, s, v);
-    LAUNCH_D(v.dim, k_expand, v.E, kExpandThreads, 0, s, v);
+static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count) {
+    View v = b->v;
+    v.env0 = env0;
+    LAUNCH_D(v.dim, k_top, count, 128, 0, s, v);
+    if (v.fx) LAUNCH_DB(v.dim, k_nearest_f32, false, dim3(v.chunks, count), 256, 0, s, v);
+    else LAUNCH_DB(v.dim, k_nearest, false, dim3(v.chunks, count), 256, 0, s, v);
+    LAUNCH_D(v.dim, k_steer, count, 32, 0, s, v);
+    if (v.fx) LAUNCH_DB(v.dim, k_near_f32, false, dim3(v.chunks, count), 256, 0, s, v);
+    else LAUNCH_DB(v.dim, k_near, false, dim3(v.chunks, count), 256, 0, s, v);
+    LAUNCH_D(v.dim, k_expand, count, kExpandThreads, 0, s, v);
     b->launches += 5;
     return NIRRT_OK;
 }
@@ -1469,7 +1762,21 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
-    for (int it = 0; it < iters; it++) launch_iteration(b, s);
+    if (b->groups == 1) {
+        for (int it = 0; it < iters; it++) launch_iteration(b, s, 0, v.E);
+    } else {
+        const int h0 = (v.E + 1) / 2, h1 = v.E - h0;
+        CUDA_TRY(cudaEventRecord(b->ev_fork, s));
+        for (int g = 0; g < 2; g++) CUDA_TRY(cudaStreamWaitEvent(b->gs[g], b->ev_fork, 0));
+        for (int it = 0; it < iters; it++) {
+            launch_iteration(b, b->gs[0], 0, h0);
+            if (h1 > 0) launch_iteration(b, b->gs[1], h0, h1);
+        }
+        for (int g = 0; g < 2; g++) {
+            CUDA_TRY(cudaEventRecord(b->ev_join[g], b->gs[g]));
+            CUDA_TRY(cudaStreamWaitEvent(s, b->ev_join[g], 0));
+        }
+    }
     CHECK_LAUNCH();
     return NIRRT_OK;
 }
@@ -1501,11 +1808,13 @@ extern "C" int nirrt_batch_run_profiled_sync(nirrt_batch *b, int iters, float *m
         cudaEventRecord(e[0], s);
         LAUNCH_D(v.dim, k_top, v.E, 128, 0, s, v);
         cudaEventRecord(e[1], s);
-        LAUNCH_DB(v.dim, k_nearest, false, dim3(v.chunks, v.E), 256, 0, s, v);
+        if (v.fx) LAUNCH_DB(v.dim, k_nearest_f32, false, dim3(v.chunks, v.E), 256, 0, s, v);
+    else LAUNCH_DB(v.dim, k_nearest, false, dim3(v.chunks, v.E), 256, 0, s, v);
         cudaEventRecord(e[2], s);
         LAUNCH_D(v.dim, k_steer, v.E, 32, 0, s, v);
         cudaEventRecord(e[3], s);
-        LAUNCH_DB(v.dim, k_near, false, dim3(v.chunks, v.E), 256, 0, s, v);
+        if (v.fx) LAUNCH_DB(v.dim, k_near_f32, false, dim3(v.chunks, v.E), 256, 0, s, v);
+    else LAUNCH_DB(v.dim, k_near, false, dim3(v.chunks, v.E), 256, 0, s, v);
         cudaEventRecord(e[4], s);
         LAUNCH_D(v.dim, k_expand, v.E, kExpandThreads, 0, s, v);
         cudaEventRecord(e[5], s);
@@ -1540,6 +1849,7 @@ static std::string err_bits(int err) {
     if (err & ERR_PATH_DEPTH) m += " path deeper than 4096 edges;";
     if (err & ERR_RECORD_OVERFLOW) m += " record buffer overflow;";
     if (err & ERR_GOAL_OVERFLOW) m += " goal-candidate overflow;";
+    if (err & ERR_OUT_OF_RANGE) m += " a loaded vertex lies outside the world range (the f32 scan margin assumes vertices inside it);";
     return m;
 }
 
@@ -1792,7 +2102,7 @@ extern "C" int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int
 extern "C" int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *reserved) {
     if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
     if (kernel_launches) *kernel_launches = b->launches;
-    if (reserved) *reserved = 0;
+    if (reserved) *reserved = (b->v.fx ? 4 : 8) * b->v.dim;   // bytes per vertex one scan pass reads
     return NIRRT_OK;
 }
 
@@ -1808,15 +2118,20 @@ extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, f
     CUDA_TRY(cudaSetDevice(b->device));
     TRY(fetch_ctl(b, s));
     int64_t total = 0;
-    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * 8 * v.dim;
+    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * (v.fx ? 4 : 8) * v.dim;
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
     float acc = 0.f;
     for (int r = 0; r < reps; r++) {
         if (which == 1) k_reset_cand<<<(v.E + 127) / 128, 128, 0, s>>>(v);
         CUDA_TRY(cudaEventRecord(e0, s));
-        if (which == 0) LAUNCH_DB(v.dim, k_nearest, true, dim3(v.chunks, v.E), 256, 0, s, v);
-        else LAUNCH_DB(v.dim, k_near, true, dim3(v.chunks, v.E), 256, 0, s, v);
+        if (v.fx) {
+            if (which == 0) LAUNCH_DB(v.dim, k_nearest_f32, true, dim3(v.chunks, v.E), 256, 0, s, v);
+            else LAUNCH_DB(v.dim, k_near_f32, true, dim3(v.chunks, v.E), 256, 0, s, v);
+        } else {
+            if (which == 0) LAUNCH_DB(v.dim, k_nearest, true, dim3(v.chunks, v.E), 256, 0, s, v);
+            else LAUNCH_DB(v.dim, k_near, true, dim3(v.chunks, v.E), 256, 0, s, v);
+        }
         CUDA_TRY(cudaEventRecord(e1, s));
         CUDA_TRY(cudaEventSynchronize(e1));
         float t = 0.f;
