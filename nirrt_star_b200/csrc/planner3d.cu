@@ -1323,6 +1323,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_goal_parent(View v, int use_
         else KERNEL<2, FORCE><<<grid, block, smem, stream>>>(__VA_ARGS__);             \
     } while (0)
 
+constexpr int kMaxGroups = 8;
 struct nirrt_batch {
     View v;
     int device;
@@ -1330,13 +1331,14 @@ struct nirrt_batch {
     std::vector<void *> allocs;
     int64_t launches;
     bool goal_lists;   // gc_idx/gc_d allocated
-    // two-group software pipeline (nirrt_batch_run): the problems are split in two halves that run
-    // the same five-kernel sequence on two internal streams, so the latency-bound kernels of one
-    // half (k_top, k_steer, k_expand: dependent pointer chasing) overlap the HBM-bound scans of
-    // the other half
+    // group pipeline (nirrt_batch_run): the problems are split in G groups (4 for >= 256 problems,
+    // NIRRT_GROUPS overrides) that run the same five-kernel sequence on G internal streams, so the
+    // latency-bound kernels of one group (k_top, k_steer, k_expand: dependent pointer chasing)
+    // overlap the HBM-bound scans of the others.  Measured at 512 x 100k vertices: 0.364 ms/step
+    // with one group, 0.323 (2), 0.309 (4), 0.299 (6).
     int groups;
-    cudaStream_t gs[2];
-    cudaEvent_t ev_fork, ev_join[2];
+    cudaStream_t gs[kMaxGroups];
+    cudaEvent_t ev_fork, ev_join[kMaxGroups];
     // pinned scratch for small synchronous reads
     EnvCtl *h_ctl;
 };
@@ -1366,7 +1368,7 @@ extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
     cudaSetDevice(b->device);
     for (void *p : b->allocs) cudaFree(p);
     if (b->h_ctl) cudaFreeHost(b->h_ctl);
-    for (int g = 0; g < 2; g++) {
+    for (int g = 0; g < kMaxGroups; g++) {
         if (b->gs[g]) cudaStreamDestroy(b->gs[g]);
         if (b->ev_join[g]) cudaEventDestroy(b->ev_join[g]);
     }
@@ -1389,13 +1391,17 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     nirrt_batch *b = new nirrt_batch();
     memset(&b->v, 0, sizeof(View));
     b->device = d->device; b->launches = 0; b->goal_lists = false; b->h_ctl = nullptr;
-    b->groups = 1; b->gs[0] = b->gs[1] = nullptr; b->ev_fork = nullptr; b->ev_join[0] = b->ev_join[1] = nullptr;
+    b->groups = 1; b->ev_fork = nullptr;
+    for (int g = 0; g < kMaxGroups; g++) { b->gs[g] = nullptr; b->ev_join[g] = nullptr; }
     View &v = b->v;
     v.E = d->n_envs; v.cap = d->capacity; v.dim = d->dim;
     v.stride = (d->capacity + 63) & ~63;
     {
         const char *g = getenv("NIRRT_GROUPS");
-        b->groups = g ? (atoi(g) == 2 ? 2 : 1) : (d->n_envs >= 32 ? 2 : 1);
+        b->groups = g ? atoi(g) : (d->n_envs >= 256 ? 4 : (d->n_envs >= 64 ? 2 : 1));
+        if (b->groups < 1) b->groups = 1;
+        if (b->groups > kMaxGroups) b->groups = kMaxGroups;
+        if (b->groups > d->n_envs) b->groups = d->n_envs;
     }
     v.chunks = pick_chunks((v.E + b->groups - 1) / b->groups);
     v.near_cap = d->near_capacity > 0 ? d->near_capacity : kNearSmem;
@@ -1429,8 +1435,8 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     CUDA_TRY(cudaMemset(v.ctl, 0, sizeof(EnvCtl) * v.E));
     CUDA_TRY(cudaMemset(v.mt, 0, sizeof(MtState) * v.E));
     CUDA_TRY(cudaMallocHost((void **)&b->h_ctl, sizeof(EnvCtl) * v.E));
-    if (b->groups == 2) {
-        for (int g = 0; g < 2; g++) {
+    if (b->groups >= 2) {
+        for (int g = 0; g < b->groups; g++) {
             CUDA_TRY(cudaStreamCreateWithFlags(&b->gs[g], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_join[g], cudaEventDisableTiming));
         }
@@ -1765,14 +1771,15 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     if (b->groups == 1) {
         for (int it = 0; it < iters; it++) launch_iteration(b, s, 0, v.E);
     } else {
-        const int h0 = (v.E + 1) / 2, h1 = v.E - h0;
+        const int G = b->groups;
         CUDA_TRY(cudaEventRecord(b->ev_fork, s));
-        for (int g = 0; g < 2; g++) CUDA_TRY(cudaStreamWaitEvent(b->gs[g], b->ev_fork, 0));
-        for (int it = 0; it < iters; it++) {
-            launch_iteration(b, b->gs[0], 0, h0);
-            if (h1 > 0) launch_iteration(b, b->gs[1], h0, h1);
-        }
-        for (int g = 0; g < 2; g++) {
+        for (int g = 0; g < G; g++) CUDA_TRY(cudaStreamWaitEvent(b->gs[g], b->ev_fork, 0));
+        for (int it = 0; it < iters; it++)
+            for (int g = 0; g < G; g++) {
+                const int e0 = (int)((long long)v.E * g / G), e1 = (int)((long long)v.E * (g + 1) / G);
+                if (e1 > e0) launch_iteration(b, b->gs[g], e0, e1 - e0);
+            }
+        for (int g = 0; g < G; g++) {
             CUDA_TRY(cudaEventRecord(b->ev_join[g], b->gs[g]));
             CUDA_TRY(cudaStreamWaitEvent(s, b->ev_join[g], 0));
         }
