@@ -84,23 +84,24 @@ __global__ void __launch_bounds__(256) k_prep(const float *pc, int dim, const fl
 // k_fps: farthest_point_sample (pointnet2_utils.py:65-86).  One CTA per cloud, the cloud's running
 // min-distance lives in registers (PPT points per thread), one barrier per selected point.
 // dist = (dx*dx + dy*dy) + dz*dz in fp32 without contraction; argmax ties -> lowest index.
-template <int PPT>
-__global__ void __launch_bounds__(256) k_fps(const float *xyz, int N, int npoint, const int *start, int level,
-                                             int *fidx, float *new_xyz) {
+template <int T, int PPT>
+__global__ void __launch_bounds__(T) k_fps(const float *xyz, int N, int npoint, const int *start, int level,
+                                           int *fidx, float *new_xyz) {
     extern __shared__ float s_xyz[];          // [N][3]
-    __shared__ float s_d[2][8];
-    __shared__ int s_i[2][8];
+    constexpr int NW = T / 32;
+    __shared__ unsigned s_d[2][NW];
+    __shared__ int s_i[2][NW];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *X = xyz + (size_t)b * N * 3;
-    for (int i = tid; i < N * 3; i += 256) s_xyz[i] = X[i];
+    for (int i = tid; i < N * 3; i += T) s_xyz[i] = X[i];
     __syncthreads();
     float px[PPT], py[PPT], pz[PPT], dist[PPT];
 #pragma unroll
     for (int j = 0; j < PPT; j++) {
-        const int i = tid + j * 256;
+        const int i = tid + j * T;
         const bool in = i < N;
         px[j] = in ? s_xyz[i * 3] : 0.f; py[j] = in ? s_xyz[i * 3 + 1] : 0.f; pz[j] = in ? s_xyz[i * 3 + 2] : 0.f;
-        dist[j] = in ? 1e10f : -1.f;           // padding lanes can never win the argmax
+        dist[j] = in ? 1e10f : 0.f;
     }
     int far = start[b * 4 + level];
     for (int it = 0; it < npoint; it++) {
@@ -110,30 +111,27 @@ __global__ void __launch_bounds__(256) k_fps(const float *xyz, int N, int npoint
             float *o = new_xyz + ((size_t)b * npoint + it) * 3;
             o[0] = cx; o[1] = cy; o[2] = cz;
         }
-        float bd = -2.f; int bi = 0x7fffffff;
+        // distances are >= 0, so their bit patterns order like unsigned integers: the arg-max with
+        // lowest-index ties is a max-reduction on the bits followed by a min-reduction on the index
+        unsigned bd = 0; int bi = 0x7fffffff;
 #pragma unroll
         for (int j = 0; j < PPT; j++) {
+            const int i = tid + j * T;
             const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(py[j], cy), dz = __fsub_rn(pz[j], cz);
             const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
             if (d < dist[j]) dist[j] = d;
-            if (dist[j] > bd) { bd = dist[j]; bi = tid + j * 256; }
+            const unsigned u = __float_as_uint(dist[j]);
+            if (i < N && (u > bd || bi == 0x7fffffff)) { bd = u; bi = i; }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, bd, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
+        unsigned wm = __reduce_max_sync(0xffffffffu, bd);
+        int wi = __reduce_min_sync(0xffffffffu, (bd == wm) ? bi : 0x7fffffff);
         const int slot = it & 1;
-        if (lane == 0) { s_d[slot][warp] = bd; s_i[slot][warp] = bi; }
+        if (lane == 0) { s_d[slot][warp] = wm; s_i[slot][warp] = wi; }
         __syncthreads();
-        bd = s_d[slot][0]; bi = s_i[slot][0];
-#pragma unroll
-        for (int w = 1; w < 8; w++) {
-            const float od = s_d[slot][w]; const int oi = s_i[slot][w];
-            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-        far = bi;
+        bd = lane < NW ? s_d[slot][lane] : 0u;
+        bi = lane < NW ? s_i[slot][lane] : 0x7fffffff;
+        wm = __reduce_max_sync(0xffffffffu, bd);
+        far = __reduce_min_sync(0xffffffffu, (bd == wm && lane < NW) ? bi : 0x7fffffff);
     }
 }
 
@@ -142,7 +140,9 @@ __global__ void __launch_bounds__(256) k_fps(const float *xyz, int N, int npoint
 // One warp per centroid scans the cloud in index order (32 points per step, ballot + prefix
 // popcount), keeps the first K members of each ball and pads with the first member.  Distances use
 // the reference's expansion -2*a.b + |a|^2 + |b|^2 (square_distance, :39-41).
-__global__ void __launch_bounds__(256) k_ball_query(const float *xyz, int N, const float *new_xyz, int S,
+// small batches: one WARP per centroid (32 points per step, ballot + prefix popcount) -- more parallelism
+// when there are few clouds; large batches use the one-thread-per-centroid kernel below
+__global__ void __launch_bounds__(256) k_ball_query_warp(const float *xyz, int N, const float *new_xyz, int S,
                                                     float r0sq, int K0, float r1sq, int K1, int *g0, int *g1) {
     extern __shared__ float s_pts[];          // x[N] y[N] z[N] sq[N]
     float *sx = s_pts, *sy = sx + N, *sz = sy + N, *sq = sz + N;
@@ -182,6 +182,41 @@ __global__ void __launch_bounds__(256) k_ball_query(const float *xyz, int N, con
     // pad with the first member (group_first); an empty ball cannot occur: the centroid is a member
     if (cnt0 < K0) { const int f = cnt0 > 0 ? o0[0] : 0; for (int p = cnt0 + lane; p < K0; p += 32) o0[p] = f; }
     if (cnt1 < K1) { const int f = cnt1 > 0 ? o1[0] : 0; for (int p = cnt1 + lane; p < K1; p += 32) o1[p] = f; }
+}
+
+__global__ void __launch_bounds__(256) k_ball_query(const float *xyz, int N, const float *new_xyz, int S,
+                                                    float r0sq, int K0, float r1sq, int K1, int *g0, int *g1) {
+    extern __shared__ float4 s_p4[];          // [N] (x, y, z, x*x + y*y + z*z): one broadcast LDS.128 per point
+    const int b = blockIdx.y;
+    const float *X = xyz + (size_t)b * N * 3;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float x = X[i * 3], y = X[i * 3 + 1], z = X[i * 3 + 2];
+        s_p4[i] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    }
+    __syncthreads();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const float *c = new_xyz + ((size_t)b * S + s) * 3;
+    const float cx = c[0], cy = c[1], cz = c[2];
+    const float cs = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
+    int *o0 = g0 + ((size_t)b * S + s) * K0, *o1 = g1 + ((size_t)b * S + s) * K1;
+    int cnt0 = 0, cnt1 = 0, f0 = 0, f1 = 0;
+    // the thread walks the cloud in index order and keeps the first K members of each ball
+    for (int i = 0; i < N; i++) {
+        const float4 p = s_p4[i];
+        const float dot = __fmaf_rn(cz, p.z, __fmaf_rn(cy, p.y, __fmul_rn(cx, p.x)));
+        float d = __fmul_rn(-2.f, dot);
+        d = __fadd_rn(d, cs);
+        d = __fadd_rn(d, p.w);
+        if (!(d > r1sq)) {                       // r0 < r1: members of the small ball are members of the large one
+            if (cnt1 < K1) { if (cnt1 == 0) f1 = i; o1[cnt1++] = i; }
+            if (!(d > r0sq) && cnt0 < K0) { if (cnt0 == 0) f0 = i; o0[cnt0++] = i; }
+            if (cnt1 >= K1 && cnt0 >= K0) break;
+        }
+    }
+    // pad with the first member (group_first); an empty ball cannot occur: the centroid is a member
+    for (int p = cnt0; p < K0; p++) o0[p] = f0;
+    for (int p = cnt1; p < K1; p++) o1[p] = f1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,7 +297,8 @@ __device__ __forceinline__ void top3_insert(Top3 &t, float d, int i) {
         } else { t.d[2] = d; t.i[2] = i; }
     }
 }
-__global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const float *xyz2, int S, const __half *feat1, int C1,
+// small batches: one warp per fine point (lane-strided scan + 3 warp arg-min rounds)
+__global__ void __launch_bounds__(256) k_interp_warp(const float *xyz1, int N, const float *xyz2, int S, const __half *feat1, int C1,
                                                 const __half *feat2, int C2, int B, __half *out) {
     const int lane = threadIdx.x & 31;
     const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -315,6 +351,66 @@ __global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const 
         const float x = __fadd_rn(__fadd_rn(__fmul_rn(a0.x, w0), __fmul_rn(a1.x, w1)), __fmul_rn(a2.x, w2));
         const float y = __fadd_rn(__fadd_rn(__fmul_rn(a0.y, w0), __fmul_rn(a1.y, w1)), __fmul_rn(a2.y, w2));
         oi[k] = __floats2half2_rn(fminf(x, 65504.f), fminf(y, 65504.f));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const float *xyz2, int S, const __half *feat1, int C1,
+                                                const __half *feat2, int C2, int B, __half *out) {
+    // phase 1: one thread per fine point walks the S coarse points (broadcast LDS.128) keeping its
+    // three nearest in ascending (distance, index) order -- the first three entries of the
+    // reference's sort; phase 2: the warp's 32 results are broadcast one at a time and all lanes
+    // interpolate / copy the channels of that point.
+    extern __shared__ float4 s_q4[];          // [S] (x, y, z, |q|^2)
+    const int b = blockIdx.y;
+    const float *Q = xyz2 + (size_t)b * S * 3;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const float x = Q[i * 3], y = Q[i * 3 + 1], z = Q[i * 3 + 2];
+        s_q4[i] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);     // first fine point of this warp
+    const int pi = i0 + lane;
+    Top3 t;
+    t.d[0] = t.d[1] = t.d[2] = INFINITY; t.i[0] = t.i[1] = t.i[2] = 0;
+    if (pi < N) {
+        const float *a = xyz1 + ((size_t)b * N + pi) * 3;
+        const float ax = a[0], ay = a[1], az = a[2];
+        const float as = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+        for (int s = 0; s < S; s++) {
+            const float4 q = s_q4[s];
+            const float dot = __fmaf_rn(az, q.z, __fmaf_rn(ay, q.y, __fmul_rn(ax, q.x)));
+            float d = __fmul_rn(-2.f, dot);
+            d = __fadd_rn(d, as);
+            d = __fadd_rn(d, q.w);
+            top3_insert(t, d, s);             // strict <: equal distances keep the lower index first
+        }
+    }
+    const float r0 = __fdiv_rn(1.f, __fadd_rn(t.d[0], 1e-8f)), r1 = __fdiv_rn(1.f, __fadd_rn(t.d[1], 1e-8f)),
+                r2 = __fdiv_rn(1.f, __fadd_rn(t.d[2], 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+    const int cnt = min(32, N - i0);
+    for (int j = 0; j < cnt; j++) {
+        const int n0 = __shfl_sync(0xffffffffu, t.i[0], j), n1 = __shfl_sync(0xffffffffu, t.i[1], j), n2 = __shfl_sync(0xffffffffu, t.i[2], j);
+        const float u0 = __shfl_sync(0xffffffffu, w0, j), u1 = __shfl_sync(0xffffffffu, w1, j), u2 = __shfl_sync(0xffffffffu, w2, j);
+        const size_t p = (size_t)b * N + i0 + j;
+        __half *o = out + p * (size_t)(C1 + C2);
+        if (C1 > 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(feat1 + p * (size_t)C1);
+            uint4 *dst = reinterpret_cast<uint4 *>(o);
+            for (int k = lane; k < (C1 >> 3); k += 32) dst[k] = src[k];
+        }
+        const __half2 *f0 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + n0) * C2);
+        const __half2 *f1 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + n1) * C2);
+        const __half2 *f2 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + n2) * C2);
+        __half2 *oi = reinterpret_cast<__half2 *>(o + C1);
+        for (int k = lane; k < (C2 >> 1); k += 32) {
+            const float2 a0 = __half22float2(f0[k]), a1 = __half22float2(f1[k]), a2 = __half22float2(f2[k]);
+            const float x = __fadd_rn(__fadd_rn(__fmul_rn(a0.x, u0), __fmul_rn(a1.x, u1)), __fmul_rn(a2.x, u2));
+            const float y = __fadd_rn(__fadd_rn(__fmul_rn(a0.y, u0), __fmul_rn(a1.y, u1)), __fmul_rn(a2.y, u2));
+            oi[k] = __floats2half2_rn(fminf(x, 65504.f), fminf(y, 65504.f));
+        }
     }
 }
 
@@ -392,6 +488,7 @@ static int gemm_attr() {
     PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PCUDA(cudaFuncSetAttribute(k_ball_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    PCUDA(cudaFuncSetAttribute(k_ball_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     g_gemm_attr = true;
     return NIRRT_OK;
 }
@@ -405,18 +502,41 @@ struct Conv {
     CUtensorMap tmW;
 };
 
+static int g_num_sms = 0;
+
 static int launch_gemm(const Conv &c, const __half *A, int M, int mode, __half *out, int ldo, int col_off, int group,
                        cudaStream_t s) {
     PTRY(gemm_attr());
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
     CUtensorMap tmA;
     PTRY(make_tmap(&tmA, A, (uint64_t)M, (uint64_t)c.K, umma::kBM));
     umma::GemmArgs g;
     g.M = M; g.N = c.N; g.K = c.K; g.BN = c.BN;
-    const int nkb = (c.K + umma::kBK - 1) / umma::kBK;
-    g.stages = nkb < umma::kMaxStages ? nkb : umma::kMaxStages;
     g.ldo = ldo; g.col_off = col_off; g.group = group; g.bias = c.b; g.out = out;
+    // CTAs per SM: bounded by TMEM (two accumulator buffers each) and shared memory; the stage count is
+    // the largest of 4/3/2 that keeps that many CTAs resident
+    int cps = 512 / (2 * umma::tmem_cols_for(c.BN));
+    if (cps > 8) cps = 8;
+    if (cps < 1) cps = 1;
+    const int nkb = (c.K + umma::kBK - 1) / umma::kBK;
+    int stages = nkb == 1 ? 2 : 4;      // one K block per tile: two stages already overlap consecutive tiles
+    for (;; ) {
+        const umma::SmemLayout L = umma::smem_layout(g.BN, stages);
+        if ((size_t)cps * (L.total + 1024 + 1024) <= 224 * 1024) break;
+        if (stages > 2) stages--;
+        else if (cps > 1) { cps--; stages = nkb == 1 ? 2 : 4; }
+        else break;
+    }
+    g.stages = stages;
     const umma::SmemLayout L = umma::smem_layout(g.BN, g.stages);
-    const dim3 grid((M + umma::kBM - 1) / umma::kBM, (c.N + c.BN - 1) / c.BN);
+    const int ntiles = (M + umma::kBM - 1) / umma::kBM;
+    const int gx = ntiles < g_num_sms * cps ? ntiles : g_num_sms * cps;
+    const dim3 grid(gx, (c.N + c.BN - 1) / c.BN);
     const size_t smem = (size_t)L.total + 1024;
     if (mode == umma::MODE_STORE) umma::k_gemm<umma::MODE_STORE><<<grid, umma::kThreads, smem, s>>>(tmA, c.tmW, g);
     else umma::k_gemm<umma::MODE_POOL><<<grid, umma::kThreads, smem, s>>>(tmA, c.tmW, g);
@@ -617,11 +737,13 @@ struct StageTimer {
 static int fps_launch(nirrt_pn2 *h, int B, int l, const int *start, cudaStream_t s) {
     const int N = h->n[l - 1], np = h->n[l];
     const size_t smem = (size_t)N * 3 * sizeof(float);
-    const int ppt = (N + 255) / 256;
-    if (ppt <= 1) k_fps<1><<<B, 256, smem, s>>>(h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]);
-    else if (ppt <= 4) k_fps<4><<<B, 256, smem, s>>>(h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]);
-    else if (ppt <= 8) k_fps<8><<<B, 256, smem, s>>>(h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]);
-    else k_fps<16><<<B, 256, smem, s>>>(h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]);
+#define FPS_ARGS h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]
+    if (N <= 64) k_fps<64, 1><<<B, 64, smem, s>>>(FPS_ARGS);
+    else if (N <= 256) k_fps<256, 1><<<B, 256, smem, s>>>(FPS_ARGS);
+    else if (N <= 1024) k_fps<512, 2><<<B, 512, smem, s>>>(FPS_ARGS);
+    else if (N <= 2048) k_fps<512, 4><<<B, 512, smem, s>>>(FPS_ARGS);
+    else k_fps<1024, 4><<<B, 1024, smem, s>>>(FPS_ARGS);
+#undef FPS_ARGS
     PCUDA(cudaGetLastError());
     h->launches++;
     return NIRRT_OK;
@@ -652,8 +774,14 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
         {
             StageTimer t(h, s, 2);
             const float r0 = (float)(kRad[l - 1][0] * kRad[l - 1][0]), r1 = (float)(kRad[l - 1][1] * kRad[l - 1][1]);
-            k_ball_query<<<dim3((S + 7) / 8, B), 256, (size_t)N * 4 * sizeof(float), s>>>(
-                h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
+            if ((long long)B * S >= 65536) {
+                const int bt = S >= 256 ? 256 : ((S + 31) / 32) * 32;
+                k_ball_query<<<dim3((S + bt - 1) / bt, B), bt, (size_t)N * 4 * sizeof(float), s>>>(
+                    h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
+            } else {
+                k_ball_query_warp<<<dim3((S + 7) / 8, B), 256, (size_t)N * 4 * sizeof(float), s>>>(
+                    h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
+            }
             PCUDA(cudaGetLastError());
             h->launches++;
         }
@@ -696,7 +824,13 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
         const int rows = B * N;
         {
             StageTimer t(h, s, 5);
-            k_interp<<<(rows + 7) / 8, 256, 0, s>>>(h->xyz[lo], N, h->xyz[lo + 1], S, C1 ? h->feat[lo] : nullptr, C1, upf, upC, B, h->bufA);
+            if ((long long)B * N >= 65536) {
+                const int bt = N >= 256 ? 256 : ((N + 31) / 32) * 32;
+                k_interp<<<dim3((N + bt - 1) / bt, B), bt, (size_t)S * sizeof(float4), s>>>(h->xyz[lo], N, h->xyz[lo + 1], S, C1 ? h->feat[lo] : nullptr,
+                                                                                              C1, upf, upC, B, h->bufA);
+            } else {
+                k_interp_warp<<<(rows + 7) / 8, 256, 0, s>>>(h->xyz[lo], N, h->xyz[lo + 1], S, C1 ? h->feat[lo] : nullptr, C1, upf, upC, B, h->bufA);
+            }
             PCUDA(cudaGetLastError());
             h->launches++;
         }

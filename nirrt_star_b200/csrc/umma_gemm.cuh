@@ -120,12 +120,23 @@ __host__ __device__ inline SmemLayout smem_layout(int BN, int stages) {
     L.a_bytes = kBM * 128;
     L.stage_bytes = L.a_bytes + ((BN * 128 + 1023) & ~1023);
     L.bars_off = stages * L.stage_bytes;
-    L.bias_off = L.bars_off + 128;                       // 2*stages+1 barriers + tmem pointer
+    L.bias_off = L.bars_off + 128;                       // 2*stages+4 barriers + tmem pointer
     L.scratch_off = L.bias_off + 256 * 4;
-    L.total = L.scratch_off + 4 * 32 * 17 * 4;
+    L.total = L.scratch_off + 4 * 32 * 20 * 4;           // per epilogue warp: 32 x 17 floats (pool) or 32 x 80 B (store staging)
     return L;
 }
+__host__ __device__ inline int tmem_cols_for(int bn) {
+    int c = 32;
+    while (c < bn) c <<= 1;
+    return c;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
+// Persistent: each CTA walks the M tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its N slice.
+// The TMA ring keeps running across tiles, and the accumulator is double buffered in TMEM
+// (2 x tmem_cols_for(bn) columns) so the epilogue of tile t overlaps the loads and MMAs of tile t+1.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) k_gemm(const __grid_constant__ CUtensorMap tmA,
                                                    const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
@@ -135,24 +146,25 @@ __global__ void __launch_bounds__(kThreads) k_gemm(const __grid_constant__ CUten
     const SmemLayout L = smem_layout(g.BN, g.stages);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L.bars_off);
     uint64_t *empty = full + kMaxStages;
-    uint64_t *tmem_full = empty + kMaxStages;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint64_t *tfull = empty + kMaxStages;       // [2] accumulator buffer ready for the epilogue
+    uint64_t *tempty = tfull + 2;               // [2] accumulator buffer drained
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty + 2);
     float *s_bias = reinterpret_cast<float *>(smem + L.bias_off);
     float *s_scratch = reinterpret_cast<float *>(smem + L.scratch_off);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM;
     const int n0 = blockIdx.y * g.BN;
     const int bn = min(g.BN, g.N - n0);                  // multiple of 16
     const int nkb = (g.K + kBK - 1) / kBK;
-    int tmem_cols = 32;
-    while (tmem_cols < bn) tmem_cols <<= 1;
+    const int ntiles = (g.M + kBM - 1) / kBM;
+    const int buf_cols = tmem_cols_for(bn);
+    const int tmem_cols = 2 * buf_cols;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmW);
         for (int s = 0; s < g.stages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -169,86 +181,122 @@ __global__ void __launch_bounds__(kThreads) k_gemm(const __grid_constant__ CUten
     if (warp == 0) {
         if (lane == 0) {
             const uint32_t tx = (uint32_t)(L.a_bytes + g.BN * 128);
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % g.stages;
-                const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-                mbar_wait(empty + s, ph ^ 1u);
-                mbar_expect_tx(full + s, tx);
-                uint8_t *sa = smem + s * L.stage_bytes;
-                tma_load_2d(sa, &tmA, kb * kBK, m0, full + s);
-                tma_load_2d(sa + L.a_bytes, &tmW, kb * kBK, n0, full + s);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = tile * kBM;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
+                    mbar_wait(empty + s, ph ^ 1u);
+                    mbar_expect_tx(full + s, tx);
+                    uint8_t *sa = smem + s * L.stage_bytes;
+                    tma_load_2d(sa, &tmA, kb * kBK, m0, full + s);
+                    tma_load_2d(sa + L.a_bytes, &tmW, kb * kBK, n0, full + s);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(bn);
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % g.stages;
-                const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-                mbar_wait(full + s, ph);
+            int it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+                const int buf = tcount & 1;
+                mbar_wait(tempty + buf, (uint32_t)((tcount >> 1) & 1) ^ 1u);     // epilogue drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + s * L.stage_bytes);
-                const uint32_t sw = sa + L.a_bytes;
-                const int ksteps = min(kBK, g.K - kb * kBK) >> 4;
-                for (int k = 0; k < ksteps; k++)
-                    mma_f16(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sw + k * 32), idesc, (uint32_t)((kb | k) != 0));
-                mma_commit(empty + s);          // frees the stage once these MMAs have read it
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * buf_cols);
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
+                    mbar_wait(full + s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + s * L.stage_bytes);
+                    const uint32_t sw = sa + L.a_bytes;
+                    const int ksteps = min(kBK, g.K - kb * kBK) >> 4;
+                    for (int k = 0; k < ksteps; k++)
+                        mma_f16(d_tmem, make_smem_desc(sa + k * 32), make_smem_desc(sw + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                    mma_commit(empty + s);          // frees the stage once these MMAs have read it
+                }
+                mma_commit(tfull + buf);            // accumulator of this tile complete
             }
-            mma_commit(tmem_full);              // accumulator complete
         }
     } else {
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + q * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (MODE == MODE_STORE) {
-            __half *orow = g.out + (size_t)row * g.ldo + n0;
-            for (int c = 0; c < bn; c += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c, v);
-                if (row < g.M) {
-                    uint32_t p[8];
+        float *sc = s_scratch + q * (32 * 20);
+        const int cl = lane & 15, half = lane >> 4;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+            const int buf = tcount & 1;
+            const int m0 = tile * kBM;
+            mbar_wait(tfull + buf, (uint32_t)((tcount >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * buf_cols);
+            if (MODE == MODE_STORE) {
+                // Each thread owns one output row; a thread can store only 16 B per instruction, and
+                // 32 threads writing 16 B at the row pitch would hit 32 half-filled sectors (measured:
+                // 3.6x DRAM write amplification).  The 32 x (<=32 columns) block of this warp is
+                // therefore transposed through shared memory and written as whole 32-byte sectors:
+                // 4 (or 2) lanes per row, 8 (or 16) rows per instruction.
+                uint4 *stg = reinterpret_cast<uint4 *>(sc);          // [32 rows][5 x 16 B] (80-byte pitch)
+                const int row0 = m0 + q * 32;
+                for (int c = 0; c < bn; c += 32) {
+                    const int w = min(32, bn - c);                   // 16 or 32 columns
+                    for (int h = 0; h < w; h += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(taddr + c + h, v);
+                        uint32_t p[8];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float a = fmaxf(__uint_as_float(v[2 * i]) + s_bias[c + 2 * i], 0.f);
-                        const float b = fmaxf(__uint_as_float(v[2 * i + 1]) + s_bias[c + 2 * i + 1], 0.f);
-                        p[i] = pack_half2_sat(a, b);
+                        for (int i = 0; i < 8; i++) {
+                            const float a = fmaxf(__uint_as_float(v[2 * i]) + s_bias[c + h + 2 * i], 0.f);
+                            const float b = fmaxf(__uint_as_float(v[2 * i + 1]) + s_bias[c + h + 2 * i + 1], 0.f);
+                            p[i] = pack_half2_sat(a, b);
+                        }
+                        stg[lane * 5 + (h >> 3)] = make_uint4(p[0], p[1], p[2], p[3]);
+                        stg[lane * 5 + (h >> 3) + 1] = make_uint4(p[4], p[5], p[6], p[7]);
                     }
-                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c);
-                    dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                    dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                    __syncwarp();
+                    const int ppr = w >> 3;                          // 16-byte pieces per row: 2 or 4
+                    const int rpi = 32 / ppr;                        // rows per store instruction
+                    const int piece = lane % ppr;
+                    for (int j = 0; j < 32; j += rpi) {
+                        const int r = j + lane / ppr;
+                        if (row0 + r < g.M)
+                            *reinterpret_cast<uint4 *>(g.out + (size_t)(row0 + r) * g.ldo + n0 + c + piece * 8) = stg[r * 5 + piece];
+                    }
+                    __syncwarp();
+                }
+            } else {
+                for (int c = 0; c < bn; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) sc[lane * 17 + i] = (row < g.M) ? __uint_as_float(v[i]) : -INFINITY;
+                    __syncwarp();
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int r = 0; r < 16; r++) mx = fmaxf(mx, sc[(half * 16 + r) * 17 + cl]);
+                    __syncwarp();
+                    if (g.group == 32) {
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+                        const int grp = (m0 + q * 32) / 32;
+                        if (half == 0 && m0 + q * 32 < g.M)
+                            g.out[(size_t)grp * g.ldo + g.col_off + n0 + c + cl] =
+                                __float2half_rn(fminf(fmaxf(mx + s_bias[c + cl], 0.f), 65504.f));
+                    } else {
+                        const int grp = (m0 + q * 32) / 16 + half;
+                        if (m0 + q * 32 + half * 16 < g.M)
+                            g.out[(size_t)grp * g.ldo + g.col_off + n0 + c + cl] =
+                                __float2half_rn(fminf(fmaxf(mx + s_bias[c + cl], 0.f), 65504.f));
+                    }
                 }
             }
-        } else {
-            float *sc = s_scratch + q * (32 * 17);
-            const int cl = lane & 15, half = lane >> 4;
-            for (int c = 0; c < bn; c += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c, v);
-#pragma unroll
-                for (int i = 0; i < 16; i++) sc[lane * 17 + i] = (row < g.M) ? __uint_as_float(v[i]) : -INFINITY;
-                __syncwarp();
-                float mx = -INFINITY;
-#pragma unroll
-                for (int r = 0; r < 16; r++) mx = fmaxf(mx, sc[(half * 16 + r) * 17 + cl]);
-                __syncwarp();
-                if (g.group == 32) {
-                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-                    const int grp = (m0 + q * 32) / 32;
-                    if (half == 0 && m0 + q * 32 < g.M)
-                        g.out[(size_t)grp * g.ldo + g.col_off + n0 + c + cl] =
-                            __float2half_rn(fminf(fmaxf(mx + s_bias[c + cl], 0.f), 65504.f));
-                } else {
-                    const int grp = (m0 + q * 32) / 16 + half;
-                    if (m0 + q * 32 + half * 16 < g.M)
-                        g.out[(size_t)grp * g.ldo + g.col_off + n0 + c + cl] =
-                            __float2half_rn(fminf(fmaxf(mx + s_bias[c + cl], 0.f), 65504.f));
-                }
-            }
+            // this warp is done reading the buffer: let the MMA warp reuse it
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + buf);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
