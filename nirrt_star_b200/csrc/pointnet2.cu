@@ -27,6 +27,7 @@
 #include "../../include/nirrt_pointnet2.h"
 #include "errors.h"
 #include "umma_gemm.cuh"
+#include "sa_fused.cuh"
 
 static int pfail(int code, const std::string &msg) { return nirrt_set_error(code, msg); }
 #define PCUDA(expr)                                                                                   \
@@ -500,6 +501,8 @@ struct Conv {
     __half *w = nullptr;           // [N][K]
     float *b = nullptr;            // [N]
     CUtensorMap tmW;
+    std::vector<__half> hw;        // host copies (used to build the fused kernels' shared-memory images)
+    std::vector<float> hb;
 };
 
 static int g_num_sms = 0;
@@ -561,6 +564,9 @@ struct nirrt_pn2 {
     int *fidx[4] = {nullptr, nullptr, nullptr, nullptr};
     int *grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     __half *bufA = nullptr, *bufB = nullptr;
+    uint8_t *sa1_img[2] = {nullptr, nullptr};   // fused sa1 kernels: swizzled weight images + biases per radius
+    float *sa1_bias[2] = {nullptr, nullptr};
+    bool fused_sa1 = true;
     __half *up[4] = {nullptr, nullptr, nullptr, nullptr};     // outputs of fp4 (level 3) .. fp1 (level 0)
     // staging for the host-pointer entry point
     float *d_pc = nullptr, *d_sm = nullptr, *d_gm = nullptr, *d_score = nullptr, *d_logp = nullptr;
@@ -604,6 +610,7 @@ static int upload_conv(nirrt_pn2 *h, Conv &c, const nirrt_pn2_layer &L, const st
         for (int k = 0; k < c.K; k++)
             if (remap[k] >= 0) w[(size_t)n * c.K + k] = __float2half_rn(L.weight[(size_t)n * L.c_in + remap[k]] * s);
     }
+    c.hw = w; c.hb = b;
     PTRY(palloc(h, &c.w, w.size()));
     PTRY(palloc(h, &c.b, b.size()));
     PCUDA(cudaMemcpy(c.w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
@@ -715,6 +722,31 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
     for (int i = 0; i < 2; i++)
         if (cudaEventCreate(&h->ev[i]) != cudaSuccess) FAILC("cudaEventCreate failed");
     if (gemm_attr()) { nirrt_pn2_destroy(h); return NIRRT_ERR_CUDA; }
+    {
+        const char *f = getenv("NIRRT_PN2_FUSED");
+        h->fused_sa1 = !(f && atoi(f) == 0);
+        for (int sc = 0; sc < 2 && h->fused_sa1; sc++) {
+            size_t rows = 0;
+            for (int j = 0; j < 3; j++) rows += h->conv[sc * 3 + j].N;
+            std::vector<uint8_t> img(rows * 128, 0);
+            std::vector<float> bias;
+            size_t r0 = 0;
+            for (int j = 0; j < 3; j++) {
+                const Conv &c = h->conv[sc * 3 + j];
+                if (c.K > 64) FAILC("fused sa1: K > 64");
+                for (int n = 0; n < c.N; n++)
+                    for (int k = 0; k < c.K; k++)
+                        memcpy(&img[r0 * 128 + safused::sw128_off(n, k >> 3) + (k & 7) * 2], &c.hw[(size_t)n * c.K + k], 2);
+                bias.insert(bias.end(), c.hb.begin(), c.hb.end());
+                r0 += c.N;
+            }
+            TRYC(palloc(h, &h->sa1_img[sc], img.size()));
+            TRYC(palloc(h, &h->sa1_bias[sc], bias.size()));
+            if (cudaMemcpy(h->sa1_img[sc], img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(h->sa1_bias[sc], bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+                FAILC("fused sa1: weight image upload failed");
+        }
+    }
 #undef FAILC
 #undef TRYC
     *out = h;
@@ -789,6 +821,22 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
             const int K = kK[sc];
             const int rows = B * S * K;
             const Conv &c0 = h->conv[li], &c1 = h->conv[li + 1], &c2 = h->conv[li + 2];
+            if (l == 1 && h->fused_sa1) {
+                // gather + 3 layers + max-pool in one persistent tcgen05 kernel (sa_fused.cuh)
+                StageTimer t(h, s, 4);
+                safused::Args fa;
+                fa.in6 = h->in6; fa.new_xyz = h->xyz[1]; fa.gidx = h->grp[sc]; fa.wimg = h->sa1_img[sc]; fa.bias = h->sa1_bias[sc];
+                fa.out = h->feat[1]; fa.N = N; fa.S = S; fa.B = B; fa.ldo = kC[1]; fa.col_off = sc == 0 ? 0 : h->conv[2].N;
+                if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
+                const int ntiles = rows / 128;
+                const int grid = ntiles < g_num_sms * 8 ? ntiles : g_num_sms * 8;
+                if (sc == 0) safused::k_sa1_fused<16, 16, 16, 32><<<grid, 128, safused::smem_bytes<16, 16, 32>(), s>>>(fa);
+                else safused::k_sa1_fused<32, 32, 32, 64><<<grid, 128, safused::smem_bytes<32, 32, 64>(), s>>>(fa);
+                PCUDA(cudaGetLastError());
+                h->launches++;
+                li += 3;
+                continue;
+            }
             {
                 StageTimer t(h, s, 3);
                 if (l == 1) {
