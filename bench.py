@@ -326,7 +326,7 @@ def bench_pointnet2(args, world, rank, local, peaks, cpu=True):
            "e2e": {"value": world * Bc / e2e_s, "unit": "clouds/s", "h2d_bytes_per_step": float(pc.nbytes + sm.nbytes + gm.nbytes + fs.nbytes),
                    "d2h_bytes_per_step": float(Bc * N * 12), "what": "nirrt_pn2_classify_sync with pinned host buffers"},
            "gpu_launches": int(launches), "stage_ms": stages,
-           "roofline": {"bound": "tensor", "kernel": "umma::k_gemm (24 SA-MLP launches, tcgen05 kind::f16)", "achieved": sa_tflops,
+           "roofline": {"bound": "tensor", "kernel": "SA MLPs: safused::k_sa1_fused x2 (gather + 3 layers + pool) + 18 umma::k_gemm launches, tcgen05 kind::f16", "achieved": sa_tflops,
                         "peak": peak, "unit": "TFLOP/s", "frac": sa_tflops / peak, "traffic": None,
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (of measured)" if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s (of fallback)",
                         "algorithmic_flops_per_step": 2 * PN2_GMAC_SA * Bc}}

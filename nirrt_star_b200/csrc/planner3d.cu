@@ -1223,38 +1223,6 @@ __global__ void k_set_problems_2d(View v, ProblemUpload2 u) {
     c->c_best = XINF; c->c_update = XINF; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
 }
 
-// AoS (reference layout, [cap][dim]) <-> device layout
-__global__ void k_scatter_tree(View v, int env, int n, const double *verts, const long long *parents) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int D = v.dim;
-    const size_t o = (size_t)env * v.stride + i;
-    Node nd; nd.x = verts[D * (size_t)i]; nd.y = verts[D * (size_t)i + 1]; nd.z = D == 3 ? verts[D * (size_t)i + 2] : 0.0; nd.parent = parents[i];
-    v.vx[o] = nd.x; v.vy[o] = nd.y;
-    if (D == 3) v.vz[o] = nd.z;
-    if (v.fx) {
-        v.fx[o] = (float)nd.x; v.fy[o] = (float)nd.y;
-        if (D == 3) v.fz[o] = (float)nd.z;
-        const double *rg = D == 3 ? v.geom[env].range : v.geom2[env].range;
-        bool out = nd.x < rg[0] || nd.x > rg[1] || nd.y < rg[2] || nd.y > rg[3];
-        if (D == 3) out = out || nd.z < rg[4] || nd.z > rg[5];
-        if (out) atomicOr(&v.ctl[env].err, ERR_OUT_OF_RANGE);
-    }
-    v.nodes[o] = nd;
-    if (i == 0) { v.ctl[env].n = n; v.ctl[env].tree_changed = 1; }
-}
-__global__ void k_gather_tree(View v, int env, double *verts, long long *parents) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.cap) return;
-    const int D = v.dim;
-    const int n = v.ctl[env].n;
-    Node nd; nd.x = nd.y = nd.z = 0.0; nd.parent = 0;
-    if (i < n) nd = v.nodes[(size_t)env * v.stride + i];
-    verts[D * (size_t)i] = nd.x; verts[D * (size_t)i + 1] = nd.y;
-    if (D == 3) verts[D * (size_t)i + 2] = nd.z;
-    parents[i] = nd.parent;
-}
-
 // stand-alone predicates ---------------------------------------------------------------------------
 template <int D>
 __global__ void k_collide_edges(View v, int env, const double *edges, long long m, uint8_t *out) {
@@ -1670,6 +1638,49 @@ extern "C" int nirrt_batch_set_cloud(nirrt_batch *b, int env, const double *poin
     return NIRRT_OK;
 }
 
+// Tree transfers move whole groups of problems per copy (staging <= 2 GB): two large PCIe
+// transfers and one layout kernel per group instead of per-problem copies.
+static int tree_chunk(const View &v) {
+    const size_t per_env = (size_t)v.cap * (v.dim * sizeof(double) + sizeof(long long));
+    size_t c = ((size_t)2 << 30) / (per_env ? per_env : 1);
+    if (c < 1) c = 1;
+    return (int)(c > 65535 ? 65535 : c);
+}
+__global__ void k_scatter_trees(View v, int env_begin, const int *n, const double *verts, const long long *parents) {
+    const int k = blockIdx.y;
+    const int nk = n[k];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x) {
+        const int D = v.dim, env = env_begin + k;
+        const double *vs = verts + ((size_t)k * v.cap + i) * D;
+        const size_t o = (size_t)env * v.stride + i;
+        Node nd; nd.x = vs[0]; nd.y = vs[1]; nd.z = D == 3 ? vs[2] : 0.0; nd.parent = parents[(size_t)k * v.cap + i];
+        v.vx[o] = nd.x; v.vy[o] = nd.y;
+        if (D == 3) v.vz[o] = nd.z;
+        if (v.fx) {
+            v.fx[o] = (float)nd.x; v.fy[o] = (float)nd.y;
+            if (D == 3) v.fz[o] = (float)nd.z;
+            const double *rg = D == 3 ? v.geom[env].range : v.geom2[env].range;
+            bool out = nd.x < rg[0] || nd.x > rg[1] || nd.y < rg[2] || nd.y > rg[3];
+            if (D == 3) out = out || nd.z < rg[4] || nd.z > rg[5];
+            if (out) atomicOr(&v.ctl[env].err, ERR_OUT_OF_RANGE);
+        }
+        v.nodes[o] = nd;
+        if (i == 0) { v.ctl[env].n = nk; v.ctl[env].tree_changed = 1; }
+    }
+}
+__global__ void k_gather_trees(View v, int env_begin, double *verts, long long *parents) {
+    const int k = blockIdx.y, env = env_begin + k, D = v.dim;
+    const int n = v.ctl[env].n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.cap; i += gridDim.x * blockDim.x) {
+        Node nd; nd.x = nd.y = nd.z = 0.0; nd.parent = 0;
+        if (i < n) nd = v.nodes[(size_t)env * v.stride + i];
+        double *vs = verts + ((size_t)k * v.cap + i) * D;
+        vs[0] = nd.x; vs[1] = nd.y;
+        if (D == 3) vs[2] = nd.z;
+        parents[(size_t)k * v.cap + i] = nd.parent;
+    }
+}
+
 extern "C" int nirrt_batch_load_trees(nirrt_batch *b, int env_begin, int count, const int *n,
                                       const double *vertices, const int64_t *parents, void *stream) {
     if (!b || !n || !vertices || !parents) return fail(NIRRT_ERR_INVALID, "nirrt_batch_load_trees: null argument");
@@ -1677,30 +1688,23 @@ extern "C" int nirrt_batch_load_trees(nirrt_batch *b, int env_begin, int count, 
     if (env_begin < 0 || count < 0 || env_begin + count > v.E) return fail(NIRRT_ERR_INVALID, "env range out of bounds");
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
-    int maxn = 0;
-    for (int k = 0; k < count; k++) {
+    for (int k = 0; k < count; k++)
         if (n[k] < 1 || n[k] > v.cap) return fail(NIRRT_ERR_INVALID, "tree size out of range");
-        if (n[k] > maxn) maxn = n[k];
-    }
-    // double-buffered staging so the copy of problem k+1 overlaps the scatter of problem k
+    if (count == 0) return NIRRT_OK;
+    const int chunk = tree_chunk(v) < count ? tree_chunk(v) : count;
     TempBufs t;
-    double *dv[2]; long long *dp[2];
-    cudaEvent_t ev[2];
-    for (int q = 0; q < 2; q++) {
-        TRY(t.make<double>(v.dim * (size_t)maxn, &dv[q])); TRY(t.make<long long>((size_t)maxn, &dp[q]));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming));
-    }
-    for (int k = 0; k < count; k++) {
-        const int q = k & 1;
-        if (k >= 2) CUDA_TRY(cudaEventSynchronize(ev[q]));
-        CUDA_TRY(cudaMemcpyAsync(dv[q], vertices + (size_t)k * v.cap * v.dim, sizeof(double) * v.dim * n[k], cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(dp[q], parents + (size_t)k * v.cap, sizeof(long long) * n[k], cudaMemcpyHostToDevice, s));
-        k_scatter_tree<<<(n[k] + 255) / 256, 256, 0, s>>>(v, env_begin + k, n[k], dv[q], dp[q]);
+    double *dv; long long *dp; int *dn;
+    TRY(t.make<double>((size_t)chunk * v.cap * v.dim, &dv)); TRY(t.make<long long>((size_t)chunk * v.cap, &dp)); TRY(t.make<int>((size_t)count, &dn));
+    CUDA_TRY(cudaMemcpyAsync(dn, n, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+    for (int k0 = 0; k0 < count; k0 += chunk) {
+        const int m = count - k0 < chunk ? count - k0 : chunk;
+        CUDA_TRY(cudaMemcpyAsync(dv, vertices + (size_t)k0 * v.cap * v.dim, sizeof(double) * v.dim * v.cap * m, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(dp, parents + (size_t)k0 * v.cap, sizeof(long long) * v.cap * m, cudaMemcpyHostToDevice, s));
+        const int gx = (v.cap + 255) / 256 < 256 ? (v.cap + 255) / 256 : 256;
+        k_scatter_trees<<<dim3(gx, m), 256, 0, s>>>(v, env_begin + k0, dn + k0, dv, dp);
         CHECK_LAUNCH();
-        CUDA_TRY(cudaEventRecord(ev[q], s));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
-    for (int q = 0; q < 2; q++) cudaEventDestroy(ev[q]);
     return NIRRT_OK;
 }
 
@@ -1712,20 +1716,21 @@ extern "C" int nirrt_batch_read_trees_sync(nirrt_batch *b, int env_begin, int co
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(b->h_ctl, v.ctl, sizeof(EnvCtl) * v.E, cudaMemcpyDeviceToHost, s));
+    if (count == 0) { CUDA_TRY(cudaStreamSynchronize(s)); return NIRRT_OK; }
+    const int chunk = tree_chunk(v) < count ? tree_chunk(v) : count;
     TempBufs t;
-    double *dv[2]; long long *dp[2];
-    for (int q = 0; q < 2; q++) { TRY(t.make<double>(v.dim * (size_t)v.cap, &dv[q])); TRY(t.make<long long>((size_t)v.cap, &dp[q])); }
-    CUDA_TRY(cudaStreamSynchronize(s));
-    for (int k = 0; k < count; k++) {
-        const int q = k & 1;
-        if (k >= 2) CUDA_TRY(cudaStreamSynchronize(s));   // staging buffer q is free again
-        k_gather_tree<<<(v.cap + 255) / 256, 256, 0, s>>>(v, env_begin + k, dv[q], dp[q]);
+    double *dv; long long *dp;
+    TRY(t.make<double>((size_t)chunk * v.cap * v.dim, &dv)); TRY(t.make<long long>((size_t)chunk * v.cap, &dp));
+    for (int k0 = 0; k0 < count; k0 += chunk) {
+        const int m = count - k0 < chunk ? count - k0 : chunk;
+        const int gx = (v.cap + 255) / 256 < 256 ? (v.cap + 255) / 256 : 256;
+        k_gather_trees<<<dim3(gx, m), 256, 0, s>>>(v, env_begin + k0, dv, dp);
         CHECK_LAUNCH();
-        CUDA_TRY(cudaMemcpyAsync(vertices + (size_t)k * v.cap * v.dim, dv[q], sizeof(double) * v.dim * v.cap, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(parents + (size_t)k * v.cap, dp[q], sizeof(long long) * v.cap, cudaMemcpyDeviceToHost, s));
-        n[k] = b->h_ctl[env_begin + k].n;
+        CUDA_TRY(cudaMemcpyAsync(vertices + (size_t)k0 * v.cap * v.dim, dv, sizeof(double) * v.dim * v.cap * m, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(parents + (size_t)k0 * v.cap, dp, sizeof(long long) * v.cap * m, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
+    for (int k = 0; k < count; k++) n[k] = b->h_ctl[env_begin + k].n;
     return NIRRT_OK;
 }
 

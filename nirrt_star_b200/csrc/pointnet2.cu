@@ -564,9 +564,9 @@ struct nirrt_pn2 {
     int *fidx[4] = {nullptr, nullptr, nullptr, nullptr};
     int *grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     __half *bufA = nullptr, *bufB = nullptr;
-    uint8_t *sa1_img[2] = {nullptr, nullptr};   // fused sa1 kernels: swizzled weight images + biases per radius
-    float *sa1_bias[2] = {nullptr, nullptr};
-    bool fused_sa1 = true;
+    uint8_t *sa_img[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // fused sa1 / sa2 kernels: swizzled weight
+    float *sa_bias[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};    // images + biases per level and radius
+    int fused_levels = 2;                                               // 0: none, 1: sa1, 2: sa1 + sa2
     __half *up[4] = {nullptr, nullptr, nullptr, nullptr};     // outputs of fp4 (level 3) .. fp1 (level 0)
     // staging for the host-pointer entry point
     float *d_pc = nullptr, *d_sm = nullptr, *d_gm = nullptr, *d_score = nullptr, *d_logp = nullptr;
@@ -724,27 +724,35 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
     if (gemm_attr()) { nirrt_pn2_destroy(h); return NIRRT_ERR_CUDA; }
     {
         const char *f = getenv("NIRRT_PN2_FUSED");
-        h->fused_sa1 = !(f && atoi(f) == 0);
-        for (int sc = 0; sc < 2 && h->fused_sa1; sc++) {
-            size_t rows = 0;
-            for (int j = 0; j < 3; j++) rows += h->conv[sc * 3 + j].N;
-            std::vector<uint8_t> img(rows * 128, 0);
-            std::vector<float> bias;
-            size_t r0 = 0;
-            for (int j = 0; j < 3; j++) {
-                const Conv &c = h->conv[sc * 3 + j];
-                if (c.K > 64) FAILC("fused sa1: K > 64");
-                for (int n = 0; n < c.N; n++)
-                    for (int k = 0; k < c.K; k++)
-                        memcpy(&img[r0 * 128 + safused::sw128_off(n, k >> 3) + (k & 7) * 2], &c.hw[(size_t)n * c.K + k], 2);
-                bias.insert(bias.end(), c.hb.begin(), c.hb.end());
-                r0 += c.N;
+        h->fused_levels = f ? atoi(f) : 2;
+        if (h->fused_levels < 0 || h->fused_levels > 2) h->fused_levels = 2;
+        for (int l = 0; l < h->fused_levels; l++)
+            for (int sc = 0; sc < 2; sc++) {
+                size_t bytes = 0;
+                for (int j = 0; j < 3; j++) { const Conv &c = h->conv[l * 6 + sc * 3 + j]; bytes += (size_t)c.N * safused::nblk(c.K) * 128; }
+                std::vector<uint8_t> img(bytes, 0);
+                std::vector<float> bias;
+                size_t base = 0;
+                for (int j = 0; j < 3; j++) {
+                    const Conv &c = h->conv[l * 6 + sc * 3 + j];
+                    for (int n = 0; n < c.N; n++)
+                        for (int k = 0; k < c.K; k++)
+                            memcpy(&img[base + safused::w_off(c.N, n, k >> 3) + (k & 7) * 2], &c.hw[(size_t)n * c.K + k], 2);
+                    bias.insert(bias.end(), c.hb.begin(), c.hb.end());
+                    base += (size_t)c.N * safused::nblk(c.K) * 128;
+                }
+                TRYC(palloc(h, &h->sa_img[l][sc], img.size()));
+                TRYC(palloc(h, &h->sa_bias[l][sc], bias.size()));
+                if (cudaMemcpy(h->sa_img[l][sc], img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaMemcpy(h->sa_bias[l][sc], bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+                    FAILC("fused SA: weight image upload failed");
             }
-            TRYC(palloc(h, &h->sa1_img[sc], img.size()));
-            TRYC(palloc(h, &h->sa1_bias[sc], bias.size()));
-            if (cudaMemcpy(h->sa1_img[sc], img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-                cudaMemcpy(h->sa1_bias[sc], bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
-                FAILC("fused sa1: weight image upload failed");
+        if (h->fused_levels >= 2) {
+            if (cudaFuncSetAttribute(safused::k_sa_fused<16, 96, 112, 64, 64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)safused::Smem<112, 64, 64, 128>::kTotal) != cudaSuccess ||
+                cudaFuncSetAttribute(safused::k_sa_fused<32, 96, 112, 64, 96, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)safused::Smem<112, 64, 96, 128>::kTotal) != cudaSuccess)
+                FAILC("fused SA: cudaFuncSetAttribute failed");
         }
     }
 #undef FAILC
@@ -821,17 +829,21 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
             const int K = kK[sc];
             const int rows = B * S * K;
             const Conv &c0 = h->conv[li], &c1 = h->conv[li + 1], &c2 = h->conv[li + 2];
-            if (l == 1 && h->fused_sa1) {
+            if (l <= h->fused_levels) {
                 // gather + 3 layers + max-pool in one persistent tcgen05 kernel (sa_fused.cuh)
                 StageTimer t(h, s, 4);
                 safused::Args fa;
-                fa.in6 = h->in6; fa.new_xyz = h->xyz[1]; fa.gidx = h->grp[sc]; fa.wimg = h->sa1_img[sc]; fa.bias = h->sa1_bias[sc];
-                fa.out = h->feat[1]; fa.N = N; fa.S = S; fa.B = B; fa.ldo = kC[1]; fa.col_off = sc == 0 ? 0 : h->conv[2].N;
+                fa.in6 = h->in6; fa.feat = h->feat[l - 1]; fa.xyz = h->xyz[l - 1]; fa.new_xyz = h->xyz[l]; fa.gidx = h->grp[(l - 1) * 2 + sc];
+                fa.wimg = h->sa_img[l - 1][sc]; fa.bias = h->sa_bias[l - 1][sc];
+                fa.out = h->feat[l]; fa.N = N; fa.S = S; fa.B = B; fa.ldo = kC[l]; fa.col_off = sc == 0 ? 0 : h->conv[li - 1].N;
                 if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
                 const int ntiles = rows / 128;
-                const int grid = ntiles < g_num_sms * 8 ? ntiles : g_num_sms * 8;
-                if (sc == 0) safused::k_sa1_fused<16, 16, 16, 32><<<grid, 128, safused::smem_bytes<16, 16, 32>(), s>>>(fa);
-                else safused::k_sa1_fused<32, 32, 32, 64><<<grid, 128, safused::smem_bytes<32, 32, 64>(), s>>>(fa);
+                const int cps = l == 1 ? 8 : (sc == 0 ? 3 : 2);
+                const int grid = ntiles < g_num_sms * cps ? ntiles : g_num_sms * cps;
+                if (l == 1 && sc == 0) safused::k_sa_fused<16, 0, 16, 16, 16, 32><<<grid, 128, safused::Smem<16, 16, 16, 32>::kTotal, s>>>(fa);
+                else if (l == 1) safused::k_sa_fused<32, 0, 16, 32, 32, 64><<<grid, 128, safused::Smem<16, 32, 32, 64>::kTotal, s>>>(fa);
+                else if (sc == 0) safused::k_sa_fused<16, 96, 112, 64, 64, 128><<<grid, 128, safused::Smem<112, 64, 64, 128>::kTotal, s>>>(fa);
+                else safused::k_sa_fused<32, 96, 112, 64, 96, 128><<<grid, 128, safused::Smem<112, 64, 96, 128>::kTotal, s>>>(fa);
                 PCUDA(cudaGetLastError());
                 h->launches++;
                 li += 3;

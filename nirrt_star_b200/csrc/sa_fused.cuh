@@ -1,19 +1,20 @@
-// sa_fused.cuh -- first set-abstraction level of PointNet++ as ONE persistent kernel per radius:
+// sa_fused.cuh -- a set-abstraction scale of PointNet++ as ONE persistent kernel:
 // grouping (gather + centroid subtraction), the three 1x1 convolutions (+ folded BatchNorm + ReLU)
 // and the max over the K neighbours (pointnet2_utils.py:243-259), for 128 (centroid, neighbour) rows
 // per tile.  The tile's activations never leave the SM: the gathered operand and every intermediate
-// layer live in one 16 KB shared-memory tile in the tcgen05 K-major / 128-byte-swizzle layout, the
-// accumulators in TMEM; weights (<= 16 KB) are copied into shared memory once per CTA.
+// layer live in one shared-memory tile in the tcgen05 K-major / 128-byte-swizzle layout (one 16 KB
+// block per 64 channels), the accumulators in TMEM; the weights of all three layers are copied into
+// shared memory once per CTA.  Used for sa1 (6 input channels) and sa2 (96); the wider levels keep
+// their weights in L2 and go through umma::k_gemm.
 //
 //   128 threads, thread = row = TMEM lane.  Per layer: all threads write their row of the operand,
-//   fence.proxy.async + __syncthreads, thread 0 issues tcgen05.mma (K <= 64: one or two
-//   instructions) and commits to an mbarrier, all threads wait, tcgen05.ld their accumulator row.
-//   Up to 8 CTAs per SM hide each other's round trips.
+//   fence.proxy.async + __syncthreads, thread 0 issues the tcgen05.mma instructions (K / 16 of them)
+//   and commits to an mbarrier, all threads wait, tcgen05.ld their accumulator row.  Several CTAs per
+//   SM hide each other's round trips.
 //
-// sa1 has the 6-channel network input as point features: rows are the 16 halves
-//   [x y z start goal free | rx ry rz | x_lo y_lo z_lo | rx_lo ry_lo rz_lo | 0]
-// (hi + lo split of the coordinates, see k_group_sa1), K = 16; layer widths 16/16/32 (K = 16
-// neighbours) and 32/32/64 (K = 32).
+// Operand rows (coordinates travel as fp16 hi + lo pairs, the weight columns are repeated):
+//   sa1   [x y z start goal free | rx ry rz | x_lo y_lo z_lo | rx_lo ry_lo rz_lo | 0]          K0 = 16
+//   sa2   [96 features | rx ry rz rx_lo ry_lo rz_lo 0 0 | 0 x 8]                               K0 = 112
 #pragma once
 #include "umma_gemm.cuh"
 
@@ -21,68 +22,88 @@ namespace safused {
 
 using umma::smem_u32;
 
-// byte offset of 16-byte chunk `c` of row `r` in a K-major SWIZZLE_128B tile (rows of 128 bytes,
-// 8-row groups of 1024 bytes, chunk index XOR (r mod 8))
+// byte offset of 16-byte chunk `c` (0..7) of row `r` in a K-major SWIZZLE_128B block (rows of 128
+// bytes, 8-row groups of 1024 bytes, chunk index XOR (r mod 8))
 __host__ __device__ __forceinline__ int sw128_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
+// operand tile: logical chunk cc of row r (block cc / 8 of 16 KB)
+__device__ __forceinline__ int a_off(int r, int cc) { return (cc >> 3) * 16384 + sw128_off(r, cc & 7); }
+// weight image of a layer with n rows: block kb is n * 128 bytes
+__host__ __device__ __forceinline__ size_t w_off(int n_rows, int n, int cc) { return (size_t)(cc >> 3) * n_rows * 128 + sw128_off(n, cc & 7); }
+__host__ __device__ constexpr int nblk(int k) { return (k + 63) / 64; }
+__host__ __device__ constexpr int imax(int a, int b) { return a > b ? a : b; }
 
 struct Args {
-    const float *in6;       // [B][N][6]
-    const float *new_xyz;   // [B][S][3]
+    const float *in6;       // sa1: [B][N][6] network input
+    const __half *feat;     // sa2: [B][N][C] features of the previous level
+    const float *xyz;       // [B][N][3] coordinates of the previous level (sa2)
+    const float *new_xyz;   // [B][S][3] centroids
     const int *gidx;        // [B][S][G]
-    const uint8_t *wimg;    // W1 | W2 | W3 shared-memory images (N_l rows x 128 B, swizzled)
+    const uint8_t *wimg;    // W1 | W2 | W3 shared-memory images
     const float *bias;      // [N1 + N2 + N3]
     __half *out;            // [B][S][ldo]
     int N, S, B, ldo, col_off;
 };
 
+__device__ __forceinline__ void split_hi_lo(float x, __half &hi, __half &lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(__fsub_rn(x, __half2float(hi)));
+}
+
+// accumulator row -> relu(. + bias) -> fp16 -> this thread's row of the next operand tile
 template <int NCOLS>
-__device__ __forceinline__ void ld_row(uint32_t taddr, float *v) {       // NCOLS accumulator columns of this thread's lane
-#pragma unroll
+__device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, uint8_t *sA, int r, const float *bias) {
+#pragma unroll 1
     for (int h = 0; h < NCOLS; h += 16) {
         uint32_t u[16];
         umma::tmem_ld16(taddr + h, u);
+        uint32_t p[8];
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[h + i] = __uint_as_float(u[i]);
-    }
-}
-
-// relu(v + bias) -> fp16 -> this thread's row of the next operand tile
-template <int NCOLS>
-__device__ __forceinline__ void store_row(uint8_t *sA, int r, const float *v, const float *bias) {
-#pragma unroll
-    for (int c = 0; c < NCOLS / 8; c++) {
-        uint32_t p[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float a = fmaxf(v[c * 8 + 2 * i] + bias[c * 8 + 2 * i], 0.f);
-            const float b = fmaxf(v[c * 8 + 2 * i + 1] + bias[c * 8 + 2 * i + 1], 0.f);
+        for (int i = 0; i < 8; i++) {
+            const float a = fmaxf(__uint_as_float(u[2 * i]) + bias[h + 2 * i], 0.f);
+            const float b = fmaxf(__uint_as_float(u[2 * i + 1]) + bias[h + 2 * i + 1], 0.f);
             p[i] = umma::pack_half2_sat(a, b);
         }
-        *reinterpret_cast<uint4 *>(sA + sw128_off(r, c)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4 *>(sA + a_off(r, h >> 3)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4 *>(sA + a_off(r, (h >> 3) + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
     }
 }
 
-template <int K>
-__device__ __forceinline__ void issue(uint32_t d_tmem, uint32_t sa, uint32_t sw, int n, uint64_t *bar) {
-    const uint32_t idesc = umma::make_idesc(n);
+template <int K, int NROWS>
+__device__ __forceinline__ void issue(uint32_t d_tmem, uint32_t sa, uint32_t sw, uint64_t *bar) {
+    const uint32_t idesc = umma::make_idesc(NROWS);
 #pragma unroll
-    for (int k = 0; k < K / 16; k++)
-        umma::mma_f16(d_tmem, umma::make_smem_desc(sa + k * 32), umma::make_smem_desc(sw + k * 32), idesc, (uint32_t)(k != 0));
+    for (int kb = 0; kb < nblk(K); kb++) {
+        const int ksteps = (K - 64 * kb < 64 ? K - 64 * kb : 64) / 16;
+#pragma unroll
+        for (int k = 0; k < ksteps; k++)
+            umma::mma_f16(d_tmem, umma::make_smem_desc(sa + kb * 16384 + k * 32), umma::make_smem_desc(sw + kb * NROWS * 128 + k * 32),
+                          idesc, (uint32_t)((kb | k) != 0));
+    }
     umma::mma_commit(bar);
 }
 
-template <int G, int N1, int N2, int N3>
-__global__ void __launch_bounds__(128) k_sa1_fused(const Args a) {
-    constexpr int K0 = 16;
+template <int K0, int N1, int N2, int N3>
+struct Smem {
+    static constexpr int kABytes = imax(imax(nblk(K0), nblk(N1)), nblk(N2)) * 16384;
+    static constexpr int kW1 = N1 * nblk(K0) * 128, kW2 = N2 * nblk(N1) * 128, kW3 = N3 * nblk(N2) * 128;
+    static constexpr int kBias = (N1 + N2 + N3 + 2) * 4;
+    static constexpr size_t kTotal = 1024 + (size_t)kABytes + kW1 + kW2 + kW3 + kBias + 64;
+};
+
+// C == 0: sa1 (in6 input); C > 0: features [.,C] of the previous level + relative coordinates
+template <int G, int C, int K0, int N1, int N2, int N3>
+__global__ void __launch_bounds__(128) k_sa_fused(const Args a) {
+    typedef Smem<K0, N1, N2, N3> SM;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-    uint8_t *sA = smem;                                   // 16 KB operand tile (also the pooling scratch)
-    uint8_t *sW1 = sA + 16384, *sW2 = sW1 + N1 * 128, *sW3 = sW2 + N2 * 128;
-    float *s_bias = reinterpret_cast<float *>(sW3 + N3 * 128);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(s_bias + N1 + N2 + N3 + ((N1 + N2 + N3) & 1));
+    uint8_t *sA = smem;                                   // operand tile (also the pooling scratch)
+    uint8_t *sW1 = sA + SM::kABytes, *sW2 = sW1 + SM::kW1, *sW3 = sW2 + SM::kW2;
+    float *s_bias = reinterpret_cast<float *>(sW3 + SM::kW3);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_bias) + SM::kBias);
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int TCOLS = N3 <= 32 ? 32 : 64;
+    constexpr int NMAX = imax(imax(N1, N2), N3);
+    constexpr int TCOLS = NMAX <= 32 ? 32 : (NMAX <= 64 ? 64 : (NMAX <= 128 ? 128 : 256));
 
     if (tid == 0) {
         umma::mbar_init(bar, 1);
@@ -96,9 +117,8 @@ __global__ void __launch_bounds__(128) k_sa1_fused(const Args a) {
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.wimg);
         uint4 *dst = reinterpret_cast<uint4 *>(sW1);
-        for (int i = tid; i < (N1 + N2 + N3) * 8; i += 128) dst[i] = src[i];
+        for (int i = tid; i < (SM::kW1 + SM::kW2 + SM::kW3) / 16; i += 128) dst[i] = src[i];
         for (int i = tid; i < N1 + N2 + N3; i += 128) s_bias[i] = a.bias[i];
-        // rows of the operand tile beyond the valid K columns are never read by the MMAs (K <= 64)
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -111,6 +131,14 @@ __global__ void __launch_bounds__(128) k_sa1_fused(const Args a) {
     const long long rows = (long long)a.B * a.S * G;
     const int ntiles = (int)(rows / 128);
 
+#define SA_LAYER_SYNC()                                                   \
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          \
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      \
+    __syncthreads();
+#define SA_WAIT()                                                         \
+    umma::mbar_wait(bar, phase); phase ^= 1u;                             \
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- grouping: this thread's row (pointnet2_utils.py:246-253)
         {
@@ -118,61 +146,58 @@ __global__ void __launch_bounds__(128) k_sa1_fused(const Args a) {
             const long long bs = r / G;
             const int b = (int)(bs / a.S);
             const int i = a.gidx[r];
-            const float *f = a.in6 + ((size_t)b * a.N + i) * 6;
             const float *c = a.new_xyz + bs * 3;
-            __half h[16];
-            float v[9];
+            if (C == 0) {
+                const float *f = a.in6 + ((size_t)b * a.N + i) * 6;
+                __half h[16];
+                float v[9];
 #pragma unroll
-            for (int k = 0; k < 6; k++) v[k] = f[k];
+                for (int k = 0; k < 6; k++) v[k] = f[k];
 #pragma unroll
-            for (int k = 0; k < 3; k++) v[6 + k] = __fsub_rn(f[k], c[k]);
+                for (int k = 0; k < 3; k++) v[6 + k] = __fsub_rn(f[k], c[k]);
 #pragma unroll
-            for (int k = 0; k < 3; k++) { h[k] = __float2half_rn(v[k]); h[9 + k] = __float2half_rn(__fsub_rn(v[k], __half2float(h[k]))); }
+                for (int k = 0; k < 3; k++) split_hi_lo(v[k], h[k], h[9 + k]);
 #pragma unroll
-            for (int k = 3; k < 6; k++) h[k] = __float2half_rn(v[k]);
+                for (int k = 3; k < 6; k++) h[k] = __float2half_rn(v[k]);
 #pragma unroll
-            for (int k = 6; k < 9; k++) { h[k] = __float2half_rn(v[k]); h[6 + k] = __float2half_rn(__fsub_rn(v[k], __half2float(h[k]))); }
-            h[15] = __float2half_rn(0.f);
-            *reinterpret_cast<uint4 *>(sA + sw128_off(tid, 0)) = *reinterpret_cast<uint4 *>(h);
-            *reinterpret_cast<uint4 *>(sA + sw128_off(tid, 1)) = *reinterpret_cast<uint4 *>(h + 8);
+                for (int k = 6; k < 9; k++) split_hi_lo(v[k], h[k], h[6 + k]);
+                h[15] = __float2half_rn(0.f);
+                *reinterpret_cast<uint4 *>(sA + a_off(tid, 0)) = *reinterpret_cast<uint4 *>(h);
+                *reinterpret_cast<uint4 *>(sA + a_off(tid, 1)) = *reinterpret_cast<uint4 *>(h + 8);
+            } else {
+                const uint4 *src = reinterpret_cast<const uint4 *>(a.feat + ((size_t)b * a.N + i) * C);
+#pragma unroll
+                for (int cc = 0; cc < C / 8; cc++) *reinterpret_cast<uint4 *>(sA + a_off(tid, cc)) = __ldg(src + cc);
+                const float *p = a.xyz + ((size_t)b * a.N + i) * 3;
+                __half h[8];
+#pragma unroll
+                for (int k = 0; k < 3; k++) split_hi_lo(__fsub_rn(p[k], c[k]), h[k], h[3 + k]);
+                h[6] = h[7] = __float2half_rn(0.f);
+                *reinterpret_cast<uint4 *>(sA + a_off(tid, C / 8)) = *reinterpret_cast<uint4 *>(h);
+#pragma unroll
+                for (int cc = C / 8 + 1; cc < K0 / 8; cc++) *reinterpret_cast<uint4 *>(sA + a_off(tid, cc)) = make_uint4(0, 0, 0, 0);
+            }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        SA_LAYER_SYNC()
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue<K0>(tmem_base, sa_u, sw1_u, N1, bar);
+            issue<K0, N1>(tmem_base, sa_u, sw1_u, bar);
         }
-        umma::mbar_wait(bar, phase); phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
-            float v[N1];
-            ld_row<N1>(taddr, v);
-            store_row<N1>(sA, tid, v, s_bias);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        SA_WAIT()
+        epilogue_to_operand<N1>(taddr, sA, tid, s_bias);
+        SA_LAYER_SYNC()
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue<N1>(tmem_base, sa_u, sw2_u, N2, bar);
+            issue<N1, N2>(tmem_base, sa_u, sw2_u, bar);
         }
-        umma::mbar_wait(bar, phase); phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
-            float v[N2];
-            ld_row<N2>(taddr, v);
-            store_row<N2>(sA, tid, v, s_bias + N1);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        SA_WAIT()
+        epilogue_to_operand<N2>(taddr, sA, tid, s_bias + N1);
+        SA_LAYER_SYNC()
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue<N2>(tmem_base, sa_u, sw3_u, N3, bar);
+            issue<N2, N3>(tmem_base, sa_u, sw3_u, bar);
         }
-        umma::mbar_wait(bar, phase); phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        SA_WAIT()
         // ---- last layer: max over the G rows of each group, then bias + ReLU (they commute with max)
         {
             float *sc = reinterpret_cast<float *>(sA) + warp * (32 * 17);      // the operand tile is free again
@@ -202,6 +227,8 @@ __global__ void __launch_bounds__(128) k_sa1_fused(const Args a) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();          // pooling scratch (aliasing the operand tile) is free before the next gather
     }
+#undef SA_LAYER_SYNC
+#undef SA_WAIT
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
@@ -210,8 +237,5 @@ __global__ void __launch_bounds__(128) k_sa1_fused(const Args a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
     }
 }
-
-template <int N1, int N2, int N3>
-constexpr size_t smem_bytes() { return 1024 + 16384 + (size_t)(N1 + N2 + N3) * 128 + (size_t)(N1 + N2 + N3 + 2) * 4 + 64; }
 
 }  // namespace safused

@@ -165,3 +165,44 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
     if bp is not None:
         bp.close()
     return out
+
+
+def run_eval(env_configs, problems, planner, dim, args=None, seeds=None, state_dict=None, problem_name=None, neural_net="none",
+             connect="none", result_root="results/evaluation", batch_size=256, device=0, distributed=False):
+    """Batched twin of the eval_planning_{2d,3d}.py main loop (:79-125 of the 3D file): writes
+    ``<result_root>/<2d|3d>/<problem>-<planner><-c-connect>-<net>-<N>.pickle`` holding the same
+    list of ``env_config`` copies with a ``'result'`` key (``path_len_list``), appended in problem order,
+    and RESUMES from an existing pickle by skipping the problems it already holds -- so
+    result_analysis_*.py read the files unchanged.  Problems are planned ``batch_size`` at a time in
+    lock step (and sharded over ranks when ``distributed``); the pickle is rewritten after every batch
+    by rank 0."""
+    import os
+    import pickle
+    from copy import copy
+    rank = 0
+    if distributed:
+        import torch.distributed as dist
+        rank = dist.get_rank()
+    n = len(env_configs)
+    problem_name = problem_name or f"random_{dim}d"
+    folder = os.path.join(result_root, f"{dim}d")
+    os.makedirs(folder, exist_ok=True)
+    connect_str = "" if connect == "none" else "-c-" + connect
+    path = os.path.join(folder, f"{problem_name}-{planner}{connect_str}-{neural_net}-{n}.pickle")
+    done = []
+    if os.path.exists(path):
+        with open(path, "rb") as f:
+            done = pickle.load(f)
+    seeds = list(range(n)) if seeds is None else list(seeds)
+    for b in range(len(done), n, batch_size):
+        e = min(n, b + batch_size)
+        lists = plan_batch(problems[b:e], planner, dim, args, seeds=seeds[b:e], state_dict=state_dict, device=device,
+                           distributed=distributed)
+        for cfg, lst in zip(env_configs[b:e], lists):
+            row = copy(cfg)
+            row["result"] = [float(x) for x in lst]
+            done.append(row)
+        if rank == 0:
+            with open(path, "wb") as f:
+                pickle.dump(done, f)
+    return path, done

@@ -62,3 +62,19 @@ def test_batched_nirrt_equals_single_problem_dropin(dim, tmp_path):
         assert np.array_equal(np.isinf(got), np.isinf(want))
         f = np.isfinite(want)
         assert np.array_equal(np.array(got)[f], np.array(want)[f])
+
+
+def test_run_eval_writes_reference_format_and_resumes(tmp_path):
+    import pickle
+    from nirrt_star_b200.eval import default_args, run_eval
+    problems = [make_problem_3d(i) for i in range(5)]
+    cfgs = [{"env_idx": i, "env_dict": p["env_dict"]} for i, p in enumerate(problems)]
+    args = default_args(3, iter_max=400, iter_after_initial=50)
+    path, rows = run_eval(cfgs[:5], problems[:5], "irrt_star", 3, args, seeds=[7, 8, 9, 10, 11], result_root=str(tmp_path), batch_size=2)
+    assert path.endswith("3d/random_3d-irrt_star-none-5.pickle")
+    got = pickle.load(open(path, "rb"))
+    assert [r["env_idx"] for r in got] == [0, 1, 2, 3, 4] and all(isinstance(r["result"], list) for r in got)
+    # resume: drop the last two problems, rerun -> identical file content
+    pickle.dump(got[:3], open(path, "wb"))
+    _, rows2 = run_eval(cfgs[:5], problems[:5], "irrt_star", 3, args, seeds=[7, 8, 9, 10, 11], result_root=str(tmp_path), batch_size=2)
+    assert [r["result"] for r in rows2] == [r["result"] for r in got]
