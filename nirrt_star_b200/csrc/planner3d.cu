@@ -559,8 +559,7 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
         // "do not create a new node if it is actually the same point" (rrt_star_3d.py:41-45)
         xnew[0] = xn[0]; xnew[1] = xn[1]; xnew[2] = xn[2];
         new_idx = nearest;
-        c->curr_cost = cost_walk<D>(nodes, nearest);
-        c->cnew_default = c->curr_cost;
+        c->cnew_default = -1.0;        // marker: x_new re-uses an existing vertex (k_expand walks it)
     } else {
         new_idx = c->n;
         if (new_idx >= v.cap) { c->err |= ERR_VERTEX_OVERFLOW; c->skip = 1; c->new_idx = -1; return; }
@@ -573,11 +572,9 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
         c->n = new_idx + 1;
         c->inserted = 1;
         c->tree_changed = 1;
-        const double e0 = edge_len<D>(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2]));
-        double cn, via;
-        cost_walk2<D>(nodes, nearest, e0, cn, via);
-        c->curr_cost = XADD(cn, e0);
-        c->cnew_default = via;
+        // Line(nearest, new) (rrt_base_3d.py:132-137); the root walk that turns it into
+        // curr_node_new_cost and node_new_cost runs in k_expand together with the neighbours' walks
+        c->cnew_default = edge_len<D>(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2]));
     }
     c->new_idx = new_idx;
     c->x_new[0] = xnew[0]; c->x_new[1] = xnew[1]; c->x_new[2] = xnew[2];
@@ -871,6 +868,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
     __shared__ unsigned long long s_anc[kNearSmem];     // Near members on near_k's root path (see below)
     __shared__ unsigned s_bloom[32];
     __shared__ unsigned s_rew[kNearSmem / 32];
+    __shared__ double s_curr[2];                        // curr_node_new_cost, cost(new) via the steer parent
     __shared__ double sm_s[4];
     __shared__ int sm_i[4];
     __shared__ int s_m;
@@ -947,7 +945,16 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
             }
             __syncthreads();
             double bs = XINF; int bk = INT_MAX;
-            for (int k = tid; k < m; k += blockDim.x) {
+            for (int k = tid; k <= m; k += blockDim.x) {
+                if (k == m) {
+                    // the steer parent: curr_node_new_cost = cost(nearest) + Line(nearest, new)
+                    // (rrt_star_3d.py:46,51) and the cost(new) ChooseParent falls back to
+                    const double e0 = c->cnew_default;
+                    double cn, via;
+                    if (e0 < 0.0) { cn = cost_walk<D>(nodes, c->nearest); s_curr[0] = cn; s_curr[1] = cn; }
+                    else { cost_walk2<D>(nodes, c->nearest, e0, cn, via); s_curr[0] = XADD(cn, e0); s_curr[1] = via; }
+                    continue;
+                }
                 int idx = s_near[k];
                 const Node nd0 = load_node(nodes + idx);
                 double cacc = 0.0;
@@ -980,9 +987,9 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
             block_lexmin(bs, bk, sm_s, sm_i);
             if (tid == 0) {
                 // ---- choose_parent (rrt_star_3d.py:80-90)
-                double c_new = c->cnew_default;
+                double c_new = s_curr[1];
                 bool new_moved = false;
-                if (bs < c->curr_cost) {
+                if (bs < s_curr[0]) {
                     store_parent(nodes + new_idx, s_near[bk]);
                     c->tree_changed = 1;
                     c_new = s_via[bk];
