@@ -628,16 +628,16 @@ static int64_t expand3(orc_plan3 *p, const double *rnd) {
 /* generate_random_node for the three families:
  * variant 0 RRT*  (rrt_star_3d.py:119-123), 1 IRRT* (irrt_star_3d.py:95-115),
  * 2 NIRRT* with a fixed guidance cloud (nirrt_star_png_3d.py:99-130; the cloud update itself
- * is driven from Python) */
+ * is driven from Python), 3 NRRT* = RRT* driver + guidance cloud (nrrt_star_png_3d.py:52-59) */
 static void gen_random3(orc_plan3 *p, int variant, double c_best, double *out) {
-    if (variant == 2) {
+    if (variant == 2 || variant == 3) {
         if (mt_double(&p->rng) < p->pc_sample_rate) {
             int64_t k = mt_randint(&p->rng, p->n_pc);
             memcpy(out, p->pc + 3 * k, 24);
             return;
         }
     }
-    if (variant >= 1 && c_best < INFINITY) sample_informed3(p, c_best, out);
+    if ((variant == 1 || variant == 2) && c_best < INFINITY) sample_informed3(p, c_best, out);
     else sample_free3(p, out);
 }
 
@@ -666,14 +666,14 @@ ORC_API long orc3_run(orc_plan3 *p, int variant, int mode, long k, int stop_on_f
     for (it = 0; it < k; it++) {
         double rnd[3], c_best = INFINITY;
         int64_t ni;
-        if (variant >= 1) {
+        if (variant == 1 || variant == 2) {
             if (p->n_sol > 0) c_best = best_solution3(p, NULL);
             if (pathlen) pathlen[it] = c_best;
             if (stop_on_first && c_best < INFINITY) { it++; break; }
         }
         gen_random3(p, variant, c_best, rnd);
         ni = expand3(p, rnd);
-        if (variant >= 1 && ni >= 0 && in_goal_region3(p, p->v + 3 * ni)) {
+        if ((variant == 1 || variant == 2) && ni >= 0 && in_goal_region3(p, p->v + 3 * ni)) {
             if (p->n_sol < p->sol_cap) p->sol[p->n_sol++] = ni;
         }
         if (t_nearest) t_nearest[it] = p->tr_nearest;
@@ -682,7 +682,7 @@ ORC_API long orc3_run(orc_plan3 *p, int variant, int mode, long k, int stop_on_f
         if (near_buf) {
             for (long q = 0; q < p->tr_near_n && used < near_buf_cap; q++) near_buf[used++] = p->tr_near[q];
         }
-        if (variant == 0 && mode == 1) {
+        if ((variant == 0 || variant == 3) && mode == 1) {
             int64_t gp = search_goal_parent3(p);
             double len = gp < 0 ? INFINITY : path_len3(p, gp);
             if (pathlen) pathlen[it] = len;

@@ -199,12 +199,12 @@ class Oracle3D:
         """RRTStar3D.planning_random (rrt_star_3d.py:200-270) for variant 0,
         IRRTStar3D.planning_random (irrt_star_3d.py:245-331) for variant 1/2."""
         iter_max = self.cap - 1
-        if variant == 0:
-            r1 = self.run(iter_max, 0, 1, stop_on_first=True)
+        if variant in (0, 3):
+            r1 = self.run(iter_max, variant, 1, stop_on_first=True)
             lst = list(r1["pathlen"])
             if lst[-1] == np.inf:
                 return lst
-            r2 = self.run(iter_after_initial, 0, 1)
+            r2 = self.run(iter_after_initial, variant, 1)
             return lst + list(r2["pathlen"])
         r1 = self.run(iter_max, variant, 1, stop_on_first=True)
         lst = list(r1["pathlen"])
@@ -272,3 +272,27 @@ class Oracle3D:
         out = np.zeros((m, 3))
         lib().orc3_draw_informed(self.h, float(c_max), m, _dp(out))
         return out
+
+
+def guidance_cloud_3d(oracle, rs, n_points=2048, over_sample_scale=5):
+    """generate_rectangle_point_cloud_3d (datasets_3d/point_cloud_mask_utils_3d.py:83-113) restated
+    with the oracle's predicates: uniform draws on `rs` (an np.random.RandomState standing for the
+    global stream), obstacle filter with clearance 0, farthest-point down-sampling with open3d's
+    semantics as stubbed in oracle/ref_shim.py (start index 0, f64, first argmax; parity unpinned)."""
+    x1, y1, z1 = oracle.range6[1], oracle.range6[3], oracle.range6[5]
+    pts = rs.uniform(low=(0, 0, 0), high=(x1, y1, z1), size=(n_points * over_sample_scale, 3))
+    inside = np.zeros(len(pts), dtype=bool)
+    for b in oracle.balls:
+        inside |= (pts[:, 0] - b[0]) ** 2 + (pts[:, 1] - b[1]) ** 2 + (pts[:, 2] - b[2]) ** 2 < b[3] ** 2
+    for b in oracle.boxes:
+        inside |= ((b[0] <= pts[:, 0]) & (pts[:, 0] <= b[0] + b[3]) & (b[1] <= pts[:, 1]) & (pts[:, 1] <= b[1] + b[4]) &
+                   (b[2] <= pts[:, 2]) & (pts[:, 2] <= b[2] + b[5]))
+    pts = pts[~inside]
+    if len(pts) > n_points:
+        dist = np.full(len(pts), np.inf); far = 0; sel = []
+        for _ in range(n_points):
+            sel.append(far)
+            dist = np.minimum(dist, ((pts - pts[far]) ** 2).sum(axis=1))
+            far = int(np.argmax(dist))
+        pts = pts[sel]
+    return pts

@@ -85,3 +85,35 @@ def test_oracle_matches_reference_trace(path):
         assert np.array_equal(np.isinf(plist), np.isinf(gp))
         f = np.isfinite(gp)
         assert np.allclose(plist[f], gp[f], rtol=1e-12, atol=0)
+
+
+def test_nrrt_oracle_matches_reference_golden():
+    """NRRT*-PNG 3D (RRT* driver + guidance cloud predicted once): the oracle regenerates the cloud
+    from the numpy stream, takes the recorded prediction and must reproduce the reference's tree
+    (tests/golden/make_golden_neural_planner.py)."""
+    import glob
+    import hashlib
+    from oracle.planner_oracle import guidance_cloud_3d
+    paths = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "neural3d_nrrt_*.npz")))
+    assert paths
+    for path in paths:
+        g = np.load(path)
+        pr = make_problem_3d(int(g["env_idx"]))
+        seed, iter_max = int(g["seed"]), int(g["iter_max"])
+        rs = np.random.RandomState(seed)
+        o = Oracle3D(pr, iter_max, seed=seed)
+        pc = guidance_cloud_3d(o, rs)
+        assert hashlib.sha1(np.ascontiguousarray(pc.astype(np.float32)).tobytes()).hexdigest() == str(g["call_pc_sha1"][0])
+        pred = np.unpackbits(g["call_pred"][0])[:len(pc)]
+        st = rs.get_state()
+        o2 = Oracle3D(pr, iter_max, rng_state=(st[1], st[2]))
+        o2.set_cloud(pc[pred.nonzero()[0]], float(g["pc_sample_rate"]))
+        if str(g["mode"]) == "planning":
+            o2.run(iter_max, 3, 0)
+        else:
+            lst = np.array(o2.planning_random(int(g["iter_after"]), 3)); want = g["path_len_list"]
+            assert len(lst) == len(want) and np.array_equal(np.isinf(lst), np.isinf(want))
+            f = np.isfinite(want)
+            assert np.allclose(lst[f], want[f], rtol=1e-12, atol=0)
+        v, p = o2.tree()
+        assert len(v) == int(g["num_vertices"]) and np.array_equal(p, g["parents"]) and np.array_equal(v, g["vertices"])
