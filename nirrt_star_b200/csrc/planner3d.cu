@@ -70,7 +70,17 @@ enum { ST_DONE = 0, ST_PHASE1 = 1, ST_PHASE2 = 2, ST_WAIT_CLOUD = 3 };
 enum { ERR_NEAR_OVERFLOW = 1, ERR_SOL_OVERFLOW = 2, ERR_VERTEX_OVERFLOW = 4, ERR_EMPTY_CLOUD = 8,
        ERR_PATH_DEPTH = 16, ERR_RECORD_OVERFLOW = 32, ERR_GOAL_OVERFLOW = 64, ERR_OUT_OF_RANGE = 128 };
 
-struct EnvCtl {
+// what a mirror-scan CTA needs before it can start streaming (written by k_top / k_steer)
+struct __align__(16) ScanHdr {
+    int go, n;
+    float qx, qy, qz;   // the query in the mirror's coordinates
+    float thr;          // Near: squared-distance threshold
+    float band;         // Nearest: 2 * margin
+    int pad;
+};
+
+struct __align__(16) EnvCtl {
+    ScanHdr hdr[2];     // [0] Nearest (query x_rand), [1] Near (query x_new)
     // problem
     double start[3], goal[3];
     double step_len, search_radius;
@@ -85,9 +95,11 @@ struct EnvCtl {
     double x_rand[3], x_new[3];
     double r, T_near, curr_cost, c_best, c_update;
     double cnew_default;  // cost(new) if ChooseParent keeps the steer parent: the walk from x_new, leaf -> root
-    double margin;    // bound on |f32-mirror distance - f64 distance| for vertices inside the world range
-    float near_thr;   // f32 scan: a <= near_thr selects the Near candidates that get the exact f64 test
-    int fallbacks;    // Nearest chunks that had to be re-scanned in f64 (more than two candidates per thread)
+    double margin;    // bound on |mirror distance - f64 distance| for vertices inside the world range, in the
+                      // mirror's units (f32 mirror: world units; u16 mirror: grid cells)
+    double qlo[3], qscale;  // u16 mirror: cell = rint((x - qlo[d]) * qscale), 65535 cells over the longest world edge
+    float near_thr;   // mirror scan: a <= near_thr selects the Near candidates that get the exact f64 test
+    int fallbacks;    // Nearest scans whose in-band candidate list overflowed (k_steer re-scanned the env in f64)
     // goal bookkeeping
     int n_sol, n_goal, tree_changed, n_pc;
     long long last_gp;
@@ -98,13 +110,16 @@ struct EnvCtl {
 struct View {
     int E, cap, stride, chunks, near_cap, rec_cap, sol_cap, pc_cap, path_cap;
     int env0;        // first problem of the group an iteration kernel works on (see nirrt_batch_run)
+    int fuse_top;    // k_expand ends with the next iteration's k_top work (driver, c_best refresh, sampling)
     int variant, mode, iter_max, iter_after;
     double stop_below; // phase 1 ends when the recorded value drops below this (+inf: planning_random; finite: planning_block_gap)
     int n_limit;     // > 0: problems whose tree reached n_limit vertices idle (benchmark pre-growth)
     double pc_rate, pc_ratio;
     double *vx, *vy, *vz;
-    float *fx, *fy, *fz;   // f32 mirror of the coordinates (scan layout, 4 B per coordinate); null = scan the f64 arrays
+    float *fx, *fy, *fz;   // f32 mirror of the coordinates (scan layout, 4 B per coordinate); null = not in use
+    unsigned short *ux, *uy, *uz;   // u16 fixed-point mirror (scan layout, 2 B per coordinate); null = not in use
     Node *nodes;
+    int4 *hints;     // [E][stride] ancestor hints of the cost walks (see walk_to_root)
     Geom3 *geom;
     Geom2 *geom2;    // 2D worlds (dim == 2)
     int dim;
@@ -179,20 +194,79 @@ __device__ __forceinline__ double hypot_band_sq(double h) {
     return __dmul_ru(__dmul_ru(h, h), 1.0000000000000018);
 }
 
+// ---- root walks with ancestor hints
+// A cost walk is a chain of dependent 32-byte loads (one DRAM round trip per hop, depth 20-60 at
+// 1e5 vertices) and the reference's summation order (leaf -> root) rules out any re-association.
+// What can be removed is the dependency between the LOADS: hints[v] = {a1, a2, a3, a4} names the four
+// vertices that were v's ancestors 1..4 hops up when the record was last written.  A walk issues the
+// loads of all four ancestors and of hints[a4] at once, then verifies the chain against the
+// authoritative parent pointers in the node records as the data arrives: four hops per round trip.
+// A stale hint (some ancestor was re-parented since) only costs one ordinary hop and is repaired on
+// the spot.  Hints never decide anything: parents, coordinates and the summation order are exactly
+// those of the plain walk.
+#ifdef NIRRT_PHASE_TIMING
+__device__ unsigned long long g_walk_stats[4];
+#endif
+struct TreeRef {
+    Node *nodes;
+    int4 *hints;
+    int cap;
+};
+__device__ __forceinline__ TreeRef tree_of(const View &v, int e) {
+    TreeRef t;
+    t.nodes = v.nodes + (size_t)e * v.stride; t.hints = v.hints + (size_t)e * v.stride; t.cap = v.cap;
+    return t;
+}
+__device__ __forceinline__ int4 load_hint(const int4 *p) { return __ldcg(p); }
+__device__ __forceinline__ void store_hint(int4 *p, int a1, const int4 &up) { __stcg(p, make_int4(a1, up.x, up.y, up.z)); }
+
+// hop(par, cur_node, par_node) is called once per edge, leaf -> root
+template <typename F>
+__device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop) {
+    if (idx == 0) return;
+    Node cur = load_node(t.nodes + idx);
+    int4 h = load_hint(t.hints + idx);
+    int ci = idx;
+    for (;;) {
+        const unsigned cap = (unsigned)t.cap;
+        const int a1 = (unsigned)h.x < cap ? h.x : 0, a2 = (unsigned)h.y < cap ? h.y : 0;
+        const int a3 = (unsigned)h.z < cap ? h.z : 0, a4 = (unsigned)h.w < cap ? h.w : 0;
+        const Node n1 = load_node(t.nodes + a1), n2 = load_node(t.nodes + a2);
+        const Node n3 = load_node(t.nodes + a3), n4 = load_node(t.nodes + a4);
+        const int4 hn = load_hint(t.hints + a4);
+        bool ok = true;
+        int p;
+#define WALK_STEP(ak, nk)                                                              \
+        if (ok) {                                                                      \
+            p = (int)cur.parent;                                                       \
+            if (p == (ak)) { hop(p, cur, nk); if (p == 0) return; cur = nk; ci = p; }  \
+            else ok = false;                                                           \
+        }
+        WALK_STEP(a1, n1) WALK_STEP(a2, n2) WALK_STEP(a3, n3) WALK_STEP(a4, n4)
+#undef WALK_STEP
+#ifdef NIRRT_PHASE_TIMING
+        atomicAdd(&g_walk_stats[ok ? 0 : 1], 1ull);
+#endif
+        if (ok) { h = hn; continue; }
+        // stale hint: one ordinary hop, repair hints[ci] from the true parent's record
+        p = (int)cur.parent;
+        const Node np = load_node(t.nodes + p);
+        const int4 hp = load_hint(t.hints + p);
+        store_hint(t.hints + ci, p, hp);
+        hop(p, cur, np);
+        if (p == 0) return;
+        cur = np; ci = p; h = hp;
+    }
+}
+
 // RRTBase{2,3}D.cost (rrt_base_3d.py:60-67, rrt_base_2d.py:54-61): leaf -> root, math.hypot per
 // edge, summed in that order
 template <int D>
-__device__ double cost_walk(const Node *nodes, int idx) {
+__device__ double cost_walk(const TreeRef &t, int idx) {
     double c = 0.0;
-    if (idx == 0) return c;
-    Node cur = load_node(nodes + idx);
-    while (idx != 0) {
-        const int par = (int)cur.parent;
-        const Node p = load_node(nodes + par);
+    walk_to_root(t, idx, [&](int, const Node &cur, const Node &p) {
         c = XADD(c, edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z)));
-        idx = par;
-        cur = p;
-    }
+    });
     return c;
 }
 
@@ -202,18 +276,12 @@ __device__ double cost_walk(const Node *nodes, int idx) {
 // so neither ChooseParent's winner nor the steer parent needs a second walk for node_new_cost
 // (rrt_star_3d.py:96).
 template <int D>
-__device__ __forceinline__ void cost_walk2(const Node *nodes, int idx, double first, double &c_out, double &via_out) {
+__device__ __forceinline__ void cost_walk2(const TreeRef &t, int idx, double first, double &c_out, double &via_out) {
     double c = 0.0, a = first;
-    if (idx != 0) {
-        Node cur = load_node(nodes + idx);
-        while (idx != 0) {
-            const int par = (int)cur.parent;
-            const Node p = load_node(nodes + par);
-            const double e = edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
-            c = XADD(c, e); a = XADD(a, e);
-            idx = par; cur = p;
-        }
-    }
+    walk_to_root(t, idx, [&](int, const Node &cur, const Node &p) {
+        const double e = edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
+        c = XADD(c, e); a = XADD(a, e);
+    });
     c_out = c; via_out = a;
 }
 
@@ -270,6 +338,63 @@ __device__ __forceinline__ void push_record(const View &v, EnvCtl *c, int e, dou
     else c->err |= ERR_RECORD_OVERFLOW;
     c->n_rec++;
 }
+
+// ---- mirror-scan helpers (see "Mirror scans" below)
+constexpr double kMarginU16 = 2.0;
+
+__device__ __forceinline__ unsigned short quantize_u16(double x, double lo, double scale) {
+    int q = __double2int_rn((x - lo) * scale);
+    return (unsigned short)min(65535, max(0, q));
+}
+__device__ __forceinline__ void mirror_store(const View &v, const EnvCtl *c, size_t o, double x, double y, double z) {
+    if (v.ux) {
+        v.ux[o] = quantize_u16(x, c->qlo[0], c->qscale);
+        v.uy[o] = quantize_u16(y, c->qlo[1], c->qscale);
+        if (v.uz) v.uz[o] = quantize_u16(z, c->qlo[2], c->qscale);
+    }
+    if (v.fx) {
+        v.fx[o] = (float)x; v.fy[o] = (float)y;
+        if (v.fz) v.fz[o] = (float)z;
+    }
+}
+// the query in the mirror's coordinates (u16: 2^23 + nearest cell, see above)
+template <bool kU16>
+__device__ __forceinline__ float mirror_query(const EnvCtl *c, const double *q, int d) {
+    if (kU16) return 8388608.0f + rintf((float)((q[d] - c->qlo[d]) * c->qscale));
+    return (float)q[d];
+}
+
+template <int D>
+__device__ __forceinline__ double exact_scan_value(const View &v, int e, int i, double qx, double qy, double qz) {
+    const size_t o = (size_t)e * v.stride + i;
+    const double dx = XSUB(qx, v.vx[o]), dy = XSUB(qy, v.vy[o]), dz = D == 3 ? XSUB(qz, v.vz[o]) : 0.0;
+    return D == 3 ? XSQRT(sq3_rows(dx, dy, dz)) : np_hypot(dx, dy);
+}
+
+// One 32-byte record per scan holds everything a scan CTA needs to start streaming: a single round
+// trip instead of a chain of dependent loads (the CTA's whole share is only ~10 us of traffic).
+__device__ __forceinline__ ScanHdr load_hdr(const ScanHdr *h) {
+    const int4 a = __ldcg(reinterpret_cast<const int4 *>(h));
+    const int4 b = __ldcg(reinterpret_cast<const int4 *>(h) + 1);
+    ScanHdr r;
+    r.go = a.x; r.n = a.y; r.qx = __int_as_float(a.z); r.qy = __int_as_float(a.w);
+    r.qz = __int_as_float(b.x); r.thr = __int_as_float(b.y); r.band = __int_as_float(b.z); r.pad = b.w;
+    return r;
+}
+template <bool kU16>
+__device__ __forceinline__ void store_hdr(ScanHdr *h, const EnvCtl *c, int go, int n, const double *q, float thr) {
+    ScanHdr r;
+    r.go = go; r.n = n;
+    r.qx = mirror_query<kU16>(c, q, 0); r.qy = mirror_query<kU16>(c, q, 1); r.qz = mirror_query<kU16>(c, q, 2);
+    r.thr = thr; r.band = __double2float_ru(2.0 * c->margin); r.pad = 0;
+    *h = r;
+}
+__device__ __forceinline__ void write_hdr(const View &v, EnvCtl *c, int which, int go, const double *q, float thr) {
+    if (v.ux) store_hdr<true>(&c->hdr[which], c, go, c->n, q, thr);
+    else if (v.fx) store_hdr<false>(&c->hdr[which], c, go, c->n, q, thr);
+}
+
+__device__ __forceinline__ void set_idle(EnvCtl *c) { c->go = 0; c->hdr[0].go = 0; c->hdr[1].go = 0; }
 
 // ------------------------------------------------------------------------------------------------
 // k_top: driver phase machine + c_best refresh + sampling
@@ -343,20 +468,17 @@ __device__ void sample_informed(const Geom2 &g, const EnvCtl *c, MtStream &, MtS
     }
 }
 
+// Called by all 128 threads of the env's CTA: from k_top (first iteration of a run) and from the tail
+// of k_expand (every following iteration -- one launch and one dependent round trip less per iteration).
 template <int D>
-__global__ void __launch_bounds__(128) k_top(View v) {
-    typedef typename GeomOf<D>::type G;
-    const int e = v.env0 + blockIdx.x;
+__device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D>::type &g, bool g_staged, double *sm_s, int *sm_i) {
     EnvCtl *c = v.ctl + e;
-    __shared__ G g;
-    __shared__ double sm_s[4];
-    __shared__ int sm_i[4];
     const int state = c->state, budget = c->budget;
     if (state == ST_DONE || state == ST_WAIT_CLOUD || budget <= 0 || (v.n_limit > 0 && c->n >= v.n_limit)) {
-        if (threadIdx.x == 0) c->go = 0;
+        if (threadIdx.x == 0) set_idle(c);
         return;
     }
-    stage_geom<D>(&g, v, e);
+    if (!g_staged) stage_geom<D>(&g, v, e);
     mt_prepare_next(v.mt + e, 160);
     if (D == 2 && fam_informed(v.variant)) mt_prepare_next(v.mt_py + e, 160);
     __syncthreads();
@@ -370,7 +492,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
         for (int k = threadIdx.x; k < n_sol; k += blockDim.x) {
             const int idx = sol[k];
             const Node nd = load_node(nodes + idx);
-            const double val = XADD(cost_walk<D>(nodes, idx),
+            const double val = XADD(cost_walk<D>(tree_of(v, e), idx),
                                     edge_len<D>(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z)));
             lexmin(bs, bk, val, k);
         }
@@ -385,9 +507,9 @@ __global__ void __launch_bounds__(128) k_top(View v) {
         if (v.mode == NIRRT_MODE_PLANNING_RANDOM) {
             if (c->state == ST_PHASE1) {
                 if (c_best < v.stop_below) { c->state = ST_PHASE2; c->left = v.iter_after; }
-                else if (c->p1_done >= v.iter_max) { push_record(v, c, e, c_best); c->state = ST_DONE; c->go = 0; return; }
+                else if (c->p1_done >= v.iter_max) { push_record(v, c, e, c_best); c->state = ST_DONE; set_idle(c); return; }
             }
-            if (c->state == ST_PHASE2 && c->left <= 0) { push_record(v, c, e, c_best); c->state = ST_DONE; c->go = 0; return; }
+            if (c->state == ST_PHASE2 && c->left <= 0) { push_record(v, c, e, c_best); c->state = ST_DONE; set_idle(c); return; }
             push_record(v, c, e, c_best);
         }
     }
@@ -397,7 +519,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
         c->saved_state = c->state;
         c->state = ST_WAIT_CLOUD;
         c->resumed = 1;
-        c->go = 0;
+        set_idle(c);
         return;
     }
     c->resumed = 0;
@@ -408,7 +530,7 @@ __global__ void __launch_bounds__(128) k_top(View v) {
     bool done = false;
     if (fam_cloud(v.variant)) {
         if (rng.next_double() < v.pc_rate) {
-            if (c->n_pc <= 0) { c->err |= ERR_EMPTY_CLOUD; c->state = ST_DONE; c->go = 0; rng.flush(); return; }
+            if (c->n_pc <= 0) { c->err |= ERR_EMPTY_CLOUD; c->state = ST_DONE; set_idle(c); rng.flush(); return; }
             const long long k = rng.randint(c->n_pc);
             const double *p = v.pc + ((size_t)e * v.pc_cap + k) * 3;
             out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
@@ -422,7 +544,18 @@ __global__ void __launch_bounds__(128) k_top(View v) {
     rng.flush();
     if (D == 2) py.flush();
     c->x_rand[0] = out[0]; c->x_rand[1] = out[1]; c->x_rand[2] = out[2];
+    c->cand_cnt = 0;     // the Nearest mirror scan appends its in-band candidates here
     c->go = 1;
+    write_hdr(v, c, 0, 1, c->x_rand, 0.f);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_top(View v) {
+    typedef typename GeomOf<D>::type G;
+    __shared__ G g;
+    __shared__ double sm_s[4];
+    __shared__ int sm_i[4];
+    top_body<D>(v, v.env0 + blockIdx.x, g, false, sm_s, sm_i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,12 +648,28 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
     if (!c->go) return;
     const int lane = threadIdx.x;
     double bs = XINF; int bi = INT_MAX;
-    for (int k = lane; k < v.chunks; k += 32) lexmin(bs, bi, v.part_s[(size_t)e * v.chunks + k], v.part_i[(size_t)e * v.chunks + k]);
+    if (v.fx || v.ux) {
+        // candidates of the mirror scan: exact distance, lexicographic (value, index) minimum
+        const int cnt = c->cand_cnt;
+        const double qx = c->x_rand[0], qy = c->x_rand[1], qz = c->x_rand[2];
+        if (cnt <= v.near_cap) {
+            const int *cand = v.cand + (size_t)e * v.near_cap;
+            for (int k = lane; k < cnt; k += 32) { const int i = cand[k]; lexmin(bs, bi, exact_scan_value<D>(v, e, i, qx, qy, qz), i); }
+        } else {
+            const int n = c->n;
+            for (int i = lane; i < n; i += 32) lexmin(bs, bi, exact_scan_value<D>(v, e, i, qx, qy, qz), i);
+            if (lane == 0) c->fallbacks++;
+        }
+    } else {
+        for (int k = lane; k < v.chunks; k += 32) lexmin(bs, bi, v.part_s[(size_t)e * v.chunks + k], v.part_i[(size_t)e * v.chunks + k]);
+    }
     warp_lexmin(bs, bi);
     const int nearest = __shfl_sync(0xffffffffu, bi, 0);
     Node *nodes = v.nodes + (size_t)e * v.stride;
     const G &g = *GeomOf<D>::ptr(v, e);
     const Node nn = load_node(nodes + nearest);
+    int4 *hints = v.hints + (size_t)e * v.stride;
+    const int4 hn = load_hint(hints + nearest);
     const double xn[3] = {nn.x, nn.y, nn.z};
     // every lane computes the same x_new (cheap, avoids broadcasts)
     const double d0 = XSUB(c->x_rand[0], xn[0]), d1 = XSUB(c->x_rand[1], xn[1]), d2 = D == 3 ? XSUB(c->x_rand[2], xn[2]) : 0.0;
@@ -550,6 +699,7 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
     c->cand_cnt = 0;
     c->near_cnt = 0;
     c->inserted = 0;
+    c->hdr[1].go = 0;
     if (hit) { c->skip = 1; c->new_idx = -1; return; }
     c->skip = 0;
     int new_idx;
@@ -566,9 +716,10 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
         const size_t o = (size_t)e * v.stride + new_idx;
         v.vx[o] = xnew[0]; v.vy[o] = xnew[1];
         if (D == 3) v.vz[o] = xnew[2];
-        if (v.fx) { v.fx[o] = (float)xnew[0]; v.fy[o] = (float)xnew[1]; if (D == 3) v.fz[o] = (float)xnew[2]; }
+        mirror_store(v, c, o, xnew[0], xnew[1], xnew[2]);
         Node nd; nd.x = xnew[0]; nd.y = xnew[1]; nd.z = xnew[2]; nd.parent = nearest;
         nodes[new_idx] = nd;
+        store_hint(hints + new_idx, nearest, hn);
         c->n = new_idx + 1;
         c->inserted = 1;
         c->tree_changed = 1;
@@ -582,9 +733,10 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
     if (c->step_len < r) r = c->step_len;            // min(gamma * f(n), step_len)
     c->r = r;
     c->T_near = D == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
-    {   // f32 pre-filter threshold: every vertex with f64 distance <= r has f32 squared distance <= near_thr
-        const double rm = r + c->margin;
+    {   // mirror pre-filter threshold: every vertex with f64 distance <= r has mirror squared distance <= near_thr
+        const double rm = (v.ux ? r * c->qscale : r) + c->margin;
         c->near_thr = __double2float_ru(rm * rm * 1.000001);
+        write_hdr(v, c, 1, 1, c->x_new, c->near_thr);
     }
 }
 
@@ -647,147 +799,156 @@ __global__ void __launch_bounds__(256) k_near(View v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// f32-mirror scans.  The two HBM-bound passes read a float copy of the coordinates (12 B / vertex
-// in 3D, 8 B in 2D instead of 24 / 16) and use it only as a conservative filter: for vertices
-// inside the world range the f32 distance differs from the reference's f64 value by less than
-// `margin` (EnvCtl.margin = 2^-19 * largest |range bound|; derivation in DESIGN.md section 4), so
-//   Nearest: the f64 argmin lies within 2*margin of the f32 minimum of its chunk; every thread
-//            keeps its two best f32 candidates (and the value of the third), the candidates inside
-//            the band are re-evaluated with the exact formula and reduced lexicographically
-//            (value, index) exactly like the f64 scan.  A thread whose third-best value is also
-//            inside the band (practically never) makes its CTA re-scan the chunk in f64.
-//   Near:    f32 squared distance <= near_thr is a superset of the exact set; k_expand applies the
-//            exact test to every candidate before anything else looks at it.
-// Results are therefore bit-identical to the f64 scans (same parity tests).
-template <int D>
-__device__ __forceinline__ double exact_scan_value(const View &v, int e, int i, double qx, double qy, double qz) {
-    const size_t o = (size_t)e * v.stride + i;
-    const double dx = XSUB(qx, v.vx[o]), dy = XSUB(qy, v.vy[o]), dz = D == 3 ? XSUB(qz, v.vz[o]) : 0.0;
-    return D == 3 ? XSQRT(sq3_rows(dx, dy, dz)) : np_hypot(dx, dy);
-}
-
-template <int D, bool kForce>
-__global__ void __launch_bounds__(256) k_nearest_f32(View v) {
-    const int e = v.env0 + blockIdx.y;
-    EnvCtl *c = v.ctl + e;
-    if (!kForce && !c->go) return;
-    const int n = c->n;
-    const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
-    const int beg = blockIdx.x * per;
-    const int end = min(n, beg + per);
-    const float *X = v.fx + (size_t)e * v.stride, *Y = v.fy + (size_t)e * v.stride;
-    const float *Z = D == 3 ? v.fz + (size_t)e * v.stride : nullptr;
-    const double qx = c->x_rand[0], qy = c->x_rand[1], qz = c->x_rand[2];
-    const float fqx = (float)qx, fqy = (float)qy, fqz = (float)qz;
-    float a1 = INFINITY, a2 = INFINITY, a3 = INFINITY;
-    int i1 = INT_MAX, i2 = INT_MAX;
-#define TOP3(xx, yy, zz, ii)                                                          \
-    {                                                                                 \
-        const float dx = fqx - (xx), dy = fqy - (yy);                                 \
-        float a = dx * dx + dy * dy;                                                  \
-        if (D == 3) { const float dz = fqz - (zz); a += dz * dz; }                    \
-        if (a < a3) {                                                                 \
-            if (a < a2) {                                                             \
-                a3 = a2;                                                              \
-                if (a < a1) { a2 = a1; i2 = i1; a1 = a; i1 = (ii); }                  \
-                else { a2 = a; i2 = (ii); }                                           \
-            } else a3 = a;                                                            \
-        }                                                                             \
-    }
-    const int step = 4 * blockDim.x;
-    for (int i = beg + 4 * threadIdx.x; i < end; i += step) {
-        const float4 x = __ldg(reinterpret_cast<const float4 *>(X + i));
-        const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + i));
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (D == 3) z = __ldg(reinterpret_cast<const float4 *>(Z + i));
-        TOP3(x.x, y.x, z.x, i)
-        if (i + 1 < end) TOP3(x.y, y.y, z.y, i + 1)
-        if (i + 2 < end) TOP3(x.z, y.z, z.z, i + 2)
-        if (i + 3 < end) TOP3(x.w, y.w, z.w, i + 3)
-    }
-#undef TOP3
-    __shared__ float sm_f[8];
-    __shared__ double sm_s[8];
-    __shared__ int sm_i[8];
-    __shared__ int s_fallback;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    float amin = a1;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, off));
-    if (threadIdx.x == 0) s_fallback = 0;
-    if (l == 0) sm_f[w] = amin;
-    __syncthreads();
-    amin = sm_f[0];
-#pragma unroll
-    for (int k = 1; k < 8; k++) amin = fminf(amin, sm_f[k]);
-    // band in the distance domain, evaluated in double: sqrt(a) <= sqrt(amin) + 2 * margin
-    const double lim = sqrt((double)amin) + 2.0 * c->margin;
-    const double band = lim * lim * 1.0000001;
-    double best_s = XINF; int best_i = INT_MAX;
-    if (beg < end) {
-        if ((double)a3 <= band) s_fallback = 1;
-        if ((double)a1 <= band) lexmin(best_s, best_i, exact_scan_value<D>(v, e, i1, qx, qy, qz), i1);
-        if ((double)a2 <= band) lexmin(best_s, best_i, exact_scan_value<D>(v, e, i2, qx, qy, qz), i2);
-    }
-    __syncthreads();
-    if (s_fallback) {      // exact f64 re-scan of this chunk (same arithmetic as k_nearest)
-        best_s = XINF; best_i = INT_MAX;
-        for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
-            const double sv = exact_scan_value<D>(v, e, i, qx, qy, qz);
-            if (sv < best_s) { best_s = sv; best_i = i; }
+// Mirror scans.  The two HBM-bound passes read a compact copy of the coordinates and use it only as
+// a conservative filter; the f64 SoA stays the source of truth and every decision is re-made with the
+// reference's exact arithmetic on the few vertices the filter lets through.
+//   u16 mirror (default, 2 B / coordinate): cell = rint((x - qlo) * qscale), 65535 cells over the
+//       longest world edge.  The scan works in cell units with the query rounded to a cell as well,
+//       so the subtraction is exact: q and the vertex are both integers carried in floats
+//       (as_float(0x4B000000 | cell) == 2^23 + cell, one PRMT per coordinate, no conversion).
+//       |sqrt(a) - d * qscale| <= sqrt(3)/2 (vertex rounding) + sqrt(3)/2 (query rounding) + 0.02
+//       (three float roundings of a <= 1.3e10) < kMarginU16 = 2 cells for vertices inside the range.
+//   f32 mirror (NIRRT_SCAN=f32, 4 B / coordinate): |sqrt(a) - d| < margin = 2^-19 * largest |range bound|.
+// Nearest: the f64 argmin of a chunk lies within 2 * margin of the chunk's mirror minimum.  Every
+//   thread tracks its best (value, index) and its second-best value; after ONE block-wide minimum
+//   (redux + shared atomicMin + one barrier) the threads whose best is inside the band append it to
+//   the env's candidate list, a thread whose second-best is inside the band too re-walks its own
+//   vertices and appends all of them (rare).  k_steer evaluates the exact formula on the candidates
+//   and takes the lexicographic (value, index) minimum == np.argmin.  If the list overflows k_steer
+//   re-scans the env in f64 (counter `fallbacks`).
+// Near: mirror squared distance <= near_thr is a superset of the exact set; k_expand applies the exact
+//   test to every candidate before anything else looks at it.
+// Results are bit-identical to the f64 scans (same parity tests).
+// Calls visit(a[kVec], base) with the mirror squared distances of vertices base .. base+kVec-1 for this
+// thread's share of [beg, end) of env e; slots past `end` (ragged last chunk only) hold +inf.
+template <int D, bool kU16, typename F>
+__device__ __forceinline__ void mirror_scan(const View &v, int e, int beg, int end, float qx, float qy, float qz, F &&visit) {
+    constexpr int kVec = kU16 ? 8 : 4;
+    const int step = kVec * blockDim.x;
+    for (int i = beg + kVec * threadIdx.x; i < end; i += step) {
+        float a[kVec];
+        if (kU16) {
+            const unsigned short *X = v.ux + (size_t)e * v.stride, *Y = v.uy + (size_t)e * v.stride;
+            const unsigned short *Z = D == 3 ? v.uz + (size_t)e * v.stride : nullptr;
+            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(X + i));
+            const uint4 y = __ldg(reinterpret_cast<const uint4 *>(Y + i));
+            uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            if (D == 3) z = __ldg(reinterpret_cast<const uint4 *>(Z + i));
+#define MIRROR_U16(wx, wy, wz, j)                                                                   \
+            {                                                                                       \
+                const float dx0 = qx - __uint_as_float(__byte_perm(wx, 0x4B00u, 0x5410));           \
+                const float dy0 = qy - __uint_as_float(__byte_perm(wy, 0x4B00u, 0x5410));           \
+                const float dx1 = qx - __uint_as_float(__byte_perm(wx, 0x4B00u, 0x5432));           \
+                const float dy1 = qy - __uint_as_float(__byte_perm(wy, 0x4B00u, 0x5432));           \
+                a[j] = fmaf(dy0, dy0, dx0 * dx0); a[(j) + 1] = fmaf(dy1, dy1, dx1 * dx1);           \
+                if (D == 3) {                                                                       \
+                    const float dz0 = qz - __uint_as_float(__byte_perm(wz, 0x4B00u, 0x5410));       \
+                    const float dz1 = qz - __uint_as_float(__byte_perm(wz, 0x4B00u, 0x5432));       \
+                    a[j] = fmaf(dz0, dz0, a[j]); a[(j) + 1] = fmaf(dz1, dz1, a[(j) + 1]);           \
+                }                                                                                   \
+            }
+            MIRROR_U16(x.x, y.x, z.x, 0)
+            MIRROR_U16(x.y, y.y, z.y, 2)
+            MIRROR_U16(x.z, y.z, z.z, 4)
+            MIRROR_U16(x.w, y.w, z.w, 6)
+#undef MIRROR_U16
+        } else {
+            const float *X = v.fx + (size_t)e * v.stride, *Y = v.fy + (size_t)e * v.stride;
+            const float *Z = D == 3 ? v.fz + (size_t)e * v.stride : nullptr;
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(X + i));
+            const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + i));
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (D == 3) z = __ldg(reinterpret_cast<const float4 *>(Z + i));
+#define MIRROR_F32(xx, yy, zz, j)                                                                   \
+            {                                                                                       \
+                const float dx = qx - (xx), dy = qy - (yy);                                         \
+                a[j] = fmaf(dy, dy, dx * dx);                                                       \
+                if (D == 3) { const float dz = qz - (zz); a[j] = fmaf(dz, dz, a[j]); }              \
+            }
+            MIRROR_F32(x.x, y.x, z.x, 0)
+            MIRROR_F32(x.y, y.y, z.y, 1)
+            MIRROR_F32(x.z, y.z, z.z, 2)
+            MIRROR_F32(x.w, y.w, z.w, 3)
+#undef MIRROR_F32
         }
-        if (threadIdx.x == 0) atomicAdd(&c->fallbacks, 1);
-    }
-    warp_lexmin(best_s, best_i);
-    if (l == 0) { sm_s[w] = best_s; sm_i[w] = best_i; }
-    __syncthreads();
-    if (w == 0) {
-        best_s = l < 8 ? sm_s[l] : XINF;
-        best_i = l < 8 ? sm_i[l] : INT_MAX;
-        warp_lexmin(best_s, best_i);
-        if (l == 0) {
-            v.part_s[(size_t)e * v.chunks + blockIdx.x] = best_s;
-            v.part_i[(size_t)e * v.chunks + blockIdx.x] = best_i;
+        if (i + kVec > end) {
+#pragma unroll
+            for (int j = 0; j < kVec; j++) if (i + j >= end) a[j] = INFINITY;
         }
+        visit(a, i);
     }
 }
+template <int N> __device__ __forceinline__ float vec_min(const float (&a)[N]) {
+    float m = fminf(a[0], a[1]);
+#pragma unroll
+    for (int j = 2; j < N; j++) m = fminf(m, a[j]);
+    return m;
+}
 
-template <int D, bool kForce>
-__global__ void __launch_bounds__(256) k_near_f32(View v) {
+__device__ __forceinline__ void append_cand(const View &v, EnvCtl *c, int e, int idx) {
+    const int slot = atomicAdd(&c->cand_cnt, 1);
+    if (slot < v.near_cap) v.cand[(size_t)e * v.near_cap + slot] = idx;
+}
+
+template <int D, bool kU16, bool kForce>
+__global__ void __launch_bounds__(256) k_nearest_m(View v) {
     const int e = v.env0 + blockIdx.y;
     EnvCtl *c = v.ctl + e;
-    if (!kForce && (!c->go || c->skip)) return;
-    const int n = c->n;
-    const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
+    const ScanHdr h = load_hdr(&c->hdr[0]);
+    if (!kForce && !h.go) return;
+    __shared__ unsigned s_min;
+    if (threadIdx.x == 0) s_min = 0x7f800000u;
+    __syncthreads();
+    constexpr int kVec = kU16 ? 8 : 4;
+    const int per = (((h.n + (int)gridDim.x - 1) / (int)gridDim.x) + kVec - 1) & ~(kVec - 1);
     const int beg = blockIdx.x * per;
-    const int end = min(n, beg + per);
-    const float *X = v.fx + (size_t)e * v.stride, *Y = v.fy + (size_t)e * v.stride;
-    const float *Z = D == 3 ? v.fz + (size_t)e * v.stride : nullptr;
-    const float fqx = (float)c->x_new[0], fqy = (float)c->x_new[1], fqz = (float)c->x_new[2];
-    const float thr = c->near_thr;
-    int *cand = v.cand + (size_t)e * v.near_cap;
-#define NEARF(xx, yy, zz, ii)                                                         \
-    {                                                                                 \
-        const float dx = fqx - (xx), dy = fqy - (yy);                                 \
-        float a = dx * dx + dy * dy;                                                  \
-        if (D == 3) { const float dz = fqz - (zz); a += dz * dz; }                    \
-        if (a <= thr) {                                                               \
-            const int slot = atomicAdd(&c->cand_cnt, 1);                              \
-            if (slot < v.near_cap) cand[slot] = (ii);                                 \
-        }                                                                             \
+    const int end = min(h.n, beg + per);
+    if (beg >= end) return;
+    float a1 = INFINITY, a2 = INFINITY;   // best and second-best mirror value of this thread
+    int i1 = INT_MAX;
+    mirror_scan<D, kU16>(v, e, beg, end, h.qx, h.qy, h.qz, [&](const float (&a)[kVec], int base) {
+        if (vec_min(a) < a2) {            // rare once the running values have settled
+#pragma unroll
+            for (int j = 0; j < kVec; j++) {
+                a2 = fminf(a2, fmaxf(a[j], a1));
+                if (a[j] < a1) { a1 = a[j]; i1 = base + j; }
+            }
+        }
+    });
+    // a >= 0: the float order is the order of the bit patterns
+    const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(a1));
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_min, wmin);
+    __syncthreads();
+    const float amin = __uint_as_float(s_min);
+    // band in the distance domain, rounded up: sqrt(a) <= sqrt(amin) + 2 * margin
+    const float lim = __fadd_ru(__fsqrt_ru(amin), h.band);
+    const float band = __fmul_ru(__fmul_ru(lim, lim), 1.000001f);
+    if (a1 <= band) {
+        if (a2 > band) append_cand(v, c, e, i1);
+        else mirror_scan<D, kU16>(v, e, beg, end, h.qx, h.qy, h.qz, [&](const float (&a)[kVec], int base) {
+#pragma unroll
+            for (int j = 0; j < kVec; j++) if (a[j] <= band) append_cand(v, c, e, base + j);
+        });
     }
-    const int step = 4 * blockDim.x;
-    for (int i = beg + 4 * threadIdx.x; i < end; i += step) {
-        const float4 x = __ldg(reinterpret_cast<const float4 *>(X + i));
-        const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + i));
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (D == 3) z = __ldg(reinterpret_cast<const float4 *>(Z + i));
-        NEARF(x.x, y.x, z.x, i)
-        if (i + 1 < end) NEARF(x.y, y.y, z.y, i + 1)
-        if (i + 2 < end) NEARF(x.z, y.z, z.z, i + 2)
-        if (i + 3 < end) NEARF(x.w, y.w, z.w, i + 3)
-    }
-#undef NEARF
+}
+
+template <int D, bool kU16, bool kForce>
+__global__ void __launch_bounds__(256) k_near_m(View v) {
+    const int e = v.env0 + blockIdx.y;
+    EnvCtl *c = v.ctl + e;
+    const ScanHdr h = load_hdr(&c->hdr[1]);
+    if (!kForce && !h.go) return;
+    constexpr int kVec = kU16 ? 8 : 4;
+    const int per = (((h.n + (int)gridDim.x - 1) / (int)gridDim.x) + kVec - 1) & ~(kVec - 1);
+    const int beg = blockIdx.x * per;
+    const int end = min(h.n, beg + per);
+    const float thr = h.thr;
+    mirror_scan<D, kU16>(v, e, beg, end, h.qx, h.qy, h.qz, [&](const float (&a)[kVec], int base) {
+        if (vec_min(a) <= thr) {
+#pragma unroll
+            for (int j = 0; j < kVec; j++) if (a[j] <= thr) append_cand(v, c, e, base + j);
+        }
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -824,7 +985,7 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
     double bs = XINF; int bk = INT_MAX;
     for (int k = threadIdx.x; k < ng; k += blockDim.x) {
         const double d = gd[k];
-        const double val = (d < XINF) ? XADD(cost_walk<D>(nodes, gi[k]), d) : XINF;
+        const double val = (d < XINF) ? XADD(cost_walk<D>(tree_of(v, e), gi[k]), d) : XINF;
         lexmin(bs, bk, val, k);
     }
     block_lexmin(bs, bk, sm_s, sm_i);
@@ -854,7 +1015,7 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
 }
 
 template <int D>
-__global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
+__global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     typedef typename GeomOf<D>::type G;
     const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
@@ -869,35 +1030,62 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
     __shared__ unsigned s_bloom[32];
     __shared__ unsigned s_rew[kNearSmem / 32];
     __shared__ double s_curr[2];                        // curr_node_new_cost, cost(new) via the steer parent
+    __shared__ int4 s_hnew;                             // ancestor hints of x_new after ChooseParent
+    double *s_first = s_via;                            // Line(near_k, x_new) by math.hypot, replaced by the walk's result
     __shared__ double sm_s[4];
     __shared__ int sm_i[4];
     __shared__ int s_m;
     Node *nodes = v.nodes + (size_t)e * v.stride;
     const int tid = threadIdx.x;
+#ifdef NIRRT_PHASE_TIMING
+    long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PHASE_MARK(k) t_ph[k] = clock64();
+#else
+#define PHASE_MARK(k)
+#endif
+    PHASE_MARK(0)
+    const bool skipped = c->skip;
 
-    if (!c->skip) {
+    if (!skipped) {
         stage_geom<D>(&g, v, e);
         int cnt = c->cand_cnt;
         if (cnt > v.near_cap || cnt > kNearSmem) {
             if (tid == 0) c->err |= ERR_NEAR_OVERFLOW;
             cnt = min(min(cnt, v.near_cap), kNearSmem);
         }
-        int p2 = 1;
-        while (p2 < cnt) p2 <<= 1;
         const int *cand = v.cand + (size_t)e * v.near_cap;
-        for (int i = tid; i < p2; i += blockDim.x) s_cand[i] = i < cnt ? cand[i] : INT_MAX;
-        if (tid == 0) s_m = 0;
-        __syncthreads();
-        bitonic_sort_int(s_cand, p2);
+        if (cnt <= 256) {
+            // ascending order by rank counting (the indices are distinct): one barrier instead of a sorting network
+            int *s_raw = s_near;                          // scratch until the compaction below fills s_near
+            for (int i = tid; i < cnt; i += blockDim.x) s_raw[i] = cand[i];
+            if (tid == 0) s_m = 0;
+            __syncthreads();
+            for (int i = tid; i < cnt; i += blockDim.x) {
+                const int mine = s_raw[i];
+                int rank = 0;
+                for (int j = 0; j < cnt; j++) rank += s_raw[j] < mine;
+                s_cand[rank] = mine;
+            }
+            __syncthreads();
+        } else {
+            int p2 = 1;
+            while (p2 < cnt) p2 <<= 1;
+            for (int i = tid; i < p2; i += blockDim.x) s_cand[i] = i < cnt ? cand[i] : INT_MAX;
+            if (tid == 0) s_m = 0;
+            __syncthreads();
+            bitonic_sort_int(s_cand, p2);
+        }
+        PHASE_MARK(1)
 
         const double xnew[3] = {c->x_new[0], c->x_new[1], c->x_new[2]};
         const int new_idx = c->new_idx;
+        const double T_near = c->T_near, r_near = c->r;
         // collision filter + ordered compaction (tiles of blockDim candidates, ascending)
         for (int base = 0; base < cnt; base += blockDim.x) {
             const int k = base + tid;
             bool keep = false;
             int idx = -1;
-            double d = 0.0;
+            double d = 0.0, first = 0.0;
             if (k < cnt) {
                 idx = s_cand[k];
                 const Node nd = load_node(nodes + idx);
@@ -905,8 +1093,9 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
                 const double ex = XSUB(xnew[0], p1[0]), ey = XSUB(xnew[1], p1[1]), ez = XSUB(xnew[2], p1[2]);
                 d = vec_dist<D>(ex, ey, ez);
                 // dist <= r exactly as the reference decides it (the scan may have over-selected)
-                const bool within = D == 3 ? (sq3_rows(ex, ey, ez) <= c->T_near) : (d <= c->r);
+                const bool within = D == 3 ? (sq3_rows(ex, ey, ez) <= T_near) : (d <= r_near);
                 keep = within && (idx != new_idx) && !seg_collides(g, xnew, p1);
+                if (keep) first = edge_len<D>(ex, ey, ez);      // Line(near_k, x_new): first term of cost(x_new) via near_k
             }
             // block-ordered positions: warp ballots + warp-count prefix through smem
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -920,12 +1109,14 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
                 const int pos = off + __popc(bal & ((1u << l) - 1u));
                 s_near[pos] = idx;
                 s_d[pos] = d;
+                s_first[pos] = first;
             }
             __syncthreads();
             if (tid == 0) { int t = 0; for (int q = 0; q < kExpandThreads / 32; q++) t += s_wcnt[q]; s_m += t; }
             __syncthreads();
         }
         const int m = s_m;
+        PHASE_MARK(2)
         int *near_out = v.near_out + (size_t)e * v.near_cap;
         for (int k = tid; k < m; k += blockDim.x) near_out[k] = s_near[k];
         if (tid == 0) c->near_cnt = m;
@@ -945,25 +1136,21 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
             }
             __syncthreads();
             double bs = XINF; int bk = INT_MAX;
+            const TreeRef t = tree_of(v, e);
             for (int k = tid; k <= m; k += blockDim.x) {
                 if (k == m) {
                     // the steer parent: curr_node_new_cost = cost(nearest) + Line(nearest, new)
                     // (rrt_star_3d.py:46,51) and the cost(new) ChooseParent falls back to
                     const double e0 = c->cnew_default;
                     double cn, via;
-                    if (e0 < 0.0) { cn = cost_walk<D>(nodes, c->nearest); s_curr[0] = cn; s_curr[1] = cn; }
-                    else { cost_walk2<D>(nodes, c->nearest, e0, cn, via); s_curr[0] = XADD(cn, e0); s_curr[1] = via; }
+                    if (e0 < 0.0) { cn = cost_walk<D>(t, c->nearest); s_curr[0] = cn; s_curr[1] = cn; }
+                    else { cost_walk2<D>(t, c->nearest, e0, cn, via); s_curr[0] = XADD(cn, e0); s_curr[1] = via; }
                     continue;
                 }
-                int idx = s_near[k];
-                const Node nd0 = load_node(nodes + idx);
-                double cacc = 0.0;
-                double vacc = edge_len<D>(XSUB(xnew[0], nd0.x), XSUB(xnew[1], nd0.y), XSUB(xnew[2], nd0.z));
+                const int idx = s_near[k];
+                double cacc = 0.0, vacc = s_first[k];
                 unsigned long long anc = 0;   // [0,30): three 10-bit positions, [30,32): count, bit 32: overflow, bit 33: through x_new
-                Node cur = nd0;
-                while (idx != 0) {
-                    const int par = (int)cur.parent;
-                    const Node p = load_node(nodes + par);
+                walk_to_root(t, idx, [&](int par, const Node &cur, const Node &p) {
                     const double eg = edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
                     cacc = XADD(cacc, eg); vacc = XADD(vacc, eg);
                     const unsigned hsh = ((unsigned)par * 2654435761u) >> 22;
@@ -979,44 +1166,93 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
                             }
                         }
                     }
-                    idx = par; cur = p;
-                }
+                });
                 s_cost[k] = cacc; s_via[k] = vacc; s_anc[k] = anc;
                 lexmin(bs, bk, XADD(cacc, s_d[k]), k);
             }
-            block_lexmin(bs, bk, sm_s, sm_i);
+            block_lexmin(bs, bk, sm_s, sm_i);      // result broadcast to every thread
+            PHASE_MARK(3)
+            // ---- choose_parent (rrt_star_3d.py:80-90)
+            const bool reparent = bs < s_curr[0];
+            const double c_new = reparent ? s_via[bk] : s_curr[1];
+            const bool new_moved = reparent && !c->inserted;   // an existing vertex (duplicate guard) changed its parent
             if (tid == 0) {
-                // ---- choose_parent (rrt_star_3d.py:80-90)
-                double c_new = s_curr[1];
-                bool new_moved = false;
-                if (bs < s_curr[0]) {
-                    store_parent(nodes + new_idx, s_near[bk]);
+                int4 hnew;
+                if (reparent) {
+                    const int q = s_near[bk];
+                    store_parent(nodes + new_idx, q);
+                    const int4 hq = load_hint(t.hints + q);
+                    hnew = make_int4(q, hq.x, hq.y, hq.z);
+                    __stcg(t.hints + new_idx, hnew);
                     c->tree_changed = 1;
-                    c_new = s_via[bk];
-                    new_moved = !c->inserted;      // an existing vertex (duplicate guard) changed its parent
-                }
-                // ---- rewire (rrt_star_3d.py:92-99): ascending index order, later neighbours see earlier re-parentings
-                bool any = false;
-                for (int k = 0; k < m; k++) {
-                    const unsigned long long anc = s_anc[k];
-                    bool dirty = (new_moved && ((anc >> 33) & 1ull)) || (any && ((anc >> 32) & 1ull));
-                    const int cntp = (int)((anc >> 30) & 3ull);
-                    for (int q = 0; q < cntp && !dirty; q++) {
-                        const int pos = (int)((anc >> (10 * q)) & 1023ull);
-                        dirty = (s_rew[pos >> 5] >> (pos & 31)) & 1u;
-                    }
-                    const double ck = dirty ? cost_walk<D>(nodes, s_near[k]) : s_cost[k];
-                    if (ck > XADD(c_new, s_d[k])) {
-                        store_parent(nodes + s_near[k], new_idx);
-                        s_rew[k >> 5] |= 1u << (k & 31);
-                        any = true;
-                        c->tree_changed = 1;
-                    }
-                }
-                __threadfence_block();
+                } else hnew = load_hint(t.hints + new_idx);
+                s_hnew = hnew;
+            }
+            // ---- rewire (rrt_star_3d.py:92-99): ascending index order, later neighbours see earlier
+            // re-parentings.  A neighbour's cost can only change inside the loop if one of ITS ancestors
+            // is a Near member at an earlier position that gets re-parented (or x_new itself moved), so:
+            // (1) every thread decides its neighbours on the pre-loop costs; (2) if no neighbour has such
+            // an ancestor with a positive decision, those decisions ARE the sequential result (induction
+            // over the position) and the stores are applied in parallel; (3) otherwise thread 0 replays
+            // the loop sequentially, re-walking exactly the neighbours the reference would see changed.
+            for (int k0 = 0; k0 < m; k0 += blockDim.x) {
+                const int k = k0 + tid;
+                const bool dec = k < m && s_cost[k] > XADD(c_new, s_d[k]);
+                const unsigned bal = __ballot_sync(0xffffffffu, dec);
+                if ((tid & 31) == 0) s_rew[k >> 5] = bal;      // k >> 5 < kNearSmem / 32 for every k0 + tid
             }
             __syncthreads();
+            bool dep = false;
+            bool any_dec = false;
+            for (int w = 0; w < (m + 31) / 32; w++) any_dec = any_dec || s_rew[w] != 0u;
+            for (int k = tid; k < m; k += blockDim.x) {
+                const unsigned long long anc = s_anc[k];
+                if (anc == 0ull) continue;
+                if (new_moved && ((anc >> 33) & 1ull)) dep = true;
+                if (any_dec && ((anc >> 32) & 1ull)) dep = true;
+                const int cntp = (int)((anc >> 30) & 3ull);
+                for (int q = 0; q < cntp; q++) {
+                    const int pos = (int)((anc >> (10 * q)) & 1023ull);
+                    if (pos < k && ((s_rew[pos >> 5] >> (pos & 31)) & 1u)) dep = true;
+                }
+            }
+            const int any_dep = __syncthreads_or(dep);
+            const int4 hnew = s_hnew;
+            if (!any_dep) {
+                for (int k = tid; k < m; k += blockDim.x)
+                    if ((s_rew[k >> 5] >> (k & 31)) & 1u) {
+                        store_parent(nodes + s_near[k], new_idx);
+                        store_hint(t.hints + s_near[k], new_idx, hnew);
+                    }
+                if (tid == 0 && any_dec) c->tree_changed = 1;
+            } else {
+                __syncthreads();
+                if (tid == 0) {
+                    for (int w = 0; w < kNearSmem / 32; w++) s_rew[w] = 0;
+                    bool any = false;
+                    for (int k = 0; k < m; k++) {
+                        const unsigned long long anc = s_anc[k];
+                        bool dirty = (new_moved && ((anc >> 33) & 1ull)) || (any && ((anc >> 32) & 1ull));
+                        const int cntp = (int)((anc >> 30) & 3ull);
+                        for (int q = 0; q < cntp && !dirty; q++) {
+                            const int pos = (int)((anc >> (10 * q)) & 1023ull);
+                            dirty = (s_rew[pos >> 5] >> (pos & 31)) & 1u;
+                        }
+                        const double ck = dirty ? cost_walk<D>(t, s_near[k]) : s_cost[k];
+                        if (ck > XADD(c_new, s_d[k])) {
+                            store_parent(nodes + s_near[k], new_idx);
+                            store_hint(t.hints + s_near[k], new_idx, hnew);
+                            s_rew[k >> 5] |= 1u << (k & 31);
+                            any = true;
+                            c->tree_changed = 1;
+                        }
+                    }
+                }
+            }
+            __threadfence_block();
+            __syncthreads();
         }
+        PHASE_MARK(4)
         // ---- goal bookkeeping
         if (tid == 0) {
             if (fam_informed(v.variant)) {
@@ -1041,6 +1277,12 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
         }
         __syncthreads();
     }
+    PHASE_MARK(5)
+#ifdef NIRRT_PHASE_TIMING
+    if (tid == 0 && (e % 97) == 0 && (c->n % 50) == 0)
+        printf("expand e=%d n=%d cand=%d near=%d sort=%lld filter=%lld walks=%lld serial=%lld goal=%lld fast=%llu slow=%llu\n", e, c->n, c->cand_cnt, c->near_cnt,
+               t_ph[1] - t_ph[0], t_ph[2] - t_ph[1], t_ph[3] - t_ph[2], t_ph[4] - t_ph[3], t_ph[5] - t_ph[4], g_walk_stats[0], g_walk_stats[1]);
+#endif
 
     // ---- per-iteration record + phase machine (RRT* family; the IRRT* family records in k_top)
     if (!fam_informed(v.variant) && v.mode == NIRRT_MODE_PLANNING_RANDOM) {
@@ -1075,6 +1317,10 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand(View v) {
         } else {  // IRRT* family planning_random: counters only, phase switches happen in k_top
             if (c->state == ST_PHASE1) c->p1_done++; else c->left--;
         }
+    }
+    if (v.fuse_top) {   // the next iteration's driver step + sample
+        __syncthreads();
+        top_body<D>(v, e, g, !skipped, sm_s, sm_i);
     }
 }
 
@@ -1133,7 +1379,7 @@ __global__ void k_begin(View v) {
     EnvCtl *c = v.ctl + e;
     c->state = ST_PHASE1; c->saved_state = ST_PHASE1;
     c->p1_done = 0; c->left = 0; c->budget = 0; c->n_rec = 0; c->resumed = 0;
-    c->go = 0; c->skip = 0; c->nearest = 0; c->new_idx = -1; c->inserted = 0; c->cand_cnt = 0; c->near_cnt = 0;
+    set_idle(c); c->skip = 0; c->nearest = 0; c->new_idx = -1; c->inserted = 0; c->cand_cnt = 0; c->near_cnt = 0;
     c->c_best = XINF; c->c_update = XINF;
     c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
     c->err = 0;
@@ -1172,18 +1418,21 @@ __global__ void k_set_problems(View v, ProblemUpload u) {
     // tree = {start}, parent[0] = 0 (rrt_base_3d.py:25-28)
     const size_t o = (size_t)e * v.stride;
     v.vx[o] = c->start[0]; v.vy[o] = c->start[1]; v.vz[o] = c->start[2];
-    if (v.fx) { v.fx[o] = (float)c->start[0]; v.fy[o] = (float)c->start[1]; v.fz[o] = (float)c->start[2]; }
     {
-        double R = 1.0;
+        double R = 1.0, ext = 0.0;
         for (int i = 0; i < 6; i++) R = fmax(R, fabs(g->range[i]));
-        c->margin = R * 0x1p-19;
+        for (int i = 0; i < 3; i++) { c->qlo[i] = g->range[2 * i]; ext = fmax(ext, g->range[2 * i + 1] - g->range[2 * i]); }
+        c->qscale = 65535.0 / fmax(ext, 1e-300);
+        c->margin = v.ux ? kMarginU16 : R * 0x1p-19;
         c->fallbacks = 0;
     }
+    mirror_store(v, c, o, c->start[0], c->start[1], c->start[2]);
     Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = c->start[2]; nd.parent = 0;
     v.nodes[o] = nd;
+    v.hints[o] = make_int4(0, 0, 0, 0);
     c->n = 1;
     c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
-    c->state = ST_DONE; c->budget = 0; c->go = 0; c->n_rec = 0; c->err = 0; c->resumed = 0;
+    c->state = ST_DONE; c->budget = 0; set_idle(c); c->n_rec = 0; c->err = 0; c->resumed = 0;
     c->c_best = XINF; c->c_update = XINF; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
 }
 
@@ -1215,18 +1464,22 @@ __global__ void k_set_problems_2d(View v, ProblemUpload2 u) {
     }
     const size_t o = (size_t)e * v.stride;
     v.vx[o] = c->start[0]; v.vy[o] = c->start[1];
-    if (v.fx) { v.fx[o] = (float)c->start[0]; v.fy[o] = (float)c->start[1]; }
     {
-        double R = 1.0;
+        double R = 1.0, ext = 0.0;
         for (int i = 0; i < 4; i++) R = fmax(R, fabs(g->range[i]));
-        c->margin = R * 0x1p-19;
+        for (int i = 0; i < 2; i++) { c->qlo[i] = g->range[2 * i]; ext = fmax(ext, g->range[2 * i + 1] - g->range[2 * i]); }
+        c->qlo[2] = 0.0;
+        c->qscale = 65535.0 / fmax(ext, 1e-300);
+        c->margin = v.ux ? kMarginU16 : R * 0x1p-19;
         c->fallbacks = 0;
     }
+    mirror_store(v, c, o, c->start[0], c->start[1], 0.0);
     Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = 0.0; nd.parent = 0;
     v.nodes[o] = nd;
+    v.hints[o] = make_int4(0, 0, 0, 0);
     c->n = 1;
     c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
-    c->state = ST_DONE; c->budget = 0; c->go = 0; c->n_rec = 0; c->err = 0; c->resumed = 0;
+    c->state = ST_DONE; c->budget = 0; set_idle(c); c->n_rec = 0; c->err = 0; c->resumed = 0;
     c->c_best = XINF; c->c_update = XINF; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
 }
 
@@ -1256,7 +1509,7 @@ __global__ void k_points_check(View v, int env, int kind, const double *pts, lon
 template <int D>
 __global__ void k_costs(View v, int env, const long long *idx, long long m, double *out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < m) out[i] = cost_walk<D>(v.nodes + (size_t)env * v.stride, (int)idx[i]);
+    if (i < m) out[i] = cost_walk<D>(tree_of(v, env), (int)idx[i]);
 }
 // goal parent of every env for the final search (rrt_star_3d.py:58; irrt_star_3d.py:74-76)
 template <int D>
@@ -1273,7 +1526,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_goal_parent(View v, int use_
         for (int k = threadIdx.x; k < n_sol; k += blockDim.x) {
             const int idx = sol[k];
             const Node nd = load_node(nodes + idx);
-            lexmin(bs, bk, XADD(cost_walk<D>(nodes, idx), edge_len<D>(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z))), k);
+            lexmin(bs, bk, XADD(cost_walk<D>(tree_of(v, e), idx), edge_len<D>(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z))), k);
         }
         block_lexmin(bs, bk, sm_s, sm_i);
         if (threadIdx.x == 0) { gp_out[e] = n_sol > 0 ? sol[bk] : -1; cost_out[e] = n_sol > 0 ? bs : XINF; }
@@ -1297,6 +1550,22 @@ __global__ void __launch_bounds__(kExpandThreads) k_goal_parent(View v, int use_
         if ((dim) == 3) KERNEL<3, FORCE><<<grid, block, smem, stream>>>(__VA_ARGS__);  \
         else KERNEL<2, FORCE><<<grid, block, smem, stream>>>(__VA_ARGS__);             \
     } while (0)
+
+// the two scans of one iteration in the batch's scan layout (u16 / f32 mirror or the f64 arrays)
+template <bool kForce>
+static void launch_scan(const View &v, int which, int count, cudaStream_t s) {
+    const dim3 grid(v.chunks, count);
+    if (v.ux) {
+        if (which == 0) { if (v.dim == 3) k_nearest_m<3, true, kForce><<<grid, 256, 0, s>>>(v); else k_nearest_m<2, true, kForce><<<grid, 256, 0, s>>>(v); }
+        else { if (v.dim == 3) k_near_m<3, true, kForce><<<grid, 256, 0, s>>>(v); else k_near_m<2, true, kForce><<<grid, 256, 0, s>>>(v); }
+    } else if (v.fx) {
+        if (which == 0) { if (v.dim == 3) k_nearest_m<3, false, kForce><<<grid, 256, 0, s>>>(v); else k_nearest_m<2, false, kForce><<<grid, 256, 0, s>>>(v); }
+        else { if (v.dim == 3) k_near_m<3, false, kForce><<<grid, 256, 0, s>>>(v); else k_near_m<2, false, kForce><<<grid, 256, 0, s>>>(v); }
+    } else {
+        if (which == 0) LAUNCH_DB(v.dim, k_nearest, kForce, grid, 256, 0, s, v);
+        else LAUNCH_DB(v.dim, k_near, kForce, grid, 256, 0, s, v);
+    }
+}
 
 constexpr int kMaxGroups = 8;
 struct nirrt_batch {
@@ -1388,13 +1657,19 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     DALLOC(v.vx, double, EV); DALLOC(v.vy, double, EV);
     if (v.dim == 3) DALLOC(v.vz, double, EV);
     {
-        const char *mode = getenv("NIRRT_SCAN");         // "f64": scan the f64 arrays (no mirror)
-        if (!(mode && strcmp(mode, "f64") == 0)) {
+        // NIRRT_SCAN: "u16" (default) fixed-point mirror, "f32" float mirror, "f64" scan the f64 arrays
+        const char *mode = getenv("NIRRT_SCAN");
+        if (mode && strcmp(mode, "f64") == 0) {
+        } else if (mode && strcmp(mode, "f32") == 0) {
             DALLOC(v.fx, float, EV); DALLOC(v.fy, float, EV);
             if (v.dim == 3) DALLOC(v.fz, float, EV);
+        } else {
+            DALLOC(v.ux, unsigned short, EV); DALLOC(v.uy, unsigned short, EV);
+            if (v.dim == 3) DALLOC(v.uz, unsigned short, EV);
         }
     }
     DALLOC(v.nodes, Node, EV);
+    DALLOC(v.hints, int4, EV);
     if (v.dim == 3) { DALLOC(v.geom, Geom3, v.E); }
     else {
         DALLOC(v.geom2, Geom2, v.E); DALLOC(v.mt_py, MtState, v.E);
@@ -1663,9 +1938,8 @@ __global__ void k_scatter_trees(View v, int env_begin, const int *n, const doubl
         Node nd; nd.x = vs[0]; nd.y = vs[1]; nd.z = D == 3 ? vs[2] : 0.0; nd.parent = parents[(size_t)k * v.cap + i];
         v.vx[o] = nd.x; v.vy[o] = nd.y;
         if (D == 3) v.vz[o] = nd.z;
-        if (v.fx) {
-            v.fx[o] = (float)nd.x; v.fy[o] = (float)nd.y;
-            if (D == 3) v.fz[o] = (float)nd.z;
+        if (v.fx || v.ux) {
+            mirror_store(v, v.ctl + env, o, nd.x, nd.y, nd.z);
             const double *rg = D == 3 ? v.geom[env].range : v.geom2[env].range;
             bool out = nd.x < rg[0] || nd.x > rg[1] || nd.y < rg[2] || nd.y > rg[3];
             if (D == 3) out = out || nd.z < rg[4] || nd.z > rg[5];
@@ -1673,6 +1947,22 @@ __global__ void k_scatter_trees(View v, int env_begin, const int *n, const doubl
         }
         v.nodes[o] = nd;
         if (i == 0) { v.ctl[env].n = nk; v.ctl[env].tree_changed = 1; }
+    }
+}
+// ancestor hints of freshly loaded trees: the true ancestors 1..4 hops up
+__global__ void k_build_hints(View v, int env_begin, const int *n) {
+    const int k = blockIdx.y, env = env_begin + k;
+    const int nk = n[k];
+    const Node *nodes = v.nodes + (size_t)env * v.stride;
+    int4 *hints = v.hints + (size_t)env * v.stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x) {
+        int a[4], cur = i;
+        for (int q = 0; q < 4; q++) {
+            const long long par = nodes[cur].parent;
+            cur = (par >= 0 && par < nk) ? (int)par : 0;     // malformed parents only make a useless hint
+            a[q] = cur;
+        }
+        hints[i] = make_int4(a[0], a[1], a[2], a[3]);
     }
 }
 __global__ void k_gather_trees(View v, int env_begin, double *verts, long long *parents) {
@@ -1709,6 +1999,7 @@ extern "C" int nirrt_batch_load_trees(nirrt_batch *b, int env_begin, int count, 
         CUDA_TRY(cudaMemcpyAsync(dp, parents + (size_t)k0 * v.cap, sizeof(long long) * v.cap * m, cudaMemcpyHostToDevice, s));
         const int gx = (v.cap + 255) / 256 < 256 ? (v.cap + 255) / 256 : 256;
         k_scatter_trees<<<dim3(gx, m), 256, 0, s>>>(v, env_begin + k0, dn + k0, dv, dp);
+        k_build_hints<<<dim3(gx, m), 256, 0, s>>>(v, env_begin + k0, dn + k0);
         CHECK_LAUNCH();
     }
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -1760,17 +2051,17 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
     return NIRRT_OK;
 }
 
-static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count) {
+// first: this iteration's k_top has not run yet (start of a run); last: no iteration follows in this run
+static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count, bool first, bool last) {
     View v = b->v;
     v.env0 = env0;
-    LAUNCH_D(v.dim, k_top, count, 128, 0, s, v);
-    if (v.fx) LAUNCH_DB(v.dim, k_nearest_f32, false, dim3(v.chunks, count), 256, 0, s, v);
-    else LAUNCH_DB(v.dim, k_nearest, false, dim3(v.chunks, count), 256, 0, s, v);
+    v.fuse_top = last ? 0 : 1;
+    if (first) { LAUNCH_D(v.dim, k_top, count, 128, 0, s, v); b->launches += 1; }
+    launch_scan<false>(v, 0, count, s);
     LAUNCH_D(v.dim, k_steer, count, 32, 0, s, v);
-    if (v.fx) LAUNCH_DB(v.dim, k_near_f32, false, dim3(v.chunks, count), 256, 0, s, v);
-    else LAUNCH_DB(v.dim, k_near, false, dim3(v.chunks, count), 256, 0, s, v);
+    launch_scan<false>(v, 1, count, s);
     LAUNCH_D(v.dim, k_expand, count, kExpandThreads, 0, s, v);
-    b->launches += 5;
+    b->launches += 4;
     return NIRRT_OK;
 }
 
@@ -1781,7 +2072,7 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
     if (b->groups == 1) {
-        for (int it = 0; it < iters; it++) launch_iteration(b, s, 0, v.E);
+        for (int it = 0; it < iters; it++) launch_iteration(b, s, 0, v.E, it == 0, it == iters - 1);
     } else {
         const int G = b->groups;
         CUDA_TRY(cudaEventRecord(b->ev_fork, s));
@@ -1789,7 +2080,7 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
         for (int it = 0; it < iters; it++)
             for (int g = 0; g < G; g++) {
                 const int e0 = (int)((long long)v.E * g / G), e1 = (int)((long long)v.E * (g + 1) / G);
-                if (e1 > e0) launch_iteration(b, b->gs[g], e0, e1 - e0);
+                if (e1 > e0) launch_iteration(b, b->gs[g], e0, e1 - e0, it == 0, it == iters - 1);
             }
         for (int g = 0; g < G; g++) {
             CUDA_TRY(cudaEventRecord(b->ev_join[g], b->gs[g]));
@@ -1827,13 +2118,11 @@ extern "C" int nirrt_batch_run_profiled_sync(nirrt_batch *b, int iters, float *m
         cudaEventRecord(e[0], s);
         LAUNCH_D(v.dim, k_top, v.E, 128, 0, s, v);
         cudaEventRecord(e[1], s);
-        if (v.fx) LAUNCH_DB(v.dim, k_nearest_f32, false, dim3(v.chunks, v.E), 256, 0, s, v);
-    else LAUNCH_DB(v.dim, k_nearest, false, dim3(v.chunks, v.E), 256, 0, s, v);
+        launch_scan<false>(v, 0, v.E, s);
         cudaEventRecord(e[2], s);
         LAUNCH_D(v.dim, k_steer, v.E, 32, 0, s, v);
         cudaEventRecord(e[3], s);
-        if (v.fx) LAUNCH_DB(v.dim, k_near_f32, false, dim3(v.chunks, v.E), 256, 0, s, v);
-    else LAUNCH_DB(v.dim, k_near, false, dim3(v.chunks, v.E), 256, 0, s, v);
+        launch_scan<false>(v, 1, v.E, s);
         cudaEventRecord(e[4], s);
         LAUNCH_D(v.dim, k_expand, v.E, kExpandThreads, 0, s, v);
         cudaEventRecord(e[5], s);
@@ -1868,7 +2157,7 @@ static std::string err_bits(int err) {
     if (err & ERR_PATH_DEPTH) m += " path deeper than 4096 edges;";
     if (err & ERR_RECORD_OVERFLOW) m += " record buffer overflow;";
     if (err & ERR_GOAL_OVERFLOW) m += " goal-candidate overflow;";
-    if (err & ERR_OUT_OF_RANGE) m += " a loaded vertex lies outside the world range (the f32 scan margin assumes vertices inside it);";
+    if (err & ERR_OUT_OF_RANGE) m += " a loaded vertex lies outside the world range (the mirror scan margin assumes vertices inside it);";
     return m;
 }
 
@@ -2043,7 +2332,7 @@ static View single_env_view(const View &v, int env) {
     View w = v;   // shift every per-env array so that blockIdx.y == 0 addresses `env`
     w.vx += (size_t)env * v.stride; w.vy += (size_t)env * v.stride;
     if (v.vz) w.vz += (size_t)env * v.stride;
-    w.nodes += (size_t)env * v.stride;
+    w.nodes += (size_t)env * v.stride; w.hints += (size_t)env * v.stride;
     if (v.geom) w.geom += env;
     if (v.geom2) w.geom2 += env;
     if (v.mt_py) w.mt_py += env;
@@ -2121,13 +2410,13 @@ extern "C" int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int
 extern "C" int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *reserved) {
     if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
     if (kernel_launches) *kernel_launches = b->launches;
-    if (reserved) *reserved = (b->v.fx ? 4 : 8) * b->v.dim;   // bytes per vertex one scan pass reads
+    if (reserved) *reserved = (b->v.ux ? 2 : (b->v.fx ? 4 : 8)) * b->v.dim;   // bytes per vertex one scan pass reads
     return NIRRT_OK;
 }
 
 __global__ void k_reset_cand(View v) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < v.E) v.ctl[e].cand_cnt = 0;
+    if (e < v.E) { EnvCtl *c = v.ctl + e; c->cand_cnt = 0; c->hdr[0].n = c->hdr[1].n = c->n; }
 }
 
 extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, float *ms, int64_t *bytes, void *stream) {
@@ -2137,20 +2426,14 @@ extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, f
     CUDA_TRY(cudaSetDevice(b->device));
     TRY(fetch_ctl(b, s));
     int64_t total = 0;
-    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * (v.fx ? 4 : 8) * v.dim;
+    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * (v.ux ? 2 : (v.fx ? 4 : 8)) * v.dim;
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
     float acc = 0.f;
     for (int r = 0; r < reps; r++) {
-        if (which == 1) k_reset_cand<<<(v.E + 127) / 128, 128, 0, s>>>(v);
+        k_reset_cand<<<(v.E + 127) / 128, 128, 0, s>>>(v);
         CUDA_TRY(cudaEventRecord(e0, s));
-        if (v.fx) {
-            if (which == 0) LAUNCH_DB(v.dim, k_nearest_f32, true, dim3(v.chunks, v.E), 256, 0, s, v);
-            else LAUNCH_DB(v.dim, k_near_f32, true, dim3(v.chunks, v.E), 256, 0, s, v);
-        } else {
-            if (which == 0) LAUNCH_DB(v.dim, k_nearest, true, dim3(v.chunks, v.E), 256, 0, s, v);
-            else LAUNCH_DB(v.dim, k_near, true, dim3(v.chunks, v.E), 256, 0, s, v);
-        }
+        launch_scan<true>(v, which, v.E, s);
         CUDA_TRY(cudaEventRecord(e1, s));
         CUDA_TRY(cudaEventSynchronize(e1));
         float t = 0.f;
