@@ -83,16 +83,18 @@ NIRRT_HD double sqrt_le_threshold(double r) {
 
 // CPython 3.12 Modules/mathmodule.c vector_norm() for 3 (or 2, dz = 0 not allowed: use hypot2)
 // components.  Scaling by a power of two is exact, so frexp/ldexp are done on the exponent bits.
+// Branch-free (special cases are selected at the end) so that several independent evaluations in one
+// basic block overlap their dependency chains (walk_to_root in planner3d.cu relies on this).
 NIRRT_HD double hypot_n(const double *in, int n) {
-    double v[3], mx = 0.0;
-    for (int i = 0; i < n; i++) { v[i] = fabs(in[i]); if (v[i] > mx) mx = v[i]; }
-    if (mx == 0.0) return 0.0;
+    double v[3] = {0.0, 0.0, 0.0}, mx = 0.0;
+    for (int i = 0; i < n; i++) { v[i] = fabs(in[i]); mx = v[i] > mx ? v[i] : mx; }
     // frexp: mx = m * 2^e with 0.5 <= m < 1  (normal numbers; planner coordinates never approach
-    // the subnormal range -- guarded below by falling back to the plain formula)
-    int ebits = (int)((d2u(mx) >> 52) & 0x7ff);
-    if (ebits == 0 || ebits == 0x7ff) return XSQRT(sq3_rows(v[0], v[1], n > 2 ? v[2] : 0.0));
-    int max_e = ebits - 1022;
-    double scale = u2d((uint64_t)(1023 - max_e) << 52);      // ldexp(1.0, -max_e)
+    // the subnormal range -- zero / subnormal / non-finite inputs take the plain formula)
+    const int ebits = (int)((d2u(mx) >> 52) & 0x7ff);
+    const bool special = ebits == 0 || ebits == 0x7ff;
+    const double plain = XSQRT(sq3_rows(v[0], v[1], v[2]));
+    const int max_e = special ? 0 : ebits - 1022;
+    const double scale = u2d((uint64_t)(1023 - max_e) << 52);      // ldexp(1.0, -max_e)
     double csum = 1.0, frac1 = 0.0, frac2 = 0.0;
     for (int i = 0; i < n; i++) {
         double x = XMUL(v[i], scale);
@@ -111,7 +113,9 @@ NIRRT_HD double hypot_n(const double *in, int n) {
     frac2 = XADD(frac2, slo);
     double x = XADD(XSUB(csum, 1.0), XADD(frac1, frac2));
     h = XADD(h, XDIV(x, XMUL(2.0, h)));
-    return XDIV(h, scale);
+    // h / scale: scale is a power of two, so the quotient is the (exact, once-rounded) product with 2^max_e
+    h = XMUL(h, u2d((uint64_t)(1023 + max_e) << 52));
+    return special ? plain : h;
 }
 NIRRT_HD double hypot3(double dx, double dy, double dz) { double v[3] = {dx, dy, dz}; return hypot_n(v, 3); }
 NIRRT_HD double hypot2(double dx, double dy) { double v[2] = {dx, dy}; return hypot_n(v, 2); }

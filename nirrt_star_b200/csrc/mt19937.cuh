@@ -45,12 +45,26 @@ __device__ __forceinline__ void mt_prepare_next(MtState *s, int margin) {
 }
 
 // Single-thread word stream over an MtState (registers hold pos/cur; call flush() when done).
+constexpr int kMtCache = 64;   // words of the current block staged in shared memory ahead of the sampling thread
+
+// Called by ALL threads: copies the next kMtCache words of the stream's current block into `cache`
+// (one coalesced round trip instead of one dependent global load per word drawn).
+__device__ __forceinline__ void mt_stage_words(const MtState *s, uint32_t *cache) {
+    const int pos = s->pos;
+    const uint32_t *k = s->key[s->cur];
+    for (int j = threadIdx.x; j < kMtCache; j += blockDim.x) cache[j] = pos + j < 624 ? k[pos + j] : 0u;
+}
+
 struct MtStream {
     MtState *s;
     uint32_t *k;
     int pos;
-    __device__ __forceinline__ explicit MtStream(MtState *st) : s(st), k(st->key[st->cur]), pos(st->pos) {}
+    const uint32_t *cache;   // words [lo, lo + kMtCache) of the current block, or null
+    int lo;
+    __device__ __forceinline__ explicit MtStream(MtState *st, const uint32_t *staged = nullptr)
+        : s(st), k(st->key[st->cur]), pos(st->pos), cache(staged), lo(st->pos) {}
     __device__ void refill() {
+        cache = nullptr;
         if (s->has_next) {
             s->cur ^= 1;
             s->has_next = 0;
@@ -65,7 +79,8 @@ struct MtStream {
     }
     __device__ __forceinline__ uint32_t next() {
         if (pos == 624) refill();
-        uint32_t y = k[pos++];
+        uint32_t y = (cache && pos - lo < kMtCache) ? cache[pos - lo] : k[pos];
+        pos++;
         y ^= (y >> 11);
         y ^= (y << 7) & 0x9d2c5680u;
         y ^= (y << 15) & 0xefc60000u;

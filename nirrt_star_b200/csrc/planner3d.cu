@@ -120,6 +120,7 @@ struct View {
     unsigned short *ux, *uy, *uz;   // u16 fixed-point mirror (scan layout, 2 B per coordinate); null = not in use
     Node *nodes;
     int4 *hints;     // [E][stride] ancestor hints of the cost walks (see walk_to_root)
+    struct Link *links;  // [E][stride] {edge length to the parent, parent}: what a cost walk reads
     Geom3 *geom;
     Geom2 *geom2;    // 2D worlds (dim == 2)
     int dim;
@@ -155,6 +156,15 @@ __device__ __forceinline__ Node load_node(const Node *p) {
 __device__ __forceinline__ void store_parent(Node *p, long long parent) {
     __stcg(reinterpret_cast<long long *>(p) + 3, parent);
 }
+
+// ---- programmatic dependent launch (PDL): the five kernels of an iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so kernel N+1's CTAs may become resident while
+// kernel N drains; every kernel therefore starts with pdl_wait() (returns once ALL memory operations
+// of the preceding kernel in the stream are complete and visible).  The scans let their (small)
+// successor launch right away; the small kernels never trigger early, so a scan grid is never parked
+// on the SMs for longer than its predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- dimension traits: which obstacle table, and which of the reference's norms evaluates what
 template <int D> struct GeomOf;
@@ -194,68 +204,104 @@ __device__ __forceinline__ double hypot_band_sq(double h) {
     return __dmul_ru(__dmul_ru(h, h), 1.0000000000000018);
 }
 
-// ---- root walks with ancestor hints
-// A cost walk is a chain of dependent 32-byte loads (one DRAM round trip per hop, depth 20-60 at
-// 1e5 vertices) and the reference's summation order (leaf -> root) rules out any re-association.
-// What can be removed is the dependency between the LOADS: hints[v] = {a1, a2, a3, a4} names the four
-// vertices that were v's ancestors 1..4 hops up when the record was last written.  A walk issues the
-// loads of all four ancestors and of hints[a4] at once, then verifies the chain against the
-// authoritative parent pointers in the node records as the data arrives: four hops per round trip.
-// A stale hint (some ancestor was re-parented since) only costs one ordinary hop and is repaired on
-// the spot.  Hints never decide anything: parents, coordinates and the summation order are exactly
-// those of the plain walk.
+// ---- root walks: cached edge lengths + ancestor hints
+// RRTBase{2,3}D.cost (rrt_base_3d.py:60-67) walks parent pointers leaf -> root and sums
+// math.hypot(v - parent(v)) in that order; the summation order rules out any re-association, and a
+// plain walk is a chain of dependent DRAM round trips with a long math.hypot (CPython vector_norm:
+// ~100 dependent f64 operations incl. a square root and a division) on every hop.  Both are removed
+// without touching the arithmetic:
+//   * links[v] = {math.hypot(v - parent(v)), parent(v)}: an edge length depends only on the two end
+//     points, which never move, so it is evaluated once when the edge is created (insert,
+//     ChooseParent, Rewire -- the same value cost() would recompute) and the walk only adds.
+//   * hints[v] = {a1, a2, a3, a4} names the vertices that were v's ancestors 1..4 hops up when the
+//     record was last written.  A walk loads the links of all four and hints[a4] at once and verifies
+//     the chain against the authoritative parent fields as the data arrives: four hops per round
+//     trip.  A stale hint (an ancestor was re-parented since) costs one ordinary hop and is repaired
+//     on the spot.  Hints never decide anything.
+struct __align__(16) Link {
+    double elen;   // math.hypot(v - parent(v)); 0 for the root
+    int parent;
+    int pad;
+};
 #ifdef NIRRT_PHASE_TIMING
 __device__ unsigned long long g_walk_stats[4];
 #endif
 struct TreeRef {
     Node *nodes;
+    Link *links;
     int4 *hints;
     int cap;
 };
 __device__ __forceinline__ TreeRef tree_of(const View &v, int e) {
     TreeRef t;
-    t.nodes = v.nodes + (size_t)e * v.stride; t.hints = v.hints + (size_t)e * v.stride; t.cap = v.cap;
+    t.nodes = v.nodes + (size_t)e * v.stride; t.links = v.links + (size_t)e * v.stride;
+    t.hints = v.hints + (size_t)e * v.stride; t.cap = v.cap;
     return t;
 }
 __device__ __forceinline__ int4 load_hint(const int4 *p) { return __ldcg(p); }
 __device__ __forceinline__ void store_hint(int4 *p, int a1, const int4 &up) { __stcg(p, make_int4(a1, up.x, up.y, up.z)); }
+__device__ __forceinline__ Link load_link(const Link *p) {
+    const int4 r = __ldcg(reinterpret_cast<const int4 *>(p));
+    Link l;
+    l.elen = __hiloint2double(r.y, r.x); l.parent = r.z; l.pad = r.w;
+    return l;
+}
+// parent(v) = par with edge length elen: the node record (what read_trees returns) and the walk record
+__device__ __forceinline__ void set_parent(const TreeRef &t, int v, int par, double elen) {
+    store_parent(t.nodes + v, par);
+    __stcg(reinterpret_cast<int4 *>(t.links + v), make_int4(__double2loint(elen), __double2hiint(elen), par, 0));
+}
 
-// hop(par, cur_node, par_node) is called once per edge, leaf -> root
+// hop(par, edge_length) is called once per edge, leaf -> root
 template <typename F>
 __device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop) {
     if (idx == 0) return;
-    Node cur = load_node(t.nodes + idx);
+    Link cur = load_link(t.links + idx);
     int4 h = load_hint(t.hints + idx);
-    int ci = idx;
+    int start = idx;
     for (;;) {
         const unsigned cap = (unsigned)t.cap;
         const int a1 = (unsigned)h.x < cap ? h.x : 0, a2 = (unsigned)h.y < cap ? h.y : 0;
         const int a3 = (unsigned)h.z < cap ? h.z : 0, a4 = (unsigned)h.w < cap ? h.w : 0;
-        const Node n1 = load_node(t.nodes + a1), n2 = load_node(t.nodes + a2);
-        const Node n3 = load_node(t.nodes + a3), n4 = load_node(t.nodes + a4);
+        const Link l1 = load_link(t.links + a1), l2 = load_link(t.links + a2);
+        const Link l3 = load_link(t.links + a3), l4 = load_link(t.links + a4);
         const int4 hn = load_hint(t.hints + a4);
-        bool ok = true;
-        int p;
-#define WALK_STEP(ak, nk)                                                              \
-        if (ok) {                                                                      \
-            p = (int)cur.parent;                                                       \
-            if (p == (ak)) { hop(p, cur, nk); if (p == 0) return; cur = nk; ci = p; }  \
-            else ok = false;                                                           \
-        }
-        WALK_STEP(a1, n1) WALK_STEP(a2, n2) WALK_STEP(a3, n3) WALK_STEP(a4, n4)
-#undef WALK_STEP
+        int j = 0;
+        int p = cur.parent;
+        if (p == a1) {
+            hop(p, cur.elen); if (p == 0) return;
+            j = 1; p = l1.parent;
+            if (p == a2) {
+                hop(p, l1.elen); if (p == 0) return;
+                j = 2; p = l2.parent;
+                if (p == a3) {
+                    hop(p, l2.elen); if (p == 0) return;
+                    j = 3; p = l3.parent;
+                    if (p == a4) {
+                        hop(p, l3.elen); if (p == 0) return;
+                        cur = l4; start = a4; h = hn;
 #ifdef NIRRT_PHASE_TIMING
-        atomicAdd(&g_walk_stats[ok ? 0 : 1], 1ull);
+                        atomicAdd(&g_walk_stats[0], 1ull);
 #endif
-        if (ok) { h = hn; continue; }
-        // stale hint: one ordinary hop, repair hints[ci] from the true parent's record
-        p = (int)cur.parent;
-        const Node np = load_node(t.nodes + p);
+                        continue;
+                    }
+                }
+            }
+        }
+#ifdef NIRRT_PHASE_TIMING
+        atomicAdd(&g_walk_stats[1], 1ull);
+#endif
+        // stale from hop j+1 on (an ancestor was re-parented since hints[start] was written): one ordinary
+        // hop from the last verified vertex, and hints[start] is rewritten with the verified prefix followed
+        // by the true parent and that parent's own hints
+        const Link cj = j == 0 ? cur : (j == 1 ? l1 : (j == 2 ? l2 : l3));
+        const Link lp = load_link(t.links + p);
         const int4 hp = load_hint(t.hints + p);
-        store_hint(t.hints + ci, p, hp);
-        hop(p, cur, np);
+        __stcg(t.hints + start, j == 0 ? make_int4(p, hp.x, hp.y, hp.z) : j == 1 ? make_int4(a1, p, hp.x, hp.y)
+                                : j == 2 ? make_int4(a1, a2, p, hp.x) : make_int4(a1, a2, a3, p));
+        hop(p, cj.elen);
         if (p == 0) return;
-        cur = np; ci = p; h = hp;
+        cur = lp; start = p; h = hp;
     }
 }
 
@@ -264,9 +310,7 @@ __device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop)
 template <int D>
 __device__ double cost_walk(const TreeRef &t, int idx) {
     double c = 0.0;
-    walk_to_root(t, idx, [&](int, const Node &cur, const Node &p) {
-        c = XADD(c, edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z)));
-    });
+    walk_to_root(t, idx, [&](int, double e) { c = XADD(c, e); });
     return c;
 }
 
@@ -278,10 +322,7 @@ __device__ double cost_walk(const TreeRef &t, int idx) {
 template <int D>
 __device__ __forceinline__ void cost_walk2(const TreeRef &t, int idx, double first, double &c_out, double &via_out) {
     double c = 0.0, a = first;
-    walk_to_root(t, idx, [&](int, const Node &cur, const Node &p) {
-        const double e = edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
-        c = XADD(c, e); a = XADD(a, e);
-    });
+    walk_to_root(t, idx, [&](int, double e) { c = XADD(c, e); a = XADD(a, e); });
     c_out = c; via_out = a;
 }
 
@@ -479,7 +520,9 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
         return;
     }
     if (!g_staged) stage_geom<D>(&g, v, e);
+    __shared__ uint32_t s_mt[kMtCache];
     mt_prepare_next(v.mt + e, 160);
+    mt_stage_words(v.mt + e, s_mt);
     if (D == 2 && fam_informed(v.variant)) mt_prepare_next(v.mt_py + e, 160);
     __syncthreads();
 
@@ -524,7 +567,7 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
     }
     c->resumed = 0;
 
-    MtStream rng(v.mt + e);
+    MtStream rng(v.mt + e, s_mt);
     MtStream py(D == 2 ? v.mt_py + e : v.mt + e);
     double out[3];
     bool done = false;
@@ -552,6 +595,7 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
 template <int D>
 __global__ void __launch_bounds__(128) k_top(View v) {
     typedef typename GeomOf<D>::type G;
+    pdl_wait();
     __shared__ G g;
     __shared__ double sm_s[4];
     __shared__ int sm_i[4];
@@ -564,6 +608,8 @@ __global__ void __launch_bounds__(128) k_top(View v) {
 //   for running-minimum candidates: s2 >= RU(best_s*best_s) implies sqrt_rn(s2) >= best_s.
 template <int D, bool kForce>
 __global__ void __launch_bounds__(256) k_nearest(View v) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
     const EnvCtl *c = v.ctl + e;
     if (!kForce && !c->go) return;
@@ -643,18 +689,34 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
 template <int D>
 __global__ void __launch_bounds__(32) k_steer(View v) {
     typedef typename GeomOf<D>::type G;
+    pdl_wait();
     const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
-    if (!c->go) return;
+    const int go = c->go, cnt = c->cand_cnt;     // independent loads: one round trip
+    if (!go) return;
     const int lane = threadIdx.x;
+    Node *nodes = v.nodes + (size_t)e * v.stride;
+    int4 *hints = v.hints + (size_t)e * v.stride;
     double bs = XINF; int bi = INT_MAX;
+    Node nn; int4 hn = make_int4(0, 0, 0, 0);    // record + hints of this lane's best candidate
+    nn.x = nn.y = nn.z = 0.0; nn.parent = 0;
+    bool have_rec = false;
     if (v.fx || v.ux) {
-        // candidates of the mirror scan: exact distance, lexicographic (value, index) minimum
-        const int cnt = c->cand_cnt;
+        // candidates of the mirror scan: exact distance, lexicographic (value, index) minimum.  The exact
+        // coordinates come from the 32-byte node record (the same doubles as vx/vy/vz, one sector instead
+        // of three), so the winner's record is already here when Steer needs it.
         const double qx = c->x_rand[0], qy = c->x_rand[1], qz = c->x_rand[2];
         if (cnt <= v.near_cap) {
             const int *cand = v.cand + (size_t)e * v.near_cap;
-            for (int k = lane; k < cnt; k += 32) { const int i = cand[k]; lexmin(bs, bi, exact_scan_value<D>(v, e, i, qx, qy, qz), i); }
+            have_rec = true;
+            for (int k = lane; k < cnt; k += 32) {
+                const int i = cand[k];
+                const Node nd = load_node(nodes + i);
+                const int4 hh = load_hint(hints + i);
+                const double dx = XSUB(qx, nd.x), dy = XSUB(qy, nd.y), dz = D == 3 ? XSUB(qz, nd.z) : 0.0;
+                const double val = D == 3 ? XSQRT(sq3_rows(dx, dy, dz)) : np_hypot(dx, dy);
+                if (val < bs || (val == bs && i < bi)) { bs = val; bi = i; nn = nd; hn = hh; }
+            }
         } else {
             const int n = c->n;
             for (int i = lane; i < n; i += 32) lexmin(bs, bi, exact_scan_value<D>(v, e, i, qx, qy, qz), i);
@@ -663,13 +725,20 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
     } else {
         for (int k = lane; k < v.chunks; k += 32) lexmin(bs, bi, v.part_s[(size_t)e * v.chunks + k], v.part_i[(size_t)e * v.chunks + k]);
     }
+    const int my_bi = bi;
     warp_lexmin(bs, bi);
     const int nearest = __shfl_sync(0xffffffffu, bi, 0);
-    Node *nodes = v.nodes + (size_t)e * v.stride;
     const G &g = *GeomOf<D>::ptr(v, e);
-    const Node nn = load_node(nodes + nearest);
-    int4 *hints = v.hints + (size_t)e * v.stride;
-    const int4 hn = load_hint(hints + nearest);
+    if (have_rec) {      // broadcast the winning lane's record
+        const int src = __ffs(__ballot_sync(0xffffffffu, my_bi == nearest)) - 1;
+        nn.x = __shfl_sync(0xffffffffu, nn.x, src); nn.y = __shfl_sync(0xffffffffu, nn.y, src);
+        nn.z = __shfl_sync(0xffffffffu, nn.z, src);
+        hn.x = __shfl_sync(0xffffffffu, hn.x, src); hn.y = __shfl_sync(0xffffffffu, hn.y, src);
+        hn.z = __shfl_sync(0xffffffffu, hn.z, src); hn.w = __shfl_sync(0xffffffffu, hn.w, src);
+    } else {
+        nn = load_node(nodes + nearest);
+        hn = load_hint(hints + nearest);
+    }
     const double xn[3] = {nn.x, nn.y, nn.z};
     // every lane computes the same x_new (cheap, avoids broadcasts)
     const double d0 = XSUB(c->x_rand[0], xn[0]), d1 = XSUB(c->x_rand[1], xn[1]), d2 = D == 3 ? XSUB(c->x_rand[2], xn[2]) : 0.0;
@@ -726,6 +795,7 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
         // Line(nearest, new) (rrt_base_3d.py:132-137); the root walk that turns it into
         // curr_node_new_cost and node_new_cost runs in k_expand together with the neighbours' walks
         c->cnew_default = edge_len<D>(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2]));
+        set_parent(tree_of(v, e), new_idx, nearest, c->cnew_default);
     }
     c->new_idx = new_idx;
     c->x_new[0] = xnew[0]; c->x_new[1] = xnew[1]; c->x_new[2] = xnew[2];
@@ -749,6 +819,8 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
 // ascending index order.
 template <int D, bool kForce>
 __global__ void __launch_bounds__(256) k_near(View v) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
     EnvCtl *c = v.ctl + e;
     if (!kForce && (!c->go || c->skip)) return;
@@ -892,6 +964,8 @@ __device__ __forceinline__ void append_cand(const View &v, EnvCtl *c, int e, int
 
 template <int D, bool kU16, bool kForce>
 __global__ void __launch_bounds__(256) k_nearest_m(View v) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
     EnvCtl *c = v.ctl + e;
     const ScanHdr h = load_hdr(&c->hdr[0]);
@@ -934,6 +1008,8 @@ __global__ void __launch_bounds__(256) k_nearest_m(View v) {
 
 template <int D, bool kU16, bool kForce>
 __global__ void __launch_bounds__(256) k_near_m(View v) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
     EnvCtl *c = v.ctl + e;
     const ScanHdr h = load_hdr(&c->hdr[1]);
@@ -1017,6 +1093,7 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
 template <int D>
 __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     typedef typename GeomOf<D>::type G;
+    pdl_wait();
     const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
     if (!c->go) return;
@@ -1025,13 +1102,12 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     __shared__ int s_near[kNearSmem];
     __shared__ double s_d[kNearSmem];
     __shared__ double s_cost[kNearSmem];                // cost(near_k) before any rewiring of this iteration
-    __shared__ double s_via[kNearSmem];                 // cost(x_new) if near_k became its parent
+    __shared__ double s_first[kNearSmem];               // Line(near_k, x_new) by math.hypot: first term of cost(x_new) via near_k, and the edge length if near_k is re-wired
     __shared__ unsigned long long s_anc[kNearSmem];     // Near members on near_k's root path (see below)
     __shared__ unsigned s_bloom[32];
     __shared__ unsigned s_rew[kNearSmem / 32];
-    __shared__ double s_curr[2];                        // curr_node_new_cost, cost(new) via the steer parent
+    __shared__ double s_curr[3];                        // curr_node_new_cost, cost(new) via the steer parent, cost(new) via ChooseParent's winner
     __shared__ int4 s_hnew;                             // ancestor hints of x_new after ChooseParent
-    double *s_first = s_via;                            // Line(near_k, x_new) by math.hypot, replaced by the walk's result
     __shared__ double sm_s[4];
     __shared__ int sm_i[4];
     __shared__ int s_m;
@@ -1135,7 +1211,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 atomicOr(&s_bloom[hsh >> 5], 1u << (hsh & 31));
             }
             __syncthreads();
-            double bs = XINF; int bk = INT_MAX;
+            double bs = XINF, via_best = 0.0; int bk = INT_MAX;
             const TreeRef t = tree_of(v, e);
             for (int k = tid; k <= m; k += blockDim.x) {
                 if (k == m) {
@@ -1150,8 +1226,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 const int idx = s_near[k];
                 double cacc = 0.0, vacc = s_first[k];
                 unsigned long long anc = 0;   // [0,30): three 10-bit positions, [30,32): count, bit 32: overflow, bit 33: through x_new
-                walk_to_root(t, idx, [&](int par, const Node &cur, const Node &p) {
-                    const double eg = edge_len<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
+                walk_to_root(t, idx, [&](int par, double eg) {
                     cacc = XADD(cacc, eg); vacc = XADD(vacc, eg);
                     const unsigned hsh = ((unsigned)par * 2654435761u) >> 22;
                     if ((s_bloom[hsh >> 5] >> (hsh & 31)) & 1u) {
@@ -1167,20 +1242,24 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                         }
                     }
                 });
-                s_cost[k] = cacc; s_via[k] = vacc; s_anc[k] = anc;
-                lexmin(bs, bk, XADD(cacc, s_d[k]), k);
+                s_cost[k] = cacc; s_anc[k] = anc;
+                const double via_cost = XADD(cacc, s_d[k]);
+                if (via_cost < bs) { bs = via_cost; bk = k; via_best = vacc; }   // k ascends per thread: first minimum
             }
+            const int my_bk = bk;
             block_lexmin(bs, bk, sm_s, sm_i);      // result broadcast to every thread
+            if (my_bk == bk) s_curr[2] = via_best; // cost(x_new) if the winner becomes its parent (one walk, two sums)
+            __syncthreads();
             PHASE_MARK(3)
             // ---- choose_parent (rrt_star_3d.py:80-90)
             const bool reparent = bs < s_curr[0];
-            const double c_new = reparent ? s_via[bk] : s_curr[1];
+            const double c_new = reparent ? s_curr[2] : s_curr[1];
             const bool new_moved = reparent && !c->inserted;   // an existing vertex (duplicate guard) changed its parent
             if (tid == 0) {
                 int4 hnew;
                 if (reparent) {
                     const int q = s_near[bk];
-                    store_parent(nodes + new_idx, q);
+                    set_parent(t, new_idx, q, s_first[bk]);    // s_first[bk] = Line(near_bk, x_new) == the new edge
                     const int4 hq = load_hint(t.hints + q);
                     hnew = make_int4(q, hq.x, hq.y, hq.z);
                     __stcg(t.hints + new_idx, hnew);
@@ -1221,7 +1300,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             if (!any_dep) {
                 for (int k = tid; k < m; k += blockDim.x)
                     if ((s_rew[k >> 5] >> (k & 31)) & 1u) {
-                        store_parent(nodes + s_near[k], new_idx);
+                        set_parent(t, s_near[k], new_idx, s_first[k]);
                         store_hint(t.hints + s_near[k], new_idx, hnew);
                     }
                 if (tid == 0 && any_dec) c->tree_changed = 1;
@@ -1240,7 +1319,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                         }
                         const double ck = dirty ? cost_walk<D>(t, s_near[k]) : s_cost[k];
                         if (ck > XADD(c_new, s_d[k])) {
-                            store_parent(nodes + s_near[k], new_idx);
+                            set_parent(t, s_near[k], new_idx, s_first[k]);
                             store_hint(t.hints + s_near[k], new_idx, hnew);
                             s_rew[k >> 5] |= 1u << (k & 31);
                             any = true;
@@ -1278,11 +1357,6 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         __syncthreads();
     }
     PHASE_MARK(5)
-#ifdef NIRRT_PHASE_TIMING
-    if (tid == 0 && (e % 97) == 0 && (c->n % 50) == 0)
-        printf("expand e=%d n=%d cand=%d near=%d sort=%lld filter=%lld walks=%lld serial=%lld goal=%lld fast=%llu slow=%llu\n", e, c->n, c->cand_cnt, c->near_cnt,
-               t_ph[1] - t_ph[0], t_ph[2] - t_ph[1], t_ph[3] - t_ph[2], t_ph[4] - t_ph[3], t_ph[5] - t_ph[4], g_walk_stats[0], g_walk_stats[1]);
-#endif
 
     // ---- per-iteration record + phase machine (RRT* family; the IRRT* family records in k_top)
     if (!fam_informed(v.variant) && v.mode == NIRRT_MODE_PLANNING_RANDOM) {
@@ -1322,6 +1396,12 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         __syncthreads();
         top_body<D>(v, e, g, !skipped, sm_s, sm_i);
     }
+#ifdef NIRRT_PHASE_TIMING
+    PHASE_MARK(6)
+    if (tid == 0 && (e % 97) == 0 && (c->n % 50) == 0)
+        printf("expand e=%d n=%d cand=%d near=%d sort=%lld filter=%lld walks=%lld serial=%lld goal=%lld top=%lld fast=%llu slow=%llu\n", e, c->n, c->cand_cnt, c->near_cnt,
+               t_ph[1] - t_ph[0], t_ph[2] - t_ph[1], t_ph[3] - t_ph[2], t_ph[4] - t_ph[3], t_ph[5] - t_ph[4], t_ph[6] - t_ph[5], g_walk_stats[0], g_walk_stats[1]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1430,6 +1510,7 @@ __global__ void k_set_problems(View v, ProblemUpload u) {
     Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = c->start[2]; nd.parent = 0;
     v.nodes[o] = nd;
     v.hints[o] = make_int4(0, 0, 0, 0);
+    { Link l; l.elen = 0.0; l.parent = 0; l.pad = 0; v.links[o] = l; }
     c->n = 1;
     c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
     c->state = ST_DONE; c->budget = 0; set_idle(c); c->n_rec = 0; c->err = 0; c->resumed = 0;
@@ -1477,6 +1558,7 @@ __global__ void k_set_problems_2d(View v, ProblemUpload2 u) {
     Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = 0.0; nd.parent = 0;
     v.nodes[o] = nd;
     v.hints[o] = make_int4(0, 0, 0, 0);
+    { Link l; l.elen = 0.0; l.parent = 0; l.pad = 0; v.links[o] = l; }
     c->n = 1;
     c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
     c->state = ST_DONE; c->budget = 0; set_idle(c); c->n_rec = 0; c->err = 0; c->resumed = 0;
@@ -1551,25 +1633,40 @@ __global__ void __launch_bounds__(kExpandThreads) k_goal_parent(View v, int use_
         else KERNEL<2, FORCE><<<grid, block, smem, stream>>>(__VA_ARGS__);             \
     } while (0)
 
+// launch of a kernel(View); pdl: allow it to become resident while its predecessor in the stream drains
+static void launch_view(void (*kernel)(View), dim3 grid, dim3 block, cudaStream_t s, const View &v, bool pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, v);
+}
+
 // the two scans of one iteration in the batch's scan layout (u16 / f32 mirror or the f64 arrays)
 template <bool kForce>
-static void launch_scan(const View &v, int which, int count, cudaStream_t s) {
+static void launch_scan(const View &v, int which, int count, cudaStream_t s, bool pdl = false) {
     const dim3 grid(v.chunks, count);
+    void (*k)(View);
     if (v.ux) {
-        if (which == 0) { if (v.dim == 3) k_nearest_m<3, true, kForce><<<grid, 256, 0, s>>>(v); else k_nearest_m<2, true, kForce><<<grid, 256, 0, s>>>(v); }
-        else { if (v.dim == 3) k_near_m<3, true, kForce><<<grid, 256, 0, s>>>(v); else k_near_m<2, true, kForce><<<grid, 256, 0, s>>>(v); }
+        if (which == 0) k = v.dim == 3 ? k_nearest_m<3, true, kForce> : k_nearest_m<2, true, kForce>;
+        else k = v.dim == 3 ? k_near_m<3, true, kForce> : k_near_m<2, true, kForce>;
     } else if (v.fx) {
-        if (which == 0) { if (v.dim == 3) k_nearest_m<3, false, kForce><<<grid, 256, 0, s>>>(v); else k_nearest_m<2, false, kForce><<<grid, 256, 0, s>>>(v); }
-        else { if (v.dim == 3) k_near_m<3, false, kForce><<<grid, 256, 0, s>>>(v); else k_near_m<2, false, kForce><<<grid, 256, 0, s>>>(v); }
+        if (which == 0) k = v.dim == 3 ? k_nearest_m<3, false, kForce> : k_nearest_m<2, false, kForce>;
+        else k = v.dim == 3 ? k_near_m<3, false, kForce> : k_near_m<2, false, kForce>;
     } else {
-        if (which == 0) LAUNCH_DB(v.dim, k_nearest, kForce, grid, 256, 0, s, v);
-        else LAUNCH_DB(v.dim, k_near, kForce, grid, 256, 0, s, v);
+        if (which == 0) k = v.dim == 3 ? k_nearest<3, kForce> : k_nearest<2, kForce>;
+        else k = v.dim == 3 ? k_near<3, kForce> : k_near<2, kForce>;
     }
+    launch_view(k, grid, 256, s, v, pdl);
 }
 
 constexpr int kMaxGroups = 8;
 struct nirrt_batch {
     View v;
+    bool pdl;        // iteration kernels use programmatic dependent launch (NIRRT_PDL=0 disables)
     int device;
     size_t stride_bytes;
     std::vector<void *> allocs;
@@ -1585,7 +1682,34 @@ struct nirrt_batch {
     cudaEvent_t ev_fork, ev_join[kMaxGroups];
     // pinned scratch for small synchronous reads
     EnvCtl *h_ctl;
+    // tree transfers (load_trees / read_trees): two persistent device staging buffers on two internal
+    // streams, so the layout kernel of one chunk of problems overlaps the PCIe copy of the next
+    void *stage[2];
+    int *stage_n;
+    int stage_envs;          // problems per staging buffer
+    cudaStream_t xs[2];
+    cudaEvent_t xe[2], xfork;
 };
+
+static int ensure_staging(nirrt_batch *b) {
+    if (b->stage[0]) return NIRRT_OK;
+    const View &v = b->v;
+    const size_t per_env = (size_t)v.cap * (v.dim * sizeof(double) + sizeof(long long));
+    size_t envs = ((size_t)128 << 20) / (per_env ? per_env : 1);   // ~128 MB per buffer
+    if (envs < 1) envs = 1;
+    if (envs > (size_t)v.E) envs = v.E;
+    b->stage_envs = (int)envs;
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaMalloc(&b->stage[i], envs * per_env));
+        b->allocs.push_back(b->stage[i]);
+        CUDA_TRY(cudaStreamCreateWithFlags(&b->xs[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&b->xe[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&b->xfork, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc((void **)&b->stage_n, sizeof(int) * v.E));
+    b->allocs.push_back(b->stage_n);
+    return NIRRT_OK;
+}
 
 static int dalloc(nirrt_batch *b, void **p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
@@ -1600,8 +1724,9 @@ static int dalloc(nirrt_batch *b, void **p, size_t bytes) {
 static int pick_chunks(int E) {
     const char *env = getenv("NIRRT_CHUNKS");
     if (env && atoi(env) > 0) return atoi(env) > 64 ? 64 : atoi(env);
-    // aim for ~8 resident 256-thread CTAs on each of the 148 SMs
-    int c = (148 * 8 + E - 1) / E;
+    // aim for ~4 resident 256-thread CTAs of one group's scan on each of the 148 SMs (the other groups'
+    // kernels fill the rest; measured on 512 x 100k: 10 chunks at 64 problems per group beat 5 and 20)
+    int c = (148 * 4 + E - 1) / E;
     if (c < 1) c = 1;
     if (c > 64) c = 64;
     return c;
@@ -1617,6 +1742,11 @@ extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
         if (b->ev_join[g]) cudaEventDestroy(b->ev_join[g]);
     }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    for (int i = 0; i < 2; i++) {
+        if (b->xs[i]) cudaStreamDestroy(b->xs[i]);
+        if (b->xe[i]) cudaEventDestroy(b->xe[i]);
+    }
+    if (b->xfork) cudaEventDestroy(b->xfork);
     delete b;
     return NIRRT_OK;
 }
@@ -1637,12 +1767,16 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     b->device = d->device; b->launches = 0; b->goal_lists = false; b->h_ctl = nullptr;
     b->groups = 1; b->ev_fork = nullptr;
     for (int g = 0; g < kMaxGroups; g++) { b->gs[g] = nullptr; b->ev_join[g] = nullptr; }
+    for (int i = 0; i < 2; i++) { b->stage[i] = nullptr; b->xs[i] = nullptr; b->xe[i] = nullptr; }
+    b->stage_n = nullptr; b->stage_envs = 0; b->xfork = nullptr;
     View &v = b->v;
     v.E = d->n_envs; v.cap = d->capacity; v.dim = d->dim;
     v.stride = (d->capacity + 63) & ~63;
     {
+        const char *pdl = getenv("NIRRT_PDL");
+        b->pdl = !(pdl && atoi(pdl) == 0);
         const char *g = getenv("NIRRT_GROUPS");
-        b->groups = g ? atoi(g) : (d->n_envs >= 256 ? 4 : (d->n_envs >= 64 ? 2 : 1));
+        b->groups = g ? atoi(g) : (d->n_envs >= 512 ? 8 : (d->n_envs >= 256 ? 4 : (d->n_envs >= 64 ? 2 : 1)));
         if (b->groups < 1) b->groups = 1;
         if (b->groups > kMaxGroups) b->groups = kMaxGroups;
         if (b->groups > d->n_envs) b->groups = d->n_envs;
@@ -1670,6 +1804,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     }
     DALLOC(v.nodes, Node, EV);
     DALLOC(v.hints, int4, EV);
+    DALLOC(v.links, Link, EV);
     if (v.dim == 3) { DALLOC(v.geom, Geom3, v.E); }
     else {
         DALLOC(v.geom2, Geom2, v.E); DALLOC(v.mt_py, MtState, v.E);
@@ -1922,12 +2057,6 @@ extern "C" int nirrt_batch_set_cloud(nirrt_batch *b, int env, const double *poin
 
 // Tree transfers move whole groups of problems per copy (staging <= 2 GB): two large PCIe
 // transfers and one layout kernel per group instead of per-problem copies.
-static int tree_chunk(const View &v) {
-    const size_t per_env = (size_t)v.cap * (v.dim * sizeof(double) + sizeof(long long));
-    size_t c = ((size_t)2 << 30) / (per_env ? per_env : 1);
-    if (c < 1) c = 1;
-    return (int)(c > 65535 ? 65535 : c);
-}
 __global__ void k_scatter_trees(View v, int env_begin, const int *n, const double *verts, const long long *parents) {
     const int k = blockIdx.y;
     const int nk = n[k];
@@ -1949,12 +2078,14 @@ __global__ void k_scatter_trees(View v, int env_begin, const int *n, const doubl
         if (i == 0) { v.ctl[env].n = nk; v.ctl[env].tree_changed = 1; }
     }
 }
-// ancestor hints of freshly loaded trees: the true ancestors 1..4 hops up
-__global__ void k_build_hints(View v, int env_begin, const int *n) {
+// walk records of freshly loaded trees: edge length to the parent and the true ancestors 1..4 hops up
+template <int D>
+__global__ void k_build_links(View v, int env_begin, const int *n) {
     const int k = blockIdx.y, env = env_begin + k;
     const int nk = n[k];
     const Node *nodes = v.nodes + (size_t)env * v.stride;
     int4 *hints = v.hints + (size_t)env * v.stride;
+    Link *links = v.links + (size_t)env * v.stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x) {
         int a[4], cur = i;
         for (int q = 0; q < 4; q++) {
@@ -1963,6 +2094,11 @@ __global__ void k_build_hints(View v, int env_begin, const int *n) {
             a[q] = cur;
         }
         hints[i] = make_int4(a[0], a[1], a[2], a[3]);
+        const Node me = nodes[i], pa = nodes[a[0]];
+        Link l;
+        l.elen = i == 0 ? 0.0 : edge_len<D>(XSUB(me.x, pa.x), XSUB(me.y, pa.y), XSUB(me.z, pa.z));
+        l.parent = a[0]; l.pad = 0;
+        links[i] = l;
     }
 }
 __global__ void k_gather_trees(View v, int env_begin, double *verts, long long *parents) {
@@ -1988,19 +2124,28 @@ extern "C" int nirrt_batch_load_trees(nirrt_batch *b, int env_begin, int count, 
     for (int k = 0; k < count; k++)
         if (n[k] < 1 || n[k] > v.cap) return fail(NIRRT_ERR_INVALID, "tree size out of range");
     if (count == 0) return NIRRT_OK;
-    const int chunk = tree_chunk(v) < count ? tree_chunk(v) : count;
-    TempBufs t;
-    double *dv; long long *dp; int *dn;
-    TRY(t.make<double>((size_t)chunk * v.cap * v.dim, &dv)); TRY(t.make<long long>((size_t)chunk * v.cap, &dp)); TRY(t.make<int>((size_t)count, &dn));
+    TRY(ensure_staging(b));
+    const int chunk = b->stage_envs;
+    int *dn = b->stage_n + env_begin;
     CUDA_TRY(cudaMemcpyAsync(dn, n, sizeof(int) * count, cudaMemcpyHostToDevice, s));
-    for (int k0 = 0; k0 < count; k0 += chunk) {
+    CUDA_TRY(cudaEventRecord(b->xfork, s));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(b->xs[i], b->xfork, 0));
+    int ci = 0;
+    for (int k0 = 0; k0 < count; k0 += chunk, ci++) {
         const int m = count - k0 < chunk ? count - k0 : chunk;
-        CUDA_TRY(cudaMemcpyAsync(dv, vertices + (size_t)k0 * v.cap * v.dim, sizeof(double) * v.dim * v.cap * m, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(dp, parents + (size_t)k0 * v.cap, sizeof(long long) * v.cap * m, cudaMemcpyHostToDevice, s));
+        cudaStream_t xs = b->xs[ci & 1];
+        double *dv = (double *)b->stage[ci & 1];
+        long long *dp = (long long *)(dv + (size_t)m * v.cap * v.dim);
+        CUDA_TRY(cudaMemcpyAsync(dv, vertices + (size_t)k0 * v.cap * v.dim, sizeof(double) * v.dim * v.cap * m, cudaMemcpyHostToDevice, xs));
+        CUDA_TRY(cudaMemcpyAsync(dp, parents + (size_t)k0 * v.cap, sizeof(long long) * v.cap * m, cudaMemcpyHostToDevice, xs));
         const int gx = (v.cap + 255) / 256 < 256 ? (v.cap + 255) / 256 : 256;
-        k_scatter_trees<<<dim3(gx, m), 256, 0, s>>>(v, env_begin + k0, dn + k0, dv, dp);
-        k_build_hints<<<dim3(gx, m), 256, 0, s>>>(v, env_begin + k0, dn + k0);
+        k_scatter_trees<<<dim3(gx, m), 256, 0, xs>>>(v, env_begin + k0, dn + k0, dv, dp);
+        LAUNCH_D(v.dim, k_build_links, dim3(gx, m), 256, 0, xs, v, env_begin + k0, dn + k0);
         CHECK_LAUNCH();
+    }
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaEventRecord(b->xe[i], b->xs[i]));
+        CUDA_TRY(cudaStreamWaitEvent(s, b->xe[i], 0));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     return NIRRT_OK;
@@ -2015,17 +2160,25 @@ extern "C" int nirrt_batch_read_trees_sync(nirrt_batch *b, int env_begin, int co
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(b->h_ctl, v.ctl, sizeof(EnvCtl) * v.E, cudaMemcpyDeviceToHost, s));
     if (count == 0) { CUDA_TRY(cudaStreamSynchronize(s)); return NIRRT_OK; }
-    const int chunk = tree_chunk(v) < count ? tree_chunk(v) : count;
-    TempBufs t;
-    double *dv; long long *dp;
-    TRY(t.make<double>((size_t)chunk * v.cap * v.dim, &dv)); TRY(t.make<long long>((size_t)chunk * v.cap, &dp));
-    for (int k0 = 0; k0 < count; k0 += chunk) {
+    TRY(ensure_staging(b));
+    const int chunk = b->stage_envs;
+    CUDA_TRY(cudaEventRecord(b->xfork, s));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(b->xs[i], b->xfork, 0));
+    int ci = 0;
+    for (int k0 = 0; k0 < count; k0 += chunk, ci++) {
         const int m = count - k0 < chunk ? count - k0 : chunk;
+        cudaStream_t xs = b->xs[ci & 1];
+        double *dv = (double *)b->stage[ci & 1];
+        long long *dp = (long long *)(dv + (size_t)m * v.cap * v.dim);
         const int gx = (v.cap + 255) / 256 < 256 ? (v.cap + 255) / 256 : 256;
-        k_gather_trees<<<dim3(gx, m), 256, 0, s>>>(v, env_begin + k0, dv, dp);
+        k_gather_trees<<<dim3(gx, m), 256, 0, xs>>>(v, env_begin + k0, dv, dp);
         CHECK_LAUNCH();
-        CUDA_TRY(cudaMemcpyAsync(vertices + (size_t)k0 * v.cap * v.dim, dv, sizeof(double) * v.dim * v.cap * m, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(parents + (size_t)k0 * v.cap, dp, sizeof(long long) * v.cap * m, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(vertices + (size_t)k0 * v.cap * v.dim, dv, sizeof(double) * v.dim * v.cap * m, cudaMemcpyDeviceToHost, xs));
+        CUDA_TRY(cudaMemcpyAsync(parents + (size_t)k0 * v.cap, dp, sizeof(long long) * v.cap * m, cudaMemcpyDeviceToHost, xs));
+    }
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaEventRecord(b->xe[i], b->xs[i]));
+        CUDA_TRY(cudaStreamWaitEvent(s, b->xe[i], 0));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     for (int k = 0; k < count; k++) n[k] = b->h_ctl[env_begin + k].n;
@@ -2056,11 +2209,12 @@ static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count,
     View v = b->v;
     v.env0 = env0;
     v.fuse_top = last ? 0 : 1;
-    if (first) { LAUNCH_D(v.dim, k_top, count, 128, 0, s, v); b->launches += 1; }
-    launch_scan<false>(v, 0, count, s);
-    LAUNCH_D(v.dim, k_steer, count, 32, 0, s, v);
-    launch_scan<false>(v, 1, count, s);
-    LAUNCH_D(v.dim, k_expand, count, kExpandThreads, 0, s, v);
+    const bool pdl = b->pdl;
+    if (first) { launch_view(v.dim == 3 ? k_top<3> : k_top<2>, count, 128, s, v, false); b->launches += 1; }
+    launch_scan<false>(v, 0, count, s, pdl);
+    launch_view(v.dim == 3 ? k_steer<3> : k_steer<2>, count, 32, s, v, pdl);
+    launch_scan<false>(v, 1, count, s, pdl);
+    launch_view(v.dim == 3 ? k_expand<3> : k_expand<2>, count, kExpandThreads, s, v, pdl);
     b->launches += 4;
     return NIRRT_OK;
 }
@@ -2332,7 +2486,7 @@ static View single_env_view(const View &v, int env) {
     View w = v;   // shift every per-env array so that blockIdx.y == 0 addresses `env`
     w.vx += (size_t)env * v.stride; w.vy += (size_t)env * v.stride;
     if (v.vz) w.vz += (size_t)env * v.stride;
-    w.nodes += (size_t)env * v.stride; w.hints += (size_t)env * v.stride;
+    w.nodes += (size_t)env * v.stride; w.hints += (size_t)env * v.stride; w.links += (size_t)env * v.stride;
     if (v.geom) w.geom += env;
     if (v.geom2) w.geom2 += env;
     if (v.mt_py) w.mt_py += env;
