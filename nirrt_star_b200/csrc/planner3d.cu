@@ -92,6 +92,9 @@ struct __align__(16) EnvCtl {
     int state, saved_state, p1_done, left, budget, n_rec, resumed;
     // iteration scratch
     int go, skip, nearest, new_idx, inserted, cand_cnt, near_cnt;
+    int spec_cnt;     // speculative Near candidates collected by the Nearest scan (ball around x_rand)
+    int use_spec;     // k_steer: x_new == x_rand (up to rounding), the speculative list is the Near superset
+    int need_scan;    // k_steer: x_new != x_rand, k_expand runs the Near scan itself before filtering
     double x_rand[3], x_new[3];
     double r, T_near, curr_cost, c_best, c_update;
     double cnew_default;  // cost(new) if ChooseParent keeps the steer parent: the walk from x_new, leaf -> root
@@ -129,7 +132,8 @@ struct View {
     EnvCtl *ctl;
     double *part_s;
     int *part_i;
-    int *cand;       // [E][near_cap] unordered Near candidates of the current iteration
+    int *cand;       // [E][near_cap] unordered Nearest candidates (k_nearest_m -> k_steer), then Near candidates of a fallback scan
+    int *cand2;      // [E][near_cap] speculative Near candidates collected during the Nearest scan
     int *near_out;   // [E][near_cap] final (ordered, collision-filtered) Near list: trace
     int *sol;        // [E][sol_cap]  path_solutions
     int *gc_idx;     // [E][cap]      vertices within step_len of the goal (RRT* eval driver)
@@ -382,6 +386,7 @@ __device__ __forceinline__ void push_record(const View &v, EnvCtl *c, int e, dou
 
 // ---- mirror-scan helpers (see "Mirror scans" below)
 constexpr double kMarginU16 = 2.0;
+constexpr double kSpecSlack = 1e-6;   // world units: |x_new - x_rand| allowed when the speculative Near list is used (k_steer checks 1e-9 per axis)
 
 __device__ __forceinline__ unsigned short quantize_u16(double x, double lo, double scale) {
     int q = __double2int_rn((x - lo) * scale);
@@ -588,8 +593,19 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
     if (D == 2) py.flush();
     c->x_rand[0] = out[0]; c->x_rand[1] = out[1]; c->x_rand[2] = out[2];
     c->cand_cnt = 0;     // the Nearest mirror scan appends its in-band candidates here
+    c->spec_cnt = 0;
     c->go = 1;
-    write_hdr(v, c, 0, 1, c->x_rand, 0.f);
+    // Speculative Near: whenever the tree already reaches within step_len of x_rand (always, once it is
+    // dense) Steer returns x_new == x_rand up to rounding, so the ball around x_rand with the largest
+    // radius the insertion can produce (the table is evaluated at n and n + 1) is a superset of Near(x_new):
+    // the Nearest scan collects it in the same pass and the second scan of the iteration disappears.
+    {
+        const int n = c->n;
+        double rs = XMUL(c->search_radius, fmax(v.near_table[n], v.near_table[n + 1]));
+        if (c->step_len < rs) rs = c->step_len;
+        const double rm = (v.ux ? (rs + kSpecSlack) * c->qscale : rs + kSpecSlack) + c->margin;
+        write_hdr(v, c, 0, 1, c->x_rand, __double2float_ru(rm * rm * 1.000001));
+    }
 }
 
 template <int D>
@@ -808,6 +824,15 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
         c->near_thr = __double2float_ru(rm * rm * 1.000001);
         write_hdr(v, c, 1, 1, c->x_new, c->near_thr);
     }
+    if (v.ux || v.fx) {
+        // x_new == x_rand up to rounding (the tree reaches within step_len of the sample): the ball the Nearest
+        // scan collected around x_rand contains Near(x_new) -- no second scan.  Otherwise k_expand scans itself.
+        bool same = fabs(XSUB(xnew[0], c->x_rand[0])) <= 1e-9 && fabs(XSUB(xnew[1], c->x_rand[1])) <= 1e-9;
+        if (D == 3) same = same && fabs(XSUB(xnew[2], c->x_rand[2])) <= 1e-9;
+        const int use_spec = same && c->spec_cnt <= v.near_cap;
+        c->use_spec = use_spec;
+        c->need_scan = !use_spec;
+    } else { c->use_spec = 0; c->need_scan = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -963,7 +988,7 @@ __device__ __forceinline__ void append_cand(const View &v, EnvCtl *c, int e, int
 }
 
 template <int D, bool kU16, bool kForce>
-__global__ void __launch_bounds__(256) k_nearest_m(View v) {
+__global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
     pdl_wait();
     pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
@@ -980,12 +1005,18 @@ __global__ void __launch_bounds__(256) k_nearest_m(View v) {
     if (beg >= end) return;
     float a1 = INFINITY, a2 = INFINITY;   // best and second-best mirror value of this thread
     int i1 = INT_MAX;
+    const float thr = h.thr;              // speculative Near ball around x_rand (see top_body)
     mirror_scan<D, kU16>(v, e, beg, end, h.qx, h.qy, h.qz, [&](const float (&a)[kVec], int base) {
-        if (vec_min(a) < a2) {            // rare once the running values have settled
+        const float m = vec_min(a);
+        if (m < a2 || m <= thr) {         // rare once the running values have settled
 #pragma unroll
             for (int j = 0; j < kVec; j++) {
                 a2 = fminf(a2, fmaxf(a[j], a1));
                 if (a[j] < a1) { a1 = a[j]; i1 = base + j; }
+                if (a[j] <= thr) {
+                    const int slot = atomicAdd(&c->spec_cnt, 1);
+                    if (slot < v.near_cap) v.cand2[(size_t)e * v.near_cap + slot] = base + j;
+                }
             }
         }
     });
@@ -1124,12 +1155,35 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
 
     if (!skipped) {
         stage_geom<D>(&g, v, e);
-        int cnt = c->cand_cnt;
+        const int *cand = v.cand + (size_t)e * v.near_cap;
+        int cnt;
+        if (c->need_scan) {
+            // Near scan by this CTA (x_new != x_rand: sparse tree or the duplicate guard) -- same filter,
+            // same candidate list as the stand-alone k_near_m
+            const ScanHdr h = load_hdr(&c->hdr[1]);
+            const float thr = h.thr;
+            if (v.ux) mirror_scan<D, true>(v, e, 0, h.n, h.qx, h.qy, h.qz, [&](const float (&a)[8], int base) {
+                if (vec_min(a) <= thr) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (a[j] <= thr) append_cand(v, c, e, base + j);
+                }
+            });
+            else mirror_scan<D, false>(v, e, 0, h.n, h.qx, h.qy, h.qz, [&](const float (&a)[4], int base) {
+                if (vec_min(a) <= thr) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (a[j] <= thr) append_cand(v, c, e, base + j);
+                }
+            });
+            __syncthreads();
+            cnt = __ldcg(&c->cand_cnt);
+        } else if (c->use_spec) {
+            cnt = c->spec_cnt;
+            cand = v.cand2 + (size_t)e * v.near_cap;
+        } else cnt = c->cand_cnt;
         if (cnt > v.near_cap || cnt > kNearSmem) {
             if (tid == 0) c->err |= ERR_NEAR_OVERFLOW;
             cnt = min(min(cnt, v.near_cap), kNearSmem);
         }
-        const int *cand = v.cand + (size_t)e * v.near_cap;
         if (cnt <= 256) {
             // ascending order by rank counting (the indices are distinct): one barrier instead of a sorting network
             int *s_raw = s_near;                          // scratch until the compaction below fills s_near
@@ -1813,6 +1867,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     DALLOC(v.mt, MtState, v.E); DALLOC(v.ctl, EnvCtl, v.E);
     DALLOC(v.part_s, double, (size_t)v.E * v.chunks); DALLOC(v.part_i, int, (size_t)v.E * v.chunks);
     DALLOC(v.cand, int, (size_t)v.E * v.near_cap); DALLOC(v.near_out, int, (size_t)v.E * v.near_cap);
+    DALLOC(v.cand2, int, (size_t)v.E * v.near_cap);
     DALLOC(v.sol, int, (size_t)v.E * v.sol_cap);
     DALLOC(v.records, double, (size_t)v.E * v.rec_cap);
     DALLOC(v.pathseg, double, (size_t)v.E * v.path_cap);
@@ -2211,11 +2266,12 @@ static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count,
     v.fuse_top = last ? 0 : 1;
     const bool pdl = b->pdl;
     if (first) { launch_view(v.dim == 3 ? k_top<3> : k_top<2>, count, 128, s, v, false); b->launches += 1; }
+    const bool mirror = v.ux || v.fx;    // mirror scans collect Near speculatively during the Nearest pass
     launch_scan<false>(v, 0, count, s, pdl);
     launch_view(v.dim == 3 ? k_steer<3> : k_steer<2>, count, 32, s, v, pdl);
-    launch_scan<false>(v, 1, count, s, pdl);
+    if (!mirror) launch_scan<false>(v, 1, count, s, pdl);
     launch_view(v.dim == 3 ? k_expand<3> : k_expand<2>, count, kExpandThreads, s, v, pdl);
-    b->launches += 4;
+    b->launches += mirror ? 3 : 4;
     return NIRRT_OK;
 }
 
@@ -2276,7 +2332,7 @@ extern "C" int nirrt_batch_run_profiled_sync(nirrt_batch *b, int iters, float *m
         cudaEventRecord(e[2], s);
         LAUNCH_D(v.dim, k_steer, v.E, 32, 0, s, v);
         cudaEventRecord(e[3], s);
-        launch_scan<false>(v, 1, v.E, s);
+        if (!(v.ux || v.fx)) launch_scan<false>(v, 1, v.E, s);   // mirror scans: Near is collected by the Nearest pass
         cudaEventRecord(e[4], s);
         LAUNCH_D(v.dim, k_expand, v.E, kExpandThreads, 0, s, v);
         cudaEventRecord(e[5], s);
@@ -2492,7 +2548,7 @@ static View single_env_view(const View &v, int env) {
     if (v.mt_py) w.mt_py += env;
     w.mt += env; w.ctl += env;
     w.part_s += (size_t)env * v.chunks; w.part_i += (size_t)env * v.chunks;
-    w.cand += (size_t)env * v.near_cap; w.near_out += (size_t)env * v.near_cap;
+    w.cand += (size_t)env * v.near_cap; w.near_out += (size_t)env * v.near_cap; w.cand2 += (size_t)env * v.near_cap;
     w.E = 1;
     return w;
 }
