@@ -107,13 +107,15 @@ struct __align__(16) EnvCtl {
     int n_sol, n_goal, tree_changed, n_pc;
     long long last_gp;
     double last_len;
-    int err, pad;
+    int err;
+    unsigned stamp;   // k_expand invocations so far: tag of the Near stamps in the walk records
 };
 
 struct View {
     int E, cap, stride, chunks, near_cap, rec_cap, sol_cap, pc_cap, path_cap;
     int env0;        // first problem of the group an iteration kernel works on (see nirrt_batch_run)
     int fuse_top;    // k_expand ends with the next iteration's k_top work (driver, c_best refresh, sampling)
+    int fuse_steer;  // k_expand starts with k_steer's work (warp 0): one kernel for everything between two scans
     int variant, mode, iter_max, iter_after;
     double stop_below; // phase 1 ends when the recorded value drops below this (+inf: planning_random; finite: planning_block_gap)
     int n_limit;     // > 0: problems whose tree reached n_limit vertices idle (benchmark pre-growth)
@@ -225,7 +227,7 @@ __device__ __forceinline__ double hypot_band_sq(double h) {
 struct __align__(16) Link {
     double elen;   // math.hypot(v - parent(v)); 0 for the root
     int parent;
-    int pad;
+    int pad;       // Near stamp: (iteration tag << 10) | position in this iteration's Near list (k_expand), else stale/0
 };
 #ifdef NIRRT_PHASE_TIMING
 __device__ unsigned long long g_walk_stats[4];
@@ -256,7 +258,7 @@ __device__ __forceinline__ void set_parent(const TreeRef &t, int v, int par, dou
     __stcg(reinterpret_cast<int4 *>(t.links + v), make_int4(__double2loint(elen), __double2hiint(elen), par, 0));
 }
 
-// hop(par, edge_length) is called once per edge, leaf -> root
+// hop(par, edge_length, pad field of par's link) is called once per edge, leaf -> root
 template <typename F>
 __device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop) {
     if (idx == 0) return;
@@ -273,16 +275,16 @@ __device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop)
         int j = 0;
         int p = cur.parent;
         if (p == a1) {
-            hop(p, cur.elen); if (p == 0) return;
+            hop(p, cur.elen, l1.pad); if (p == 0) return;
             j = 1; p = l1.parent;
             if (p == a2) {
-                hop(p, l1.elen); if (p == 0) return;
+                hop(p, l1.elen, l2.pad); if (p == 0) return;
                 j = 2; p = l2.parent;
                 if (p == a3) {
-                    hop(p, l2.elen); if (p == 0) return;
+                    hop(p, l2.elen, l3.pad); if (p == 0) return;
                     j = 3; p = l3.parent;
                     if (p == a4) {
-                        hop(p, l3.elen); if (p == 0) return;
+                        hop(p, l3.elen, l4.pad); if (p == 0) return;
                         cur = l4; start = a4; h = hn;
 #ifdef NIRRT_PHASE_TIMING
                         atomicAdd(&g_walk_stats[0], 1ull);
@@ -303,7 +305,7 @@ __device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop)
         const int4 hp = load_hint(t.hints + p);
         __stcg(t.hints + start, j == 0 ? make_int4(p, hp.x, hp.y, hp.z) : j == 1 ? make_int4(a1, p, hp.x, hp.y)
                                 : j == 2 ? make_int4(a1, a2, p, hp.x) : make_int4(a1, a2, a3, p));
-        hop(p, cj.elen);
+        hop(p, cj.elen, lp.pad);
         if (p == 0) return;
         cur = lp; start = p; h = hp;
     }
@@ -314,7 +316,7 @@ __device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop)
 template <int D>
 __device__ double cost_walk(const TreeRef &t, int idx) {
     double c = 0.0;
-    walk_to_root(t, idx, [&](int, double e) { c = XADD(c, e); });
+    walk_to_root(t, idx, [&](int, double e, int) { c = XADD(c, e); });
     return c;
 }
 
@@ -326,7 +328,7 @@ __device__ double cost_walk(const TreeRef &t, int idx) {
 template <int D>
 __device__ __forceinline__ void cost_walk2(const TreeRef &t, int idx, double first, double &c_out, double &via_out) {
     double c = 0.0, a = first;
-    walk_to_root(t, idx, [&](int, double e) { c = XADD(c, e); a = XADD(a, e); });
+    walk_to_root(t, idx, [&](int, double e, int) { c = XADD(c, e); a = XADD(a, e); });
     c_out = c; via_out = a;
 }
 
@@ -702,15 +704,14 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
 // ------------------------------------------------------------------------------------------------
 // k_steer: argmin finish + new_state (rrt_star_3d.py:67-78 / rrt_star_2d.py:67-78) + steer-edge
 //          collision + duplicate guard / vertex insert (:40-51) + Near radius (:134 / :133)
+// Called by ONE warp per env: the k_steer kernel, or warp 0 of k_expand when the two are fused.
 template <int D>
-__global__ void __launch_bounds__(32) k_steer(View v) {
+__device__ __forceinline__ void steer_body(const View &v, int e) {
     typedef typename GeomOf<D>::type G;
-    pdl_wait();
-    const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
     const int go = c->go, cnt = c->cand_cnt;     // independent loads: one round trip
     if (!go) return;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     Node *nodes = v.nodes + (size_t)e * v.stride;
     int4 *hints = v.hints + (size_t)e * v.stride;
     double bs = XINF; int bi = INT_MAX;
@@ -833,6 +834,12 @@ __global__ void __launch_bounds__(32) k_steer(View v) {
         c->use_spec = use_spec;
         c->need_scan = !use_spec;
     } else { c->use_spec = 0; c->need_scan = 0; }
+}
+
+template <int D>
+__global__ void __launch_bounds__(32) k_steer(View v) {
+    pdl_wait();
+    steer_body<D>(v, v.env0 + blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1128,6 +1135,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
     if (!c->go) return;
+    if (v.fuse_steer) {
+        if (threadIdx.x < 32) steer_body<D>(v, e);
+        __syncthreads();
+    }
     __shared__ G g;
     __shared__ int s_cand[kNearSmem];
     __shared__ int s_near[kNearSmem];
@@ -1135,7 +1146,6 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     __shared__ double s_cost[kNearSmem];                // cost(near_k) before any rewiring of this iteration
     __shared__ double s_first[kNearSmem];               // Line(near_k, x_new) by math.hypot: first term of cost(x_new) via near_k, and the edge length if near_k is re-wired
     __shared__ unsigned long long s_anc[kNearSmem];     // Near members on near_k's root path (see below)
-    __shared__ unsigned s_bloom[32];
     __shared__ unsigned s_rew[kNearSmem / 32];
     __shared__ double s_curr[3];                        // curr_node_new_cost, cost(new) via the steer parent, cost(new) via ChooseParent's winner
     __shared__ int4 s_hnew;                             // ancestor hints of x_new after ChooseParent
@@ -1257,16 +1267,15 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             // existing vertex) lie on its path: Rewire is sequential in the reference
             // (rrt_star_3d.py:96-99), a neighbour's cost only changes when one of its ancestors was
             // re-parented earlier in the same loop, and only then is it walked again.
-            for (int i = tid; i < 32; i += blockDim.x) s_bloom[i] = 0;
             for (int i = tid; i < kNearSmem / 32; i += blockDim.x) s_rew[i] = 0;
-            __syncthreads();
-            for (int k = tid; k <= m; k += blockDim.x) {
-                const unsigned hsh = ((unsigned)(k < m ? s_near[k] : new_idx) * 2654435761u) >> 22;
-                atomicOr(&s_bloom[hsh >> 5], 1u << (hsh & 31));
-            }
+            // stamp the Near members in their walk records: a walk recognises them from the record it loads anyway
+            const TreeRef t = tree_of(v, e);
+            const int tag = (int)(c->stamp % 4194303u) + 1;
+            for (int k = tid; k < m; k += blockDim.x)
+                __stcg(reinterpret_cast<int *>(t.links + s_near[k]) + 3, (tag << 10) | k);
             __syncthreads();
             double bs = XINF, via_best = 0.0; int bk = INT_MAX;
-            const TreeRef t = tree_of(v, e);
+            PHASE_MARK(6)
             for (int k = tid; k <= m; k += blockDim.x) {
                 if (k == m) {
                     // the steer parent: curr_node_new_cost = cost(nearest) + Line(nearest, new)
@@ -1280,20 +1289,14 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 const int idx = s_near[k];
                 double cacc = 0.0, vacc = s_first[k];
                 unsigned long long anc = 0;   // [0,30): three 10-bit positions, [30,32): count, bit 32: overflow, bit 33: through x_new
-                walk_to_root(t, idx, [&](int par, double eg) {
+                walk_to_root(t, idx, [&](int par, double eg, int pad) {
                     cacc = XADD(cacc, eg); vacc = XADD(vacc, eg);
-                    const unsigned hsh = ((unsigned)par * 2654435761u) >> 22;
-                    if ((s_bloom[hsh >> 5] >> (hsh & 31)) & 1u) {
-                        if (par == new_idx) anc |= 1ull << 33;
-                        else {
-                            int lo = 0, hi = m - 1, pos = -1;
-                            while (lo <= hi) { const int mid = (lo + hi) >> 1; const int vv = s_near[mid]; if (vv == par) { pos = mid; break; } if (vv < par) lo = mid + 1; else hi = mid - 1; }
-                            if (pos >= 0) {
-                                const int cntp = (int)((anc >> 30) & 3ull);
-                                if (cntp < 3) { anc |= (unsigned long long)pos << (10 * cntp); anc = (anc & ~(3ull << 30)) | ((unsigned long long)(cntp + 1) << 30); }
-                                else anc |= 1ull << 32;
-                            }
-                        }
+                    if (par == new_idx) anc |= 1ull << 33;
+                    else if ((pad >> 10) == tag) {      // a stale or aliased stamp can only add a (harmless) dependency
+                        const int pos = pad & 1023;
+                        const int cntp = (int)((anc >> 30) & 3ull);
+                        if (cntp < 3) { anc |= (unsigned long long)pos << (10 * cntp); anc = (anc & ~(3ull << 30)) | ((unsigned long long)(cntp + 1) << 30); }
+                        else anc |= 1ull << 32;
                     }
                 });
                 s_cost[k] = cacc; s_anc[k] = anc;
@@ -1301,6 +1304,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 if (via_cost < bs) { bs = via_cost; bk = k; via_best = vacc; }   // k ascends per thread: first minimum
             }
             const int my_bk = bk;
+            PHASE_MARK(7)
             block_lexmin(bs, bk, sm_s, sm_i);      // result broadcast to every thread
             if (my_bk == bk) s_curr[2] = via_best; // cost(x_new) if the winner becomes its parent (one walk, two sums)
             __syncthreads();
@@ -1310,6 +1314,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             const double c_new = reparent ? s_curr[2] : s_curr[1];
             const bool new_moved = reparent && !c->inserted;   // an existing vertex (duplicate guard) changed its parent
             if (tid == 0) {
+                c->stamp++;
                 int4 hnew;
                 if (reparent) {
                     const int q = s_near[bk];
@@ -1451,10 +1456,9 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         top_body<D>(v, e, g, !skipped, sm_s, sm_i);
     }
 #ifdef NIRRT_PHASE_TIMING
-    PHASE_MARK(6)
     if (tid == 0 && (e % 97) == 0 && (c->n % 50) == 0)
         printf("expand e=%d n=%d cand=%d near=%d sort=%lld filter=%lld walks=%lld serial=%lld goal=%lld top=%lld fast=%llu slow=%llu\n", e, c->n, c->cand_cnt, c->near_cnt,
-               t_ph[1] - t_ph[0], t_ph[2] - t_ph[1], t_ph[3] - t_ph[2], t_ph[4] - t_ph[3], t_ph[5] - t_ph[4], t_ph[6] - t_ph[5], g_walk_stats[0], g_walk_stats[1]);
+               t_ph[1] - t_ph[0], t_ph[2] - t_ph[1], t_ph[3] - t_ph[2], t_ph[4] - t_ph[3], t_ph[5] - t_ph[4], clock64() - t_ph[5], t_ph[6] - t_ph[2], t_ph[7] - t_ph[6]);
 #endif
 }
 
@@ -2266,12 +2270,15 @@ static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count,
     v.fuse_top = last ? 0 : 1;
     const bool pdl = b->pdl;
     if (first) { launch_view(v.dim == 3 ? k_top<3> : k_top<2>, count, 128, s, v, false); b->launches += 1; }
-    const bool mirror = v.ux || v.fx;    // mirror scans collect Near speculatively during the Nearest pass
+    const bool mirror = v.ux || v.fx;    // mirror scans collect Near speculatively during the Nearest pass:
+    v.fuse_steer = mirror ? 1 : 0;       // the iteration is two kernels, the scan and everything else
     launch_scan<false>(v, 0, count, s, pdl);
-    launch_view(v.dim == 3 ? k_steer<3> : k_steer<2>, count, 32, s, v, pdl);
-    if (!mirror) launch_scan<false>(v, 1, count, s, pdl);
+    if (!mirror) {
+        launch_view(v.dim == 3 ? k_steer<3> : k_steer<2>, count, 32, s, v, pdl);
+        launch_scan<false>(v, 1, count, s, pdl);
+    }
     launch_view(v.dim == 3 ? k_expand<3> : k_expand<2>, count, kExpandThreads, s, v, pdl);
-    b->launches += mirror ? 3 : 4;
+    b->launches += mirror ? 2 : 4;
     return NIRRT_OK;
 }
 
