@@ -1015,15 +1015,22 @@ __global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
     const float thr = h.thr;              // speculative Near ball around x_rand (see top_body)
     mirror_scan<D, kU16>(v, e, beg, end, h.qx, h.qy, h.qz, [&](const float (&a)[kVec], int base) {
         const float m = vec_min(a);
-        if (m < a2 || m <= thr) {         // rare once the running values have settled
+        if (m < a2) {                     // rare once the running values have settled
 #pragma unroll
             for (int j = 0; j < kVec; j++) {
                 a2 = fminf(a2, fmaxf(a[j], a1));
                 if (a[j] < a1) { a1 = a[j]; i1 = base + j; }
-                if (a[j] <= thr) {
-                    const int slot = atomicAdd(&c->spec_cnt, 1);
-                    if (slot < v.near_cap) v.cand2[(size_t)e * v.near_cap + slot] = base + j;
-                }
+            }
+        }
+        if (m <= thr) {                   // ~|Near| of the env's vertices: cost proportional to the hits
+            unsigned hit = 0;
+#pragma unroll
+            for (int j = 0; j < kVec; j++) hit |= (a[j] <= thr ? 1u : 0u) << j;
+            while (hit) {
+                const int j = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const int slot = atomicAdd(&c->spec_cnt, 1);
+                if (slot < v.near_cap) v.cand2[(size_t)e * v.near_cap + slot] = base + j;
             }
         }
     });
@@ -1721,7 +1728,7 @@ static void launch_scan(const View &v, int which, int count, cudaStream_t s, boo
     launch_view(k, grid, 256, s, v, pdl);
 }
 
-constexpr int kMaxGroups = 8;
+constexpr int kMaxGroups = 16;
 struct nirrt_batch {
     View v;
     bool pdl;        // iteration kernels use programmatic dependent launch (NIRRT_PDL=0 disables)

@@ -299,12 +299,17 @@ __device__ __forceinline__ void top3_insert(Top3 &t, float d, int i) {
     }
 }
 // small batches: one warp per fine point (lane-strided scan + 3 warp arg-min rounds)
+// MODE 0: 3-NN search + interpolation; MODE 1: 3-NN search only (indices / weights -> knn_i / knn_w, runs
+// on the geometry stream, it needs coordinates only); MODE 2: interpolation from stored indices / weights.
+template <int MODE>
 __global__ void __launch_bounds__(256) k_interp_warp(const float *xyz1, int N, const float *xyz2, int S, const __half *feat1, int C1,
-                                                const __half *feat2, int C2, int B, __half *out) {
+                                                const __half *feat2, int C2, int B, __half *out, int4 *knn_i, float4 *knn_w) {
     const int lane = threadIdx.x & 31;
     const size_t p = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (p >= (size_t)B * N) return;
     const int b = (int)(p / N);
+    float w0, w1, w2; int ni[3];
+    if (MODE != 2) {
     const float *a = xyz1 + p * 3;
     const float ax = a[0], ay = a[1], az = a[2];
     const float as = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(256) k_interp_warp(const float *xyz1, int N, c
         d = __fadd_rn(d, qs);
         top3_insert(t, d, s);
     }
-    float nd[3]; int ni[3];
+    float nd[3];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         float bd = t.d[0]; int bi = t.i[0];
@@ -336,7 +341,15 @@ __global__ void __launch_bounds__(256) k_interp_warp(const float *xyz1, int N, c
     const float r0 = __fdiv_rn(1.f, __fadd_rn(nd[0], 1e-8f)), r1 = __fdiv_rn(1.f, __fadd_rn(nd[1], 1e-8f)),
                 r2 = __fdiv_rn(1.f, __fadd_rn(nd[2], 1e-8f));
     const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
-    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+    w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
+    if (MODE == 1) {
+        if (lane == 0) { knn_i[p] = make_int4(ni[0], ni[1], ni[2], 0); knn_w[p] = make_float4(w0, w1, w2, 0.f); }
+        return;
+    }
+    } else {
+        const int4 ki = knn_i[p]; const float4 kw = knn_w[p];
+        ni[0] = ki.x; ni[1] = ki.y; ni[2] = ki.z; w0 = kw.x; w1 = kw.y; w2 = kw.z;
+    }
     __half *o = out + p * (size_t)(C1 + C2);
     if (C1 > 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(feat1 + p * (size_t)C1);
@@ -355,8 +368,9 @@ __global__ void __launch_bounds__(256) k_interp_warp(const float *xyz1, int N, c
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const float *xyz2, int S, const __half *feat1, int C1,
-                                                const __half *feat2, int C2, int B, __half *out) {
+                                                const __half *feat2, int C2, int B, __half *out, int4 *knn_i, float4 *knn_w) {
     // phase 1: one thread per fine point walks the S coarse points (broadcast LDS.128) keeping its
     // three nearest in ascending (distance, index) order -- the first three entries of the
     // reference's sort; phase 2: the warp's 32 results are broadcast one at a time and all lanes
@@ -364,16 +378,25 @@ __global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const 
     extern __shared__ float4 s_q4[];          // [S] (x, y, z, |q|^2)
     const int b = blockIdx.y;
     const float *Q = xyz2 + (size_t)b * S * 3;
-    for (int i = threadIdx.x; i < S; i += blockDim.x) {
-        const float x = Q[i * 3], y = Q[i * 3 + 1], z = Q[i * 3 + 2];
-        s_q4[i] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    if (MODE != 2) {
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+            const float x = Q[i * 3], y = Q[i * 3 + 1], z = Q[i * 3 + 2];
+            s_q4[i] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);     // first fine point of this warp
     const int pi = i0 + lane;
     Top3 t;
     t.d[0] = t.d[1] = t.d[2] = INFINITY; t.i[0] = t.i[1] = t.i[2] = 0;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+    if (MODE == 2) {
+        if (pi < N) {
+            const int4 ki = knn_i[(size_t)b * N + pi]; const float4 kw = knn_w[(size_t)b * N + pi];
+            t.i[0] = ki.x; t.i[1] = ki.y; t.i[2] = ki.z; w0 = kw.x; w1 = kw.y; w2 = kw.z;
+        }
+    } else {
     if (pi < N) {
         const float *a = xyz1 + ((size_t)b * N + pi) * 3;
         const float ax = a[0], ay = a[1], az = a[2];
@@ -390,7 +413,12 @@ __global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const 
     const float r0 = __fdiv_rn(1.f, __fadd_rn(t.d[0], 1e-8f)), r1 = __fdiv_rn(1.f, __fadd_rn(t.d[1], 1e-8f)),
                 r2 = __fdiv_rn(1.f, __fadd_rn(t.d[2], 1e-8f));
     const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
-    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+    w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
+    if (MODE == 1) {
+        if (pi < N) { knn_i[(size_t)b * N + pi] = make_int4(t.i[0], t.i[1], t.i[2], 0); knn_w[(size_t)b * N + pi] = make_float4(w0, w1, w2, 0.f); }
+        return;
+    }
+    }
     const int cnt = min(32, N - i0);
     for (int j = 0; j < cnt; j++) {
         const int n0 = __shfl_sync(0xffffffffu, t.i[0], j), n1 = __shfl_sync(0xffffffffu, t.i[1], j), n2 = __shfl_sync(0xffffffffu, t.i[2], j);
@@ -578,6 +606,13 @@ struct nirrt_pn2 {
     bool profiling = false;
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // geometry stream: everything that needs coordinates only (FPS, ball query, 3-NN of the feature
+    // propagation levels) runs beside the feature stream's MLPs; events hand each level over
+    cudaStream_t gs = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_bq[4] = {nullptr, nullptr, nullptr, nullptr}, ev_knn[4] = {nullptr, nullptr, nullptr, nullptr};
+    int4 *knn_i[4] = {nullptr, nullptr, nullptr, nullptr};      // per FP level: the three nearest coarse points of every fine point
+    float4 *knn_w[4] = {nullptr, nullptr, nullptr, nullptr};    // and their normalised inverse-distance weights
+    bool two_streams = true;                                    // NIRRT_PN2_STREAMS=1 disables
 };
 
 template <typename T>
@@ -630,6 +665,9 @@ extern "C" int nirrt_pn2_destroy(nirrt_pn2 *h) {
     cudaSetDevice(h->device);
     for (void *p : h->allocs) cudaFree(p);
     for (int i = 0; i < 2; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->gs) cudaStreamDestroy(h->gs);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int i = 0; i < 4; i++) { if (h->ev_bq[i]) cudaEventDestroy(h->ev_bq[i]); if (h->ev_knn[i]) cudaEventDestroy(h->ev_knn[i]); }
     delete h;
     return NIRRT_OK;
 }
@@ -716,6 +754,14 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
     TRYC(palloc(h, &h->bufA, B * per_cloud + 4096));
     TRYC(palloc(h, &h->bufB, B * per_cloud + 4096));
     for (int f = 0; f < 4; f++) TRYC(palloc(h, &h->up[f], B * h->n[3 - f] * kUpC[f]));
+    for (int f = 0; f < 4; f++) { TRYC(palloc(h, &h->knn_i[f], B * h->n[3 - f])); TRYC(palloc(h, &h->knn_w[f], B * h->n[3 - f])); }
+    {
+        const char *st = getenv("NIRRT_PN2_STREAMS");
+        h->two_streams = !(st && atoi(st) == 1);
+        if (cudaStreamCreateWithFlags(&h->gs, cudaStreamNonBlocking) != cudaSuccess) FAILC("nirrt_pn2_create: cudaStreamCreate failed");
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+        for (int i = 0; i < 4; i++) { cudaEventCreateWithFlags(&h->ev_bq[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_knn[i], cudaEventDisableTiming); }
+    }
     TRYC(palloc(h, &h->d_pc, B * h->N0 * 3)); TRYC(palloc(h, &h->d_sm, B * h->N0)); TRYC(palloc(h, &h->d_gm, B * h->N0));
     TRYC(palloc(h, &h->d_fps, B * 4)); TRYC(palloc(h, &h->d_pred, B * h->N0)); TRYC(palloc(h, &h->d_score, B * h->N0));
     TRYC(palloc(h, &h->d_logp, B * h->N0 * 2));
@@ -789,6 +835,49 @@ static int fps_launch(nirrt_pn2 *h, int B, int l, const int *start, cudaStream_t
     return NIRRT_OK;
 }
 
+static int ball_query_launch(nirrt_pn2 *h, int B, int l, cudaStream_t s) {
+    const int N = h->n[l - 1], S = h->n[l];
+    const float r0 = (float)(kRad[l - 1][0] * kRad[l - 1][0]), r1 = (float)(kRad[l - 1][1] * kRad[l - 1][1]);
+    if ((long long)B * S >= 65536) {
+        const int bt = S >= 256 ? 256 : ((S + 31) / 32) * 32;
+        k_ball_query<<<dim3((S + bt - 1) / bt, B), bt, (size_t)N * 4 * sizeof(float), s>>>(
+            h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
+    } else {
+        k_ball_query_warp<<<dim3((S + 7) / 8, B), 256, (size_t)N * 4 * sizeof(float), s>>>(
+            h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
+    }
+    PCUDA(cudaGetLastError());
+    h->launches++;
+    return NIRRT_OK;
+}
+
+// feature propagation level f (fp4 .. fp1): mode 0 = 3-NN + interpolation, 1 = 3-NN only (coordinates),
+// 2 = interpolation from the stored neighbours (PointNetFeaturePropagation.forward, pointnet2_utils.py:278-309)
+static int interp_launch(nirrt_pn2 *h, int B, int f, int mode, const __half *upf, int upC, cudaStream_t s) {
+    const int lo = 3 - f;
+    const int N = h->n[lo], S = h->n[lo + 1];
+    const int C1 = lo == 0 ? 0 : kC[lo];
+    const int rows = B * N;
+    const __half *f1 = C1 ? h->feat[lo] : nullptr;
+#define INTERP_ARGS h->xyz[lo], N, h->xyz[lo + 1], S, f1, C1, upf, upC, B, h->bufA, h->knn_i[f], h->knn_w[f]
+    if ((long long)B * N >= 65536) {
+        const int bt = N >= 256 ? 256 : ((N + 31) / 32) * 32;
+        const dim3 grid((N + bt - 1) / bt, B);
+        const size_t smem = (size_t)S * sizeof(float4);
+        if (mode == 0) k_interp<0><<<grid, bt, smem, s>>>(INTERP_ARGS);
+        else if (mode == 1) k_interp<1><<<grid, bt, smem, s>>>(INTERP_ARGS);
+        else k_interp<2><<<grid, bt, 0, s>>>(INTERP_ARGS);
+    } else {
+        if (mode == 0) k_interp_warp<0><<<(rows + 7) / 8, 256, 0, s>>>(INTERP_ARGS);
+        else if (mode == 1) k_interp_warp<1><<<(rows + 7) / 8, 256, 0, s>>>(INTERP_ARGS);
+        else k_interp_warp<2><<<(rows + 7) / 8, 256, 0, s>>>(INTERP_ARGS);
+    }
+#undef INTERP_ARGS
+    PCUDA(cudaGetLastError());
+    h->launches++;
+    return NIRRT_OK;
+}
+
 extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const float *pc, const float *start_mask,
                                          const float *goal_mask, const int32_t *fps_start, int64_t *path_pred,
                                          float *path_score, float *logp, void *stream) {
@@ -801,30 +890,35 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
     const int B = batch;
     h->lastB = B;
     if (h->profiling) for (int i = 0; i < 8; i++) h->stage_ms[i] = 0.f;
+    // g: the geometry stream (coordinates only).  With stage profiling on everything stays on s so that the
+    // event brackets attribute serial times.
+    const bool split = h->two_streams && !h->profiling;
+    cudaStream_t g = split ? h->gs : s;
+    if (split) { PCUDA(cudaEventRecord(h->ev_fork, s)); PCUDA(cudaStreamWaitEvent(g, h->ev_fork, 0)); }
     {
         StageTimer t(h, s, 0);
-        k_prep<<<B, 256, 0, s>>>(pc, dim, start_mask, goal_mask, h->N0, h->xyz[0], h->in6);
+        k_prep<<<B, 256, 0, g>>>(pc, dim, start_mask, goal_mask, h->N0, h->xyz[0], h->in6);
         PCUDA(cudaGetLastError());
         h->launches++;
+    }
+    if (split) {
+        // the whole geometry chain is queued first: FPS + ball query per level, then the 3-NN searches
+        for (int l = 1; l <= 4; l++) {
+            PTRY(fps_launch(h, B, l, fps_start, g));
+            PTRY(ball_query_launch(h, B, l, g));
+            PCUDA(cudaEventRecord(h->ev_bq[l - 1], g));
+        }
+        for (int f = 0; f < 4; f++) {
+            PTRY(interp_launch(h, B, f, 1, nullptr, 0, g));
+            PCUDA(cudaEventRecord(h->ev_knn[f], g));
+        }
     }
     int li = 0;
     for (int l = 1; l <= 4; l++) {
         const int N = h->n[l - 1], S = h->n[l];
-        { StageTimer t(h, s, 1); PTRY(fps_launch(h, B, l, fps_start, s)); }
-        {
-            StageTimer t(h, s, 2);
-            const float r0 = (float)(kRad[l - 1][0] * kRad[l - 1][0]), r1 = (float)(kRad[l - 1][1] * kRad[l - 1][1]);
-            if ((long long)B * S >= 65536) {
-                const int bt = S >= 256 ? 256 : ((S + 31) / 32) * 32;
-                k_ball_query<<<dim3((S + bt - 1) / bt, B), bt, (size_t)N * 4 * sizeof(float), s>>>(
-                    h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
-            } else {
-                k_ball_query_warp<<<dim3((S + 7) / 8, B), 256, (size_t)N * 4 * sizeof(float), s>>>(
-                    h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
-            }
-            PCUDA(cudaGetLastError());
-            h->launches++;
-        }
+        if (split) PCUDA(cudaStreamWaitEvent(s, h->ev_bq[l - 1], 0));
+        if (!split) { StageTimer t(h, s, 1); PTRY(fps_launch(h, B, l, fps_start, s)); }
+        if (!split) { StageTimer t(h, s, 2); PTRY(ball_query_launch(h, B, l, s)); }
         for (int sc = 0; sc < 2; sc++) {
             const int K = kK[sc];
             const int rows = B * S * K;
@@ -884,15 +978,8 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
         const int rows = B * N;
         {
             StageTimer t(h, s, 5);
-            if ((long long)B * N >= 65536) {
-                const int bt = N >= 256 ? 256 : ((N + 31) / 32) * 32;
-                k_interp<<<dim3((N + bt - 1) / bt, B), bt, (size_t)S * sizeof(float4), s>>>(h->xyz[lo], N, h->xyz[lo + 1], S, C1 ? h->feat[lo] : nullptr,
-                                                                                              C1, upf, upC, B, h->bufA);
-            } else {
-                k_interp_warp<<<(rows + 7) / 8, 256, 0, s>>>(h->xyz[lo], N, h->xyz[lo + 1], S, C1 ? h->feat[lo] : nullptr, C1, upf, upC, B, h->bufA);
-            }
-            PCUDA(cudaGetLastError());
-            h->launches++;
+            if (split) PCUDA(cudaStreamWaitEvent(s, h->ev_knn[f], 0));
+            PTRY(interp_launch(h, B, f, split ? 2 : 0, upf, upC, s));
         }
         {
             StageTimer t(h, s, 6);

@@ -87,9 +87,11 @@ class PointNet2Engine:
         except Exception:
             pass
 
-    def classify(self, pc, start_mask, goal_mask, fps_start=None, return_logp=False):
+    def classify(self, pc, start_mask, goal_mask, fps_start=None, return_logp=False, out=None):
         """pc [B][N][2|3] f32, masks [B][N] f32 -> (path_pred int64 [B][N], path_score f32 [B][N]
-        [, log-probabilities f32 [B][N][2]]).  Host arrays in, host arrays out."""
+        [, log-probabilities f32 [B][N][2]]).  Host arrays in, host arrays out.  ``out=(pred, score)``
+        lets the caller supply the result arrays (e.g. pinned memory, which the device-to-host copies
+        reach at full PCIe rate); otherwise fresh arrays are returned like the reference's wrapper does."""
         pc = np.ascontiguousarray(pc, dtype=np.float32)
         if pc.ndim == 2:
             pc = pc[None]
@@ -101,8 +103,14 @@ class PointNet2Engine:
         if fps_start is None:
             fps_start = draw_fps_starts(B, N)
         fs = np.ascontiguousarray(fps_start, dtype=np.int32).reshape(B, 4)
-        pred = np.zeros((B, N), dtype=np.int64)
-        score = np.zeros((B, N), dtype=np.float32)
+        if out is not None:
+            pred, score = out
+            if pred.shape != (B, N) or pred.dtype != np.int64 or score.shape != (B, N) or score.dtype != np.float32 \
+                    or not pred.flags.c_contiguous or not score.flags.c_contiguous:
+                raise ValueError("out=(pred int64 [B][N], score float32 [B][N]) C-contiguous arrays expected")
+        else:
+            pred = np.empty((B, N), dtype=np.int64)
+            score = np.empty((B, N), dtype=np.float32)
         logp = np.zeros((B, N, 2), dtype=np.float32) if return_logp else None
         check(self.L.nirrt_pn2_classify_sync(self.h, B, dim, fp(pc), fp(sm), fp(gm),
                                              fs.ctypes.data_as(C.POINTER(C.c_int32)), i64p(pred), fp(score),

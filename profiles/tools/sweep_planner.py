@@ -65,11 +65,14 @@ def main():
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        import time
+        t0 = time.perf_counter()
         bp.run(K)
+        host_ms = (time.perf_counter() - t0) * 1e3 / K      # host time to ENQUEUE one step (no sync)
         ev1.record()
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / K
-        out = {"groups": int(g), "chunks": int(c), "ms_per_step": ms, "env_iters_per_s": E / (ms * 1e-3)}
+        out = {"groups": int(g), "chunks": int(c), "ms_per_step": ms, "env_iters_per_s": E / (ms * 1e-3), "host_enqueue_ms_per_step": host_ms}
         if args.profiled:
             prof = bp.run_profiled(100)
             out["kernel_us"] = {k: round(1e3 * x / 100, 2) for k, x in prof.items()}

@@ -194,3 +194,119 @@ def test_large_tree_window_matches_oracle(B):
         assert n2[e] == len(ov)
         assert np.array_equal(p2[e, :n2[e]], op)
         assert np.array_equal(v2[e, :n2[e]], ov)
+
+
+def _run_batch(B, problems, seeds, iters, variant=0, env=None):
+    """Trees after `iters` lock-step iterations with the given environment overrides (read at batch creation)."""
+    old = {}
+    for k, val in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = val
+    try:
+        bp = B.BatchPlanner3D(problems, iters, seeds=seeds)
+    finally:
+        for k, val in old.items():
+            if val is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = val
+    bp.begin(variant, B.MODE_PLANNING, iters)
+    bp.run(iters)
+    v, p, n = bp.read_trees()
+    bpv = bp.scan_bytes_per_vertex()
+    bp.close()
+    return v, p, n, bpv
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_scan_layouts_and_pipelines_agree(B, variant):
+    """The u16 fixed-point mirror (default), the f32 mirror and the plain f64 scans are three filters in
+    front of the same exact arithmetic, and groups / programmatic dependent launch only reorder
+    independent problems: every configuration must produce bit-identical trees (and match the oracle)."""
+    E, iters = 12, 1200
+    problems = [make_problem_3d(70 + i) for i in range(E)]
+    seeds = [300 + i for i in range(E)]
+    base = _run_batch(B, problems, seeds, iters, variant)
+    assert base[3] == 6                                           # default layout: 2 B per coordinate
+    for env, bpv in (({"NIRRT_SCAN": "f32"}, 12), ({"NIRRT_SCAN": "f64"}, 24), ({"NIRRT_GROUPS": "5"}, 6),
+                     ({"NIRRT_GROUPS": "1", "NIRRT_PDL": "0"}, 6), ({"NIRRT_CHUNKS": "3"}, 6)):
+        v, p, n, got_bpv = _run_batch(B, problems, seeds, iters, variant, env)
+        assert got_bpv == bpv, env
+        assert np.array_equal(n, base[2]), env
+        for e in range(E):
+            assert np.array_equal(p[e, :n[e]], base[1][e, :n[e]]), (env, e)
+            assert np.array_equal(v[e, :n[e]], base[0][e, :n[e]]), (env, e)
+    for e in range(0, E, 4):
+        o = _oracle(problems[e], iters, seeds[e])
+        o.run(iters, variant, 0)
+        ov, op = o.tree()
+        assert base[2][e] == len(ov) and np.array_equal(base[1][e, :len(ov)], op)
+        if variant == 0:
+            assert np.array_equal(base[0][e, :len(ov)], ov)
+
+
+def test_loaded_trees_continue_identically(B):
+    """load_trees rebuilds the walk records (cached edge lengths, ancestor hints, mirrors) from the
+    reference layout: a run continued on a fresh batch from a snapshot equals the uninterrupted run,
+    split runs equal one run, and both equal the oracle continued from the same snapshot."""
+    from oracle.planner_oracle import Oracle3D
+    E, first, second = 6, 2500, 700
+    problems = [make_problem_3d(90 + i) for i in range(E)]
+    seeds = [40 + i for i in range(E)]
+    total = first + second
+    a = B.BatchPlanner3D(problems, total, seeds=seeds)
+    a.begin(0, B.MODE_PLANNING, total)
+    a.run(first)
+    v, p, n = a.read_trees()
+    rng = a.get_rng()
+    a.run(second)
+    va, pa, na = a.read_trees()
+    b = B.BatchPlanner3D(problems, total, rng_states=rng)
+    b.load_trees(v, p, n)
+    b.begin(0, B.MODE_PLANNING, total)
+    b.run(second // 3); b.run(second - second // 3)
+    vb, pb, nb = b.read_trees()
+    assert np.array_equal(na, nb)
+    for e in range(E):
+        assert np.array_equal(pa[e, :na[e]], pb[e, :na[e]]) and np.array_equal(va[e, :na[e]], vb[e, :na[e]])
+        o = Oracle3D(problems[e], total, rng_state=rng[e])
+        o.load_tree(v[e, :n[e]], p[e, :n[e]])
+        o.run(second, 0, 0)
+        ov, op = o.tree()
+        assert nb[e] == len(ov) and np.array_equal(pb[e, :nb[e]], op) and np.array_equal(vb[e, :nb[e]], ov)
+    a.close(); b.close()
+
+
+def test_tree_invariants_at_scale(B):
+    """Size-independent properties on bigger trees than the oracle grows in test time: rooted and acyclic,
+    edges no longer than step_len and collision free, costs strictly increasing along every edge, and the
+    device scans agree with a brute-force numpy search on the final vertex arrays."""
+    E, iters = 32, 12000
+    problems = [make_problem_3d(200 + i) for i in range(E)]
+    bp = B.BatchPlanner3D(problems, iters, seeds=[77 + i for i in range(E)])
+    bp.begin(0, B.MODE_PLANNING, iters)
+    bp.run(iters)
+    v, p, n = bp.read_trees()
+    rng = np.random.default_rng(5)
+    for e in range(E):
+        ne = int(n[e]); ve = v[e, :ne]; pe = p[e, :ne]
+        assert ne > iters // 4 and pe[0] == 0 and pe.min() >= 0 and pe.max() < ne
+        # pointer jumping: every vertex reaches the root within ne hops (no cycles)
+        anc = pe.copy()
+        for _ in range(int(np.ceil(np.log2(ne))) + 1):
+            anc = anc[anc]
+        assert not anc.any()
+        seg = np.linalg.norm(ve - ve[pe], axis=1)
+        assert seg[1:].max() <= 10.0 + 1e-9 and seg[1:].min() > 1e-8
+        if e % 8 == 0:
+            edges = np.stack([ve[pe[1:]], ve[1:]], 1)
+            assert not bp.collide_edges(e, edges).any()
+            idx = rng.integers(1, ne, 300)
+            c = bp.costs(e, idx); cp = bp.costs(e, pe[idx])
+            assert np.all(c > cp)
+            q = rng.uniform(2, 48, (40, 3))
+            d = np.sqrt(((q[:, None, :] - ve[None, :, :]) ** 2).sum(-1))
+            assert np.array_equal(bp.nearest(e, q), d.argmin(1))
+            for k in range(4):
+                assert np.array_equal(bp.within(e, q[k], 3.0), np.nonzero(np.linalg.norm(q[k] - ve, axis=-1) <= 3.0)[0])
+    bp.close()
