@@ -118,6 +118,16 @@ NIRRT_HD bool point_in_rects(const Geom2 &g, const double *p) {      // inclusiv
         if (point_in_single_rect(p, g.rects[k], g.clearance)) return true;
     return false;
 }
+// one term of is_inside_obs: obstacle k (circles first, then rectangles), so lanes can split the OR
+NIRRT_HD bool point_in_obstacle(const Geom2 &g, int k, const double *p) {
+    if (k < g.n_circles) {
+        const double *c = g.circles[k];
+        const double rc = XADD(c[2], g.clearance);
+        const double dx = XSUB(p[0], c[0]), dy = XSUB(p[1], c[1]);
+        return XADD(XMUL(dx, dx), XMUL(dy, dy)) < XMUL(rc, rc);
+    }
+    return point_in_single_rect(p, g.rects[k - g.n_circles], g.clearance);
+}
 // Utils.is_inside_obs (rrt_utils_2d.py:36-48)
 NIRRT_HD bool point_inside_obs(const Geom2 &g, const double *p) { return point_in_circles(g, p) || point_in_rects(g, p); }
 // Utils.is_valid (rrt_utils_2d.py:62-79); range test == points_in_rectangles with clearance -c

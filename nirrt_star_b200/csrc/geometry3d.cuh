@@ -126,6 +126,16 @@ NIRRT_HD bool point_in_boxes(const Geom3 &g, const double *p) {  // inclusive
         if (point_in_single_box(p, g.boxes[k], g.clearance)) return true;
     return false;
 }
+// one term of is_inside_obs: obstacle k (balls first, then boxes), so lanes can split the OR
+NIRRT_HD bool point_in_obstacle(const Geom3 &g, int k, const double *p) {
+    if (k < g.n_balls) {
+        const double *b = g.balls[k];
+        const double rc = XADD(b[3], g.clearance);
+        const double dx = XSUB(p[0], b[0]), dy = XSUB(p[1], b[1]), dz = XSUB(p[2], b[2]);
+        return XADD(XADD(XMUL(dx, dx), XMUL(dy, dy)), XMUL(dz, dz)) < XMUL(rc, rc);
+    }
+    return point_in_single_box(p, g.boxes[k - g.n_balls], g.clearance);
+}
 // Utils.is_inside_obs (rrt_utils_3d.py:39-51)
 NIRRT_HD bool point_inside_obs(const Geom3 &g, const double *p) { return point_in_balls(g, p) || point_in_boxes(g, p); }
 // Utils.is_valid (rrt_utils_3d.py:68-86); range test == points_in_boxes with clearance -c

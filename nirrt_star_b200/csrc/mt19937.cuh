@@ -45,6 +45,19 @@ __device__ __forceinline__ void mt_prepare_next(MtState *s, int margin) {
 }
 
 // Single-thread word stream over an MtState (registers hold pos/cur; call flush() when done).
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+// mt19937_next_double from two consecutive raw state words: (a >> 5, b >> 6) -> 53-bit fraction
+__device__ __forceinline__ double mt_double(uint32_t raw0, uint32_t raw1) {
+    const int a = (int)(mt_temper(raw0) >> 5), b = (int)(mt_temper(raw1) >> 6);
+    return __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+}
+
 constexpr int kMtCache = 64;   // words of the current block staged in shared memory ahead of the sampling thread
 
 // Called by ALL threads: copies the next kMtCache words of the stream's current block into `cache`
@@ -79,14 +92,12 @@ struct MtStream {
     }
     __device__ __forceinline__ uint32_t next() {
         if (pos == 624) refill();
-        uint32_t y = (cache && pos - lo < kMtCache) ? cache[pos - lo] : k[pos];
+        const uint32_t y = (cache && pos - lo < kMtCache) ? cache[pos - lo] : k[pos];
         pos++;
-        y ^= (y >> 11);
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= (y >> 18);
-        return y;
+        return mt_temper(y);
     }
+    // words already consumed elsewhere from the staged cache (same block, pos + n <= 624)
+    __device__ __forceinline__ void skip(int n) { pos += n; }
     // mt19937_next_double: (a >> 5, b >> 6) -> 53-bit fraction
     __device__ __forceinline__ double next_double() {
         int a = (int)(next() >> 5), b = (int)(next() >> 6);

@@ -124,7 +124,7 @@ struct View {
     float *fx, *fy, *fz;   // f32 mirror of the coordinates (scan layout, 4 B per coordinate); null = not in use
     unsigned short *ux, *uy, *uz;   // u16 fixed-point mirror (scan layout, 2 B per coordinate); null = not in use
     Node *nodes;
-    int4 *hints;     // [E][stride] ancestor hints of the cost walks (see walk_to_root)
+    struct Hint *hints;  // [E][stride] ancestor hints of the cost walks (see walk_to_root)
     struct Link *links;  // [E][stride] {edge length to the parent, parent}: what a cost walk reads
     Geom3 *geom;
     Geom2 *geom2;    // 2D worlds (dim == 2)
@@ -232,10 +232,14 @@ struct __align__(16) Link {
 #ifdef NIRRT_PHASE_TIMING
 __device__ unsigned long long g_walk_stats[4];
 #endif
+constexpr int kHintHops = 8;
+struct __align__(32) Hint {     // one 32-byte sector
+    int a[kHintHops];           // the vertices that were v's ancestors 1..8 hops up when the record was last written
+};
 struct TreeRef {
     Node *nodes;
     Link *links;
-    int4 *hints;
+    Hint *hints;
     int cap;
 };
 __device__ __forceinline__ TreeRef tree_of(const View &v, int e) {
@@ -244,8 +248,30 @@ __device__ __forceinline__ TreeRef tree_of(const View &v, int e) {
     t.hints = v.hints + (size_t)e * v.stride; t.cap = v.cap;
     return t;
 }
-__device__ __forceinline__ int4 load_hint(const int4 *p) { return __ldcg(p); }
-__device__ __forceinline__ void store_hint(int4 *p, int a1, const int4 &up) { __stcg(p, make_int4(a1, up.x, up.y, up.z)); }
+__device__ __forceinline__ Hint load_hint(const Hint *p) {
+    const int4 lo = __ldcg(reinterpret_cast<const int4 *>(p)), hi = __ldcg(reinterpret_cast<const int4 *>(p) + 1);
+    Hint h;
+    h.a[0] = lo.x; h.a[1] = lo.y; h.a[2] = lo.z; h.a[3] = lo.w; h.a[4] = hi.x; h.a[5] = hi.y; h.a[6] = hi.z; h.a[7] = hi.w;
+    return h;
+}
+__device__ __forceinline__ void store_hint_raw(Hint *p, const Hint &h) {
+    __stcg(reinterpret_cast<int4 *>(p), make_int4(h.a[0], h.a[1], h.a[2], h.a[3]));
+    __stcg(reinterpret_cast<int4 *>(p) + 1, make_int4(h.a[4], h.a[5], h.a[6], h.a[7]));
+}
+// hints of a vertex whose parent is a1 and whose parent's hints are `up`
+__device__ __forceinline__ void store_hint(Hint *p, int a1, const Hint &up) {
+    Hint h;
+    h.a[0] = a1;
+#pragma unroll
+    for (int q = 1; q < kHintHops; q++) h.a[q] = up.a[q - 1];
+    store_hint_raw(p, h);
+}
+__device__ __forceinline__ Hint zero_hint() {
+    Hint h;
+#pragma unroll
+    for (int q = 0; q < kHintHops; q++) h.a[q] = 0;
+    return h;
+}
 __device__ __forceinline__ Link load_link(const Link *p) {
     const int4 r = __ldcg(reinterpret_cast<const int4 *>(p));
     Link l;
@@ -263,36 +289,38 @@ template <typename F>
 __device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop) {
     if (idx == 0) return;
     Link cur = load_link(t.links + idx);
-    int4 h = load_hint(t.hints + idx);
+    Hint h = load_hint(t.hints + idx);
     int start = idx;
     for (;;) {
         const unsigned cap = (unsigned)t.cap;
-        const int a1 = (unsigned)h.x < cap ? h.x : 0, a2 = (unsigned)h.y < cap ? h.y : 0;
-        const int a3 = (unsigned)h.z < cap ? h.z : 0, a4 = (unsigned)h.w < cap ? h.w : 0;
-        const Link l1 = load_link(t.links + a1), l2 = load_link(t.links + a2);
-        const Link l3 = load_link(t.links + a3), l4 = load_link(t.links + a4);
-        const int4 hn = load_hint(t.hints + a4);
-        int j = 0;
+        int a[kHintHops];
+        Link l[kHintHops];
+#pragma unroll
+        for (int q = 0; q < kHintHops; q++) {
+            a[q] = (unsigned)h.a[q] < cap ? h.a[q] : 0;
+            l[q] = load_link(t.links + a[q]);
+        }
+        const Hint hn = load_hint(t.hints + a[kHintHops - 1]);
+        int j = 0;                       // verified hops of this group
         int p = cur.parent;
-        if (p == a1) {
-            hop(p, cur.elen, l1.pad); if (p == 0) return;
-            j = 1; p = l1.parent;
-            if (p == a2) {
-                hop(p, l1.elen, l2.pad); if (p == 0) return;
-                j = 2; p = l2.parent;
-                if (p == a3) {
-                    hop(p, l2.elen, l3.pad); if (p == 0) return;
-                    j = 3; p = l3.parent;
-                    if (p == a4) {
-                        hop(p, l3.elen, l4.pad); if (p == 0) return;
-                        cur = l4; start = a4; h = hn;
-#ifdef NIRRT_PHASE_TIMING
-                        atomicAdd(&g_walk_stats[0], 1ull);
-#endif
-                        continue;
-                    }
-                }
+        Link cj = cur;                   // link of the last verified vertex
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < kHintHops; q++) {
+            if (ok) {
+                if (p == a[q]) {
+                    hop(p, cj.elen, l[q].pad);
+                    if (p == 0) return;
+                    cj = l[q]; p = cj.parent; j = q + 1;
+                } else ok = false;
             }
+        }
+        if (ok) {
+            cur = cj; start = a[kHintHops - 1]; h = hn;
+#ifdef NIRRT_PHASE_TIMING
+            atomicAdd(&g_walk_stats[0], 1ull);
+#endif
+            continue;
         }
 #ifdef NIRRT_PHASE_TIMING
         atomicAdd(&g_walk_stats[1], 1ull);
@@ -300,11 +328,17 @@ __device__ __forceinline__ void walk_to_root(const TreeRef &t, int idx, F &&hop)
         // stale from hop j+1 on (an ancestor was re-parented since hints[start] was written): one ordinary
         // hop from the last verified vertex, and hints[start] is rewritten with the verified prefix followed
         // by the true parent and that parent's own hints
-        const Link cj = j == 0 ? cur : (j == 1 ? l1 : (j == 2 ? l2 : l3));
         const Link lp = load_link(t.links + p);
-        const int4 hp = load_hint(t.hints + p);
-        __stcg(t.hints + start, j == 0 ? make_int4(p, hp.x, hp.y, hp.z) : j == 1 ? make_int4(a1, p, hp.x, hp.y)
-                                : j == 2 ? make_int4(a1, a2, p, hp.x) : make_int4(a1, a2, a3, p));
+        const Hint hp = load_hint(t.hints + p);
+        Hint r;
+#pragma unroll
+        for (int q = 0; q < kHintHops; q++) {
+            int val = q < j ? a[q] : p;
+#pragma unroll
+            for (int k = 0; k < kHintHops - 1; k++) if (q - j - 1 == k) val = hp.a[k];
+            r.a[q] = val;
+        }
+        store_hint_raw(t.hints + start, r);
         hop(p, cj.elen, lp.pad);
         if (p == 0) return;
         cur = lp; start = p; h = hp;
@@ -516,6 +550,43 @@ __device__ void sample_informed(const Geom2 &g, const EnvCtl *c, MtStream &, MtS
     }
 }
 
+// SampleFree (rrt_base_{2,3}d.py:46-58) evaluated speculatively by the whole CTA: attempt a consumes the words
+// [2*D*a, 2*D*(a+1)) of the staged stream, one warp per attempt, the lanes of a warp split the OR over
+// the obstacles; the first free attempt wins -- exactly the point and the stream position the sequential
+// rejection loop arrives at.  words_out = 0: undecided inside the staged words (the caller's serial loop
+// takes over).  Nothing is committed here; the sampling thread skips the words if the driver samples.
+template <int D, typename G>
+__device__ __forceinline__ void spec_sample_free(const G &g, const MtState *st, const uint32_t *cache, double *s_out, int *words_out) {
+    __shared__ int s_win;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    constexpr int W = 2 * D;
+    const int avail = min(kMtCache, 624 - st->pos);
+    const int max_att = avail / W;
+    if (tid == 0) { s_win = INT_MAX; *words_out = 0; }
+    __syncthreads();
+    double lo[3] = {0.0, 0.0, 0.0}, hi[3] = {0.0, 0.0, 0.0};
+    for (int d = 0; d < D; d++) { lo[d] = XADD(g.range[2 * d], g.clearance); hi[d] = XSUB(g.range[2 * d + 1], g.clearance); }
+    const int m = n_obstacles(g);
+    for (int a0 = 0; a0 < max_att; a0 += nw) {
+        const int a = a0 + warp;
+        double p[3] = {0.0, 0.0, 0.0};
+        if (a < max_att) {
+            for (int d = 0; d < D; d++)
+                p[d] = XADD(lo[d], XMUL(XSUB(hi[d], lo[d]), mt_double(cache[a * W + 2 * d], cache[a * W + 2 * d + 1])));
+            bool hit = false;
+            for (int k = lane; k < m; k += 32) hit = hit || point_in_obstacle(g, k, p);
+            if (!__any_sync(0xffffffffu, hit) && lane == 0) atomicMin(&s_win, a);
+        }
+        __syncthreads();
+        const int win = s_win;
+        if (win != INT_MAX) {
+            if (a == win && lane == 0) { s_out[0] = p[0]; s_out[1] = p[1]; s_out[2] = p[2]; *words_out = (win + 1) * W; }
+            break;
+        }
+    }
+    __syncthreads();
+}
+
 // Called by all 128 threads of the env's CTA: from k_top (first iteration of a run) and from the tail
 // of k_expand (every following iteration -- one launch and one dependent round trip less per iteration).
 template <int D>
@@ -549,6 +620,11 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
         block_lexmin(bs, bk, sm_s, sm_i);
         if (n_sol > 0) c_best = bs;
     }
+    // RRT* (and IRRT* before its first solution) draw nothing before SampleFree: evaluate it with all threads
+    __shared__ double s_spec[3];
+    __shared__ int s_spec_words;
+    const bool spec_ok = !fam_cloud(v.variant) && !(fam_informed(v.variant) && c_best < XINF);
+    if (spec_ok) spec_sample_free<D>(g, v.mt + e, s_mt, s_spec, &s_spec_words);
     if (threadIdx.x != 0) return;
 
     const bool fresh = !(v.variant == 2 && c->resumed);
@@ -589,6 +665,7 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
     }
     if (!done) {
         if (fam_informed(v.variant) && c_best < XINF) sample_informed(g, c, rng, py, c_best, out);
+        else if (spec_ok && s_spec_words > 0) { out[0] = s_spec[0]; out[1] = s_spec[1]; out[2] = s_spec[2]; rng.skip(s_spec_words); }
         else sample_free(g, rng, py, out);
     }
     rng.flush();
@@ -713,9 +790,9 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
     if (!go) return;
     const int lane = threadIdx.x & 31;
     Node *nodes = v.nodes + (size_t)e * v.stride;
-    int4 *hints = v.hints + (size_t)e * v.stride;
+    Hint *hints = v.hints + (size_t)e * v.stride;
     double bs = XINF; int bi = INT_MAX;
-    Node nn; int4 hn = make_int4(0, 0, 0, 0);    // record + hints of this lane's best candidate
+    Node nn; Hint hn = zero_hint();              // record + hints of this lane's best candidate
     nn.x = nn.y = nn.z = 0.0; nn.parent = 0;
     bool have_rec = false;
     if (v.fx || v.ux) {
@@ -729,7 +806,7 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
             for (int k = lane; k < cnt; k += 32) {
                 const int i = cand[k];
                 const Node nd = load_node(nodes + i);
-                const int4 hh = load_hint(hints + i);
+                const Hint hh = load_hint(hints + i);
                 const double dx = XSUB(qx, nd.x), dy = XSUB(qy, nd.y), dz = D == 3 ? XSUB(qz, nd.z) : 0.0;
                 const double val = D == 3 ? XSQRT(sq3_rows(dx, dy, dz)) : np_hypot(dx, dy);
                 if (val < bs || (val == bs && i < bi)) { bs = val; bi = i; nn = nd; hn = hh; }
@@ -750,8 +827,8 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
         const int src = __ffs(__ballot_sync(0xffffffffu, my_bi == nearest)) - 1;
         nn.x = __shfl_sync(0xffffffffu, nn.x, src); nn.y = __shfl_sync(0xffffffffu, nn.y, src);
         nn.z = __shfl_sync(0xffffffffu, nn.z, src);
-        hn.x = __shfl_sync(0xffffffffu, hn.x, src); hn.y = __shfl_sync(0xffffffffu, hn.y, src);
-        hn.z = __shfl_sync(0xffffffffu, hn.z, src); hn.w = __shfl_sync(0xffffffffu, hn.w, src);
+#pragma unroll
+        for (int q = 0; q < kHintHops; q++) hn.a[q] = __shfl_sync(0xffffffffu, hn.a[q], src);
     } else {
         nn = load_node(nodes + nearest);
         hn = load_hint(hints + nearest);
@@ -1155,7 +1232,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     __shared__ unsigned long long s_anc[kNearSmem];     // Near members on near_k's root path (see below)
     __shared__ unsigned s_rew[kNearSmem / 32];
     __shared__ double s_curr[3];                        // curr_node_new_cost, cost(new) via the steer parent, cost(new) via ChooseParent's winner
-    __shared__ int4 s_hnew;                             // ancestor hints of x_new after ChooseParent
+    __shared__ Hint s_hnew;                             // ancestor hints of x_new after ChooseParent
     __shared__ double sm_s[4];
     __shared__ int sm_i[4];
     __shared__ int s_m;
@@ -1322,13 +1399,15 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             const bool new_moved = reparent && !c->inserted;   // an existing vertex (duplicate guard) changed its parent
             if (tid == 0) {
                 c->stamp++;
-                int4 hnew;
+                Hint hnew;
                 if (reparent) {
                     const int q = s_near[bk];
                     set_parent(t, new_idx, q, s_first[bk]);    // s_first[bk] = Line(near_bk, x_new) == the new edge
-                    const int4 hq = load_hint(t.hints + q);
-                    hnew = make_int4(q, hq.x, hq.y, hq.z);
-                    __stcg(t.hints + new_idx, hnew);
+                    const Hint hq = load_hint(t.hints + q);
+                    hnew.a[0] = q;
+#pragma unroll
+                    for (int w = 1; w < kHintHops; w++) hnew.a[w] = hq.a[w - 1];
+                    store_hint_raw(t.hints + new_idx, hnew);
                     c->tree_changed = 1;
                 } else hnew = load_hint(t.hints + new_idx);
                 s_hnew = hnew;
@@ -1362,7 +1441,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 }
             }
             const int any_dep = __syncthreads_or(dep);
-            const int4 hnew = s_hnew;
+            const Hint hnew = s_hnew;
             if (!any_dep) {
                 for (int k = tid; k < m; k += blockDim.x)
                     if ((s_rew[k >> 5] >> (k & 31)) & 1u) {
@@ -1574,7 +1653,7 @@ __global__ void k_set_problems(View v, ProblemUpload u) {
     mirror_store(v, c, o, c->start[0], c->start[1], c->start[2]);
     Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = c->start[2]; nd.parent = 0;
     v.nodes[o] = nd;
-    v.hints[o] = make_int4(0, 0, 0, 0);
+    v.hints[o] = zero_hint();
     { Link l; l.elen = 0.0; l.parent = 0; l.pad = 0; v.links[o] = l; }
     c->n = 1;
     c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
@@ -1622,7 +1701,7 @@ __global__ void k_set_problems_2d(View v, ProblemUpload2 u) {
     mirror_store(v, c, o, c->start[0], c->start[1], 0.0);
     Node nd; nd.x = c->start[0]; nd.y = c->start[1]; nd.z = 0.0; nd.parent = 0;
     v.nodes[o] = nd;
-    v.hints[o] = make_int4(0, 0, 0, 0);
+    v.hints[o] = zero_hint();
     { Link l; l.elen = 0.0; l.parent = 0; l.pad = 0; v.links[o] = l; }
     c->n = 1;
     c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
@@ -1868,7 +1947,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         }
     }
     DALLOC(v.nodes, Node, EV);
-    DALLOC(v.hints, int4, EV);
+    DALLOC(v.hints, Hint, EV);
     DALLOC(v.links, Link, EV);
     if (v.dim == 3) { DALLOC(v.geom, Geom3, v.E); }
     else {
@@ -2150,20 +2229,21 @@ __global__ void k_build_links(View v, int env_begin, const int *n) {
     const int k = blockIdx.y, env = env_begin + k;
     const int nk = n[k];
     const Node *nodes = v.nodes + (size_t)env * v.stride;
-    int4 *hints = v.hints + (size_t)env * v.stride;
+    Hint *hints = v.hints + (size_t)env * v.stride;
     Link *links = v.links + (size_t)env * v.stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x) {
-        int a[4], cur = i;
-        for (int q = 0; q < 4; q++) {
+        Hint hh;
+        int cur = i;
+        for (int q = 0; q < kHintHops; q++) {
             const long long par = nodes[cur].parent;
             cur = (par >= 0 && par < nk) ? (int)par : 0;     // malformed parents only make a useless hint
-            a[q] = cur;
+            hh.a[q] = cur;
         }
-        hints[i] = make_int4(a[0], a[1], a[2], a[3]);
-        const Node me = nodes[i], pa = nodes[a[0]];
+        hints[i] = hh;
+        const Node me = nodes[i], pa = nodes[hh.a[0]];
         Link l;
         l.elen = i == 0 ? 0.0 : edge_len<D>(XSUB(me.x, pa.x), XSUB(me.y, pa.y), XSUB(me.z, pa.z));
-        l.parent = a[0]; l.pad = 0;
+        l.parent = hh.a[0]; l.pad = 0;
         links[i] = l;
     }
 }

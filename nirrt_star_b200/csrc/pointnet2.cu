@@ -973,9 +973,7 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
     int upC = kC[4];
     for (int f = 0; f < 4; f++) {
         const int lo = 3 - f;
-        const int N = h->n[lo], S = h->n[lo + 1];
-        const int C1 = lo == 0 ? 0 : kC[lo];
-        const int rows = B * N;
+        const int rows = B * h->n[lo];
         {
             StageTimer t(h, s, 5);
             if (split) PCUDA(cudaStreamWaitEvent(s, h->ev_knn[f], 0));
