@@ -2,20 +2,27 @@
 // C ABI over it (include/nirrt_b200.h).
 //
 // One "iteration" advances every running planning problem (env) by one loop body of the reference
-// (rrt_star_3d.py:37-55 == irrt_star_3d.py:50-71) with five kernels:
+// (rrt_star_3d.py:37-55 == irrt_star_3d.py:50-71) with TWO kernels per group of problems:
 //
-//   k_top      1 CTA / env   driver phase machine, c_best refresh (IRRT*), MT19937 sampling
-//   k_nearest  (chunks x E)  HBM-bound argmin scan over the env's SoA vertex coordinates
-//   k_steer    1 warp / env  argmin finish, Steer, steer-edge collision, vertex insert, Near radius
-//   k_near     (chunks x E)  HBM-bound radius scan, sparse append of candidate indices
-//   k_expand   1 CTA / env   sort candidates, edge collision filter, cost walks, ChooseParent,
-//                            sequential Rewire, goal bookkeeping, per-iteration record
+//   k_nearest_m  (chunks x E)  the one HBM-bound pass: Nearest filter over the 2-byte fixed-point mirror
+//                              of the coordinates + speculative collection of the Near ball around x_rand
+//   k_expand     1 CTA / env   steer_body (exact Nearest finish, Steer, steer-edge collision, insert),
+//                              exact Near test + sort + edge collision filter, cost walks, ChooseParent,
+//                              Rewire, goal bookkeeping / records, top_body (driver phase machine, c_best
+//                              refresh for IRRT*, MT19937 sampling of the NEXT iteration)
+//
+// (k_top opens a run; k_steer / k_nearest / k_near are the unfused f64 kernels behind NIRRT_SCAN=f64, the
+// stand-alone query entry points and the per-kernel attribution of nirrt_batch_run_profiled_sync.)
 //
 // HBM layout per env (flat, capacity-strided):
-//   vx[], vy[], vz[]   f64 SoA      -- what the two scans stream (24 B / vertex / scan)
-//   nodes[]            {x,y,z,parent} 32 B records -- one sector per hop of a cost walk
+//   vx[], vy[], vz[]   f64 SoA       -- source of truth of the coordinates (exact re-checks)
+//   ux[], uy[], uz[]   u16 SoA       -- fixed-point mirror, what the scan streams (6 B / vertex / iteration)
+//   nodes[]            {x,y,z,parent} 32 B records -- coordinates of candidates, what read_trees returns
+//   links[]            {math.hypot(v - parent), parent, Near stamp} 16 B -- what a cost walk reads
+//   hints[]            8 ancestor indices, 32 B -- eight hops of a cost walk per round trip
 // All index-deciding arithmetic is IEEE-exact float64 in the reference's operand order
-// (exact_math.cuh, geometry3d.cuh); there is no CPU fallback anywhere in this file.
+// (exact_math.cuh, geometry3d.cuh); the mirror, the hints and the stamps only select what is evaluated.
+// There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -219,9 +226,9 @@ __device__ __forceinline__ double hypot_band_sq(double h) {
 //   * links[v] = {math.hypot(v - parent(v)), parent(v)}: an edge length depends only on the two end
 //     points, which never move, so it is evaluated once when the edge is created (insert,
 //     ChooseParent, Rewire -- the same value cost() would recompute) and the walk only adds.
-//   * hints[v] = {a1, a2, a3, a4} names the vertices that were v's ancestors 1..4 hops up when the
-//     record was last written.  A walk loads the links of all four and hints[a4] at once and verifies
-//     the chain against the authoritative parent fields as the data arrives: four hops per round
+//   * hints[v] = {a1 .. a8} names the vertices that were v's ancestors 1..8 hops up when the
+//     record was last written.  A walk loads the links of all eight and hints[a8] at once and verifies
+//     the chain against the authoritative parent fields as the data arrives: eight hops per round
 //     trip.  A stale hint (an ancestor was re-parented since) costs one ordinary hop and is repaired
 //     on the spot.  Hints never decide anything.
 struct __align__(16) Link {
@@ -1011,10 +1018,10 @@ __device__ __forceinline__ void mirror_scan(const View &v, int e, int beg, int e
         if (kU16) {
             const unsigned short *X = v.ux + (size_t)e * v.stride, *Y = v.uy + (size_t)e * v.stride;
             const unsigned short *Z = D == 3 ? v.uz + (size_t)e * v.stride : nullptr;
-            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(X + i));
-            const uint4 y = __ldg(reinterpret_cast<const uint4 *>(Y + i));
+            const uint4 x = __ldcs(reinterpret_cast<const uint4 *>(X + i));
+            const uint4 y = __ldcs(reinterpret_cast<const uint4 *>(Y + i));
             uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            if (D == 3) z = __ldg(reinterpret_cast<const uint4 *>(Z + i));
+            if (D == 3) z = __ldcs(reinterpret_cast<const uint4 *>(Z + i));
 #define MIRROR_U16(wx, wy, wz, j)                                                                   \
             {                                                                                       \
                 const float dx0 = qx - __uint_as_float(__byte_perm(wx, 0x4B00u, 0x5410));           \
@@ -1036,10 +1043,10 @@ __device__ __forceinline__ void mirror_scan(const View &v, int e, int beg, int e
         } else {
             const float *X = v.fx + (size_t)e * v.stride, *Y = v.fy + (size_t)e * v.stride;
             const float *Z = D == 3 ? v.fz + (size_t)e * v.stride : nullptr;
-            const float4 x = __ldg(reinterpret_cast<const float4 *>(X + i));
-            const float4 y = __ldg(reinterpret_cast<const float4 *>(Y + i));
+            const float4 x = __ldcs(reinterpret_cast<const float4 *>(X + i));
+            const float4 y = __ldcs(reinterpret_cast<const float4 *>(Y + i));
             float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (D == 3) z = __ldg(reinterpret_cast<const float4 *>(Z + i));
+            if (D == 3) z = __ldcs(reinterpret_cast<const float4 *>(Z + i));
 #define MIRROR_F32(xx, yy, zz, j)                                                                   \
             {                                                                                       \
                 const float dx = qx - (xx), dy = qy - (yy);                                         \
@@ -2223,7 +2230,7 @@ __global__ void k_scatter_trees(View v, int env_begin, const int *n, const doubl
         if (i == 0) { v.ctl[env].n = nk; v.ctl[env].tree_changed = 1; }
     }
 }
-// walk records of freshly loaded trees: edge length to the parent and the true ancestors 1..4 hops up
+// walk records of freshly loaded trees: edge length to the parent and the true ancestors 1..8 hops up
 template <int D>
 __global__ void k_build_links(View v, int env_begin, const int *n) {
     const int k = blockIdx.y, env = env_begin + k;
