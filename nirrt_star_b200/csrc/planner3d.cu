@@ -1814,10 +1814,17 @@ static void launch_scan(const View &v, int which, int count, cudaStream_t s, boo
     launch_view(k, grid, 256, s, v, pdl);
 }
 
-constexpr int kMaxGroups = 16;
+constexpr int kMaxGroups = 32;
+constexpr int kGraphItersDefault = 16;   // steady-state iterations per CUDA graph replay (see ensure_graph)
 struct nirrt_batch {
     View v;
     bool pdl;        // iteration kernels use programmatic dependent launch (NIRRT_PDL=0 disables)
+    bool use_graph;  // steady-state iterations are replayed from a CUDA graph (NIRRT_GRAPH=0 disables)
+    cudaGraphExec_t gexec;
+    View gview;      // the View the graph was captured with
+    int64_t graph_launches;
+    int graph_iters; // iterations per graph replay
+    cudaStream_t cs; // capture origin
     int device;
     size_t stride_bytes;
     std::vector<void *> allocs;
@@ -1878,6 +1885,7 @@ static int pick_chunks(int E) {
     // aim for ~4 resident 256-thread CTAs of one group's scan on each of the 148 SMs (the other groups'
     // kernels fill the rest; measured on 512 x 100k: 10 chunks at 64 problems per group beat 5 and 20)
     int c = (148 * 4 + E - 1) / E;
+    if (E >= 32 && c > 10) c = 10;        // 16 groups of 32 problems: 10 chunks (72.3 us / step) beat 19 (76.9)
     if (c < 1) c = 1;
     if (c > 64) c = 64;
     return c;
@@ -1893,6 +1901,8 @@ extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
         if (b->ev_join[g]) cudaEventDestroy(b->ev_join[g]);
     }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->gexec) cudaGraphExecDestroy(b->gexec);
+    if (b->cs) cudaStreamDestroy(b->cs);
     for (int i = 0; i < 2; i++) {
         if (b->xs[i]) cudaStreamDestroy(b->xs[i]);
         if (b->xe[i]) cudaEventDestroy(b->xe[i]);
@@ -1926,8 +1936,13 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     {
         const char *pdl = getenv("NIRRT_PDL");
         b->pdl = !(pdl && atoi(pdl) == 0);
+        const char *gr = getenv("NIRRT_GRAPH");
+        b->graph_iters = gr ? atoi(gr) : kGraphItersDefault;     // NIRRT_GRAPH=<iterations per graph>, 0 disables
+        if (b->graph_iters > 256) b->graph_iters = 256;
+        b->use_graph = b->graph_iters > 0;
+        b->gexec = nullptr; b->graph_launches = 0; b->cs = nullptr;
         const char *g = getenv("NIRRT_GROUPS");
-        b->groups = g ? atoi(g) : (d->n_envs >= 512 ? 8 : (d->n_envs >= 256 ? 4 : (d->n_envs >= 64 ? 2 : 1)));
+        b->groups = g ? atoi(g) : (d->n_envs >= 512 ? 16 : (d->n_envs >= 256 ? 8 : (d->n_envs >= 128 ? 4 : (d->n_envs >= 64 ? 2 : 1))));
         if (b->groups < 1) b->groups = 1;
         if (b->groups > kMaxGroups) b->groups = kMaxGroups;
         if (b->groups > d->n_envs) b->groups = d->n_envs;
@@ -1978,6 +1993,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_join[g], cudaEventDisableTiming));
         }
         CUDA_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&b->cs, cudaStreamNonBlocking));
     }
     *out = b;
     return NIRRT_OK;
@@ -2376,27 +2392,71 @@ static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count,
     return NIRRT_OK;
 }
 
+// `n` iterations of every group: fork from `s` to the group streams, launch, join back into `s`
+static int run_groups(nirrt_batch *b, cudaStream_t s, int n, bool first, bool last) {
+    const View &v = b->v;
+    if (n <= 0) return NIRRT_OK;
+    if (b->groups == 1) {
+        for (int it = 0; it < n; it++) launch_iteration(b, s, 0, v.E, first && it == 0, last && it == n - 1);
+        return NIRRT_OK;
+    }
+    const int G = b->groups;
+    CUDA_TRY(cudaEventRecord(b->ev_fork, s));
+    for (int g = 0; g < G; g++) CUDA_TRY(cudaStreamWaitEvent(b->gs[g], b->ev_fork, 0));
+    for (int it = 0; it < n; it++)
+        for (int g = 0; g < G; g++) {
+            const int e0 = (int)((long long)v.E * g / G), e1 = (int)((long long)v.E * (g + 1) / G);
+            if (e1 > e0) launch_iteration(b, b->gs[g], e0, e1 - e0, first && it == 0, last && it == n - 1);
+        }
+    for (int g = 0; g < G; g++) {
+        CUDA_TRY(cudaEventRecord(b->ev_join[g], b->gs[g]));
+        CUDA_TRY(cudaStreamWaitEvent(s, b->ev_join[g], 0));
+    }
+    return NIRRT_OK;
+}
+
+// CUDA graph of b->graph_iters steady-state iterations of all groups (kernel arguments are the View by value,
+// so the graph is rebuilt whenever the View changed): one graph launch replaces 2 x groups x b->graph_iters
+// kernel launches, which keeps the host far ahead of the device even with many small groups.
+static bool ensure_graph(nirrt_batch *b) {
+    if (!b->use_graph || b->groups < 2) return false;
+    if (b->gexec && memcmp(&b->gview, &b->v, sizeof(View)) == 0) return true;
+    if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
+    const int64_t launches0 = b->launches;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(b->cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        const int rc = run_groups(b, b->cs, b->graph_iters, false, false);
+        const cudaError_t e = cudaStreamEndCapture(b->cs, &graph);
+        ok = rc == NIRRT_OK && e == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&b->gexec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    b->graph_launches = b->launches - launches0;     // kernels per replay
+    b->launches = launches0;
+    if (!ok) {              // capture is an optimisation only: fall back to plain launches for this batch
+        cudaGetLastError();
+        b->gexec = nullptr; b->use_graph = false;
+        return false;
+    }
+    memcpy(&b->gview, &b->v, sizeof(View));     // byte copy: the comparison above is a memcmp
+    return true;
+}
+
 extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     if (!b || iters < 0) return fail(NIRRT_ERR_INVALID, "nirrt_batch_run: bad argument");
     View &v = b->v;
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
-    if (b->groups == 1) {
-        for (int it = 0; it < iters; it++) launch_iteration(b, s, 0, v.E, it == 0, it == iters - 1);
+    if (iters >= b->graph_iters + 2 && ensure_graph(b)) {
+        TRY(run_groups(b, s, 1, true, false));
+        const int mid = iters - 2;
+        for (int r = 0; r < mid / b->graph_iters; r++) { CUDA_TRY(cudaGraphLaunch(b->gexec, s)); b->launches += b->graph_launches; }
+        TRY(run_groups(b, s, mid % b->graph_iters, false, false));
+        TRY(run_groups(b, s, 1, false, true));
     } else {
-        const int G = b->groups;
-        CUDA_TRY(cudaEventRecord(b->ev_fork, s));
-        for (int g = 0; g < G; g++) CUDA_TRY(cudaStreamWaitEvent(b->gs[g], b->ev_fork, 0));
-        for (int it = 0; it < iters; it++)
-            for (int g = 0; g < G; g++) {
-                const int e0 = (int)((long long)v.E * g / G), e1 = (int)((long long)v.E * (g + 1) / G);
-                if (e1 > e0) launch_iteration(b, b->gs[g], e0, e1 - e0, it == 0, it == iters - 1);
-            }
-        for (int g = 0; g < G; g++) {
-            CUDA_TRY(cudaEventRecord(b->ev_join[g], b->gs[g]));
-            CUDA_TRY(cudaStreamWaitEvent(s, b->ev_join[g], 0));
-        }
+        TRY(run_groups(b, s, iters, true, true));
     }
     CHECK_LAUNCH();
     return NIRRT_OK;

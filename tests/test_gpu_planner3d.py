@@ -229,6 +229,7 @@ def test_scan_layouts_and_pipelines_agree(B, variant):
     base = _run_batch(B, problems, seeds, iters, variant)
     assert base[3] == 6                                           # default layout: 2 B per coordinate
     for env, bpv in (({"NIRRT_SCAN": "f32"}, 12), ({"NIRRT_SCAN": "f64"}, 24), ({"NIRRT_GROUPS": "5"}, 6),
+                     ({"NIRRT_GROUPS": "5", "NIRRT_GRAPH": "0"}, 6), ({"NIRRT_SCAN": "f64", "NIRRT_GROUPS": "3"}, 24),
                      ({"NIRRT_GROUPS": "1", "NIRRT_PDL": "0"}, 6), ({"NIRRT_CHUNKS": "3"}, 6)):
         v, p, n, got_bpv = _run_batch(B, problems, seeds, iters, variant, env)
         assert got_bpv == bpv, env
