@@ -123,3 +123,44 @@ def test_batch_of_problems_equals_singles(B):
         assert n1[0] == n[e] and np.array_equal(p1[0], p[e]) and np.array_equal(v1[0], v[e])
         one.close()
     bp.close()
+
+
+def test_config1_shape_64_problems_5000_iterations(B):
+    """BASELINE configs[1]: irrt_star 2D random_2d, 64 problems batched, iter_max = 5000 (planning_random with
+    iter_after_initial = 500).  The batch (2 pipelined groups, CUDA-graph replay, u16 mirror scans) must
+    equal one-problem batches bit for bit, and the trees keep their invariants."""
+    E, iter_max, iter_after = 64, 5000, 500
+    problems = [make_problem_2d(100 + i) for i in range(E)]
+    seeds = [700 + i for i in range(E)]
+    bp = B.BatchPlanner2D(problems, iter_max, seeds=seeds, record_capacity=iter_max + iter_after + 8)
+    bp.begin(B.VARIANT_IRRT_STAR, B.MODE_PLANNING_RANDOM, iter_max, iter_after)
+    bp.run_to_completion(chunk=512)
+    lists = bp.path_len_lists()
+    v, p, n = bp.read_trees()
+    solved = 0
+    for e in range(E):
+        ne = int(n[e]); pe = p[e, :ne]; ve = v[e, :ne]
+        assert pe[0] == 0 and pe.min() >= 0 and pe.max() < ne
+        anc = pe.copy()
+        for _ in range(int(np.ceil(np.log2(max(ne, 2)))) + 1):
+            anc = anc[anc]
+        assert not anc.any()
+        seg = np.hypot(*(ve - ve[pe]).T)
+        assert seg[1:].max() <= 10.0 + 1e-9
+        got = np.array(lists[e])
+        assert len(got) <= iter_max + iter_after + 1
+        f = np.isfinite(got)
+        if f.any():
+            solved += 1
+            assert np.all(np.diff(got[f]) <= 1e-9)               # the best cost never increases
+            assert not f[:int(np.argmax(f))].any() and f[int(np.argmax(f)):].all()   # inf ... inf, then finite to the end
+    assert solved >= E // 2
+    for e in (0, 21, 63):
+        one = B.BatchPlanner2D([problems[e]], iter_max, seeds=[seeds[e]], record_capacity=iter_max + iter_after + 8)
+        one.begin(B.VARIANT_IRRT_STAR, B.MODE_PLANNING_RANDOM, iter_max, iter_after)
+        one.run_to_completion(chunk=512)
+        v1, p1, n1 = one.read_trees()
+        assert n1[0] == n[e] and np.array_equal(p1[0], p[e]) and np.array_equal(v1[0], v[e])
+        assert np.array_equal(np.array(one.path_len_lists()[0]), np.array(lists[e]))
+        one.close()
+    bp.close()
