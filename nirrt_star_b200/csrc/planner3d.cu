@@ -83,11 +83,31 @@ struct __align__(16) ScanHdr {
     float qx, qy, qz;   // the query in the mirror's coordinates
     float thr;          // Near: squared-distance threshold
     float band;         // Nearest: 2 * margin
-    int pad;
+    int base;           // Nearest: value of the iteration copy's (never reset) spec_cnt when the sample was drawn;
+                        // list position of a speculative candidate = atomicAdd(spec_cnt) - base
+};
+
+// What one iteration hands from Steer to the expansion (and to the trace readers).  Two copies per problem:
+// in the pipelined RRT* driver the next iteration's scan + Steer + sample run while this iteration's
+// expansion still reads its copy (View::par selects the copy, 0 everywhere else).
+struct __align__(16) IterScratch {
+    ScanHdr hdr1;       // Near scan header (query x_new) for the fallback scan
+    int go, skip, nearest, new_idx, inserted, near_cnt;
+    int spec_cnt;     // speculative Near candidates appended by the Nearest scans so far (never reset)
+    int spec_base;    // its value when this iteration's list started: the list holds spec_cnt - spec_base entries
+    int fb_cnt;       // matches of the fallback Near scan (k_expand), its own counter: spec_cnt is read by the next sample
+    int use_spec;     // steer: x_new == x_rand (up to rounding), the speculative list is the Near superset
+    int need_scan;    // steer: x_new != x_rand, k_expand runs the Near scan itself before filtering
+    double x_new[3];
+    double r, T_near;
+    double cnew_default;  // cost(new) if ChooseParent keeps the steer parent: the walk from x_new, leaf -> root
+    float near_thr;   // mirror scan: a <= near_thr selects the Near candidates that get the exact f64 test
+    int pad1;
 };
 
 struct __align__(16) EnvCtl {
-    ScanHdr hdr[2];     // [0] Nearest (query x_rand), [1] Near (query x_new)
+    ScanHdr hdr0;       // Nearest scan header (query x_rand)
+    IterScratch s[2];
     // problem
     double start[3], goal[3];
     double step_len, search_radius;
@@ -98,17 +118,12 @@ struct __align__(16) EnvCtl {
     // driver
     int state, saved_state, p1_done, left, budget, n_rec, resumed;
     // iteration scratch
-    int go, skip, nearest, new_idx, inserted, cand_cnt, near_cnt;
-    int spec_cnt;     // speculative Near candidates collected by the Nearest scan (ball around x_rand)
-    int use_spec;     // k_steer: x_new == x_rand (up to rounding), the speculative list is the Near superset
-    int need_scan;    // k_steer: x_new != x_rand, k_expand runs the Near scan itself before filtering
-    double x_rand[3], x_new[3];
-    double r, T_near, curr_cost, c_best, c_update;
-    double cnew_default;  // cost(new) if ChooseParent keeps the steer parent: the walk from x_new, leaf -> root
+    int cand_cnt;
+    double x_rand[3];
+    double curr_cost, c_best, c_update;
     double margin;    // bound on |mirror distance - f64 distance| for vertices inside the world range, in the
                       // mirror's units (f32 mirror: world units; u16 mirror: grid cells)
     double qlo[3], qscale;  // u16 mirror: cell = rint((x - qlo[d]) * qscale), 65535 cells over the longest world edge
-    float near_thr;   // mirror scan: a <= near_thr selects the Near candidates that get the exact f64 test
     int fallbacks;    // Nearest scans whose in-band candidate list overflowed (k_steer re-scanned the env in f64)
     // goal bookkeeping
     int n_sol, n_goal, tree_changed, n_pc;
@@ -123,6 +138,8 @@ struct View {
     int env0;        // first problem of the group an iteration kernel works on (see nirrt_batch_run)
     int fuse_top;    // k_expand ends with the next iteration's k_top work (driver, c_best refresh, sampling)
     int fuse_steer;  // k_expand starts with k_steer's work (warp 0): one kernel for everything between two scans
+    int par;         // which IterScratch copy / cand2 half this launch works on (iteration parity when pipelined, else 0)
+    int pipe;        // 1: pipelined RRT* driver (k_front does Steer + accounting + next sample, k_expand only expands)
     int variant, mode, iter_max, iter_after;
     double stop_below; // phase 1 ends when the recorded value drops below this (+inf: planning_random; finite: planning_block_gap)
     int n_limit;     // > 0: problems whose tree reached n_limit vertices idle (benchmark pre-growth)
@@ -152,6 +169,9 @@ struct View {
     double *pathseg; // [E][path_cap]
     const double *near_table;
 };
+
+#define IT (c->s[v.par])     // this launch's IterScratch copy (every user names its EnvCtl pointer c and its View v)
+__device__ __forceinline__ int *cand2_of(const View &v, int e) { return v.cand2 + ((size_t)v.par * v.E + e) * v.near_cap; }
 
 // planner families: 0 RRT*, 1 IRRT*, 2 NIRRT* (informed + guidance cloud with updates),
 // 3 NRRT* (RRT* driver + a fixed guidance cloud, nrrt_star_png_3d.py:52-56)
@@ -423,7 +443,7 @@ __device__ int block_min_int(int v, int *sm_i) {
 
 __device__ __forceinline__ void push_record(const View &v, EnvCtl *c, int e, double val) {
     if (c->n_rec < v.rec_cap) v.records[(size_t)e * v.rec_cap + c->n_rec] = val;
-    else c->err |= ERR_RECORD_OVERFLOW;
+    else atomicOr(&c->err, ERR_RECORD_OVERFLOW);
     c->n_rec++;
 }
 
@@ -467,23 +487,27 @@ __device__ __forceinline__ ScanHdr load_hdr(const ScanHdr *h) {
     const int4 b = __ldcg(reinterpret_cast<const int4 *>(h) + 1);
     ScanHdr r;
     r.go = a.x; r.n = a.y; r.qx = __int_as_float(a.z); r.qy = __int_as_float(a.w);
-    r.qz = __int_as_float(b.x); r.thr = __int_as_float(b.y); r.band = __int_as_float(b.z); r.pad = b.w;
+    r.qz = __int_as_float(b.x); r.thr = __int_as_float(b.y); r.band = __int_as_float(b.z); r.base = b.w;
     return r;
 }
-template <bool kU16>
-__device__ __forceinline__ void store_hdr(ScanHdr *h, const EnvCtl *c, int go, int n, const double *q, float thr) {
+template <int kMirror>   // 2: u16 mirror, 1: f32 mirror, 0: none (f64 scans: only go / n matter)
+__device__ __forceinline__ void store_hdr(ScanHdr *h, const EnvCtl *c, int go, int n, const double *q, float thr, int base) {
     ScanHdr r;
     r.go = go; r.n = n;
-    r.qx = mirror_query<kU16>(c, q, 0); r.qy = mirror_query<kU16>(c, q, 1); r.qz = mirror_query<kU16>(c, q, 2);
-    r.thr = thr; r.band = __double2float_ru(2.0 * c->margin); r.pad = 0;
+    r.qx = r.qy = r.qz = 0.f;
+    if (kMirror) { r.qx = mirror_query<kMirror == 2>(c, q, 0); r.qy = mirror_query<kMirror == 2>(c, q, 1); r.qz = mirror_query<kMirror == 2>(c, q, 2); }
+    r.thr = thr; r.band = __double2float_ru(2.0 * c->margin); r.base = base;
     *h = r;
 }
-__device__ __forceinline__ void write_hdr(const View &v, EnvCtl *c, int which, int go, const double *q, float thr) {
-    if (v.ux) store_hdr<true>(&c->hdr[which], c, go, c->n, q, thr);
-    else if (v.fx) store_hdr<false>(&c->hdr[which], c, go, c->n, q, thr);
+__device__ __forceinline__ void write_hdr(const View &v, EnvCtl *c, int which, int go, const double *q, float thr, int base = 0) {
+    ScanHdr *h = which == 0 ? &c->hdr0 : &IT.hdr1;
+    if (v.ux) store_hdr<2>(h, c, go, c->n, q, thr, base);
+    else if (v.fx) store_hdr<1>(h, c, go, c->n, q, thr, base);
+    else store_hdr<0>(h, c, go, c->n, q, thr, base);
 }
 
-__device__ __forceinline__ void set_idle(EnvCtl *c) { c->go = 0; c->hdr[0].go = 0; c->hdr[1].go = 0; }
+// the go flag of the NEXT iteration lives in the Nearest header only; steer_body copies it into its iteration copy
+__device__ __forceinline__ void set_idle(EnvCtl *c) { c->hdr0.go = 0; }
 
 // ------------------------------------------------------------------------------------------------
 // k_top: driver phase machine + c_best refresh + sampling
@@ -663,7 +687,7 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
     bool done = false;
     if (fam_cloud(v.variant)) {
         if (rng.next_double() < v.pc_rate) {
-            if (c->n_pc <= 0) { c->err |= ERR_EMPTY_CLOUD; c->state = ST_DONE; set_idle(c); rng.flush(); return; }
+            if (c->n_pc <= 0) { atomicOr(&c->err, ERR_EMPTY_CLOUD); c->state = ST_DONE; set_idle(c); rng.flush(); return; }
             const long long k = rng.randint(c->n_pc);
             const double *p = v.pc + ((size_t)e * v.pc_cap + k) * 3;
             out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
@@ -679,8 +703,9 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
     if (D == 2) py.flush();
     c->x_rand[0] = out[0]; c->x_rand[1] = out[1]; c->x_rand[2] = out[2];
     c->cand_cnt = 0;     // the Nearest mirror scan appends its in-band candidates here
-    c->spec_cnt = 0;
-    c->go = 1;
+    // the iteration this sample belongs to works on copy par ^ pipe; its speculative list starts at the copy's
+    // current (never reset) counter value -- nothing of that copy is written here, its previous user may still run
+    const int spec_base = c->s[v.par ^ v.pipe].spec_cnt;
     // Speculative Near: whenever the tree already reaches within step_len of x_rand (always, once it is
     // dense) Steer returns x_new == x_rand up to rounding, so the ball around x_rand with the largest
     // radius the insertion can produce (the table is evaluated at n and n + 1) is a superset of Near(x_new):
@@ -690,7 +715,7 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
         double rs = XMUL(c->search_radius, fmax(v.near_table[n], v.near_table[n + 1]));
         if (c->step_len < rs) rs = c->step_len;
         const double rm = (v.ux ? (rs + kSpecSlack) * c->qscale : rs + kSpecSlack) + c->margin;
-        write_hdr(v, c, 0, 1, c->x_rand, __double2float_ru(rm * rm * 1.000001));
+        write_hdr(v, c, 0, 1, c->x_rand, __double2float_ru(rm * rm * 1.000001), spec_base);
     }
 }
 
@@ -714,7 +739,7 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
     pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
     const EnvCtl *c = v.ctl + e;
-    if (!kForce && !c->go) return;
+    if (!kForce && !c->hdr0.go) return;
     const int n = c->n;
     const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 1) & ~1;
     const int beg = blockIdx.x * per;
@@ -793,9 +818,10 @@ template <int D>
 __device__ __forceinline__ void steer_body(const View &v, int e) {
     typedef typename GeomOf<D>::type G;
     EnvCtl *c = v.ctl + e;
-    const int go = c->go, cnt = c->cand_cnt;     // independent loads: one round trip
-    if (!go) return;
     const int lane = threadIdx.x & 31;
+    const int go = c->hdr0.go, spec_base = c->hdr0.base, cnt = c->cand_cnt;     // independent loads: one round trip
+    if (lane == 0) { IT.go = go; IT.spec_base = spec_base; }     // what k_expand of this iteration reads
+    if (!go) return;
     Node *nodes = v.nodes + (size_t)e * v.stride;
     Hint *hints = v.hints + (size_t)e * v.stride;
     double bs = XINF; int bi = INT_MAX;
@@ -865,13 +891,13 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
     for (int k = lane; k < m; k += 32) hit = hit || seg_hits_obstacle(g, k, xn, xnew);
     hit = __any_sync(0xffffffffu, hit);
     if (lane != 0) return;
-    c->nearest = nearest;
+    IT.nearest = nearest;
     c->cand_cnt = 0;
-    c->near_cnt = 0;
-    c->inserted = 0;
-    c->hdr[1].go = 0;
-    if (hit) { c->skip = 1; c->new_idx = -1; return; }
-    c->skip = 0;
+    IT.near_cnt = 0;
+    IT.inserted = 0;
+    IT.hdr1.go = 0;
+    if (hit) { IT.skip = 1; IT.new_idx = -1; return; }
+    IT.skip = 0;
     int new_idx;
     const double dup = D == 3 ? vecnorm3(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2]))
                               : vecnorm2(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]));
@@ -879,10 +905,10 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
         // "do not create a new node if it is actually the same point" (rrt_star_3d.py:41-45)
         xnew[0] = xn[0]; xnew[1] = xn[1]; xnew[2] = xn[2];
         new_idx = nearest;
-        c->cnew_default = -1.0;        // marker: x_new re-uses an existing vertex (k_expand walks it)
+        IT.cnew_default = -1.0;        // marker: x_new re-uses an existing vertex (k_expand walks it)
     } else {
         new_idx = c->n;
-        if (new_idx >= v.cap) { c->err |= ERR_VERTEX_OVERFLOW; c->skip = 1; c->new_idx = -1; return; }
+        if (new_idx >= v.cap) { atomicOr(&c->err, ERR_VERTEX_OVERFLOW); IT.skip = 1; IT.new_idx = -1; return; }
         const size_t o = (size_t)e * v.stride + new_idx;
         v.vx[o] = xnew[0]; v.vy[o] = xnew[1];
         if (D == 3) v.vz[o] = xnew[2];
@@ -891,39 +917,68 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
         nodes[new_idx] = nd;
         store_hint(hints + new_idx, nearest, hn);
         c->n = new_idx + 1;
-        c->inserted = 1;
+        IT.inserted = 1;
         c->tree_changed = 1;
         // Line(nearest, new) (rrt_base_3d.py:132-137); the root walk that turns it into
         // curr_node_new_cost and node_new_cost runs in k_expand together with the neighbours' walks
-        c->cnew_default = edge_len<D>(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2]));
-        set_parent(tree_of(v, e), new_idx, nearest, c->cnew_default);
+        IT.cnew_default = edge_len<D>(XSUB(xnew[0], xn[0]), XSUB(xnew[1], xn[1]), XSUB(xnew[2], xn[2]));
+        set_parent(tree_of(v, e), new_idx, nearest, IT.cnew_default);
     }
-    c->new_idx = new_idx;
-    c->x_new[0] = xnew[0]; c->x_new[1] = xnew[1]; c->x_new[2] = xnew[2];
+    IT.new_idx = new_idx;
+    IT.x_new[0] = xnew[0]; IT.x_new[1] = xnew[1]; IT.x_new[2] = xnew[2];
     double r = XMUL(c->search_radius, v.near_table[c->n]);
     if (c->step_len < r) r = c->step_len;            // min(gamma * f(n), step_len)
-    c->r = r;
-    c->T_near = D == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
+    IT.r = r;
+    IT.T_near = D == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
     {   // mirror pre-filter threshold: every vertex with f64 distance <= r has mirror squared distance <= near_thr
         const double rm = (v.ux ? r * c->qscale : r) + c->margin;
-        c->near_thr = __double2float_ru(rm * rm * 1.000001);
-        write_hdr(v, c, 1, 1, c->x_new, c->near_thr);
+        IT.near_thr = __double2float_ru(rm * rm * 1.000001);
+        write_hdr(v, c, 1, 1, IT.x_new, IT.near_thr);
     }
     if (v.ux || v.fx) {
         // x_new == x_rand up to rounding (the tree reaches within step_len of the sample): the ball the Nearest
         // scan collected around x_rand contains Near(x_new) -- no second scan.  Otherwise k_expand scans itself.
         bool same = fabs(XSUB(xnew[0], c->x_rand[0])) <= 1e-9 && fabs(XSUB(xnew[1], c->x_rand[1])) <= 1e-9;
         if (D == 3) same = same && fabs(XSUB(xnew[2], c->x_rand[2])) <= 1e-9;
-        const int use_spec = same && c->spec_cnt <= v.near_cap;
-        c->use_spec = use_spec;
-        c->need_scan = !use_spec;
-    } else { c->use_spec = 0; c->need_scan = 0; }
+        const int use_spec = same && IT.spec_cnt - spec_base <= v.near_cap;
+        IT.use_spec = use_spec;
+        IT.need_scan = !use_spec;
+    } else { IT.use_spec = 0; IT.need_scan = 0; }
 }
 
 template <int D>
 __global__ void __launch_bounds__(32) k_steer(View v) {
     pdl_wait();
     steer_body<D>(v, v.env0 + blockIdx.x);
+}
+
+// Pipelined RRT* driver (planning() loop body, rrt_star_3d.py:36-55): nothing the NEXT iteration's sample and
+// Nearest scan need depends on this iteration's ChooseParent / Rewire -- only on the inserted vertex and the
+// RNG stream.  k_front therefore does Steer of iteration i, the loop accounting and the sample of iteration
+// i + 1, so that scan(i + 1) streams while k_expand(i) (launched on a second stream, View::pipe = 1) still walks.
+// The two iterations in flight work on the two IterScratch copies (View::par).
+template <int D>
+__global__ void __launch_bounds__(128) k_front(View v) {
+    typedef typename GeomOf<D>::type G;
+    pdl_wait();
+    const int e = v.env0 + blockIdx.x;
+    EnvCtl *c = v.ctl + e;
+    if (!c->hdr0.go) {
+        if (threadIdx.x == 0) IT.go = 0;
+        return;
+    }
+    __shared__ G g;
+    __shared__ double sm_s[4];
+    __shared__ int sm_i[4];
+    if (threadIdx.x < 32) steer_body<D>(v, e);
+    __syncthreads();
+    if (threadIdx.x == 0) {      // the accounting k_expand does at its end in the unpipelined flow
+        c->budget--;
+        c->p1_done++;
+        if (c->p1_done >= v.iter_max) c->state = ST_DONE;
+    }
+    __syncthreads();
+    top_body<D>(v, e, g, false, sm_s, sm_i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -939,15 +994,15 @@ __global__ void __launch_bounds__(256) k_near(View v) {
     pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
     EnvCtl *c = v.ctl + e;
-    if (!kForce && (!c->go || c->skip)) return;
+    if (!kForce && (!IT.go || IT.skip)) return;
     const int n = c->n;
     const int per = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 1) & ~1;
     const int beg = blockIdx.x * per;
     const int end = min(n, beg + per);
     const double *X = v.vx + (size_t)e * v.stride, *Y = v.vy + (size_t)e * v.stride;
     const double *Z = D == 3 ? v.vz + (size_t)e * v.stride : nullptr;
-    const double qx = c->x_new[0], qy = c->x_new[1], qz = c->x_new[2];
-    const double T = c->T_near, r = c->r;
+    const double qx = IT.x_new[0], qy = IT.x_new[1], qz = IT.x_new[2];
+    const double T = IT.T_near, r = IT.r;
     int *cand = v.cand + (size_t)e * v.near_cap;
 
 #define NEAR_ONE(xx, yy, zz, ii)                                                      \
@@ -1084,7 +1139,7 @@ __global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
     pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
     EnvCtl *c = v.ctl + e;
-    const ScanHdr h = load_hdr(&c->hdr[0]);
+    const ScanHdr h = load_hdr(&c->hdr0);
     if (!kForce && !h.go) return;
     __shared__ unsigned s_min;
     if (threadIdx.x == 0) s_min = 0x7f800000u;
@@ -1113,8 +1168,8 @@ __global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
             while (hit) {
                 const int j = __ffs(hit) - 1;
                 hit &= hit - 1;
-                const int slot = atomicAdd(&c->spec_cnt, 1);
-                if (slot < v.near_cap) v.cand2[(size_t)e * v.near_cap + slot] = base + j;
+                const int slot = atomicAdd(&IT.spec_cnt, 1) - h.base;
+                if (slot < v.near_cap) cand2_of(v, e)[slot] = base + j;
             }
         }
     });
@@ -1141,7 +1196,7 @@ __global__ void __launch_bounds__(256) k_near_m(View v) {
     pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
     EnvCtl *c = v.ctl + e;
-    const ScanHdr h = load_hdr(&c->hdr[1]);
+    const ScanHdr h = load_hdr(&IT.hdr1);
     if (!kForce && !h.go) return;
     constexpr int kVec = kU16 ? 8 : 4;
     const int per = (((h.n + (int)gridDim.x - 1) / (int)gridDim.x) + kVec - 1) & ~(kVec - 1);
@@ -1201,7 +1256,7 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
         int depth = 0;
         for (int i = gp; i != 0; i = (int)load_node(nodes + i).parent) depth++;
         const int M = depth + 1;
-        if (M > v.path_cap) { c->err |= ERR_PATH_DEPTH; }
+        if (M > v.path_cap) { atomicOr(&c->err, ERR_PATH_DEPTH); }
         else {
             double *seg = v.pathseg + (size_t)e * v.path_cap;
             Node cur = load_node(nodes + gp);
@@ -1225,11 +1280,11 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     pdl_wait();
     const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
-    if (!c->go) return;
     if (v.fuse_steer) {
+        if (!c->hdr0.go) return;
         if (threadIdx.x < 32) steer_body<D>(v, e);
         __syncthreads();
-    }
+    } else if (!IT.go) return;
     __shared__ G g;
     __shared__ int s_cand[kNearSmem];
     __shared__ int s_near[kNearSmem];
@@ -1252,37 +1307,42 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
 #define PHASE_MARK(k)
 #endif
     PHASE_MARK(0)
-    const bool skipped = c->skip;
+    const bool skipped = IT.skip;
 
     if (!skipped) {
         stage_geom<D>(&g, v, e);
         const int *cand = v.cand + (size_t)e * v.near_cap;
         int cnt;
-        if (c->need_scan) {
-            // Near scan by this CTA (x_new != x_rand: sparse tree or the duplicate guard) -- same filter,
-            // same candidate list as the stand-alone k_near_m
-            const ScanHdr h = load_hdr(&c->hdr[1]);
+        if (IT.need_scan) {
+            // Near scan by this CTA (x_new != x_rand: sparse tree or the duplicate guard) -- same filter as the
+            // stand-alone k_near_m; the matches replace the (useless) speculative list of this iteration
+            const ScanHdr h = load_hdr(&IT.hdr1);
             const float thr = h.thr;
+            int *list = cand2_of(v, e);
+            if (tid == 0) atomicExch(&IT.fb_cnt, 0);
+            __syncthreads();
+            auto add = [&](int idx) { const int slot = atomicAdd(&IT.fb_cnt, 1); if (slot < v.near_cap) list[slot] = idx; };
             if (v.ux) mirror_scan<D, true>(v, e, 0, h.n, h.qx, h.qy, h.qz, [&](const float (&a)[8], int base) {
                 if (vec_min(a) <= thr) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) if (a[j] <= thr) append_cand(v, c, e, base + j);
+                    for (int j = 0; j < 8; j++) if (a[j] <= thr) add(base + j);
                 }
             });
             else mirror_scan<D, false>(v, e, 0, h.n, h.qx, h.qy, h.qz, [&](const float (&a)[4], int base) {
                 if (vec_min(a) <= thr) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (a[j] <= thr) append_cand(v, c, e, base + j);
+                    for (int j = 0; j < 4; j++) if (a[j] <= thr) add(base + j);
                 }
             });
             __syncthreads();
-            cnt = __ldcg(&c->cand_cnt);
-        } else if (c->use_spec) {
-            cnt = c->spec_cnt;
-            cand = v.cand2 + (size_t)e * v.near_cap;
+            cnt = __ldcg(&IT.fb_cnt);
+            cand = list;
+        } else if (IT.use_spec) {
+            cnt = IT.spec_cnt - IT.spec_base;
+            cand = cand2_of(v, e);
         } else cnt = c->cand_cnt;
         if (cnt > v.near_cap || cnt > kNearSmem) {
-            if (tid == 0) c->err |= ERR_NEAR_OVERFLOW;
+            if (tid == 0) atomicOr(&c->err, ERR_NEAR_OVERFLOW);
             cnt = min(min(cnt, v.near_cap), kNearSmem);
         }
         if (cnt <= 256) {
@@ -1308,9 +1368,9 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         }
         PHASE_MARK(1)
 
-        const double xnew[3] = {c->x_new[0], c->x_new[1], c->x_new[2]};
-        const int new_idx = c->new_idx;
-        const double T_near = c->T_near, r_near = c->r;
+        const double xnew[3] = {IT.x_new[0], IT.x_new[1], IT.x_new[2]};
+        const int new_idx = IT.new_idx;
+        const double T_near = IT.T_near, r_near = IT.r;
         // collision filter + ordered compaction (tiles of blockDim candidates, ascending)
         for (int base = 0; base < cnt; base += blockDim.x) {
             const int k = base + tid;
@@ -1350,7 +1410,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         PHASE_MARK(2)
         int *near_out = v.near_out + (size_t)e * v.near_cap;
         for (int k = tid; k < m; k += blockDim.x) near_out[k] = s_near[k];
-        if (tid == 0) c->near_cnt = m;
+        if (tid == 0) IT.near_cnt = m;
 
         if (m > 0) {
             // One parallel round of root walks serves ChooseParent, node_new_cost and Rewire.
@@ -1371,10 +1431,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 if (k == m) {
                     // the steer parent: curr_node_new_cost = cost(nearest) + Line(nearest, new)
                     // (rrt_star_3d.py:46,51) and the cost(new) ChooseParent falls back to
-                    const double e0 = c->cnew_default;
+                    const double e0 = IT.cnew_default;
                     double cn, via;
-                    if (e0 < 0.0) { cn = cost_walk<D>(t, c->nearest); s_curr[0] = cn; s_curr[1] = cn; }
-                    else { cost_walk2<D>(t, c->nearest, e0, cn, via); s_curr[0] = XADD(cn, e0); s_curr[1] = via; }
+                    if (e0 < 0.0) { cn = cost_walk<D>(t, IT.nearest); s_curr[0] = cn; s_curr[1] = cn; }
+                    else { cost_walk2<D>(t, IT.nearest, e0, cn, via); s_curr[0] = XADD(cn, e0); s_curr[1] = via; }
                     continue;
                 }
                 const int idx = s_near[k];
@@ -1403,7 +1463,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             // ---- choose_parent (rrt_star_3d.py:80-90)
             const bool reparent = bs < s_curr[0];
             const double c_new = reparent ? s_curr[2] : s_curr[1];
-            const bool new_moved = reparent && !c->inserted;   // an existing vertex (duplicate guard) changed its parent
+            const bool new_moved = reparent && !IT.inserted;   // an existing vertex (duplicate guard) changed its parent
             if (tid == 0) {
                 c->stamp++;
                 Hint hnew;
@@ -1491,10 +1551,10 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 if (edge_len<D>(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2])) < c->step_len &&
                     !seg_collides(g, xnew, c->goal)) {
                     if (c->n_sol < v.sol_cap) v.sol[(size_t)e * v.sol_cap + c->n_sol] = new_idx;
-                    else c->err |= ERR_SOL_OVERFLOW;
+                    else atomicOr(&c->err, ERR_SOL_OVERFLOW);
                     c->n_sol++;
                 }
-            } else if (v.mode == NIRRT_MODE_PLANNING_RANDOM && c->inserted) {
+            } else if (v.mode == NIRRT_MODE_PLANNING_RANDOM && IT.inserted) {
                 const double gx = XSUB(c->goal[0], xnew[0]), gy = XSUB(c->goal[1], xnew[1]), gz = XSUB(c->goal[2], xnew[2]);
                 const double s2 = scan_sq<D>(gx, gy, gz);
                 // dist_to_goal <= step_len (rrt_star_3d.py:103-104 / rrt_star_2d.py:103-104)
@@ -1535,7 +1595,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             }
             c->budget--;
         }
-    } else if (tid == 0) {
+    } else if (tid == 0 && !v.pipe) {
         c->budget--;
         if (v.mode == NIRRT_MODE_PLANNING) {
             c->p1_done++;
@@ -1550,7 +1610,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     }
 #ifdef NIRRT_PHASE_TIMING
     if (tid == 0 && (e % 97) == 0 && (c->n % 50) == 0)
-        printf("expand e=%d n=%d cand=%d near=%d sort=%lld filter=%lld walks=%lld serial=%lld goal=%lld top=%lld fast=%llu slow=%llu\n", e, c->n, c->cand_cnt, c->near_cnt,
+        printf("expand e=%d n=%d cand=%d near=%d sort=%lld filter=%lld walks=%lld serial=%lld goal=%lld top=%lld fast=%llu slow=%llu\n", e, c->n, c->cand_cnt, IT.near_cnt,
                t_ph[1] - t_ph[0], t_ph[2] - t_ph[1], t_ph[3] - t_ph[2], t_ph[4] - t_ph[3], t_ph[5] - t_ph[4], clock64() - t_ph[5], t_ph[6] - t_ph[2], t_ph[7] - t_ph[6]);
 #endif
 }
@@ -1610,7 +1670,7 @@ __global__ void k_begin(View v) {
     EnvCtl *c = v.ctl + e;
     c->state = ST_PHASE1; c->saved_state = ST_PHASE1;
     c->p1_done = 0; c->left = 0; c->budget = 0; c->n_rec = 0; c->resumed = 0;
-    set_idle(c); c->skip = 0; c->nearest = 0; c->new_idx = -1; c->inserted = 0; c->cand_cnt = 0; c->near_cnt = 0;
+    set_idle(c); IT.skip = 0; IT.nearest = 0; IT.new_idx = -1; IT.inserted = 0; c->cand_cnt = 0; IT.near_cnt = 0;
     c->c_best = XINF; c->c_update = XINF;
     c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
     c->err = 0;
@@ -1979,7 +2039,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     DALLOC(v.mt, MtState, v.E); DALLOC(v.ctl, EnvCtl, v.E);
     DALLOC(v.part_s, double, (size_t)v.E * v.chunks); DALLOC(v.part_i, int, (size_t)v.E * v.chunks);
     DALLOC(v.cand, int, (size_t)v.E * v.near_cap); DALLOC(v.near_out, int, (size_t)v.E * v.near_cap);
-    DALLOC(v.cand2, int, (size_t)v.E * v.near_cap);
+    DALLOC(v.cand2, int, (size_t)2 * v.E * v.near_cap);     // two halves: IterScratch copies 0 / 1
     DALLOC(v.sol, int, (size_t)v.E * v.sol_cap);
     DALLOC(v.records, double, (size_t)v.E * v.rec_cap);
     DALLOC(v.pathseg, double, (size_t)v.E * v.path_cap);
@@ -2634,12 +2694,13 @@ extern "C" int nirrt_batch_read_trace_sync(nirrt_batch *b, int *nearest, int *ne
     }
     for (int e = 0; e < v.E; e++) {
         const EnvCtl &c = b->h_ctl[e];
-        if (nearest) nearest[e] = c.nearest;
-        if (new_index) new_index[e] = c.new_idx;
-        if (near_count) near_count[e] = c.near_cnt;
+        const IterScratch &it = c.s[0];         // runs end with a non-pipelined iteration on copy 0
+        if (nearest) nearest[e] = it.nearest;
+        if (new_index) new_index[e] = it.new_idx;
+        if (near_count) near_count[e] = it.near_cnt;
         if (x_rand) for (int i = 0; i < v.dim; i++) x_rand[v.dim * e + i] = c.x_rand[i];
         if (near && near_stride > 0) {
-            const int m = c.near_cnt < near_stride ? c.near_cnt : near_stride;
+            const int m = it.near_cnt < near_stride ? it.near_cnt : near_stride;
             for (int k = 0; k < m; k++) near[(size_t)e * near_stride + k] = h[(size_t)e * v.near_cap + k];
         }
     }
@@ -2686,9 +2747,9 @@ __global__ void k_set_query(View v, int env, const double *q, int which, double 
     const double qz = v.dim == 3 ? q[2] : 0.0;
     if (which == 0) { c->x_rand[0] = q[0]; c->x_rand[1] = q[1]; c->x_rand[2] = qz; }
     else {
-        c->x_new[0] = q[0]; c->x_new[1] = q[1]; c->x_new[2] = qz;
-        c->r = r;
-        c->T_near = v.dim == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
+        IT.x_new[0] = q[0]; IT.x_new[1] = q[1]; IT.x_new[2] = qz;
+        IT.r = r;
+        IT.T_near = v.dim == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
         c->cand_cnt = 0;
     }
 }
@@ -2709,7 +2770,7 @@ static View single_env_view(const View &v, int env) {
     if (v.mt_py) w.mt_py += env;
     w.mt += env; w.ctl += env;
     w.part_s += (size_t)env * v.chunks; w.part_i += (size_t)env * v.chunks;
-    w.cand += (size_t)env * v.near_cap; w.near_out += (size_t)env * v.near_cap; w.cand2 += (size_t)env * v.near_cap;
+    w.cand += (size_t)env * v.near_cap; w.near_out += (size_t)env * v.near_cap; w.cand2 += (size_t)env * v.near_cap;   /* single-env views always use copy 0 */
     w.E = 1;
     return w;
 }
@@ -2787,7 +2848,7 @@ extern "C" int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, in
 
 __global__ void k_reset_cand(View v) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < v.E) { EnvCtl *c = v.ctl + e; c->cand_cnt = 0; c->hdr[0].n = c->hdr[1].n = c->n; }
+    if (e < v.E) { EnvCtl *c = v.ctl + e; c->cand_cnt = 0; c->hdr0.n = IT.hdr1.n = c->n; }
 }
 
 extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, float *ms, int64_t *bytes, void *stream) {
