@@ -1845,10 +1845,10 @@ __global__ void __launch_bounds__(kExpandThreads) k_goal_parent(View v, int use_
     } while (0)
 
 // launch of a kernel(View); pdl: allow it to become resident while its predecessor in the stream drains
-static void launch_view(void (*kernel)(View), dim3 grid, dim3 block, cudaStream_t s, const View &v, bool pdl) {
+static void launch_view(void (*kernel)(View), dim3 grid, dim3 block, cudaStream_t s, const View &v, bool pdl, size_t smem = 0) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1871,6 +1871,8 @@ static void launch_scan(const View &v, int which, int count, cudaStream_t s, boo
         if (which == 0) k = v.dim == 3 ? k_nearest<3, kForce> : k_nearest<2, kForce>;
         else k = v.dim == 3 ? k_near<3, kForce> : k_near<2, kForce>;
     }
+    // (Capping the scan's residency with a dummy shared-memory reservation so that k_expand CTAs always find room
+    // was measured and is worse: 86-94 us per step at 6 / 5 / 4 scan CTAs per SM against 72 us uncapped.)
     launch_view(k, grid, 256, s, v, pdl);
 }
 
@@ -1898,6 +1900,11 @@ struct nirrt_batch {
     int groups;
     cudaStream_t gs[kMaxGroups];
     cudaEvent_t ev_fork, ev_join[kMaxGroups];
+    // pipelined RRT* driver: second stream per group for k_expand, events per IterScratch copy
+    bool pipeline;   // NIRRT_PIPELINE=0 disables
+    bool gpipe;      // the cached graph holds pipelined iterations
+    cudaStream_t gs2[kMaxGroups];
+    cudaEvent_t ev_a[kMaxGroups][2], ev_b[kMaxGroups][2];
     // pinned scratch for small synchronous reads
     EnvCtl *h_ctl;
     // tree transfers (load_trees / read_trees): two persistent device staging buffers on two internal
@@ -1959,6 +1966,11 @@ extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
     for (int g = 0; g < kMaxGroups; g++) {
         if (b->gs[g]) cudaStreamDestroy(b->gs[g]);
         if (b->ev_join[g]) cudaEventDestroy(b->ev_join[g]);
+        if (b->gs2[g]) cudaStreamDestroy(b->gs2[g]);
+        for (int q = 0; q < 2; q++) {
+            if (b->ev_a[g][q]) cudaEventDestroy(b->ev_a[g][q]);
+            if (b->ev_b[g][q]) cudaEventDestroy(b->ev_b[g][q]);
+        }
     }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->gexec) cudaGraphExecDestroy(b->gexec);
@@ -1987,7 +1999,13 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     memset(&b->v, 0, sizeof(View));
     b->device = d->device; b->launches = 0; b->goal_lists = false; b->h_ctl = nullptr;
     b->groups = 1; b->ev_fork = nullptr;
-    for (int g = 0; g < kMaxGroups; g++) { b->gs[g] = nullptr; b->ev_join[g] = nullptr; }
+    for (int g = 0; g < kMaxGroups; g++) {
+        b->gs[g] = nullptr; b->ev_join[g] = nullptr; b->gs2[g] = nullptr;
+        for (int q = 0; q < 2; q++) { b->ev_a[g][q] = nullptr; b->ev_b[g][q] = nullptr; }
+    }
+    // off by default: measured 77-79 us per step against 72 us unpipelined at 512 x 100k (the step is bound by the
+    // SM time of the scan, not by the dependency chain); NIRRT_PIPELINE=1 enables it
+    { const char *pl = getenv("NIRRT_PIPELINE"); b->pipeline = pl && atoi(pl) == 1; b->gpipe = false; }
     for (int i = 0; i < 2; i++) { b->stage[i] = nullptr; b->xs[i] = nullptr; b->xe[i] = nullptr; }
     b->stage_n = nullptr; b->stage_envs = 0; b->xfork = nullptr;
     View &v = b->v;
@@ -1999,6 +2017,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         const char *gr = getenv("NIRRT_GRAPH");
         b->graph_iters = gr ? atoi(gr) : kGraphItersDefault;     // NIRRT_GRAPH=<iterations per graph>, 0 disables
         if (b->graph_iters > 256) b->graph_iters = 256;
+        b->graph_iters &= ~1;      // even: a pipelined block ends on IterScratch copy 0
         b->use_graph = b->graph_iters > 0;
         b->gexec = nullptr; b->graph_launches = 0; b->cs = nullptr;
         const char *g = getenv("NIRRT_GROUPS");
@@ -2051,6 +2070,11 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         for (int g = 0; g < b->groups; g++) {
             CUDA_TRY(cudaStreamCreateWithFlags(&b->gs[g], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&b->ev_join[g], cudaEventDisableTiming));
+            CUDA_TRY(cudaStreamCreateWithFlags(&b->gs2[g], cudaStreamNonBlocking));
+            for (int q = 0; q < 2; q++) {
+                CUDA_TRY(cudaEventCreateWithFlags(&b->ev_a[g][q], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&b->ev_b[g][q], cudaEventDisableTiming));
+            }
         }
         CUDA_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaStreamCreateWithFlags(&b->cs, cudaStreamNonBlocking));
@@ -2475,18 +2499,59 @@ static int run_groups(nirrt_batch *b, cudaStream_t s, int n, bool first, bool la
     return NIRRT_OK;
 }
 
+// The pipelined RRT* driver applies to the plain planning() loop body of RRT* with a mirror scan: nothing the
+// next sample / scan needs depends on ChooseParent / Rewire there (see k_front).
+static bool can_pipeline(const nirrt_batch *b) {
+    const View &v = b->v;
+    return b->pipeline && b->groups >= 2 && (v.ux || v.fx) && v.variant == 0 && v.mode == NIRRT_MODE_PLANNING;
+}
+
+// `m` (even) pipelined iterations of every group.  Per group, stream gs: scan(j) -> k_front(j) -> scan(j+1) ...,
+// stream gs2: k_expand(j) after k_front(j); scan(j+2) waits for k_expand(j), whose IterScratch copy and
+// candidate-list half it re-uses.  Entered and left with everything joined into `s` and the sample of the
+// next iteration ready on copy 0.
+static int run_pipelined(nirrt_batch *b, cudaStream_t s, int m) {
+    if (m <= 0) return NIRRT_OK;
+    const int G = b->groups;
+    CUDA_TRY(cudaEventRecord(b->ev_fork, s));
+    for (int g = 0; g < G; g++) CUDA_TRY(cudaStreamWaitEvent(b->gs[g], b->ev_fork, 0));
+    for (int j = 0; j < m; j++)
+        for (int g = 0; g < G; g++) {
+            View v = b->v;
+            const int e0 = (int)((long long)v.E * g / G), e1 = (int)((long long)v.E * (g + 1) / G);
+            if (e1 <= e0) continue;
+            const int count = e1 - e0, q = j & 1;
+            v.env0 = e0; v.par = q; v.pipe = 1; v.fuse_steer = 0; v.fuse_top = 0;
+            if (j >= 2) CUDA_TRY(cudaStreamWaitEvent(b->gs[g], b->ev_b[g][q], 0));
+            launch_scan<false>(v, 0, count, b->gs[g], false);               // follows event operations: plain stream order
+            launch_view(v.dim == 3 ? k_front<3> : k_front<2>, count, 128, b->gs[g], v, b->pdl);
+            CUDA_TRY(cudaEventRecord(b->ev_a[g][q], b->gs[g]));
+            CUDA_TRY(cudaStreamWaitEvent(b->gs2[g], b->ev_a[g][q], 0));
+            launch_view(v.dim == 3 ? k_expand<3> : k_expand<2>, count, kExpandThreads, b->gs2[g], v, false);
+            CUDA_TRY(cudaEventRecord(b->ev_b[g][q], b->gs2[g]));
+            b->launches += 3;
+        }
+    for (int g = 0; g < G; g++) {
+        if ((long long)b->v.E * (g + 1) / G <= (long long)b->v.E * g / G) continue;
+        CUDA_TRY(cudaEventRecord(b->ev_join[g], b->gs[g]));
+        CUDA_TRY(cudaStreamWaitEvent(s, b->ev_join[g], 0));
+        CUDA_TRY(cudaStreamWaitEvent(s, b->ev_b[g][(m - 1) & 1], 0));        // the last k_expand on gs2 (stream ordered)
+    }
+    return NIRRT_OK;
+}
+
 // CUDA graph of b->graph_iters steady-state iterations of all groups (kernel arguments are the View by value,
-// so the graph is rebuilt whenever the View changed): one graph launch replaces 2 x groups x b->graph_iters
+// so the graph is rebuilt whenever the View changed): one graph launch replaces 2-3 x groups x b->graph_iters
 // kernel launches, which keeps the host far ahead of the device even with many small groups.
-static bool ensure_graph(nirrt_batch *b) {
+static bool ensure_graph(nirrt_batch *b, bool pipelined) {
     if (!b->use_graph || b->groups < 2) return false;
-    if (b->gexec && memcmp(&b->gview, &b->v, sizeof(View)) == 0) return true;
+    if (b->gexec && b->gpipe == pipelined && memcmp(&b->gview, &b->v, sizeof(View)) == 0) return true;
     if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
     const int64_t launches0 = b->launches;
     cudaGraph_t graph = nullptr;
     bool ok = cudaStreamBeginCapture(b->cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
-        const int rc = run_groups(b, b->cs, b->graph_iters, false, false);
+        const int rc = pipelined ? run_pipelined(b, b->cs, b->graph_iters) : run_groups(b, b->cs, b->graph_iters, false, false);
         const cudaError_t e = cudaStreamEndCapture(b->cs, &graph);
         ok = rc == NIRRT_OK && e == cudaSuccess && graph != nullptr;
     }
@@ -2500,6 +2565,7 @@ static bool ensure_graph(nirrt_batch *b) {
         return false;
     }
     memcpy(&b->gview, &b->v, sizeof(View));     // byte copy: the comparison above is a memcmp
+    b->gpipe = pipelined;
     return true;
 }
 
@@ -2509,11 +2575,23 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
-    if (iters >= b->graph_iters + 2 && ensure_graph(b)) {
+    const int GI = b->graph_iters > 0 ? (b->graph_iters & ~1) : 0;     // even: a pipelined block ends on copy 0
+    if (can_pipeline(b) && iters >= 6) {
+        // first and last iteration unpipelined (k_top opens, the last k_expand samples nothing), an even
+        // number of pipelined iterations in between
+        TRY(run_groups(b, s, 1, true, false));
+        const int mid = iters - 2, m = mid & ~1;
+        int done = 0;
+        if (GI >= 2 && m >= GI && ensure_graph(b, true))
+            for (; done + GI <= m; done += GI) { CUDA_TRY(cudaGraphLaunch(b->gexec, s)); b->launches += b->graph_launches; }
+        TRY(run_pipelined(b, s, m - done));
+        TRY(run_groups(b, s, mid - m, false, false));
+        TRY(run_groups(b, s, 1, false, true));
+    } else if (GI >= 2 && iters >= GI + 2 && ensure_graph(b, false)) {
         TRY(run_groups(b, s, 1, true, false));
         const int mid = iters - 2;
-        for (int r = 0; r < mid / b->graph_iters; r++) { CUDA_TRY(cudaGraphLaunch(b->gexec, s)); b->launches += b->graph_launches; }
-        TRY(run_groups(b, s, mid % b->graph_iters, false, false));
+        for (int r = 0; r < mid / GI; r++) { CUDA_TRY(cudaGraphLaunch(b->gexec, s)); b->launches += b->graph_launches; }
+        TRY(run_groups(b, s, mid % GI, false, false));
         TRY(run_groups(b, s, 1, false, true));
     } else {
         TRY(run_groups(b, s, iters, true, true));
