@@ -147,6 +147,7 @@ struct View {
     double *vx, *vy, *vz;
     float *fx, *fy, *fz;   // f32 mirror of the coordinates (scan layout, 4 B per coordinate); null = not in use
     unsigned short *ux, *uy, *uz;   // u16 fixed-point mirror (scan layout, 2 B per coordinate); null = not in use
+    unsigned *m8;                   // u8 fixed-point mirror: one word {x8, y8, z8, 0} per vertex (NIRRT_SCAN=u8); null = not in use
     Node *nodes;
     struct Hint *hints;  // [E][stride] ancestor hints of the cost walks (see walk_to_root)
     struct Link *links;  // [E][stride] {edge length to the parent, parent}: what a cost walk reads
@@ -170,6 +171,8 @@ struct View {
     const double *near_table;
 };
 
+__host__ __device__ __forceinline__ bool has_mirror(const View &v) { return v.ux || v.fx || v.m8; }
+__host__ __device__ __forceinline__ int scan_bytes_per_vertex(const View &v) { return v.m8 ? 4 : (v.ux ? 2 : (v.fx ? 4 : 8)) * v.dim; }
 #define IT (c->s[v.par])     // this launch's IterScratch copy (every user names its EnvCtl pointer c and its View v)
 __device__ __forceinline__ int *cand2_of(const View &v, int e) { return v.cand2 + ((size_t)v.par * v.E + e) * v.near_cap; }
 
@@ -449,13 +452,25 @@ __device__ __forceinline__ void push_record(const View &v, EnvCtl *c, int e, dou
 
 // ---- mirror-scan helpers (see "Mirror scans" below)
 constexpr double kMarginU16 = 2.0;
+// u8 mirror: 255 cells over the longest world edge, vertex and query both rounded to a cell and all scan
+// arithmetic in exact integers: |sqrt(d8^2) - d * qscale| <= sqrt(3)/2 + sqrt(3)/2 < kMarginU8 cells
+constexpr double kMarginU8 = 1.75;
 constexpr double kSpecSlack = 1e-6;   // world units: |x_new - x_rand| allowed when the speculative Near list is used (k_steer checks 1e-9 per axis)
 
 __device__ __forceinline__ unsigned short quantize_u16(double x, double lo, double scale) {
     int q = __double2int_rn((x - lo) * scale);
     return (unsigned short)min(65535, max(0, q));
 }
+__device__ __forceinline__ unsigned quantize_u8(double x, double lo, double scale) {
+    int q = __double2int_rn((x - lo) * scale);
+    return (unsigned)min(255, max(0, q));
+}
 __device__ __forceinline__ void mirror_store(const View &v, const EnvCtl *c, size_t o, double x, double y, double z) {
+    if (v.m8) {
+        unsigned w = quantize_u8(x, c->qlo[0], c->qscale) | (quantize_u8(y, c->qlo[1], c->qscale) << 8);
+        if (v.dim == 3) w |= quantize_u8(z, c->qlo[2], c->qscale) << 16;
+        v.m8[o] = w;
+    }
     if (v.ux) {
         v.ux[o] = quantize_u16(x, c->qlo[0], c->qscale);
         v.uy[o] = quantize_u16(y, c->qlo[1], c->qscale);
@@ -490,6 +505,25 @@ __device__ __forceinline__ ScanHdr load_hdr(const ScanHdr *h) {
     r.qz = __int_as_float(b.x); r.thr = __int_as_float(b.y); r.band = __int_as_float(b.z); r.base = b.w;
     return r;
 }
+// u8 mirror: the scan compares the exact integer a' = |m|^2 - 2 m.q8 (two DP4A per vertex) with thresholds that
+// have |q8|^2 folded in; qx = packed query cells, qy = |q8|^2, thr = integer threshold - |q8|^2 (as bit patterns).
+// A query outside the world range (never produced by the planners) selects everything: the exact fallbacks decide.
+__device__ __forceinline__ void store_hdr_u8(ScanHdr *h, const EnvCtl *c, int dim, int go, int n, const double *q, float thr, int base) {
+    ScanHdr r;
+    r.go = go; r.n = n;
+    unsigned packed = 0; int qq = 0; bool inside = true;
+    for (int d = 0; d < dim; d++) {
+        int qi = __double2int_rn((q[d] - c->qlo[d]) * c->qscale);
+        if (qi < 0 || qi > 255) { inside = false; qi = min(255, max(0, qi)); }
+        packed |= (unsigned)qi << (8 * d);
+        qq += qi * qi;
+    }
+    r.qx = __uint_as_float(packed); r.qy = __int_as_float(qq); r.qz = 0.f;
+    r.thr = __int_as_float(inside ? (int)fminf(thr, 1.0e9f) + 1 - qq : 0x3fffffff);
+    r.band = inside ? __double2float_ru(2.0 * c->margin) : 3.0e4f;
+    r.base = base;
+    *h = r;
+}
 template <int kMirror>   // 2: u16 mirror, 1: f32 mirror, 0: none (f64 scans: only go / n matter)
 __device__ __forceinline__ void store_hdr(ScanHdr *h, const EnvCtl *c, int go, int n, const double *q, float thr, int base) {
     ScanHdr r;
@@ -501,7 +535,8 @@ __device__ __forceinline__ void store_hdr(ScanHdr *h, const EnvCtl *c, int go, i
 }
 __device__ __forceinline__ void write_hdr(const View &v, EnvCtl *c, int which, int go, const double *q, float thr, int base = 0) {
     ScanHdr *h = which == 0 ? &c->hdr0 : &IT.hdr1;
-    if (v.ux) store_hdr<2>(h, c, go, c->n, q, thr, base);
+    if (v.m8) store_hdr_u8(h, c, v.dim, go, c->n, q, thr, base);
+    else if (v.ux) store_hdr<2>(h, c, go, c->n, q, thr, base);
     else if (v.fx) store_hdr<1>(h, c, go, c->n, q, thr, base);
     else store_hdr<0>(h, c, go, c->n, q, thr, base);
 }
@@ -714,7 +749,7 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
         const int n = c->n;
         double rs = XMUL(c->search_radius, fmax(v.near_table[n], v.near_table[n + 1]));
         if (c->step_len < rs) rs = c->step_len;
-        const double rm = (v.ux ? (rs + kSpecSlack) * c->qscale : rs + kSpecSlack) + c->margin;
+        const double rm = ((v.ux || v.m8) ? (rs + kSpecSlack) * c->qscale : rs + kSpecSlack) + c->margin;
         write_hdr(v, c, 0, 1, c->x_rand, __double2float_ru(rm * rm * 1.000001), spec_base);
     }
 }
@@ -828,7 +863,7 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
     Node nn; Hint hn = zero_hint();              // record + hints of this lane's best candidate
     nn.x = nn.y = nn.z = 0.0; nn.parent = 0;
     bool have_rec = false;
-    if (v.fx || v.ux) {
+    if (has_mirror(v)) {
         // candidates of the mirror scan: exact distance, lexicographic (value, index) minimum.  The exact
         // coordinates come from the 32-byte node record (the same doubles as vx/vy/vz, one sector instead
         // of three), so the winner's record is already here when Steer needs it.
@@ -931,11 +966,11 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
     IT.r = r;
     IT.T_near = D == 3 ? sqrt_le_threshold(r) : hypot_band_sq(r);
     {   // mirror pre-filter threshold: every vertex with f64 distance <= r has mirror squared distance <= near_thr
-        const double rm = (v.ux ? r * c->qscale : r) + c->margin;
+        const double rm = ((v.ux || v.m8) ? r * c->qscale : r) + c->margin;
         IT.near_thr = __double2float_ru(rm * rm * 1.000001);
         write_hdr(v, c, 1, 1, IT.x_new, IT.near_thr);
     }
-    if (v.ux || v.fx) {
+    if (has_mirror(v)) {
         // x_new == x_rand up to rounding (the tree reaches within step_len of the sample): the ball the Nearest
         // scan collected around x_rand contains Near(x_new) -- no second scan.  Otherwise k_expand scans itself.
         bool same = fabs(XSUB(xnew[0], c->x_rand[0])) <= 1e-9 && fabs(XSUB(xnew[1], c->x_rand[1])) <= 1e-9;
@@ -1190,6 +1225,105 @@ __global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
     }
 }
 
+// ---- u8 mirror scan (NIRRT_SCAN=u8): 4 bytes per vertex, two DP4A + one IMAD per vertex.
+// A CTA iteration covers 16 vertices per thread: four fully coalesced LDG.128 per thread (load u of lane l of
+// warp w reads vertices i0 + w*512 + u*128 + l*4 .. +3).  visit(a[16], base): a[j] = |m|^2 - 2 m.q8 (exact
+// integer, |q8|^2 is folded into the thresholds) of vertex base + (j >> 2) * 128 + (j & 3); INT_MAX past `end`.
+__device__ __forceinline__ int byte_index(int base, int j) { return base + (j >> 2) * 128 + (j & 3); }
+template <typename F>
+__device__ __forceinline__ void byte_scan(const View &v, int e, int beg, int end, unsigned q, F &&visit) {
+    const unsigned *M = v.m8 + (size_t)e * v.stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int step = 16 * blockDim.x;
+    for (int i0 = beg; i0 < end; i0 += step) {
+        const int base = i0 + warp * 512 + lane * 4;
+        int a[16];
+        if (i0 + step <= end) {           // the whole CTA tile lies inside the chunk: no per-vertex range checks
+            uint4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) w[u] = __ldcs(reinterpret_cast<const uint4 *>(M + base + u * 128));   // streaming: evict-first
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned m[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) a[4 * u + k] = (int)__dp4a(m[k], m[k], 0u) - 2 * (int)__dp4a(m[k], q, 0u);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 128;
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (i < end) w = __ldcs(reinterpret_cast<const uint4 *>(M + i));
+                const unsigned m[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    a[4 * u + k] = (i + k < end) ? (int)__dp4a(m[k], m[k], 0u) - 2 * (int)__dp4a(m[k], q, 0u) : INT_MAX;
+            }
+        }
+        visit(a, base);
+    }
+}
+__device__ __forceinline__ int vec_min_int16(const int (&a)[16]) {
+    int m = min(a[0], a[1]);
+#pragma unroll
+    for (int j = 2; j < 16; j++) m = min(m, a[j]);
+    return m;
+}
+
+template <int D, bool kForce>
+__global__ void __launch_bounds__(256, 5) k_nearest_b(View v) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int e = v.env0 + blockIdx.y;
+    EnvCtl *c = v.ctl + e;
+    const ScanHdr h = load_hdr(&c->hdr0);
+    if (!kForce && !h.go) return;
+    __shared__ int s_min;
+    if (threadIdx.x == 0) s_min = INT_MAX;
+    __syncthreads();
+    const int per = (((h.n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
+    const int beg = blockIdx.x * per;
+    const int end = min(h.n, beg + per);
+    if (beg >= end) return;
+    const unsigned q = __float_as_uint(h.qx);
+    const int qq = __float_as_int(h.qy), thr = __float_as_int(h.thr);
+    int a1 = INT_MAX, a2 = INT_MAX, i1 = INT_MAX;     // best and second-best value of this thread (a' = d8^2 - |q8|^2)
+    byte_scan(v, e, beg, end, q, [&](const int (&a)[16], int base) {
+        const int m = vec_min_int16(a);
+        if (m < a2) {                     // rare once the running values have settled
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                a2 = min(a2, max(a[j], a1));
+                if (a[j] < a1) { a1 = a[j]; i1 = byte_index(base, j); }
+            }
+        }
+        if (m <= thr) {                   // speculative Near ball around x_rand (see top_body)
+            unsigned hit = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) hit |= (a[j] <= thr ? 1u : 0u) << j;
+            while (hit) {
+                const int j = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const int slot = atomicAdd(&IT.spec_cnt, 1) - h.base;
+                if (slot < v.near_cap) cand2_of(v, e)[slot] = byte_index(base, j);
+            }
+        }
+    });
+    const int wmin = __reduce_min_sync(0xffffffffu, a1);
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_min, wmin);
+    __syncthreads();
+    // band in the distance domain, rounded up: sqrt(d8^2) <= sqrt(min d8^2) + 2 * margin
+    const float lim = __fadd_ru(__fsqrt_ru((float)(s_min + qq)), h.band);
+    const int band = (int)fminf(__fmul_ru(__fmul_ru(lim, lim), 1.000001f), 1.0e9f) + 1 - qq;
+    if (a1 <= band) {
+        if (a2 > band) append_cand(v, c, e, i1);
+        else byte_scan(v, e, beg, end, q, [&](const int (&a)[16], int base) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) if (a[j] <= band) append_cand(v, c, e, byte_index(base, j));
+        });
+    }
+}
+
 template <int D, bool kU16, bool kForce>
 __global__ void __launch_bounds__(256) k_near_m(View v) {
     pdl_wait();
@@ -1322,7 +1456,15 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             if (tid == 0) atomicExch(&IT.fb_cnt, 0);
             __syncthreads();
             auto add = [&](int idx) { const int slot = atomicAdd(&IT.fb_cnt, 1); if (slot < v.near_cap) list[slot] = idx; };
-            if (v.ux) mirror_scan<D, true>(v, e, 0, h.n, h.qx, h.qy, h.qz, [&](const float (&a)[8], int base) {
+            if (v.m8) {
+                const int thr8 = __float_as_int(h.thr);
+                byte_scan(v, e, 0, h.n, __float_as_uint(h.qx), [&](const int (&a)[16], int base) {
+                    if (vec_min_int16(a) <= thr8) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) if (a[j] <= thr8) add(byte_index(base, j));
+                    }
+                });
+            } else if (v.ux) mirror_scan<D, true>(v, e, 0, h.n, h.qx, h.qy, h.qz, [&](const float (&a)[8], int base) {
                 if (vec_min(a) <= thr) {
 #pragma unroll
                     for (int j = 0; j < 8; j++) if (a[j] <= thr) add(base + j);
@@ -1713,8 +1855,8 @@ __global__ void k_set_problems(View v, ProblemUpload u) {
         double R = 1.0, ext = 0.0;
         for (int i = 0; i < 6; i++) R = fmax(R, fabs(g->range[i]));
         for (int i = 0; i < 3; i++) { c->qlo[i] = g->range[2 * i]; ext = fmax(ext, g->range[2 * i + 1] - g->range[2 * i]); }
-        c->qscale = 65535.0 / fmax(ext, 1e-300);
-        c->margin = v.ux ? kMarginU16 : R * 0x1p-19;
+        c->qscale = (v.m8 ? 255.0 : 65535.0) / fmax(ext, 1e-300);
+        c->margin = v.m8 ? kMarginU8 : (v.ux ? kMarginU16 : R * 0x1p-19);
         c->fallbacks = 0;
     }
     mirror_store(v, c, o, c->start[0], c->start[1], c->start[2]);
@@ -1761,8 +1903,8 @@ __global__ void k_set_problems_2d(View v, ProblemUpload2 u) {
         for (int i = 0; i < 4; i++) R = fmax(R, fabs(g->range[i]));
         for (int i = 0; i < 2; i++) { c->qlo[i] = g->range[2 * i]; ext = fmax(ext, g->range[2 * i + 1] - g->range[2 * i]); }
         c->qlo[2] = 0.0;
-        c->qscale = 65535.0 / fmax(ext, 1e-300);
-        c->margin = v.ux ? kMarginU16 : R * 0x1p-19;
+        c->qscale = (v.m8 ? 255.0 : 65535.0) / fmax(ext, 1e-300);
+        c->margin = v.m8 ? kMarginU8 : (v.ux ? kMarginU16 : R * 0x1p-19);
         c->fallbacks = 0;
     }
     mirror_store(v, c, o, c->start[0], c->start[1], 0.0);
@@ -1861,7 +2003,9 @@ template <bool kForce>
 static void launch_scan(const View &v, int which, int count, cudaStream_t s, bool pdl = false) {
     const dim3 grid(v.chunks, count);
     void (*k)(View);
-    if (v.ux) {
+    if (v.m8 && which == 0) {
+        k = v.dim == 3 ? k_nearest_b<3, kForce> : k_nearest_b<2, kForce>;
+    } else if (v.ux) {
         if (which == 0) k = v.dim == 3 ? k_nearest_m<3, true, kForce> : k_nearest_m<2, true, kForce>;
         else k = v.dim == 3 ? k_near_m<3, true, kForce> : k_near_m<2, true, kForce>;
     } else if (v.fx) {
@@ -2042,6 +2186,8 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         } else if (mode && strcmp(mode, "f32") == 0) {
             DALLOC(v.fx, float, EV); DALLOC(v.fy, float, EV);
             if (v.dim == 3) DALLOC(v.fz, float, EV);
+        } else if (mode && strcmp(mode, "u8") == 0) {
+            DALLOC(v.m8, unsigned, EV);
         } else {
             DALLOC(v.ux, unsigned short, EV); DALLOC(v.uy, unsigned short, EV);
             if (v.dim == 3) DALLOC(v.uz, unsigned short, EV);
@@ -2319,7 +2465,7 @@ __global__ void k_scatter_trees(View v, int env_begin, const int *n, const doubl
         Node nd; nd.x = vs[0]; nd.y = vs[1]; nd.z = D == 3 ? vs[2] : 0.0; nd.parent = parents[(size_t)k * v.cap + i];
         v.vx[o] = nd.x; v.vy[o] = nd.y;
         if (D == 3) v.vz[o] = nd.z;
-        if (v.fx || v.ux) {
+        if (has_mirror(v)) {
             mirror_store(v, v.ctl + env, o, nd.x, nd.y, nd.z);
             const double *rg = D == 3 ? v.geom[env].range : v.geom2[env].range;
             bool out = nd.x < rg[0] || nd.x > rg[1] || nd.y < rg[2] || nd.y > rg[3];
@@ -2464,7 +2610,7 @@ static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count,
     v.fuse_top = last ? 0 : 1;
     const bool pdl = b->pdl;
     if (first) { launch_view(v.dim == 3 ? k_top<3> : k_top<2>, count, 128, s, v, false); b->launches += 1; }
-    const bool mirror = v.ux || v.fx;    // mirror scans collect Near speculatively during the Nearest pass:
+    const bool mirror = has_mirror(v);   // mirror scans collect Near speculatively during the Nearest pass:
     v.fuse_steer = mirror ? 1 : 0;       // the iteration is two kernels, the scan and everything else
     launch_scan<false>(v, 0, count, s, pdl);
     if (!mirror) {
@@ -2503,7 +2649,7 @@ static int run_groups(nirrt_batch *b, cudaStream_t s, int n, bool first, bool la
 // next sample / scan needs depends on ChooseParent / Rewire there (see k_front).
 static bool can_pipeline(const nirrt_batch *b) {
     const View &v = b->v;
-    return b->pipeline && b->groups >= 2 && (v.ux || v.fx) && v.variant == 0 && v.mode == NIRRT_MODE_PLANNING;
+    return b->pipeline && b->groups >= 2 && has_mirror(v) && v.variant == 0 && v.mode == NIRRT_MODE_PLANNING;
 }
 
 // `m` (even) pipelined iterations of every group.  Per group, stream gs: scan(j) -> k_front(j) -> scan(j+1) ...,
@@ -2631,7 +2777,7 @@ extern "C" int nirrt_batch_run_profiled_sync(nirrt_batch *b, int iters, float *m
         cudaEventRecord(e[2], s);
         LAUNCH_D(v.dim, k_steer, v.E, 32, 0, s, v);
         cudaEventRecord(e[3], s);
-        if (!(v.ux || v.fx)) launch_scan<false>(v, 1, v.E, s);   // mirror scans: Near is collected by the Nearest pass
+        if (!has_mirror(v)) launch_scan<false>(v, 1, v.E, s);   // mirror scans: Near is collected by the Nearest pass
         cudaEventRecord(e[4], s);
         LAUNCH_D(v.dim, k_expand, v.E, kExpandThreads, 0, s, v);
         cudaEventRecord(e[5], s);
@@ -2920,7 +3066,7 @@ extern "C" int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int
 extern "C" int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *reserved) {
     if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
     if (kernel_launches) *kernel_launches = b->launches;
-    if (reserved) *reserved = (b->v.ux ? 2 : (b->v.fx ? 4 : 8)) * b->v.dim;   // bytes per vertex one scan pass reads
+    if (reserved) *reserved = scan_bytes_per_vertex(b->v);   // bytes per vertex one scan pass reads
     return NIRRT_OK;
 }
 
@@ -2936,7 +3082,7 @@ extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, f
     CUDA_TRY(cudaSetDevice(b->device));
     TRY(fetch_ctl(b, s));
     int64_t total = 0;
-    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * (v.ux ? 2 : (v.fx ? 4 : 8)) * v.dim;
+    for (int e = 0; e < v.E; e++) total += (int64_t)b->h_ctl[e].n * scan_bytes_per_vertex(v);
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
     float acc = 0.f;

@@ -229,6 +229,8 @@ def test_scan_layouts_and_pipelines_agree(B, variant):
     base = _run_batch(B, problems, seeds, iters, variant)
     assert base[3] == 6                                           # default layout: 2 B per coordinate
     for env, bpv in (({"NIRRT_SCAN": "f32"}, 12), ({"NIRRT_SCAN": "f64"}, 24), ({"NIRRT_GROUPS": "5"}, 6),
+                     ({"NIRRT_SCAN": "u8"}, 4), ({"NIRRT_SCAN": "u8", "NIRRT_GROUPS": "4", "NIRRT_CHUNKS": "3"}, 4),
+                     ({"NIRRT_SCAN": "u8", "NIRRT_GROUPS": "3", "NIRRT_PIPELINE": "1"}, 4),
                      ({"NIRRT_GROUPS": "5", "NIRRT_GRAPH": "0"}, 6), ({"NIRRT_SCAN": "f64", "NIRRT_GROUPS": "3"}, 24),
                      ({"NIRRT_GROUPS": "4", "NIRRT_PIPELINE": "1"}, 6), ({"NIRRT_GROUPS": "5", "NIRRT_PIPELINE": "1", "NIRRT_GRAPH": "0"}, 6),
                      ({"NIRRT_GROUPS": "3", "NIRRT_SCAN": "f32", "NIRRT_GRAPH": "6", "NIRRT_PIPELINE": "1"}, 12),
