@@ -222,7 +222,8 @@ class BatchPlanner3D:
         check(self.L.nirrt_batch_set_vertex_limit(self.h, int(limit)))
 
     def run_profiled(self, iters):
-        """Like run(), synchronous, returning summed device ms of the five kernels."""
+        """Like run(), synchronous, with the kernels launched unfused and serialised: returns the summed device ms of
+        k_top / Nearest scan / k_steer / Near scan (0 with a mirror scan: Near is collected by the Nearest pass) / k_expand."""
         ms = (C.c_float * 5)()
         check(self.L.nirrt_batch_run_profiled_sync(self.h, int(iters), ms, self.stream))
         return dict(zip(("top", "nearest", "steer", "near", "expand"), [float(x) for x in ms]))
@@ -329,7 +330,8 @@ class BatchPlanner3D:
         return n.value
 
     def scan_bytes_per_vertex(self):
-        """bytes one Nearest / Near pass reads per vertex: 4*dim with the f32 mirror, 8*dim without"""
+        """bytes one scan pass reads per vertex: 2*dim with the u16 mirror (default), 4 with the u8 mirror,
+        4*dim with the f32 mirror, 8*dim without a mirror"""
         n = C.c_int64(0); b = C.c_int64(0)
         check(self.L.nirrt_batch_counters(self.h, C.byref(n), C.byref(b)))
         return b.value

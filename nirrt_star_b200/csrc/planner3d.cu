@@ -193,7 +193,7 @@ __device__ __forceinline__ void store_parent(Node *p, long long parent) {
     __stcg(reinterpret_cast<long long *>(p) + 3, parent);
 }
 
-// ---- programmatic dependent launch (PDL): the five kernels of an iteration are launched with
+// ---- programmatic dependent launch (PDL): the kernels of an iteration are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so kernel N+1's CTAs may become resident while
 // kernel N drains; every kernel therefore starts with pdl_wait() (returns once ALL memory operations
 // of the preceding kernel in the stream are complete and visible).  The scans let their (small)
@@ -2036,11 +2036,11 @@ struct nirrt_batch {
     std::vector<void *> allocs;
     int64_t launches;
     bool goal_lists;   // gc_idx/gc_d allocated
-    // group pipeline (nirrt_batch_run): the problems are split in G groups (4 for >= 256 problems,
-    // NIRRT_GROUPS overrides) that run the same five-kernel sequence on G internal streams, so the
-    // latency-bound kernels of one group (k_top, k_steer, k_expand: dependent pointer chasing)
-    // overlap the HBM-bound scans of the others.  Measured at 512 x 100k vertices: 0.364 ms/step
-    // with one group, 0.323 (2), 0.309 (4), 0.299 (6).
+    // group pipeline (nirrt_batch_run): the problems are split in G groups (16 for >= 512 problems,
+    // NIRRT_GROUPS overrides) that run the same kernel sequence on G internal streams, so the
+    // latency-bound k_expand of one group (dependent pointer chasing) overlaps the HBM-bound scans of
+    // the others.  Measured at 512 x 100k vertices (final kernels): 0.108 ms/step with one group,
+    // 0.106 (2), 0.091 (4), 0.073 (8), 0.072 (16 groups, CUDA-graph replay).
     int groups;
     cudaStream_t gs[kMaxGroups];
     cudaEvent_t ev_fork, ev_join[kMaxGroups];
