@@ -2039,7 +2039,7 @@ struct nirrt_batch {
     // group pipeline (nirrt_batch_run): the problems are split in G groups (16 for >= 512 problems,
     // NIRRT_GROUPS overrides) that run the same kernel sequence on G internal streams, so the
     // latency-bound k_expand of one group (dependent pointer chasing) overlaps the HBM-bound scans of
-    // the others.  Measured at 512 x 100k vertices (final kernels): 0.108 ms/step with one group,
+    // the others.  Measured at 512 x 100k vertices (late builds of round 1): 0.108 ms/step with one group,
     // 0.106 (2), 0.091 (4), 0.073 (8), 0.072 (16 groups, CUDA-graph replay).
     int groups;
     cudaStream_t gs[kMaxGroups];
