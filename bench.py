@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- RRT* iterations/s at 100k-node trees on random_3d worlds (BASELINE.json metric).
 
-A "step" is ONE lock-step iteration of the RRT* loop body (Sample, Nearest scan, Steer + collision,
-Near scan, ChooseParent, Rewire -- rrt_star_3d.py:36-55 of the reference) over a batch of E
-independent planning problems per GPU whose trees already hold `--nodes` vertices.  Workload at
+A "step" is a block of `--iters-per-step` (default 64) lock-step iterations of the RRT* loop body (Sample,
+Nearest scan, Steer + collision, Near scan, ChooseParent, Rewire -- rrt_star_3d.py:36-55 of the reference)
+over a batch of E independent planning problems per GPU whose trees hold `--nodes` vertices when the timed
+window starts; one step = one nirrt_batch_run call = k_top + 4 replays of the 16-iteration CUDA graph that
+nirrt_batch_begin built (no graph is ever captured inside the timed window).  Every leg starts from the same
+host snapshot of the 100k-vertex trees.  Workload at
 N=1: BASELINE.json configs[4] scaled to one GPU (4096 envs / 8 GPUs = 512 envs per GPU, 100k-node
 trees); more GPUs shard more problems (weak scaling), with one NCCL gather of per-problem results.
 
@@ -39,8 +42,11 @@ UNIT = "env-iters/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--iters-per-step", type=int, default=64, help="lock-step iterations per step (both arms)")
+    ap.add_argument("--parity-iters", type=int, default=128,
+                    help="iterations the CPU baseline and the GPU both continue from the snapshot before their trees are compared")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=512, help="planning problems per GPU")
     ap.add_argument("--nodes", type=int, default=100000, help="tree size at the start of the timed window")
@@ -114,8 +120,10 @@ class ClockSampler:
 # the two places allowed to execute it)
 
 def _cpu_worker_snapshot(args):
-    """Times the numpy port for ~seconds on a tree snapshot; returns (iters, elapsed)."""
-    path, env_idx, seconds = args
+    """Continues the numpy port from a tree snapshot: first `parity_iters` iterations (their result is returned for
+    the parity check against the GPU continuing from the same snapshot), then on until `seconds` have passed.
+    Returns (iterations, elapsed, n, parents, vertices-after-parity_iters)."""
+    path, env_idx, seconds, parity_iters = args
     from nirrt_star_b200.synthetic import make_problem_3d
     from oracle.numpy_port import RRTStar3DPort
     d = np.load(path)
@@ -125,33 +133,38 @@ def _cpu_worker_snapshot(args):
     n = int(d["n"])
     port = RRTStar3DPort(pr, n + 20000, rng=rs)
     port.load_tree(d["v"][:n], d["p"][:n])
-    port.run(3)
     t0 = time.perf_counter(); it = 0
+    for _ in range(parity_iters):
+        port.iterate(); it += 1
+    pn = int(port.num_vertices)
+    pp = np.array(port.vertex_parents[:pn], dtype=np.int64)
+    pv = np.array(port.vertices[:pn], dtype=np.float64)
     while time.perf_counter() - t0 < seconds:
         port.iterate(); it += 1
-    return it, time.perf_counter() - t0
+    return it, time.perf_counter() - t0, pn, pp, pv
 
 
-def cpu_baseline_from_snapshot(bp, v, p, n, rng_states, env_base, seconds):
+def cpu_baseline_from_snapshot(E, v, p, n, rng_states, env_base, seconds, parity_iters):
     cores = os.cpu_count() or 1
-    workers = min(cores, bp.E)
+    workers = min(cores, E)
     tmp = tempfile.mkdtemp(prefix="nirrt_cpu_")
     jobs = []
     for k in range(workers):
         path = os.path.join(tmp, f"env{k}.npz")
         np.savez(path, v=v[k], p=p[k], n=n[k], key=rng_states[k][0], pos=rng_states[k][1])
-        jobs.append((path, env_base + k, seconds))
+        jobs.append((path, env_base + k, seconds, parity_iters))
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(workers) as pool:
         res = pool.map(_cpu_worker_snapshot, jobs)
     wall = time.perf_counter() - t0
-    rate = sum(it / el for it, el in res)
-    return {"value": rate, "unit": UNIT, "cores": workers, "kind": "port",
+    rate = sum(r[0] / r[1] for r in res)
+    base = {"value": rate, "unit": UNIT, "cores": workers, "kind": "port",
             "sample": f"{workers} problems (one per host core) x ~{seconds:.0f} s of the numpy port of the reference "
                       f"loop body, continuing from the same {int(n[0])}-vertex GPU-grown trees and RNG states; "
-                      f"{sum(it for it, _ in res)} iterations in {wall:.0f} s wall",
+                      f"{sum(r[0] for r in res)} iterations in {wall:.0f} s wall",
             "per_core": rate / workers}
+    return base, [(r[2], r[3], r[4]) for r in res]
 
 
 def _ref_worker(conn, env_idx, seed, nodes):
@@ -197,8 +210,12 @@ def run_reference_arm(args):
     rates = []
     for c in conns:
         tag, rate, n = c.recv(); rates.append(rate)
-    # bounded sample: iterations per worker per step so that the whole run takes ~2 minutes
-    per_step = max(1, int(120.0 * min(rates) / max(1, args.steps + args.warmup)))
+    # One step = the same block of iterations per problem as our arm's step (--iters-per-step), one problem per
+    # host core.  Only if that would take more than ~4 minutes in total is the block shortened (and reported).
+    per_step = args.iters_per_step
+    budget_s = 240.0
+    if per_step * (args.steps + args.warmup) / max(1e-9, min(rates)) > budget_s:
+        per_step = max(1, int(budget_s * min(rates) / max(1, args.steps + args.warmup)))
 
     def step():
         for c in conns:
@@ -216,12 +233,13 @@ def run_reference_arm(args):
         c.send("stop")
     value = cores * per_step * args.steps / el
     sample = (f"{cores} processes (one per host core), each a {args.nodes}-vertex RRT* tree grown by the C oracle; "
-              f"one step = {per_step} numpy-port iteration(s) per process")
+              f"one step = {per_step} numpy-port iterations per process")
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"rrt_star 3D random_3d, {args.nodes}-node trees, CPU numpy port of the reference loop body",
-                      "nodes": args.nodes, "iters_per_step_per_process": per_step},
+                      "nodes": args.nodes, "iters_per_step": per_step, "problems": cores,
+                      "iters_per_step_requested": args.iters_per_step},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -372,19 +390,19 @@ def main():
             print(json.dumps(pn2), flush=True)
         return
 
-    E, nodes, K, W = args.envs, args.nodes, args.steps, args.warmup
+    E, nodes, K, W, ips = args.envs, args.nodes, args.steps, args.warmup, args.iters_per_step
     env_base = rank * E
     problems = [make_problem_3d(env_base + i) for i in range(E)]
     seeds = [5000 + env_base + i for i in range(E)]
-    slack = W + 3 * K + 4096
-    bp = B.BatchPlanner3D(problems, nodes + slack, seeds=seeds, device=local, record_capacity=K + W + 64)
+    slack = (W + K) * ips + 4096
+    bp = B.BatchPlanner3D(problems, nodes + slack, seeds=seeds, device=local, record_capacity=(K + W) * ips + 64)
 
     # ---- untimed: grow every tree to exactly `nodes` vertices with the CUDA planner itself
     t_grow0 = time.perf_counter()
     bp.begin(B.VARIANT_RRT_STAR, B.MODE_PLANNING, 1 << 30)
     bp.set_vertex_limit(nodes)
     while True:
-        bp.run(4000)
+        bp.run(4096)
         _, _, nv = bp.env_state()
         if nv.min() >= nodes:
             break
@@ -397,20 +415,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # snapshot (host, pinned) for the e2e leg and the CPU baseline
-    snap = None
-    if not args.no_e2e or (rank == 0 and not args.no_cpu_baseline):
-        v_pin = torch.empty((E, bp.capacity, 3), dtype=torch.float64, pin_memory=True)
-        p_pin = torch.empty((E, bp.capacity), dtype=torch.int64, pin_memory=True)
-        v_np, p_np = v_pin.numpy(), p_pin.numpy()
-        _, _, n_np = bp.read_trees(out=(v_np, p_np))
-        snap = (v_np, p_np, n_np, bp.get_rng())
+    # host snapshot (pinned) of the grown trees + RNG streams: every leg below starts from it
+    v_pin = torch.empty((E, bp.capacity, 3), dtype=torch.float64, pin_memory=True)
+    p_pin = torch.empty((E, bp.capacity), dtype=torch.int64, pin_memory=True)
+    v_np, p_np = v_pin.numpy(), p_pin.numpy()
+    _, _, n_np = bp.read_trees(out=(v_np, p_np))
+    rng_states = bp.get_rng()
 
-    # ---- timed: core variant (planning() loop body)
+    def restore():
+        bp.load_trees(v_np, p_np, n_np)
+        bp.set_rng(rng_states)
+
+    # ---- timed: K steps of `ips` iterations each (device-resident)
     def timed_region(variant_mode):
-        bp.begin(B.VARIANT_RRT_STAR, variant_mode, 1 << 30, 1 << 30)
-        bp.run(W)
+        restore()
+        bp.begin(B.VARIANT_RRT_STAR, variant_mode, 1 << 30, 1 << 30)     # builds (or finds) the iteration graph: untimed
+        for _ in range(W):
+            bp.run(ips)
         _, _, n0 = bp.env_state()
+        g0 = bp.graph_stats()
         barrier()
         sampler = ClockSampler(local); sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -418,7 +441,8 @@ def main():
         if args.profile_range:
             torch.cuda.profiler.start()
         ev0.record()
-        bp.run(K)
+        for _ in range(K):
+            bp.run(ips)
         ev1.record()
         if args.profile_range:
             torch.cuda.synchronize()
@@ -431,20 +455,24 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         _, _, n1 = bp.env_state()
-        return ms, clocks, bp.kernel_launches() - launches0, n0, n1
+        g1 = bp.graph_stats()
+        graph = {"built_inside_timed_region": g1["builds"] - g0["builds"], "replays": g1["replays"] - g0["replays"],
+                 "fallbacks": g1["fallbacks"]}
+        return ms, clocks, bp.kernel_launches() - launches0, n0, n1, graph
 
-    ms_core, clocks, launches, n0, n1 = timed_region(B.MODE_PLANNING)
-    value = world * E * K / (ms_core / 1e3)
+    ms_core, clocks, launches, n0, n1, graph_core = timed_region(B.MODE_PLANNING)
+    value = world * E * K * ips / (ms_core / 1e3)
     if args.core_only:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_core / K, "core_only": True}))
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_core / K,
+                              "ms_per_iteration": ms_core / K / ips, "graph": graph_core, "core_only": True}))
         return
 
-    # ---- roofline attribution: same steps with an event bracket around every launch
-    prof_iters = min(K, 200)
+    # ---- roofline attribution: same iterations with an event bracket around every launch
+    prof_iters = min(K * ips, 200)
     prof = bp.run_profiled(prof_iters)
     _, _, n2 = bp.env_state()
-    bpv = bp.scan_bytes_per_vertex()      # layout actually scanned: 12 B (f32 mirror) or 24 B (f64) per vertex
+    bpv = bp.scan_bytes_per_vertex()      # layout actually scanned: 6 B (u16 mirror), 12 B (f32 mirror) or 24 B (f64) per vertex
     scan_bytes = float(0.5 * (n1.astype(np.float64).sum() + n2.astype(np.float64).sum()) * bpv)
     peak = float(peaks.get("hbm_gbs", 6650.0))
     t_near_ms = prof["nearest"] / prof_iters
@@ -455,7 +483,10 @@ def main():
     except Exception:
         pass
     step_ms = sum(prof.values()) / prof_iters
-    kernel_names = {6: "k_nearest_m<3,u16>: ONE pass over the u16 fixed-point mirror does the Nearest argmin filter and collects the "
+    ms_iter = ms_core / K / ips
+    kernel_names = {4: "k_nearest_p<3>: ONE pass over the 10-10-10 packed mirror (4 B / vertex) does the Nearest argmin filter and collects "
+                       "the speculative Near ball around x_rand; exact f64 re-check of the few candidates in k_expand",
+                    6: "k_nearest_m<3,u16>: ONE pass over the u16 fixed-point mirror does the Nearest argmin filter and collects the "
                        "speculative Near ball around x_rand; exact f64 re-check of the few candidates in k_expand",
                     12: "k_nearest_m<3,f32> (Nearest + speculative Near over the f32 SoA mirror, exact f64 re-check of the candidates)",
                     24: "k_nearest (Nearest argmin scan, f64 SoA)"}
@@ -467,20 +498,21 @@ def main():
                 "scans_per_iteration": 1 if fused_near else 2,
                 "near_scan": None if fused_near else {"achieved": scan_bytes / (prof["near"] / prof_iters * 1e-3) / 1e9,
                                                       "frac": scan_bytes / (prof["near"] / prof_iters * 1e-3) / 1e9 / peak},
-                "whole_step_hbm_frac": (1 if fused_near else 2) * scan_bytes / (ms_core / K * 1e-3) / 1e9 / peak,
-                "kernel_ms_per_step": {k: v / prof_iters for k, v in prof.items()},
-                "kernel_share_of_step": {k: v / prof_iters / step_ms for k, v in prof.items()},
+                "whole_step_hbm_frac": (1 if fused_near else 2) * scan_bytes / (ms_iter * 1e-3) / 1e9 / peak,
+                "kernel_ms_per_iteration": {k: v / prof_iters for k, v in prof.items()},
+                "kernel_share_of_iteration": {k: v / prof_iters / step_ms for k, v in prof.items()},
                 "attribution": "event bracket around each of k_top / scan / k_steer / k_expand launched UNFUSED and serialised over all "
-                               "problems; the timed region runs them as 2 fused kernels per iteration on 8 overlapped groups"}
+                               "problems, one launch per iteration; the timed region runs them as 2 fused kernels per iteration on "
+                               "overlapped groups of problems, replayed from a CUDA graph"}
 
     # ---- eval variant (planning_random body: + search_goal_parent / path length every iteration)
-    ms_eval, _, _, _, _ = timed_region(B.MODE_PLANNING_RANDOM)
-    value_eval = world * E * K / (ms_eval / 1e3)
+    ms_eval, _, _, _, _, graph_eval = timed_region(B.MODE_PLANNING_RANDOM)
+    value_eval = world * E * K * ips / (ms_eval / 1e3)
 
-    # ---- e2e through the C ABI with host buffers: snapshot H2D + K iterations + results D2H
+    # ---- e2e through the C ABI with host buffers: one job = trees + RNG streams H2D, K steps each followed by the
+    # D2H read of the per-problem status rows a caller polls, then trees + goal parents D2H
     e2e = None
     if not args.no_e2e:
-        v_np, p_np, n_np, rng_states = snap
         out_v = torch.empty((E, bp.capacity, 3), dtype=torch.float64, pin_memory=True).numpy()
         out_p = torch.empty((E, bp.capacity), dtype=torch.int64, pin_memory=True).numpy()
         reps = 2
@@ -493,8 +525,9 @@ def main():
             bp.set_rng(rng_states)                               # H2D: RNG streams
             t1 = time.perf_counter()
             bp.begin(B.VARIANT_RRT_STAR, B.MODE_PLANNING, 1 << 30)
-            bp.run(K)
-            torch.cuda.synchronize()
+            for _ in range(K):
+                bp.run(ips)
+                bp.env_state()                                   # D2H: per-problem state / record count / vertex count
             t2 = time.perf_counter()
             bp.read_trees(out=(out_v, out_p))                    # D2H: vertices / parents / num_vertices
             gp, cost = bp.goal_parents()                         # D2H: goal parent + path cost per problem
@@ -508,10 +541,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             best = float(t.item())
         h2d = float((n_np.astype(np.float64) * 32).sum() + E * 625 * 4)
-        d2h = float(E * bp.capacity * 32 + E * 16)
-        e2e = {"value": world * E * K / best, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+        d2h = float(E * bp.capacity * 32 + E * 16 + K * E * 12)
+        e2e = {"value": world * E * K * ips / best, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                "seconds": best, "breakdown": parts,
-               "what": "nirrt_batch_load_trees + set_rng (pinned host -> HBM) + K iterations + read_trees + goal_parents (HBM -> pinned host)"}
+               "what": "nirrt_batch_load_trees + set_rng (pinned host -> HBM), K x (nirrt_batch_run(iters_per_step) + "
+                       "nirrt_batch_env_state_sync), read_trees + goal_parents (HBM -> pinned host)"}
 
     # ---- the one collective: gather per-problem result rows on every rank (NCCL all_gather,
     # nirrt_star_b200/shard.py -- the same code path the gloo CPU tests exercise)
@@ -524,9 +558,23 @@ def main():
     solved = int(sum(1 for r in rows if np.isfinite(r[0])))
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v_np, p_np, n_np, rng_states = snap
-        cpu = cpu_baseline_from_snapshot(bp, v_np, p_np, n_np, rng_states, env_base, args.cpu_seconds)
+        M = args.parity_iters
+        cpu, cpu_trees = cpu_baseline_from_snapshot(E, v_np, p_np, n_np, rng_states, env_base, args.cpu_seconds, M)
+        # parity at the benchmark size: the GPU continues from the SAME snapshot for the same M iterations
+        restore()
+        bp.begin(B.VARIANT_RRT_STAR, B.MODE_PLANNING, 1 << 30)
+        bp.run(M)
+        gv, gpar, gn = bp.read_trees(env_begin=0, count=len(cpu_trees))
+        same = 0
+        for k, (cn, cp, cv) in enumerate(cpu_trees):
+            if gn[k] == cn and np.array_equal(gpar[k, :cn], cp) and np.array_equal(gv[k, :cn], cv):
+                same += 1
+        parity = {"problems": len(cpu_trees), "iterations": M, "vertices_at_start": int(n_np[0]),
+                  "identical": same == len(cpu_trees), "identical_problems": same,
+                  "what": "parents and vertices (bit-exact) of the CUDA planner vs the numpy port, both continued from the same "
+                          "GPU-grown snapshot and RNG states"}
 
     pn2 = None
     if not args.no_pointnet2:
@@ -535,17 +583,19 @@ def main():
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": ms_core / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": ms_core / K, "ms_per_iteration": ms_core / K / ips, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic",
                "config": {"workload": f"rrt_star 3D random_3d (BASELINE configs[4] per-GPU shard): {E} problems/GPU in lock step, "
-                                      f"{nodes}-node trees, planning() loop body",
-                          "envs_per_gpu": E, "nodes_at_window_start": int(n0.min()), "nodes_at_window_end": int(n1.max()),
+                                      f"{nodes}-node trees, planning() loop body, {ips} iterations per step",
+                          "envs_per_gpu": E, "iters_per_step": ips, "nodes_at_window_start": int(n0.min()), "nodes_at_window_end": int(n1.max()),
                           "l2": "inputs larger than L2: every step streams %.2f GB of mirror coordinates (all problems, all groups) "
                                 "through the 126 MB L2, no flush needed" % (scan_bytes / 1e9),
                           "tree_growth": "grown 1 -> %d vertices by the same CUDA planner, untimed (%.0f s)" % (nodes, grow_s),
                           "timing": "CUDA events on the launch stream, barrier + synchronize both sides, max over ranks"},
-               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-               "eval_variant": {"value": value_eval, "unit": UNIT, "ms_per_step": ms_eval / K,
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "graph": graph_core, "roofline": roofline,
+               "cpu_baseline": cpu, "parity_at_100k": parity,
+               "eval_variant": {"value": value_eval, "unit": UNIT, "ms_per_step": ms_eval / K, "ms_per_iteration": ms_eval / K / ips,
+                                "graph": graph_eval,
                                 "what": "planning_random loop body (adds goal-parent search + path length per iteration)"},
                "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2}
         print(json.dumps(out), flush=True)

@@ -51,7 +51,11 @@ typedef struct nirrt_batch_desc {
     int n_envs;         /* E: independent planning problems advanced in lock step */
     int capacity;       /* vertices per problem = 1 + iter_max (rrt_base_3d.py:25) */
     int record_capacity;/* per-problem path_len_list rows (>= iter_max + iter_after_initial + 2) */
-    int near_capacity;  /* per-problem Near candidate buffer (entries); 0 = default 2048 */
+    int near_capacity;  /* per-problem candidate buffer (entries) of the PRE-FILTER superset of Near
+                           (speculative ball + mirror margin); 0 = default 1024.  An iteration handles at most 1024
+                           candidates (shared-memory staging); larger values only enlarge the result buffer of
+                           nirrt_within_sync.  Overflow is a hard error (NIRRT_ERR_CAPACITY) reported by
+                           nirrt_batch_status_sync, never a silent truncation. */
     int device;         /* CUDA device ordinal */
 } nirrt_batch_desc;
 
@@ -125,7 +129,8 @@ int nirrt_batch_set_stop_threshold(nirrt_batch *b, double stop_below);
 
 /* Enqueues `iters` lock-step iterations of the loop body on every problem that is still running
  * (Sample -> Nearest scan -> Steer + collision -> Near scan -> ChooseParent/Rewire/goal work).
- * Problems that finished their driver idle.  No host synchronisation. */
+ * Problems that finished their driver idle.  No host synchronisation.  Blocks of 16 iterations replay from
+ * the CUDA graph nirrt_batch_begin built for this variant/mode; a run never builds a graph it can find. */
 int nirrt_batch_run(nirrt_batch *b, int iters, void *stream);
 
 /* Benchmark pre-growth: while limit > 0, problems whose tree already holds `limit` vertices idle
@@ -184,6 +189,10 @@ int nirrt_fps_f64_sync(const double *points, int64_t n, int npoint, int start, i
 
 /* Device-resident benchmark hooks: bytes scanned per Nearest+Near pass and launch counters. */
 int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *scan_bytes_per_vertex);
+/* CUDA-graph bookkeeping of nirrt_batch_run: executables built (one per variant/mode, by nirrt_batch_begin),
+ * graph replays launched, and capture failures (each one downgrades the batch to plain kernel launches --
+ * a performance regression that is otherwise invisible). */
+int nirrt_batch_graph_stats(nirrt_batch *b, int64_t *builds, int64_t *replays, int64_t *fallbacks);
 /* Times `reps` back-to-back launches of ONE scan kernel (0 = Nearest, 1 = Near) on the batch's
  * current trees with CUDA events on `stream`; returns average milliseconds per launch in *ms and
  * the vertex-coordinate bytes one launch reads in *bytes. */

@@ -40,11 +40,12 @@ def lib():
         return _LIB
     path = _build.LIB
     if not os.path.exists(path) or _build.needs_build():
+        # sources newer than the binary (or no binary): rebuild under a file lock (several ranks may get here at
+        # once); a stale binary is never loaded silently -- its ABI may no longer match the argtypes below
         try:
-            _build.build()
+            _build.build_locked()
         except Exception as exc:  # pragma: no cover - build environment problem
-            if not os.path.exists(path):
-                raise NirrtError(f"libnirrt_b200.so is missing and could not be built: {exc}") from exc
+            raise NirrtError(f"libnirrt_b200.so is missing or older than its sources and could not be rebuilt: {exc}") from exc
     L = C.CDLL(path)
     V = C.c_void_p
     L.nirrt_last_error.restype = C.c_char_p
@@ -80,6 +81,7 @@ def lib():
     L.nirrt_batch_set_vertex_limit.argtypes = [V, C.c_int]
     L.nirrt_batch_run_profiled_sync.argtypes = [V, C.c_int, c_fp, V]
     L.nirrt_batch_counters.argtypes = [V, c_i64p, c_i64p]
+    L.nirrt_batch_graph_stats.argtypes = [V, c_i64p, c_i64p, c_i64p]
     L.nirrt_batch_time_scan_sync.argtypes = [V, C.c_int, C.c_int, c_fp, c_i64p, V]
     # PointNet++ (include/nirrt_pointnet2.h)
     c_i32p = C.POINTER(C.c_int32)

@@ -329,6 +329,12 @@ class BatchPlanner3D:
         check(self.L.nirrt_batch_counters(self.h, C.byref(n), None))
         return n.value
 
+    def graph_stats(self):
+        """{builds, replays, fallbacks} of the CUDA-graph replay path (a fallback = capture failed, plain launches)."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(self.L.nirrt_batch_graph_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"builds": a.value, "replays": b.value, "fallbacks": c.value}
+
     def scan_bytes_per_vertex(self):
         """bytes one scan pass reads per vertex: 2*dim with the u16 mirror (default), 4 with the u8 mirror,
         4*dim with the f32 mirror, 8*dim without a mirror"""

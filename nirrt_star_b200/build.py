@@ -37,10 +37,23 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
+def build_locked():
+    """build() under an exclusive file lock: concurrent ranks wait for the first one instead of all writing
+    csrc/*.o and the library at once; whoever gets the lock second finds nothing left to do."""
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build(force=False)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     objs = []
+    tmp_lib = LIB + f".tmp{os.getpid()}"
     for name, extra in UNITS:
         obj = os.path.join(CSRC, name.replace(".cu", ".o"))
         cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -49,7 +62,8 @@ def build(force=False, verbose=False):
             cmd += ["-Xptxas", "-v"]
         subprocess.check_call(cmd)
         objs.append(obj)
-    subprocess.check_call([_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+    subprocess.check_call([_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp_lib] + objs)
+    os.replace(tmp_lib, LIB)      # atomic: a concurrent loader sees the old or the new library, never a partial one
     return LIB
 
 

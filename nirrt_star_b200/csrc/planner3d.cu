@@ -105,9 +105,21 @@ struct __align__(16) IterScratch {
     int pad1;
 };
 
+// Driver parameters of the current run.  They live in the per-problem control block (written by k_set_budget at
+// the start of every nirrt_batch_run), NOT in the by-value View: changing them never invalidates a captured
+// CUDA graph (see ensure_graph).
+struct RunCfg {
+    int iter_max, iter_after;
+    int n_limit;       // > 0: problems whose tree reached n_limit vertices idle (benchmark pre-growth)
+    int pad;
+    double stop_below; // phase 1 ends when the recorded value drops below this (+inf: planning_random; finite: planning_block_gap)
+    double pc_rate, pc_ratio;
+};
+
 struct __align__(16) EnvCtl {
     ScanHdr hdr0;       // Nearest scan header (query x_rand)
     IterScratch s[2];
+    RunCfg cfg;
     // problem
     double start[3], goal[3];
     double step_len, search_radius;
@@ -140,10 +152,7 @@ struct View {
     int fuse_steer;  // k_expand starts with k_steer's work (warp 0): one kernel for everything between two scans
     int par;         // which IterScratch copy / cand2 half this launch works on (iteration parity when pipelined, else 0)
     int pipe;        // 1: pipelined RRT* driver (k_front does Steer + accounting + next sample, k_expand only expands)
-    int variant, mode, iter_max, iter_after;
-    double stop_below; // phase 1 ends when the recorded value drops below this (+inf: planning_random; finite: planning_block_gap)
-    int n_limit;     // > 0: problems whose tree reached n_limit vertices idle (benchmark pre-growth)
-    double pc_rate, pc_ratio;
+    int variant, mode;   // planner family / loop driver: select code paths, part of the graph cache key
     double *vx, *vy, *vz;
     float *fx, *fy, *fz;   // f32 mirror of the coordinates (scan layout, 4 B per coordinate); null = not in use
     unsigned short *ux, *uy, *uz;   // u16 fixed-point mirror (scan layout, 2 B per coordinate); null = not in use
@@ -659,7 +668,7 @@ template <int D>
 __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D>::type &g, bool g_staged, double *sm_s, int *sm_i) {
     EnvCtl *c = v.ctl + e;
     const int state = c->state, budget = c->budget;
-    if (state == ST_DONE || state == ST_WAIT_CLOUD || budget <= 0 || (v.n_limit > 0 && c->n >= v.n_limit)) {
+    if (state == ST_DONE || state == ST_WAIT_CLOUD || budget <= 0 || (c->cfg.n_limit > 0 && c->n >= c->cfg.n_limit)) {
         if (threadIdx.x == 0) set_idle(c);
         return;
     }
@@ -698,14 +707,14 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
         c->c_best = c_best;
         if (v.mode == NIRRT_MODE_PLANNING_RANDOM) {
             if (c->state == ST_PHASE1) {
-                if (c_best < v.stop_below) { c->state = ST_PHASE2; c->left = v.iter_after; }
-                else if (c->p1_done >= v.iter_max) { push_record(v, c, e, c_best); c->state = ST_DONE; set_idle(c); return; }
+                if (c_best < c->cfg.stop_below) { c->state = ST_PHASE2; c->left = c->cfg.iter_after; }
+                else if (c->p1_done >= c->cfg.iter_max) { push_record(v, c, e, c_best); c->state = ST_DONE; set_idle(c); return; }
             }
             if (c->state == ST_PHASE2 && c->left <= 0) { push_record(v, c, e, c_best); c->state = ST_DONE; set_idle(c); return; }
             push_record(v, c, e, c_best);
         }
     }
-    if (v.variant == 2 && fresh && c_best < XMUL(v.pc_ratio, c->c_update)) {
+    if (v.variant == 2 && fresh && c_best < XMUL(c->cfg.pc_ratio, c->c_update)) {
         // update_point_cloud (nirrt_star_png_3d.py:113-115): the host runs PointNet++ and resumes us
         c->c_update = c_best;
         c->saved_state = c->state;
@@ -721,7 +730,7 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
     double out[3];
     bool done = false;
     if (fam_cloud(v.variant)) {
-        if (rng.next_double() < v.pc_rate) {
+        if (rng.next_double() < c->cfg.pc_rate) {
             if (c->n_pc <= 0) { atomicOr(&c->err, ERR_EMPTY_CLOUD); c->state = ST_DONE; set_idle(c); rng.flush(); return; }
             const long long k = rng.randint(c->n_pc);
             const double *p = v.pc + ((size_t)e * v.pc_cap + k) * 3;
@@ -1010,7 +1019,7 @@ __global__ void __launch_bounds__(128) k_front(View v) {
     if (threadIdx.x == 0) {      // the accounting k_expand does at its end in the unpipelined flow
         c->budget--;
         c->p1_done++;
-        if (c->p1_done >= v.iter_max) c->state = ST_DONE;
+        if (c->p1_done >= c->cfg.iter_max) c->state = ST_DONE;
     }
     __syncthreads();
     top_body<D>(v, e, g, false, sm_s, sm_i);
@@ -1563,7 +1572,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             for (int i = tid; i < kNearSmem / 32; i += blockDim.x) s_rew[i] = 0;
             // stamp the Near members in their walk records: a walk recognises them from the record it loads anyway
             const TreeRef t = tree_of(v, e);
-            const int tag = (int)(c->stamp % 4194303u) + 1;
+            const int tag = (int)(c->stamp % 2097151u) + 1;   // <= 2^21 - 1: (tag << 10) | k stays a non-negative int
             for (int k = tid; k < m; k += blockDim.x)
                 __stcg(reinterpret_cast<int *>(t.links + s_near[k]) + 3, (tag << 10) | k);
             __syncthreads();
@@ -1729,8 +1738,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             push_record(v, c, e, len);
             if (c->state == ST_PHASE1) {
                 c->p1_done++;
-                if (len < v.stop_below) { c->state = ST_PHASE2; c->left = v.iter_after; if (c->left <= 0) c->state = ST_DONE; }
-                else if (c->p1_done >= v.iter_max) c->state = ST_DONE;
+                if (len < c->cfg.stop_below) { c->state = ST_PHASE2; c->left = c->cfg.iter_after; if (c->left <= 0) c->state = ST_DONE; }
+                else if (c->p1_done >= c->cfg.iter_max) c->state = ST_DONE;
             } else {
                 c->left--;
                 if (c->left <= 0) c->state = ST_DONE;
@@ -1741,7 +1750,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         c->budget--;
         if (v.mode == NIRRT_MODE_PLANNING) {
             c->p1_done++;
-            if (c->p1_done >= v.iter_max) c->state = ST_DONE;
+            if (c->p1_done >= c->cfg.iter_max) c->state = ST_DONE;
         } else {  // IRRT* family planning_random: counters only, phase switches happen in k_top
             if (c->state == ST_PHASE1) c->p1_done++; else c->left--;
         }
@@ -1818,9 +1827,9 @@ __global__ void k_begin(View v) {
     c->err = 0;
 }
 
-__global__ void k_set_budget(View v, int iters) {
+__global__ void k_set_budget(View v, int iters, RunCfg cfg) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < v.E) v.ctl[e].budget = iters;
+    if (e < v.E) { v.ctl[e].budget = iters; v.ctl[e].cfg = cfg; }
 }
 
 struct ProblemUpload {
@@ -2026,10 +2035,13 @@ struct nirrt_batch {
     View v;
     bool pdl;        // iteration kernels use programmatic dependent launch (NIRRT_PDL=0 disables)
     bool use_graph;  // steady-state iterations are replayed from a CUDA graph (NIRRT_GRAPH=0 disables)
-    cudaGraphExec_t gexec;
-    View gview;      // the View the graph was captured with
-    int64_t graph_launches;
+    // graph cache: one executable per distinct (View, pipelined) -- i.e. per (variant, mode) of this batch; the
+    // run parameters live in EnvCtl::cfg, so begin() with a known variant/mode re-uses its graph
+    struct GraphEntry { View view; bool pipelined; cudaGraphExec_t exec; int64_t launches; int64_t last_use; };
+    std::vector<GraphEntry> graphs;
+    int64_t graph_builds, graph_replays, graph_fallbacks, graph_clock;
     int graph_iters; // iterations per graph replay
+    RunCfg cfg;      // run parameters, handed to the device by k_set_budget at the start of every run
     cudaStream_t cs; // capture origin
     int device;
     size_t stride_bytes;
@@ -2046,7 +2058,6 @@ struct nirrt_batch {
     cudaEvent_t ev_fork, ev_join[kMaxGroups];
     // pipelined RRT* driver: second stream per group for k_expand, events per IterScratch copy
     bool pipeline;   // NIRRT_PIPELINE=0 disables
-    bool gpipe;      // the cached graph holds pipelined iterations
     cudaStream_t gs2[kMaxGroups];
     cudaEvent_t ev_a[kMaxGroups][2], ev_b[kMaxGroups][2];
     // pinned scratch for small synchronous reads
@@ -2117,7 +2128,7 @@ extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
         }
     }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
-    if (b->gexec) cudaGraphExecDestroy(b->gexec);
+    for (auto &g : b->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (b->cs) cudaStreamDestroy(b->cs);
     for (int i = 0; i < 2; i++) {
         if (b->xs[i]) cudaStreamDestroy(b->xs[i]);
@@ -2149,7 +2160,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     }
     // off by default: measured 77-79 us per step against 72 us unpipelined at 512 x 100k (the step is bound by the
     // SM time of the scan, not by the dependency chain); NIRRT_PIPELINE=1 enables it
-    { const char *pl = getenv("NIRRT_PIPELINE"); b->pipeline = pl && atoi(pl) == 1; b->gpipe = false; }
+    { const char *pl = getenv("NIRRT_PIPELINE"); b->pipeline = pl && atoi(pl) == 1; }
     for (int i = 0; i < 2; i++) { b->stage[i] = nullptr; b->xs[i] = nullptr; b->xe[i] = nullptr; }
     b->stage_n = nullptr; b->stage_envs = 0; b->xfork = nullptr;
     View &v = b->v;
@@ -2163,7 +2174,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         if (b->graph_iters > 256) b->graph_iters = 256;
         b->graph_iters &= ~1;      // even: a pipelined block ends on IterScratch copy 0
         b->use_graph = b->graph_iters > 0;
-        b->gexec = nullptr; b->graph_launches = 0; b->cs = nullptr;
+        b->graph_builds = b->graph_replays = b->graph_fallbacks = b->graph_clock = 0; b->cs = nullptr;
         const char *g = getenv("NIRRT_GROUPS");
         b->groups = g ? atoi(g) : (d->n_envs >= 512 ? 16 : (d->n_envs >= 256 ? 8 : (d->n_envs >= 128 ? 4 : (d->n_envs >= 64 ? 2 : 1))));
         if (b->groups < 1) b->groups = 1;
@@ -2175,7 +2186,8 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     v.rec_cap = d->record_capacity > 0 ? d->record_capacity : d->capacity + 8;
     v.sol_cap = v.rec_cap > v.cap + 8 ? v.rec_cap : v.cap + 8;   // at most one append per iteration
     v.pc_cap = 4096; v.path_cap = 4096;
-    v.pc_rate = 0.5; v.pc_ratio = 0.9; v.stop_below = (double)INFINITY;
+    memset(&b->cfg, 0, sizeof(RunCfg));
+    b->cfg.pc_rate = 0.5; b->cfg.pc_ratio = 0.9; b->cfg.stop_below = (double)INFINITY;
     const size_t EV = (size_t)v.E * v.stride;
     DALLOC(v.vx, double, EV); DALLOC(v.vy, double, EV);
     if (v.dim == 3) DALLOC(v.vz, double, EV);
@@ -2416,7 +2428,7 @@ extern "C" int nirrt_batch_get_rng_sync(nirrt_batch *b, uint32_t *key, int *pos,
 
 extern "C" int nirrt_batch_set_guidance(nirrt_batch *b, double pc_sample_rate, double pc_update_cost_ratio) {
     if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
-    b->v.pc_rate = pc_sample_rate; b->v.pc_ratio = pc_update_cost_ratio;
+    b->cfg.pc_rate = pc_sample_rate; b->cfg.pc_ratio = pc_update_cost_ratio;
     return NIRRT_OK;
 }
 
@@ -2584,6 +2596,9 @@ extern "C" int nirrt_batch_read_trees_sync(nirrt_batch *b, int env_begin, int co
     return NIRRT_OK;
 }
 
+static bool can_pipeline(const nirrt_batch *b);
+static nirrt_batch::GraphEntry *ensure_graph(nirrt_batch *b, bool pipelined);
+
 extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter_max, int iter_after_initial, void *stream) {
     if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
     if (variant < 0 || variant > 3 || mode < 0 || mode > 1 || iter_max < 0 || iter_after_initial < 0)
@@ -2591,8 +2606,8 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
     View &v = b->v;
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
-    v.variant = variant; v.mode = mode; v.iter_max = iter_max; v.iter_after = iter_after_initial;
-    v.stop_below = (double)INFINITY;
+    v.variant = variant; v.mode = mode; b->cfg.iter_max = iter_max; b->cfg.iter_after = iter_after_initial;
+    b->cfg.stop_below = (double)INFINITY;
     k_begin<<<(v.E + 127) / 128, 128, 0, s>>>(v);
     CHECK_LAUNCH();
     if (!fam_informed(variant) && mode == NIRRT_MODE_PLANNING_RANDOM) {
@@ -2600,16 +2615,22 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
         LAUNCH_D(v.dim, k_goal_init, v.E, 256, 0, s, v);
         CHECK_LAUNCH();
     }
+    // one-time cost of this (variant, mode): capture + instantiate + upload its iteration graph HERE, so that no
+    // nirrt_batch_run ever builds one in its steady state (a later begin() with the same variant/mode finds it)
+    ensure_graph(b, can_pipeline(b));
     return NIRRT_OK;
 }
 
-// first: this iteration's k_top has not run yet (start of a run); last: no iteration follows in this run
-static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count, bool first, bool last) {
+// One lock-step iteration of problems [env0, env0 + count) on stream s.  Every iteration is the same two launches
+// (scan + k_expand, whose tail draws the next sample): the run's first sample comes from one k_top launch in
+// nirrt_batch_run, and the tail of the run's last k_expand finds the iteration budget exhausted and idles the
+// problem (top_body) -- so a run of any length is k_top + uniform iterations, and whole blocks of them replay
+// from one CUDA graph.
+static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count) {
     View v = b->v;
     v.env0 = env0;
-    v.fuse_top = last ? 0 : 1;
+    v.fuse_top = 1;
     const bool pdl = b->pdl;
-    if (first) { launch_view(v.dim == 3 ? k_top<3> : k_top<2>, count, 128, s, v, false); b->launches += 1; }
     const bool mirror = has_mirror(v);   // mirror scans collect Near speculatively during the Nearest pass:
     v.fuse_steer = mirror ? 1 : 0;       // the iteration is two kernels, the scan and everything else
     launch_scan<false>(v, 0, count, s, pdl);
@@ -2622,12 +2643,20 @@ static int launch_iteration(nirrt_batch *b, cudaStream_t s, int env0, int count,
     return NIRRT_OK;
 }
 
+// the sample of a run's first iteration, all problems in one launch
+static void launch_top(nirrt_batch *b, cudaStream_t s) {
+    View v = b->v;
+    v.env0 = 0;
+    launch_view(v.dim == 3 ? k_top<3> : k_top<2>, v.E, 128, s, v, false);
+    b->launches += 1;
+}
+
 // `n` iterations of every group: fork from `s` to the group streams, launch, join back into `s`
-static int run_groups(nirrt_batch *b, cudaStream_t s, int n, bool first, bool last) {
+static int run_groups(nirrt_batch *b, cudaStream_t s, int n) {
     const View &v = b->v;
     if (n <= 0) return NIRRT_OK;
     if (b->groups == 1) {
-        for (int it = 0; it < n; it++) launch_iteration(b, s, 0, v.E, first && it == 0, last && it == n - 1);
+        for (int it = 0; it < n; it++) launch_iteration(b, s, 0, v.E);
         return NIRRT_OK;
     }
     const int G = b->groups;
@@ -2636,7 +2665,7 @@ static int run_groups(nirrt_batch *b, cudaStream_t s, int n, bool first, bool la
     for (int it = 0; it < n; it++)
         for (int g = 0; g < G; g++) {
             const int e0 = (int)((long long)v.E * g / G), e1 = (int)((long long)v.E * (g + 1) / G);
-            if (e1 > e0) launch_iteration(b, b->gs[g], e0, e1 - e0, first && it == 0, last && it == n - 1);
+            if (e1 > e0) launch_iteration(b, b->gs[g], e0, e1 - e0);
         }
     for (int g = 0; g < G; g++) {
         CUDA_TRY(cudaEventRecord(b->ev_join[g], b->gs[g]));
@@ -2686,33 +2715,54 @@ static int run_pipelined(nirrt_batch *b, cudaStream_t s, int m) {
     return NIRRT_OK;
 }
 
-// CUDA graph of b->graph_iters steady-state iterations of all groups (kernel arguments are the View by value,
-// so the graph is rebuilt whenever the View changed): one graph launch replaces 2-3 x groups x b->graph_iters
-// kernel launches, which keeps the host far ahead of the device even with many small groups.
-static bool ensure_graph(nirrt_batch *b, bool pipelined) {
-    if (!b->use_graph || b->groups < 2) return false;
-    if (b->gexec && b->gpipe == pipelined && memcmp(&b->gview, &b->v, sizeof(View)) == 0) return true;
-    if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
+// CUDA graph of b->graph_iters iterations of all groups: one graph launch replaces 2 x groups x graph_iters
+// kernel launches, which keeps the host far ahead of the device even with many small groups (and, for a single
+// small group, removes the per-launch cost from the latency-bound small-tree regime).  Kernel arguments are the
+// View by value, so there is one executable per distinct View -- in practice per (variant, mode): everything a
+// run changes (iteration counts, thresholds, vertex limit, guidance knobs) lives in EnvCtl::cfg.  Graphs are
+// built by nirrt_batch_begin (never inside a run that finds its graph) and kept for the life of the batch.
+constexpr size_t kMaxGraphs = 8;
+static nirrt_batch::GraphEntry *ensure_graph(nirrt_batch *b, bool pipelined) {
+    if (!b->use_graph || b->graph_iters < 2) return nullptr;
+    if (!b->cs) {
+        if (cudaStreamCreateWithFlags(&b->cs, cudaStreamNonBlocking) != cudaSuccess) { b->use_graph = false; b->graph_fallbacks++; return nullptr; }
+    }
+    for (auto &g : b->graphs)
+        if (g.pipelined == pipelined && memcmp(&g.view, &b->v, sizeof(View)) == 0) { g.last_use = ++b->graph_clock; return &g; }
+    if (b->graphs.size() >= kMaxGraphs) {       // evict the least recently used executable
+        size_t lru = 0;
+        for (size_t i = 1; i < b->graphs.size(); i++) if (b->graphs[i].last_use < b->graphs[lru].last_use) lru = i;
+        cudaGraphExecDestroy(b->graphs[lru].exec);
+        b->graphs.erase(b->graphs.begin() + lru);
+    }
     const int64_t launches0 = b->launches;
     cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
     bool ok = cudaStreamBeginCapture(b->cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
-        const int rc = pipelined ? run_pipelined(b, b->cs, b->graph_iters) : run_groups(b, b->cs, b->graph_iters, false, false);
+        const int rc = pipelined ? run_pipelined(b, b->cs, b->graph_iters) : run_groups(b, b->cs, b->graph_iters);
         const cudaError_t e = cudaStreamEndCapture(b->cs, &graph);
         ok = rc == NIRRT_OK && e == cudaSuccess && graph != nullptr;
     }
-    if (ok) ok = cudaGraphInstantiate(&b->gexec, graph, 0) == cudaSuccess;
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (ok) ok = cudaGraphUpload(exec, b->cs) == cudaSuccess && cudaStreamSynchronize(b->cs) == cudaSuccess;
     if (graph) cudaGraphDestroy(graph);
-    b->graph_launches = b->launches - launches0;     // kernels per replay
+    const int64_t per_replay = b->launches - launches0;     // kernels per replay
     b->launches = launches0;
-    if (!ok) {              // capture is an optimisation only: fall back to plain launches for this batch
+    if (!ok) {              // capture is an optimisation only: plain launches from here on, and the counter says so
         cudaGetLastError();
-        b->gexec = nullptr; b->use_graph = false;
-        return false;
+        if (exec) cudaGraphExecDestroy(exec);
+        b->use_graph = false;
+        b->graph_fallbacks++;
+        fprintf(stderr, "libnirrt_b200: CUDA graph capture failed; this batch falls back to plain kernel launches\n");
+        return nullptr;
     }
-    memcpy(&b->gview, &b->v, sizeof(View));     // byte copy: the comparison above is a memcmp
-    b->gpipe = pipelined;
-    return true;
+    nirrt_batch::GraphEntry g;
+    memcpy(&g.view, &b->v, sizeof(View));     // byte copy: the lookup above is a memcmp
+    g.pipelined = pipelined; g.exec = exec; g.launches = per_replay; g.last_use = ++b->graph_clock;
+    b->graphs.push_back(g);
+    b->graph_builds++;
+    return &b->graphs.back();
 }
 
 extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
@@ -2720,41 +2770,51 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     View &v = b->v;
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
-    k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
-    const int GI = b->graph_iters > 0 ? (b->graph_iters & ~1) : 0;     // even: a pipelined block ends on copy 0
+    k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters, b->cfg);
+    if (iters == 0) { CHECK_LAUNCH(); return NIRRT_OK; }
+    const int GI = b->graph_iters;
+    launch_top(b, s);
     if (can_pipeline(b) && iters >= 6) {
-        // first and last iteration unpipelined (k_top opens, the last k_expand samples nothing), an even
-        // number of pipelined iterations in between
-        TRY(run_groups(b, s, 1, true, false));
+        // first and last iteration unpipelined (the first consumes k_top's sample, the last k_expand finds the budget
+        // exhausted), an even number of pipelined iterations in between
+        TRY(run_groups(b, s, 1));
         const int mid = iters - 2, m = mid & ~1;
         int done = 0;
-        if (GI >= 2 && m >= GI && ensure_graph(b, true))
-            for (; done + GI <= m; done += GI) { CUDA_TRY(cudaGraphLaunch(b->gexec, s)); b->launches += b->graph_launches; }
+        if (GI >= 2 && m >= GI) {
+            if (nirrt_batch::GraphEntry *g = ensure_graph(b, true))
+                for (; done + GI <= m; done += GI) { CUDA_TRY(cudaGraphLaunch(g->exec, s)); b->launches += g->launches; b->graph_replays++; }
+        }
         TRY(run_pipelined(b, s, m - done));
-        TRY(run_groups(b, s, mid - m, false, false));
-        TRY(run_groups(b, s, 1, false, true));
-    } else if (GI >= 2 && iters >= GI + 2 && ensure_graph(b, false)) {
-        TRY(run_groups(b, s, 1, true, false));
-        const int mid = iters - 2;
-        for (int r = 0; r < mid / GI; r++) { CUDA_TRY(cudaGraphLaunch(b->gexec, s)); b->launches += b->graph_launches; }
-        TRY(run_groups(b, s, mid % GI, false, false));
-        TRY(run_groups(b, s, 1, false, true));
+        TRY(run_groups(b, s, mid - m + 1));
     } else {
-        TRY(run_groups(b, s, iters, true, true));
+        int done = 0;
+        if (GI >= 2 && iters >= GI) {
+            if (nirrt_batch::GraphEntry *g = ensure_graph(b, false))
+                for (; done + GI <= iters; done += GI) { CUDA_TRY(cudaGraphLaunch(g->exec, s)); b->launches += g->launches; b->graph_replays++; }
+        }
+        TRY(run_groups(b, s, iters - done));
     }
     CHECK_LAUNCH();
     return NIRRT_OK;
 }
 
+extern "C" int nirrt_batch_graph_stats(nirrt_batch *b, int64_t *builds, int64_t *replays, int64_t *fallbacks) {
+    if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
+    if (builds) *builds = b->graph_builds;
+    if (replays) *replays = b->graph_replays;
+    if (fallbacks) *fallbacks = b->graph_fallbacks;
+    return NIRRT_OK;
+}
+
 extern "C" int nirrt_batch_set_stop_threshold(nirrt_batch *b, double stop_below) {
     if (!b) return fail(NIRRT_ERR_INVALID, "null batch");
-    b->v.stop_below = stop_below;
+    b->cfg.stop_below = stop_below;
     return NIRRT_OK;
 }
 
 extern "C" int nirrt_batch_set_vertex_limit(nirrt_batch *b, int limit) {
     if (!b || limit < 0) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_vertex_limit: bad argument");
-    b->v.n_limit = limit;
+    b->cfg.n_limit = limit;
     return NIRRT_OK;
 }
 
@@ -2767,7 +2827,7 @@ extern "C" int nirrt_batch_run_profiled_sync(nirrt_batch *b, int iters, float *m
     cudaStream_t s = (cudaStream_t)stream;
     std::vector<cudaEvent_t> ev((size_t)iters * 6);
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
-    k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters);
+    k_set_budget<<<(v.E + 127) / 128, 128, 0, s>>>(v, iters, b->cfg);
     for (int it = 0; it < iters; it++) {
         cudaEvent_t *e = ev.data() + (size_t)it * 6;
         cudaEventRecord(e[0], s);

@@ -315,3 +315,72 @@ def test_tree_invariants_at_scale(B):
             for k in range(4):
                 assert np.array_equal(bp.within(e, q[k], 3.0), np.nonzero(np.linalg.norm(q[k] - ve, axis=-1) <= 3.0)[0])
     bp.close()
+
+
+def test_parity_at_100k_vertices(B):
+    """The benchmark regime itself (missing #3): trees of >= 100 000 vertices grown by the CUDA planner,
+    then BOTH sides continue from the same snapshot + RNG state -- the C oracle (pinned against the reference's
+    golden traces) and the GPU -- for the same window; parents and vertices must be bit-identical
+    (rrt_star_3d.py:36-55).  At n = 1e5 this exercises the u16 mirror margins, the speculative Near ball, the
+    candidate-band Nearest finish and the hint walks at the depth / density the bench runs them at."""
+    from oracle.planner_oracle import Oracle3D
+    E, nodes, window = 3, 100000, 384
+    problems = [make_problem_3d(400 + i) for i in range(E)]
+    seeds = [6100 + i for i in range(E)]
+    cap_iters = nodes + window + 64
+    bp = B.BatchPlanner3D(problems, cap_iters, seeds=seeds)
+    bp.begin(0, B.MODE_PLANNING, 1 << 30)
+    bp.set_vertex_limit(nodes)
+    for _ in range(200):
+        bp.run(4096)
+        _, _, nv = bp.env_state()
+        if nv.min() >= nodes:
+            break
+    bp.set_vertex_limit(0)
+    v, p, n = bp.read_trees()
+    assert n.min() >= nodes
+    states = bp.get_rng()
+    bp.begin(0, B.MODE_PLANNING, 1 << 30)
+    bp.run(window)
+    v2, p2, n2 = bp.read_trees()
+    assert bp.graph_stats()["fallbacks"] == 0
+    for e in range(E):
+        o = Oracle3D(problems[e], cap_iters, rng_state=states[e])
+        o.load_tree(v[e, :n[e]], p[e, :n[e]])
+        o.run(window, 0, 0)
+        ov, op = o.tree()
+        assert n2[e] == len(ov), e
+        assert np.array_equal(p2[e, :n2[e]], op), e
+        assert np.array_equal(v2[e, :n2[e]], ov), e
+    bp.close()
+
+
+def test_graph_is_built_by_begin_and_reused(B):
+    """nirrt_batch_run never captures a CUDA graph it can find: begin() builds one executable per (variant, mode),
+    a second begin() with the same pair re-uses it, changing the run parameters (vertex limit, stop threshold,
+    iteration counts) does not invalidate it, and graph replay == plain launches bit for bit."""
+    E, iters = 64, 160
+    problems = [make_problem_3d(500 + i) for i in range(E)]
+    seeds = [9000 + i for i in range(E)]
+    bp = B.BatchPlanner3D(problems, 3 * iters, seeds=seeds)
+    bp.begin(0, B.MODE_PLANNING, 3 * iters)
+    g = bp.graph_stats()
+    assert g == {"builds": 1, "replays": 0, "fallbacks": 0}
+    bp.run(iters)                                  # 160 = 10 replays of the 16-iteration graph
+    g = bp.graph_stats()
+    assert g["builds"] == 1 and g["replays"] == iters // 16 and g["fallbacks"] == 0
+    bp.set_vertex_limit(1 << 20); bp.set_stop_threshold(1e9)
+    bp.begin(0, B.MODE_PLANNING, 5 * iters, 7)
+    bp.run(iters - 3)                              # 9 replays + 13 plain iterations
+    g = bp.graph_stats()
+    assert g["builds"] == 1 and g["replays"] == iters // 16 + (iters - 3) // 16
+    bp.begin(1, B.MODE_PLANNING_RANDOM, iters, 10)
+    assert bp.graph_stats()["builds"] == 2
+    bp.begin(0, B.MODE_PLANNING, 3 * iters)
+    assert bp.graph_stats()["builds"] == 2
+    v, p, n = bp.read_trees()
+    bp.close()
+    ref = _run_batch(B, problems, seeds, 2 * iters - 3, 0, {"NIRRT_GRAPH": "0"})
+    assert np.array_equal(n, ref[2])
+    for e in range(E):
+        assert np.array_equal(p[e, :n[e]], ref[1][e, :n[e]]) and np.array_equal(v[e, :n[e]], ref[0][e, :n[e]])
