@@ -141,6 +141,8 @@ struct __align__(16) EnvCtl {
     int n_sol, n_goal, tree_changed, n_pc;
     long long last_gp;
     double last_len;
+    int best_k, pad_k;   // RRT* eval driver: slot of the current goal parent in the goal-candidate list (-1: none)
+    double best_val;     // its cost(vertex) + goal distance
     int err;
     unsigned stamp;   // k_expand invocations so far: tag of the Near stamps in the walk records
 };
@@ -174,6 +176,8 @@ struct View {
     int *sol;        // [E][sol_cap]  path_solutions
     int *gc_idx;     // [E][cap]      vertices within step_len of the goal (RRT* eval driver)
     double *gc_d;    // [E][cap]      their goal distance, +inf when the goal edge collides
+    double *gc_cost; // [E][cap]      cached cost(vertex) + goal distance (+inf when the goal edge collides), see goal_track
+    struct Kid *kid; // [E][stride]   child lists + goal-candidate slot of every vertex (RRT* eval driver), see goal_track
     double *records; // [E][rec_cap]
     double *pc;      // [E][pc_cap][3]
     double *pathseg; // [E][path_cap]
@@ -1377,44 +1381,223 @@ __device__ void bitonic_sort_int(int *a, int n_pow2) {
     }
 }
 
-// RRT* eval driver: best goal parent over the incrementally maintained goal-candidate list and the
-// numpy-ordered path length (rrt_base_3d.py:69-91).  Called by all threads; result in thread 0.
+// ---- RRT* eval driver (planning_random of RRT* / NRRT*, rrt_star_3d.py:200-270): search_goal_parent (:101-117) +
+// extract_path + get_path_len (rrt_base_3d.py:69-91) after EVERY iteration.
+// The reference re-scans the tree for vertices within step_len of the goal and re-walks cost() for each of them
+// (thousands at 1e5 vertices) every iteration.  Here:
+//   * the candidate list (ascending vertex index == np.where order) is maintained incrementally: a vertex enters it
+//     when it is inserted (coordinates never change), gc_d = its goal distance or +inf when the goal edge collides;
+//   * gc_cost[k] caches cost(vertex_k) + gc_d[k].  cost() of a vertex changes only when the vertex or one of its
+//     ancestors is re-parented, i.e. exactly for the subtrees below this iteration's re-wired vertices.  Every
+//     vertex carries a child list (Kid: first child + doubly linked siblings, kept current on insert / ChooseParent /
+//     Rewire), so those subtrees are enumerated (a few vertices on average) and only the goal candidates found in
+//     them are re-walked -- with the reference's own leaf -> root summation, so the cached values ARE what
+//     search_goal_parent would recompute;
+//   * the arg-min is np.argmin over the list == lexicographic (value, slot) minimum: the previous winner stays the
+//     minimum of the untouched candidates, so it is merged with the refreshed and the new ones; if the winner
+//     itself was refreshed the cached array is re-reduced (coalesced, no walks);
+//   * the path length only changes when the winner or its root path changed; otherwise the last value stands.
+struct __align__(16) Kid {
+    int head;    // first child, -1: leaf
+    int next;    // next sibling
+    int prev;    // previous sibling, -1: this vertex is its parent's first child
+    int gslot;   // slot in the goal-candidate list if the vertex is a candidate with a free goal edge, else -1
+};
+__device__ __forceinline__ Kid load_kid(const Kid *p) {
+    const int4 r = __ldcg(reinterpret_cast<const int4 *>(p));
+    Kid k; k.head = r.x; k.next = r.y; k.prev = r.z; k.gslot = r.w;
+    return k;
+}
+__device__ __forceinline__ void store_kid(Kid *p, int head, int next, int prev, int gslot) {
+    __stcg(reinterpret_cast<int4 *>(p), make_int4(head, next, prev, gslot));
+}
+// thread-serial list surgery (one thread per problem; L2-coherent accesses, the traversal reads after a barrier)
+__device__ __forceinline__ void kid_unlink(Kid *kid, int v, int old_parent) {
+    const Kid k = load_kid(kid + v);
+    if (k.prev >= 0) __stcg(&kid[k.prev].next, k.next); else __stcg(&kid[old_parent].head, k.next);
+    if (k.next >= 0) __stcg(&kid[k.next].prev, k.prev);
+}
+// makes v the first child of `parent`, whose current first child is `head`
+__device__ __forceinline__ void kid_link(Kid *kid, int v, int parent, int head) {
+    __stcg(&kid[v].next, head); __stcg(&kid[v].prev, -1);
+    if (head >= 0) __stcg(&kid[head].prev, v);
+    __stcg(&kid[parent].head, v);
+}
+
+// get_path_len(extract_path(gp)) (rrt_base_3d.py:69-91): row norms root -> goal, numpy pairwise summation.  One thread.
+template <int D>
+__device__ double goal_path_len_from(const View &v, EnvCtl *c, int e, const Node *nodes, int gp) {
+    int depth = 0;
+    for (int i = gp; i != 0; i = (int)load_node(nodes + i).parent) depth++;
+    const int M = depth + 1;
+    if (M > v.path_cap) { atomicOr(&c->err, ERR_PATH_DEPTH); return XINF; }
+    double *seg = v.pathseg + (size_t)e * v.path_cap;
+    Node cur = load_node(nodes + gp);
+    seg[M - 1] = row_norm<D>(XSUB(c->goal[0], cur.x), XSUB(c->goal[1], cur.y), XSUB(c->goal[2], cur.z));
+    int idx = gp;
+    for (int j = 0; idx != 0; j++) {
+        const int par = (int)cur.parent;
+        const Node p = load_node(nodes + par);
+        seg[M - 2 - j] = row_norm<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
+        idx = par; cur = p;
+    }
+    return (M == 1) ? seg[0] : XADD(seg[0], pairwise_sum(seg + 1, M - 1));
+}
+
+// Full evaluation: walks every candidate, refreshes the cache, arg-min, path length.  Called by all threads (any block
+// size); result in thread 0, which also updates the problem's bookkeeping.
 template <int D>
 __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nodes, double *sm_s, int *sm_i) {
     const int ng = c->n_goal;
-    if (ng == 0) { if (threadIdx.x == 0) c->last_gp = -1; return XINF; }
+    if (ng == 0) {
+        if (threadIdx.x == 0) { c->last_gp = -1; c->best_k = -1; c->best_val = XINF; c->last_len = XINF; }
+        return XINF;
+    }
     const int *gi = v.gc_idx + (size_t)e * v.cap;
     const double *gd = v.gc_d + (size_t)e * v.cap;
+    double *gcst = v.gc_cost + (size_t)e * v.cap;
     double bs = XINF; int bk = INT_MAX;
     for (int k = threadIdx.x; k < ng; k += blockDim.x) {
         const double d = gd[k];
         const double val = (d < XINF) ? XADD(cost_walk<D>(tree_of(v, e), gi[k]), d) : XINF;
+        __stcg(gcst + k, val);
         lexmin(bs, bk, val, k);
     }
     block_lexmin(bs, bk, sm_s, sm_i);
     double len = XINF;
     if (threadIdx.x == 0) {
         const int gp = gi[bk];
-        c->last_gp = gp;
-        int depth = 0;
-        for (int i = gp; i != 0; i = (int)load_node(nodes + i).parent) depth++;
-        const int M = depth + 1;
-        if (M > v.path_cap) { atomicOr(&c->err, ERR_PATH_DEPTH); }
-        else {
-            double *seg = v.pathseg + (size_t)e * v.path_cap;
-            Node cur = load_node(nodes + gp);
-            seg[M - 1] = row_norm<D>(XSUB(c->goal[0], cur.x), XSUB(c->goal[1], cur.y), XSUB(c->goal[2], cur.z));
-            int idx = gp;
-            for (int j = 0; idx != 0; j++) {
-                const int par = (int)cur.parent;
-                const Node p = load_node(nodes + par);
-                seg[M - 2 - j] = row_norm<D>(XSUB(cur.x, p.x), XSUB(cur.y, p.y), XSUB(cur.z, p.z));
-                idx = par; cur = p;
-            }
-            len = (M == 1) ? seg[0] : XADD(seg[0], pairwise_sum(seg + 1, M - 1));
-        }
+        len = goal_path_len_from<D>(v, c, e, nodes, gp);
+        c->last_gp = gp; c->best_k = bk; c->best_val = bs; c->last_len = len;
     }
     return len;
+}
+
+constexpr int kFrontMax = 512;   // subtree traversal frontier (two of them live in k_expand's candidate staging)
+constexpr int kDirtyMax = 512;   // goal candidates refreshed individually per iteration; more: full evaluation
+
+// One iteration's goal bookkeeping of the RRT* eval driver (see the comment above Kid).  Called by all threads of
+// k_expand after ChooseParent / Rewire have been applied.
+//   s_near / s_par / s_rew: Near list, each member's parent BEFORE this iteration, and the Rewire decisions (bit k)
+//   par_new_old: parent of x_new's vertex before ChooseParent when it re-used an existing vertex (duplicate guard)
+//   s_front (2 * kFrontMax ints) and s_dirty (kDirtyMax ints): scratch
+template <int D, typename G>
+__device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const TreeRef &t, const Node *nodes,
+                           int new_idx, bool inserted, bool new_moved, int m, const int *s_near, const int *s_par,
+                           const unsigned *s_rew, int par_new_old, bool have_cnew, double c_new, const double *xnew,
+                           int *s_front, int *s_dirty, double *sm_s, int *sm_i) {
+    __shared__ int s_cnt[4];     // [0] next frontier size, [1] dirty candidates, [2] overflow, [3] slot of the new candidate / -1
+    Kid *kid = v.kid + (size_t)e * v.stride;
+    int *gi = v.gc_idx + (size_t)e * v.cap;
+    double *gd = v.gc_d + (size_t)e * v.cap;
+    double *gcst = v.gc_cost + (size_t)e * v.cap;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int ns = 0, newk = -1, gslot_new = -1;
+        bool ovf = false;
+        if (inserted) {
+            const double gx = XSUB(c->goal[0], xnew[0]), gy = XSUB(c->goal[1], xnew[1]), gz = XSUB(c->goal[2], xnew[2]);
+            const double s2 = scan_sq<D>(gx, gy, gz);
+            // dist_to_goal <= step_len (rrt_star_3d.py:103-104 / rrt_star_2d.py:103-104)
+            if (s2 <= c->T_goal && (D == 3 || np_hypot(gx, gy) <= c->step_len)) {
+                newk = c->n_goal;
+                const bool hit = seg_collides(g, xnew, c->goal);
+                gi[newk] = new_idx;
+                gd[newk] = hit ? XINF : (D == 3 ? XSQRT(s2) : np_hypot(gx, gy));
+                c->n_goal = newk + 1;
+                if (!hit) gslot_new = newk;
+            }
+            // the new vertex under its final parent (after ChooseParent)
+            const int pn = load_link(t.links + new_idx).parent;
+            const int h = __ldcg(&kid[pn].head);
+            store_kid(kid + new_idx, -1, h, -1, gslot_new);
+            if (h >= 0) __stcg(&kid[h].prev, new_idx);
+            __stcg(&kid[pn].head, new_idx);
+        } else if (new_moved) {
+            // the duplicate guard re-used an existing vertex and ChooseParent moved it: its whole subtree got cheaper
+            const int pn = load_link(t.links + new_idx).parent;
+            kid_unlink(kid, new_idx, par_new_old);
+            kid_link(kid, new_idx, pn, __ldcg(&kid[pn].head));
+            s_front[ns++] = new_idx | 0x40000000;
+        }
+        bool any = false;
+        for (int w = 0; w < (m + 31) / 32 && !any; w++) any = s_rew[w] != 0u;
+        if (any) {
+            int head = inserted ? -1 : __ldcg(&kid[new_idx].head);
+            for (int k = 0; k < m; k++)
+                if ((s_rew[k >> 5] >> (k & 31)) & 1u) {
+                    const int q = s_near[k];
+                    kid_unlink(kid, q, s_par[k]);
+                    kid_link(kid, q, new_idx, head);
+                    head = q;
+                    if (ns < kFrontMax) s_front[ns++] = q | 0x40000000; else ovf = true;
+                }
+        }
+        s_cnt[0] = ns; s_cnt[1] = 0; s_cnt[2] = ovf ? 1 : 0; s_cnt[3] = newk;
+        __threadfence_block();
+    }
+    __syncthreads();
+    // ---- the subtrees below the re-parented vertices (left-child / right-sibling walk, one level per round)
+    int *cur = s_front, *nxt = s_front + kFrontMax;
+    int ncur = s_cnt[0];
+    while (ncur > 0 && !s_cnt[2]) {
+        __syncthreads();
+        if (tid == 0) s_cnt[0] = 0;
+        __syncthreads();
+        for (int i = tid; i < ncur; i += blockDim.x) {
+            const int raw = cur[i], u = raw & 0x3fffffff;
+            const Kid k = load_kid(kid + u);
+            if (k.gslot >= 0) { const int p = atomicAdd(&s_cnt[1], 1); if (p < kDirtyMax) s_dirty[p] = k.gslot; }
+            if (k.head >= 0) { const int p = atomicAdd(&s_cnt[0], 1); if (p < kFrontMax) nxt[p] = k.head; else s_cnt[2] = 1; }
+            if (!(raw >> 30) && k.next >= 0) { const int p = atomicAdd(&s_cnt[0], 1); if (p < kFrontMax) nxt[p] = k.next; else s_cnt[2] = 1; }
+        }
+        __syncthreads();
+        ncur = min(s_cnt[0], kFrontMax);
+        int *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    __syncthreads();
+    const int nd = s_cnt[1], newk = s_cnt[3];
+    if (s_cnt[2] || nd > kDirtyMax) {       // a huge subtree moved: evaluate everything (what the reference does every time)
+        goal_path_len<D>(v, c, e, nodes, sm_s, sm_i);
+        return;
+    }
+    const int old_k = c->best_k;
+    const double old_val = c->best_val;
+    if (nd == 0 && newk < 0) return;        // nothing that search_goal_parent looks at changed
+    double bs = XINF; int bk = INT_MAX;
+    bool best_dirty = false;
+    for (int i = tid; i < nd; i += blockDim.x) {
+        const int k = s_dirty[i];
+        const double val = XADD(cost_walk<D>(t, gi[k]), gd[k]);
+        __stcg(gcst + k, val);
+        lexmin(bs, bk, val, k);
+        best_dirty = best_dirty || k == old_k;
+    }
+    if (tid == 0 && newk >= 0) {
+        const double dn = gd[newk];
+        // c_new == cost(new_idx) as cost() would walk it now (no Near member: nobody walked it yet)
+        const double val = dn < XINF ? XADD(have_cnew ? c_new : cost_walk<D>(t, new_idx), dn) : XINF;
+        __stcg(gcst + newk, val);
+        lexmin(bs, bk, val, newk);
+    }
+    const int any_best_dirty = __syncthreads_or(best_dirty);
+    if (any_best_dirty) {
+        __threadfence_block();
+        __syncthreads();
+        const int ng = c->n_goal;
+        bs = XINF; bk = INT_MAX;
+        for (int k = tid; k < ng; k += blockDim.x) lexmin(bs, bk, __ldcg(gcst + k), k);
+    }
+    block_lexmin(bs, bk, sm_s, sm_i);
+    if (tid == 0) {
+        if (!any_best_dirty && old_k >= 0) lexmin(bs, bk, old_val, old_k);
+        if (any_best_dirty || bk != old_k) {
+            const int gp = gi[bk];
+            c->last_gp = gp;
+            c->last_len = goal_path_len_from<D>(v, c, e, nodes, gp);
+        }
+        c->best_k = bk; c->best_val = bs;
+    }
 }
 
 template <int D>
@@ -1436,6 +1619,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     __shared__ double s_first[kNearSmem];               // Line(near_k, x_new) by math.hypot: first term of cost(x_new) via near_k, and the edge length if near_k is re-wired
     __shared__ unsigned long long s_anc[kNearSmem];     // Near members on near_k's root path (see below)
     __shared__ unsigned s_rew[kNearSmem / 32];
+    __shared__ int s_par[kNearSmem];                    // parent(near_k) before this iteration (RRT* eval driver: child-list surgery)
+    __shared__ int s_par_new;                           // parent of the re-used vertex before ChooseParent (duplicate guard)
     __shared__ double s_curr[3];                        // curr_node_new_cost, cost(new) via the steer parent, cost(new) via ChooseParent's winner
     __shared__ Hint s_hnew;                             // ancestor hints of x_new after ChooseParent
     __shared__ double sm_s[4];
@@ -1563,6 +1748,9 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         for (int k = tid; k < m; k += blockDim.x) near_out[k] = s_near[k];
         if (tid == 0) IT.near_cnt = m;
 
+        const bool track = !fam_informed(v.variant) && v.mode == NIRRT_MODE_PLANNING_RANDOM;   // RRT* eval driver
+        double c_new_final = 0.0;          // cost(new_idx) after ChooseParent (valid when m > 0)
+        bool moved_final = false;          // the duplicate guard's vertex was re-parented by ChooseParent
         if (m > 0) {
             // One parallel round of root walks serves ChooseParent, node_new_cost and Rewire.
             // Every walk also notes which OTHER Near members (and x_new itself when it re-used an
@@ -1584,15 +1772,22 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                     // (rrt_star_3d.py:46,51) and the cost(new) ChooseParent falls back to
                     const double e0 = IT.cnew_default;
                     double cn, via;
-                    if (e0 < 0.0) { cn = cost_walk<D>(t, IT.nearest); s_curr[0] = cn; s_curr[1] = cn; }
+                    if (e0 < 0.0) {
+                        int fp = -1;
+                        cn = 0.0;
+                        walk_to_root(t, IT.nearest, [&](int par, double eg, int) { if (fp < 0) fp = par; cn = XADD(cn, eg); });
+                        s_curr[0] = cn; s_curr[1] = cn; s_par_new = fp;
+                    }
                     else { cost_walk2<D>(t, IT.nearest, e0, cn, via); s_curr[0] = XADD(cn, e0); s_curr[1] = via; }
                     continue;
                 }
                 const int idx = s_near[k];
                 double cacc = 0.0, vacc = s_first[k];
                 unsigned long long anc = 0;   // [0,30): three 10-bit positions, [30,32): count, bit 32: overflow, bit 33: through x_new
+                int fpar = -1;
                 walk_to_root(t, idx, [&](int par, double eg, int pad) {
                     cacc = XADD(cacc, eg); vacc = XADD(vacc, eg);
+                    if (fpar < 0) fpar = par;
                     if (par == new_idx) anc |= 1ull << 33;
                     else if ((pad >> 10) == tag) {      // a stale or aliased stamp can only add a (harmless) dependency
                         const int pos = pad & 1023;
@@ -1601,7 +1796,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                         else anc |= 1ull << 32;
                     }
                 });
-                s_cost[k] = cacc; s_anc[k] = anc;
+                s_cost[k] = cacc; s_anc[k] = anc; s_par[k] = fpar;
                 const double via_cost = XADD(cacc, s_d[k]);
                 if (via_cost < bs) { bs = via_cost; bk = k; via_best = vacc; }   // k ascends per thread: first minimum
             }
@@ -1615,6 +1810,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             const bool reparent = bs < s_curr[0];
             const double c_new = reparent ? s_curr[2] : s_curr[1];
             const bool new_moved = reparent && !IT.inserted;   // an existing vertex (duplicate guard) changed its parent
+            c_new_final = c_new; moved_final = new_moved;
             if (tid == 0) {
                 c->stamp++;
                 Hint hnew;
@@ -1696,8 +1892,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         }
         PHASE_MARK(4)
         // ---- goal bookkeeping
-        if (tid == 0) {
-            if (fam_informed(v.variant)) {
+        if (fam_informed(v.variant)) {
+            if (tid == 0) {
                 // InGoalRegion (rrt_base_3d.py:93-95)
                 if (edge_len<D>(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2])) < c->step_len &&
                     !seg_collides(g, xnew, c->goal)) {
@@ -1705,17 +1901,11 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                     else atomicOr(&c->err, ERR_SOL_OVERFLOW);
                     c->n_sol++;
                 }
-            } else if (v.mode == NIRRT_MODE_PLANNING_RANDOM && IT.inserted) {
-                const double gx = XSUB(c->goal[0], xnew[0]), gy = XSUB(c->goal[1], xnew[1]), gz = XSUB(c->goal[2], xnew[2]);
-                const double s2 = scan_sq<D>(gx, gy, gz);
-                // dist_to_goal <= step_len (rrt_star_3d.py:103-104 / rrt_star_2d.py:103-104)
-                if (s2 <= c->T_goal && (D == 3 || np_hypot(gx, gy) <= c->step_len)) {
-                    const int k = c->n_goal;
-                    v.gc_idx[(size_t)e * v.cap + k] = new_idx;
-                    v.gc_d[(size_t)e * v.cap + k] = seg_collides(g, xnew, c->goal) ? XINF : (D == 3 ? XSQRT(s2) : np_hypot(gx, gy));
-                    c->n_goal = k + 1;
-                }
             }
+        } else if (track) {
+            __syncthreads();
+            goal_track<D>(v, c, e, g, tree_of(v, e), nodes, new_idx, IT.inserted != 0, moved_final, m, s_near, s_par, s_rew,
+                          s_par_new, m > 0, c_new_final, xnew, s_cand, reinterpret_cast<int *>(s_anc), sm_s, sm_i);
         }
         __syncthreads();
     }
@@ -1723,18 +1913,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
 
     // ---- per-iteration record + phase machine (RRT* family; the IRRT* family records in k_top)
     if (!fam_informed(v.variant) && v.mode == NIRRT_MODE_PLANNING_RANDOM) {
-        double len;
-        __syncthreads();
-        const int changed = c->tree_changed;        // uniform: every thread reads before thread 0 clears it
-        __syncthreads();
-        if (changed) {
-            len = goal_path_len<D>(v, c, e, nodes, sm_s, sm_i);
-        } else {
-            len = c->last_len;
-        }
         if (tid == 0) {
-            c->last_len = len;
-            c->tree_changed = 0;
+            const double len = c->last_len;         // kept current by goal_track (k_goal_init at begin)
             push_record(v, c, e, len);
             if (c->state == ST_PHASE1) {
                 c->p1_done++;
@@ -1769,7 +1949,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
 // ------------------------------------------------------------------------------------------------
 // setup / IO kernels
 
-// builds the goal-candidate list of an existing tree in ascending index order (1 CTA / env)
+// RRT* eval driver, start of a run (1 CTA / env): the goal-candidate list of the existing tree in ascending index
+// order, the child lists of every vertex, the cached candidate costs, the current goal parent and path length
 template <int D>
 __global__ void __launch_bounds__(256) k_goal_init(View v) {
     typedef typename GeomOf<D>::type G;
@@ -1778,11 +1959,25 @@ __global__ void __launch_bounds__(256) k_goal_init(View v) {
     __shared__ G g;
     __shared__ int s_wcnt[8];
     __shared__ int s_total;
+    __shared__ double sm_s[8];
+    __shared__ int sm_i[8];
     stage_geom<D>(&g, v, e);
     if (threadIdx.x == 0) s_total = 0;
-    __syncthreads();
     const int n = c->n;
     const Node *nodes = v.nodes + (size_t)e * v.stride;
+    Kid *kid = v.kid + (size_t)e * v.stride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) store_kid(kid + i, -1, -1, -1, -1);
+    __threadfence_block();
+    __syncthreads();
+    // child lists: every field below has exactly one writer (v writes its own next, its successor in the push
+    // order writes its prev)
+    for (int i = 1 + threadIdx.x; i < n; i += blockDim.x) {
+        const int p = (int)load_node(nodes + i).parent;
+        const int old = atomicExch(&kid[p].head, i);
+        __stcg(&kid[i].next, old);
+        if (old >= 0) __stcg(&kid[old].prev, i);
+    }
+    __syncthreads();
     for (int base = 0; base < n; base += blockDim.x) {
         const int i = base + threadIdx.x;
         bool keep = false;
@@ -1807,12 +2002,16 @@ __global__ void __launch_bounds__(256) k_goal_init(View v) {
             const int pos = off + __popc(bal & ((1u << l) - 1u));
             v.gc_idx[(size_t)e * v.cap + pos] = i;
             v.gc_d[(size_t)e * v.cap + pos] = d;
+            if (d < XINF) __stcg(&kid[i].gslot, pos);
         }
         __syncthreads();
         if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; q++) t += s_wcnt[q]; s_total += t; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { c->n_goal = s_total; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1; }
+    if (threadIdx.x == 0) c->n_goal = s_total;
+    __threadfence_block();
+    __syncthreads();
+    goal_path_len<D>(v, c, e, nodes, sm_s, sm_i);      // fills the cost cache, best_k / best_val / last_gp / last_len
 }
 
 __global__ void k_begin(View v) {
@@ -2247,6 +2446,8 @@ static int ensure_goal_lists(nirrt_batch *b) {
     void *p = nullptr;
     int r = dalloc(b, &p, sizeof(int) * (size_t)v.E * v.cap); if (r) return r; v.gc_idx = (int *)p;
     r = dalloc(b, &p, sizeof(double) * (size_t)v.E * v.cap); if (r) return r; v.gc_d = (double *)p;
+    r = dalloc(b, &p, sizeof(double) * (size_t)v.E * v.cap); if (r) return r; v.gc_cost = (double *)p;
+    r = dalloc(b, &p, sizeof(Kid) * (size_t)v.E * v.stride); if (r) return r; v.kid = (Kid *)p;
     b->goal_lists = true;
     return NIRRT_OK;
 }
@@ -2722,13 +2923,21 @@ static int run_pipelined(nirrt_batch *b, cudaStream_t s, int m) {
 // run changes (iteration counts, thresholds, vertex limit, guidance knobs) lives in EnvCtl::cfg.  Graphs are
 // built by nirrt_batch_begin (never inside a run that finds its graph) and kept for the life of the batch.
 constexpr size_t kMaxGraphs = 8;
+// what the captured kernels read of the View: the goal-candidate buffers (allocated lazily, possibly after other
+// graphs were built) only matter to the RRT* eval driver
+static void graph_key(const View &v, View *k) {
+    memcpy(k, &v, sizeof(View));     // byte copies throughout: the lookup is a memcmp
+    if (!(v.mode == NIRRT_MODE_PLANNING_RANDOM && !fam_informed(v.variant))) { k->gc_idx = nullptr; k->gc_d = nullptr; k->gc_cost = nullptr; k->kid = nullptr; }
+}
 static nirrt_batch::GraphEntry *ensure_graph(nirrt_batch *b, bool pipelined) {
     if (!b->use_graph || b->graph_iters < 2) return nullptr;
     if (!b->cs) {
         if (cudaStreamCreateWithFlags(&b->cs, cudaStreamNonBlocking) != cudaSuccess) { b->use_graph = false; b->graph_fallbacks++; return nullptr; }
     }
+    View key;
+    graph_key(b->v, &key);
     for (auto &g : b->graphs)
-        if (g.pipelined == pipelined && memcmp(&g.view, &b->v, sizeof(View)) == 0) { g.last_use = ++b->graph_clock; return &g; }
+        if (g.pipelined == pipelined && memcmp(&g.view, &key, sizeof(View)) == 0) { g.last_use = ++b->graph_clock; return &g; }
     if (b->graphs.size() >= kMaxGraphs) {       // evict the least recently used executable
         size_t lru = 0;
         for (size_t i = 1; i < b->graphs.size(); i++) if (b->graphs[i].last_use < b->graphs[lru].last_use) lru = i;
@@ -2758,7 +2967,7 @@ static nirrt_batch::GraphEntry *ensure_graph(nirrt_batch *b, bool pipelined) {
         return nullptr;
     }
     nirrt_batch::GraphEntry g;
-    memcpy(&g.view, &b->v, sizeof(View));     // byte copy: the lookup above is a memcmp
+    memcpy(&g.view, &key, sizeof(View));      // byte copy: the lookup above is a memcmp
     g.pipelined = pipelined; g.exec = exec; g.launches = per_replay; g.last_use = ++b->graph_clock;
     b->graphs.push_back(g);
     b->graph_builds++;

@@ -352,6 +352,57 @@ def test_parity_at_100k_vertices(B):
         assert n2[e] == len(ov), e
         assert np.array_equal(p2[e, :n2[e]], op), e
         assert np.array_equal(v2[e, :n2[e]], ov), e
+    # the eval variant (planning_random body: search_goal_parent + path length after every iteration,
+    # rrt_star_3d.py:101-117,225-231) from the same snapshot: per-iteration path lengths and the trees
+    b2 = B.BatchPlanner3D(problems, cap_iters, rng_states=states, record_capacity=window + 8)
+    b2.load_trees(v, p, n)
+    b2.begin(0, B.MODE_PLANNING_RANDOM, 1 << 30, 1 << 30)
+    b2.run(window)
+    recs = b2.records()
+    v3, p3, n3 = b2.read_trees()
+    gp, _ = b2.goal_parents()
+    for e in range(E):
+        o = Oracle3D(problems[e], cap_iters, rng_state=states[e])
+        o.load_tree(v[e, :n[e]], p[e, :n[e]])
+        want = o.run(window, 0, 1)["pathlen"]
+        got = recs[e]
+        assert len(got) == window and np.array_equal(np.isinf(got), np.isinf(want)), e
+        f = np.isfinite(want)
+        assert f.any() and np.allclose(got[f], want[f], rtol=1e-12, atol=0), e
+        ov, op = o.tree()
+        assert n3[e] == len(ov) and np.array_equal(p3[e, :n3[e]], op) and np.array_equal(v3[e, :n3[e]], ov), e
+        assert gp[e] == o.search_goal_parent(), e
+    b2.close()
+    bp.close()
+
+
+def test_eval_variant_goal_tracking_long_run(B):
+    """RRT* planning_random keeps search_goal_parent's answer current incrementally (child lists + cached candidate
+    costs, refreshed only below re-wired vertices).  Long runs on small worlds re-wire constantly, move whole
+    subtrees (incl. through the duplicate guard) and improve the goal path many times: the per-iteration path
+    lengths must equal the oracle's, which re-walks every candidate every iteration like the reference."""
+    from oracle.planner_oracle import Oracle3D
+    E, iter_max, iter_after = 6, 6000, 3000
+    problems = [make_problem_3d(600 + i) for i in range(E)]
+    seeds = [1234 + i for i in range(E)]
+    bp = B.BatchPlanner3D(problems, iter_max, seeds=seeds, record_capacity=iter_max + iter_after + 8)
+    bp.begin(0, B.MODE_PLANNING_RANDOM, iter_max, iter_after)
+    bp.run_to_completion(chunk=512)
+    lists = bp.path_len_lists()
+    v, p, n = bp.read_trees()
+    improved = 0
+    for e in range(E):
+        o = Oracle3D(problems[e], iter_max, seed=seeds[e])
+        want = np.array(o.planning_random(iter_after, 0))
+        got = np.array(lists[e])
+        assert len(got) == len(want), (e, len(got), len(want))
+        assert np.array_equal(np.isinf(got), np.isinf(want)), e
+        f = np.isfinite(want)
+        assert np.allclose(got[f], want[f], rtol=1e-12, atol=0), e
+        improved += len(np.unique(want[f]))
+        ov, op = o.tree()
+        assert n[e] == len(ov) and np.array_equal(p[e, :n[e]], op) and np.array_equal(v[e, :n[e]], ov)
+    assert improved > 10 * E          # the goal path really changed many times
     bp.close()
 
 
