@@ -155,6 +155,19 @@ def test_config1_shape_64_problems_5000_iterations(B):
             assert np.all(np.diff(got[f]) <= 1e-9)               # the best cost never increases
             assert not f[:int(np.argmax(f))].any() and f[int(np.argmax(f)):].all()   # inf ... inf, then finite to the end
     assert solved >= E // 2
+    # against the CPU oracle (numpy restatement of irrt_star_2d.py:230-316, pinned to the reference's golden traces
+    # by tests/test_oracle_pin2d.py) for problems spread over both groups of the batch
+    from oracle.planner2d_oracle import Oracle2D
+    for e in (0, 13, 31, 32, 47, 63):
+        o = Oracle2D(problems[e], iter_max, seed=seeds[e])
+        want = np.array(o.planning_random(iter_after, 1))
+        got = np.array(lists[e])
+        assert len(got) == len(want), (e, len(got), len(want))
+        assert np.array_equal(np.isinf(got), np.isinf(want)), e
+        f = np.isfinite(want)
+        assert np.allclose(got[f], want[f], rtol=1e-5, atol=0), e
+        assert n[e] == o.n and np.array_equal(p[e, :o.n], o.parent[:o.n]), e
+        assert np.allclose(v[e, :o.n], o.v[:o.n], rtol=0, atol=1e-9), e
     for e in (0, 21, 63):
         one = B.BatchPlanner2D([problems[e]], iter_max, seeds=[seeds[e]], record_capacity=iter_max + iter_after + 8)
         one.begin(B.VARIANT_IRRT_STAR, B.MODE_PLANNING_RANDOM, iter_max, iter_after)
