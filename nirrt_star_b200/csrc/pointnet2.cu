@@ -518,6 +518,7 @@ static int gemm_attr() {
     PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PCUDA(cudaFuncSetAttribute(k_ball_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     PCUDA(cudaFuncSetAttribute(k_ball_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    PCUDA(cudaFuncSetAttribute(k_fps<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));   // 4096 points x 12 B + static
     g_gemm_attr = true;
     return NIRRT_OK;
 }
@@ -676,7 +677,9 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
                                 nirrt_pn2 **out) {
     if (!layers || !out) return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_create: null argument");
     if (n_layers != NIRRT_PN2_NUM_LAYERS) return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_create: expected 35 layers");
-    if (n_points < 1024 || n_points > 4096) return pfail(NIRRT_ERR_INVALID, "n_points must be in [1024, 4096] (sa1 samples 1024 points)");
+    // any cloud size the reference's forward accepts up to 4096 points: with fewer than 1024 points sa1's farthest point
+    // sampling re-selects index 0 once every point is taken (torch.max on all-zero distances), which k_fps reproduces
+    if (n_points < 16 || n_points > 4096) return pfail(NIRRT_ERR_INVALID, "n_points must be in [16, 4096]");
     if (max_batch < 1) return pfail(NIRRT_ERR_INVALID, "max_batch >= 1 required");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pfail(NIRRT_ERR_NO_DEVICE, "no CUDA device visible");

@@ -107,15 +107,31 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                     raise ValueError("neural planners need state_dict= or classify=")
                 engine = PointNet2Engine(state_dict, n_points=args.pc_n_points, max_batch=E, device=device)
 
+                short_engines = {}
+
                 def classify(items, envs):
+                    # torch.randint on each problem's own generator, in problem order (pointnet2_utils.py:77)
+                    fs = np.stack([[int(torch.randint(0, n, (1,), generator=gens[env], dtype=torch.long)) for n in (len(it[0]),) + NPOINTS]
+                                   for it, env in zip(items, envs)]).astype(np.int32)
+                    preds = [None] * len(items)
                     full = [k for k, it in enumerate(items) if len(it[0]) == args.pc_n_points]
-                    if len(full) != len(items):
-                        raise ValueError("a guidance cloud has fewer than pc_n_points free points")
-                    fs = np.stack([[int(torch.randint(0, n, (1,), generator=gens[env], dtype=torch.long)) for n in (args.pc_n_points,) + NPOINTS]
-                                   for env in envs]).astype(np.int32)
-                    pred, _ = engine.classify(np.stack([it[0].astype(np.float32) for it in items]),
-                                              np.stack([it[1] for it in items]), np.stack([it[2] for it in items]), fps_start=fs)
-                    return list(pred)
+                    if full:            # every full-size cloud of this lock-step round in ONE forward
+                        pred, _ = engine.classify(np.stack([items[k][0].astype(np.float32) for k in full]),
+                                                  np.stack([items[k][1] for k in full]), np.stack([items[k][2] for k in full]),
+                                                  fps_start=fs[full])
+                        for k, pr in zip(full, pred):
+                            preds[k] = pr
+                    # clouds with fewer free points than pc_n_points (large informed ellipsoid at the world border, heavy
+                    # clutter): the reference only down-samples `if len(point_cloud) > n_points` and classifies whatever
+                    # is left (point_cloud_mask_utils_3d.py:104-112) -- one engine per distinct size, kept for the run
+                    for k, it in enumerate(items):
+                        if preds[k] is None:
+                            n = len(it[0])
+                            if n not in short_engines:
+                                short_engines[n] = PointNet2Engine(state_dict, n_points=n, max_batch=1, device=device)
+                            pred, _ = short_engines[n].classify(it[0].astype(np.float32)[None], it[1][None], it[2][None], fps_start=fs[k:k + 1])
+                            preds[k] = pred[0]
+                    return preds
             else:
                 user = classify
 

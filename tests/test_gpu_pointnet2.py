@@ -159,3 +159,36 @@ def test_dropin_wrapper_matches_reference_golden(path, tmp_path):
     torch.manual_seed(int(g["seed"]))
     w.classify_path_points(g["pc"], g["start_mask"], g["goal_mask"])
     assert torch.equal(torch.rand(1), expect_next)
+
+
+@pytest.mark.parametrize("n", [1500, 700, 3000])
+def test_short_and_odd_sized_clouds(n):
+    """The reference classifies clouds of ANY size: the samplers only down-sample `if len(point_cloud) > n_points`
+    (point_cloud_mask_utils_3d.py:104-112), so a cluttered world yields fewer than 2048 points; with fewer than 1024
+    points sa1's farthest point sampling re-selects index 0 once every point is taken (pointnet2_utils.py:79-85).
+    FPS indices exact, log-probabilities within the fp16-operand tolerance of the fp32 oracle."""
+    from nirrt_star_b200.pointnet2 import PointNet2Engine
+    from oracle import pointnet2_oracle as O
+    sd = make_pointnet2_state(0)
+    pc, sm, gm = make_cloud_3d(3)
+    rs = np.random.RandomState(n)
+    if n <= len(pc):
+        keep = np.sort(rs.choice(len(pc), n, replace=False))
+        pc, sm, gm = pc[keep], sm[keep], gm[keep]
+    else:
+        extra = rs.randint(0, len(pc), n - len(pc))
+        pc = np.concatenate([pc, pc[extra] + rs.uniform(-0.5, 0.5, (len(extra), 3)).astype(np.float32)])
+        sm = np.concatenate([sm, sm[extra]]); gm = np.concatenate([gm, gm[extra]])
+    eng = PointNet2Engine(sd, n_points=n, max_batch=1)
+    fs = np.array([[n // 3, 11, 12, 13]], dtype=np.int32)
+    pred, score, logp = eng.classify(pc, sm, gm, fps_start=fs, return_logp=True)
+    tr = {}
+    wpred, wscore, want = O.classify_path_points(sd, pc, sm, gm, fs[0], trace=tr)
+    got_fps = eng.read_buffer("fps0", np.int32, (1, 1024))[0]
+    assert np.array_equal(got_fps, np.asarray(tr["fps"][0][0]).astype(np.int32))
+    if n < 1024:
+        assert (got_fps[n:] == 0).all() and len(set(got_fps[:n].tolist())) == n
+    assert np.abs(logp[0] - want).max() <= LOGP_TOL
+    flip = pred[0] != wpred
+    assert not np.any(flip & (np.abs(wscore - 0.5) >= 0.05))
+    eng.close()
