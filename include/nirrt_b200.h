@@ -187,6 +187,11 @@ int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int64_t m, dou
  * (datasets_3d/point_cloud_mask_utils_3d.py:49-52,196-199; datasets/point_cloud_mask_utils.py:69-72,170-173) */
 int nirrt_fps_f64_sync(const double *points, int64_t n, int npoint, int start, int64_t *out_idx, void *stream);
 
+/* math.sin / math.cos as the reference's runtime evaluates them (glibc 2.39 x86-64 FMA kernels, restated operation
+ * by operation in csrc/glibc_trig.cuh -- NOT the correctly rounded values): what the device uses for the informed
+ * sampler (irrt_star_3d.py:154-156) and the 2D steer (rrt_star_2d.py:77).  x, out_sin, out_cos: host [n]. */
+int nirrt_sincos_sync(const double *x, int64_t n, double *out_sin, double *out_cos, void *stream);
+
 /* Device-resident benchmark hooks: bytes scanned per Nearest+Near pass and launch counters. */
 int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *scan_bytes_per_vertex);
 /* CUDA-graph bookkeeping of nirrt_batch_run: executables built (one per variant/mode, by nirrt_batch_begin),

@@ -384,6 +384,15 @@ class BatchPlanner2D(BatchPlanner3D):
                                                  ip(nc), dp(circles), ip(nr), dp(rects), dp(table), dp(rot), self.stream))
 
 
+def sincos(x, stream=None):
+    """(math.sin(x), math.cos(x)) element-wise on the device, bit-identical to the reference runtime's libm."""
+    _lib.require_device()
+    x = f64(x).reshape(-1)
+    s = np.empty_like(x); c = np.empty_like(x)
+    check(_lib.lib().nirrt_sincos_sync(dp(x), len(x), dp(s), dp(c), C.c_void_p(stream) if stream else None))
+    return s, c
+
+
 def fps_f64(points, npoint, start=0, stream=None):
     """Indices of the farthest-point down-sampling of an (n,3) f64 point set (open3d semantics:
     start index 0, squared distances in f64, first argmax)."""

@@ -33,6 +33,7 @@
 
 #include "../../include/nirrt_b200.h"
 #include "exact_math.cuh"
+#include "glibc_trig.cuh"
 #include "geometry3d.cuh"
 #include "geometry2d.cuh"
 #include "mt19937.cuh"
@@ -598,9 +599,8 @@ __device__ void sample_informed(const Geom3 &g, const EnvCtl *c, MtStream &rng, 
         const double rr = rng.uniform(0.0, 1.0);
         const double th = rng.uniform(0.0, PI);
         const double ph = rng.uniform(0.0, TWO_PI);
-        double st, ct, sp, cp;
-        cr_sincos(th, &st, &ct);
-        cr_sincos(ph, &sp, &cp);
+        // np.sin / np.cos == glibc's sin / cos, restated operation by operation (glibc_trig.cuh)
+        const double st = glibc_sin(th), ct = glibc_cos(th), sp = glibc_sin(ph), cp = glibc_cos(ph);
         const double rs = XMUL(rr, st);
         const double xb0 = XMUL(rs, cp), xb1 = XMUL(rs, sp), xb2 = XMUL(rr, ct);
         for (int i = 0; i < 3; i++)
@@ -928,8 +928,7 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
         // theta = math.atan2(dy, dx); node_new = start + dist * [cos(theta), sin(theta)]
         const double theta = cr_atan2(d1, d0);
         if (!(dist < c->step_len)) dist = c->step_len;
-        double sn, cs;
-        cr_sincos(theta, &sn, &cs);
+        const double sn = glibc_sin(theta), cs = glibc_cos(theta);     // math.sin / math.cos (glibc_trig.cuh)
         xnew[0] = XADD(xn[0], XMUL(dist, cs));
         xnew[1] = XADD(xn[1], XMUL(dist, sn));
         xnew[2] = 0.0;
@@ -3328,6 +3327,26 @@ extern "C" int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int
     LAUNCH_D(b->v.dim, k_costs, (int)((m + 127) / 128), 128, 0, s, b->v, env, di, m, dout);
     CHECK_LAUNCH();
     CUDA_TRY(cudaMemcpyAsync(out, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+// ---- math.sin / math.cos of the reference's runtime (glibc 2.39 kernels restated, glibc_trig.cuh), element-wise
+__global__ void k_sincos(const double *x, long long n, double *s, double *c) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) { s[i] = glibc_sin(x[i]); c[i] = glibc_cos(x[i]); }
+}
+extern "C" int nirrt_sincos_sync(const double *x, int64_t n, double *out_sin, double *out_cos, void *stream) {
+    if (n < 0 || (n > 0 && (!x || !out_sin || !out_cos))) return fail(NIRRT_ERR_INVALID, "nirrt_sincos_sync: bad argument");
+    if (n == 0) return NIRRT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    TempBufs t;
+    double *dx, *ds, *dc;
+    TRY(t.up(x, (size_t)n, s, &dx)); TRY(t.make<double>((size_t)n, &ds)); TRY(t.make<double>((size_t)n, &dc));
+    k_sincos<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dx, n, ds, dc);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out_sin, ds, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_cos, dc, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return NIRRT_OK;
 }

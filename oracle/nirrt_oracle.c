@@ -478,7 +478,9 @@ static void sample_free3(orc_plan3 *p, double *out) {
  * c*c in ~0.09% of inputs, probed); the oracle uses c*c.  C@L@xball is evaluated as (C@L)@xball;
  * L is diagonal so (C@L)[i][j] = C[i][j]*r[j] (single rounding), and the 3-term row dot products
  * follow the order this container's BLAS dgemv produces: fma(M2,x2, fma(M0,x0, M1*x1))
- * (probed, 60000/60000 rows).  sin/cos: see cr_sincos above. */
+ * (probed, 60000/60000 rows).  sin/cos: the platform libm, exactly what numpy calls (the CUDA path restates glibc
+ * 2.39's kernels operation by operation, nirrt_star_b200/csrc/glibc_trig.cuh; cr_sincos above is kept as the
+ * correctly rounded yardstick the tests compare both against). */
 static void sample_informed3(orc_plan3 *p, double c_max, double *out) {
     double c2 = c_max * c_max - p->c_min * p->c_min;
     double eps = (c2 < 0) ? 1e-6 : 0;
@@ -491,8 +493,9 @@ static void sample_informed3(orc_plan3 *p, double c_max, double *out) {
         double th = mt_uniform(&p->rng, 0, M_PI);
         double ph = mt_uniform(&p->rng, 0, 2 * M_PI);
         double xb[3], st, ct, sp, cp;
-        cr_sincos(th, &st, &ct);
-        cr_sincos(ph, &sp, &cp);
+        /* np.sin / np.cos == the C library's sin / cos (probed: np.sin(array) == [math.sin(x)] on 2e6 samples) */
+        st = sin(th); ct = cos(th);
+        sp = sin(ph); cp = cos(ph);
         xb[0] = rr * st * cp;
         xb[1] = rr * st * sp;
         xb[2] = rr * ct;

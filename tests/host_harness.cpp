@@ -3,6 +3,7 @@
 // Test infrastructure only; built by tests/test_host_math.py with g++ -ffp-contract=off -mfma.
 #include <cstring>
 #include "../nirrt_star_b200/csrc/exact_math.cuh"
+#include "../nirrt_star_b200/csrc/glibc_trig.cuh"
 #include "../nirrt_star_b200/csrc/geometry3d.cuh"
 #include "../nirrt_star_b200/csrc/geometry2d.cuh"
 
@@ -14,6 +15,10 @@ double hh_hypot2(double a, double b) { return hypot2(a, b); }
 double hh_rownorm3(double a, double b, double c) { return rownorm3(a, b, c); }
 double hh_vecnorm3(double a, double b, double c) { return vecnorm3(a, b, c); }
 void hh_cr_sincos(double x, double *s, double *c) { cr_sincos(x, s, c); }
+// vectorised: out_s[i] = glibc_sin(x[i]), out_c[i] = glibc_cos(x[i])
+void hh_glibc_sincos(long n, const double *x, double *out_s, double *out_c) {
+    for (long i = 0; i < n; i++) { out_s[i] = glibc_sin(x[i]); out_c[i] = glibc_cos(x[i]); }
+}
 double hh_sqrt_le_threshold(double r) { return sqrt_le_threshold(r); }
 double hh_pairwise_sum(const double *a, long n) { return pairwise_sum(a, n); }
 

@@ -72,6 +72,31 @@ def test_cr_sincos_same_as_oracle(hh):
     assert mism_libm < 0.01 * len(xs)      # libm itself misrounds ~0.13 % of calls
 
 
+def test_glibc_sin_cos_restatement_equals_libm(hh):
+    """glibc_trig.cuh restates glibc 2.39's FMA-variant sin / cos kernels operation by operation: on this image's
+    libm (what math.sin / np.sin of the reference call) the results must be bit-identical -- including the ~0.15 % of
+    arguments where libm is NOT correctly rounded -- over every branch: |x| < 2^-26, Taylor (< 0.126), table
+    (< 0.855469), pi/2 - x (< 2.426265), range reduction with n = 0..3 (< 105414350)."""
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(-2 * math.pi, 2 * math.pi, 1500000), rng.uniform(0, math.pi, 500000),
+                         rng.uniform(-0.2, 0.2, 300000), rng.uniform(-1e-7, 1e-7, 100000), rng.uniform(-1e4, 1e4, 800000),
+                         rng.uniform(-1e8, 1e8, 400000), rng.uniform(0.85, 0.86, 200000), rng.uniform(2.42, 2.43, 200000),
+                         [0.0, -0.0, 0.126, 0.855469, 2.426265, math.pi, -math.pi, 2 * math.pi, math.pi / 2, 1e-300]])
+    s = np.empty_like(xs); c = np.empty_like(xs)
+    dp = C.POINTER(C.c_double)
+    hh.hh_glibc_sincos.argtypes = [C.c_long, dp, dp, dp]
+    hh.hh_glibc_sincos(len(xs), xs.ctypes.data_as(dp), s.ctypes.data_as(dp), c.ctypes.data_as(dp))
+    assert np.array_equal(s, np.sin(xs)) and np.array_equal(c, np.cos(xs))
+    assert all(s[i] == math.sin(xs[i]) and c[i] == math.cos(xs[i]) for i in range(0, len(xs), 997))
+    # and the thing it is NOT: the correctly rounded value (that is why a restatement is needed)
+    s1, c1 = C.c_double(), C.c_double()
+    differ = 0
+    for x in xs[:40000]:
+        hh.hh_cr_sincos(x, C.byref(s1), C.byref(c1))
+        differ += (s1.value != math.sin(x)) + (c1.value != math.cos(x))
+    assert 0 < differ < 400
+
+
 def test_pairwise_sum_matches_numpy(hh):
     rng = np.random.default_rng(4)
     for n in (1, 2, 7, 8, 9, 15, 16, 17, 31, 100, 128, 129, 300, 1000):

@@ -77,7 +77,7 @@ def test_oracle_matches_reference_trace(path):
     if kind == "rrt":
         assert np.array_equal(v, g["vertices"])          # RRT*: no transcendental in the loop -> bit exact
     else:
-        assert np.allclose(v, g["vertices"], rtol=0, atol=1e-12)
+        assert np.array_equal(v, g["vertices"])          # np.sin / np.cos are the C library's: bit exact as well
         assert np.array_equal(o.solutions(), g["solutions"])
     gp = g["path_len_list"]
     assert len(plist) == len(gp)
