@@ -191,6 +191,8 @@ int nirrt_fps_f64_sync(const double *points, int64_t n, int npoint, int start, i
  * by operation in csrc/glibc_trig.cuh -- NOT the correctly rounded values): what the device uses for the informed
  * sampler (irrt_star_3d.py:154-156) and the 2D steer (rrt_star_2d.py:77).  x, out_sin, out_cos: host [n]. */
 int nirrt_sincos_sync(const double *x, int64_t n, double *out_sin, double *out_cos, void *stream);
+/* math.atan2(y, x) likewise (2D steer, rrt_star_2d.py:74 / rrt_base_2d.py:120); y, x, out: host [n] */
+int nirrt_atan2_sync(const double *y, const double *x, int64_t n, double *out, void *stream);
 
 /* Device-resident benchmark hooks: bytes scanned per Nearest+Near pass and launch counters. */
 int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *scan_bytes_per_vertex);

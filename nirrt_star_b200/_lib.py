@@ -78,6 +78,7 @@ def lib():
     L.nirrt_batch_read_cbest_sync.argtypes = [V, c_dp, c_dp, V]
     L.nirrt_fps_f64_sync.argtypes = [c_dp, C.c_int64, C.c_int, C.c_int, c_i64p, V]
     L.nirrt_sincos_sync.argtypes = [c_dp, C.c_int64, c_dp, c_dp, V]
+    L.nirrt_atan2_sync.argtypes = [c_dp, c_dp, C.c_int64, c_dp, V]
     L.nirrt_batch_set_stop_threshold.argtypes = [V, C.c_double]
     L.nirrt_batch_set_vertex_limit.argtypes = [V, C.c_int]
     L.nirrt_batch_run_profiled_sync.argtypes = [V, C.c_int, c_fp, V]

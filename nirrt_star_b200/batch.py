@@ -393,6 +393,15 @@ def sincos(x, stream=None):
     return s, c
 
 
+def atan2(y, x, stream=None):
+    """math.atan2(y, x) element-wise on the device, bit-identical to the reference runtime's libm."""
+    _lib.require_device()
+    y = f64(y).reshape(-1); x = f64(x).reshape(-1)
+    out = np.empty_like(y)
+    check(_lib.lib().nirrt_atan2_sync(dp(y), dp(x), len(y), dp(out), C.c_void_p(stream) if stream else None))
+    return out
+
+
 def fps_f64(points, npoint, start=0, stream=None):
     """Indices of the farthest-point down-sampling of an (n,3) f64 point set (open3d semantics:
     start index 0, squared distances in f64, first argmax)."""

@@ -136,4 +136,126 @@ NIRRT_HD double glibc_cos(double x) {
     return c;
 }
 
+// ---- math.atan2 (rrt_star_2d.py:74, rrt_base_2d.py:120): glibc 2.39 __ieee754_atan2, FMA variant
+// (sysdeps/ieee754/dbl-64/e_atan2.c): u = min(|x|,|y|) / max(|x|,|y|) with its division error du (exact product by
+// FMA), then either the odd polynomial (u < 1/16) or the degree-6 expansion around the nearest of 241 table points
+// (glibc_atantab.inc), combined with 0 / pi/2 / pi in two-term arithmetic per quadrant.  Max error 0.56 ulp: not
+// correctly rounded, restated with the fused operations exactly where that build has them.
+NIRRT_HD const double *glibc_atan_row(int i) {
+    static const double t[241 * 7] = {
+#include "glibc_atantab.inc"
+    };
+    return t + 7 * i;
+}
+
+namespace gt {
+constexpr double hpi = 0x1.921fb54442d18p+0, hpi1 = 0x1.1a62633145c07p-54, opi = 0x1.921fb54442d18p+1, opi1 = 0x1.1a62633145c07p-53;
+constexpr double d3 = -0x1.5555555555555p-2, d5 = 0x1.99999999997fdp-3, d7 = -0x1.24924923f7603p-3, d9 = 0x1.c71c6e5129a3bp-4,
+                 d11 = -0x1.7458022b13c25p-4, d13 = 0x1.375f08b31cbcep-4;
+constexpr double two52 = 0x1p52, two500 = 0x1p500, twom500 = 0x1p-500;
+}  // namespace gt
+
+NIRRT_HD double glibc_atan_poly(double v) {
+    double p = XFMA(v, gt::d13, gt::d11);
+    p = XFMA(v, p, gt::d9); p = XFMA(v, p, gt::d7); p = XFMA(v, p, gt::d5);
+    return XFMA(v, p, gt::d3);
+}
+// degree-4 tail c2 + v (c3 + v (c4 + v (c5 + v c6))) of a table row
+NIRRT_HD double glibc_atan_tail(const double *c, double v) {
+    double p = XFMA(v, c[6], c[5]);
+    p = XFMA(v, p, c[4]); p = XFMA(v, p, c[3]);
+    return XFMA(v, p, c[2]);
+}
+
+NIRRT_HD double glibc_atan2(double y, double x) {
+    const uint64_t bx = d2u(x), by = d2u(y);
+    const uint32_t ux = (uint32_t)(bx >> 32), uy = (uint32_t)(by >> 32);
+    // NaN / infinity: not produced by the planners; defer to the library formula
+    if ((ux & 0x7ff00000u) == 0x7ff00000u || (uy & 0x7ff00000u) == 0x7ff00000u) return atan2(y, x);
+    if ((by << 1) == 0) {                                   // y = +-0
+        const bool neg_x = (bx >> 63) != 0;
+        if (by == 0) return neg_x ? gt::opi : 0.0;
+        return neg_x ? -gt::opi : -0.0;
+    }
+    if ((bx << 1) == 0) return y > 0 ? gt::hpi : -gt::hpi;  // x = +-0
+    double ax = x < 0 ? -x : x, ay = y < 0 ? -y : y;
+    const int de = (int)(uy & 0x7ff00000u) - (int)(ux & 0x7ff00000u);
+    if (de >= 59768832) return y > 0 ? gt::hpi : -gt::hpi;
+    if (de <= -59768832) {
+        if (x > 0) return copysign(XDIV(ay, ax), y);        // (the subnormal-quotient branch differs only in flags)
+        return y > 0 ? gt::opi : -gt::opi;
+    }
+    if (ax < gt::twom500 || ay < gt::twom500) { ax = XMUL(ax, gt::two500); ay = XMUL(ay, gt::two500); }
+    if (ax > gt::two500 || ay > gt::two500) { ax = XMUL(ax, gt::twom500); ay = XMUL(ay, gt::twom500); }
+    double u, du;
+    if (ay < ax) {
+        u = XDIV(ay, ax);
+        const double v = XMUL(ax, u), vv = XFMA(ax, u, -v);
+        du = XDIV(XSUB(XSUB(ay, v), vv), ax);
+    } else {
+        u = XDIV(ax, ay);
+        const double v = XMUL(ay, u), vv = XFMA(ay, u, -v);
+        du = XDIV(XSUB(XSUB(ax, v), vv), ay);
+    }
+    const bool small = u < 0.0625;
+    const double *c = nullptr;
+    if (!small) c = glibc_atan_row((int)XSUB(XFMA(u, 256.0, gt::two52), gt::two52) - 16);
+    double z;
+    if (x > 0) {
+        if (ay < ax) {                                      // (i) atan(ay/ax)
+            if (small) {
+                const double v = XMUL(u, u);
+                z = XADD(u, XFMA(XMUL(u, v), glibc_atan_poly(v), du));
+            } else {
+                const double t3 = XSUB(u, c[0]);
+                const double v = XADD(du, t3);
+                const double dv = fabs(t3) > fabs(du) ? XADD(XSUB(t3, v), du) : XADD(XSUB(du, v), t3);
+                double p = XFMA(v, c[6], c[5]);
+                p = XFMA(v, p, c[4]); p = XFMA(v, p, c[3]);
+                const double zz = XFMA(v, c[2], XFMA(dv, c[2], XMUL(XMUL(v, v), p)));
+                z = XADD(zz, c[1]);
+            }
+        } else {                                            // (ii) pi/2 - atan(ax/ay)
+            if (small) {
+                const double v = XMUL(u, u);
+                const double zz = XMUL(XMUL(u, v), glibc_atan_poly(v));
+                const double t2 = XSUB(gt::hpi, u);
+                const double cor = XSUB(XSUB(gt::hpi, t2), u);
+                z = XADD(XSUB(XSUB(XADD(cor, gt::hpi1), du), zz), t2);
+            } else {
+                const double v = XADD(XSUB(u, c[0]), du);
+                const double zz = GT_FNMA(v, glibc_atan_tail(c, v), gt::hpi1);
+                z = XADD(XSUB(gt::hpi, c[1]), zz);
+            }
+        }
+    } else {
+        if (ax < ay) {                                      // (iii) pi/2 + atan(ax/ay)
+            if (small) {
+                const double v = XMUL(u, u);
+                const double zz = XMUL(XMUL(u, v), glibc_atan_poly(v));
+                const double t2 = XADD(u, gt::hpi);
+                const double cor = XADD(XSUB(gt::hpi, t2), u);
+                z = XADD(XADD(XADD(XADD(cor, gt::hpi1), du), zz), t2);
+            } else {
+                const double v = XADD(XSUB(u, c[0]), du);
+                const double zz = XFMA(v, glibc_atan_tail(c, v), gt::hpi1);
+                z = XADD(XADD(gt::hpi, c[1]), zz);
+            }
+        } else {                                            // (iv) pi - atan(ay/ax)
+            if (small) {
+                const double v = XMUL(u, u);
+                const double zz = XMUL(XMUL(u, v), glibc_atan_poly(v));
+                const double t2 = XSUB(gt::opi, u);
+                const double cor = XSUB(XSUB(gt::opi, t2), u);
+                z = XADD(XSUB(XSUB(XADD(cor, gt::opi1), du), zz), t2);
+            } else {
+                const double v = XADD(XSUB(u, c[0]), du);
+                const double zz = GT_FNMA(v, glibc_atan_tail(c, v), gt::opi1);
+                z = XADD(XSUB(gt::opi, c[1]), zz);
+            }
+        }
+    }
+    return copysign(z, y);
+}
+
 }  // namespace nirrt

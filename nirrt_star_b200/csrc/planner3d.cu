@@ -926,7 +926,7 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
         for (int i = 0; i < 3; i++) xnew[i] = XADD(xn[i], XMUL(dist, dir[i]));
     } else {
         // theta = math.atan2(dy, dx); node_new = start + dist * [cos(theta), sin(theta)]
-        const double theta = cr_atan2(d1, d0);
+        const double theta = glibc_atan2(d1, d0);      // math.atan2, glibc kernels restated (glibc_trig.cuh)
         if (!(dist < c->step_len)) dist = c->step_len;
         const double sn = glibc_sin(theta), cs = glibc_cos(theta);     // math.sin / math.cos (glibc_trig.cuh)
         xnew[0] = XADD(xn[0], XMUL(dist, cs));
@@ -3335,6 +3335,23 @@ extern "C" int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int
 __global__ void k_sincos(const double *x, long long n, double *s, double *c) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) { s[i] = glibc_sin(x[i]); c[i] = glibc_cos(x[i]); }
+}
+__global__ void k_atan2(const double *y, const double *x, long long n, double *out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = glibc_atan2(y[i], x[i]);
+}
+extern "C" int nirrt_atan2_sync(const double *y, const double *x, int64_t n, double *out, void *stream) {
+    if (n < 0 || (n > 0 && (!x || !y || !out))) return fail(NIRRT_ERR_INVALID, "nirrt_atan2_sync: bad argument");
+    if (n == 0) return NIRRT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    TempBufs t;
+    double *dy, *dx, *dout;
+    TRY(t.up(y, (size_t)n, s, &dy)); TRY(t.up(x, (size_t)n, s, &dx)); TRY(t.make<double>((size_t)n, &dout));
+    k_atan2<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dy, dx, n, dout);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
 }
 extern "C" int nirrt_sincos_sync(const double *x, int64_t n, double *out_sin, double *out_cos, void *stream) {
     if (n < 0 || (n > 0 && (!x || !out_sin || !out_cos))) return fail(NIRRT_ERR_INVALID, "nirrt_sincos_sync: bad argument");

@@ -39,6 +39,7 @@ void hh_valid(long m, const double *p, unsigned char *out) { for (long i = 0; i 
 // ---- 2D
 double hh_np_hypot(double a, double b) { return np_hypot(a, b); }
 double hh_cr_atan2(double y, double x) { return cr_atan2(y, x); }
+void hh_glibc_atan2(long n, const double *y, const double *x, double *out) { for (long i = 0; i < n; i++) out[i] = glibc_atan2(y[i], x[i]); }
 double hh_vecnorm2(double a, double b) { return vecnorm2(a, b); }
 double hh_rownorm2(double a, double b) { return rownorm2(a, b); }
 static Geom2 g2;

@@ -52,7 +52,7 @@ def test_planning_block_gap_matches_reference_golden(path):
     n = planner.num_vertices
     assert n == int(g["num_vertices"])
     assert np.array_equal(planner.vertex_parents[:n], g["parents"])
-    assert np.allclose(planner.vertices[:n], g["vertices"], rtol=0, atol=1e-9)
+    assert np.array_equal(planner.vertices[:n], g["vertices"])
     if kind == "irrt":
         assert list(planner.path_solutions) == list(g["solutions"])
     assert np.random.random() == float(g["next_random"])

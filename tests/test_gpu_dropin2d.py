@@ -37,7 +37,7 @@ def test_dropin_planner_matches_reference_golden(path):
         want_path = g["path"]
         if len(want_path):
             assert planner.check_success(planner.path)
-            assert np.allclose(planner.path, want_path, rtol=0, atol=1e-9)
+            assert np.array_equal(planner.path, want_path)
         else:
             assert len(planner.path) == 0
     else:
@@ -51,7 +51,7 @@ def test_dropin_planner_matches_reference_golden(path):
     assert n == int(g["num_vertices"])
     assert planner.vertices.shape == (1 + args.iter_max, 2) and planner.vertex_parents.shape == (1 + args.iter_max,)
     assert np.array_equal(planner.vertex_parents[:n], g["parents"])
-    assert np.allclose(planner.vertices[:n], g["vertices"], rtol=0, atol=1e-9)
+    assert np.array_equal(planner.vertices[:n], g["vertices"])
     if kind == "irrt":
         assert list(planner.path_solutions) == list(g["solutions"])
     assert np.random.random() == float(g["next_random"])

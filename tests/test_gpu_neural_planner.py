@@ -32,7 +32,7 @@ class ReplayWrapper:
             assert hashlib.sha1(np.ascontiguousarray(pc).tobytes()).hexdigest() == str(g["call_pc_sha1"][k]), f"cloud {k} differs"
             assert hashlib.sha1(start_mask.tobytes() + goal_mask.tobytes()).hexdigest() == str(g["call_mask_sha1"][k])
         else:
-            assert np.allclose(pc, g[f"call_pc{k}"], rtol=0, atol=1e-5), f"cloud {k} differs"
+            assert np.array_equal(pc, g[f"call_pc{k}"]), f"cloud {k} differs"
         pred = np.unpackbits(g["call_pred"][k])[:len(pc)].astype(np.int64)
         self.k += 1
         return pred, pred.astype(np.float32)
@@ -63,7 +63,7 @@ def test_neural_planner_matches_reference_golden(path):
     if mode == "planning":
         planner.planning(False)
         if len(g["path"]):
-            assert np.array_equal(planner.path, g["path"]) if dim == 3 else np.allclose(planner.path, g["path"], rtol=0, atol=1e-9)
+            assert np.array_equal(planner.path, g["path"])
         else:
             assert len(planner.path) == 0
     else:
@@ -77,10 +77,7 @@ def test_neural_planner_matches_reference_golden(path):
     n = planner.num_vertices
     assert n == int(g["num_vertices"])
     assert np.array_equal(planner.vertex_parents[:n], g["parents"])
-    if dim == 3:
-        assert np.array_equal(planner.vertices[:n], g["vertices"])
-    else:
-        assert np.allclose(planner.vertices[:n], g["vertices"], rtol=0, atol=1e-9)
+    assert np.array_equal(planner.vertices[:n], g["vertices"])
     if kind == "nirrt":
         assert list(planner.path_solutions) == list(g["solutions"])
     assert np.random.random() == float(g["next_random"])

@@ -19,3 +19,12 @@ def test_device_sin_cos_equal_libm():
     assert np.array_equal(s, np.sin(xs)) and np.array_equal(c, np.cos(xs))
     assert s[5] == math.sin(xs[5]) and c[5] == math.cos(xs[5])
     assert sincos(np.zeros(0))[0].shape == (0,)
+
+
+def test_device_atan2_equals_libm():
+    from nirrt_star_b200.batch import atan2
+    rng = np.random.default_rng(12)
+    for sy, sx in ((224, 224), (10, 10), (1, 1000), (1000, 1), (1e-3, 1), (1, 1e-3)):
+        y = rng.uniform(-sy, sy, 300000); x = rng.uniform(-sx, sx, 300000)
+        y[::7] = np.rint(y[::7]); x[::11] = np.rint(x[::11])
+        assert np.array_equal(atan2(y, x), np.array([math.atan2(a, b) for a, b in zip(y, x)]))

@@ -97,6 +97,26 @@ def test_glibc_sin_cos_restatement_equals_libm(hh):
     assert 0 < differ < 400
 
 
+def test_glibc_atan2_restatement_equals_libm(hh):
+    """math.atan2 of the 2D steer (rrt_star_2d.py:74): glibc 2.39's __ieee754_atan2 (FMA variant) restated -- all four
+    quadrants, polynomial and table branches, axis-aligned and integer arguments, extreme ratios."""
+    rng = np.random.default_rng(8)
+    dp = C.POINTER(C.c_double)
+    hh.hh_glibc_atan2.argtypes = [C.c_long, dp, dp, dp]
+    for sy, sx in ((224, 224), (10, 10), (1, 1000), (1000, 1), (1e-3, 1), (1, 1e-3), (1e-9, 1e-9), (1e200, 1e-200)):
+        y = rng.uniform(-sy, sy, 250000); x = rng.uniform(-sx, sx, 250000)
+        y[::7] = np.rint(y[::7]); x[::11] = np.rint(x[::11])
+        out = np.empty_like(y)
+        hh.hh_glibc_atan2(len(y), y.ctypes.data_as(dp), x.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        # math.atan2 is the C library's; np.arctan2 on arrays is numpy's own SIMD kernel (differs in ~8 % of last bits)
+        assert np.array_equal(out, np.array([math.atan2(a, b) for a, b in zip(y, x)]))
+    for y, x in ((0.0, 1.0), (0.0, -1.0), (-0.0, 1.0), (-0.0, -1.0), (1.0, 0.0), (-1.0, 0.0), (1.0, -0.0), (0.0, 0.0), (0.0, -0.0),
+                 (-0.0, -0.0), (3.0, 3.0), (-3.0, 3.0), (3.0, -3.0), (-3.0, -3.0), (1e-310, 1.0), (1.0, 1e-310)):
+        a = np.array([y]); b = np.array([x]); out = np.empty(1)
+        hh.hh_glibc_atan2(1, a.ctypes.data_as(dp), b.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        assert out[0] == math.atan2(y, x) and math.copysign(1, out[0]) == math.copysign(1, math.atan2(y, x)), (y, x)
+
+
 def test_pairwise_sum_matches_numpy(hh):
     rng = np.random.default_rng(4)
     for n in (1, 2, 7, 8, 9, 15, 16, 17, 31, 100, 128, 129, 300, 1000):
