@@ -59,6 +59,11 @@ def parse_args():
     ap.add_argument("--clouds", type=int, default=256, help="PointNet++ leg: clouds per batch per GPU (2048 points each)")
     ap.add_argument("--pn2-steps", type=int, default=20, help="PointNet++ leg: timed forwards")
     ap.add_argument("--no-pointnet2", action="store_true")
+    ap.add_argument("--nirrt-envs", type=int, default=512, help="NIRRT* leg: planning problems per GPU (BASELINE configs[3]/[4] shape)")
+    ap.add_argument("--nirrt-iter-max", type=int, default=10000)
+    ap.add_argument("--nirrt-iter-after", type=int, default=5000)
+    ap.add_argument("--no-nirrt", action="store_true")
+    ap.add_argument("--nirrt-only", action="store_true", help="run only the NIRRT* leg (profiling runs)")
     ap.add_argument("--pointnet2-only", action="store_true", help="run only the PointNet++ leg (profiling runs)")
     return ap.parse_args()
 
@@ -357,6 +362,56 @@ def bench_pointnet2(args, world, rank, local, peaks, cpu=True):
 
 
 # ------------------------------------------------------------------------------------------------
+# NIRRT* leg: the whole planner of BASELINE configs[3]/[4] -- informed + guidance-cloud sampling, cloud updates by
+# batched PointNet++ forwards -- through nirrt_star_b200.eval.plan_batch (what eval_planning_3d.py -p nirrt_star
+# -n pointnet2 does one problem at a time, eval_planning_3d.py:101-126)
+
+def bench_nirrt(args, world, rank, local):
+    import torch
+    import torch.distributed as dist
+    from nirrt_star_b200.eval import default_args, plan_batch
+    from nirrt_star_b200.synthetic import make_pointnet2_state, make_problem_3d
+    E = args.nirrt_envs
+    sd = make_pointnet2_state(0)
+    a = default_args(3, iter_max=args.nirrt_iter_max, iter_after_initial=args.nirrt_iter_after)
+    base = 100000 + rank * E
+    problems = [make_problem_3d(base + i) for i in range(E)]
+    seeds = [base + i for i in range(E)]
+    # warm-up on a slice (library load, engine + graph construction paths), untimed
+    plan_batch(problems[:max(8, E // 16)], "nirrt_star", 3, default_args(3, iter_max=300, iter_after_initial=50),
+               seeds=seeds[:max(8, E // 16)], state_dict=sd, device=local)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    stats = {}
+    t0 = time.perf_counter()
+    lists = plan_batch(problems, "nirrt_star", 3, a, seeds=seeds, state_dict=sd, device=local, stats_out=stats)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    iters = float(sum(len(x) for x in lists))
+    solved = int(sum(1 for x in lists if len(x) and np.isfinite(x[-1])))
+    agg = torch.tensor([el, iters, solved, stats.get("cloud_updates", 0), stats.get("forward_calls", 0), stats.get("update_seconds", 0.0)],
+                       device="cuda", dtype=torch.float64)
+    if world > 1:
+        mx = agg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = agg.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        el = float(mx[0]); iters = float(sm[1]); solved = int(sm[2])
+        upd, fwd, upd_s = float(sm[3]), float(sm[4]), float(mx[5])
+    else:
+        upd, fwd, upd_s = float(agg[3]), float(agg[4]), float(agg[5])
+    return {"metric": "NIRRT* env-iters/sec, whole planner incl. batched cloud updates (random_3d)", "value": iters / el, "unit": UNIT,
+            "seconds": el, "env_iterations": iters,
+            "config": {"workload": f"nirrt_star -n pointnet2 3D random_3d (BASELINE configs[3]/[4] shape): {E} problems/GPU in lock step, "
+                                   f"iter_max={a.iter_max}, iter_after_initial={a.iter_after_initial}, 2048-pt clouds (10240 raw samples), "
+                                   "synthetic checkpoint", "envs_per_gpu": E},
+            "problems_solved": solved, "problems_total": world * E,
+            "cloud_updates": upd, "pointnet2_forward_calls": fwd, "clouds_per_forward": upd / max(1.0, fwd),
+            "cloud_update_seconds": upd_s, "cloud_update_share_of_time": upd_s / el,
+            "what": "wall clock of plan_batch (max over ranks): device-side cloud sampling (MT19937 draws, filters, FPS) + masks + "
+                    "ONE PointNet++ forward per lock-step round + commit, interleaved with the lock-step planner iterations"}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 
 def main():
@@ -388,6 +443,11 @@ def main():
         pn2 = bench_pointnet2(args, world, rank, local, peaks, cpu=False)
         if rank == 0:
             print(json.dumps(pn2), flush=True)
+        return
+    if args.nirrt_only:
+        nr = bench_nirrt(args, world, rank, local)
+        if rank == 0:
+            print(json.dumps(nr), flush=True)
         return
 
     E, nodes, K, W, ips = args.envs, args.nodes, args.steps, args.warmup, args.iters_per_step
@@ -577,9 +637,12 @@ def main():
                           "GPU-grown snapshot and RNG states"}
 
     pn2 = None
+    nirrt = None
+    bp.close()
     if not args.no_pointnet2:
-        bp.close()
         pn2 = bench_pointnet2(args, world, rank, local, peaks)
+    if not args.no_nirrt:
+        nirrt = bench_nirrt(args, world, rank, local)
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -597,7 +660,7 @@ def main():
                "eval_variant": {"value": value_eval, "unit": UNIT, "ms_per_step": ms_eval / K, "ms_per_iteration": ms_eval / K / ips,
                                 "graph": graph_eval,
                                 "what": "planning_random loop body (adds goal-parent search + path length per iteration)"},
-               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2}
+               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2, "nirrt_star": nirrt}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -109,6 +109,29 @@ int nirrt_batch_set_guidance(nirrt_batch *b, double pc_sample_rate, double pc_up
 /* path_point_cloud_pred of one problem (nirrt_star_png_3d.py:172): points [n][3] f64 host */
 int nirrt_batch_set_cloud(nirrt_batch *b, int env, const double *points, int n, void *stream);
 
+/* ---- guidance clouds on the device (3D; datasets_3d/point_cloud_mask_utils_3d.py:83-113,132-200 + the mask
+ * helper datasets/point_cloud_mask_utils.py:20-31), for a list of `count` problems in one call:
+ *   envs[count]    problem indices;  kind[count]  0 = generate_rectangle_point_cloud_3d, 1 = ellipsoid_point_cloud_sampling_3d
+ *   params[count][12]  kind 1: M = C @ L (row major 3x3) and the ellipsoid centre, evaluated by the caller with numpy as
+ *                      the reference does (c_max ** 2 is libm pow); ignored for kind 0
+ *   n_points, n_raw    pc_n_points and pc_n_points * pc_over_sample_scale (nirrt_star_png_3d.py:141-156)
+ * Each problem's numpy MT19937 stream is consumed on the device exactly as the reference consumes it (3 * n_raw
+ * doubles), candidates are filtered at clearance 0 and farthest-point down-sampled (open3d semantics) when more than
+ * n_points survive.  Outputs, written to DEVICE buffers the caller owns (they are the PointNet++ engine's inputs):
+ * pc32 [count][n_points][3] f32, start / goal masks [count][n_points] f32 (|p - x_start| < neighbor_radius, strict);
+ * counts[count] (host) = points in each cloud (rows beyond it are zero; < n_points means a short cloud).  The three
+ * device buffers may all be NULL (the batch then uses internal scratch; callers that only want the points).  Waits for
+ * the stream.  The f64 clouds stay in the batch's workspace until the next call. */
+int nirrt_batch_sample_clouds_sync(nirrt_batch *b, const int *envs, int count, const int *kind, const double *params,
+                                   int n_points, int n_raw, double neighbor_radius, float *d_pc32, float *d_start_mask,
+                                   float *d_goal_mask, int *counts, void *stream);
+/* f64 clouds first .. first+count-1 of the last nirrt_batch_sample_clouds_sync call -> points [count][n_points][3] (host) */
+int nirrt_batch_read_sampled_clouds_sync(nirrt_batch *b, int first, int count, double *points, void *stream);
+/* path_point_cloud_pred = pc[path_pred.nonzero()[0]] (nirrt_star_png_3d.py:172) for the clouds of the last sample call:
+ * d_pred device int64 [count][n_points] (the engine's path_pred); sel = host list of cloud positions to commit (NULL:
+ * all).  Resumes the problems that were waiting for a cloud.  Enqueues only. */
+int nirrt_batch_commit_clouds(nirrt_batch *b, const int64_t *d_pred, const int *sel, int n_sel, void *stream);
+
 /* Tree snapshot in the reference's own layout: vertices [count][capacity][3] f64 (AoS),
  * parents [count][capacity] int64, n [count]  (RRTBase3D.vertices / vertex_parents / num_vertices,
  * rrt_base_3d.py:25-28) for problems env_begin .. env_begin+count-1. */

@@ -49,6 +49,24 @@ def rotation_to_world_frame_3d(x_start, x_goal):
     return U @ np.diag([1, 1, np.linalg.det(U) * np.linalg.det(V)]) @ V.T
 
 
+def ellipsoid_params_3d(x_start, x_goal, max_min_ratio):
+    """The scalars of ellipsoid_point_cloud_sampling_3d (datasets_3d/point_cloud_mask_utils_3d.py:132-160) that go
+    through numpy / libm on the host -- c_min (np.linalg.norm), the rotation (SVD), c_max ** 2 (libm pow), np.sqrt --
+    as the 12 numbers the device sampler takes: M = C @ L (row major) and the ellipsoid centre."""
+    x_start = np.asarray(x_start, dtype=np.float64); x_goal = np.asarray(x_goal, dtype=np.float64)
+    c_min = np.linalg.norm(x_goal - x_start)
+    a1 = (x_goal - x_start) / c_min
+    U, _, V = np.linalg.svd(np.outer(a1, [1, 0, 0]))
+    Crot = U @ np.diag([1, 1, np.linalg.det(U) * np.linalg.det(V)]) @ V.T
+    centre = (x_start + x_goal) / 2.
+    c_max = c_min * max_min_ratio
+    eps = 1e-6 if c_max ** 2 - c_min ** 2 < 0 else 0
+    r = np.zeros(3)
+    r[0] = c_max / 2
+    r[1] = r[2] = np.sqrt(c_max ** 2 - c_min ** 2 + eps) / 2
+    return np.concatenate([np.dot(Crot, np.diag(r)).reshape(9), centre])
+
+
 def seed_state(seed):
     """(key[624] uint32, pos) of ``np.random.seed(seed)``."""
     st = np.random.RandomState(seed).get_state()
@@ -176,6 +194,33 @@ class BatchPlanner3D:
     def set_cloud(self, env, points):
         pts = f64(points).reshape(-1, self.dim)
         check(self.L.nirrt_batch_set_cloud(self.h, int(env), dp(pts), len(pts), self.stream))
+
+    # ------------------------------------------------------------------ guidance clouds on the device (3D)
+    def sample_clouds(self, envs, kinds, params, n_points, n_raw, radius, d_pc32, d_start_mask, d_goal_mask):
+        """Device-side generate_rectangle_point_cloud_3d (kind 0) / ellipsoid_point_cloud_sampling_3d (kind 1) +
+        start / goal masks for the listed problems (include/nirrt_b200.h: nirrt_batch_sample_clouds_sync).
+        d_* are device pointers (ints) of f32 buffers [count][n_points][3] / [count][n_points].  Returns counts."""
+        envs = np.ascontiguousarray(envs, dtype=np.int32); kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+        params = np.ascontiguousarray(params, dtype=np.float64).reshape(len(envs), 12)
+        counts = np.zeros(len(envs), dtype=np.int32)
+        check(self.L.nirrt_batch_sample_clouds_sync(self.h, ip(envs), len(envs), ip(kinds), dp(params), int(n_points), int(n_raw),
+                                                    float(radius), C.c_void_p(d_pc32) if d_pc32 else None,
+                                                    C.c_void_p(d_start_mask) if d_start_mask else None,
+                                                    C.c_void_p(d_goal_mask) if d_goal_mask else None, ip(counts), self.stream))
+        return counts
+
+    def read_sampled_clouds(self, first, count, n_points):
+        out = np.zeros((count, n_points, 3))
+        check(self.L.nirrt_batch_read_sampled_clouds_sync(self.h, int(first), int(count), dp(out), self.stream))
+        return out
+
+    def commit_clouds(self, d_pred, sel=None):
+        """path_point_cloud_pred = cloud[pred != 0] for the clouds of the last sample_clouds call (all, or positions `sel`)."""
+        if sel is None:
+            check(self.L.nirrt_batch_commit_clouds(self.h, C.c_void_p(d_pred), None, 0, self.stream))
+        else:
+            sel = np.ascontiguousarray(sel, dtype=np.int32)
+            check(self.L.nirrt_batch_commit_clouds(self.h, C.c_void_p(d_pred), ip(sel), len(sel), self.stream))
 
     def close(self):
         if getattr(self, "h", None):

@@ -2240,6 +2240,8 @@ struct nirrt_batch {
     int64_t graph_builds, graph_replays, graph_fallbacks, graph_clock;
     int graph_iters; // iterations per graph replay
     RunCfg cfg;      // run parameters, handed to the device by k_set_budget at the start of every run
+    struct CloudWs *cloud_ws;   // device workspace of the guidance-cloud generator (allocated on first use)
+    int cloud_count;            // problems in the last nirrt_batch_sample_clouds_sync call
     cudaStream_t cs; // capture origin
     int device;
     size_t stride_bytes;
@@ -2316,6 +2318,7 @@ extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
     cudaSetDevice(b->device);
     for (void *p : b->allocs) cudaFree(p);
     if (b->h_ctl) cudaFreeHost(b->h_ctl);
+    free(b->cloud_ws);
     for (int g = 0; g < kMaxGroups; g++) {
         if (b->gs[g]) cudaStreamDestroy(b->gs[g]);
         if (b->ev_join[g]) cudaEventDestroy(b->ev_join[g]);
@@ -2351,6 +2354,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     nirrt_batch *b = new nirrt_batch();
     memset(&b->v, 0, sizeof(View));
     b->device = d->device; b->launches = 0; b->goal_lists = false; b->h_ctl = nullptr;
+    b->cloud_ws = nullptr; b->cloud_count = 0;
     b->groups = 1; b->ev_fork = nullptr;
     for (int g = 0; g < kMaxGroups; g++) {
         b->gs[g] = nullptr; b->ev_join[g] = nullptr; b->gs2[g] = nullptr;
@@ -3331,6 +3335,331 @@ extern "C" int nirrt_costs_sync(nirrt_batch *b, int env, const int64_t *idx, int
     return NIRRT_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Guidance-cloud generation on the device (3D worlds):
+//   generate_rectangle_point_cloud_3d     datasets_3d/point_cloud_mask_utils_3d.py:83-113   (kind 0)
+//   ellipsoid_point_cloud_sampling_3d     datasets_3d/point_cloud_mask_utils_3d.py:132-200  (kind 1)
+//   get_point_cloud_mask_around_points    datasets/point_cloud_mask_utils.py:20-31
+// for a LIST of problems at once, one CTA per problem, consuming each problem's own numpy MT19937 stream word for
+// word: kind 0 draws np.random.uniform(low, high, size=(n_raw, 3)) (row-major fill), kind 1 three vectors of n_raw
+// (radius, theta, phi).  The candidates are filtered with the reference's predicates at clearance 0
+// (points_in_balls_boxes / points_validity_3d), compacted in order, and -- if more than n_points survive --
+// down-sampled by farthest point sampling with open3d's semantics (start 0, f64 squared distances, first arg-max;
+// third-party arithmetic, parity unpinned).  The cloud never leaves HBM: its float32 copy and the start / goal
+// neighbourhood masks go straight into the PointNet++ engine's input buffers, and k_cloud_commit turns the
+// network's prediction into the problem's path_point_cloud_pred (nirrt_star_png_3d.py:172).
+// kind 1 parameters (host, a handful of scalars per update, evaluated with numpy exactly as the reference does):
+// M = C @ L (3x3, row major) and the ellipsoid centre; the device evaluates np.dot(M, samples.T).T + centre as the
+// BLAS kernel does, fma(M2, z, fma(M1, y, M0 * x)) + c (probed on 10240 columns), with glibc's sin / cos.
+struct CloudWs {
+    uint32_t *words;   // [E][6 * n_raw]   raw MT19937 words of this update
+    double *cand;      // [E][n_raw][3]    valid candidates, in draw order
+    double *cloud;     // [E][n_points][3] the sampled cloud (after down-sampling)
+    int *cand_cnt;     // [E]
+    int *cloud_cnt;    // [E]
+    int *envs;         // [E]              device copy of the env list of the current update
+    int *kind;         // [E]
+    double *params;    // [E][12]
+    float *pc32, *smask, *gmask;   // network inputs when the caller does not supply its own buffers
+    int n_raw, n_points;
+};
+
+__global__ void __launch_bounds__(256) k_cloud_draw(View v, CloudWs w) {
+    const int k = blockIdx.x, e = w.envs[k], tid = threadIdx.x;
+    MtState *st = v.mt + e;
+    uint32_t *wb = w.words + (size_t)k * 6 * w.n_raw;
+    const int total = 6 * w.n_raw;
+    __shared__ int s_pos, s_cur, s_has;
+    if (tid == 0) { s_pos = st->pos; s_cur = st->cur; s_has = st->has_next; }
+    __syncthreads();
+    // ---- the next `total` words of the stream (mt19937_gen block by block, three barrier-separated phases)
+    for (int produced = 0; produced < total;) {
+        int pos = s_pos, cur = s_cur;
+        if (pos == 624) {
+            const uint32_t *o = st->key[cur];
+            uint32_t *nx = st->key[cur ^ 1];
+            if (!s_has) {
+                for (int i = tid; i < 227; i += blockDim.x) nx[i] = o[i + 397] ^ mt_twist(o[i], o[i + 1]);
+                __syncthreads();
+                for (int i = 227 + tid; i < 454; i += blockDim.x) nx[i] = nx[i - 227] ^ mt_twist(o[i], o[i + 1]);
+                __syncthreads();
+                for (int i = 454 + tid; i < 623; i += blockDim.x) nx[i] = nx[i - 227] ^ mt_twist(o[i], o[i + 1]);
+                __syncthreads();
+                if (tid == 0) nx[623] = nx[396] ^ mt_twist(o[623], nx[0]);
+            }
+            __syncthreads();
+            if (tid == 0) { s_cur = cur ^ 1; s_pos = 0; s_has = 0; }
+            __syncthreads();
+            pos = 0; cur ^= 1;
+        }
+        const int take = min(624 - pos, total - produced);
+        const uint32_t *kk = st->key[cur];
+        for (int i = tid; i < take; i += blockDim.x) wb[produced + i] = kk[pos + i];
+        __syncthreads();
+        if (tid == 0) s_pos = pos + take;
+        produced += take;
+        __syncthreads();
+    }
+    if (tid == 0) { st->pos = s_pos; st->cur = s_cur; st->has_next = 0; }
+    // ---- candidates, validity, ordered compaction
+    __shared__ Geom3 g;
+    stage_geom<3>(&g, v, e);
+    __syncthreads();
+    if (tid == 0) g.clearance = 0.0;                 // the samplers are called with clearance = 0
+    __shared__ int s_wcnt[8];
+    __shared__ int s_total;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    const int kind = w.kind[k];
+    const double *P = w.params + (size_t)k * 12;
+    double lo[3], sc[3];
+    for (int d = 0; d < 3; d++) { lo[d] = XADD(g.range[2 * d], 0.0); sc[d] = XSUB(XSUB(g.range[2 * d + 1], 0.0), lo[d]); }
+    double *cand = w.cand + (size_t)k * w.n_raw * 3;
+    const int n_raw = w.n_raw;
+    for (int base = 0; base < n_raw; base += blockDim.x) {
+        const int i = base + tid;
+        bool keep = false;
+        double p[3] = {0.0, 0.0, 0.0};
+        if (i < n_raw) {
+            if (kind == 0) {
+                for (int d = 0; d < 3; d++) {
+                    const int q = 2 * (3 * i + d);
+                    p[d] = XADD(lo[d], XMUL(sc[d], mt_double(wb[q], wb[q + 1])));
+                }
+                keep = !point_inside_obs(g, p);
+            } else {
+                const double r = mt_double(wb[2 * i], wb[2 * i + 1]);                                  // 0.0 + 1.0 * u == u
+                const double th = XMUL(3.141592653589793, mt_double(wb[2 * (n_raw + i)], wb[2 * (n_raw + i) + 1]));
+                const double ph = XMUL(6.283185307179586, mt_double(wb[2 * (2 * n_raw + i)], wb[2 * (2 * n_raw + i) + 1]));
+                const double st_ = glibc_sin(th), ct = glibc_cos(th), sp = glibc_sin(ph), cp = glibc_cos(ph);
+                const double rs = XMUL(r, st_);
+                const double x = XMUL(rs, cp), y = XMUL(rs, sp), z = XMUL(r, ct);
+                for (int d = 0; d < 3; d++)
+                    p[d] = XADD(XFMA(P[3 * d + 2], z, XFMA(P[3 * d + 1], y, XMUL(P[3 * d], x))), P[9 + d]);
+                keep = point_valid(g, p);
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int wi = tid >> 5, l = tid & 31;
+        if (l == 0) s_wcnt[wi] = __popc(bal);
+        __syncthreads();
+        int off = s_total;
+        for (int q = 0; q < wi; q++) off += s_wcnt[q];
+        if (keep) {
+            double *o = cand + (size_t)(off + __popc(bal & ((1u << l) - 1u))) * 3;
+            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int q = 0; q < 8; q++) t += s_wcnt[q]; s_total += t; }
+        __syncthreads();
+    }
+    if (tid == 0) w.cand_cnt[k] = s_total;
+}
+
+constexpr int kFpsThreads = 1024, kFpsPPT = 16;
+// farthest point down-sampling of pts[0..n) to npoint points starting at `start` (open3d semantics); all threads of a
+// 1024-thread CTA; visit(it, index) is called by thread 0 for every selected point
+template <typename F>
+__device__ __forceinline__ void fps_f64_body(const double *pts, int n, int npoint, int start, F &&visit) {
+    __shared__ double s_d[2][32];
+    __shared__ int s_i[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double px[kFpsPPT], py[kFpsPPT], pz[kFpsPPT], dist[kFpsPPT];
+#pragma unroll
+    for (int j = 0; j < kFpsPPT; j++) {
+        const int i = tid + j * kFpsThreads;
+        const bool in = i < n;
+        px[j] = in ? pts[3 * (size_t)i] : 0.0; py[j] = in ? pts[3 * (size_t)i + 1] : 0.0; pz[j] = in ? pts[3 * (size_t)i + 2] : 0.0;
+        dist[j] = in ? XINF : -1.0;
+    }
+    int far = start;
+    for (int it = 0; it < npoint; it++) {
+        if (tid == 0) visit(it, far);
+        const double cx = __ldg(pts + 3 * (size_t)far), cy = __ldg(pts + 3 * (size_t)far + 1), cz = __ldg(pts + 3 * (size_t)far + 2);
+        double bd = -2.0; int bi = INT_MAX;
+#pragma unroll
+        for (int j = 0; j < kFpsPPT; j++) {
+            const double d = sq3_rows(XSUB(px[j], cx), XSUB(py[j], cy), XSUB(pz[j], cz));
+            if (d < dist[j]) dist[j] = d;
+            if (dist[j] > bd) { bd = dist[j]; bi = tid + j * kFpsThreads; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        const int slot = it & 1;
+        if (lane == 0) { s_d[slot][warp] = bd; s_i[slot][warp] = bi; }
+        __syncthreads();
+        bd = s_d[slot][lane]; bi = s_i[slot][lane];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        far = bi;
+    }
+}
+
+// down-sampling + the network's inputs: pc32 [count][n_points][3], start / goal masks [count][n_points]
+__global__ void __launch_bounds__(kFpsThreads) k_cloud_fps(View v, CloudWs w, double radius, float *pc32, float *smask, float *gmask) {
+    const int k = blockIdx.x, e = w.envs[k], tid = threadIdx.x;
+    const int n = w.cand_cnt[k], np_ = w.n_points;
+    const double *cand = w.cand + (size_t)k * w.n_raw * 3;
+    double *cloud = w.cloud + (size_t)k * np_ * 3;
+    int m;
+    if (n > np_) {
+        m = np_;
+        fps_f64_body(cand, n, np_, 0, [&](int it, int idx) {
+            cloud[3 * (size_t)it] = cand[3 * (size_t)idx]; cloud[3 * (size_t)it + 1] = cand[3 * (size_t)idx + 1];
+            cloud[3 * (size_t)it + 2] = cand[3 * (size_t)idx + 2];
+        });
+    } else {
+        m = n;
+        for (int i = tid; i < 3 * n; i += blockDim.x) cloud[i] = cand[i];
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) w.cloud_cnt[k] = m;
+    const EnvCtl *c = v.ctl + e;
+    for (int i = tid; i < np_; i += blockDim.x) {
+        const size_t o = (size_t)k * np_ + i;
+        if (i < m) {
+            const double x = cloud[3 * (size_t)i], y = cloud[3 * (size_t)i + 1], z = cloud[3 * (size_t)i + 2];
+            pc32[3 * o] = (float)x; pc32[3 * o + 1] = (float)y; pc32[3 * o + 2] = (float)z;
+            // np.linalg.norm(pc[:, None] - p, axis=2) < radius  (strict)
+            smask[o] = rownorm3(XSUB(x, c->start[0]), XSUB(y, c->start[1]), XSUB(z, c->start[2])) < radius ? 1.f : 0.f;
+            gmask[o] = rownorm3(XSUB(x, c->goal[0]), XSUB(y, c->goal[1]), XSUB(z, c->goal[2])) < radius ? 1.f : 0.f;
+        } else {
+            pc32[3 * o] = pc32[3 * o + 1] = pc32[3 * o + 2] = 0.f; smask[o] = gmask[o] = 0.f;
+        }
+    }
+}
+
+// path_point_cloud_pred = pc[path_pred.nonzero()[0]] (nirrt_star_png_3d.py:172) and the resume of the paused problem
+__global__ void __launch_bounds__(256) k_cloud_commit(View v, CloudWs w, const long long *pred, const int *sel) {
+    const int k = sel ? sel[blockIdx.x] : blockIdx.x, e = w.envs[k], tid = threadIdx.x;
+    const int m = w.cloud_cnt[k], np_ = w.n_points;
+    const double *cloud = w.cloud + (size_t)k * np_ * 3;
+    const long long *pr = pred + (size_t)k * np_;
+    double *out = v.pc + (size_t)e * v.pc_cap * 3;
+    __shared__ int s_wcnt[8];
+    __shared__ int s_total;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += blockDim.x) {
+        const int i = base + tid;
+        const bool keep = i < m && pr[i] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int wi = tid >> 5, l = tid & 31;
+        if (l == 0) s_wcnt[wi] = __popc(bal);
+        __syncthreads();
+        int off = s_total;
+        for (int q = 0; q < wi; q++) off += s_wcnt[q];
+        if (keep) {
+            double *o = out + (size_t)(off + __popc(bal & ((1u << l) - 1u))) * 3;
+            o[0] = cloud[3 * (size_t)i]; o[1] = cloud[3 * (size_t)i + 1]; o[2] = cloud[3 * (size_t)i + 2];
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int q = 0; q < 8; q++) t += s_wcnt[q]; s_total += t; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        EnvCtl *c = v.ctl + e;
+        c->n_pc = s_total;
+        if (c->state == ST_WAIT_CLOUD) c->state = c->saved_state;
+    }
+}
+
+static int ensure_cloud_ws(nirrt_batch *b, int n_points, int n_raw) {
+    View &v = b->v;
+    if (b->cloud_ws && b->cloud_ws->n_raw == n_raw && b->cloud_ws->n_points == n_points) return NIRRT_OK;
+    if (b->cloud_ws) return fail(NIRRT_ERR_INVALID, "guidance-cloud workspace was created for other n_points / n_raw");
+    CloudWs *w = (CloudWs *)calloc(1, sizeof(CloudWs));
+    if (!w) return fail(NIRRT_ERR_CUDA, "out of host memory");
+    w->n_raw = n_raw; w->n_points = n_points;
+    void *p = nullptr;
+    const size_t E = (size_t)v.E;
+#define WS_ALLOC(field, type, count) do { int _r = dalloc(b, &p, sizeof(type) * (count)); if (_r) { free(w); return _r; } w->field = (type *)p; } while (0)
+    WS_ALLOC(words, uint32_t, E * 6 * n_raw);
+    WS_ALLOC(cand, double, E * 3 * n_raw);
+    WS_ALLOC(cloud, double, E * 3 * n_points);
+    WS_ALLOC(cand_cnt, int, E); WS_ALLOC(cloud_cnt, int, E); WS_ALLOC(envs, int, E); WS_ALLOC(kind, int, E);
+    WS_ALLOC(params, double, E * 12);
+    WS_ALLOC(pc32, float, E * 3 * n_points); WS_ALLOC(smask, float, E * n_points); WS_ALLOC(gmask, float, E * n_points);
+#undef WS_ALLOC
+    if (!v.pc) {
+        int r = dalloc(b, &p, sizeof(double) * 3 * E * v.pc_cap);
+        if (r) { free(w); return r; }
+        v.pc = (double *)p;
+    }
+    b->cloud_ws = w;
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_sample_clouds_sync(nirrt_batch *b, const int *envs, int count, const int *kind, const double *params,
+                                              int n_points, int n_raw, double neighbor_radius, float *d_pc32, float *d_start_mask,
+                                              float *d_goal_mask, int *counts, void *stream) {
+    if (!b || !envs || !kind || !params || !counts) return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: null argument");
+    if ((d_pc32 == nullptr) != (d_start_mask == nullptr) || (d_pc32 == nullptr) != (d_goal_mask == nullptr))
+        return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: pass all three device buffers or none");
+    View &v = b->v;
+    if (v.dim != 3) return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: 3D batches only");
+    if (count < 1 || count > v.E) return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: bad problem count");
+    if (n_points < 1 || n_points > v.pc_cap || n_raw < n_points || n_raw > kFpsThreads * kFpsPPT)
+        return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: need 1 <= n_points <= 4096 and n_points <= n_raw <= 16384");
+    for (int k = 0; k < count; k++)
+        if (envs[k] < 0 || envs[k] >= v.E || kind[k] < 0 || kind[k] > 1) return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: bad env / kind");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    TRY(ensure_cloud_ws(b, n_points, n_raw));
+    CloudWs &w = *b->cloud_ws;
+    CUDA_TRY(cudaMemcpyAsync(w.envs, envs, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(w.kind, kind, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(w.params, params, sizeof(double) * 12 * count, cudaMemcpyHostToDevice, s));
+    k_cloud_draw<<<count, 256, 0, s>>>(v, w);
+    if (!d_pc32) { d_pc32 = w.pc32; d_start_mask = w.smask; d_goal_mask = w.gmask; }
+    k_cloud_fps<<<count, kFpsThreads, 0, s>>>(v, w, neighbor_radius, d_pc32, d_start_mask, d_goal_mask);
+    CHECK_LAUNCH();
+    b->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(counts, w.cloud_cnt, sizeof(int) * count, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    b->cloud_count = count;
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_read_sampled_clouds_sync(nirrt_batch *b, int first, int count, double *points, void *stream) {
+    if (!b || !b->cloud_ws || !points || first < 0 || count < 1 || first + count > b->cloud_count)
+        return fail(NIRRT_ERR_INVALID, "nirrt_batch_read_sampled_clouds_sync: bad argument");
+    const CloudWs &w = *b->cloud_ws;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaMemcpyAsync(points, w.cloud + (size_t)first * w.n_points * 3, sizeof(double) * 3 * (size_t)count * w.n_points,
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_batch_commit_clouds(nirrt_batch *b, const int64_t *d_pred, const int *sel, int n_sel, void *stream) {
+    if (!b || !b->cloud_ws || !d_pred || n_sel < 0 || n_sel > b->cloud_count) return fail(NIRRT_ERR_INVALID, "nirrt_batch_commit_clouds: bad argument");
+    const CloudWs &w = *b->cloud_ws;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(b->device));
+    if (sel) {
+        if (n_sel == 0) return NIRRT_OK;
+        for (int i = 0; i < n_sel; i++) if (sel[i] < 0 || sel[i] >= b->cloud_count) return fail(NIRRT_ERR_INVALID, "nirrt_batch_commit_clouds: bad selection");
+        CUDA_TRY(cudaMemcpyAsync(w.kind, sel, sizeof(int) * n_sel, cudaMemcpyHostToDevice, s));     // kind[] is free again: selection list
+        k_cloud_commit<<<n_sel, 256, 0, s>>>(b->v, w, (const long long *)d_pred, w.kind);
+    } else {
+        k_cloud_commit<<<b->cloud_count, 256, 0, s>>>(b->v, w, (const long long *)d_pred, nullptr);
+    }
+    CHECK_LAUNCH();
+    b->launches += 1;
+    return NIRRT_OK;
+}
+
 // ---- math.sin / math.cos of the reference's runtime (glibc 2.39 kernels restated, glibc_trig.cuh), element-wise
 __global__ void k_sincos(const double *x, long long n, double *s, double *c) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -3416,48 +3745,8 @@ extern "C" int nirrt_batch_time_scan_sync(nirrt_batch *b, int which, int reps, f
 // 196-199): start at `start`, running minimum of the squared distance (dx*dx + dy*dy) + dz*dz in
 // f64, next = first argmax.  One CTA; distances live in registers, the selected point's
 // coordinates are re-read from L2 each step.
-constexpr int kFpsThreads = 1024, kFpsPPT = 16;
 __global__ void __launch_bounds__(kFpsThreads) k_fps_f64(const double *pts, int n, int npoint, int start, long long *out) {
-    __shared__ double s_d[2][32];
-    __shared__ int s_i[2][32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double px[kFpsPPT], py[kFpsPPT], pz[kFpsPPT], dist[kFpsPPT];
-#pragma unroll
-    for (int j = 0; j < kFpsPPT; j++) {
-        const int i = tid + j * kFpsThreads;
-        const bool in = i < n;
-        px[j] = in ? pts[3 * (size_t)i] : 0.0; py[j] = in ? pts[3 * (size_t)i + 1] : 0.0; pz[j] = in ? pts[3 * (size_t)i + 2] : 0.0;
-        dist[j] = in ? XINF : -1.0;
-    }
-    int far = start;
-    for (int it = 0; it < npoint; it++) {
-        if (tid == 0) out[it] = far;
-        const double cx = __ldg(pts + 3 * (size_t)far), cy = __ldg(pts + 3 * (size_t)far + 1), cz = __ldg(pts + 3 * (size_t)far + 2);
-        double bd = -2.0; int bi = INT_MAX;
-#pragma unroll
-        for (int j = 0; j < kFpsPPT; j++) {
-            const double d = sq3_rows(XSUB(px[j], cx), XSUB(py[j], cy), XSUB(pz[j], cz));
-            if (d < dist[j]) dist[j] = d;
-            if (dist[j] > bd) { bd = dist[j]; bi = tid + j * kFpsThreads; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-        const int slot = it & 1;
-        if (lane == 0) { s_d[slot][warp] = bd; s_i[slot][warp] = bi; }
-        __syncthreads();
-        bd = s_d[slot][lane]; bi = s_i[slot][lane];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-        far = bi;
-    }
+    fps_f64_body(pts, n, npoint, start, [&](int it, int idx) { out[it] = idx; });
 }
 
 extern "C" int nirrt_fps_f64_sync(const double *points, int64_t n, int npoint, int start, int64_t *out_idx, void *stream) {

@@ -1,12 +1,46 @@
-"""datasets_3d/point_cloud_mask_utils_3d.py drop-in: guidance point-cloud generation (SURVEY.md row
-f1).  Random draws stay on the process-global numpy stream exactly as in the reference; the
-obstacle / range filters run as CUDA predicates (nirrt_points_check_sync) and the farthest-point
-down-sampling as a CUDA kernel (nirrt_fps_f64_sync) with open3d's semantics (start index 0, f64
-squared distances, first argmax; third-party arithmetic, parity unpinned -- SURVEY.md 8c)."""
+"""datasets_3d/point_cloud_mask_utils_3d.py drop-in: guidance point-cloud generation with the
+reference's function names and arguments, executed on the device (nirrt_batch_sample_clouds_sync): the uniform /
+(r, theta, phi) draws come from the process-global numpy MT19937 stream, which is handed to the device and handed back
+(the stream position afterwards is exactly the reference's), the obstacle / range filters are the CUDA predicates and
+the down-sampling is farthest point sampling with open3d's semantics (start index 0, f64 squared distances, first
+argmax; third-party arithmetic, parity unpinned -- SURVEY.md 8c).  Only the handful of scalars that go through
+numpy's SVD / libm pow (batch.ellipsoid_params_3d) are evaluated on the host."""
 import numpy as np
 
-from nirrt_star_b200.batch import fps_f64
-from path_planning_classes_3d.collision_check_utils_3d import points_in_balls_boxes, points_validity_3d
+from nirrt_star_b200.batch import BatchPlanner3D, ellipsoid_params_3d, fps_f64
+
+_cache = {}
+
+
+def _context(env, n_points, n_raw):
+    """A one-problem batch holding the world (obstacle table, ranges) and the sampler workspace; cached per world."""
+    b = np.asarray(env.obs_ball, dtype=np.float64).reshape(-1, 4)
+    x = np.asarray(env.obs_box, dtype=np.float64).reshape(-1, 6)
+    key = (b.tobytes(), x.tobytes(), tuple(map(float, env.x_range + env.y_range + env.z_range)), int(n_points), int(n_raw))
+    ctx = _cache.get(key)
+    if ctx is None:
+        if env.x_range[0] != 0 or env.y_range[0] != 0 or env.z_range[0] != 0:
+            raise ValueError("ranges must start at 0 (Env.x_range = (0, width), rrt_env_3d.py:6-9)")
+        if len(_cache) > 16:
+            for c in _cache.values():
+                c.close()
+            _cache.clear()
+        problem = {"x_start": (0., 0., 0.), "x_goal": (1., 0., 0.), "search_radius": 1.0,
+                   "env_dict": {"env_dims": [env.y_range[1], env.x_range[1], env.z_range[1]],
+                                "ball_obstacles": b.tolist(), "box_obstacles": x.tolist()}}
+        ctx = BatchPlanner3D([problem], 1, clearance=0)
+        _cache[key] = ctx
+    return ctx
+
+
+def _sample(env, kind, params, n_points, n_raw):
+    ctx = _context(env, n_points, n_raw)
+    st = np.random.get_state()
+    ctx.set_rng([(st[1], st[2])])
+    count = int(ctx.sample_clouds([0], [kind], params, n_points, n_raw, 1.0, None, None, None)[0])
+    key, pos = ctx.get_rng()[0]
+    np.random.set_state(("MT19937", key, pos, 0, 0.0))
+    return ctx.read_sampled_clouds(0, 1, n_points)[0, :count].copy()
 
 
 def farthest_point_sample_open3d(points, npoint):
@@ -17,63 +51,14 @@ def farthest_point_sample_open3d(points, npoint):
 
 def generate_rectangle_point_cloud_3d(env, n_points, over_sample_scale=5, use_open3d=True, clearance=0):
     """point_cloud_mask_utils_3d.py:83-113"""
-    point_cloud = np.random.uniform(
-        low=(env.x_range[0] + clearance, env.y_range[0] + clearance, env.z_range[0] + clearance),
-        high=(env.x_range[1] - clearance, env.y_range[1] - clearance, env.z_range[1] - clearance),
-        size=(n_points * over_sample_scale, 3),
-    )
-    in_obs = points_in_balls_boxes(
-        point_cloud,
-        np.array(env.obs_ball).astype(np.float64),
-        np.array(env.obs_box).astype(np.float64),
-        clearance=clearance,
-    )
-    point_cloud = point_cloud[(1 - in_obs).astype(bool)]
-    if len(point_cloud) > n_points:
-        point_cloud = farthest_point_sample_open3d(point_cloud, n_points)
-    return point_cloud
-
-
-def RotationToWorldFrame(x_start, x_goal, L):
-    """point_cloud_mask_utils_3d.py:117-129"""
-    a1 = (x_goal - x_start) / L
-    M = np.outer(a1, [1, 0, 0])
-    U, S, V = np.linalg.svd(M)
-    C = U @ np.diag([1, 1, np.linalg.det(U) * np.linalg.det(V)]) @ V.T
-    return C
+    if clearance != 0:
+        raise NotImplementedError("the device sampler implements the planners' call (clearance = 0)")
+    return _sample(env, 0, np.zeros(12), n_points, n_points * over_sample_scale)
 
 
 def ellipsoid_point_cloud_sampling_3d(start_point, goal_point, max_min_ratio, env, n_points=1000, n_raw_samples=10000,
                                       clearance=0):
     """point_cloud_mask_utils_3d.py:132-200"""
-    c_min = np.linalg.norm(goal_point - start_point)
-    C = RotationToWorldFrame(start_point, goal_point, c_min)
-    x_center = (start_point + goal_point) / 2.
-    c_max = c_min * max_min_ratio
-    if c_max ** 2 - c_min ** 2 < 0:
-        eps = 1e-6
-    else:
-        eps = 0
-    r = np.zeros(3)
-    r[0] = c_max / 2
-    for i in [1, 2]:
-        r[i] = np.sqrt(c_max ** 2 - c_min ** 2 + eps) / 2
-    L = np.diag(r)
-
-    radius = np.random.uniform(0.0, 1.0, n_raw_samples)
-    theta = np.random.uniform(0, np.pi, n_raw_samples)
-    phi = np.random.uniform(0, 2 * np.pi, n_raw_samples)
-    samples_x = radius * np.sin(theta) * np.cos(phi)
-    samples_y = radius * np.sin(theta) * np.sin(phi)
-    samples_z = radius * np.cos(theta)
-    samples = np.array([samples_x, samples_y, samples_z]).T
-    point_cloud = np.dot(np.dot(C, L), samples.T).T + x_center
-
-    obs_ball = np.array(env.obs_ball).astype(np.float64) if len(env.obs_ball) > 0 else None
-    obs_box = np.array(env.obs_box).astype(np.float64) if len(env.obs_box) > 0 else None
-    valid_flag = points_validity_3d(point_cloud, obs_ball, obs_box, env.x_range, env.y_range, env.z_range,
-                                    obstacle_clearance=clearance, range_clearance=clearance)
-    point_cloud = point_cloud[valid_flag]
-    if len(point_cloud) > n_points:
-        point_cloud = farthest_point_sample_open3d(point_cloud, n_points)
-    return point_cloud
+    if clearance != 0:
+        raise NotImplementedError("the device sampler implements the planners' call (clearance = 0)")
+    return _sample(env, 1, ellipsoid_params_3d(start_point, goal_point, max_min_ratio), n_points, n_raw_samples)

@@ -12,6 +12,7 @@ Neural planners (nrrt_star / nirrt_star): guidance clouds are generated per prob
 own numpy stream (host, same code as the drop-in classes), classified in ONE batched PointNet++
 forward for all problems that wait for a cloud at the same lock-step iteration, and uploaded.
 """
+import time
 import types
 
 import numpy as np
@@ -70,13 +71,16 @@ class _CloudMaker:
 
 
 def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, classify=None, device=0, chunk=256,
-               distributed=False, return_planner=False):
+               distributed=False, return_planner=False, host_clouds=False, stats_out=None):
     """path_len_list of every problem (global order on every rank when ``distributed``).
 
     planner: 'rrt_star' | 'irrt_star' | 'nrrt_star' | 'nirrt_star'
     state_dict: PointNet++ ``model_state_dict`` for the neural planners (the sm_100a engine is built
         from it), or pass ``classify(list_of_(pc, start_mask, goal_mask)) -> list_of_path_pred`` to
         supply predictions some other way (tests replay recorded ones).
+    host_clouds: force the host (numpy) guidance-cloud generation also for 3D (the device path is the default there).
+    stats_out: dict that receives {iterations, cloud_updates, forward_calls, clouds_classified, short_clouds,
+        update_seconds, plan_seconds} of this rank's shard.
     """
     import torch
     args = default_args(dim) if args is None else args
@@ -101,13 +105,15 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
             makers = [_CloudMaker(dim, p, args) for p in local]
             gens = [torch.Generator().manual_seed(int(s)) for s in lseeds]
             engine = None
+            from .pointnet2 import NPOINTS, PointNet2Engine
+            from .dropin import install as _install
+            _install()
+            from datasets.point_cloud_mask_utils import get_point_cloud_mask_around_points as get_mask
+            short_engines = {}
             if classify is None:
-                from .pointnet2 import NPOINTS, PointNet2Engine
                 if state_dict is None:
                     raise ValueError("neural planners need state_dict= or classify=")
                 engine = PointNet2Engine(state_dict, n_points=args.pc_n_points, max_batch=E, device=device)
-
-                short_engines = {}
 
                 def classify(items, envs):
                     # torch.randint on each problem's own generator, in problem order (pointnet2_utils.py:77)
@@ -139,13 +145,10 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                     return user([(it[0].astype(np.float32), it[1], it[2]) for it in items], envs)
 
             bp.set_guidance(args.pc_sample_rate, args.pc_update_cost_ratio if variant == _B.VARIANT_NIRRT_STAR else 0.0)
+            stats = {"cloud_updates": 0, "forward_calls": 0, "clouds_classified": 0, "short_clouds": 0, "update_seconds": 0.0}
 
-            def update(envs, cbest, cmin):
+            def update_host(envs, cbest, cmin):
                 """host half of update_point_cloud for the listed problems, one batched forward"""
-                if args.pc_sample_rate == 0:          # nirrt_star_png_3d.py:137-140: no cloud, no draws
-                    for env in envs:
-                        bp.set_cloud(int(env), np.zeros((0, dim)))
-                    return
                 states = bp.get_rng()
                 items = []
                 for env in envs:
@@ -157,10 +160,77 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                 bp.set_rng(states)
                 for env, it, pred in zip(envs, items, preds):
                     bp.set_cloud(int(env), it[0][np.asarray(pred).nonzero()[0]])
+                stats["forward_calls"] += 1; stats["clouds_classified"] += len(envs)
+
+            dev = None
+            if dim == 3 and not host_clouds:
+                # 3D: the whole update stays in HBM -- draws from each problem's device MT19937 stream, filters, farthest
+                # point down-sampling, masks, ONE PointNet++ forward for every waiting problem, and the predicted points go
+                # straight into the planner's guidance-cloud buffer.  (With a caller-supplied classify= the clouds are read
+                # back for it; sampling still runs on the device.)
+                n_pts = args.pc_n_points
+                dev = {"pc": torch.empty((E, n_pts, 3), dtype=torch.float32, device=f"cuda:{device}"),
+                       "sm": torch.empty((E, n_pts), dtype=torch.float32, device=f"cuda:{device}"),
+                       "gm": torch.empty((E, n_pts), dtype=torch.float32, device=f"cuda:{device}"),
+                       "pred": torch.empty((E, n_pts), dtype=torch.int64, device=f"cuda:{device}"),
+                       "score": torch.empty((E, n_pts), dtype=torch.float32, device=f"cuda:{device}")}
+
+            def update_device(envs, cbest, cmin):
+                n_pts, n_raw = args.pc_n_points, args.pc_n_points * args.pc_over_sample_scale
+                kinds = [1 if cbest[env] < np.inf else 0 for env in envs]
+                params = np.zeros((len(envs), 12))
+                for k, env in enumerate(envs):
+                    if kinds[k]:
+                        params[k] = _B.ellipsoid_params_3d(makers[env].x_start, makers[env].x_goal, cbest[env] / cmin[env])
+                counts = bp.sample_clouds(envs, kinds, params, n_pts, n_raw, args.step_len, dev["pc"].data_ptr(),
+                                          dev["sm"].data_ptr(), dev["gm"].data_ptr())
+                if engine is None:          # caller-supplied classifier: hand it the clouds, upload what it predicts
+                    pts = bp.read_sampled_clouds(0, len(envs), n_pts)
+                    items = []
+                    for k, env in enumerate(envs):
+                        pc = pts[k, :counts[k]]
+                        items.append((pc, get_mask(pc, makers[env].x_start[np.newaxis, :], args.step_len).astype(np.float32),
+                                      get_mask(pc, makers[env].x_goal[np.newaxis, :], args.step_len).astype(np.float32)))
+                    preds = classify(items, list(envs))
+                    for env, it, pred in zip(envs, items, preds):
+                        bp.set_cloud(int(env), it[0][np.asarray(pred).nonzero()[0]])
+                    stats["forward_calls"] += 1; stats["clouds_classified"] += len(envs)
+                    return
+                # torch.randint on each problem's own generator, in problem order (pointnet2_utils.py:77)
+                fs = np.stack([[int(torch.randint(0, n, (1,), generator=gens[env], dtype=torch.long)) for n in (int(counts[k]),) + NPOINTS]
+                               for k, env in enumerate(envs)]).astype(np.int32)
+                d_fs = torch.from_numpy(fs).to(dev["pc"].device)
+                engine.classify_device(len(envs), 3, dev["pc"].data_ptr(), dev["sm"].data_ptr(), dev["gm"].data_ptr(),
+                                       d_fs.data_ptr(), dev["pred"].data_ptr(), dev["score"].data_ptr())
+                full = [k for k in range(len(envs)) if counts[k] == n_pts]
+                bp.commit_clouds(dev["pred"].data_ptr(), None if len(full) == len(envs) else full)
+                stats["forward_calls"] += 1; stats["clouds_classified"] += len(envs)
+                for k, env in enumerate(envs):          # short clouds: classified at their own size, like the reference
+                    if counts[k] != n_pts:
+                        pts = bp.read_sampled_clouds(k, 1, n_pts)[0, :counts[k]]
+                        sm = get_mask(pts, makers[env].x_start[np.newaxis, :], args.step_len).astype(np.float32)
+                        gm = get_mask(pts, makers[env].x_goal[np.newaxis, :], args.step_len).astype(np.float32)
+                        n = len(pts)
+                        if n not in short_engines:
+                            short_engines[n] = PointNet2Engine(state_dict, n_points=n, max_batch=1, device=device)
+                        pred, _ = short_engines[n].classify(pts.astype(np.float32)[None], sm[None], gm[None], fps_start=fs[k:k + 1])
+                        bp.set_cloud(int(env), pts[pred[0].nonzero()[0]])
+                        stats["short_clouds"] += 1; stats["forward_calls"] += 1
+
+            def update(envs, cbest, cmin):
+                if args.pc_sample_rate == 0:          # nirrt_star_png_3d.py:137-140: no cloud, no draws
+                    for env in envs:
+                        bp.set_cloud(int(env), np.zeros((0, dim)))
+                    return
+                t0 = time.perf_counter()
+                (update_device if dev is not None else update_host)(list(envs), cbest, cmin)
+                stats["cloud_updates"] += len(envs)
+                stats["update_seconds"] += time.perf_counter() - t0
 
             keep = np.random.get_state()
             if args.pc_sample_rate != 0:
                 update(list(range(E)), np.full(E, np.inf), np.full(E, np.nan))        # init_pc()
+        t_plan = time.perf_counter()
         bp.begin(variant, _B.MODE_PLANNING_RANDOM, args.iter_max, args.iter_after_initial)
         while True:
             bp.run(chunk)
@@ -175,6 +245,10 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
         if neural:
             np.random.set_state(keep)
         lists = bp.path_len_lists()
+        if stats_out is not None:
+            stats_out.update(stats if neural else {})
+            stats_out["plan_seconds"] = time.perf_counter() - t_plan
+            stats_out["iterations"] = int(sum(len(x) for x in lists))
     out = gather_lists(lists, n_total, device=torch.device("cuda", device)) if distributed else lists
     if return_planner:
         return out, bp

@@ -78,3 +78,86 @@ def test_run_eval_writes_reference_format_and_resumes(tmp_path):
     pickle.dump(got[:3], open(path, "wb"))
     _, rows2 = run_eval(cfgs[:5], problems[:5], "irrt_star", 3, args, seeds=[7, 8, 9, 10, 11], result_root=str(tmp_path), batch_size=2)
     assert [r["result"] for r in rows2] == [r["result"] for r in got]
+
+
+def test_nirrt_golden_inside_a_batch_device_clouds():
+    """The reference's own NIRRT*-PNG 3D trace (tests/golden/neural3d_nirrt_random_e0_s31: recorded predictions,
+    SHA-1 of every guidance cloud and mask) reproduced INSIDE a lock-step batch of 8 problems whose clouds are sampled
+    on the device (nirrt_batch_sample_clouds_sync: MT19937 draws, filters, farthest point down-sampling): same clouds,
+    same tree, same path_len_list -- the neighbours in the batch must not matter."""
+    import hashlib
+    from nirrt_star_b200.eval import default_args, plan_batch
+    g = np.load(os.path.join(GOLD, "neural3d_nirrt_random_e0_s31_i1500.npz"))
+    slot = 5
+    problems = [make_problem_3d(40 + k) for k in range(8)]
+    problems[slot] = make_problem_3d(int(g["env_idx"]))
+    seeds = [700 + k for k in range(8)]
+    seeds[slot] = int(g["seed"])
+    args = default_args(3, iter_max=int(g["iter_max"]), iter_after_initial=int(g["iter_after"]),
+                        pc_sample_rate=float(g["pc_sample_rate"]), pc_update_cost_ratio=float(g["ratio"]))
+    calls = {"k": 0}
+
+    def classify(items, envs):
+        preds = []
+        for (pc, sm, gm), env in zip(items, envs):
+            if env == slot:
+                k = calls["k"]
+                assert pc.dtype == np.float32 and len(pc) == int(g["call_n"][k])
+                assert hashlib.sha1(np.ascontiguousarray(pc).tobytes()).hexdigest() == str(g["call_pc_sha1"][k]), f"cloud {k} differs"
+                assert hashlib.sha1(sm.tobytes() + gm.tobytes()).hexdigest() == str(g["call_mask_sha1"][k])
+                preds.append(np.unpackbits(g["call_pred"][k])[:len(pc)].astype(np.int64))
+                calls["k"] += 1
+            else:       # some deterministic guidance for the neighbours: points near the start-goal segment
+                a = np.asarray(problems[env]["x_start"], dtype=np.float64); b = np.asarray(problems[env]["x_goal"], dtype=np.float64)
+                t = np.clip(((pc - a) @ (b - a)) / ((b - a) @ (b - a)), 0, 1)
+                preds.append((np.linalg.norm(pc - (a + t[:, None] * (b - a)), axis=1) < 12).astype(np.int64))
+        return preds
+
+    out, bp = plan_batch(problems, "nirrt_star", 3, args, seeds=seeds, classify=classify, return_planner=True)
+    assert calls["k"] == int(g["n_calls"])
+    lst, want = np.array(out[slot]), g["path_len_list"]
+    assert len(lst) == len(want) and np.array_equal(np.isinf(lst), np.isinf(want))
+    f = np.isfinite(want)
+    assert np.allclose(lst[f], want[f], rtol=1e-5, atol=0)
+    v, p, n = bp.read_trees()
+    n = int(n[slot])
+    assert n == int(g["num_vertices"]) and np.array_equal(p[slot, :n], g["parents"]) and np.array_equal(v[slot, :n], g["vertices"])
+    assert list(bp.solutions(slot)) == list(g["solutions"])
+    bp.close()
+
+
+def test_nirrt_batch_of_64_equals_single_problem_dropin(tmp_path):
+    """BASELINE configs[3] shape scaled to a test: 64 NIRRT* problems in lock step with device-side cloud updates and
+    batched PointNet++ forwards == the single-problem drop-in planner (reference API, one problem, B = 1 forwards) on 8
+    of them, bit for bit; the host-numpy cloud path gives the same answer too."""
+    import torch
+    from nirrt_star_b200 import dropin
+    from nirrt_star_b200.eval import default_args, plan_batch
+    dropin.install()
+    from path_planning_classes_3d.nirrt_star_png_3d import get_path_planner
+    from wrapper_3d.pointnet_pointnet2.pointnet2_wrapper import PNGWrapper
+    sd = make_pointnet2_state(0)
+    d = tmp_path / "results/model_training/pointnet2_3d/checkpoints"
+    d.mkdir(parents=True)
+    torch.save({"model_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, str(d / "best_pointnet2_3d.pth"))
+    E = 64
+    problems = [make_problem_3d(300 + i) for i in range(E)]
+    seeds = [4000 + i for i in range(E)]
+    args = default_args(3, iter_max=1000, iter_after_initial=200)
+    stats = {}
+    batch = plan_batch(problems, "nirrt_star", 3, args, seeds=seeds, state_dict=sd, stats_out=stats)
+    assert stats["cloud_updates"] >= E and stats["forward_calls"] < stats["cloud_updates"]     # updates really are batched
+    w = PNGWrapper(root_dir=str(tmp_path), device="cuda")
+    for e in (0, 7, 13, 22, 31, 40, 55, 63):
+        s = seeds[e]
+        np.random.seed(s); random.seed(s); torch.manual_seed(s)
+        want = get_path_planner(args, problems[e], w).planning_random(args.iter_after_initial)
+        got = batch[e]
+        assert len(got) == len(want), e
+        assert np.array_equal(np.isinf(got), np.isinf(want)), e
+        f = np.isfinite(want)
+        assert np.array_equal(np.array(got)[f], np.array(want)[f]), e
+    sub = [0, 7, 13, 22]
+    host = plan_batch([problems[e] for e in sub], "nirrt_star", 3, args, seeds=[seeds[e] for e in sub], state_dict=sd, host_clouds=True)
+    for k, e in enumerate(sub):
+        assert np.array_equal(np.array(host[k]), np.array(batch[e]))
