@@ -23,6 +23,7 @@ VARIANT_RRT_STAR, VARIANT_IRRT_STAR, VARIANT_NIRRT_STAR, VARIANT_NRRT_STAR = 0, 
 INFORMED = (VARIANT_IRRT_STAR, VARIANT_NIRRT_STAR)
 MODE_PLANNING, MODE_PLANNING_RANDOM = 0, 1
 ST_DONE, ST_PHASE1, ST_PHASE2, ST_WAIT_CLOUD = 0, 1, 2, 3
+NEAR_CAPACITY_INFORMED = 8192   # per-iteration Near candidate limit for the informed planners (maximum; default is 1024)
 
 
 def near_radius_table(capacity, dim=3):

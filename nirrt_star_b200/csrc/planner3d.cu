@@ -174,6 +174,7 @@ struct View {
     int *cand;       // [E][near_cap] unordered Nearest candidates (k_nearest_m -> k_steer), then Near candidates of a fallback scan
     int *cand2;      // [E][near_cap] speculative Near candidates collected during the Nearest scan
     int *near_out;   // [E][near_cap] final (ordered, collision-filtered) Near list: trace
+    unsigned char *big;  // [E][near_cap * kNearRowAlloc] HBM staging of k_expand for more than kNearSmem candidates; null if near_cap <= kNearSmem
     int *sol;        // [E][sol_cap]  path_solutions
     int *gc_idx;     // [E][cap]      vertices within step_len of the goal (RRT* eval driver)
     double *gc_d;    // [E][cap]      their goal distance, +inf when the goal edge collides
@@ -271,7 +272,7 @@ __device__ __forceinline__ double hypot_band_sq(double h) {
 struct __align__(16) Link {
     double elen;   // math.hypot(v - parent(v)); 0 for the root
     int parent;
-    int pad;       // Near stamp: (iteration tag << 10) | position in this iteration's Near list (k_expand), else stale/0
+    int pad;       // Near stamp: (iteration tag << kPosBits) | position in this iteration's Near list (k_expand), else stale/0
 };
 #ifdef NIRRT_PHASE_TIMING
 __device__ unsigned long long g_walk_stats[4];
@@ -1362,7 +1363,14 @@ __global__ void __launch_bounds__(256) k_near_m(View v) {
 // (:80-90), rewire (:92-99), InGoalRegion append (irrt_star_3d.py:70-71), search_goal_parent +
 // path length record (rrt_star_3d.py:101-117,225-231), iteration accounting.
 constexpr int kExpandThreads = 128;
-constexpr int kNearSmem = 1024;
+constexpr int kNearSmem = 1024;   // Near candidates of one iteration staged in shared memory (the common case)
+constexpr int kNearBig = 8192;    // upper limit with near_capacity > kNearSmem: per-problem HBM staging (View::big) --
+                                  // dense informed trees (a thin ellipsoid holding thousands of vertices inside one Near ball)
+constexpr int kPosBits = 13;      // bits of a Near-list position in the stamps / ancestor words (2^13 = kNearBig)
+constexpr int kNearRow = 44;      // staging bytes per candidate: cand, near, par (int) + d, cost, first (double) + anc (u64)
+constexpr int kNearRowAlloc = 45; // + the Rewire decision bits (1 bit per candidate, rounded up)
+// ancestor word of a Near member: three positions, [3 * kPosBits, +2): their count, then: more than three, through x_new
+constexpr int kAncCnt = 3 * kPosBits, kAncOver = kAncCnt + 2, kAncNew = kAncCnt + 3;
 
 __device__ void bitonic_sort_int(int *a, int n_pow2) {
     for (int k = 2; k <= n_pow2; k <<= 1) {
@@ -1611,14 +1619,23 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         __syncthreads();
     } else if (!IT.go) return;
     __shared__ G g;
-    __shared__ int s_cand[kNearSmem];
-    __shared__ int s_near[kNearSmem];
-    __shared__ double s_d[kNearSmem];
-    __shared__ double s_cost[kNearSmem];                // cost(near_k) before any rewiring of this iteration
-    __shared__ double s_first[kNearSmem];               // Line(near_k, x_new) by math.hypot: first term of cost(x_new) via near_k, and the edge length if near_k is re-wired
-    __shared__ unsigned long long s_anc[kNearSmem];     // Near members on near_k's root path (see below)
-    __shared__ unsigned s_rew[kNearSmem / 32];
-    __shared__ int s_par[kNearSmem];                    // parent(near_k) before this iteration (RRT* eval driver: child-list surgery)
+    // per-candidate staging, kNearRow bytes each: shared memory for up to kNearSmem candidates, else the problem's HBM
+    // staging area (same layout, capacity near_cap) after the index sort, which always runs in shared memory
+    __shared__ __align__(16) unsigned char s_buf[kNearSmem * kNearRow];
+    int stage_cap = kNearSmem;
+    unsigned char *stage = s_buf;
+#define STAGE_INT(slot) (reinterpret_cast<int *>(stage) + (size_t)(slot) * stage_cap)
+#define STAGE_F64(slot) (reinterpret_cast<double *>(stage + (size_t)12 * stage_cap) + (size_t)(slot) * stage_cap)
+    int *s_cand = STAGE_INT(0);
+    int *s_near = STAGE_INT(1);
+    int *s_par = STAGE_INT(2);                          // parent(near_k) before this iteration (RRT* eval driver: child-list surgery)
+    double *s_d = STAGE_F64(0);
+    double *s_cost = STAGE_F64(1);                      // cost(near_k) before any rewiring of this iteration
+    double *s_first = STAGE_F64(2);                     // Line(near_k, x_new) by math.hypot: first term of cost(x_new) via near_k, and the edge length if near_k is re-wired
+    unsigned long long *s_anc = reinterpret_cast<unsigned long long *>(STAGE_F64(3));   // Near members on near_k's root path (see below)
+    __shared__ unsigned s_rew_small[kNearSmem / 32];
+    unsigned *s_rew = s_rew_small;                      // Rewire decisions, one bit per Near position
+    int rew_words = kNearSmem / 32;
     __shared__ int s_par_new;                           // parent of the re-used vertex before ChooseParent (duplicate guard)
     __shared__ double s_curr[3];                        // curr_node_new_cost, cost(new) via the steer parent, cost(new) via ChooseParent's winner
     __shared__ Hint s_hnew;                             // ancestor hints of x_new after ChooseParent
@@ -1676,11 +1693,33 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             cnt = IT.spec_cnt - IT.spec_base;
             cand = cand2_of(v, e);
         } else cnt = c->cand_cnt;
-        if (cnt > v.near_cap || cnt > kNearSmem) {
-            if (tid == 0) atomicOr(&c->err, ERR_NEAR_OVERFLOW);
-            cnt = min(min(cnt, v.near_cap), kNearSmem);
+        {
+            const int limit = v.big ? min(v.near_cap, kNearBig) : kNearSmem;
+            if (cnt > limit) {
+                if (tid == 0) atomicOr(&c->err, ERR_NEAR_OVERFLOW);
+                cnt = limit;
+            }
         }
-        if (cnt <= 256) {
+        if (cnt > kNearSmem) {
+            // More candidates than the shared staging holds (dense informed tree): sort the indices in shared memory
+            // (the whole staging buffer as keys), then continue with every per-candidate array in HBM.
+            int p2 = 1;
+            while (p2 < cnt) p2 <<= 1;
+            int *keys = reinterpret_cast<int *>(s_buf);        // kNearSmem * kNearRow / 4 = 11264 >= kNearBig ints
+            for (int i = tid; i < p2; i += blockDim.x) keys[i] = i < cnt ? cand[i] : INT_MAX;
+            if (tid == 0) s_m = 0;
+            __syncthreads();
+            bitonic_sort_int(keys, p2);
+            stage_cap = v.near_cap;
+            stage = v.big + (size_t)e * v.near_cap * kNearRowAlloc;
+            s_cand = STAGE_INT(0); s_near = STAGE_INT(1); s_par = STAGE_INT(2);
+            s_d = STAGE_F64(0); s_cost = STAGE_F64(1); s_first = STAGE_F64(2);
+            s_anc = reinterpret_cast<unsigned long long *>(STAGE_F64(3));
+            s_rew = reinterpret_cast<unsigned *>(stage + (size_t)kNearRow * stage_cap); rew_words = stage_cap / 32;
+            for (int i = tid; i < cnt; i += blockDim.x) s_cand[i] = keys[i];
+            __threadfence_block();
+            __syncthreads();
+        } else if (cnt <= 256) {
             // ascending order by rank counting (the indices are distinct): one barrier instead of a sorting network
             int *s_raw = s_near;                          // scratch until the compaction below fills s_near
             for (int i = tid; i < cnt; i += blockDim.x) s_raw[i] = cand[i];
@@ -1756,12 +1795,12 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             // existing vertex) lie on its path: Rewire is sequential in the reference
             // (rrt_star_3d.py:96-99), a neighbour's cost only changes when one of its ancestors was
             // re-parented earlier in the same loop, and only then is it walked again.
-            for (int i = tid; i < kNearSmem / 32; i += blockDim.x) s_rew[i] = 0;
+            for (int i = tid; i < rew_words; i += blockDim.x) s_rew[i] = 0;
             // stamp the Near members in their walk records: a walk recognises them from the record it loads anyway
             const TreeRef t = tree_of(v, e);
-            const int tag = (int)(c->stamp % 2097151u) + 1;   // <= 2^21 - 1: (tag << 10) | k stays a non-negative int
+            const int tag = (int)(c->stamp % ((1u << (31 - kPosBits)) - 1u)) + 1;   // (tag << kPosBits) | k stays a non-negative int
             for (int k = tid; k < m; k += blockDim.x)
-                __stcg(reinterpret_cast<int *>(t.links + s_near[k]) + 3, (tag << 10) | k);
+                __stcg(reinterpret_cast<int *>(t.links + s_near[k]) + 3, (tag << kPosBits) | k);
             __syncthreads();
             double bs = XINF, via_best = 0.0; int bk = INT_MAX;
             PHASE_MARK(6)
@@ -1782,17 +1821,17 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 }
                 const int idx = s_near[k];
                 double cacc = 0.0, vacc = s_first[k];
-                unsigned long long anc = 0;   // [0,30): three 10-bit positions, [30,32): count, bit 32: overflow, bit 33: through x_new
+                unsigned long long anc = 0;   // three kPosBits-bit positions, their count, overflow flag, through-x_new flag (kAnc*)
                 int fpar = -1;
                 walk_to_root(t, idx, [&](int par, double eg, int pad) {
                     cacc = XADD(cacc, eg); vacc = XADD(vacc, eg);
                     if (fpar < 0) fpar = par;
-                    if (par == new_idx) anc |= 1ull << 33;
-                    else if ((pad >> 10) == tag) {      // a stale or aliased stamp can only add a (harmless) dependency
-                        const int pos = pad & 1023;
-                        const int cntp = (int)((anc >> 30) & 3ull);
-                        if (cntp < 3) { anc |= (unsigned long long)pos << (10 * cntp); anc = (anc & ~(3ull << 30)) | ((unsigned long long)(cntp + 1) << 30); }
-                        else anc |= 1ull << 32;
+                    if (par == new_idx) anc |= 1ull << kAncNew;
+                    else if ((pad >> kPosBits) == tag) {      // a stale or aliased stamp can only add a (harmless) dependency
+                        const int pos = pad & (kNearBig - 1);
+                        const int cntp = (int)((anc >> kAncCnt) & 3ull);
+                        if (cntp < 3) { anc |= (unsigned long long)pos << (kPosBits * cntp); anc = (anc & ~(3ull << kAncCnt)) | ((unsigned long long)(cntp + 1) << kAncCnt); }
+                        else anc |= 1ull << kAncOver;
                     }
                 });
                 s_cost[k] = cacc; s_anc[k] = anc; s_par[k] = fpar;
@@ -1836,7 +1875,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
                 const int k = k0 + tid;
                 const bool dec = k < m && s_cost[k] > XADD(c_new, s_d[k]);
                 const unsigned bal = __ballot_sync(0xffffffffu, dec);
-                if ((tid & 31) == 0) s_rew[k >> 5] = bal;      // k >> 5 < kNearSmem / 32 for every k0 + tid
+                if ((tid & 31) == 0 && (k >> 5) < rew_words) s_rew[k >> 5] = bal;
             }
             __syncthreads();
             bool dep = false;
@@ -1845,11 +1884,11 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             for (int k = tid; k < m; k += blockDim.x) {
                 const unsigned long long anc = s_anc[k];
                 if (anc == 0ull) continue;
-                if (new_moved && ((anc >> 33) & 1ull)) dep = true;
-                if (any_dec && ((anc >> 32) & 1ull)) dep = true;
-                const int cntp = (int)((anc >> 30) & 3ull);
+                if (new_moved && ((anc >> kAncNew) & 1ull)) dep = true;
+                if (any_dec && ((anc >> kAncOver) & 1ull)) dep = true;
+                const int cntp = (int)((anc >> kAncCnt) & 3ull);
                 for (int q = 0; q < cntp; q++) {
-                    const int pos = (int)((anc >> (10 * q)) & 1023ull);
+                    const int pos = (int)((anc >> (kPosBits * q)) & (unsigned long long)(kNearBig - 1));
                     if (pos < k && ((s_rew[pos >> 5] >> (pos & 31)) & 1u)) dep = true;
                 }
             }
@@ -1865,14 +1904,14 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             } else {
                 __syncthreads();
                 if (tid == 0) {
-                    for (int w = 0; w < kNearSmem / 32; w++) s_rew[w] = 0;
+                    for (int w = 0; w < rew_words; w++) s_rew[w] = 0;
                     bool any = false;
                     for (int k = 0; k < m; k++) {
                         const unsigned long long anc = s_anc[k];
-                        bool dirty = (new_moved && ((anc >> 33) & 1ull)) || (any && ((anc >> 32) & 1ull));
-                        const int cntp = (int)((anc >> 30) & 3ull);
+                        bool dirty = (new_moved && ((anc >> kAncNew) & 1ull)) || (any && ((anc >> kAncOver) & 1ull));
+                        const int cntp = (int)((anc >> kAncCnt) & 3ull);
                         for (int q = 0; q < cntp && !dirty; q++) {
-                            const int pos = (int)((anc >> (10 * q)) & 1023ull);
+                            const int pos = (int)((anc >> (kPosBits * q)) & (unsigned long long)(kNearBig - 1));
                             dirty = (s_rew[pos >> 5] >> (pos & 31)) & 1u;
                         }
                         const double ck = dirty ? cost_walk<D>(t, s_near[k]) : s_cost[k];
@@ -2384,7 +2423,8 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         if (b->groups > d->n_envs) b->groups = d->n_envs;
     }
     v.chunks = pick_chunks((v.E + b->groups - 1) / b->groups);
-    v.near_cap = d->near_capacity > 0 ? d->near_capacity : kNearSmem;
+    v.near_cap = d->near_capacity > 0 ? ((d->near_capacity + 63) & ~63) : kNearSmem;
+    if (v.near_cap > kNearBig) { delete b; return fail(NIRRT_ERR_INVALID, "near_capacity: at most 8192"); }
     v.rec_cap = d->record_capacity > 0 ? d->record_capacity : d->capacity + 8;
     v.sol_cap = v.rec_cap > v.cap + 8 ? v.rec_cap : v.cap + 8;   // at most one append per iteration
     v.pc_cap = 4096; v.path_cap = 4096;
@@ -2419,6 +2459,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     DALLOC(v.part_s, double, (size_t)v.E * v.chunks); DALLOC(v.part_i, int, (size_t)v.E * v.chunks);
     DALLOC(v.cand, int, (size_t)v.E * v.near_cap); DALLOC(v.near_out, int, (size_t)v.E * v.near_cap);
     DALLOC(v.cand2, int, (size_t)2 * v.E * v.near_cap);     // two halves: IterScratch copies 0 / 1
+    if (v.near_cap > kNearSmem) DALLOC(v.big, unsigned char, (size_t)v.E * v.near_cap * kNearRowAlloc);
     DALLOC(v.sol, int, (size_t)v.E * v.sol_cap);
     DALLOC(v.records, double, (size_t)v.E * v.rec_cap);
     DALLOC(v.pathseg, double, (size_t)v.E * v.path_cap);

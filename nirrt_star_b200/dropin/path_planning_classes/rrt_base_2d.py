@@ -53,7 +53,8 @@ class RRTBase2D:
             raise RuntimeError("we can only run planning once per planner object (demo_planning_2d.py:90)")
         self._engine = _B.BatchPlanner2D([self._problem()], self.iter_max, step_len=self.step_len,
                                          clearance=self.clearance, rng_states=[self._np_state()],
-                                         py_rng_states=[self._py_state()], record_capacity=record_capacity)
+                                         py_rng_states=[self._py_state()], record_capacity=record_capacity,
+                                         near_capacity=_B.NEAR_CAPACITY_INFORMED if self._variant in _B.INFORMED else 0)
         return self._engine
 
     def _sync_rng_to_host(self, eng):

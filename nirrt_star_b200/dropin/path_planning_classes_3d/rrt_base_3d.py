@@ -43,7 +43,8 @@ class RRTBase3D:
         st = np.random.get_state()
         self._engine = _B.BatchPlanner3D([self._problem()], self.iter_max, step_len=self.step_len,
                                          clearance=self.clearance, rng_states=[(st[1], st[2])],
-                                         record_capacity=record_capacity)
+                                         record_capacity=record_capacity,
+                                         near_capacity=_B.NEAR_CAPACITY_INFORMED if self._variant in _B.INFORMED else 0)
         return self._engine
 
     def _finish_engine(self):

@@ -98,8 +98,10 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
     if local:
         E = len(local)
         cls = _B.BatchPlanner3D if dim == 3 else _B.BatchPlanner2D
+        # informed planners concentrate the tree in a thin ellipsoid: one Near ball can hold thousands of vertices there
         bp = cls(local, args.iter_max, step_len=args.step_len, clearance=args.clearance, seeds=lseeds, device=device,
-                 record_capacity=args.iter_max + args.iter_after_initial + 8)
+                 record_capacity=args.iter_max + args.iter_after_initial + 8,
+                 near_capacity=_B.NEAR_CAPACITY_INFORMED if variant in _B.INFORMED else 0)
         neural = variant in (_B.VARIANT_NIRRT_STAR, _B.VARIANT_NRRT_STAR)
         if neural:
             makers = [_CloudMaker(dim, p, args) for p in local]

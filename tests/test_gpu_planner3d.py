@@ -435,3 +435,43 @@ def test_graph_is_built_by_begin_and_reused(B):
     assert np.array_equal(n, ref[2])
     for e in range(E):
         assert np.array_equal(p[e, :n[e]], ref[1][e, :n[e]]) and np.array_equal(v[e, :n[e]], ref[0][e, :n[e]])
+
+
+def test_dense_informed_tree_with_thousands_of_near_candidates(B):
+    """Informed planners concentrate the tree in a thin ellipsoid, where one Near ball holds thousands of vertices (the
+    reference has no limit on |Near|).  Beyond 1024 candidates k_expand stages its per-candidate arrays in HBM
+    (near_capacity up to 8192): index sort, collision filter, parallel walks, ChooseParent and the sequential-equivalent
+    Rewire must still reproduce the oracle bit for bit.  gamma is raised so that r = step_len throughout."""
+    from oracle.planner_oracle import Oracle3D
+    E, iters = 3, 3500
+    problems = []
+    for i in range(E):
+        pr = dict(make_problem_3d(700 + i))
+        pr["search_radius"] = 500.0
+        problems.append(pr)
+    seeds = [8100 + i for i in range(E)]
+    bp = B.BatchPlanner3D(problems, iters, seeds=seeds, near_capacity=B.NEAR_CAPACITY_INFORMED)
+    bp.begin(1, B.MODE_PLANNING, iters)
+    biggest = 0
+    for _ in range(iters // 250):
+        bp.run(250)
+        _, _, cnt, _, _ = bp.trace(near_stride=B.NEAR_CAPACITY_INFORMED)
+        biggest = max(biggest, int(cnt.max()))
+    running, need = bp.status()          # raises on any overflow
+    v, p, n = bp.read_trees()
+    assert biggest > 1024, biggest       # the HBM-staged path really ran
+    for e in range(E):
+        o = Oracle3D(problems[e], iters, seed=seeds[e])
+        o.run(iters, 1, 0)
+        ov, op = o.tree()
+        assert n[e] == len(ov) and np.array_equal(p[e, :n[e]], op) and np.array_equal(v[e, :n[e]], ov), e
+        assert np.array_equal(bp.solutions(e), o.solutions())
+    bp.close()
+    # without the large capacity the same run is a hard error, never a silent truncation
+    from nirrt_star_b200._lib import NirrtError
+    small = B.BatchPlanner3D(problems[:1], iters, seeds=seeds[:1])
+    small.begin(1, B.MODE_PLANNING, iters)
+    small.run(iters)
+    with pytest.raises(NirrtError, match="near-candidate"):
+        small.status()
+    small.close()
