@@ -178,7 +178,8 @@ struct View {
     int *sol;        // [E][sol_cap]  path_solutions
     int *gc_idx;     // [E][cap]      vertices within step_len of the goal (RRT* eval driver)
     double *gc_d;    // [E][cap]      their goal distance, +inf when the goal edge collides
-    double *gc_cost; // [E][cap]      cached cost(vertex) + goal distance (+inf when the goal edge collides), see goal_track
+    double *gc_cost; // [E][gc_stride] cached cost(vertex) + goal distance (+inf when the goal edge collides), see goal_track
+    int gc_stride;   // row length of gc_d / gc_cost: max(cap, sol_cap) -- the informed family keeps its candidates in `sol`
     struct Kid *kid; // [E][stride]   child lists + goal-candidate slot of every vertex (RRT* eval driver), see goal_track
     double *records; // [E][rec_cap]
     double *pc;      // [E][pc_cap][3]
@@ -684,22 +685,10 @@ __device__ __forceinline__ void top_body(const View &v, int e, typename GeomOf<D
     if (D == 2 && fam_informed(v.variant)) mt_prepare_next(v.mt_py + e, 160);
     __syncthreads();
 
+    // find_best_path_solution (irrt_star_3d.py:80-93): kept current incrementally by goal_track (the reference re-walks
+    // every stored solution at the top of every iteration -- thousands of walks in a dense informed tree)
     double c_best = XINF;
-    if (fam_informed(v.variant)) {
-        const int n_sol = c->n_sol;
-        const Node *nodes = v.nodes + (size_t)e * v.stride;
-        const int *sol = v.sol + (size_t)e * v.sol_cap;
-        double bs = XINF; int bk = INT_MAX;
-        for (int k = threadIdx.x; k < n_sol; k += blockDim.x) {
-            const int idx = sol[k];
-            const Node nd = load_node(nodes + idx);
-            const double val = XADD(cost_walk<D>(tree_of(v, e), idx),
-                                    edge_len<D>(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z)));
-            lexmin(bs, bk, val, k);
-        }
-        block_lexmin(bs, bk, sm_s, sm_i);
-        if (n_sol > 0) c_best = bs;
-    }
+    if (fam_informed(v.variant) && c->n_sol > 0) c_best = c->best_val;
     // RRT* (and IRRT* before its first solution) draw nothing before SampleFree: evaluate it with all threads
     __shared__ double s_spec[3];
     __shared__ int s_spec_words;
@@ -1431,6 +1420,19 @@ __device__ __forceinline__ void kid_link(Kid *kid, int v, int parent, int head) 
     __stcg(&kid[parent].head, v);
 }
 
+// The goal-candidate list of a problem: the RRT* eval driver's vertices within step_len of the goal (gc_idx, count
+// n_goal), or the informed family's path_solutions (sol, count n_sol, irrt_star_3d.py:70-71 -- it may hold a vertex
+// twice, through the duplicate guard; only the first slot of a vertex carries a cached value, the later ones +inf,
+// which never changes the first-minimum rule).
+struct GoalList { int *idx; double *d; double *cost; int *count; int cap; };
+__device__ __forceinline__ GoalList goal_list(const View &v, EnvCtl *c, int e) {
+    GoalList L;
+    if (fam_informed(v.variant)) { L.idx = v.sol + (size_t)e * v.sol_cap; L.count = &c->n_sol; L.cap = v.sol_cap; }
+    else { L.idx = v.gc_idx + (size_t)e * v.cap; L.count = &c->n_goal; L.cap = v.cap; }
+    L.d = v.gc_d + (size_t)e * v.gc_stride; L.cost = v.gc_cost + (size_t)e * v.gc_stride;
+    return L;
+}
+
 // get_path_len(extract_path(gp)) (rrt_base_3d.py:69-91): row norms root -> goal, numpy pairwise summation.  One thread.
 template <int D>
 __device__ double goal_path_len_from(const View &v, EnvCtl *c, int e, const Node *nodes, int gp) {
@@ -1455,14 +1457,15 @@ __device__ double goal_path_len_from(const View &v, EnvCtl *c, int e, const Node
 // size); result in thread 0, which also updates the problem's bookkeeping.
 template <int D>
 __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nodes, double *sm_s, int *sm_i) {
-    const int ng = c->n_goal;
+    const GoalList L = goal_list(v, c, e);
+    const int ng = min(*L.count, L.cap);
     if (ng == 0) {
         if (threadIdx.x == 0) { c->last_gp = -1; c->best_k = -1; c->best_val = XINF; c->last_len = XINF; }
         return XINF;
     }
-    const int *gi = v.gc_idx + (size_t)e * v.cap;
-    const double *gd = v.gc_d + (size_t)e * v.cap;
-    double *gcst = v.gc_cost + (size_t)e * v.cap;
+    const int *gi = L.idx;
+    const double *gd = L.d;
+    double *gcst = L.cost;
     double bs = XINF; int bk = INT_MAX;
     for (int k = threadIdx.x; k < ng; k += blockDim.x) {
         const double d = gd[k];
@@ -1474,7 +1477,8 @@ __device__ double goal_path_len(const View &v, EnvCtl *c, int e, const Node *nod
     double len = XINF;
     if (threadIdx.x == 0) {
         const int gp = gi[bk];
-        len = goal_path_len_from<D>(v, c, e, nodes, gp);
+        // the informed family records c_best itself (irrt_star_3d.py:80-93), not the numpy path length
+        len = fam_informed(v.variant) ? bs : goal_path_len_from<D>(v, c, e, nodes, gp);
         c->last_gp = gp; c->best_k = bk; c->best_val = bs; c->last_len = len;
     }
     return len;
@@ -1495,15 +1499,31 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
                            int *s_front, int *s_dirty, double *sm_s, int *sm_i) {
     __shared__ int s_cnt[4];     // [0] next frontier size, [1] dirty candidates, [2] overflow, [3] slot of the new candidate / -1
     Kid *kid = v.kid + (size_t)e * v.stride;
-    int *gi = v.gc_idx + (size_t)e * v.cap;
-    double *gd = v.gc_d + (size_t)e * v.cap;
-    double *gcst = v.gc_cost + (size_t)e * v.cap;
+    const GoalList L = goal_list(v, c, e);
+    int *gi = L.idx;
+    double *gd = L.d;
+    double *gcst = L.cost;
+    const bool informed = fam_informed(v.variant);
     const int tid = threadIdx.x;
     if (tid == 0) {
         int ns = 0, newk = -1, gslot_new = -1;
         bool ovf = false;
-        if (inserted) {
-            const double gx = XSUB(c->goal[0], xnew[0]), gy = XSUB(c->goal[1], xnew[1]), gz = XSUB(c->goal[2], xnew[2]);
+        const double gx = XSUB(c->goal[0], xnew[0]), gy = XSUB(c->goal[1], xnew[1]), gz = XSUB(c->goal[2], xnew[2]);
+        if (informed) {
+            // InGoalRegion (rrt_base_3d.py:93-95) -> path_solutions.append(node_new_index) (irrt_star_3d.py:70-71), also when
+            // the duplicate guard re-used an existing vertex
+            const double dg = edge_len<D>(gx, gy, gz);
+            if (dg < c->step_len && !seg_collides(g, xnew, c->goal)) {
+                const int k = c->n_sol;
+                c->n_sol = k + 1;
+                if (k < v.sol_cap) {
+                    gi[k] = new_idx;
+                    gd[k] = dg;
+                    if (inserted || __ldcg(&kid[new_idx].gslot) < 0) { newk = k; gslot_new = k; }
+                    else __stcg(gcst + k, XINF);      // a second slot of the same vertex: the first one carries the value
+                } else atomicOr(&c->err, ERR_SOL_OVERFLOW);
+            }
+        } else if (inserted) {
             const double s2 = scan_sq<D>(gx, gy, gz);
             // dist_to_goal <= step_len (rrt_star_3d.py:103-104 / rrt_star_2d.py:103-104)
             if (s2 <= c->T_goal && (D == 3 || np_hypot(gx, gy) <= c->step_len)) {
@@ -1514,13 +1534,16 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
                 c->n_goal = newk + 1;
                 if (!hit) gslot_new = newk;
             }
+        }
+        if (inserted) {
             // the new vertex under its final parent (after ChooseParent)
             const int pn = load_link(t.links + new_idx).parent;
             const int h = __ldcg(&kid[pn].head);
             store_kid(kid + new_idx, -1, h, -1, gslot_new);
             if (h >= 0) __stcg(&kid[h].prev, new_idx);
             __stcg(&kid[pn].head, new_idx);
-        } else if (new_moved) {
+        } else if (gslot_new >= 0) __stcg(&kid[new_idx].gslot, gslot_new);      // an existing vertex became a candidate
+        if (!inserted && new_moved) {
             // the duplicate guard re-used an existing vertex and ChooseParent moved it: its whole subtree got cheaper
             const int pn = load_link(t.links + new_idx).parent;
             kid_unlink(kid, new_idx, par_new_old);
@@ -1591,14 +1614,15 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
     if (any_best_dirty) {
         __threadfence_block();
         __syncthreads();
-        const int ng = c->n_goal;
+        const int ng = min(*L.count, L.cap);
         bs = XINF; bk = INT_MAX;
         for (int k = tid; k < ng; k += blockDim.x) lexmin(bs, bk, __ldcg(gcst + k), k);
     }
     block_lexmin(bs, bk, sm_s, sm_i);
     if (tid == 0) {
         if (!any_best_dirty && old_k >= 0) lexmin(bs, bk, old_val, old_k);
-        if (any_best_dirty || bk != old_k) {
+        if (informed) { c->last_gp = gi[bk]; c->last_len = bs; }
+        else if (any_best_dirty || bk != old_k) {
             const int gp = gi[bk];
             c->last_gp = gp;
             c->last_len = goal_path_len_from<D>(v, c, e, nodes, gp);
@@ -1786,7 +1810,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         for (int k = tid; k < m; k += blockDim.x) near_out[k] = s_near[k];
         if (tid == 0) IT.near_cnt = m;
 
-        const bool track = !fam_informed(v.variant) && v.mode == NIRRT_MODE_PLANNING_RANDOM;   // RRT* eval driver
+        // the informed family needs c_best every iteration (its sampler); the RRT* family only in the eval driver
+        const bool track = fam_informed(v.variant) || v.mode == NIRRT_MODE_PLANNING_RANDOM;
         double c_new_final = 0.0;          // cost(new_idx) after ChooseParent (valid when m > 0)
         bool moved_final = false;          // the duplicate guard's vertex was re-parented by ChooseParent
         if (m > 0) {
@@ -1929,18 +1954,8 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             __syncthreads();
         }
         PHASE_MARK(4)
-        // ---- goal bookkeeping
-        if (fam_informed(v.variant)) {
-            if (tid == 0) {
-                // InGoalRegion (rrt_base_3d.py:93-95)
-                if (edge_len<D>(XSUB(c->goal[0], xnew[0]), XSUB(c->goal[1], xnew[1]), XSUB(c->goal[2], xnew[2])) < c->step_len &&
-                    !seg_collides(g, xnew, c->goal)) {
-                    if (c->n_sol < v.sol_cap) v.sol[(size_t)e * v.sol_cap + c->n_sol] = new_idx;
-                    else atomicOr(&c->err, ERR_SOL_OVERFLOW);
-                    c->n_sol++;
-                }
-            }
-        } else if (track) {
+        // ---- goal bookkeeping: path_solutions / goal candidates, their cached costs, the current best (goal_track)
+        if (track) {
             __syncthreads();
             goal_track<D>(v, c, e, g, tree_of(v, e), nodes, new_idx, IT.inserted != 0, moved_final, m, s_near, s_par, s_rew,
                           s_par_new, m > 0, c_new_final, xnew, s_cand, reinterpret_cast<int *>(s_anc), sm_s, sm_i);
@@ -2016,6 +2031,29 @@ __global__ void __launch_bounds__(256) k_goal_init(View v) {
         if (old >= 0) __stcg(&kid[old].prev, i);
     }
     __syncthreads();
+    if (fam_informed(v.variant)) {
+        // the candidates are the stored path_solutions; the first slot of a vertex carries its cached value
+        const GoalList L = goal_list(v, c, e);
+        const int ns = min(*L.count, L.cap);
+        for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+            const int i = L.idx[k];
+            const Node nd = load_node(nodes + i);
+            L.d[k] = edge_len<D>(XSUB(c->goal[0], nd.x), XSUB(c->goal[1], nd.y), XSUB(c->goal[2], nd.z));
+        }
+        __syncthreads();
+        // first occurrence of every vertex: slots are visited in ascending order by one thread per 32-slot stripe, the
+        // minimum slot wins through atomicMin on a scratch encoding (gslot = -1 means "none": use unsigned compare)
+        for (int k = threadIdx.x; k < ns; k += blockDim.x)
+            atomicMin(reinterpret_cast<unsigned *>(&kid[L.idx[k]].gslot), (unsigned)k);
+        __threadfence_block();
+        __syncthreads();
+        for (int k = threadIdx.x; k < ns; k += blockDim.x)
+            if (__ldcg(&kid[L.idx[k]].gslot) != k) L.d[k] = XINF;     // later slot of the same vertex: never the first minimum
+        __threadfence_block();
+        __syncthreads();
+        goal_path_len<D>(v, c, e, nodes, sm_s, sm_i);
+        return;
+    }
     for (int base = 0; base < n; base += blockDim.x) {
         const int i = base + threadIdx.x;
         bool keep = false;
@@ -2039,7 +2077,7 @@ __global__ void __launch_bounds__(256) k_goal_init(View v) {
         if (keep) {
             const int pos = off + __popc(bal & ((1u << l) - 1u));
             v.gc_idx[(size_t)e * v.cap + pos] = i;
-            v.gc_d[(size_t)e * v.cap + pos] = d;
+            v.gc_d[(size_t)e * v.gc_stride + pos] = d;
             if (d < XINF) __stcg(&kid[i].gslot, pos);
         }
         __syncthreads();
@@ -2489,8 +2527,9 @@ static int ensure_goal_lists(nirrt_batch *b) {
     View &v = b->v;
     void *p = nullptr;
     int r = dalloc(b, &p, sizeof(int) * (size_t)v.E * v.cap); if (r) return r; v.gc_idx = (int *)p;
-    r = dalloc(b, &p, sizeof(double) * (size_t)v.E * v.cap); if (r) return r; v.gc_d = (double *)p;
-    r = dalloc(b, &p, sizeof(double) * (size_t)v.E * v.cap); if (r) return r; v.gc_cost = (double *)p;
+    v.gc_stride = v.sol_cap > v.cap ? v.sol_cap : v.cap;
+    r = dalloc(b, &p, sizeof(double) * (size_t)v.E * v.gc_stride); if (r) return r; v.gc_d = (double *)p;
+    r = dalloc(b, &p, sizeof(double) * (size_t)v.E * v.gc_stride); if (r) return r; v.gc_cost = (double *)p;
     r = dalloc(b, &p, sizeof(Kid) * (size_t)v.E * v.stride); if (r) return r; v.kid = (Kid *)p;
     b->goal_lists = true;
     return NIRRT_OK;
@@ -2855,7 +2894,7 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
     b->cfg.stop_below = (double)INFINITY;
     k_begin<<<(v.E + 127) / 128, 128, 0, s>>>(v);
     CHECK_LAUNCH();
-    if (!fam_informed(variant) && mode == NIRRT_MODE_PLANNING_RANDOM) {
+    if (fam_informed(variant) || mode == NIRRT_MODE_PLANNING_RANDOM) {      // drivers that track the goal candidates
         TRY(ensure_goal_lists(b));
         LAUNCH_D(v.dim, k_goal_init, v.E, 256, 0, s, v);
         CHECK_LAUNCH();
@@ -2971,7 +3010,7 @@ constexpr size_t kMaxGraphs = 8;
 // graphs were built) only matter to the RRT* eval driver
 static void graph_key(const View &v, View *k) {
     memcpy(k, &v, sizeof(View));     // byte copies throughout: the lookup is a memcmp
-    if (!(v.mode == NIRRT_MODE_PLANNING_RANDOM && !fam_informed(v.variant))) { k->gc_idx = nullptr; k->gc_d = nullptr; k->gc_cost = nullptr; k->kid = nullptr; }
+    if (!(v.mode == NIRRT_MODE_PLANNING_RANDOM || fam_informed(v.variant))) { k->gc_idx = nullptr; k->gc_d = nullptr; k->gc_cost = nullptr; k->kid = nullptr; k->gc_stride = 0; }
 }
 static nirrt_batch::GraphEntry *ensure_graph(nirrt_batch *b, bool pipelined) {
     if (!b->use_graph || b->graph_iters < 2) return nullptr;
