@@ -76,7 +76,7 @@ struct __align__(32) Node {
 
 enum { ST_DONE = 0, ST_PHASE1 = 1, ST_PHASE2 = 2, ST_WAIT_CLOUD = 3 };
 enum { ERR_NEAR_OVERFLOW = 1, ERR_SOL_OVERFLOW = 2, ERR_VERTEX_OVERFLOW = 4, ERR_EMPTY_CLOUD = 8,
-       ERR_PATH_DEPTH = 16, ERR_RECORD_OVERFLOW = 32, ERR_GOAL_OVERFLOW = 64, ERR_OUT_OF_RANGE = 128 };
+       ERR_PATH_DEPTH = 16, ERR_RECORD_OVERFLOW = 32, ERR_GOAL_OVERFLOW = 64, ERR_OUT_OF_RANGE = 128, ERR_CHILD_LISTS = 256 };
 
 // what a mirror-scan CTA needs before it can start streaming (written by k_top / k_steer)
 struct __align__(16) ScanHdr {
@@ -1553,11 +1553,14 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
         bool any = false;
         for (int w = 0; w < (m + 31) / 32 && !any; w++) any = s_rew[w] != 0u;
         if (any) {
-            int head = inserted ? -1 : __ldcg(&kid[new_idx].head);
+            int head = -1;       // a vertex inserted in this iteration has no children yet
             for (int k = 0; k < m; k++)
                 if ((s_rew[k >> 5] >> (k & 31)) & 1u) {
                     const int q = s_near[k];
                     kid_unlink(kid, q, s_par[k]);
+                    // a re-used vertex (duplicate guard) may already be q's parent -- the unlink above then changed its
+                    // child list, possibly its head: read it back instead of tracking it
+                    if (!inserted) head = __ldcg(&kid[new_idx].head);
                     kid_link(kid, q, new_idx, head);
                     head = q;
                     if (ns < kFrontMax) s_front[ns++] = q | 0x40000000; else ovf = true;
@@ -1570,7 +1573,8 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
     // ---- the subtrees below the re-parented vertices (left-child / right-sibling walk, one level per round)
     int *cur = s_front, *nxt = s_front + kFrontMax;
     int ncur = s_cnt[0];
-    while (ncur > 0 && !s_cnt[2]) {
+    for (int round = 0; ncur > 0 && !s_cnt[2]; round++) {
+        if (round > v.cap) { if (tid == 0) { s_cnt[2] = 1; atomicOr(&c->err, ERR_CHILD_LISTS); } break; }   // never: a tree has < cap levels
         __syncthreads();
         if (tid == 0) s_cnt[0] = 0;
         __syncthreads();
@@ -3164,6 +3168,7 @@ static std::string err_bits(int err) {
     if (err & ERR_PATH_DEPTH) m += " path deeper than 4096 edges;";
     if (err & ERR_RECORD_OVERFLOW) m += " record buffer overflow;";
     if (err & ERR_GOAL_OVERFLOW) m += " goal-candidate overflow;";
+    if (err & ERR_CHILD_LISTS) m += " internal: child lists inconsistent (goal tracking fell back to full evaluation);";
     if (err & ERR_OUT_OF_RANGE) m += " a loaded vertex lies outside the world range (the mirror scan margin assumes vertices inside it);";
     return m;
 }
