@@ -219,6 +219,10 @@ int nirrt_atan2_sync(const double *y, const double *x, int64_t n, double *out, v
 
 /* Device-resident benchmark hooks: bytes scanned per Nearest+Near pass and launch counters. */
 int nirrt_batch_counters(nirrt_batch *b, int64_t *kernel_launches, int64_t *scan_bytes_per_vertex);
+/* Work counters summed over all problems since nirrt_batch_set_problems: out8 = {expansions, sum |Near|, sum pre-filter
+ * candidates, goal-tracking traversal rounds, full goal evaluations, refreshed goal candidates, re-parented subtree
+ * roots, sum of the candidate-list length at full evaluations}.  Waits for the stream. */
+int nirrt_batch_work_stats_sync(nirrt_batch *b, int64_t *out8, void *stream);
 /* CUDA-graph bookkeeping of nirrt_batch_run: executables built (one per variant/mode, by nirrt_batch_begin),
  * graph replays launched, and capture failures (each one downgrades the batch to plain kernel launches --
  * a performance regression that is otherwise invisible). */

@@ -55,6 +55,11 @@ int nirrt_pn2_destroy(nirrt_pn2 *h);
 int nirrt_pn2_classify_sync(nirrt_pn2 *h, int batch, int dim, const float *pc, const float *start_mask,
                             const float *goal_mask, const int32_t *fps_start, int64_t *path_pred,
                             float *path_score, float *logp, void *stream);
+/* Cloud size of the following classify calls: any 16 <= n_points <= the value given to nirrt_pn2_create (buffers are
+ * sized for that).  The reference's samplers only down-sample `if len(point_cloud) > n_points`
+ * (datasets_3d/point_cloud_mask_utils_3d.py:104-112), so clouds come in every size up to pc_n_points. */
+int nirrt_pn2_set_n_points(nirrt_pn2 *h, int n_points);
+
 /* Same with DEVICE pointers, asynchronous on `stream` (no host synchronisation). */
 int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const float *pc, const float *start_mask,
                               const float *goal_mask, const int32_t *fps_start, int64_t *path_pred,

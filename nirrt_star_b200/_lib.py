@@ -86,6 +86,7 @@ def lib():
     L.nirrt_batch_set_vertex_limit.argtypes = [V, C.c_int]
     L.nirrt_batch_run_profiled_sync.argtypes = [V, C.c_int, c_fp, V]
     L.nirrt_batch_counters.argtypes = [V, c_i64p, c_i64p]
+    L.nirrt_batch_work_stats_sync.argtypes = [V, c_i64p, V]
     L.nirrt_batch_graph_stats.argtypes = [V, c_i64p, c_i64p, c_i64p]
     L.nirrt_batch_time_scan_sync.argtypes = [V, C.c_int, C.c_int, c_fp, c_i64p, V]
     # PointNet++ (include/nirrt_pointnet2.h)
@@ -93,6 +94,7 @@ def lib():
     c_u16p = C.POINTER(C.c_uint16)
     L.nirrt_pn2_create.argtypes = [C.POINTER(Pn2Layer), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(V)]
     L.nirrt_pn2_destroy.argtypes = [V]
+    L.nirrt_pn2_set_n_points.argtypes = [V, C.c_int]
     L.nirrt_pn2_classify_sync.argtypes = [V, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_i32p, c_i64p, c_fp, c_fp, V]
     L.nirrt_pn2_classify_device.argtypes = [V, C.c_int, C.c_int, V, V, V, V, V, V, V, V]
     L.nirrt_pn2_read_buffer_sync.restype = C.c_int64

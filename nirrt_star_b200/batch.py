@@ -381,6 +381,13 @@ class BatchPlanner3D:
         check(self.L.nirrt_batch_graph_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"builds": a.value, "replays": b.value, "fallbacks": c.value}
 
+    def work_stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        check(self.L.nirrt_batch_work_stats_sync(self.h, i64p(out), self.stream))
+        keys = ("expansions", "near_sum", "candidate_sum", "track_rounds", "full_goal_evals", "refreshed_candidates",
+                "reparented_roots", "full_eval_list_sum")
+        return dict(zip(keys, [int(x) for x in out]))
+
     def scan_bytes_per_vertex(self):
         """bytes one scan pass reads per vertex: 2*dim with the u16 mirror (default), 4 with the u8 mirror,
         4*dim with the f32 mirror, 8*dim without a mirror"""

@@ -146,6 +146,9 @@ struct __align__(16) EnvCtl {
     double best_val;     // its cost(vertex) + goal distance
     int err;
     unsigned stamp;   // k_expand invocations so far: tag of the Near stamps in the walk records
+    // work counters (nirrt_batch_work_stats_sync): expansions, sum |Near|, sum candidates, goal-tracking traversal
+    // rounds, full goal evaluations, refreshed goal candidates, re-parented seeds, sum of list length at full evaluations
+    unsigned long long work[8];
 };
 
 struct View {
@@ -1567,6 +1570,7 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
                 }
         }
         s_cnt[0] = ns; s_cnt[1] = 0; s_cnt[2] = ovf ? 1 : 0; s_cnt[3] = newk;
+        c->work[6] += (unsigned long long)ns;
         __threadfence_block();
     }
     __syncthreads();
@@ -1588,10 +1592,13 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
         __syncthreads();
         ncur = min(s_cnt[0], kFrontMax);
         int *tmp = cur; cur = nxt; nxt = tmp;
+        if (tid == 0) c->work[3] += 1;
     }
     __syncthreads();
     const int nd = s_cnt[1], newk = s_cnt[3];
+    if (tid == 0) c->work[5] += (unsigned long long)min(nd, kDirtyMax);
     if (s_cnt[2] || nd > kDirtyMax) {       // a huge subtree moved: evaluate everything (what the reference does every time)
+        if (tid == 0) { c->work[4] += 1; c->work[7] += (unsigned long long)*L.count; }
         goal_path_len<D>(v, c, e, nodes, sm_s, sm_i);
         return;
     }
@@ -1812,7 +1819,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         PHASE_MARK(2)
         int *near_out = v.near_out + (size_t)e * v.near_cap;
         for (int k = tid; k < m; k += blockDim.x) near_out[k] = s_near[k];
-        if (tid == 0) IT.near_cnt = m;
+        if (tid == 0) { IT.near_cnt = m; c->work[0] += 1; c->work[1] += (unsigned long long)m; c->work[2] += (unsigned long long)cnt; }
 
         // the informed family needs c_best every iteration (its sampler); the RRT* family only in the eval driver
         const bool track = fam_informed(v.variant) || v.mode == NIRRT_MODE_PLANNING_RANDOM;
@@ -2154,6 +2161,7 @@ __global__ void k_set_problems(View v, ProblemUpload u) {
     { Link l; l.elen = 0.0; l.parent = 0; l.pad = 0; v.links[o] = l; }
     c->n = 1;
     c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
+    for (int k = 0; k < 8; k++) c->work[k] = 0;
     c->state = ST_DONE; c->budget = 0; set_idle(c); c->n_rec = 0; c->err = 0; c->resumed = 0;
     c->c_best = XINF; c->c_update = XINF; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
 }
@@ -2202,6 +2210,7 @@ __global__ void k_set_problems_2d(View v, ProblemUpload2 u) {
     { Link l; l.elen = 0.0; l.parent = 0; l.pad = 0; v.links[o] = l; }
     c->n = 1;
     c->n_sol = 0; c->n_goal = 0; c->n_pc = 0;
+    for (int k = 0; k < 8; k++) c->work[k] = 0;
     c->state = ST_DONE; c->budget = 0; set_idle(c); c->n_rec = 0; c->err = 0; c->resumed = 0;
     c->c_best = XINF; c->c_update = XINF; c->tree_changed = 1; c->last_len = XINF; c->last_gp = -1;
 }
@@ -3091,6 +3100,16 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
         TRY(run_groups(b, s, iters - done));
     }
     CHECK_LAUNCH();
+    return NIRRT_OK;
+}
+
+static int fetch_ctl(nirrt_batch *b, cudaStream_t s);
+extern "C" int nirrt_batch_work_stats_sync(nirrt_batch *b, int64_t *out8, void *stream) {
+    if (!b || !out8) return fail(NIRRT_ERR_INVALID, "nirrt_batch_work_stats_sync: null argument");
+    TRY(fetch_ctl(b, (cudaStream_t)stream));
+    for (int k = 0; k < 8; k++) out8[k] = 0;
+    for (int e = 0; e < b->v.E; e++)
+        for (int k = 0; k < 8; k++) out8[k] += (int64_t)b->h_ctl[e].work[k];
     return NIRRT_OK;
 }
 

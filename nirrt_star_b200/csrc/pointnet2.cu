@@ -584,6 +584,7 @@ static const int kUpC[4] = {256, 256, 128, 128};             // outputs of fp4, 
 
 struct nirrt_pn2 {
     int N0 = 0, maxB = 0, device = 0;
+    int N0cap = 0;     // cloud size the buffers were allocated for (nirrt_pn2_set_n_points can select any size up to it)
     int n[5];
     Conv conv[34];
     float *w2 = nullptr, *b2 = nullptr;
@@ -692,7 +693,7 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
     static const int sa_mlp[4][2][3] = {{{16, 16, 32}, {32, 32, 64}}, {{64, 64, 128}, {64, 96, 128}},
                                         {{128, 196, 256}, {128, 196, 256}}, {{256, 256, 512}, {256, 384, 512}}};
     nirrt_pn2 *h = new nirrt_pn2();
-    h->N0 = n_points; h->maxB = max_batch; h->device = device;
+    h->N0 = n_points; h->N0cap = n_points; h->maxB = max_batch; h->device = device;
     h->n[0] = n_points;
     for (int l = 1; l <= 4; l++) h->n[l] = kNp[l];
 #define FAILC(msg) do { nirrt_pn2_destroy(h); return pfail(NIRRT_ERR_INVALID, msg); } while (0)
@@ -878,6 +879,16 @@ static int interp_launch(nirrt_pn2 *h, int B, int f, int mode, const __half *upf
 #undef INTERP_ARGS
     PCUDA(cudaGetLastError());
     h->launches++;
+    return NIRRT_OK;
+}
+
+// Selects the cloud size of the following classify calls (16 .. the n_points given at creation): level-0 buffers are
+// sized for the creation value and every kernel takes the size as an argument, so one engine serves clouds of any
+// size the reference's samplers produce (they only down-sample `if len(point_cloud) > n_points`).
+extern "C" int nirrt_pn2_set_n_points(nirrt_pn2 *h, int n_points) {
+    if (!h) return pfail(NIRRT_ERR_INVALID, "null handle");
+    if (n_points < 16 || n_points > h->N0cap) return pfail(NIRRT_ERR_INVALID, "nirrt_pn2_set_n_points: 16 <= n_points <= creation size required");
+    h->N0 = n_points; h->n[0] = n_points;
     return NIRRT_OK;
 }
 

@@ -29,10 +29,15 @@ class PNGWrapper:
         print(self._banner)
 
     def _engine(self, n_points):
-        eng = self._engines.get(n_points)
-        if eng is None:
-            eng = PointNet2Engine(self.state_dict, n_points=n_points, max_batch=1, device=self._device_index)
-            self._engines[n_points] = eng
+        """One engine sized for the largest cloud seen so far, re-targeted to each call's size (the samplers hand over
+        clouds of every size up to pc_n_points)."""
+        eng = self._engines.get("e")
+        if eng is None or eng.capacity < n_points:
+            if eng is not None:
+                eng.close()
+            eng = PointNet2Engine(self.state_dict, n_points=max(n_points, 2048), max_batch=1, device=self._device_index)
+            self._engines["e"] = eng
+        eng.set_n_points(n_points)
         return eng
 
     def classify_path_points(self, pc, start_mask, goal_mask):

@@ -134,10 +134,10 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                     # is left (point_cloud_mask_utils_3d.py:104-112) -- one engine per distinct size, kept for the run
                     for k, it in enumerate(items):
                         if preds[k] is None:
-                            n = len(it[0])
-                            if n not in short_engines:
-                                short_engines[n] = PointNet2Engine(state_dict, n_points=n, max_batch=1, device=device)
-                            pred, _ = short_engines[n].classify(it[0].astype(np.float32)[None], it[1][None], it[2][None], fps_start=fs[k:k + 1])
+                            if "e" not in short_engines:      # one spare engine, re-targeted to each short cloud's size
+                                short_engines["e"] = PointNet2Engine(state_dict, n_points=args.pc_n_points, max_batch=1, device=device)
+                            short_engines["e"].set_n_points(len(it[0]))
+                            pred, _ = short_engines["e"].classify(it[0].astype(np.float32)[None], it[1][None], it[2][None], fps_start=fs[k:k + 1])
                             preds[k] = pred[0]
                     return preds
             else:
@@ -147,7 +147,8 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                     return user([(it[0].astype(np.float32), it[1], it[2]) for it in items], envs)
 
             bp.set_guidance(args.pc_sample_rate, args.pc_update_cost_ratio if variant == _B.VARIANT_NIRRT_STAR else 0.0)
-            stats = {"cloud_updates": 0, "forward_calls": 0, "clouds_classified": 0, "short_clouds": 0, "update_seconds": 0.0}
+            stats = {"cloud_updates": 0, "forward_calls": 0, "clouds_classified": 0, "short_clouds": 0, "update_seconds": 0.0,
+                     "rounds": 0, "t_params": 0.0, "t_sample": 0.0, "t_forward": 0.0, "t_short": 0.0}
 
             def update_host(envs, cbest, cmin):
                 """host half of update_point_cloud for the listed problems, one batched forward"""
@@ -179,13 +180,17 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
 
             def update_device(envs, cbest, cmin):
                 n_pts, n_raw = args.pc_n_points, args.pc_n_points * args.pc_over_sample_scale
+                ta = time.perf_counter()
                 kinds = [1 if cbest[env] < np.inf else 0 for env in envs]
                 params = np.zeros((len(envs), 12))
                 for k, env in enumerate(envs):
                     if kinds[k]:
                         params[k] = _B.ellipsoid_params_3d(makers[env].x_start, makers[env].x_goal, cbest[env] / cmin[env])
+                tb = time.perf_counter()
                 counts = bp.sample_clouds(envs, kinds, params, n_pts, n_raw, args.step_len, dev["pc"].data_ptr(),
                                           dev["sm"].data_ptr(), dev["gm"].data_ptr())
+                tc = time.perf_counter()
+                stats["rounds"] += 1; stats["t_params"] += tb - ta; stats["t_sample"] += tc - tb
                 if engine is None:          # caller-supplied classifier: hand it the clouds, upload what it predicts
                     pts = bp.read_sampled_clouds(0, len(envs), n_pts)
                     items = []
@@ -206,18 +211,22 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                                        d_fs.data_ptr(), dev["pred"].data_ptr(), dev["score"].data_ptr())
                 full = [k for k in range(len(envs)) if counts[k] == n_pts]
                 bp.commit_clouds(dev["pred"].data_ptr(), None if len(full) == len(envs) else full)
+                torch.cuda.synchronize()
+                td = time.perf_counter()
+                stats["t_forward"] += td - tc
                 stats["forward_calls"] += 1; stats["clouds_classified"] += len(envs)
                 for k, env in enumerate(envs):          # short clouds: classified at their own size, like the reference
                     if counts[k] != n_pts:
                         pts = bp.read_sampled_clouds(k, 1, n_pts)[0, :counts[k]]
                         sm = get_mask(pts, makers[env].x_start[np.newaxis, :], args.step_len).astype(np.float32)
                         gm = get_mask(pts, makers[env].x_goal[np.newaxis, :], args.step_len).astype(np.float32)
-                        n = len(pts)
-                        if n not in short_engines:
-                            short_engines[n] = PointNet2Engine(state_dict, n_points=n, max_batch=1, device=device)
-                        pred, _ = short_engines[n].classify(pts.astype(np.float32)[None], sm[None], gm[None], fps_start=fs[k:k + 1])
+                        if "e" not in short_engines:
+                            short_engines["e"] = PointNet2Engine(state_dict, n_points=n_pts, max_batch=1, device=device)
+                        short_engines["e"].set_n_points(len(pts))
+                        pred, _ = short_engines["e"].classify(pts.astype(np.float32)[None], sm[None], gm[None], fps_start=fs[k:k + 1])
                         bp.set_cloud(int(env), pts[pred[0].nonzero()[0]])
                         stats["short_clouds"] += 1; stats["forward_calls"] += 1
+                stats["t_short"] += time.perf_counter() - td
 
             def update(envs, cbest, cmin):
                 if args.pc_sample_rate == 0:          # nirrt_star_png_3d.py:137-140: no cloud, no draws
@@ -251,6 +260,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
             stats_out.update(stats if neural else {})
             stats_out["plan_seconds"] = time.perf_counter() - t_plan
             stats_out["iterations"] = int(sum(len(x) for x in lists))
+            stats_out["work"] = bp.work_stats()
     out = gather_lists(lists, n_total, device=torch.device("cuda", device)) if distributed else lists
     if return_planner:
         return out, bp

@@ -56,6 +56,7 @@ class PointNet2Engine:
         _lib.require_device()
         self.L = _lib.lib()
         self.n_points, self.max_batch = int(n_points), int(max_batch)
+        self.capacity = int(n_points)      # largest cloud the buffers hold; set_n_points selects any size up to it
         self.stream = C.c_void_p(stream) if stream else None
         names = layer_names()
         layers = (_lib.Pn2Layer * len(names))()
@@ -75,6 +76,12 @@ class PointNet2Engine:
         h = C.c_void_p()
         check(self.L.nirrt_pn2_create(layers, len(names), self.n_points, self.max_batch, int(device), C.byref(h)))
         self.h = h
+
+    def set_n_points(self, n_points):
+        """Cloud size of the following classify calls (16 .. capacity)."""
+        if int(n_points) != self.n_points:
+            check(self.L.nirrt_pn2_set_n_points(self.h, int(n_points)))
+            self.n_points = int(n_points)
 
     def close(self):
         if getattr(self, "h", None):

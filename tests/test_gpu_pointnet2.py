@@ -192,3 +192,28 @@ def test_short_and_odd_sized_clouds(n):
     flip = pred[0] != wpred
     assert not np.any(flip & (np.abs(wscore - 0.5) >= 0.05))
     eng.close()
+
+
+def test_retargeted_engine_equals_dedicated_engine():
+    """nirrt_pn2_set_n_points: one engine sized for 2048 points, re-targeted to a 1300-point cloud, must give exactly
+    what an engine created for 1300 points gives (the batch planner classifies short clouds this way)."""
+    from nirrt_star_b200.pointnet2 import PointNet2Engine
+    sd = make_pointnet2_state(0)
+    pc, sm, gm = make_cloud_3d(2)
+    keep = np.sort(np.random.RandomState(5).choice(len(pc), 1300, replace=False))
+    fs = np.array([[100, 11, 12, 13]], dtype=np.int32)
+    a = PointNet2Engine(sd, n_points=1300, max_batch=1)
+    want = a.classify(pc[keep], sm[keep], gm[keep], fps_start=fs, return_logp=True)
+    b = PointNet2Engine(sd, n_points=2048, max_batch=1)
+    full = b.classify(pc, sm, gm, fps_start=fs, return_logp=True)
+    b.set_n_points(1300)
+    got = b.classify(pc[keep], sm[keep], gm[keep], fps_start=fs, return_logp=True)
+    for x, y in zip(got, want):
+        assert np.array_equal(x, y)
+    b.set_n_points(2048)
+    again = b.classify(pc, sm, gm, fps_start=fs, return_logp=True)
+    for x, y in zip(again, full):
+        assert np.array_equal(x, y)
+    with pytest.raises(Exception):
+        b.set_n_points(4096)
+    a.close(); b.close()
