@@ -162,6 +162,7 @@ struct View {
     double *vx, *vy, *vz;
     float *fx, *fy, *fz;   // f32 mirror of the coordinates (scan layout, 4 B per coordinate); null = not in use
     unsigned short *ux, *uy, *uz;   // u16 fixed-point mirror (scan layout, 2 B per coordinate); null = not in use
+    int tma;                        // u16 mirror: Nearest pass by the TMA-staged kernel (k_nearest_t); 0: LDG kernel (NIRRT_SCAN=u16ldg)
     unsigned *m8;                   // u8 fixed-point mirror: one word {x8, y8, z8, 0} per vertex (NIRRT_SCAN=u8); null = not in use
     Node *nodes;
     struct Hint *hints;  // [E][stride] ancestor hints of the cost walks (see walk_to_root)
@@ -1227,6 +1228,175 @@ __global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
 #pragma unroll
             for (int j = 0; j < kVec; j++) if (a[j] <= band) append_cand(v, c, e, base + j);
         });
+    }
+}
+
+// ---- TMA-staged u16 mirror scan (default).  Same filter, same candidate logic, same results as k_nearest_m<D, true>;
+// what changes is how the bytes reach the SM.  k_nearest_m issues three LDG.128 per thread and iteration and waits for
+// them (a CTA's share is only ~5 iterations: every one of them exposes a full DRAM round trip -- long-scoreboard stalls
+// dominate its profile, 0.80 of the copy peak).  Here one thread per CTA issues bulk copies (cp.async.bulk, completion on
+// an mbarrier) of whole 2048-vertex tiles of the x / y / z arrays into a ring of shared-memory stages as soon as the
+// scan header has arrived, so up to kTileStages * 12 KB per CTA are in flight before the first vertex is looked at and
+// the compute only ever waits on shared memory.  Evict-first L2 policy: the mirror streams through once per iteration.
+constexpr int kTileVerts = 2048;   // 256 threads x 8 vertices: 4 KB per coordinate array and stage
+constexpr int kTileStages = 3;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a mis-programmed pipeline traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_addr(bar);
+    for (uint32_t spins = 0;; spins++) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+
+// mirror squared distances of 8 consecutive vertices (see mirror_scan: cells carried as 2^23 + cell floats, exact subtraction)
+template <int D>
+__device__ __forceinline__ void mirror_u16_vals(const uint4 &x, const uint4 &y, const uint4 &z, float qx, float qy, float qz, float (&a)[8]) {
+    const unsigned wx[4] = {x.x, x.y, x.z, x.w}, wy[4] = {y.x, y.y, y.z, y.w}, wz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float dx0 = qx - __uint_as_float(__byte_perm(wx[j], 0x4B00u, 0x5410));
+        const float dy0 = qy - __uint_as_float(__byte_perm(wy[j], 0x4B00u, 0x5410));
+        const float dx1 = qx - __uint_as_float(__byte_perm(wx[j], 0x4B00u, 0x5432));
+        const float dy1 = qy - __uint_as_float(__byte_perm(wy[j], 0x4B00u, 0x5432));
+        a[2 * j] = fmaf(dy0, dy0, dx0 * dx0); a[2 * j + 1] = fmaf(dy1, dy1, dx1 * dx1);
+        if (D == 3) {
+            const float dz0 = qz - __uint_as_float(__byte_perm(wz[j], 0x4B00u, 0x5410));
+            const float dz1 = qz - __uint_as_float(__byte_perm(wz[j], 0x4B00u, 0x5432));
+            a[2 * j] = fmaf(dz0, dz0, a[2 * j]); a[2 * j + 1] = fmaf(dz1, dz1, a[2 * j + 1]);
+        }
+    }
+}
+
+template <int D, bool kForce>
+__global__ void __launch_bounds__(256, 4) k_nearest_t(View v) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int e = v.env0 + blockIdx.y;
+    EnvCtl *c = v.ctl + e;
+    const ScanHdr h = load_hdr(&c->hdr0);
+    if (!kForce && !h.go) return;
+    __shared__ __align__(128) unsigned short s_t[kTileStages][3][kTileVerts];
+    __shared__ __align__(8) uint64_t s_full[kTileStages];
+    __shared__ unsigned s_min;
+    const int tid = threadIdx.x;
+    const int per = (((h.n + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
+    const int beg = blockIdx.x * per;
+    const int end = min(h.n, beg + per);
+    if (beg >= end) return;
+    const int ntiles = (end - beg + kTileVerts - 1) / kTileVerts;
+    const unsigned short *X = v.ux + (size_t)e * v.stride, *Y = v.uy + (size_t)e * v.stride;
+    const unsigned short *Z = D == 3 ? v.uz + (size_t)e * v.stride : nullptr;
+    uint64_t policy = 0;
+    auto issue = [&](int t) {        // thread 0 only
+        const int st = t % kTileStages, first = beg + t * kTileVerts;
+        const uint32_t bytes = (uint32_t)((min(kTileVerts, end - first) * 2 + 15) & ~15);
+        mbar_expect_tx(&s_full[st], D * bytes);
+        bulk_load(s_t[st][0], X + first, bytes, &s_full[st], policy);
+        bulk_load(s_t[st][1], Y + first, bytes, &s_full[st], policy);
+        if (D == 3) bulk_load(s_t[st][2], Z + first, bytes, &s_full[st], policy);
+    };
+    if (tid == 0) {
+        s_min = 0x7f800000u;
+#pragma unroll
+        for (int st = 0; st < kTileStages; st++) mbar_init(&s_full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        policy = l2_evict_first_policy();
+        for (int t = 0; t < min(kTileStages, ntiles); t++) issue(t);
+    }
+    __syncthreads();
+    float a1 = INFINITY, a2 = INFINITY;   // best and second-best mirror value of this thread
+    int i1 = INT_MAX;
+    const float thr = h.thr;              // speculative Near ball around x_rand (see top_body)
+    for (int t = 0; t < ntiles; t++) {
+        const int st = t % kTileStages;
+        mbar_wait(&s_full[st], (uint32_t)((t / kTileStages) & 1));
+        const int base = beg + t * kTileVerts + tid * 8;
+        if (base < end) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(&s_t[st][0][tid * 8]);
+            const uint4 y = *reinterpret_cast<const uint4 *>(&s_t[st][1][tid * 8]);
+            uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            if (D == 3) z = *reinterpret_cast<const uint4 *>(&s_t[st][2][tid * 8]);
+            float a[8];
+            mirror_u16_vals<D>(x, y, z, h.qx, h.qy, h.qz, a);
+            if (base + 8 > end) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (base + j >= end) a[j] = INFINITY;
+            }
+            const float m = vec_min(a);
+            if (m < a2) {                     // rare once the running values have settled
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    a2 = fminf(a2, fmaxf(a[j], a1));
+                    if (a[j] < a1) { a1 = a[j]; i1 = base + j; }
+                }
+            }
+            if (m <= thr) {                   // ~|Near| of the env's vertices: cost proportional to the hits
+                unsigned hit = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) hit |= (a[j] <= thr ? 1u : 0u) << j;
+                while (hit) {
+                    const int j = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    const int slot = atomicAdd(&IT.spec_cnt, 1) - h.base;
+                    if (slot < v.near_cap) cand2_of(v, e)[slot] = base + j;
+                }
+            }
+        }
+        if (t + kTileStages < ntiles) {       // the stage is free once every thread has read its vertices
+            __syncthreads();
+            if (tid == 0) issue(t + kTileStages);
+        }
+    }
+    // a >= 0: the float order is the order of the bit patterns
+    const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(a1));
+    if ((tid & 31) == 0) atomicMin(&s_min, wmin);
+    __syncthreads();
+    const float amin = __uint_as_float(s_min);
+    // band in the distance domain, rounded up: sqrt(a) <= sqrt(amin) + 2 * margin
+    const float lim = __fadd_ru(__fsqrt_ru(amin), h.band);
+    const float band = __fmul_ru(__fmul_ru(lim, lim), 1.000001f);
+    if (a1 <= band) {
+        if (a2 > band) append_cand(v, c, e, i1);
+        else {      // rare: several of this thread's vertices inside the band -- re-read them (tiles t with base < end)
+            for (int t = 0; t < ntiles; t++) {
+                const int base = beg + t * kTileVerts + tid * 8;
+                if (base >= end) break;
+                const uint4 x = __ldcs(reinterpret_cast<const uint4 *>(X + base));
+                const uint4 y = __ldcs(reinterpret_cast<const uint4 *>(Y + base));
+                uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                if (D == 3) z = __ldcs(reinterpret_cast<const uint4 *>(Z + base));
+                float a[8];
+                mirror_u16_vals<D>(x, y, z, h.qx, h.qy, h.qz, a);
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (base + j < end && a[j] <= band) append_cand(v, c, e, base + j);
+            }
+        }
     }
 }
 
@@ -2303,7 +2473,8 @@ static void launch_scan(const View &v, int which, int count, cudaStream_t s, boo
     if (v.m8 && which == 0) {
         k = v.dim == 3 ? k_nearest_b<3, kForce> : k_nearest_b<2, kForce>;
     } else if (v.ux) {
-        if (which == 0) k = v.dim == 3 ? k_nearest_m<3, true, kForce> : k_nearest_m<2, true, kForce>;
+        if (which == 0 && v.tma) k = v.dim == 3 ? k_nearest_t<3, kForce> : k_nearest_t<2, kForce>;
+        else if (which == 0) k = v.dim == 3 ? k_nearest_m<3, true, kForce> : k_nearest_m<2, true, kForce>;
         else k = v.dim == 3 ? k_near_m<3, true, kForce> : k_near_m<2, true, kForce>;
     } else if (v.fx) {
         if (which == 0) k = v.dim == 3 ? k_nearest_m<3, false, kForce> : k_nearest_m<2, false, kForce>;
@@ -2496,6 +2667,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         } else {
             DALLOC(v.ux, unsigned short, EV); DALLOC(v.uy, unsigned short, EV);
             if (v.dim == 3) DALLOC(v.uz, unsigned short, EV);
+            v.tma = !(mode && strcmp(mode, "u16ldg") == 0);
         }
     }
     DALLOC(v.nodes, Node, EV);

@@ -220,7 +220,7 @@ def _run_batch(B, problems, seeds, iters, variant=0, env=None):
 
 @pytest.mark.parametrize("variant", [0, 1])
 def test_scan_layouts_and_pipelines_agree(B, variant):
-    """The u16 fixed-point mirror (default), the f32 mirror and the plain f64 scans are three filters in
+    """The u16 fixed-point mirror (default: TMA-staged k_nearest_t; u16ldg: the LDG kernel), the f32 mirror and the plain f64 scans are filters in
     front of the same exact arithmetic, and groups / programmatic dependent launch only reorder
     independent problems: every configuration must produce bit-identical trees (and match the oracle)."""
     E, iters = 12, 1200
@@ -229,6 +229,8 @@ def test_scan_layouts_and_pipelines_agree(B, variant):
     base = _run_batch(B, problems, seeds, iters, variant)
     assert base[3] == 6                                           # default layout: 2 B per coordinate
     for env, bpv in (({"NIRRT_SCAN": "f32"}, 12), ({"NIRRT_SCAN": "f64"}, 24), ({"NIRRT_GROUPS": "5"}, 6),
+                     ({"NIRRT_SCAN": "u16ldg"}, 6), ({"NIRRT_SCAN": "u16ldg", "NIRRT_GROUPS": "3", "NIRRT_CHUNKS": "7"}, 6),
+                     ({"NIRRT_CHUNKS": "1"}, 6), ({"NIRRT_CHUNKS": "13", "NIRRT_GROUPS": "2"}, 6),
                      ({"NIRRT_SCAN": "u8"}, 4), ({"NIRRT_SCAN": "u8", "NIRRT_GROUPS": "4", "NIRRT_CHUNKS": "3"}, 4),
                      ({"NIRRT_SCAN": "u8", "NIRRT_GROUPS": "3", "NIRRT_PIPELINE": "1"}, 4),
                      ({"NIRRT_GROUPS": "5", "NIRRT_GRAPH": "0"}, 6), ({"NIRRT_SCAN": "f64", "NIRRT_GROUPS": "3"}, 24),
