@@ -132,6 +132,7 @@ struct __align__(16) EnvCtl {
     int state, saved_state, p1_done, left, budget, n_rec, resumed;
     // iteration scratch
     int cand_cnt;
+    int scan_min;     // SAD scan: smallest L1 cell distance any chunk of this problem has seen so far in this iteration
     double x_rand[3];
     double curr_cost, c_best, c_update;
     double margin;    // bound on |mirror distance - f64 distance| for vertices inside the world range, in the
@@ -163,6 +164,7 @@ struct View {
     float *fx, *fy, *fz;   // f32 mirror of the coordinates (scan layout, 4 B per coordinate); null = not in use
     unsigned short *ux, *uy, *uz;   // u16 fixed-point mirror (scan layout, 2 B per coordinate); null = not in use
     int tma;                        // u16 mirror: Nearest pass by the TMA-staged kernel (k_nearest_t); 0: LDG kernel (NIRRT_SCAN=u16ldg)
+    int sad;                        // u8 mirror: Nearest pass by the SAD kernel (k_nearest_s, L1 filter); 0: DP4A kernel (NIRRT_SCAN=u8)
     unsigned *m8;                   // u8 fixed-point mirror: one word {x8, y8, z8, 0} per vertex (NIRRT_SCAN=u8); null = not in use
     Node *nodes;
     struct Hint *hints;  // [E][stride] ancestor hints of the cost walks (see walk_to_root)
@@ -544,6 +546,27 @@ __device__ __forceinline__ void store_hdr_u8(ScanHdr *h, const EnvCtl *c, int di
     r.base = base;
     *h = r;
 }
+// SAD scan (k_nearest_s): qx = packed query cells, thr = L1 threshold in cells of the speculative Near ball.
+// With vertex and query rounded to cells, every axis of the cell difference is within 1 of the scaled true difference,
+// so a vertex at scaled L2 distance d has L1 cell distance <= sqrt(dim) * d + dim, and d <= L1 + dim.
+__device__ __forceinline__ int sad_bound(const View &v, float d_cells) {
+    return (int)(d_cells * (v.dim == 3 ? 1.7320509f : 1.4142136f) * 1.000001f) + v.dim + 1;
+}
+__device__ __forceinline__ void store_hdr_sad(const View &v, ScanHdr *h, const EnvCtl *c, int go, int n, const double *q, float thr_sq, int base) {
+    ScanHdr r;
+    r.go = go; r.n = n;
+    unsigned packed = 0; bool inside = true;
+    for (int d = 0; d < v.dim; d++) {
+        int qi = __double2int_rn((q[d] - c->qlo[d]) * c->qscale);
+        if (qi < 0 || qi > 255) { inside = false; qi = min(255, max(0, qi)); }
+        packed |= (unsigned)qi << (8 * d);
+    }
+    r.qx = __uint_as_float(packed); r.qy = 0.f; r.qz = 0.f;
+    // thr_sq = (scaled radius + margin)^2, rounded up: everything inside that ball has L1 <= sad_bound(radius)
+    r.thr = __int_as_float(inside ? sad_bound(v, __fsqrt_ru(fminf(thr_sq, 1.0e9f))) : 0x3fffffff);
+    r.band = 0.f; r.base = base;
+    *h = r;
+}
 template <int kMirror>   // 2: u16 mirror, 1: f32 mirror, 0: none (f64 scans: only go / n matter)
 __device__ __forceinline__ void store_hdr(ScanHdr *h, const EnvCtl *c, int go, int n, const double *q, float thr, int base) {
     ScanHdr r;
@@ -555,7 +578,8 @@ __device__ __forceinline__ void store_hdr(ScanHdr *h, const EnvCtl *c, int go, i
 }
 __device__ __forceinline__ void write_hdr(const View &v, EnvCtl *c, int which, int go, const double *q, float thr, int base = 0) {
     ScanHdr *h = which == 0 ? &c->hdr0 : &IT.hdr1;
-    if (v.m8) store_hdr_u8(h, c, v.dim, go, c->n, q, thr, base);
+    if (v.m8 && v.sad && which == 0) { store_hdr_sad(v, h, c, go, c->n, q, thr, base); c->scan_min = 0x3fffffff; }
+    else if (v.m8) store_hdr_u8(h, c, v.dim, go, c->n, q, thr, base);
     else if (v.ux) store_hdr<2>(h, c, go, c->n, q, thr, base);
     else if (v.fx) store_hdr<1>(h, c, go, c->n, q, thr, base);
     else store_hdr<0>(h, c, go, c->n, q, thr, base);
@@ -1239,7 +1263,6 @@ __global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
 // scan header has arrived, so up to kTileStages * 12 KB per CTA are in flight before the first vertex is looked at and
 // the compute only ever waits on shared memory.  Evict-first L2 policy: the mirror streams through once per iteration.
 constexpr int kTileVerts = 2048;   // 256 threads x 8 vertices: 4 KB per coordinate array and stage
-constexpr int kTileStages = 3;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -1292,8 +1315,8 @@ __device__ __forceinline__ void mirror_u16_vals(const uint4 &x, const uint4 &y, 
     }
 }
 
-template <int D, bool kForce>
-__global__ void __launch_bounds__(256, 4) k_nearest_t(View v) {
+template <int D, bool kForce, int kTileStages, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_nearest_t(View v) {
     pdl_wait();
     pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
@@ -1496,6 +1519,113 @@ __global__ void __launch_bounds__(256, 5) k_nearest_b(View v) {
 #pragma unroll
             for (int j = 0; j < 16; j++) if (a[j] <= band) append_cand(v, c, e, byte_index(base, j));
         });
+    }
+}
+
+// ---- SAD scan (default): 4 bytes per vertex {x8, y8, z8, 0}, ONE instruction per vertex.
+// VABSDIFF4 with accumulation sums |m_b - q_b| over the four bytes of a word: the L1 distance of the vertex to the
+// query in cells.  L1 is a conservative stand-in for the L2 test (see sad_bound): the pass keeps every vertex whose L1
+// distance is within the bound of the speculative Near ball -- staged in shared memory with the CTA-local counter,
+// flushed with ONE global atomic per CTA -- and tracks the minimum; the Nearest candidates are the staged vertices
+// within the bound derived from the smallest L1 distance ANY chunk of the problem has published so far (any vertex's
+// distance is an upper bound of the nearest one's, so a stale value only widens the band).  Everything that passes is
+// re-decided in exact float64 by k_expand, so the results are bit-identical to every other scan layout.
+// Against the u16 pass: 4 instead of 6 bytes per vertex and ~3 instead of ~12 issued instructions per vertex -- the
+// pass is bound by HBM, not by instruction issue -- at the price of a coarser filter (~2.5x the Near candidates and
+// ~30 instead of ~12 Nearest candidates for k_expand's exact tests at 1e5 vertices).
+constexpr int kHitCap = 1024;     // staged hits per CTA; more: the problem falls back to its own scans for this iteration
+template <int D, bool kForce>
+__global__ void __launch_bounds__(256, 6) k_nearest_s(View v) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int e = v.env0 + blockIdx.y;
+    EnvCtl *c = v.ctl + e;
+    const ScanHdr h = load_hdr(&c->hdr0);
+    if (!kForce && !h.go) return;
+    __shared__ int s_cnt, s_min, s_band, s_slot;
+    __shared__ int s_hidx[kHitCap];
+    __shared__ unsigned short s_hs[kHitCap];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_cnt = 0; s_min = 0x3fffffff; }
+    __syncthreads();
+    const int per = (((h.n + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
+    const int beg = blockIdx.x * per;
+    const int end = min(h.n, beg + per);
+    if (beg >= end) return;
+    const unsigned q = __float_as_uint(h.qx);
+    const int thr = __float_as_int(h.thr);
+    const unsigned *M = v.m8 + (size_t)e * v.stride;
+    int best = 0x3fffffff;
+    auto one = [&](unsigned w, int idx) {
+        const int s = (int)__vsadu4(w, q);
+        best = min(best, s);
+        if (s <= thr) {
+            const int p = atomicAdd(&s_cnt, 1);
+            if (p < kHitCap) { s_hidx[p] = idx; s_hs[p] = (unsigned short)s; }
+        }
+    };
+    // a CTA iteration covers 16 vertices per thread: four coalesced LDG.128 per thread (warp w, load u, lane l reads
+    // vertices i0 + w*512 + u*128 + l*4 .. +3), all in flight before the first is used
+    const int step = 16 * 256;
+    for (int i0 = beg; i0 < end; i0 += step) {
+        const int base = i0 + warp * 512 + lane * 4;
+        if (i0 + step <= end) {
+            uint4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) w[u] = __ldcs(reinterpret_cast<const uint4 *>(M + base + u * 128));
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                one(w[u].x, base + u * 128); one(w[u].y, base + u * 128 + 1); one(w[u].z, base + u * 128 + 2); one(w[u].w, base + u * 128 + 3);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 128;
+                if (i < end) {
+                    const uint4 w = __ldcs(reinterpret_cast<const uint4 *>(M + i));
+                    one(w.x, i);
+                    if (i + 1 < end) one(w.y, i + 1);
+                    if (i + 2 < end) one(w.z, i + 2);
+                    if (i + 3 < end) one(w.w, i + 3);
+                }
+            }
+        }
+    }
+    const int wmin = __reduce_min_sync(0xffffffffu, best);
+    if (lane == 0) atomicMin(&s_min, wmin);
+    __syncthreads();
+    const int nh_all = s_cnt;
+    if (tid == 0) {
+        // publish this chunk's minimum, take the problem-wide one (so far): any vertex's L1 distance bounds the nearest one's
+        const int g = min(atomicMin(&c->scan_min, s_min), s_min);
+        s_band = sad_bound(v, (float)(g + D));
+        if (nh_all > kHitCap) {
+            // too many hits to stage: make both candidate lists overflow -- the problem then re-scans on its own
+            // (steer_body's exact Nearest fallback, k_expand's Near scan)
+            atomicAdd(&IT.spec_cnt, v.near_cap + 1);
+            atomicAdd(&c->cand_cnt, v.near_cap + 1);
+            s_slot = -1;
+        } else s_slot = nh_all ? atomicAdd(&IT.spec_cnt, nh_all) - h.base : 0;
+    }
+    __syncthreads();
+    if (s_slot < 0) return;
+    const int band = s_band, slot0 = s_slot;
+    int *spec = cand2_of(v, e);
+    for (int i = tid; i < nh_all; i += blockDim.x) {
+        if (slot0 + i < v.near_cap) spec[slot0 + i] = s_hidx[i];
+        if ((int)s_hs[i] <= band) append_cand(v, c, e, s_hidx[i]);
+    }
+    if (band > thr) {
+        // the Nearest band reaches beyond the staged Near ball (sparse tree): collect it from the chunk directly
+        for (int i = beg + 4 * tid; i < end; i += 4 * blockDim.x) {
+            const uint4 w = __ldcs(reinterpret_cast<const uint4 *>(M + i));
+            const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int s = (int)__vsadu4(ww[j], q);
+                if (i + j < end && s > thr && s <= band) append_cand(v, c, e, i + j);
+            }
+        }
     }
 }
 
@@ -2470,10 +2600,14 @@ template <bool kForce>
 static void launch_scan(const View &v, int which, int count, cudaStream_t s, bool pdl = false) {
     const dim3 grid(v.chunks, count);
     void (*k)(View);
-    if (v.m8 && which == 0) {
+    if (v.m8 && which == 0 && v.sad) {
+        k = v.dim == 3 ? k_nearest_s<3, kForce> : k_nearest_s<2, kForce>;
+    } else if (v.m8 && which == 0) {
         k = v.dim == 3 ? k_nearest_b<3, kForce> : k_nearest_b<2, kForce>;
     } else if (v.ux) {
-        if (which == 0 && v.tma) k = v.dim == 3 ? k_nearest_t<3, kForce> : k_nearest_t<2, kForce>;
+        if (which == 0 && v.tma == 1) k = v.dim == 3 ? k_nearest_t<3, kForce, 3, 4> : k_nearest_t<2, kForce, 3, 4>;
+        else if (which == 0 && v.tma == 2) k = v.dim == 3 ? k_nearest_t<3, kForce, 2, 6> : k_nearest_t<2, kForce, 2, 6>;
+        else if (which == 0 && v.tma == 3) k = v.dim == 3 ? k_nearest_t<3, kForce, 2, 8> : k_nearest_t<2, kForce, 2, 8>;
         else if (which == 0) k = v.dim == 3 ? k_nearest_m<3, true, kForce> : k_nearest_m<2, true, kForce>;
         else k = v.dim == 3 ? k_near_m<3, true, kForce> : k_near_m<2, true, kForce>;
     } else if (v.fx) {
@@ -2662,12 +2796,14 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         } else if (mode && strcmp(mode, "f32") == 0) {
             DALLOC(v.fx, float, EV); DALLOC(v.fy, float, EV);
             if (v.dim == 3) DALLOC(v.fz, float, EV);
-        } else if (mode && strcmp(mode, "u8") == 0) {
+        } else if (mode && (strcmp(mode, "u8") == 0 || strcmp(mode, "s8") == 0)) {
             DALLOC(v.m8, unsigned, EV);
+            v.sad = strcmp(mode, "s8") == 0;
         } else {
             DALLOC(v.ux, unsigned short, EV); DALLOC(v.uy, unsigned short, EV);
             if (v.dim == 3) DALLOC(v.uz, unsigned short, EV);
-            v.tma = !(mode && strcmp(mode, "u16ldg") == 0);
+            v.tma = (mode && strcmp(mode, "u16ldg") == 0) ? 0 : 1;
+            if (const char *tv = getenv("NIRRT_TMA")) v.tma = atoi(tv);
         }
     }
     DALLOC(v.nodes, Node, EV);
