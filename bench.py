@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--nirrt-iter-max", type=int, default=10000)
     ap.add_argument("--nirrt-iter-after", type=int, default=5000)
     ap.add_argument("--no-nirrt", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the small-tree legs (BASELINE configs[0] and configs[1])")
+    ap.add_argument("--small-only", action="store_true", help="run only the small-tree legs (profiling runs)")
     ap.add_argument("--nirrt-only", action="store_true", help="run only the NIRRT* leg (profiling runs)")
     ap.add_argument("--pointnet2-only", action="store_true", help="run only the PointNet++ leg (profiling runs)")
     return ap.parse_args()
@@ -362,6 +364,65 @@ def bench_pointnet2(args, world, rank, local, peaks, cpu=True):
 
 
 # ------------------------------------------------------------------------------------------------
+# small-tree legs: BASELINE configs[0] (rrt_star 2D, 1 problem, iter_max = 500: the reference's demo_planning_2d.py path)
+# and configs[1] (irrt_star 2D, 64 problems batched, iter_max = 5000).  Here the scan is a few microseconds; what is
+# measured is the latency of one lock-step iteration (launch + dependency chain of k_expand), the regime every real
+# eval configuration of the reference (iter_max <= 10000) lives in.
+
+def _small_cpu_worker(args):
+    """numpy oracle of the 2D planners (restates rrt_star_2d.py / irrt_star_2d.py) for `seconds` on one problem"""
+    env_idx, seed, iter_max, variant, seconds = args
+    from nirrt_star_b200.synthetic import make_problem_2d
+    from oracle.planner2d_oracle import Oracle2D
+    o = Oracle2D(make_problem_2d(env_idx), iter_max, seed=seed)
+    t0 = time.perf_counter(); it = 0
+    while it < iter_max and time.perf_counter() - t0 < seconds:
+        o.run(min(50, iter_max - it), variant, 0); it += min(50, iter_max - it)
+    return it, time.perf_counter() - t0
+
+
+def bench_small(args, local, cpu=True):
+    import torch
+    from nirrt_star_b200 import batch as B
+    from nirrt_star_b200.synthetic import make_problem_2d
+    out = {}
+    for name, E, iter_max, variant, reps in (("config0_rrt_star_2d_1x500", 1, 500, B.VARIANT_RRT_STAR, 20),
+                                              ("config1_irrt_star_2d_64x5000", 64, 5000, B.VARIANT_IRRT_STAR, 3)):
+        problems = [make_problem_2d(300 + i) for i in range(E)]
+        best = None
+        nv = None
+        for r in range(reps + 1):                      # first repetition = warm-up (library, graph build)
+            bp = B.BatchPlanner2D(problems, iter_max, seeds=[900 + i for i in range(E)], device=local)
+            bp.begin(variant, B.MODE_PLANNING, iter_max)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            bp.run(iter_max)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            if r > 0 and (best is None or ms < best):
+                best = ms
+            _, _, nv = bp.env_state()
+            bp.close()
+        leg = {"value": E * iter_max / (best / 1e3), "unit": UNIT, "problems": E, "iter_max": iter_max,
+               "us_per_lockstep_iteration": 1e3 * best / iter_max, "ms_total": best, "mean_vertices_at_end": float(nv.mean()),
+               "what": "nirrt_batch_run(iter_max) of the planning() loop body, device-resident, CUDA events, best of %d" % reps}
+        if cpu:
+            cores = os.cpu_count() or 1
+            workers = min(cores, E)
+            ctx = mp.get_context("spawn")
+            with ctx.Pool(workers) as pool:
+                res = pool.map(_small_cpu_worker, [(300 + i, 900 + i, iter_max, variant, 8.0) for i in range(workers)])
+            rate = sum(it / el for it, el in res)
+            leg["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": workers, "kind": "port", "per_core": rate / workers,
+                                   "sample": f"{workers} problem(s), one per host core, numpy oracle of the same loop body for up to 8 s or "
+                                             f"{iter_max} iterations each ({sum(it for it, _ in res)} iterations)"}
+        out[name] = leg
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # NIRRT* leg: the whole planner of BASELINE configs[3]/[4] -- informed + guidance-cloud sampling, cloud updates by
 # batched PointNet++ forwards -- through nirrt_star_b200.eval.plan_batch (what eval_planning_3d.py -p nirrt_star
 # -n pointnet2 does one problem at a time, eval_planning_3d.py:101-126)
@@ -444,6 +505,11 @@ def main():
         pn2 = bench_pointnet2(args, world, rank, local, peaks, cpu=False)
         if rank == 0:
             print(json.dumps(pn2), flush=True)
+        return
+    if args.small_only:
+        sm = bench_small(args, local, cpu=not args.no_cpu_baseline) if rank == 0 else None
+        if rank == 0:
+            print(json.dumps(sm), flush=True)
         return
     if args.nirrt_only:
         nr = bench_nirrt(args, world, rank, local)
@@ -644,6 +710,9 @@ def main():
         pn2 = bench_pointnet2(args, world, rank, local, peaks)
     if not args.no_nirrt:
         nirrt = bench_nirrt(args, world, rank, local)
+    small = None
+    if not args.no_small and rank == 0 and world == 1:
+        small = bench_small(args, local, cpu=not args.no_cpu_baseline)
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -661,7 +730,7 @@ def main():
                "eval_variant": {"value": value_eval, "unit": UNIT, "ms_per_step": ms_eval / K, "ms_per_iteration": ms_eval / K / ips,
                                 "graph": graph_eval,
                                 "what": "planning_random loop body (adds goal-parent search + path length per iteration)"},
-               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2, "nirrt_star": nirrt}
+               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2, "nirrt_star": nirrt, "small_trees": small}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
