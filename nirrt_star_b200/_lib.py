@@ -39,7 +39,12 @@ def lib():
     if _LIB is not None:
         return _LIB
     path = _build.LIB
-    if not os.path.exists(path) or _build.needs_build():
+    variant = os.environ.get("NIRRT_LIB_VARIANT")
+    if variant:      # development build (profiles/tools/phase_timing.py); must have been built explicitly
+        path = os.path.join(os.path.dirname(_build.LIB), f"libnirrt_b200_{variant}.so")
+        if not os.path.exists(path):
+            raise NirrtError(f"{path} not found: build it with nirrt_star_b200.build.build_variant")
+    elif not os.path.exists(path) or _build.needs_build():
         # sources newer than the binary (or no binary): rebuild under a file lock (several ranks may get here at
         # once); a stale binary is never loaded silently -- its ABI may no longer match the argtypes below
         try:

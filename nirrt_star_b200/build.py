@@ -49,6 +49,20 @@ def build_locked():
             fcntl.flock(lock, fcntl.LOCK_UN)
 
 
+def build_variant(name, extra_flags):
+    """Development builds beside the product library (e.g. -DNIRRT_PHASE_TIMING): libnirrt_b200_<name>.so, selected at
+    load time with NIRRT_LIB_VARIANT=<name> (profiles/tools/phase_timing.py).  Never used by tests or the bench."""
+    lib = os.path.join(HERE, f"libnirrt_b200_{name}.so")
+    objs = []
+    for unit, extra in UNITS:
+        obj = os.path.join(CSRC, unit.replace(".cu", f".{name}.o"))
+        subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                               "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, unit), "-o", obj] + extra + list(extra_flags))
+        objs.append(obj)
+    subprocess.check_call([_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs)
+    return lib
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB

@@ -283,6 +283,10 @@ struct __align__(16) Link {
 };
 #ifdef NIRRT_PHASE_TIMING
 __device__ unsigned long long g_walk_stats[4];
+// k_expand phase clocks summed over CTAs (development build only, profiles/tools/phase_timing.py):
+// [0] entry->steer done, [1] sort, [2] filter, [3] walks + ChooseParent, [4] Rewire, [5] goal bookkeeping, [6] records,
+// [7] top (next sample), [8] CTA count
+__device__ unsigned long long g_phase[16];
 #endif
 constexpr int kHintHops = 8;
 struct __align__(32) Hint {     // one 32-byte sector
@@ -1186,6 +1190,14 @@ __device__ __forceinline__ void mirror_scan(const View &v, int e, int beg, int e
         visit(a, i);
     }
 }
+// u16 mirror, software pipelined: the loads of iteration i + 1 are issued before iteration i is evaluated, so a warp
+// always has one set of loads in flight while it computes (the plain loop alternates "wait for the loads" and "compute":
+// per-SM throughput = bytes in flight / (latency + compute time); pipelined it is bytes in flight / max of the two).
+template <int D, typename F>
+__device__ __forceinline__ void mirror_scan_u16_pipelined(const View &v, int e, int beg, int end, float qx, float qy, float qz, F &&visit);
+
+template <int D>
+__device__ __forceinline__ void mirror_u16_vals(const uint4 &x, const uint4 &y, const uint4 &z, float qx, float qy, float qz, float (&a)[8]);
 template <int N> __device__ __forceinline__ float vec_min(const float (&a)[N]) {
     float m = fminf(a[0], a[1]);
 #pragma unroll
@@ -1193,13 +1205,42 @@ template <int N> __device__ __forceinline__ float vec_min(const float (&a)[N]) {
     return m;
 }
 
+template <int D, typename F>
+__device__ __forceinline__ void mirror_scan_u16_pipelined(const View &v, int e, int beg, int end, float qx, float qy, float qz, F &&visit) {
+    const unsigned short *X = v.ux + (size_t)e * v.stride, *Y = v.uy + (size_t)e * v.stride;
+    const unsigned short *Z = D == 3 ? v.uz + (size_t)e * v.stride : nullptr;
+    const int step = 8 * blockDim.x;
+    int i = beg + 8 * threadIdx.x;
+    if (i >= end) return;
+    uint4 x = __ldcs(reinterpret_cast<const uint4 *>(X + i)), y = __ldcs(reinterpret_cast<const uint4 *>(Y + i));
+    uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    if (D == 3) z = __ldcs(reinterpret_cast<const uint4 *>(Z + i));
+    for (;;) {
+        const int nx = i + step;
+        uint4 x2 = x, y2 = y, z2 = z;
+        if (nx < end) {
+            x2 = __ldcs(reinterpret_cast<const uint4 *>(X + nx)); y2 = __ldcs(reinterpret_cast<const uint4 *>(Y + nx));
+            if (D == 3) z2 = __ldcs(reinterpret_cast<const uint4 *>(Z + nx));
+        }
+        float a[8];
+        mirror_u16_vals<D>(x, y, z, qx, qy, qz, a);
+        if (i + 8 > end) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (i + j >= end) a[j] = INFINITY;
+        }
+        visit(a, i);
+        if (nx >= end) break;
+        x = x2; y = y2; z = z2; i = nx;
+    }
+}
+
 __device__ __forceinline__ void append_cand(const View &v, EnvCtl *c, int e, int idx) {
     const int slot = atomicAdd(&c->cand_cnt, 1);
     if (slot < v.near_cap) v.cand[(size_t)e * v.near_cap + slot] = idx;
 }
 
-template <int D, bool kU16, bool kForce>
-__global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
+template <int D, bool kU16, bool kForce, bool kPipe = false>
+__global__ void __launch_bounds__(256, kPipe ? 5 : 8) k_nearest_m(View v) {
     pdl_wait();
     pdl_launch_dependents();
     const int e = v.env0 + blockIdx.y;
@@ -1217,7 +1258,7 @@ __global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
     float a1 = INFINITY, a2 = INFINITY;   // best and second-best mirror value of this thread
     int i1 = INT_MAX;
     const float thr = h.thr;              // speculative Near ball around x_rand (see top_body)
-    mirror_scan<D, kU16>(v, e, beg, end, h.qx, h.qy, h.qz, [&](const float (&a)[kVec], int base) {
+    auto visit = [&](const float (&a)[kVec], int base) {
         const float m = vec_min(a);
         if (m < a2) {                     // rare once the running values have settled
 #pragma unroll
@@ -1237,7 +1278,9 @@ __global__ void __launch_bounds__(256, 8) k_nearest_m(View v) {
                 if (slot < v.near_cap) cand2_of(v, e)[slot] = base + j;
             }
         }
-    });
+    };
+    if constexpr (kPipe) mirror_scan_u16_pipelined<D>(v, e, beg, end, h.qx, h.qy, h.qz, visit);
+    else mirror_scan<D, kU16>(v, e, beg, end, h.qx, h.qy, h.qz, visit);
     // a >= 0: the float order is the order of the bit patterns
     const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(a1));
     if ((threadIdx.x & 31) == 0) atomicMin(&s_min, wmin);
@@ -1948,6 +1991,9 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
     pdl_wait();
     const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
+#ifdef NIRRT_PHASE_TIMING
+    const long long t_entry = clock64();
+#endif
     if (v.fuse_steer) {
         if (!c->hdr0.go) return;
         if (threadIdx.x < 32) steer_body<D>(v, e);
@@ -2299,14 +2345,26 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             if (c->state == ST_PHASE1) c->p1_done++; else c->left--;
         }
     }
+#ifdef NIRRT_PHASE_TIMING
+    const long long t_rec = clock64();
+#endif
     if (v.fuse_top) {   // the next iteration's driver step + sample
         __syncthreads();
         top_body<D>(v, e, g, !skipped, sm_s, sm_i);
     }
 #ifdef NIRRT_PHASE_TIMING
-    if (tid == 0 && (e % 97) == 0 && (c->n % 50) == 0)
-        printf("expand e=%d n=%d cand=%d near=%d sort=%lld filter=%lld walks=%lld serial=%lld goal=%lld top=%lld fast=%llu slow=%llu\n", e, c->n, c->cand_cnt, IT.near_cnt,
-               t_ph[1] - t_ph[0], t_ph[2] - t_ph[1], t_ph[3] - t_ph[2], t_ph[4] - t_ph[3], t_ph[5] - t_ph[4], clock64() - t_ph[5], t_ph[6] - t_ph[2], t_ph[7] - t_ph[6]);
+    if (tid == 0 && !skipped) {
+        const long long t_end = clock64();
+        atomicAdd(&g_phase[0], (unsigned long long)(t_ph[0] - t_entry));
+        atomicAdd(&g_phase[1], (unsigned long long)(t_ph[1] - t_ph[0]));
+        atomicAdd(&g_phase[2], (unsigned long long)(t_ph[2] - t_ph[1]));
+        atomicAdd(&g_phase[3], (unsigned long long)(t_ph[3] > t_ph[2] ? t_ph[3] - t_ph[2] : 0));
+        atomicAdd(&g_phase[4], (unsigned long long)(t_ph[3] > t_ph[2] ? t_ph[4] - t_ph[3] : t_ph[4] - t_ph[2]));
+        atomicAdd(&g_phase[5], (unsigned long long)(t_ph[5] - t_ph[4]));
+        atomicAdd(&g_phase[6], (unsigned long long)(t_rec - t_ph[5]));
+        atomicAdd(&g_phase[7], (unsigned long long)(t_end - t_rec));
+        atomicAdd(&g_phase[8], 1ull);
+    }
 #endif
 }
 
@@ -2608,6 +2666,7 @@ static void launch_scan(const View &v, int which, int count, cudaStream_t s, boo
         if (which == 0 && v.tma == 1) k = v.dim == 3 ? k_nearest_t<3, kForce, 3, 4> : k_nearest_t<2, kForce, 3, 4>;
         else if (which == 0 && v.tma == 2) k = v.dim == 3 ? k_nearest_t<3, kForce, 2, 6> : k_nearest_t<2, kForce, 2, 6>;
         else if (which == 0 && v.tma == 3) k = v.dim == 3 ? k_nearest_t<3, kForce, 2, 8> : k_nearest_t<2, kForce, 2, 8>;
+        else if (which == 0 && v.tma == 4) k = v.dim == 3 ? k_nearest_m<3, true, kForce, true> : k_nearest_m<2, true, kForce, true>;
         else if (which == 0) k = v.dim == 3 ? k_nearest_m<3, true, kForce> : k_nearest_m<2, true, kForce>;
         else k = v.dim == 3 ? k_near_m<3, true, kForce> : k_near_m<2, true, kForce>;
     } else if (v.fx) {
@@ -3420,6 +3479,19 @@ extern "C" int nirrt_batch_work_stats_sync(nirrt_batch *b, int64_t *out8, void *
         for (int k = 0; k < 8; k++) out8[k] += (int64_t)b->h_ctl[e].work[k];
     return NIRRT_OK;
 }
+
+#ifdef NIRRT_PHASE_TIMING
+// development build only: mean SM clocks per k_expand phase since the last call (see g_phase)
+extern "C" int nirrt_debug_phase_clocks(double *out9) {
+    unsigned long long h[16];
+    CUDA_TRY(cudaMemcpyFromSymbol(h, g_phase, sizeof(h)));
+    for (int k = 0; k < 8; k++) out9[k] = h[8] ? (double)h[k] / (double)h[8] : 0.0;
+    out9[8] = (double)h[8];
+    memset(h, 0, sizeof(h));
+    CUDA_TRY(cudaMemcpyToSymbol(g_phase, h, sizeof(h)));
+    return NIRRT_OK;
+}
+#endif
 
 extern "C" int nirrt_batch_graph_stats(nirrt_batch *b, int64_t *builds, int64_t *replays, int64_t *fallbacks) {
     if (!b) return fail(NIRRT_ERR_INVALID, "null batch");

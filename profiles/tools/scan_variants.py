@@ -26,11 +26,11 @@ v, p, n = bp.read_trees()
 bp.close()
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6545.6
 out = []
-variants = [("u16 LDG", {"NIRRT_SCAN": "u16ldg"}), ("u16 TMA 3 stages x 4 CTAs", {"NIRRT_TMA": "1"}), ("u16 TMA 2 x 6", {"NIRRT_TMA": "2"}),
+variants = [("u16 LDG", {"NIRRT_SCAN": "u16ldg"}), ("u16 LDG pipelined", {"NIRRT_TMA": "4"}), ("u16 TMA 3 stages x 4 CTAs", {"NIRRT_TMA": "1"}), ("u16 TMA 2 x 6", {"NIRRT_TMA": "2"}),
             ("u16 TMA 2 x 8", {"NIRRT_TMA": "3"}), ("f32 LDG", {"NIRRT_SCAN": "f32"}), ("u8 dp4a", {"NIRRT_SCAN": "u8"}), ("u8 SAD", {"NIRRT_SCAN": "s8"})]
 for chunks in ("10", "5", "20"):
     for name, env in variants:
-        if chunks != "10" and name.startswith(("f32", "u8 dp4a", "u16 TMA")):
+        if chunks != "10" and name.startswith(("f32", "u8", "u16 TMA")):
             continue
         for k in ("NIRRT_SCAN", "NIRRT_TMA"):
             os.environ.pop(k, None)

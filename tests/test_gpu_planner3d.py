@@ -231,6 +231,7 @@ def test_scan_layouts_and_pipelines_agree(B, variant):
     for env, bpv in (({"NIRRT_SCAN": "f32"}, 12), ({"NIRRT_SCAN": "f64"}, 24), ({"NIRRT_GROUPS": "5"}, 6),
                      ({"NIRRT_SCAN": "s8"}, 4), ({"NIRRT_SCAN": "s8", "NIRRT_GROUPS": "4", "NIRRT_CHUNKS": "3"}, 4),
                      ({"NIRRT_SCAN": "s8", "NIRRT_GROUPS": "2", "NIRRT_CHUNKS": "16", "NIRRT_GRAPH": "0"}, 4),
+                     ({"NIRRT_TMA": "4"}, 6), ({"NIRRT_TMA": "4", "NIRRT_CHUNKS": "7", "NIRRT_GROUPS": "3"}, 6), ({"NIRRT_TMA": "3"}, 6),
                      ({"NIRRT_SCAN": "u16ldg"}, 6), ({"NIRRT_SCAN": "u16ldg", "NIRRT_GROUPS": "3", "NIRRT_CHUNKS": "7"}, 6),
                      ({"NIRRT_CHUNKS": "1"}, 6), ({"NIRRT_CHUNKS": "13", "NIRRT_GROUPS": "2"}, 6),
                      ({"NIRRT_SCAN": "u8"}, 4), ({"NIRRT_SCAN": "u8", "NIRRT_GROUPS": "4", "NIRRT_CHUNKS": "3"}, 4),
