@@ -889,7 +889,7 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
     typedef typename GeomOf<D>::type G;
     EnvCtl *c = v.ctl + e;
     const int lane = threadIdx.x & 31;
-    const int go = c->hdr0.go, spec_base = c->hdr0.base, cnt = c->cand_cnt;     // independent loads: one round trip
+    const int go = __ldcg(&c->hdr0.go), spec_base = __ldcg(&c->hdr0.base), cnt = __ldcg(&c->cand_cnt);     // independent loads: one round trip (L2: cand_cnt is updated by atomics)
     if (lane == 0) { IT.go = go; IT.spec_base = spec_base; }     // what k_expand of this iteration reads
     if (!go) return;
     Node *nodes = v.nodes + (size_t)e * v.stride;
@@ -907,7 +907,7 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
             const int *cand = v.cand + (size_t)e * v.near_cap;
             have_rec = true;
             for (int k = lane; k < cnt; k += 32) {
-                const int i = cand[k];
+                const int i = __ldcg(cand + k);
                 const Node nd = load_node(nodes + i);
                 const Hint hh = load_hint(hints + i);
                 const double dx = XSUB(qx, nd.x), dy = XSUB(qy, nd.y), dz = D == 3 ? XSUB(qz, nd.z) : 0.0;
@@ -1009,7 +1009,7 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
         // scan collected around x_rand contains Near(x_new) -- no second scan.  Otherwise k_expand scans itself.
         bool same = fabs(XSUB(xnew[0], c->x_rand[0])) <= 1e-9 && fabs(XSUB(xnew[1], c->x_rand[1])) <= 1e-9;
         if (D == 3) same = same && fabs(XSUB(xnew[2], c->x_rand[2])) <= 1e-9;
-        const int use_spec = same && IT.spec_cnt - spec_base <= v.near_cap;
+        const int use_spec = same && __ldcg(&IT.spec_cnt) - spec_base <= v.near_cap;
         IT.use_spec = use_spec;
         IT.need_scan = !use_spec;
     } else { IT.use_spec = 0; IT.need_scan = 0; }
@@ -1239,21 +1239,14 @@ __device__ __forceinline__ void append_cand(const View &v, EnvCtl *c, int e, int
     if (slot < v.near_cap) v.cand[(size_t)e * v.near_cap + slot] = idx;
 }
 
-template <int D, bool kU16, bool kForce, bool kPipe = false>
-__global__ void __launch_bounds__(256, kPipe ? 5 : 8) k_nearest_m(View v) {
-    pdl_wait();
-    pdl_launch_dependents();
-    const int e = v.env0 + blockIdx.y;
-    EnvCtl *c = v.ctl + e;
-    const ScanHdr h = load_hdr(&c->hdr0);
-    if (!kForce && !h.go) return;
+// the mirror pass over vertices [beg, end) of problem e by the calling CTA (any block size): Nearest candidates of
+// the range into the problem's candidate list, speculative Near members into its cand2 list
+template <int D, bool kU16, bool kPipe>
+__device__ __forceinline__ void nearest_m_range(const View &v, int e, EnvCtl *c, const ScanHdr &h, int beg, int end) {
     __shared__ unsigned s_min;
     if (threadIdx.x == 0) s_min = 0x7f800000u;
     __syncthreads();
     constexpr int kVec = kU16 ? 8 : 4;
-    const int per = (((h.n + (int)gridDim.x - 1) / (int)gridDim.x) + kVec - 1) & ~(kVec - 1);
-    const int beg = blockIdx.x * per;
-    const int end = min(h.n, beg + per);
     if (beg >= end) return;
     float a1 = INFINITY, a2 = INFINITY;   // best and second-best mirror value of this thread
     int i1 = INT_MAX;
@@ -1298,7 +1291,21 @@ __global__ void __launch_bounds__(256, kPipe ? 5 : 8) k_nearest_m(View v) {
     }
 }
 
-// ---- TMA-staged u16 mirror scan (default).  Same filter, same candidate logic, same results as k_nearest_m<D, true>;
+template <int D, bool kU16, bool kForce, bool kPipe = false>
+__global__ void __launch_bounds__(256, kPipe ? 5 : 8) k_nearest_m(View v) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int e = v.env0 + blockIdx.y;
+    EnvCtl *c = v.ctl + e;
+    const ScanHdr h = load_hdr(&c->hdr0);
+    if (!kForce && !h.go) return;
+    constexpr int kVec = kU16 ? 8 : 4;
+    const int per = (((h.n + (int)gridDim.x - 1) / (int)gridDim.x) + kVec - 1) & ~(kVec - 1);
+    const int beg = blockIdx.x * per;
+    nearest_m_range<D, kU16, kPipe>(v, e, c, h, beg, min(h.n, beg + per));
+}
+
+// ---- TMA-staged u16 mirror scan (NIRRT_TMA=1..3; measured slower than the LDG kernel).  Same filter, same candidate logic, same results as k_nearest_m<D, true>;
 // what changes is how the bytes reach the SM.  k_nearest_m issues three LDG.128 per thread and iteration and waits for
 // them (a CTA's share is only ~5 iterations: every one of them exposes a full DRAM round trip -- long-scoreboard stalls
 // dominate its profile, 0.80 of the copy peak).  Here one thread per CTA issues bulk copies (cp.async.bulk, completion on
@@ -1986,16 +1993,14 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
 }
 
 template <int D>
-__global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
+__device__ __forceinline__ void expand_iteration(const View &v, const int e) {
     typedef typename GeomOf<D>::type G;
-    pdl_wait();
-    const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
 #ifdef NIRRT_PHASE_TIMING
     const long long t_entry = clock64();
 #endif
     if (v.fuse_steer) {
-        if (!c->hdr0.go) return;
+        if (!__ldcg(&c->hdr0.go)) return;
         if (threadIdx.x < 32) steer_body<D>(v, e);
         __syncthreads();
     } else if (!IT.go) return;
@@ -2071,9 +2076,9 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             cnt = __ldcg(&IT.fb_cnt);
             cand = list;
         } else if (IT.use_spec) {
-            cnt = IT.spec_cnt - IT.spec_base;
+            cnt = __ldcg(&IT.spec_cnt) - IT.spec_base;
             cand = cand2_of(v, e);
-        } else cnt = c->cand_cnt;
+        } else cnt = __ldcg(&c->cand_cnt);
         {
             const int limit = v.big ? min(v.near_cap, kNearBig) : kNearSmem;
             if (cnt > limit) {
@@ -2087,7 +2092,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
             int p2 = 1;
             while (p2 < cnt) p2 <<= 1;
             int *keys = reinterpret_cast<int *>(s_buf);        // kNearSmem * kNearRow / 4 = 11264 >= kNearBig ints
-            for (int i = tid; i < p2; i += blockDim.x) keys[i] = i < cnt ? cand[i] : INT_MAX;
+            for (int i = tid; i < p2; i += blockDim.x) keys[i] = i < cnt ? __ldcg(cand + i) : INT_MAX;
             if (tid == 0) s_m = 0;
             __syncthreads();
             bitonic_sort_int(keys, p2);
@@ -2103,7 +2108,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         } else if (cnt <= 256) {
             // ascending order by rank counting (the indices are distinct): one barrier instead of a sorting network
             int *s_raw = s_near;                          // scratch until the compaction below fills s_near
-            for (int i = tid; i < cnt; i += blockDim.x) s_raw[i] = cand[i];
+            for (int i = tid; i < cnt; i += blockDim.x) s_raw[i] = __ldcg(cand + i);
             if (tid == 0) s_m = 0;
             __syncthreads();
             for (int i = tid; i < cnt; i += blockDim.x) {
@@ -2116,7 +2121,7 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         } else {
             int p2 = 1;
             while (p2 < cnt) p2 <<= 1;
-            for (int i = tid; i < p2; i += blockDim.x) s_cand[i] = i < cnt ? cand[i] : INT_MAX;
+            for (int i = tid; i < p2; i += blockDim.x) s_cand[i] = i < cnt ? __ldcg(cand + i) : INT_MAX;
             if (tid == 0) s_m = 0;
             __syncthreads();
             bitonic_sort_int(s_cand, p2);
@@ -2366,6 +2371,36 @@ __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
         atomicAdd(&g_phase[8], 1ull);
     }
 #endif
+}
+
+template <int D>
+__global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
+    pdl_wait();
+    expand_iteration<D>(v, v.env0 + blockIdx.x);
+}
+
+// Small trees (capacity <= kPersistCap): the whole run of `iters` iterations of a problem in ONE launch by ONE CTA --
+// the CTA scans its own problem's mirror (a few thousand vertices: L2-resident, a few microseconds), then runs the
+// expansion (steer, Near filter, walks, ChooseParent, Rewire, goal bookkeeping, next sample), and loops.  No kernel
+// boundary between iterations, and no lock step: with one launch per iteration of a group of problems every iteration
+// lasts as long as the slowest problem of the group (measured at 64 x 5000 IRRT* 2D: 242 us per lock-step iteration
+// against a mean of 63 us per problem); here a problem's time is the sum of ITS iterations.  Same device functions,
+// same results (tests run both paths against each other).  Large trees keep the two-kernel pipeline: their scan needs
+// the whole machine.
+template <int D>
+__global__ void __launch_bounds__(kExpandThreads, 4) k_iterate(View v, int iters) {
+    const int e = v.env0 + blockIdx.x;
+    EnvCtl *c = v.ctl + e;
+    for (int it = 0; it < iters; it++) {
+        const ScanHdr h = load_hdr(&c->hdr0);          // written by k_top / by this CTA's top_body of the previous iteration
+        if (!h.go) break;                              // driver finished, waits for a guidance cloud, or budget exhausted
+        nearest_m_range<D, true, false>(v, e, c, h, 0, h.n);
+        __threadfence_block();
+        __syncthreads();
+        expand_iteration<D>(v, e);
+        __threadfence_block();
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2681,6 +2716,7 @@ static void launch_scan(const View &v, int which, int count, cudaStream_t s, boo
     launch_view(k, grid, 256, s, v, pdl);
 }
 
+constexpr int kPersistCap = 32768;       // capacity up to which a problem runs as one persistent CTA (k_iterate)
 constexpr int kMaxGroups = 32;
 constexpr int kGraphItersDefault = 16;   // steady-state iterations per CUDA graph replay (see ensure_graph)
 struct nirrt_batch {
@@ -2694,6 +2730,7 @@ struct nirrt_batch {
     int64_t graph_builds, graph_replays, graph_fallbacks, graph_clock;
     int graph_iters; // iterations per graph replay
     RunCfg cfg;      // run parameters, handed to the device by k_set_budget at the start of every run
+    bool persistent;            // small trees: one k_iterate launch per run instead of two kernels per iteration
     struct CloudWs *cloud_ws;   // device workspace of the guidance-cloud generator (allocated on first use)
     int cloud_count;            // problems in the last nirrt_batch_sample_clouds_sync call
     cudaStream_t cs; // capture origin
@@ -2808,7 +2845,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
     nirrt_batch *b = new nirrt_batch();
     memset(&b->v, 0, sizeof(View));
     b->device = d->device; b->launches = 0; b->goal_lists = false; b->h_ctl = nullptr;
-    b->cloud_ws = nullptr; b->cloud_count = 0;
+    b->cloud_ws = nullptr; b->cloud_count = 0; b->persistent = false;
     b->groups = 1; b->ev_fork = nullptr;
     for (int g = 0; g < kMaxGroups; g++) {
         b->gs[g] = nullptr; b->ev_join[g] = nullptr; b->gs2[g] = nullptr;
@@ -2838,6 +2875,13 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         if (b->groups > d->n_envs) b->groups = d->n_envs;
     }
     v.chunks = pick_chunks((v.E + b->groups - 1) / b->groups);
+    {
+        // NIRRT_PERSIST: largest capacity (vertices per problem) that runs as one persistent CTA per problem (0 disables)
+        const char *pe = getenv("NIRRT_PERSIST");
+        const int persist_cap = pe ? atoi(pe) : kPersistCap;
+        const char *mode = getenv("NIRRT_SCAN");
+        b->persistent = persist_cap > 0 && d->capacity <= persist_cap && (!mode || strcmp(mode, "u16") == 0 || strcmp(mode, "u16ldg") == 0);
+    }
     v.near_cap = d->near_capacity > 0 ? ((d->near_capacity + 63) & ~63) : kNearSmem;
     if (v.near_cap > kNearBig) { delete b; return fail(NIRRT_ERR_INVALID, "near_capacity: at most 8192"); }
     v.rec_cap = d->record_capacity > 0 ? d->record_capacity : d->capacity + 8;
@@ -2861,7 +2905,7 @@ extern "C" int nirrt_batch_create(const nirrt_batch_desc *d, nirrt_batch **out) 
         } else {
             DALLOC(v.ux, unsigned short, EV); DALLOC(v.uy, unsigned short, EV);
             if (v.dim == 3) DALLOC(v.uz, unsigned short, EV);
-            v.tma = (mode && strcmp(mode, "u16ldg") == 0) ? 0 : 1;
+            v.tma = 0;      // 0: LDG kernel (measured best); NIRRT_TMA = 1..3: TMA-staged variants, 4: software-pipelined LDG
             if (const char *tv = getenv("NIRRT_TMA")) v.tma = atoi(tv);
         }
     }
@@ -3281,7 +3325,7 @@ extern "C" int nirrt_batch_begin(nirrt_batch *b, int variant, int mode, int iter
     }
     // one-time cost of this (variant, mode): capture + instantiate + upload its iteration graph HERE, so that no
     // nirrt_batch_run ever builds one in its steady state (a later begin() with the same variant/mode finds it)
-    ensure_graph(b, can_pipeline(b));
+    if (!b->persistent) ensure_graph(b, can_pipeline(b));
     return NIRRT_OK;
 }
 
@@ -3446,6 +3490,15 @@ extern "C" int nirrt_batch_run(nirrt_batch *b, int iters, void *stream) {
     if (iters == 0) { CHECK_LAUNCH(); return NIRRT_OK; }
     const int GI = b->graph_iters;
     launch_top(b, s);
+    if (b->persistent && v.ux) {
+        View w = v;
+        w.env0 = 0; w.fuse_top = 1; w.fuse_steer = 1;
+        if (v.dim == 3) k_iterate<3><<<v.E, kExpandThreads, 0, s>>>(w, iters);
+        else k_iterate<2><<<v.E, kExpandThreads, 0, s>>>(w, iters);
+        b->launches += 1;
+        CHECK_LAUNCH();
+        return NIRRT_OK;
+    }
     if (can_pipeline(b) && iters >= 6) {
         // first and last iteration unpipelined (the first consumes k_top's sample, the last k_expand finds the budget
         // exhausted), an even number of pipelined iterations in between

@@ -228,18 +228,23 @@ def test_scan_layouts_and_pipelines_agree(B, variant):
     seeds = [300 + i for i in range(E)]
     base = _run_batch(B, problems, seeds, iters, variant)
     assert base[3] == 6                                           # default layout: 2 B per coordinate
-    for env, bpv in (({"NIRRT_SCAN": "f32"}, 12), ({"NIRRT_SCAN": "f64"}, 24), ({"NIRRT_GROUPS": "5"}, 6),
+    # the default run above is the persistent one-CTA-per-problem path (small trees); NIRRT_PERSIST=0 and every explicit
+    # NIRRT_SCAN select the two-kernels-per-iteration pipeline
+    for env, bpv in (({"NIRRT_SCAN": "f32"}, 12), ({"NIRRT_SCAN": "f64"}, 24), ({"NIRRT_GROUPS": "5", "NIRRT_PERSIST": "0"}, 6),
                      ({"NIRRT_SCAN": "s8"}, 4), ({"NIRRT_SCAN": "s8", "NIRRT_GROUPS": "4", "NIRRT_CHUNKS": "3"}, 4),
                      ({"NIRRT_SCAN": "s8", "NIRRT_GROUPS": "2", "NIRRT_CHUNKS": "16", "NIRRT_GRAPH": "0"}, 4),
-                     ({"NIRRT_TMA": "4"}, 6), ({"NIRRT_TMA": "4", "NIRRT_CHUNKS": "7", "NIRRT_GROUPS": "3"}, 6), ({"NIRRT_TMA": "3"}, 6),
-                     ({"NIRRT_SCAN": "u16ldg"}, 6), ({"NIRRT_SCAN": "u16ldg", "NIRRT_GROUPS": "3", "NIRRT_CHUNKS": "7"}, 6),
-                     ({"NIRRT_CHUNKS": "1"}, 6), ({"NIRRT_CHUNKS": "13", "NIRRT_GROUPS": "2"}, 6),
+                     ({"NIRRT_PERSIST": "0", "NIRRT_TMA": "4"}, 6), ({"NIRRT_PERSIST": "0", "NIRRT_TMA": "4", "NIRRT_CHUNKS": "7", "NIRRT_GROUPS": "3"}, 6),
+                     ({"NIRRT_PERSIST": "0", "NIRRT_TMA": "3"}, 6),
+                     ({"NIRRT_PERSIST": "0"}, 6), ({"NIRRT_PERSIST": "0", "NIRRT_GROUPS": "3", "NIRRT_CHUNKS": "7"}, 6),
+                     ({"NIRRT_PERSIST": "0", "NIRRT_TMA": "1"}, 6),
+                     ({"NIRRT_CHUNKS": "1", "NIRRT_PERSIST": "0"}, 6), ({"NIRRT_CHUNKS": "13", "NIRRT_GROUPS": "2", "NIRRT_PERSIST": "0"}, 6),
                      ({"NIRRT_SCAN": "u8"}, 4), ({"NIRRT_SCAN": "u8", "NIRRT_GROUPS": "4", "NIRRT_CHUNKS": "3"}, 4),
                      ({"NIRRT_SCAN": "u8", "NIRRT_GROUPS": "3", "NIRRT_PIPELINE": "1"}, 4),
-                     ({"NIRRT_GROUPS": "5", "NIRRT_GRAPH": "0"}, 6), ({"NIRRT_SCAN": "f64", "NIRRT_GROUPS": "3"}, 24),
-                     ({"NIRRT_GROUPS": "4", "NIRRT_PIPELINE": "1"}, 6), ({"NIRRT_GROUPS": "5", "NIRRT_PIPELINE": "1", "NIRRT_GRAPH": "0"}, 6),
+                     ({"NIRRT_GROUPS": "5", "NIRRT_GRAPH": "0", "NIRRT_PERSIST": "0"}, 6), ({"NIRRT_SCAN": "f64", "NIRRT_GROUPS": "3"}, 24),
+                     ({"NIRRT_GROUPS": "4", "NIRRT_PIPELINE": "1", "NIRRT_PERSIST": "0"}, 6),
+                     ({"NIRRT_GROUPS": "5", "NIRRT_PIPELINE": "1", "NIRRT_GRAPH": "0", "NIRRT_PERSIST": "0"}, 6),
                      ({"NIRRT_GROUPS": "3", "NIRRT_SCAN": "f32", "NIRRT_GRAPH": "6", "NIRRT_PIPELINE": "1"}, 12),
-                     ({"NIRRT_GROUPS": "1", "NIRRT_PDL": "0"}, 6), ({"NIRRT_CHUNKS": "3"}, 6)):
+                     ({"NIRRT_GROUPS": "1", "NIRRT_PDL": "0", "NIRRT_PERSIST": "0"}, 6), ({"NIRRT_CHUNKS": "3", "NIRRT_PERSIST": "0"}, 6)):
         v, p, n, got_bpv = _run_batch(B, problems, seeds, iters, variant, env)
         assert got_bpv == bpv, env
         assert np.array_equal(n, base[2]), env
@@ -418,7 +423,11 @@ def test_graph_is_built_by_begin_and_reused(B):
     E, iters = 64, 160
     problems = [make_problem_3d(500 + i) for i in range(E)]
     seeds = [9000 + i for i in range(E)]
-    bp = B.BatchPlanner3D(problems, 3 * iters, seeds=seeds)
+    os.environ["NIRRT_PERSIST"] = "0"          # small trees would otherwise take the persistent path (no graph at all)
+    try:
+        bp = B.BatchPlanner3D(problems, 3 * iters, seeds=seeds)
+    finally:
+        os.environ.pop("NIRRT_PERSIST", None)
     bp.begin(0, B.MODE_PLANNING, 3 * iters)
     g = bp.graph_stats()
     assert g == {"builds": 1, "replays": 0, "fallbacks": 0}
@@ -436,7 +445,9 @@ def test_graph_is_built_by_begin_and_reused(B):
     assert bp.graph_stats()["builds"] == 2
     v, p, n = bp.read_trees()
     bp.close()
-    ref = _run_batch(B, problems, seeds, 2 * iters - 3, 0, {"NIRRT_GRAPH": "0"})
+    ref = _run_batch(B, problems, seeds, 2 * iters - 3, 0, {"NIRRT_GRAPH": "0", "NIRRT_PERSIST": "0"})
+    per = _run_batch(B, problems, seeds, 2 * iters - 3, 0)        # and the persistent path gives the same trees
+    assert np.array_equal(per[2], ref[2]) and np.array_equal(per[1], ref[1]) and np.array_equal(per[0], ref[0])
     assert np.array_equal(n, ref[2])
     for e in range(E):
         assert np.array_equal(p[e, :n[e]], ref[1][e, :n[e]]) and np.array_equal(v[e, :n[e]], ref[0][e, :n[e]])
