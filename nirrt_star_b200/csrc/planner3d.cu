@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(256) k_nearest(View v) {
 //          collision + duplicate guard / vertex insert (:40-51) + Near radius (:134 / :133)
 // Called by ONE warp per env: the k_steer kernel, or warp 0 of k_expand when the two are fused.
 template <int D>
-__device__ __forceinline__ void steer_body(const View &v, int e) {
+__device__ __forceinline__ void steer_body(const View &v, int e, const typename GeomOf<D>::type *staged = nullptr) {
     typedef typename GeomOf<D>::type G;
     EnvCtl *c = v.ctl + e;
     const int lane = threadIdx.x & 31;
@@ -925,7 +925,7 @@ __device__ __forceinline__ void steer_body(const View &v, int e) {
     const int my_bi = bi;
     warp_lexmin(bs, bi);
     const int nearest = __shfl_sync(0xffffffffu, bi, 0);
-    const G &g = *GeomOf<D>::ptr(v, e);
+    const G &g = staged ? *staged : *GeomOf<D>::ptr(v, e);     // the persistent kernel keeps the obstacle table in shared memory
     if (have_rec) {      // broadcast the winning lane's record
         const int src = __ffs(__ballot_sync(0xffffffffu, my_bi == nearest)) - 1;
         nn.x = __shfl_sync(0xffffffffu, nn.x, src); nn.y = __shfl_sync(0xffffffffu, nn.y, src);
@@ -1992,8 +1992,12 @@ __device__ void goal_track(const View &v, EnvCtl *c, int e, const G &g, const Tr
     }
 }
 
+// g: the CTA's shared-memory copy of the obstacle table (g_ready: already staged by the caller); s_buf: the CTA's
+// candidate staging (kNearSmem * kNearRow bytes of shared memory); presorted >= 0: the caller's own scan left that many
+// speculative Near candidates in ascending index order at the start of s_buf (persistent kernel), -1: lists are in HBM
 template <int D>
-__device__ __forceinline__ void expand_iteration(const View &v, const int e) {
+__device__ __forceinline__ void expand_iteration(const View &v, const int e, typename GeomOf<D>::type &g, const bool g_ready,
+                                                 unsigned char *s_buf, const int presorted) {
     typedef typename GeomOf<D>::type G;
     EnvCtl *c = v.ctl + e;
 #ifdef NIRRT_PHASE_TIMING
@@ -2001,13 +2005,11 @@ __device__ __forceinline__ void expand_iteration(const View &v, const int e) {
 #endif
     if (v.fuse_steer) {
         if (!__ldcg(&c->hdr0.go)) return;
-        if (threadIdx.x < 32) steer_body<D>(v, e);
+        if (threadIdx.x < 32) steer_body<D>(v, e, g_ready ? &g : nullptr);
         __syncthreads();
     } else if (!IT.go) return;
-    __shared__ G g;
     // per-candidate staging, kNearRow bytes each: shared memory for up to kNearSmem candidates, else the problem's HBM
     // staging area (same layout, capacity near_cap) after the index sort, which always runs in shared memory
-    __shared__ __align__(16) unsigned char s_buf[kNearSmem * kNearRow];
     int stage_cap = kNearSmem;
     unsigned char *stage = s_buf;
 #define STAGE_INT(slot) (reinterpret_cast<int *>(stage) + (size_t)(slot) * stage_cap)
@@ -2040,9 +2042,10 @@ __device__ __forceinline__ void expand_iteration(const View &v, const int e) {
     const bool skipped = IT.skip;
 
     if (!skipped) {
-        stage_geom<D>(&g, v, e);
+        if (!g_ready) stage_geom<D>(&g, v, e);
         const int *cand = v.cand + (size_t)e * v.near_cap;
         int cnt;
+        bool sorted = false;
         if (IT.need_scan) {
             // Near scan by this CTA (x_new != x_rand: sparse tree or the duplicate guard) -- same filter as the
             // stand-alone k_near_m; the matches replace the (useless) speculative list of this iteration
@@ -2078,6 +2081,7 @@ __device__ __forceinline__ void expand_iteration(const View &v, const int e) {
         } else if (IT.use_spec) {
             cnt = __ldcg(&IT.spec_cnt) - IT.spec_base;
             cand = cand2_of(v, e);
+            if (presorted >= 0) { cnt = presorted; sorted = true; }     // already in s_cand, ascending
         } else cnt = __ldcg(&c->cand_cnt);
         {
             const int limit = v.big ? min(v.near_cap, kNearBig) : kNearSmem;
@@ -2086,7 +2090,10 @@ __device__ __forceinline__ void expand_iteration(const View &v, const int e) {
                 cnt = limit;
             }
         }
-        if (cnt > kNearSmem) {
+        if (sorted) {
+            if (tid == 0) s_m = 0;
+            __syncthreads();
+        } else if (cnt > kNearSmem) {
             // More candidates than the shared staging holds (dense informed tree): sort the indices in shared memory
             // (the whole staging buffer as keys), then continue with every per-candidate array in HBM.
             int p2 = 1;
@@ -2355,7 +2362,7 @@ __device__ __forceinline__ void expand_iteration(const View &v, const int e) {
 #endif
     if (v.fuse_top) {   // the next iteration's driver step + sample
         __syncthreads();
-        top_body<D>(v, e, g, !skipped, sm_s, sm_i);
+        top_body<D>(v, e, g, g_ready || !skipped, sm_s, sm_i);
     }
 #ifdef NIRRT_PHASE_TIMING
     if (tid == 0 && !skipped) {
@@ -2375,8 +2382,124 @@ __device__ __forceinline__ void expand_iteration(const View &v, const int e) {
 
 template <int D>
 __global__ void __launch_bounds__(kExpandThreads, 4) k_expand(View v) {
+    __shared__ typename GeomOf<D>::type g;
+    __shared__ __align__(16) unsigned char s_buf[kNearSmem * kNearRow];
     pdl_wait();
-    expand_iteration<D>(v, v.env0 + blockIdx.x);
+    expand_iteration<D>(v, v.env0 + blockIdx.x, g, false, s_buf, -1);
+}
+
+// The persistent kernel's own scan: the same mirror filter as nearest_m_range over the whole tree, with the warps
+// working on contiguous quarters of the vertex range so that the speculative Near members come out in ascending index
+// order without any sort -- each warp compacts its hits with a prefix over its lanes into its own shared-memory
+// segment, and the segments are concatenated in warp order at the start of s_buf (where expand_iteration keeps its
+// sorted candidate indices).  Returns their number, or -1 when they do not fit into the shared staging (the list is
+// then in the problem's HBM list, still ordered).  Nearest candidates go to the HBM candidate list as usual.
+constexpr int kSegCap = 1024;
+template <int D>
+__device__ __forceinline__ int scan_own_sorted(const View &v, int e, EnvCtl *c, const ScanHdr &h, unsigned char *s_buf) {
+    __shared__ unsigned s_min;
+    __shared__ int s_wcnt[kExpandThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) s_min = 0x7f800000u;
+    __syncthreads();
+    int *s_cand = reinterpret_cast<int *>(s_buf);
+    int *seg = s_cand + kNearSmem + warp * kSegCap;
+    const int per = ((h.n + nw - 1) / nw + 255) & ~255;
+    const int beg = warp * per, end = min(h.n, beg + per);
+    const unsigned short *X = v.ux + (size_t)e * v.stride, *Y = v.uy + (size_t)e * v.stride;
+    const unsigned short *Z = D == 3 ? v.uz + (size_t)e * v.stride : nullptr;
+    float a1 = INFINITY, a2 = INFINITY;
+    int i1 = INT_MAX, wc = 0;
+    const float thr = h.thr;
+    for (int b0 = beg; b0 < end; b0 += 256) {          // warp-uniform trip count
+        const int base = b0 + 8 * lane;
+        float a[8];
+        unsigned hit = 0;
+        if (base < end) {
+            const uint4 x = __ldcs(reinterpret_cast<const uint4 *>(X + base)), y = __ldcs(reinterpret_cast<const uint4 *>(Y + base));
+            uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            if (D == 3) z = __ldcs(reinterpret_cast<const uint4 *>(Z + base));
+            mirror_u16_vals<D>(x, y, z, h.qx, h.qy, h.qz, a);
+            if (base + 8 > end) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (base + j >= end) a[j] = INFINITY;
+            }
+            const float m = vec_min(a);
+            if (m < a2) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    a2 = fminf(a2, fmaxf(a[j], a1));
+                    if (a[j] < a1) { a1 = a[j]; i1 = base + j; }
+                }
+            }
+            if (m <= thr) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) hit |= (a[j] <= thr ? 1u : 0u) << j;
+            }
+        }
+        if (__any_sync(0xffffffffu, hit != 0u)) {
+            const int mine = __popc(hit);
+            int incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += t;
+            }
+            int pos = wc + incl - mine;
+            while (hit) {
+                const int j = __ffs(hit) - 1;
+                hit &= hit - 1;
+                if (pos < kSegCap) seg[pos] = base + j;
+                pos++;
+            }
+            wc += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(a1));
+    if (lane == 0) { atomicMin(&s_min, wmin); s_wcnt[warp] = wc; }
+    __syncthreads();
+    // ---- Nearest candidates (as nearest_m_range)
+    const float amin = __uint_as_float(s_min);
+    const float lim = __fadd_ru(__fsqrt_ru(amin), h.band);
+    const float band = __fmul_ru(__fmul_ru(lim, lim), 1.000001f);
+    if (a1 <= band) {
+        if (a2 > band) append_cand(v, c, e, i1);
+        else {
+            for (int b0 = beg; b0 < end; b0 += 256) {
+                const int base = b0 + 8 * lane;
+                if (base >= end) continue;
+                const uint4 x = __ldcs(reinterpret_cast<const uint4 *>(X + base)), y = __ldcs(reinterpret_cast<const uint4 *>(Y + base));
+                uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                if (D == 3) z = __ldcs(reinterpret_cast<const uint4 *>(Z + base));
+                float a[8];
+                mirror_u16_vals<D>(x, y, z, h.qx, h.qy, h.qz, a);
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (base + j < end && a[j] <= band) append_cand(v, c, e, base + j);
+            }
+        }
+    }
+    // ---- the speculative Near list: warp segments concatenated in warp order == ascending index order
+    int off = 0, total = 0;
+    bool overflow = false;
+    for (int w = 0; w < nw; w++) {
+        const int cw = s_wcnt[w];
+        if (w < warp) off += cw;
+        total += cw;
+        overflow = overflow || cw > kSegCap;
+    }
+    const bool fits = !overflow && total <= kNearSmem;
+    if (fits) {
+        for (int k = lane; k < wc; k += 32) s_cand[off + k] = seg[k];
+    } else if (!overflow && total <= v.near_cap) {
+        int *list = cand2_of(v, e);
+        for (int k = lane; k < wc; k += 32) list[off + k] = seg[k];
+    }
+    // the counter arithmetic steer_body / expand_iteration use (list length = spec_cnt - base); an overflow makes the
+    // length exceed near_cap, which sends the iteration to its own Near scan
+    if (tid == 0) __stcg(&IT.spec_cnt, h.base + ((overflow || total > v.near_cap) ? v.near_cap + 1 : total));
+    __threadfence_block();
+    __syncthreads();
+    return fits ? total : -1;
 }
 
 // Small trees (capacity <= kPersistCap): the whole run of `iters` iterations of a problem in ONE launch by ONE CTA --
@@ -2391,13 +2514,15 @@ template <int D>
 __global__ void __launch_bounds__(kExpandThreads, 4) k_iterate(View v, int iters) {
     const int e = v.env0 + blockIdx.x;
     EnvCtl *c = v.ctl + e;
+    __shared__ typename GeomOf<D>::type g;            // the obstacle table stays in shared memory for the whole run
+    __shared__ __align__(16) unsigned char s_buf[kNearSmem * kNearRow];
+    stage_geom<D>(&g, v, e);
+    __syncthreads();
     for (int it = 0; it < iters; it++) {
         const ScanHdr h = load_hdr(&c->hdr0);          // written by k_top / by this CTA's top_body of the previous iteration
         if (!h.go) break;                              // driver finished, waits for a guidance cloud, or budget exhausted
-        nearest_m_range<D, true, false>(v, e, c, h, 0, h.n);
-        __threadfence_block();
-        __syncthreads();
-        expand_iteration<D>(v, e);
+        const int presorted = scan_own_sorted<D>(v, e, c, h, s_buf);
+        expand_iteration<D>(v, e, g, true, s_buf, presorted);
         __threadfence_block();
         __syncthreads();
     }
