@@ -4165,6 +4165,59 @@ __device__ __forceinline__ void fps_f64_body(const double *pts, int n, int npoin
     }
 }
 
+// The same selection with the coordinates in shared memory (n <= kFpsSmemMax points: 24 B each) and only the running
+// minimum distances in registers: no register spills at 1024 threads and no global load on the critical path of a
+// selection step (the chosen point's coordinates are a shared-memory broadcast).  Identical arithmetic, identical result.
+constexpr int kFpsSmemMax = 9600, kFpsSmemPPT = 10;      // 9600 x 24 B = 230 400 B of dynamic shared memory
+// sp: where the coordinates are read from during the selection -- the shared-memory copy (kStage: filled here), or the
+// candidates themselves in L2 for the rare set larger than the staging (slower, but also without register spills)
+template <int kPPT, bool kStage, typename F>
+__device__ __forceinline__ void fps_f64_smem(const double *pts, int n, int npoint, int start, const double *sp_in, double *sp_stage, F &&visit) {
+    __shared__ double s_d[2][32];
+    __shared__ int s_i[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (kStage) {
+        for (int i = tid; i < 3 * n; i += blockDim.x) sp_stage[i] = pts[i];
+        __syncthreads();
+    }
+    const double *sp = kStage ? sp_stage : sp_in;
+    double dist[kPPT];
+#pragma unroll
+    for (int j = 0; j < kPPT; j++) dist[j] = (tid + j * kFpsThreads < n) ? XINF : -1.0;
+    int far = start;
+    for (int it = 0; it < npoint; it++) {
+        if (tid == 0) visit(it, far);
+        const double cx = sp[3 * far], cy = sp[3 * far + 1], cz = sp[3 * far + 2];
+        double bd = -2.0; int bi = INT_MAX;
+#pragma unroll
+        for (int j = 0; j < kPPT; j++) {
+            const int i = tid + j * kFpsThreads;
+            if (i < n) {
+                const double d = sq3_rows(XSUB(sp[3 * i], cx), XSUB(sp[3 * i + 1], cy), XSUB(sp[3 * i + 2], cz));
+                if (d < dist[j]) dist[j] = d;
+            }
+            if (dist[j] > bd) { bd = dist[j]; bi = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        const int slot = it & 1;
+        if (lane == 0) { s_d[slot][warp] = bd; s_i[slot][warp] = bi; }
+        __syncthreads();
+        bd = s_d[slot][lane]; bi = s_i[slot][lane];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        far = bi;
+    }
+}
+
 // down-sampling + the network's inputs: pc32 [count][n_points][3], start / goal masks [count][n_points]
 __global__ void __launch_bounds__(kFpsThreads) k_cloud_fps(View v, CloudWs w, double radius, float *pc32, float *smask, float *gmask) {
     const int k = blockIdx.x, e = w.envs[k], tid = threadIdx.x;
@@ -4172,12 +4225,15 @@ __global__ void __launch_bounds__(kFpsThreads) k_cloud_fps(View v, CloudWs w, do
     const double *cand = w.cand + (size_t)k * w.n_raw * 3;
     double *cloud = w.cloud + (size_t)k * np_ * 3;
     int m;
+    extern __shared__ double s_fps_pts[];
+    auto take = [&](int it, int idx) {
+        cloud[3 * (size_t)it] = cand[3 * (size_t)idx]; cloud[3 * (size_t)it + 1] = cand[3 * (size_t)idx + 1];
+        cloud[3 * (size_t)it + 2] = cand[3 * (size_t)idx + 2];
+    };
     if (n > np_) {
         m = np_;
-        fps_f64_body(cand, n, np_, 0, [&](int it, int idx) {
-            cloud[3 * (size_t)it] = cand[3 * (size_t)idx]; cloud[3 * (size_t)it + 1] = cand[3 * (size_t)idx + 1];
-            cloud[3 * (size_t)it + 2] = cand[3 * (size_t)idx + 2];
-        });
+        if (n <= kFpsSmemMax) fps_f64_smem<kFpsSmemPPT, true>(cand, n, np_, 0, nullptr, s_fps_pts, take);
+        else fps_f64_smem<kFpsPPT, false>(cand, n, np_, 0, cand, nullptr, take);
     } else {
         m = n;
         for (int i = tid; i < 3 * n; i += blockDim.x) cloud[i] = cand[i];
@@ -4283,7 +4339,14 @@ extern "C" int nirrt_batch_sample_clouds_sync(nirrt_batch *b, const int *envs, i
     CUDA_TRY(cudaMemcpyAsync(w.params, params, sizeof(double) * 12 * count, cudaMemcpyHostToDevice, s));
     k_cloud_draw<<<count, 256, 0, s>>>(v, w);
     if (!d_pc32) { d_pc32 = w.pc32; d_start_mask = w.smask; d_goal_mask = w.gmask; }
-    k_cloud_fps<<<count, kFpsThreads, 0, s>>>(v, w, neighbor_radius, d_pc32, d_start_mask, d_goal_mask);
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_cloud_fps, cudaFuncAttributeMaxDynamicSharedMemorySize, kFpsSmemMax * 24));
+            attr_set = true;
+        }
+    }
+    k_cloud_fps<<<count, kFpsThreads, kFpsSmemMax * 24, s>>>(v, w, neighbor_radius, d_pc32, d_start_mask, d_goal_mask);
     CHECK_LAUNCH();
     b->launches += 2;
     CUDA_TRY(cudaMemcpyAsync(counts, w.cloud_cnt, sizeof(int) * count, cudaMemcpyDeviceToHost, s));

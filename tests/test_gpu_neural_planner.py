@@ -116,3 +116,45 @@ def test_nirrt_with_the_cuda_network_end_to_end(tmp_path):
     lst = planner.planning_random(200)
     assert np.isfinite(lst[-1]) and len(planner.path_point_cloud_pred) > 0
     assert all(b <= a + 1e-9 for a, b in zip(lst[-200:], lst[-199:]))      # best cost never increases
+
+
+def test_device_cloud_sampler_matches_numpy_on_an_empty_world():
+    """generate_rectangle_point_cloud_3d / ellipsoid_point_cloud_sampling_3d on the device vs the plain numpy recipe
+    (datasets_3d/point_cloud_mask_utils_3d.py:83-113,132-200) in a world without obstacles: every raw sample survives,
+    so the farthest point down-sampling runs on more candidates than its shared-memory staging holds (the L2 path),
+    and the global numpy stream must end at the same position."""
+    from datasets_3d.point_cloud_mask_utils_3d import ellipsoid_point_cloud_sampling_3d, generate_rectangle_point_cloud_3d
+    from path_planning_utils_3d.rrt_env_3d import Env
+    env = Env({"env_dims": [50, 50, 50], "box_obstacles": [], "ball_obstacles": []})
+
+    def fps(pts, m):
+        dist = np.full(len(pts), np.inf); far = 0; sel = []
+        for _ in range(m):
+            sel.append(far)
+            dist = np.minimum(dist, ((pts - pts[far]) ** 2).sum(axis=1))
+            far = int(np.argmax(dist))
+        return pts[sel]
+
+    np.random.seed(123)
+    got = generate_rectangle_point_cloud_3d(env, 2048, over_sample_scale=5)
+    after = np.random.random()
+    np.random.seed(123)
+    raw = np.random.uniform(low=(0, 0, 0), high=(50, 50, 50), size=(10240, 3))
+    assert np.random.random() == after
+    assert np.array_equal(got, fps(raw, 2048))
+    # ellipsoid (all of it inside the world): (r, theta, phi) vectors, np.sin / np.cos, C @ L @ x + centre
+    a, b = np.array([20., 25., 25.]), np.array([30., 25., 25.])
+    np.random.seed(7)
+    got = ellipsoid_point_cloud_sampling_3d(a, b, 1.5, env, n_points=2048, n_raw_samples=10240)
+    after = np.random.random()
+    np.random.seed(7)
+    c_min = np.linalg.norm(b - a); c_max = c_min * 1.5
+    r = np.array([c_max / 2, np.sqrt(c_max ** 2 - c_min ** 2) / 2, np.sqrt(c_max ** 2 - c_min ** 2) / 2])
+    a1 = (b - a) / c_min
+    U, _, V = np.linalg.svd(np.outer(a1, [1, 0, 0]))
+    Crot = U @ np.diag([1, 1, np.linalg.det(U) * np.linalg.det(V)]) @ V.T
+    rad = np.random.uniform(0.0, 1.0, 10240); th = np.random.uniform(0, np.pi, 10240); ph = np.random.uniform(0, 2 * np.pi, 10240)
+    smp = np.array([rad * np.sin(th) * np.cos(ph), rad * np.sin(th) * np.sin(ph), rad * np.cos(th)]).T
+    pc = np.dot(np.dot(Crot, np.diag(r)), smp.T).T + (a + b) / 2.
+    assert np.random.random() == after
+    assert np.array_equal(got, fps(pc, 2048))
