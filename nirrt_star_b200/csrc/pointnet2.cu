@@ -518,7 +518,7 @@ static int gemm_attr() {
     PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PCUDA(cudaFuncSetAttribute(k_ball_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     PCUDA(cudaFuncSetAttribute(k_ball_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    PCUDA(cudaFuncSetAttribute(k_fps<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));   // 4096 points x 12 B + static
+    PCUDA(cudaFuncSetAttribute(k_fps<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));   // 4096 points x 12 B + static
     g_gemm_attr = true;
     return NIRRT_OK;
 }
@@ -828,11 +828,14 @@ static int fps_launch(nirrt_pn2 *h, int B, int l, const int *start, cudaStream_t
     const int N = h->n[l - 1], np = h->n[l];
     const size_t smem = (size_t)N * 3 * sizeof(float);
 #define FPS_ARGS h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]
-    if (N <= 64) k_fps<64, 1><<<B, 64, smem, s>>>(FPS_ARGS);
-    else if (N <= 256) k_fps<256, 1><<<B, 256, smem, s>>>(FPS_ARGS);
-    else if (N <= 1024) k_fps<512, 2><<<B, 512, smem, s>>>(FPS_ARGS);
-    else if (N <= 2048) k_fps<512, 4><<<B, 512, smem, s>>>(FPS_ARGS);
-    else k_fps<1024, 4><<<B, 1024, smem, s>>>(FPS_ARGS);
+    // Few fat threads: the selection step is issue-bound (distance update ~12 instructions per point, arg-max reduction
+    // ~30 per warp), so 16 points per thread on 4 warps issue ~1.9x fewer warp instructions per step than 4 points per
+    // thread on 16 warps, and the 16 independent points per thread hide the arithmetic latency that more warps would.
+    if (N <= 64) k_fps<32, 2><<<B, 32, smem, s>>>(FPS_ARGS);
+    else if (N <= 256) k_fps<32, 8><<<B, 32, smem, s>>>(FPS_ARGS);
+    else if (N <= 1024) k_fps<64, 16><<<B, 64, smem, s>>>(FPS_ARGS);
+    else if (N <= 2048) k_fps<128, 16><<<B, 128, smem, s>>>(FPS_ARGS);
+    else k_fps<256, 16><<<B, 256, smem, s>>>(FPS_ARGS);
 #undef FPS_ARGS
     PCUDA(cudaGetLastError());
     h->launches++;
