@@ -427,7 +427,7 @@ def bench_small(args, local, cpu=True):
 # batched PointNet++ forwards -- through nirrt_star_b200.eval.plan_batch (what eval_planning_3d.py -p nirrt_star
 # -n pointnet2 does one problem at a time, eval_planning_3d.py:101-126)
 
-def bench_nirrt(args, world, rank, local):
+def bench_nirrt(args, world, rank, local, connect="none"):
     import torch
     import torch.distributed as dist
     from nirrt_star_b200.eval import default_args, plan_batch
@@ -440,13 +440,13 @@ def bench_nirrt(args, world, rank, local):
     seeds = [base + i for i in range(E)]
     # warm-up on a slice (library load, engine + graph construction paths), untimed
     plan_batch(problems[:max(8, E // 16)], "nirrt_star", 3, default_args(3, iter_max=300, iter_after_initial=50),
-               seeds=seeds[:max(8, E // 16)], state_dict=sd, device=local)
+               seeds=seeds[:max(8, E // 16)], state_dict=sd, device=local, connect=connect)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     stats = {}
     t0 = time.perf_counter()
-    lists = plan_batch(problems, "nirrt_star", 3, a, seeds=seeds, state_dict=sd, device=local, stats_out=stats)
+    lists = plan_batch(problems, "nirrt_star", 3, a, seeds=seeds, state_dict=sd, device=local, stats_out=stats, connect=connect)
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
     iters = float(sum(len(x) for x in lists))
@@ -462,7 +462,7 @@ def bench_nirrt(args, world, rank, local):
         upd, fwd, upd_s = float(agg[3]), float(agg[4]), float(agg[5])
     return {"metric": "NIRRT* env-iters/sec, whole planner incl. batched cloud updates (random_3d)", "value": iters / el, "unit": UNIT,
             "seconds": el, "env_iterations": iters,
-            "config": {"workload": f"nirrt_star -n pointnet2 3D random_3d (BASELINE configs[3]/[4] shape): {E} problems/GPU in lock step, "
+            "config": {"workload": f"nirrt_star -n pointnet2{' -c bfs' if connect == 'bfs' else ''} 3D random_3d (BASELINE configs[3]/[4] shape): {E} problems/GPU, "
                                    f"iter_max={a.iter_max}, iter_after_initial={a.iter_after_initial}, 2048-pt clouds (10240 raw samples), "
                                    "synthetic checkpoint", "envs_per_gpu": E},
             "problems_solved": solved, "problems_total": world * E,
@@ -513,8 +513,9 @@ def main():
         return
     if args.nirrt_only:
         nr = bench_nirrt(args, world, rank, local)
+        nc = bench_nirrt(args, world, rank, local, connect="bfs")
         if rank == 0:
-            print(json.dumps(nr), flush=True)
+            print(json.dumps({"nirrt_star": nr, "nirrt_star_connect_bfs": nc}), flush=True)
         return
 
     E, nodes, K, W, ips = args.envs, args.nodes, args.steps, args.warmup, args.iters_per_step
@@ -708,8 +709,10 @@ def main():
     bp.close()
     if not args.no_pointnet2:
         pn2 = bench_pointnet2(args, world, rank, local, peaks)
+    nirrt_c = None
     if not args.no_nirrt:
         nirrt = bench_nirrt(args, world, rank, local)
+        nirrt_c = bench_nirrt(args, world, rank, local, connect="bfs")
     small = None
     if not args.no_small and rank == 0 and world == 1:
         small = bench_small(args, local, cpu=not args.no_cpu_baseline)
@@ -730,7 +733,7 @@ def main():
                "eval_variant": {"value": value_eval, "unit": UNIT, "ms_per_step": ms_eval / K, "ms_per_iteration": ms_eval / K / ips,
                                 "graph": graph_eval,
                                 "what": "planning_random loop body (adds goal-parent search + path length per iteration)"},
-               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2, "nirrt_star": nirrt, "small_trees": small}
+               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2, "nirrt_star": nirrt, "nirrt_star_connect_bfs": nirrt_c, "small_trees": small}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

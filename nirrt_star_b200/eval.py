@@ -27,7 +27,7 @@ VARIANTS = {"rrt_star": _B.VARIANT_RRT_STAR, "irrt_star": _B.VARIANT_IRRT_STAR,
 def default_args(dim, **kw):
     """The argparse defaults of eval_planning_{2d,3d}.py:10-31 that reach the planners."""
     a = dict(step_len=10, iter_max=30000, clearance=3 if dim == 2 else 2, pc_n_points=2048, pc_over_sample_scale=5,
-             pc_sample_rate=0.5, pc_update_cost_ratio=0.9, iter_after_initial=5000)
+             pc_sample_rate=0.5, pc_update_cost_ratio=0.9, iter_after_initial=5000, connect_max_trial_attempts=5)
     a.update(kw)
     return types.SimpleNamespace(**a)
 
@@ -71,13 +71,17 @@ class _CloudMaker:
 
 
 def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, classify=None, device=0, chunk=256,
-               distributed=False, return_planner=False, host_clouds=False, stats_out=None):
+               distributed=False, return_planner=False, host_clouds=False, stats_out=None, connect="none"):
     """path_len_list of every problem (global order on every rank when ``distributed``).
 
     planner: 'rrt_star' | 'irrt_star' | 'nrrt_star' | 'nirrt_star'
     state_dict: PointNet++ ``model_state_dict`` for the neural planners (the sm_100a engine is built
         from it), or pass ``classify(list_of_(pc, start_mask, goal_mask)) -> list_of_path_pred`` to
         supply predictions some other way (tests replay recorded ones).
+    connect: 'none' | 'bfs' -- Neural Connect (nirrt_star_png_c_3d.py:50-84, pointnet2_wrapper_connect_bfs.py:66-233): up to
+        args.connect_max_trial_attempts network calls per cloud update, the calls of one trial batched over all waiting
+        problems, each followed by the start->goal / goal->start searches over the predicted points' r-disc graph (CUDA)
+        and the boundary-point heuristic.  3D, device-sampled clouds.
     host_clouds: force the host (numpy) guidance-cloud generation also for 3D (the device path is the default there).
     stats_out: dict that receives {iterations, cloud_updates, forward_calls, clouds_classified, short_clouds,
         update_seconds, plan_seconds} of this rank's shard.
@@ -165,6 +169,10 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                     bp.set_cloud(int(env), it[0][np.asarray(pred).nonzero()[0]])
                 stats["forward_calls"] += 1; stats["clouds_classified"] += len(envs)
 
+            if connect not in ("none", "bfs"):
+                raise ValueError("connect must be 'none' or 'bfs'")
+            if connect == "bfs" and (dim != 3 or host_clouds):
+                raise NotImplementedError("batched Neural Connect is implemented for 3D with device-sampled clouds")
             dev = None
             if dim == 3 and not host_clouds:
                 # 3D: the whole update stays in HBM -- draws from each problem's device MT19937 stream, filters, farthest
@@ -177,6 +185,43 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                        "gm": torch.empty((E, n_pts), dtype=torch.float32, device=f"cuda:{device}"),
                        "pred": torch.empty((E, n_pts), dtype=torch.int64, device=f"cuda:{device}"),
                        "score": torch.empty((E, n_pts), dtype=torch.float32, device=f"cuda:{device}")}
+
+            def connect_round(envs, pts, counts):
+                """generate_connected_path_points for every listed problem, trial by trial"""
+                from wrapper.utils.bfs_connect_heuristic import select_heuristic_boundary_point
+                from .pointnet2 import connect_analyse
+                r = args.step_len
+                st = []
+                for k, env in enumerate(envs):
+                    pc = pts[k, :counts[k]].astype(np.float32)
+                    xs, xg = makers[env].x_start.astype(np.float32), makers[env].x_goal.astype(np.float32)
+                    st.append({"pc": pc, "xs": xs, "xg": xg, "sm": get_mask(pc, xs[np.newaxis], r), "gm": get_mask(pc, xg[np.newaxis], r),
+                               "mask": np.zeros(len(pc), dtype=np.float32), "active": True})
+                for _ in range(args.connect_max_trial_attempts):
+                    act = [k for k in range(len(envs)) if st[k]["active"]]
+                    if not act:
+                        break
+                    preds = classify([(st[k]["pc"], st[k]["sm"].astype(np.float32), st[k]["gm"].astype(np.float32)) for k in act],
+                                     [envs[k] for k in act])
+                    stats["forward_calls"] += 1; stats["clouds_classified"] += len(act)
+                    for k, pred in zip(act, preds):
+                        q = st[k]
+                        q["mask"] = ((q["mask"] + pred) > 0).astype(np.float32)
+                        has_path, _, bnd = connect_analyse(q["pc"], q["mask"], q["xs"], q["xg"], r)
+                        if has_path:
+                            q["active"] = False
+                            continue
+                        _, bpt, _ = select_heuristic_boundary_point(q["pc"], bnd, q["xs"], q["xg"])
+                        nsm = q["sm"] if bpt is None else get_mask(q["pc"], bpt, r)
+                        has_path, _, bnd = connect_analyse(q["pc"], q["mask"], q["xg"], q["xs"], r)
+                        if has_path:
+                            q["active"] = False
+                            continue
+                        _, bpt, _ = select_heuristic_boundary_point(q["pc"], bnd, q["xg"], q["xs"])
+                        ngm = q["gm"] if bpt is None else get_mask(q["pc"], bpt, r)
+                        q["sm"], q["gm"] = nsm, ngm
+                for k, env in enumerate(envs):
+                    bp.set_cloud(int(env), pts[k, :counts[k]][st[k]["mask"].nonzero()[0]])
 
             def update_device(envs, cbest, cmin):
                 n_pts, n_raw = args.pc_n_points, args.pc_n_points * args.pc_over_sample_scale
@@ -191,6 +236,9 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                                           dev["sm"].data_ptr(), dev["gm"].data_ptr())
                 tc = time.perf_counter()
                 stats["rounds"] += 1; stats["t_params"] += tb - ta; stats["t_sample"] += tc - tb
+                if connect == "bfs":
+                    connect_round(envs, bp.read_sampled_clouds(0, len(envs), n_pts), counts)
+                    return
                 if engine is None:          # caller-supplied classifier: hand it the clouds, upload what it predicts
                     pts = bp.read_sampled_clouds(0, len(envs), n_pts)
                     items = []
@@ -299,7 +347,7 @@ def run_eval(env_configs, problems, planner, dim, args=None, seeds=None, state_d
     for b in range(len(done), n, batch_size):
         e = min(n, b + batch_size)
         lists = plan_batch(problems[b:e], planner, dim, args, seeds=seeds[b:e], state_dict=state_dict, device=device,
-                           distributed=distributed)
+                           distributed=distributed, connect=connect)
         for cfg, lst in zip(env_configs[b:e], lists):
             row = copy(cfg)
             row["result"] = [float(x) for x in lst]

@@ -161,3 +161,37 @@ def test_nirrt_batch_of_64_equals_single_problem_dropin(tmp_path):
     host = plan_batch([problems[e] for e in sub], "nirrt_star", 3, args, seeds=[seeds[e] for e in sub], state_dict=sd, host_clouds=True)
     for k, e in enumerate(sub):
         assert np.array_equal(np.array(host[k]), np.array(batch[e]))
+
+
+def test_batched_neural_connect_equals_single_problem_dropin(tmp_path):
+    """-c bfs (BASELINE configs[3]): NIRRT* with Neural Connect in a lock-step batch -- the network calls of one trial
+    batched over the waiting problems, the r-disc graph searches on the GPU -- equals the single-problem drop-in
+    NIRRTStarPNGC3D + connect PNGWrapper (reference API: nirrt_star_png_c_3d.py:50-84,
+    pointnet2_wrapper_connect_bfs.py:66-233) bit for bit."""
+    import torch
+    from nirrt_star_b200 import dropin
+    from nirrt_star_b200.eval import default_args, plan_batch
+    dropin.install()
+    from path_planning_classes_3d.nirrt_star_png_c_3d import get_path_planner
+    from wrapper_3d.pointnet_pointnet2.pointnet2_wrapper_connect_bfs import PNGWrapper
+    sd = make_pointnet2_state(0)
+    d = tmp_path / "results/model_training/pointnet2_3d/checkpoints"
+    d.mkdir(parents=True)
+    torch.save({"model_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, str(d / "best_pointnet2_3d.pth"))
+    E = 12
+    problems = [make_problem_3d(350 + i) for i in range(E)]
+    seeds = [5200 + i for i in range(E)]
+    args = default_args(3, iter_max=900, iter_after_initial=150)
+    stats = {}
+    batch = plan_batch(problems, "nirrt_star", 3, args, seeds=seeds, state_dict=sd, connect="bfs", stats_out=stats)
+    assert stats["forward_calls"] >= 2              # several trials happened
+    w = PNGWrapper(root_dir=str(tmp_path), device="cuda")
+    for e in (0, 3, 5, 8, 11):
+        s = seeds[e]
+        np.random.seed(s); random.seed(s); torch.manual_seed(s)
+        want = get_path_planner(args, problems[e], w).planning_random(args.iter_after_initial)
+        got = batch[e]
+        assert len(got) == len(want), e
+        assert np.array_equal(np.isinf(got), np.isinf(want)), e
+        f = np.isfinite(want)
+        assert np.array_equal(np.array(got)[f], np.array(want)[f]), e
