@@ -89,6 +89,14 @@ int nirrt_connect_analyse_sync(const float *pc, int n, int dim, const uint8_t *p
                                const float *dst, float radius, int *has_path, uint8_t *visited_mask,
                                uint8_t *boundary_mask, void *stream);
 
+/* The same analysis for `batch` (cloud, mask, src, dst) tuples in one launch, one CTA each: pc [batch][n_max][dim] with
+ * n_pts[b] valid points, path_mask / visited_mask / boundary_mask [batch][n_max], src / dst [batch][3] (z ignored in
+ * 2D), has_path [batch].  What a lock-step batch of NIRRT*-PNG(C) planners issues per Neural Connect trial (both
+ * search directions of every waiting problem). */
+int nirrt_connect_analyse_batch_sync(const float *pc, const int *n_pts, int n_max, int dim, int batch, const uint8_t *path_mask,
+                                     const float *src, const float *dst, float radius, int *has_path,
+                                     uint8_t *visited_mask, uint8_t *boundary_mask, void *stream);
+
 /* Stand-alone tensor-core GEMM (the kernel the network uses), host buffers, synchronous:
  *   A [m][k] fp16, W [n][k] fp16, bias [n] f32; k, n multiples of 16.
  *   mode 0: out [m][n]        = fp16(relu(A W^T + bias))

@@ -108,6 +108,7 @@ def lib():
     L.nirrt_pn2_last_stage_ms.argtypes = [V, c_fp]
     L.nirrt_pn2_launch_count.restype = C.c_int64
     L.nirrt_pn2_launch_count.argtypes = [V]
+    L.nirrt_connect_analyse_batch_sync.argtypes = [c_fp, c_ip, C.c_int, C.c_int, C.c_int, c_u8p, c_fp, c_fp, C.c_float, c_ip, c_u8p, c_u8p, V]
     L.nirrt_connect_analyse_sync.argtypes = [c_fp, C.c_int, C.c_int, c_u8p, c_fp, c_fp, C.c_float, c_ip, c_u8p, c_u8p, V]
     L.nirrt_gemm_f16_sync.argtypes = [c_u16p, c_u16p, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_u16p, V]
     _LIB = L

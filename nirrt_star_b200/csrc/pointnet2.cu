@@ -1134,9 +1134,17 @@ __device__ __forceinline__ float norm_f32(float dx, float dy, float dz, int dim)
     if (dim == 3) s = __fadd_rn(s, __fmul_rn(dz, dz));
     return __fsqrt_rn(s);
 }
-__global__ void __launch_bounds__(1024) k_connect(const float *pc, int n, int dim, const uint8_t *path_mask, const float *src,
-                                                  const float *dst, float radius, int *has_path, uint8_t *visited_mask,
-                                                  uint8_t *boundary_mask) {
+// One CTA per analysis (blockIdx.x): clouds [B][n_max][dim] with n_pts[b] valid points each, masks / outputs [B][n_max],
+// src / dst [B][3].
+__global__ void __launch_bounds__(1024) k_connect(const float *pc_all, const int *n_pts, int n_max, int dim, const uint8_t *path_mask_all,
+                                                  const float *src_all, const float *dst_all, float radius, int *has_path_all,
+                                                  uint8_t *visited_all, uint8_t *boundary_all) {
+    const int b = blockIdx.x, n = n_pts[b];
+    const float *pc = pc_all + (size_t)b * n_max * dim;
+    const uint8_t *path_mask = path_mask_all + (size_t)b * n_max;
+    const float *src = src_all + 3 * b, *dst = dst_all + 3 * b;
+    int *has_path = has_path_all + b;
+    uint8_t *visited_mask = visited_all + (size_t)b * n_max, *boundary_mask = boundary_all + (size_t)b * n_max;
     extern __shared__ unsigned char s_raw[];
     float *vx = reinterpret_cast<float *>(s_raw);            // [m] vertices: 0 = src, 1 = dst, 2.. = path points
     float *vy = vx + (kConnMax + 2), *vz = vy + (kConnMax + 2);
@@ -1219,35 +1227,55 @@ __global__ void __launch_bounds__(1024) k_connect(const float *pc, int n, int di
     }
 }
 
+// Grow-only device workspace of the connect analyses (one per process; the entry points are not re-entrant)
+struct ConnWs { void *p = nullptr; size_t bytes = 0; };
+static ConnWs g_conn_ws;
+
+extern "C" int nirrt_connect_analyse_batch_sync(const float *pc, const int *n_pts, int n_max, int dim, int batch, const uint8_t *path_mask,
+                                                const float *src, const float *dst, float radius, int *has_path,
+                                                uint8_t *visited_mask, uint8_t *boundary_mask, void *stream) {
+    if (!pc || !n_pts || !path_mask || !src || !dst || !has_path || !visited_mask || !boundary_mask)
+        return pfail(NIRRT_ERR_INVALID, "nirrt_connect_analyse_batch_sync: null argument");
+    if (batch < 1 || n_max < 1 || n_max > kConnMax || (dim != 2 && dim != 3))
+        return pfail(NIRRT_ERR_INVALID, "nirrt_connect_analyse_batch_sync: batch >= 1, 1 <= n_max <= 4096, dim 2 or 3");
+    for (int b = 0; b < batch; b++)
+        if (n_pts[b] < 1 || n_pts[b] > n_max) return pfail(NIRRT_ERR_INVALID, "nirrt_connect_analyse_batch_sync: 1 <= n_pts[b] <= n_max");
+    if (nirrt_device_count() <= 0) return pfail(NIRRT_ERR_NO_DEVICE, "no sm_100 device");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = (size_t)batch, N = (size_t)n_max;
+    const size_t o_pc = 0, o_sd = o_pc + sizeof(float) * B * N * dim, o_n = o_sd + sizeof(float) * B * 6, o_hp = o_n + sizeof(int) * B,
+                 o_mask = o_hp + sizeof(int) * B, o_out = o_mask + B * N, total = o_out + 2 * B * N;
+    if (g_conn_ws.bytes < total) {
+        if (g_conn_ws.p) cudaFree(g_conn_ws.p);
+        g_conn_ws.p = nullptr; g_conn_ws.bytes = 0;
+        PCUDA(cudaMalloc(&g_conn_ws.p, total + (total >> 2)));
+        g_conn_ws.bytes = total + (total >> 2);
+    }
+    unsigned char *w = (unsigned char *)g_conn_ws.p;
+    float *d_pc = (float *)(w + o_pc), *d_sd = (float *)(w + o_sd);
+    int *d_n = (int *)(w + o_n), *d_hp = (int *)(w + o_hp);
+    uint8_t *d_mask = w + o_mask, *d_out = w + o_out;
+    PCUDA(cudaMemcpyAsync(d_pc, pc, sizeof(float) * B * N * dim, cudaMemcpyHostToDevice, s));
+    PCUDA(cudaMemcpyAsync(d_sd, src, sizeof(float) * B * 3, cudaMemcpyHostToDevice, s));
+    PCUDA(cudaMemcpyAsync(d_sd + 3 * B, dst, sizeof(float) * B * 3, cudaMemcpyHostToDevice, s));
+    PCUDA(cudaMemcpyAsync(d_n, n_pts, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    PCUDA(cudaMemcpyAsync(d_mask, path_mask, B * N, cudaMemcpyHostToDevice, s));
+    const size_t smem = (size_t)(kConnMax + 2) * (3 * sizeof(float) + 3 * sizeof(int) + 1) + 16;
+    static bool attr = false;
+    if (!attr) { PCUDA(cudaFuncSetAttribute(k_connect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_connect<<<batch, 1024, smem, s>>>(d_pc, d_n, n_max, dim, d_mask, d_sd, d_sd + 3 * B, radius, d_hp, d_out, d_out + B * N);
+    PCUDA(cudaGetLastError());
+    PCUDA(cudaMemcpyAsync(has_path, d_hp, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    PCUDA(cudaMemcpyAsync(visited_mask, d_out, B * N, cudaMemcpyDeviceToHost, s));
+    PCUDA(cudaMemcpyAsync(boundary_mask, d_out + B * N, B * N, cudaMemcpyDeviceToHost, s));
+    PCUDA(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
 extern "C" int nirrt_connect_analyse_sync(const float *pc, int n, int dim, const uint8_t *path_mask, const float *src,
                                           const float *dst, float radius, int *has_path, uint8_t *visited_mask,
                                           uint8_t *boundary_mask, void *stream) {
-    if (!pc || !path_mask || !src || !dst || !has_path || !visited_mask || !boundary_mask)
-        return pfail(NIRRT_ERR_INVALID, "nirrt_connect_analyse_sync: null argument");
-    if (n < 1 || n > kConnMax || (dim != 2 && dim != 3)) return pfail(NIRRT_ERR_INVALID, "nirrt_connect_analyse_sync: 1 <= n <= 4096, dim 2 or 3");
-    if (nirrt_device_count() <= 0) return pfail(NIRRT_ERR_NO_DEVICE, "no sm_100 device");
-    cudaStream_t s = (cudaStream_t)stream;
-    float *d_pc = nullptr, *d_sd = nullptr;
-    uint8_t *d_mask = nullptr, *d_out = nullptr;
-    int *d_hp = nullptr;
-    auto cleanup = [&]() { cudaFree(d_pc); cudaFree(d_sd); cudaFree(d_mask); cudaFree(d_out); cudaFree(d_hp); };
-#define CT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return pfail(NIRRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
-    CT(cudaMalloc(&d_pc, sizeof(float) * (size_t)n * dim)); CT(cudaMalloc(&d_sd, sizeof(float) * 6));
-    CT(cudaMalloc(&d_mask, (size_t)n)); CT(cudaMalloc(&d_out, 2 * (size_t)n)); CT(cudaMalloc(&d_hp, sizeof(int)));
-    CT(cudaMemcpyAsync(d_pc, pc, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice, s));
-    CT(cudaMemcpyAsync(d_sd, src, sizeof(float) * dim, cudaMemcpyHostToDevice, s));
-    CT(cudaMemcpyAsync(d_sd + 3, dst, sizeof(float) * dim, cudaMemcpyHostToDevice, s));
-    CT(cudaMemcpyAsync(d_mask, path_mask, (size_t)n, cudaMemcpyHostToDevice, s));
-    const size_t smem = (size_t)(kConnMax + 2) * (3 * sizeof(float) + 3 * sizeof(int) + 1) + 16;
-    static bool attr = false;
-    if (!attr) { CT(cudaFuncSetAttribute(k_connect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k_connect<<<1, 1024, smem, s>>>(d_pc, n, dim, d_mask, d_sd, d_sd + 3, radius, d_hp, d_out, d_out + n);
-    CT(cudaGetLastError());
-    CT(cudaMemcpyAsync(has_path, d_hp, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CT(cudaMemcpyAsync(visited_mask, d_out, (size_t)n, cudaMemcpyDeviceToHost, s));
-    CT(cudaMemcpyAsync(boundary_mask, d_out + n, (size_t)n, cudaMemcpyDeviceToHost, s));
-    CT(cudaStreamSynchronize(s));
-#undef CT
-    cleanup();
-    return NIRRT_OK;
+    if (!src || !dst) return pfail(NIRRT_ERR_INVALID, "nirrt_connect_analyse_sync: null argument");
+    float s3[3] = {src[0], src[1], dim == 3 ? src[2] : 0.f}, d3[3] = {dst[0], dst[1], dim == 3 ? dst[2] : 0.f};
+    return nirrt_connect_analyse_batch_sync(pc, &n, n, dim, 1, path_mask, s3, d3, radius, has_path, visited_mask, boundary_mask, stream);
 }

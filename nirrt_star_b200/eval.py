@@ -189,7 +189,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
             def connect_round(envs, pts, counts):
                 """generate_connected_path_points for every listed problem, trial by trial"""
                 from wrapper.utils.bfs_connect_heuristic import select_heuristic_boundary_point
-                from .pointnet2 import connect_analyse
+                from .pointnet2 import connect_analyse_batch
                 r = args.step_len
                 st = []
                 for k, env in enumerate(envs):
@@ -205,19 +205,21 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                                      [envs[k] for k in act])
                     stats["forward_calls"] += 1; stats["clouds_classified"] += len(act)
                     for k, pred in zip(act, preds):
+                        st[k]["mask"] = ((st[k]["mask"] + pred) > 0).astype(np.float32)
+                    # both search directions of every active problem in ONE launch (a path start -> goal exists iff one
+                    # goal -> start does, so the second search never depends on the first)
+                    hp, _, bnd = connect_analyse_batch([st[k]["pc"] for k in act] * 2, [st[k]["mask"] for k in act] * 2,
+                                                       [st[k]["xs"] for k in act] + [st[k]["xg"] for k in act],
+                                                       [st[k]["xg"] for k in act] + [st[k]["xs"] for k in act], r)
+                    A = len(act)
+                    for j, k in enumerate(act):
                         q = st[k]
-                        q["mask"] = ((q["mask"] + pred) > 0).astype(np.float32)
-                        has_path, _, bnd = connect_analyse(q["pc"], q["mask"], q["xs"], q["xg"], r)
-                        if has_path:
+                        if hp[j] or hp[A + j]:
                             q["active"] = False
                             continue
-                        _, bpt, _ = select_heuristic_boundary_point(q["pc"], bnd, q["xs"], q["xg"])
+                        _, bpt, _ = select_heuristic_boundary_point(q["pc"], bnd[j], q["xs"], q["xg"])
                         nsm = q["sm"] if bpt is None else get_mask(q["pc"], bpt, r)
-                        has_path, _, bnd = connect_analyse(q["pc"], q["mask"], q["xg"], q["xs"], r)
-                        if has_path:
-                            q["active"] = False
-                            continue
-                        _, bpt, _ = select_heuristic_boundary_point(q["pc"], bnd, q["xg"], q["xs"])
+                        _, bpt, _ = select_heuristic_boundary_point(q["pc"], bnd[A + j], q["xg"], q["xs"])
                         ngm = q["gm"] if bpt is None else get_mask(q["pc"], bpt, r)
                         q["sm"], q["gm"] = nsm, ngm
                 for k, env in enumerate(envs):

@@ -164,6 +164,27 @@ def gemm_f16(A, W, bias, mode=0, group=16, stream=None):
     return out
 
 
+def connect_analyse_batch(pcs, path_masks, srcs, dsts, radius, stream=None):
+    """connect_analyse for a list of (cloud, mask, src, dst) tuples in ONE launch (one CTA each).
+    Returns (has_path bool[B], [visited_mask f32[n_b]], [boundary_mask f32[n_b]])."""
+    _lib.require_device()
+    L = _lib.lib()
+    B = len(pcs)
+    dim = np.asarray(pcs[0]).shape[1]
+    n_pts = np.array([len(p) for p in pcs], dtype=np.int32)
+    n_max = int(n_pts.max())
+    pc = np.zeros((B, n_max, dim), dtype=np.float32); pm = np.zeros((B, n_max), dtype=np.uint8)
+    s3 = np.zeros((B, 3), dtype=np.float32); d3 = np.zeros((B, 3), dtype=np.float32)
+    for b in range(B):
+        pc[b, :n_pts[b]] = pcs[b]; pm[b, :n_pts[b]] = np.asarray(path_masks[b]) != 0
+        s3[b, :dim] = srcs[b]; d3[b, :dim] = dsts[b]
+    hp = np.zeros(B, dtype=np.int32); vis = np.zeros((B, n_max), dtype=np.uint8); bnd = np.zeros((B, n_max), dtype=np.uint8)
+    check(L.nirrt_connect_analyse_batch_sync(fp(pc), n_pts.ctypes.data_as(_lib.c_ip), n_max, dim, B, _lib.u8p(pm), fp(s3), fp(d3),
+                                             C.c_float(float(radius)), hp.ctypes.data_as(_lib.c_ip), _lib.u8p(vis), _lib.u8p(bnd),
+                                             C.c_void_p(stream) if stream else None))
+    return hp.astype(bool), [vis[b, :n_pts[b]].astype(np.float32) for b in range(B)], [bnd[b, :n_pts[b]].astype(np.float32) for b in range(B)]
+
+
 def connect_analyse(pc, path_mask, src, dst, radius, stream=None):
     """(has_path, visited_mask f32 [n], boundary_mask f32 [n]) of the r-disc graph over
     [src, dst, pc[path_mask]] -- bfs_point_cloud + get_boundary_mask of the reference's Neural Connect
