@@ -109,13 +109,20 @@ int nirrt_batch_set_guidance(nirrt_batch *b, double pc_sample_rate, double pc_up
 /* path_point_cloud_pred of one problem (nirrt_star_png_3d.py:172): points [n][3] f64 host */
 int nirrt_batch_set_cloud(nirrt_batch *b, int env, const double *points, int n, void *stream);
 
+/* 2D worlds: the free-space image of every problem (binary_mask of datasets/planning_problem_utils_2d.py: 1 = free),
+ * masks [E][height][width] u8 host; needed by nirrt_batch_sample_clouds_sync on a 2D batch
+ * (datasets/point_cloud_mask_utils.py:52-66: a point is free iff the four pixels around it are). */
+int nirrt_batch_set_free_masks(nirrt_batch *b, const uint8_t *masks, int height, int width, void *stream);
+
 /* ---- guidance clouds on the device (3D; datasets_3d/point_cloud_mask_utils_3d.py:83-113,132-200 + the mask
  * helper datasets/point_cloud_mask_utils.py:20-31), for a list of `count` problems in one call:
  *   envs[count]    problem indices;  kind[count]  0 = generate_rectangle_point_cloud_3d, 1 = ellipsoid_point_cloud_sampling_3d
  *   params[count][12]  kind 1: M = C @ L (row major 3x3) and the ellipsoid centre, evaluated by the caller with numpy as
  *                      the reference does (c_max ** 2 is libm pow); ignored for kind 0
  *   n_points, n_raw    pc_n_points and pc_n_points * pc_over_sample_scale (nirrt_star_png_3d.py:141-156)
- * Each problem's numpy MT19937 stream is consumed on the device exactly as the reference consumes it (3 * n_raw
+ * 2D batches (datasets/point_cloud_mask_utils.py:35-73,104-174): kind 0 = generate_rectangle_point_cloud, kind 1 =
+ * ellipsoid_point_cloud_sampling (params: M = C @ L and the centre padded to 3), pc32 is [count][n_points][2].
+ * Each problem's numpy MT19937 stream is consumed on the device exactly as the reference consumes it (dim * n_raw
  * doubles), candidates are filtered at clearance 0 and farthest-point down-sampled (open3d semantics) when more than
  * n_points survive.  Outputs, written to DEVICE buffers the caller owns (they are the PointNet++ engine's inputs):
  * pc32 [count][n_points][3] f32, start / goal masks [count][n_points] f32 (|p - x_start| < neighbor_radius, strict);

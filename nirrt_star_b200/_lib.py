@@ -82,6 +82,7 @@ def lib():
     L.nirrt_costs_sync.argtypes = [V, C.c_int, c_i64p, C.c_int64, c_dp, V]
     L.nirrt_batch_read_cbest_sync.argtypes = [V, c_dp, c_dp, V]
     L.nirrt_fps_f64_sync.argtypes = [c_dp, C.c_int64, C.c_int, C.c_int, c_i64p, V]
+    L.nirrt_batch_set_free_masks.argtypes = [V, c_u8p, C.c_int, C.c_int, V]
     L.nirrt_batch_sample_clouds_sync.argtypes = [V, c_ip, C.c_int, c_ip, c_dp, C.c_int, C.c_int, C.c_double, V, V, V, c_ip, V]
     L.nirrt_batch_read_sampled_clouds_sync.argtypes = [V, C.c_int, C.c_int, c_dp, V]
     L.nirrt_batch_commit_clouds.argtypes = [V, V, c_ip, C.c_int, V]

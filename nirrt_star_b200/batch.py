@@ -68,6 +68,22 @@ def ellipsoid_params_3d(x_start, x_goal, max_min_ratio):
     return np.concatenate([np.dot(Crot, np.diag(r)).reshape(9), centre])
 
 
+def ellipsoid_params_2d(x_start, x_goal, max_min_ratio):
+    """The host-side scalars of the 2D ellipsoid_point_cloud_sampling (datasets/point_cloud_mask_utils.py:104-133):
+    math.hypot, the SVD rotation, c_max ** 2 (libm pow), math.sqrt -> M = C @ L (row major 3x3) and the centre (z = 0)."""
+    x_start = np.asarray(x_start, dtype=np.float64); x_goal = np.asarray(x_goal, dtype=np.float64)
+    dx, dy = x_goal - x_start
+    c_min = math.hypot(dx, dy)
+    a1 = np.concatenate([(x_goal - x_start) / c_min, np.array([0.])], axis=0)[:, np.newaxis]
+    U, _, V_T = np.linalg.svd(a1 @ np.array([[1.0], [0.0], [0.0]]).T, True, True)
+    Crot = U @ np.diag([1.0, 1.0, np.linalg.det(U) * np.linalg.det(V_T.T)]) @ V_T
+    centre = np.concatenate([(x_start + x_goal) / 2., np.array([0.])], axis=0)
+    c_max = c_min * max_min_ratio
+    eps = 1e-6 if c_max ** 2 - c_min ** 2 < 0 else 0
+    r = [c_max / 2.0, math.sqrt(c_max ** 2 - c_min ** 2 + eps) / 2.0, math.sqrt(c_max ** 2 - c_min ** 2 + eps) / 2.0]
+    return np.concatenate([np.dot(Crot, np.diag(r)).reshape(9), centre])
+
+
 def seed_state(seed):
     """(key[624] uint32, pos) of ``np.random.seed(seed)``."""
     st = np.random.RandomState(seed).get_state()
@@ -210,10 +226,16 @@ class BatchPlanner3D:
                                                     C.c_void_p(d_goal_mask) if d_goal_mask else None, ip(counts), self.stream))
         return counts
 
+    def set_free_masks(self, masks):
+        """2D: binary_mask of every problem (1 = free), all of one shape: needed by sample_clouds on a 2D batch."""
+        m = np.ascontiguousarray(np.stack([np.asarray(x) != 0 for x in masks]), dtype=np.uint8)
+        assert m.shape[0] == self.E and m.ndim == 3
+        check(self.L.nirrt_batch_set_free_masks(self.h, u8p(m), m.shape[1], m.shape[2], self.stream))
+
     def read_sampled_clouds(self, first, count, n_points):
         out = np.zeros((count, n_points, 3))
         check(self.L.nirrt_batch_read_sampled_clouds_sync(self.h, int(first), int(count), dp(out), self.stream))
-        return out
+        return out if self.dim == 3 else np.ascontiguousarray(out[:, :, :2])
 
     def commit_clouds(self, d_pred, sel=None):
         """path_point_cloud_pred = cloud[pred != 0] for the clouds of the last sample_clouds call (all, or positions `sel`)."""

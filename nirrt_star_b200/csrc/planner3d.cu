@@ -188,6 +188,8 @@ struct View {
     int gc_stride;   // row length of gc_d / gc_cost: max(cap, sol_cap) -- the informed family keeps its candidates in `sol`
     struct Kid *kid; // [E][stride]   child lists + goal-candidate slot of every vertex (RRT* eval driver), see goal_track
     double *records; // [E][rec_cap]
+    const unsigned char *occ;   // 2D guidance clouds: free-space masks [E][occ_h][occ_w], 1 = free (binary_mask), null until set
+    int occ_h, occ_w;
     double *pc;      // [E][pc_cap][3]
     double *pathseg; // [E][path_cap]
     const double *near_table;
@@ -3559,6 +3561,7 @@ constexpr size_t kMaxGraphs = 8;
 // graphs were built) only matter to the RRT* eval driver
 static void graph_key(const View &v, View *k) {
     memcpy(k, &v, sizeof(View));     // byte copies throughout: the lookup is a memcmp
+    k->occ = nullptr; k->occ_h = 0; k->occ_w = 0;     // the 2D free-space masks are only read by the guidance-cloud kernels
     if (!(v.mode == NIRRT_MODE_PLANNING_RANDOM || fam_informed(v.variant))) { k->gc_idx = nullptr; k->gc_d = nullptr; k->gc_cost = nullptr; k->kid = nullptr; k->gc_stride = 0; }
 }
 static nirrt_batch::GraphEntry *ensure_graph(nirrt_batch *b, bool pipelined) {
@@ -4026,11 +4029,16 @@ struct CloudWs {
     int n_raw, n_points;
 };
 
+// 2D (datasets/point_cloud_mask_utils.py:35-73,104-174): kind 0 draws np.random.uniform([0, 0], [W, H], (n_raw, 2)); kind 1
+// np.random.uniform(-1, 1, (n_raw, 2)), keeps the unit disc (np.linalg.norm(axis=1) <= 1), maps it with np.dot(C @ L, .) +
+// centre.  A point is free iff the four pixels around it (astype(int) truncation, clipped to the image) are free in the
+// problem's binary_mask; kind 1 additionally requires 0 <= x <= W, 0 <= y <= H (points_in_range, inclusive).
+template <int D>
 __global__ void __launch_bounds__(256) k_cloud_draw(View v, CloudWs w) {
     const int k = blockIdx.x, e = w.envs[k], tid = threadIdx.x;
     MtState *st = v.mt + e;
     uint32_t *wb = w.words + (size_t)k * 6 * w.n_raw;
-    const int total = 6 * w.n_raw;
+    const int total = 2 * D * w.n_raw;
     __shared__ int s_pos, s_cur, s_has;
     if (tid == 0) { s_pos = st->pos; s_cur = st->cur; s_has = st->has_next; }
     __syncthreads();
@@ -4064,8 +4072,9 @@ __global__ void __launch_bounds__(256) k_cloud_draw(View v, CloudWs w) {
     }
     if (tid == 0) { st->pos = s_pos; st->cur = s_cur; st->has_next = 0; }
     // ---- candidates, validity, ordered compaction
-    __shared__ Geom3 g;
-    stage_geom<3>(&g, v, e);
+    typedef typename GeomOf<D>::type G;
+    __shared__ G g;
+    stage_geom<D>(&g, v, e);
     __syncthreads();
     if (tid == 0) g.clearance = 0.0;                 // the samplers are called with clearance = 0
     __shared__ int s_wcnt[8];
@@ -4074,16 +4083,40 @@ __global__ void __launch_bounds__(256) k_cloud_draw(View v, CloudWs w) {
     __syncthreads();
     const int kind = w.kind[k];
     const double *P = w.params + (size_t)k * 12;
-    double lo[3], sc[3];
-    for (int d = 0; d < 3; d++) { lo[d] = XADD(g.range[2 * d], 0.0); sc[d] = XSUB(XSUB(g.range[2 * d + 1], 0.0), lo[d]); }
+    double lo[3] = {0.0, 0.0, 0.0}, sc[3] = {0.0, 0.0, 0.0};
+    for (int d = 0; d < D; d++) { lo[d] = XADD(g.range[2 * d], 0.0); sc[d] = XSUB(XSUB(g.range[2 * d + 1], 0.0), lo[d]); }
     double *cand = w.cand + (size_t)k * w.n_raw * 3;
     const int n_raw = w.n_raw;
+    const unsigned char *occ = D == 2 ? v.occ + (size_t)e * v.occ_h * v.occ_w : nullptr;
+    auto free_pixels = [&](const double *p) {        // np.prod(binary_mask[4 neighbours]) != 0
+        const int px = (int)p[0], py = (int)p[1];    // astype(int): truncation toward zero
+        bool ok = true;
+        for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++) {
+                const int x = min(max(px + a, 0), v.occ_w - 1), y = min(max(py + b, 0), v.occ_h - 1);
+                ok = ok && occ[(size_t)y * v.occ_w + x] != 0;
+            }
+        return ok;
+    };
     for (int base = 0; base < n_raw; base += blockDim.x) {
         const int i = base + tid;
         bool keep = false;
         double p[3] = {0.0, 0.0, 0.0};
         if (i < n_raw) {
-            if (kind == 0) {
+            if (D == 2) {
+                const double u0 = mt_double(wb[4 * i], wb[4 * i + 1]), u1 = mt_double(wb[4 * i + 2], wb[4 * i + 3]);
+                if (kind == 0) {
+                    p[0] = XADD(lo[0], XMUL(sc[0], u0)); p[1] = XADD(lo[1], XMUL(sc[1], u1));
+                    keep = free_pixels(p);
+                } else {
+                    const double x = XADD(-1.0, XMUL(2.0, u0)), y = XADD(-1.0, XMUL(2.0, u1));
+                    if (XSQRT(XADD(XMUL(x, x), XMUL(y, y))) <= 1.0) {
+                        for (int d = 0; d < 2; d++) p[d] = XADD(XFMA(P[3 * d + 1], y, XMUL(P[3 * d], x)), P[9 + d]);
+                        keep = free_pixels(p) && XSUB(g.range[0], 0.0) <= p[0] && p[0] <= XADD(XADD(g.range[0], XSUB(g.range[1], g.range[0])), 0.0) &&
+                               XSUB(g.range[2], 0.0) <= p[1] && p[1] <= XADD(XADD(g.range[2], XSUB(g.range[3], g.range[2])), 0.0);
+                    }
+                }
+            } else if (kind == 0) {
                 for (int d = 0; d < 3; d++) {
                     const int q = 2 * (3 * i + d);
                     p[d] = XADD(lo[d], XMUL(sc[d], mt_double(wb[q], wb[q + 1])));
@@ -4098,7 +4131,7 @@ __global__ void __launch_bounds__(256) k_cloud_draw(View v, CloudWs w) {
                 const double x = XMUL(rs, cp), y = XMUL(rs, sp), z = XMUL(r, ct);
                 for (int d = 0; d < 3; d++)
                     p[d] = XADD(XFMA(P[3 * d + 2], z, XFMA(P[3 * d + 1], y, XMUL(P[3 * d], x))), P[9 + d]);
-                keep = point_valid(g, p);
+                keep = point_valid(g, p);      // (2D never gets here: point_valid(Geom2) would also test the obstacles)
             }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -4219,6 +4252,7 @@ __device__ __forceinline__ void fps_f64_smem(const double *pts, int n, int npoin
 }
 
 // down-sampling + the network's inputs: pc32 [count][n_points][3], start / goal masks [count][n_points]
+template <int D>
 __global__ void __launch_bounds__(kFpsThreads) k_cloud_fps(View v, CloudWs w, double radius, float *pc32, float *smask, float *gmask) {
     const int k = blockIdx.x, e = w.envs[k], tid = threadIdx.x;
     const int n = w.cand_cnt[k], np_ = w.n_points;
@@ -4246,12 +4280,14 @@ __global__ void __launch_bounds__(kFpsThreads) k_cloud_fps(View v, CloudWs w, do
         const size_t o = (size_t)k * np_ + i;
         if (i < m) {
             const double x = cloud[3 * (size_t)i], y = cloud[3 * (size_t)i + 1], z = cloud[3 * (size_t)i + 2];
-            pc32[3 * o] = (float)x; pc32[3 * o + 1] = (float)y; pc32[3 * o + 2] = (float)z;
+            pc32[D * o] = (float)x; pc32[D * o + 1] = (float)y;
+            if (D == 3) pc32[D * o + 2] = (float)z;
             // np.linalg.norm(pc[:, None] - p, axis=2) < radius  (strict)
-            smask[o] = rownorm3(XSUB(x, c->start[0]), XSUB(y, c->start[1]), XSUB(z, c->start[2])) < radius ? 1.f : 0.f;
-            gmask[o] = rownorm3(XSUB(x, c->goal[0]), XSUB(y, c->goal[1]), XSUB(z, c->goal[2])) < radius ? 1.f : 0.f;
+            smask[o] = row_norm<D>(XSUB(x, c->start[0]), XSUB(y, c->start[1]), XSUB(z, c->start[2])) < radius ? 1.f : 0.f;
+            gmask[o] = row_norm<D>(XSUB(x, c->goal[0]), XSUB(y, c->goal[1]), XSUB(z, c->goal[2])) < radius ? 1.f : 0.f;
         } else {
-            pc32[3 * o] = pc32[3 * o + 1] = pc32[3 * o + 2] = 0.f; smask[o] = gmask[o] = 0.f;
+            for (int d = 0; d < D; d++) pc32[D * o + d] = 0.f;
+            smask[o] = gmask[o] = 0.f;
         }
     }
 }
@@ -4317,6 +4353,23 @@ static int ensure_cloud_ws(nirrt_batch *b, int n_points, int n_raw) {
     return NIRRT_OK;
 }
 
+extern "C" int nirrt_batch_set_free_masks(nirrt_batch *b, const uint8_t *masks, int height, int width, void *stream) {
+    if (!b || !masks || height < 1 || width < 1) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_free_masks: bad argument");
+    View &v = b->v;
+    if (v.dim != 2) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_free_masks: 2D batches only");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (v.occ && (v.occ_h != height || v.occ_w != width)) return fail(NIRRT_ERR_INVALID, "nirrt_batch_set_free_masks: mask size changed");
+    if (!v.occ) {
+        void *p = nullptr;
+        TRY(dalloc(b, &p, (size_t)v.E * height * width));
+        v.occ = (const unsigned char *)p; v.occ_h = height; v.occ_w = width;
+    }
+    CUDA_TRY(cudaMemcpyAsync(const_cast<unsigned char *>(v.occ), masks, (size_t)v.E * height * width, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
 extern "C" int nirrt_batch_sample_clouds_sync(nirrt_batch *b, const int *envs, int count, const int *kind, const double *params,
                                               int n_points, int n_raw, double neighbor_radius, float *d_pc32, float *d_start_mask,
                                               float *d_goal_mask, int *counts, void *stream) {
@@ -4324,7 +4377,7 @@ extern "C" int nirrt_batch_sample_clouds_sync(nirrt_batch *b, const int *envs, i
     if ((d_pc32 == nullptr) != (d_start_mask == nullptr) || (d_pc32 == nullptr) != (d_goal_mask == nullptr))
         return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: pass all three device buffers or none");
     View &v = b->v;
-    if (v.dim != 3) return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: 3D batches only");
+    if (v.dim == 2 && !v.occ) return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: 2D batches need nirrt_batch_set_free_masks first");
     if (count < 1 || count > v.E) return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: bad problem count");
     if (n_points < 1 || n_points > v.pc_cap || n_raw < n_points || n_raw > kFpsThreads * kFpsPPT)
         return fail(NIRRT_ERR_INVALID, "nirrt_batch_sample_clouds_sync: need 1 <= n_points <= 4096 and n_points <= n_raw <= 16384");
@@ -4337,16 +4390,19 @@ extern "C" int nirrt_batch_sample_clouds_sync(nirrt_batch *b, const int *envs, i
     CUDA_TRY(cudaMemcpyAsync(w.envs, envs, sizeof(int) * count, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(w.kind, kind, sizeof(int) * count, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(w.params, params, sizeof(double) * 12 * count, cudaMemcpyHostToDevice, s));
-    k_cloud_draw<<<count, 256, 0, s>>>(v, w);
+    if (v.dim == 3) k_cloud_draw<3><<<count, 256, 0, s>>>(v, w);
+    else k_cloud_draw<2><<<count, 256, 0, s>>>(v, w);
     if (!d_pc32) { d_pc32 = w.pc32; d_start_mask = w.smask; d_goal_mask = w.gmask; }
     {
         static bool attr_set = false;
         if (!attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_cloud_fps, cudaFuncAttributeMaxDynamicSharedMemorySize, kFpsSmemMax * 24));
+            CUDA_TRY(cudaFuncSetAttribute(k_cloud_fps<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFpsSmemMax * 24));
+            CUDA_TRY(cudaFuncSetAttribute(k_cloud_fps<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFpsSmemMax * 24));
             attr_set = true;
         }
     }
-    k_cloud_fps<<<count, kFpsThreads, kFpsSmemMax * 24, s>>>(v, w, neighbor_radius, d_pc32, d_start_mask, d_goal_mask);
+    if (v.dim == 3) k_cloud_fps<3><<<count, kFpsThreads, kFpsSmemMax * 24, s>>>(v, w, neighbor_radius, d_pc32, d_start_mask, d_goal_mask);
+    else k_cloud_fps<2><<<count, kFpsThreads, kFpsSmemMax * 24, s>>>(v, w, neighbor_radius, d_pc32, d_start_mask, d_goal_mask);
     CHECK_LAUNCH();
     b->launches += 2;
     CUDA_TRY(cudaMemcpyAsync(counts, w.cloud_cnt, sizeof(int) * count, cudaMemcpyDeviceToHost, s));

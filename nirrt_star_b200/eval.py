@@ -81,8 +81,8 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
     connect: 'none' | 'bfs' -- Neural Connect (nirrt_star_png_c_3d.py:50-84, pointnet2_wrapper_connect_bfs.py:66-233): up to
         args.connect_max_trial_attempts network calls per cloud update, the calls of one trial batched over all waiting
         problems, each followed by the start->goal / goal->start searches over the predicted points' r-disc graph (CUDA)
-        and the boundary-point heuristic.  3D, device-sampled clouds.
-    host_clouds: force the host (numpy) guidance-cloud generation also for 3D (the device path is the default there).
+        and the boundary-point heuristic.  Needs device-sampled clouds.
+    host_clouds: run the per-problem drop-in samplers one cloud at a time instead of the batched device update.
     stats_out: dict that receives {iterations, cloud_updates, forward_calls, clouds_classified, short_clouds,
         update_seconds, plan_seconds} of this rank's shard.
     """
@@ -171,16 +171,18 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
 
             if connect not in ("none", "bfs"):
                 raise ValueError("connect must be 'none' or 'bfs'")
-            if connect == "bfs" and (dim != 3 or host_clouds):
-                raise NotImplementedError("batched Neural Connect is implemented for 3D with device-sampled clouds")
+            if connect == "bfs" and host_clouds:
+                raise NotImplementedError("batched Neural Connect needs device-sampled clouds")
             dev = None
-            if dim == 3 and not host_clouds:
-                # 3D: the whole update stays in HBM -- draws from each problem's device MT19937 stream, filters, farthest
+            if not host_clouds:
+                # the whole update stays in HBM -- draws from each problem's device MT19937 stream, filters, farthest
                 # point down-sampling, masks, ONE PointNet++ forward for every waiting problem, and the predicted points go
                 # straight into the planner's guidance-cloud buffer.  (With a caller-supplied classify= the clouds are read
                 # back for it; sampling still runs on the device.)
                 n_pts = args.pc_n_points
-                dev = {"pc": torch.empty((E, n_pts, 3), dtype=torch.float32, device=f"cuda:{device}"),
+                if dim == 2:
+                    bp.set_free_masks([p["binary_mask"] for p in local])
+                dev = {"pc": torch.empty((E, n_pts, dim), dtype=torch.float32, device=f"cuda:{device}"),
                        "sm": torch.empty((E, n_pts), dtype=torch.float32, device=f"cuda:{device}"),
                        "gm": torch.empty((E, n_pts), dtype=torch.float32, device=f"cuda:{device}"),
                        "pred": torch.empty((E, n_pts), dtype=torch.int64, device=f"cuda:{device}"),
@@ -232,7 +234,8 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                 params = np.zeros((len(envs), 12))
                 for k, env in enumerate(envs):
                     if kinds[k]:
-                        params[k] = _B.ellipsoid_params_3d(makers[env].x_start, makers[env].x_goal, cbest[env] / cmin[env])
+                        params[k] = (_B.ellipsoid_params_3d if dim == 3 else _B.ellipsoid_params_2d)(
+                            makers[env].x_start, makers[env].x_goal, cbest[env] / cmin[env])
                 tb = time.perf_counter()
                 counts = bp.sample_clouds(envs, kinds, params, n_pts, n_raw, args.step_len, dev["pc"].data_ptr(),
                                           dev["sm"].data_ptr(), dev["gm"].data_ptr())
@@ -257,7 +260,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                 fs = np.stack([[int(torch.randint(0, n, (1,), generator=gens[env], dtype=torch.long)) for n in (int(counts[k]),) + NPOINTS]
                                for k, env in enumerate(envs)]).astype(np.int32)
                 d_fs = torch.from_numpy(fs).to(dev["pc"].device)
-                engine.classify_device(len(envs), 3, dev["pc"].data_ptr(), dev["sm"].data_ptr(), dev["gm"].data_ptr(),
+                engine.classify_device(len(envs), dim, dev["pc"].data_ptr(), dev["sm"].data_ptr(), dev["gm"].data_ptr(),
                                        d_fs.data_ptr(), dev["pred"].data_ptr(), dev["score"].data_ptr())
                 full = [k for k in range(len(envs)) if counts[k] == n_pts]
                 bp.commit_clouds(dev["pred"].data_ptr(), None if len(full) == len(envs) else full)

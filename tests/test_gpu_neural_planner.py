@@ -158,3 +158,60 @@ def test_device_cloud_sampler_matches_numpy_on_an_empty_world():
     pc = np.dot(np.dot(Crot, np.diag(r)), smp.T).T + (a + b) / 2.
     assert np.random.random() == after
     assert np.array_equal(got, fps(pc, 2048))
+
+
+def test_device_cloud_sampler_2d_matches_numpy_recipe():
+    """generate_rectangle_point_cloud / ellipsoid_point_cloud_sampling on the device vs the plain numpy recipe
+    (datasets/point_cloud_mask_utils.py:35-73,104-174) on an image with blocked rectangles: uniform draws, the 4-pixel
+    free-space product, the unit-disc rejection, (C @ L) @ x + centre through a 3x3 dgemm, the range test, farthest point
+    down-sampling, and the position of the global numpy stream afterwards."""
+    import math
+    from datasets.point_cloud_mask_utils import ellipsoid_point_cloud_sampling, generate_rectangle_point_cloud
+    H, W = 160, 224
+    mask = np.ones((H, W))
+    mask[30:70, 50:90] = 0; mask[100:150, 120:200] = 0; mask[0:12, 180:224] = 0
+
+    def free(pc):
+        pix = pc.astype(int)
+        nei = (pix + np.array([[0, 0], [0, 1], [1, 0], [1, 1]])[:, np.newaxis]).reshape(-1, 2)
+        nei[:, 1] = np.clip(nei[:, 1], 0, H - 1); nei[:, 0] = np.clip(nei[:, 0], 0, W - 1)
+        return np.prod(mask[nei[:, 1], nei[:, 0]].reshape(4, -1), axis=0).nonzero()[0]
+
+    def fps(pts, m):
+        dist = np.full(len(pts), np.inf); far = 0; sel = []
+        for _ in range(m):
+            sel.append(far)
+            dist = np.minimum(dist, ((pts - pts[far]) ** 2).sum(axis=1))
+            far = int(np.argmax(dist))
+        return pts[sel]
+
+    np.random.seed(11)
+    got = generate_rectangle_point_cloud(mask, 2048, over_sample_scale=5)
+    after = np.random.random()
+    np.random.seed(11)
+    raw = np.random.uniform(low=[0, 0], high=[W, H], size=(10240, 2))
+    assert np.random.random() == after
+    raw = raw[free(raw)]
+    assert len(raw) > 2048 and np.array_equal(got, fps(raw, 2048))
+
+    for seed, a, b, ratio, n_pts in ((5, [40., 90.], [180., 60.], 1.25, 2048), (6, [10., 10.], [200., 150.], 1.02, 2048),
+                                     (7, [100., 80.], [110., 85.], 1.5, 2048), (8, [20., 20.], [215., 20.], 1.8, 512)):
+        a, b = np.array(a), np.array(b)
+        np.random.seed(seed)
+        got = ellipsoid_point_cloud_sampling(a, b, ratio, mask, n_points=n_pts, n_raw_samples=10240)
+        after = np.random.random()
+        np.random.seed(seed)
+        c_min = math.hypot(*(b - a)); c_max = c_min * ratio
+        a1 = np.concatenate([(b - a) / c_min, [0.]])[:, np.newaxis]
+        U, _, V_T = np.linalg.svd(a1 @ np.array([[1.0, 0.0, 0.0]]), True, True)
+        C = U @ np.diag([1.0, 1.0, np.linalg.det(U) * np.linalg.det(V_T.T)]) @ V_T
+        r = [c_max / 2.0, math.sqrt(c_max ** 2 - c_min ** 2) / 2.0, math.sqrt(c_max ** 2 - c_min ** 2) / 2.0]
+        smp = np.random.uniform(-1, 1, size=(10240, 2))
+        assert np.random.random() == after
+        smp = smp[np.linalg.norm(smp, axis=1) <= 1]
+        smp = np.concatenate([smp, np.zeros((len(smp), 1))], axis=1)
+        pc = (np.dot(np.dot(C, np.diag(r)), smp.T).T + np.concatenate([(a + b) / 2., [0.]]))[:, :2]
+        pc = pc[free(pc)]
+        pc = pc[(pc[:, 0] >= 0) & (pc[:, 0] <= W) & (pc[:, 1] >= 0) & (pc[:, 1] <= H)]
+        want = fps(pc, n_pts) if len(pc) > n_pts else pc
+        assert np.array_equal(got, want), seed
