@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--pn2-steps", type=int, default=20, help="PointNet++ leg: timed forwards")
     ap.add_argument("--no-pointnet2", action="store_true")
     ap.add_argument("--nirrt-envs", type=int, default=512, help="NIRRT* leg: planning problems per GPU (BASELINE configs[3]/[4] shape)")
+    ap.add_argument("--nirrt-envs-2d", type=int, default=256, help="2D NIRRT* leg: planning problems per GPU (BASELINE configs[2])")
     ap.add_argument("--nirrt-iter-max", type=int, default=10000)
     ap.add_argument("--nirrt-iter-after", type=int, default=5000)
     ap.add_argument("--no-nirrt", action="store_true")
@@ -427,26 +428,26 @@ def bench_small(args, local, cpu=True):
 # batched PointNet++ forwards -- through nirrt_star_b200.eval.plan_batch (what eval_planning_3d.py -p nirrt_star
 # -n pointnet2 does one problem at a time, eval_planning_3d.py:101-126)
 
-def bench_nirrt(args, world, rank, local, connect="none"):
+def bench_nirrt(args, world, rank, local, connect="none", dim=3):
     import torch
     import torch.distributed as dist
     from nirrt_star_b200.eval import default_args, plan_batch
-    from nirrt_star_b200.synthetic import make_pointnet2_state, make_problem_3d
-    E = args.nirrt_envs
+    from nirrt_star_b200.synthetic import make_pointnet2_state, make_problem_2d, make_problem_3d
+    E = args.nirrt_envs if dim == 3 else args.nirrt_envs_2d
     sd = make_pointnet2_state(0)
-    a = default_args(3, iter_max=args.nirrt_iter_max, iter_after_initial=args.nirrt_iter_after)
+    a = default_args(dim, iter_max=args.nirrt_iter_max, iter_after_initial=args.nirrt_iter_after)
     base = 100000 + rank * E
-    problems = [make_problem_3d(base + i) for i in range(E)]
+    problems = [(make_problem_3d if dim == 3 else make_problem_2d)(base + i) for i in range(E)]
     seeds = [base + i for i in range(E)]
     # warm-up on a slice (library load, engine + graph construction paths), untimed
-    plan_batch(problems[:max(8, E // 16)], "nirrt_star", 3, default_args(3, iter_max=300, iter_after_initial=50),
+    plan_batch(problems[:max(8, E // 16)], "nirrt_star", dim, default_args(dim, iter_max=300, iter_after_initial=50),
                seeds=seeds[:max(8, E // 16)], state_dict=sd, device=local, connect=connect)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     stats = {}
     t0 = time.perf_counter()
-    lists = plan_batch(problems, "nirrt_star", 3, a, seeds=seeds, state_dict=sd, device=local, stats_out=stats, connect=connect)
+    lists = plan_batch(problems, "nirrt_star", dim, a, seeds=seeds, state_dict=sd, device=local, stats_out=stats, connect=connect)
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
     iters = float(sum(len(x) for x in lists))
@@ -460,15 +461,16 @@ def bench_nirrt(args, world, rank, local, connect="none"):
         upd, fwd, upd_s = float(sm[3]), float(sm[4]), float(mx[5])
     else:
         upd, fwd, upd_s = float(agg[3]), float(agg[4]), float(agg[5])
-    return {"metric": "NIRRT* env-iters/sec, whole planner incl. batched cloud updates (random_3d)", "value": iters / el, "unit": UNIT,
+    return {"metric": f"NIRRT* env-iters/sec, whole planner incl. batched cloud updates (random_{dim}d)", "value": iters / el, "unit": UNIT,
             "seconds": el, "env_iterations": iters,
-            "config": {"workload": f"nirrt_star -n pointnet2{' -c bfs' if connect == 'bfs' else ''} 3D random_3d (BASELINE configs[3]/[4] shape): {E} problems/GPU, "
+            "config": {"workload": f"nirrt_star -n pointnet2{' -c bfs' if connect == 'bfs' else ''} {dim}D random_{dim}d (BASELINE {'configs[3]/[4]' if dim == 3 else 'configs[2]'} shape): {E} problems/GPU, "
                                    f"iter_max={a.iter_max}, iter_after_initial={a.iter_after_initial}, 2048-pt clouds (10240 raw samples), "
                                    "synthetic checkpoint", "envs_per_gpu": E},
             "problems_solved": solved, "problems_total": world * E,
             "cloud_updates": upd, "pointnet2_forward_calls": fwd, "clouds_per_forward": upd / max(1.0, fwd),
             "cloud_update_seconds": upd_s, "cloud_update_share_of_time": upd_s / el, "work_rank0": stats.get("work"),
             "update_breakdown_rank0": {k: stats.get(k) for k in ("rounds", "t_params", "t_sample", "t_forward", "t_short", "short_clouds")},
+            "time_breakdown_rank0": {k: stats.get(k) for k in ("create_seconds", "setup_seconds", "plan_seconds", "loop_seconds", "run_seconds", "update_seconds", "close_seconds")},
             "what": "wall clock of plan_batch (max over ranks): device-side cloud sampling (MT19937 draws, filters, FPS) + masks + "
                     "ONE PointNet++ forward per lock-step round + commit, interleaved with the lock-step planner iterations"}
 
@@ -514,8 +516,9 @@ def main():
     if args.nirrt_only:
         nr = bench_nirrt(args, world, rank, local)
         nc = bench_nirrt(args, world, rank, local, connect="bfs")
+        n2 = bench_nirrt(args, world, rank, local, dim=2)
         if rank == 0:
-            print(json.dumps({"nirrt_star": nr, "nirrt_star_connect_bfs": nc}), flush=True)
+            print(json.dumps({"nirrt_star": nr, "nirrt_star_connect_bfs": nc, "nirrt_star_2d": n2}), flush=True)
         return
 
     E, nodes, K, W, ips = args.envs, args.nodes, args.steps, args.warmup, args.iters_per_step
@@ -709,10 +712,11 @@ def main():
     bp.close()
     if not args.no_pointnet2:
         pn2 = bench_pointnet2(args, world, rank, local, peaks)
-    nirrt_c = None
+    nirrt_c = nirrt_2d = None
     if not args.no_nirrt:
         nirrt = bench_nirrt(args, world, rank, local)
         nirrt_c = bench_nirrt(args, world, rank, local, connect="bfs")
+        nirrt_2d = bench_nirrt(args, world, rank, local, dim=2)
     small = None
     if not args.no_small and rank == 0 and world == 1:
         small = bench_small(args, local, cpu=not args.no_cpu_baseline)
@@ -733,7 +737,7 @@ def main():
                "eval_variant": {"value": value_eval, "unit": UNIT, "ms_per_step": ms_eval / K, "ms_per_iteration": ms_eval / K / ips,
                                 "graph": graph_eval,
                                 "what": "planning_random loop body (adds goal-parent search + path length per iteration)"},
-               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2, "nirrt_star": nirrt, "nirrt_star_connect_bfs": nirrt_c, "small_trees": small}
+               "problems_with_solution": solved, "problems_total": world * E, "pointnet2": pn2, "nirrt_star": nirrt, "nirrt_star_connect_bfs": nirrt_c, "nirrt_star_2d": nirrt_2d, "small_trees": small}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

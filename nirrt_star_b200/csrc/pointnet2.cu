@@ -85,54 +85,100 @@ __global__ void __launch_bounds__(256) k_prep(const float *pc, int dim, const fl
 // k_fps: farthest_point_sample (pointnet2_utils.py:65-86).  One CTA per cloud, the cloud's running
 // min-distance lives in registers (PPT points per thread), one barrier per selected point.
 // dist = (dx*dx + dy*dy) + dz*dz in fp32 without contraction; argmax ties -> lowest index.
+// A selection step is one dependent chain (centroid -> distances -> arg-max -> next centroid), so what counts is its
+// length, not the instruction count: the per-thread maximum is an order-free max over the PPT values (the compiler
+// builds a tree), the arg-max is a max-reduction on the bit patterns (distances are >= 0) followed by a min-reduction
+// on the index, both REDUX, and every thread combines the per-warp results itself after the one barrier.
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2: two IEEE round-to-nearest operations per instruction, the same results as two
+// scalar instructions at half the fma-pipe slots).  ptxas contracts a packed multiply feeding a packed add into FFMA2 even
+// for .rn operands and with --fmad=false (it even folds fma(a, b, -0) back into a multiply first), so wherever the reference
+// rounds the product the sum is formed with SCALAR adds on the unpacked halves: the SASS of those kernels must show
+// FMUL2 / FADD2 / FADD and no FFMA2 (checked by tests/test_build_sass.py).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 template <int T, int PPT>
 __global__ void __launch_bounds__(T) k_fps(const float *xyz, int N, int npoint, const int *start, int level,
-                                           int *fidx, float *new_xyz) {
+                                           int *fidx, float *new_xyz, int it0, int it1, float *carry_dist, int *carry_far) {
     extern __shared__ float s_xyz[];          // [N][3]
     constexpr int NW = T / 32;
-    __shared__ unsigned s_d[2][NW];
-    __shared__ int s_i[2][NW];
+    __shared__ __align__(16) unsigned s_d[2][NW];
+    __shared__ __align__(16) int s_i[2][NW];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *X = xyz + (size_t)b * N * 3;
     for (int i = tid; i < N * 3; i += T) s_xyz[i] = X[i];
     __syncthreads();
-    float px[PPT], py[PPT], pz[PPT], dist[PPT];
+    static_assert(PPT % 2 == 0, "points are processed in packed pairs");
+    f32x2 px[PPT / 2], py[PPT / 2], pz[PPT / 2];
+    float dist[PPT];
+    // [it0, it1) of the npoint selections: a later chunk picks the running distances up where the previous launch left
+    // them (the level-1 selections are issued in chunks so that grouping and the first MLPs start on the early centroids)
+    float *cd = carry_dist + (size_t)b * N;
 #pragma unroll
-    for (int j = 0; j < PPT; j++) {
-        const int i = tid + j * T;
-        const bool in = i < N;
-        px[j] = in ? s_xyz[i * 3] : 0.f; py[j] = in ? s_xyz[i * 3 + 1] : 0.f; pz[j] = in ? s_xyz[i * 3 + 2] : 0.f;
-        dist[j] = in ? 1e10f : 0.f;
+    for (int j = 0; j < PPT; j += 2) {
+        float c[2][3];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = tid + (j + k) * T;
+            const bool in = i < N;
+            c[k][0] = in ? s_xyz[i * 3] : 0.f; c[k][1] = in ? s_xyz[i * 3 + 1] : 0.f; c[k][2] = in ? s_xyz[i * 3 + 2] : 0.f;
+            dist[j + k] = in ? (it0 > 0 ? cd[i] : 1e10f) : 0.f;
+        }
+        px[j / 2] = pack2(c[0][0], c[1][0]); py[j / 2] = pack2(c[0][1], c[1][1]); pz[j / 2] = pack2(c[0][2], c[1][2]);
     }
-    int far = start[b * 4 + level];
-    for (int it = 0; it < npoint; it++) {
+    int far = it0 > 0 ? carry_far[b] : start[b * 4 + level];
+    for (int it = it0; it < it1; it++) {
         const float cx = s_xyz[far * 3], cy = s_xyz[far * 3 + 1], cz = s_xyz[far * 3 + 2];
         if (tid == 0) {
             fidx[(size_t)b * npoint + it] = far;
             float *o = new_xyz + ((size_t)b * npoint + it) * 3;
             o[0] = cx; o[1] = cy; o[2] = cz;
         }
-        // distances are >= 0, so their bit patterns order like unsigned integers: the arg-max with
-        // lowest-index ties is a max-reduction on the bits followed by a min-reduction on the index
-        unsigned bd = 0; int bi = 0x7fffffff;
+        unsigned u[PPT], m = 0u;
+        const f32x2 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz);
 #pragma unroll
-        for (int j = 0; j < PPT; j++) {
-            const int i = tid + j * T;
-            const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(py[j], cy), dz = __fsub_rn(pz[j], cz);
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (d < dist[j]) dist[j] = d;
-            const unsigned u = __float_as_uint(dist[j]);
-            if (i < N && (u > bd || bi == 0x7fffffff)) { bd = u; bi = i; }
+        for (int j = 0; j < PPT; j += 2) {
+            const f32x2 dx = sub2(px[j / 2], cx2), dy = sub2(py[j / 2], cy2), dz = sub2(pz[j / 2], cz2);
+            float x0, x1, y0, y1, z0, z1;
+            unpack2(mul2(dx, dx), x0, x1); unpack2(mul2(dy, dy), y0, y1); unpack2(mul2(dz, dz), z0, z1);
+            const float d0 = __fadd_rn(__fadd_rn(x0, y0), z0), d1 = __fadd_rn(__fadd_rn(x1, y1), z1);
+            dist[j] = fminf(dist[j], d0); dist[j + 1] = fminf(dist[j + 1], d1);      // no NaNs: the same as `if (d < dist)`
+            u[j] = __float_as_uint(dist[j]); u[j + 1] = __float_as_uint(dist[j + 1]);          // out-of-range slots hold 0
+            m = max(m, max(u[j], u[j + 1]));
         }
-        unsigned wm = __reduce_max_sync(0xffffffffu, bd);
-        int wi = __reduce_min_sync(0xffffffffu, (bd == wm) ? bi : 0x7fffffff);
+        const unsigned wm = __reduce_max_sync(0xffffffffu, m);
+        // lowest index of this thread at the warp's maximum (slot j <-> index tid + j*T, ascending; an out-of-range slot
+        // can only match when every distance is 0, and then only after all of the thread's in-range slots)
+        unsigned eq = 0u;
+#pragma unroll
+        for (int j = 0; j < PPT; j++) eq |= (u[j] == wm ? 1u : 0u) << j;
+        int bi = eq ? tid + (__ffs(eq) - 1) * T : 0x7fffffff;
+        if (bi >= N) bi = 0x7fffffff;
+        const int wi = __reduce_min_sync(0xffffffffu, bi);
+        if (NW == 1) { far = wi; continue; }
         const int slot = it & 1;
         if (lane == 0) { s_d[slot][warp] = wm; s_i[slot][warp] = wi; }
         __syncthreads();
-        bd = lane < NW ? s_d[slot][lane] : 0u;
-        bi = lane < NW ? s_i[slot][lane] : 0x7fffffff;
-        wm = __reduce_max_sync(0xffffffffu, bd);
-        far = __reduce_min_sync(0xffffffffu, (bd == wm && lane < NW) ? bi : 0x7fffffff);
+        unsigned gm = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; w++) gm = max(gm, s_d[slot][w]);
+        int gi = 0x7fffffff;
+#pragma unroll
+        for (int w = 0; w < NW; w++) gi = min(gi, s_d[slot][w] == gm ? s_i[slot][w] : 0x7fffffff);
+        far = gi;
+    }
+    if (it1 < npoint) {
+#pragma unroll
+        for (int j = 0; j < PPT; j++) {
+            const int i = tid + j * T;
+            if (i < N) cd[i] = dist[j];
+        }
+        if (tid == 0) carry_far[b] = far;
     }
 }
 
@@ -144,7 +190,7 @@ __global__ void __launch_bounds__(T) k_fps(const float *xyz, int N, int npoint, 
 // small batches: one WARP per centroid (32 points per step, ballot + prefix popcount) -- more parallelism
 // when there are few clouds; large batches use the one-thread-per-centroid kernel below
 __global__ void __launch_bounds__(256) k_ball_query_warp(const float *xyz, int N, const float *new_xyz, int S,
-                                                    float r0sq, int K0, float r1sq, int K1, int *g0, int *g1) {
+                                                    float r0sq, int K0, float r1sq, int K1, int *g0, int *g1, int s0, int s1) {
     extern __shared__ float s_pts[];          // x[N] y[N] z[N] sq[N]
     float *sx = s_pts, *sy = sx + N, *sz = sy + N, *sq = sz + N;
     const int b = blockIdx.y;
@@ -156,8 +202,8 @@ __global__ void __launch_bounds__(256) k_ball_query_warp(const float *xyz, int N
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (s >= S) return;
+    const int s = s0 + blockIdx.x * 8 + (threadIdx.x >> 5);      // centroids [s0, s1) of every cloud
+    if (s >= s1) return;
     const float *c = new_xyz + ((size_t)b * S + s) * 3;
     const float cx = c[0], cy = c[1], cz = c[2];
     const float cs = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
@@ -186,33 +232,51 @@ __global__ void __launch_bounds__(256) k_ball_query_warp(const float *xyz, int N
 }
 
 __global__ void __launch_bounds__(256) k_ball_query(const float *xyz, int N, const float *new_xyz, int S,
-                                                    float r0sq, int K0, float r1sq, int K1, int *g0, int *g1) {
-    extern __shared__ float4 s_p4[];          // [N] (x, y, z, x*x + y*y + z*z): one broadcast LDS.128 per point
+                                                    float r0sq, int K0, float r1sq, int K1, int *g0, int *g1, int s0, int s1) {
+    // points in pairs for the packed fp32 pipe: s_pp[2k] = (x_2k, x_2k+1, y_2k, y_2k+1), s_pp[2k + 1] = (z_2k, z_2k+1, |p|^2_2k,
+    // |p|^2_2k+1): two broadcast LDS.128 per two points; an odd cloud is padded with a point far outside every ball
+    extern __shared__ float4 s_pp[];
     const int b = blockIdx.y;
     const float *X = xyz + (size_t)b * N * 3;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const float x = X[i * 3], y = X[i * 3 + 1], z = X[i * 3 + 2];
-        s_p4[i] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    for (int k = threadIdx.x; 2 * k < N; k += blockDim.x) {
+        float c[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int i = 2 * k + u;
+            const bool in = i < N;
+            const float x = in ? X[i * 3] : 1e10f, y = in ? X[i * 3 + 1] : 1e10f, z = in ? X[i * 3 + 2] : 1e10f;
+            c[u][0] = x; c[u][1] = y; c[u][2] = z;
+            c[u][3] = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+        }
+        s_pp[2 * k] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
+        s_pp[2 * k + 1] = make_float4(c[0][2], c[1][2], c[0][3], c[1][3]);
     }
     __syncthreads();
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
+    const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;      // centroids [s0, s1) of every cloud
+    if (s >= s1) return;
     const float *c = new_xyz + ((size_t)b * S + s) * 3;
     const float cx = c[0], cy = c[1], cz = c[2];
     const float cs = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
     int *o0 = g0 + ((size_t)b * S + s) * K0, *o1 = g1 + ((size_t)b * S + s) * K1;
     int cnt0 = 0, cnt1 = 0, f0 = 0, f1 = 0;
-    // the thread walks the cloud in index order and keeps the first K members of each ball
-    for (int i = 0; i < N; i++) {
-        const float4 p = s_p4[i];
-        const float dot = __fmaf_rn(cz, p.z, __fmaf_rn(cy, p.y, __fmul_rn(cx, p.x)));
-        float d = __fmul_rn(-2.f, dot);
-        d = __fadd_rn(d, cs);
-        d = __fadd_rn(d, p.w);
-        if (!(d > r1sq)) {                       // r0 < r1: members of the small ball are members of the large one
-            if (cnt1 < K1) { if (cnt1 == 0) f1 = i; o1[cnt1++] = i; }
-            if (!(d > r0sq) && cnt0 < K0) { if (cnt0 == 0) f0 = i; o0[cnt0++] = i; }
-            if (cnt1 >= K1 && cnt0 >= K0) break;
+    // the thread walks the cloud in index order, two points per step (FMUL2 / FFMA2 / FADD2: the reference's
+    // -2 * (a . b) + |a|^2 + |b|^2 with the same roundings), and keeps the first K members of each ball
+    const f32x2 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz), cs2 = pack2(cs, cs), m2 = pack2(-2.f, -2.f);
+    bool full = false;
+    for (int i = 0; i < N && !full; i += 2) {
+        const float4 pa = s_pp[i], pb = s_pp[i + 1];
+        const f32x2 dot = fma2(cz2, pack2(pb.x, pb.y), fma2(cy2, pack2(pa.z, pa.w), mul2(cx2, pack2(pa.x, pa.y))));
+        float d[2];
+        unpack2(add2(add2(mul2(m2, dot), cs2), pack2(pb.z, pb.w)), d[0], d[1]);      // -2 * dot is exact: a contraction changes nothing
+        if (!(d[0] > r1sq) || !(d[1] > r1sq)) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!(d[u] > r1sq) && i + u < N && !full) {     // r0 < r1: members of the small ball are members of the large one
+                    if (cnt1 < K1) { if (cnt1 == 0) f1 = i + u; o1[cnt1++] = i + u; }
+                    if (!(d[u] > r0sq) && cnt0 < K0) { if (cnt0 == 0) f0 = i + u; o0[cnt0++] = i + u; }
+                    full = cnt1 >= K1 && cnt0 >= K0;
+                }
+            }
         }
     }
     // pad with the first member (group_first); an empty ball cannot occur: the centroid is a member
@@ -375,13 +439,22 @@ __global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const 
     // three nearest in ascending (distance, index) order -- the first three entries of the
     // reference's sort; phase 2: the warp's 32 results are broadcast one at a time and all lanes
     // interpolate / copy the channels of that point.
-    extern __shared__ float4 s_q4[];          // [S] (x, y, z, |q|^2)
+    // coarse points in pairs (S is even at every level): s_qq[2k] = (x_2k, x_2k+1, y_2k, y_2k+1), s_qq[2k + 1] = (z.., |q|^2..)
+    extern __shared__ float4 s_qq[];
     const int b = blockIdx.y;
     const float *Q = xyz2 + (size_t)b * S * 3;
     if (MODE != 2) {
-        for (int i = threadIdx.x; i < S; i += blockDim.x) {
-            const float x = Q[i * 3], y = Q[i * 3 + 1], z = Q[i * 3 + 2];
-            s_q4[i] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        for (int k = threadIdx.x; 2 * k < S; k += blockDim.x) {
+            float c[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = 2 * k + u;
+                const float x = Q[i * 3], y = Q[i * 3 + 1], z = Q[i * 3 + 2];
+                c[u][0] = x; c[u][1] = y; c[u][2] = z;
+                c[u][3] = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+            }
+            s_qq[2 * k] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
+            s_qq[2 * k + 1] = make_float4(c[0][2], c[1][2], c[0][3], c[1][3]);
         }
         __syncthreads();
     }
@@ -401,13 +474,16 @@ __global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const 
         const float *a = xyz1 + ((size_t)b * N + pi) * 3;
         const float ax = a[0], ay = a[1], az = a[2];
         const float as = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
-        for (int s = 0; s < S; s++) {
-            const float4 q = s_q4[s];
-            const float dot = __fmaf_rn(az, q.z, __fmaf_rn(ay, q.y, __fmul_rn(ax, q.x)));
-            float d = __fmul_rn(-2.f, dot);
-            d = __fadd_rn(d, as);
-            d = __fadd_rn(d, q.w);
-            top3_insert(t, d, s);             // strict <: equal distances keep the lower index first
+        const f32x2 ax2 = pack2(ax, ax), ay2 = pack2(ay, ay), az2 = pack2(az, az), as2 = pack2(as, as), m2 = pack2(-2.f, -2.f);
+        for (int s = 0; s < S; s += 2) {      // two coarse points per step on the packed fp32 pipe, the reference's roundings
+            const float4 qa = s_qq[s], qb = s_qq[s + 1];
+            const f32x2 dot = fma2(az2, pack2(qb.x, qb.y), fma2(ay2, pack2(qa.z, qa.w), mul2(ax2, pack2(qa.x, qa.y))));
+            float d0, d1;
+            unpack2(add2(add2(mul2(m2, dot), as2), pack2(qb.z, qb.w)), d0, d1);      // -2 * dot is exact
+            if (fminf(d0, d1) < t.d[2]) {     // rare once the three running values have settled
+                top3_insert(t, d0, s);        // strict <: equal distances keep the lower index first
+                top3_insert(t, d1, s + 1);
+            }
         }
     }
     const float r0 = __fdiv_rn(1.f, __fadd_rn(t.d[0], 1e-8f)), r1 = __fdiv_rn(1.f, __fadd_rn(t.d[1], 1e-8f)),
@@ -592,6 +668,8 @@ struct nirrt_pn2 {
     float *in6 = nullptr;
     __half *feat[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int *fidx[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *fps_dist = nullptr;      // [maxB][N0cap] running distances carried between the chunks of a level's selection
+    int *fps_far = nullptr;         // [maxB]
     int *grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     __half *bufA = nullptr, *bufB = nullptr;
     uint8_t *sa_img[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // fused sa1 / sa2 kernels: swizzled weight
@@ -610,7 +688,9 @@ struct nirrt_pn2 {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // geometry stream: everything that needs coordinates only (FPS, ball query, 3-NN of the feature
     // propagation levels) runs beside the feature stream's MLPs; events hand each level over
-    cudaStream_t gs = nullptr;
+    cudaStream_t gs = nullptr, gs2 = nullptr;      // FPS chain | ball queries + 3-NN searches
+    cudaEvent_t ev_fc[8] = {}, ev_bc[8] = {}, ev_fl[4] = {};      // level-1 FPS chunk / ball-query chunk done; FPS of a level done
+    int l1_chunks = 1;
     cudaEvent_t ev_fork = nullptr, ev_bq[4] = {nullptr, nullptr, nullptr, nullptr}, ev_knn[4] = {nullptr, nullptr, nullptr, nullptr};
     int4 *knn_i[4] = {nullptr, nullptr, nullptr, nullptr};      // per FP level: the three nearest coarse points of every fine point
     float4 *knn_w[4] = {nullptr, nullptr, nullptr, nullptr};    // and their normalised inverse-distance weights
@@ -668,6 +748,9 @@ extern "C" int nirrt_pn2_destroy(nirrt_pn2 *h) {
     for (void *p : h->allocs) cudaFree(p);
     for (int i = 0; i < 2; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->gs) cudaStreamDestroy(h->gs);
+    if (h->gs2) cudaStreamDestroy(h->gs2);
+    for (int i = 0; i < 8; i++) { if (h->ev_fc[i]) cudaEventDestroy(h->ev_fc[i]); if (h->ev_bc[i]) cudaEventDestroy(h->ev_bc[i]); }
+    for (int i = 0; i < 4; i++) if (h->ev_fl[i]) cudaEventDestroy(h->ev_fl[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int i = 0; i < 4; i++) { if (h->ev_bq[i]) cudaEventDestroy(h->ev_bq[i]); if (h->ev_knn[i]) cudaEventDestroy(h->ev_knn[i]); }
     delete h;
@@ -746,6 +829,8 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
     const size_t B = (size_t)max_batch;
     for (int l = 0; l <= 4; l++) TRYC(palloc(h, &h->xyz[l], B * h->n[l] * 3));
     TRYC(palloc(h, &h->in6, B * h->N0 * 6));
+    TRYC(palloc(h, &h->fps_dist, B * h->N0));
+    TRYC(palloc(h, &h->fps_far, B));
     for (int l = 1; l <= 4; l++) {
         TRYC(palloc(h, &h->feat[l], B * h->n[l] * kC[l]));
         TRYC(palloc(h, &h->fidx[l - 1], B * h->n[l]));
@@ -763,6 +848,11 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
         const char *st = getenv("NIRRT_PN2_STREAMS");
         h->two_streams = !(st && atoi(st) == 1);
         if (cudaStreamCreateWithFlags(&h->gs, cudaStreamNonBlocking) != cudaSuccess) FAILC("nirrt_pn2_create: cudaStreamCreate failed");
+        if (cudaStreamCreateWithFlags(&h->gs2, cudaStreamNonBlocking) != cudaSuccess) FAILC("nirrt_pn2_create: cudaStreamCreate failed");
+        for (int i = 0; i < 8; i++) { cudaEventCreateWithFlags(&h->ev_fc[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_bc[i], cudaEventDisableTiming); }
+        for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&h->ev_fl[i], cudaEventDisableTiming);
+        const char *ch = getenv("NIRRT_PN2_CHUNKS");
+        if (ch) { const int c = atoi(ch); h->l1_chunks = (c == 1 || c == 2 || c == 4 || c == 8) ? c : 1; }
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
         for (int i = 0; i < 4; i++) { cudaEventCreateWithFlags(&h->ev_bq[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_knn[i], cudaEventDisableTiming); }
     }
@@ -824,34 +914,69 @@ struct StageTimer {
     }
 };
 
-static int fps_launch(nirrt_pn2 *h, int B, int l, const int *start, cudaStream_t s) {
+// development aid (NIRRT_PN2_TRACE=1): completion time of every launch of a forward on its stream, printed to stderr
+static const bool g_trace = getenv("NIRRT_PN2_TRACE") && atoi(getenv("NIRRT_PN2_TRACE")) > 0;
+static std::vector<std::pair<std::string, cudaEvent_t>> g_trace_ev;
+static void trace_mark(const char *name, int a, int b, cudaStream_t s) {
+    if (!g_trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    char buf[64];
+    snprintf(buf, sizeof buf, "%s[%d,%d]", name, a, b);
+    g_trace_ev.emplace_back(buf, e);
+}
+static void trace_dump() {
+    if (!g_trace || g_trace_ev.empty()) return;
+    cudaDeviceSynchronize();
+    for (size_t i = 1; i < g_trace_ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_trace_ev[0].second, g_trace_ev[i].second);
+        fprintf(stderr, "pn2-trace %-16s %8.1f us\n", g_trace_ev[i].first.c_str(), ms * 1e3f);
+    }
+    for (auto &p : g_trace_ev) cudaEventDestroy(p.second);
+    g_trace_ev.clear();
+}
+
+// selections [it0, it1) of level l (it1 < 0: all of them)
+static int fps_launch(nirrt_pn2 *h, int B, int l, const int *start, cudaStream_t s, int it0 = 0, int it1 = -1) {
     const int N = h->n[l - 1], np = h->n[l];
+    if (it1 < 0) it1 = np;
     const size_t smem = (size_t)N * 3 * sizeof(float);
-#define FPS_ARGS h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]
-    // Few fat threads: the selection step is issue-bound (distance update ~12 instructions per point, arg-max reduction
-    // ~30 per warp), so 16 points per thread on 4 warps issue ~1.9x fewer warp instructions per step than 4 points per
-    // thread on 16 warps, and the 16 independent points per thread hide the arithmetic latency that more warps would.
+    static const int cfg = getenv("NIRRT_FPS_CFG") ? atoi(getenv("NIRRT_FPS_CFG")) : 0;      // development knob: threads per cloud
+#define FPS_ARGS h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l], it0, it1, h->fps_dist, h->fps_far
+    // Few fat threads: 16 independent points per thread hide the arithmetic latency, and few warps keep the one barrier
+    // per selection step short.
     if (N <= 64) k_fps<32, 2><<<B, 32, smem, s>>>(FPS_ARGS);
     else if (N <= 256) k_fps<32, 8><<<B, 32, smem, s>>>(FPS_ARGS);
-    else if (N <= 1024) k_fps<64, 16><<<B, 64, smem, s>>>(FPS_ARGS);
-    else if (N <= 2048) k_fps<128, 16><<<B, 128, smem, s>>>(FPS_ARGS);
-    else k_fps<256, 16><<<B, 256, smem, s>>>(FPS_ARGS);
+    else if (N <= 1024) {
+        if (cfg == 1) k_fps<128, 8><<<B, 128, smem, s>>>(FPS_ARGS);
+        else if (cfg == 2) k_fps<256, 4><<<B, 256, smem, s>>>(FPS_ARGS);
+        else k_fps<64, 16><<<B, 64, smem, s>>>(FPS_ARGS);
+    } else if (N <= 2048) {
+        if (cfg == 1) k_fps<256, 8><<<B, 256, smem, s>>>(FPS_ARGS);
+        else if (cfg == 2) k_fps<512, 4><<<B, 512, smem, s>>>(FPS_ARGS);
+        else k_fps<128, 16><<<B, 128, smem, s>>>(FPS_ARGS);
+    } else k_fps<256, 16><<<B, 256, smem, s>>>(FPS_ARGS);
 #undef FPS_ARGS
     PCUDA(cudaGetLastError());
     h->launches++;
     return NIRRT_OK;
 }
 
-static int ball_query_launch(nirrt_pn2 *h, int B, int l, cudaStream_t s) {
+// centroids [s0, s1) of level l (s1 < 0: all of them)
+static int ball_query_launch(nirrt_pn2 *h, int B, int l, cudaStream_t s, int s0 = 0, int s1 = -1) {
     const int N = h->n[l - 1], S = h->n[l];
+    if (s1 < 0) s1 = S;
+    const int Sc = s1 - s0;
     const float r0 = (float)(kRad[l - 1][0] * kRad[l - 1][0]), r1 = (float)(kRad[l - 1][1] * kRad[l - 1][1]);
     if ((long long)B * S >= 65536) {
-        const int bt = S >= 256 ? 256 : ((S + 31) / 32) * 32;
-        k_ball_query<<<dim3((S + bt - 1) / bt, B), bt, (size_t)N * 4 * sizeof(float), s>>>(
-            h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
+        const int bt = Sc >= 256 ? 256 : ((Sc + 31) / 32) * 32;
+        k_ball_query<<<dim3((Sc + bt - 1) / bt, B), bt, (size_t)(N + 1) * 4 * sizeof(float), s>>>(
+            h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1], s0, s1);
     } else {
-        k_ball_query_warp<<<dim3((S + 7) / 8, B), 256, (size_t)N * 4 * sizeof(float), s>>>(
-            h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1]);
+        k_ball_query_warp<<<dim3((Sc + 7) / 8, B), 256, (size_t)N * 4 * sizeof(float), s>>>(
+            h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1], s0, s1);
     }
     PCUDA(cudaGetLastError());
     h->launches++;
@@ -910,56 +1035,90 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
     // g: the geometry stream (coordinates only).  With stage profiling on everything stays on s so that the
     // event brackets attribute serial times.
     const bool split = h->two_streams && !h->profiling;
-    cudaStream_t g = split ? h->gs : s;
+    // Default: ONE geometry stream (FPS and ball query of a level alternate).  NIRRT_PN2_CHUNKS > 1 moves the ball queries
+    // and 3-NN searches to a second stream and issues level 1 in chunks of centroids (FPS selects them in order, so ball
+    // query, grouping and the first MLPs of the early centroids can run while the later ones are still being selected).
+    // At 256 clouds the forward is throughput-bound (the kernels' serial times add up to the forward's), so the extra
+    // overlap buys nothing there (measured 4.38 vs 4.41 ms); kept for small batches on an otherwise idle GPU.
+    const int NC = (split && h->fused_levels >= 1) ? h->l1_chunks : 1;
+    cudaStream_t g = split ? h->gs : s, g2 = (split && NC > 1) ? h->gs2 : g;
+    trace_mark("start", 0, 0, s);
     if (split) { PCUDA(cudaEventRecord(h->ev_fork, s)); PCUDA(cudaStreamWaitEvent(g, h->ev_fork, 0)); }
     {
         StageTimer t(h, s, 0);
         k_prep<<<B, 256, 0, g>>>(pc, dim, start_mask, goal_mask, h->N0, h->xyz[0], h->in6);
         PCUDA(cudaGetLastError());
         h->launches++;
+        trace_mark("prep", 0, 0, g);
     }
     if (split) {
-        // the whole geometry chain is queued first: FPS + ball query per level, then the 3-NN searches
-        for (int l = 1; l <= 4; l++) {
+        // the whole geometry is queued first.  g: the FPS chain of all four levels back to back (each level only needs
+        // the previous level's centroids); g2: the ball queries behind their level's FPS, then the 3-NN searches
+        const int Sc = h->n[1] / NC;
+        for (int c = 0; c < NC; c++) {
+            PTRY(fps_launch(h, B, 1, fps_start, g, c * Sc, (c + 1) * Sc));
+            trace_mark("fps", 1, c, g);
+            PCUDA(cudaEventRecord(h->ev_fc[c], g));
+            PCUDA(cudaStreamWaitEvent(g2, h->ev_fc[c], 0));
+            PTRY(ball_query_launch(h, B, 1, g2, c * Sc, (c + 1) * Sc));
+            trace_mark("bq", 1, c, g2);
+            PCUDA(cudaEventRecord(h->ev_bc[c], g2));
+        }
+        for (int l = 2; l <= 4; l++) {
             PTRY(fps_launch(h, B, l, fps_start, g));
-            PTRY(ball_query_launch(h, B, l, g));
-            PCUDA(cudaEventRecord(h->ev_bq[l - 1], g));
+            trace_mark("fps", l, 0, g);
+            PCUDA(cudaEventRecord(h->ev_fl[l - 1], g));
+            PCUDA(cudaStreamWaitEvent(g2, h->ev_fl[l - 1], 0));
+            PTRY(ball_query_launch(h, B, l, g2));
+            trace_mark("bq", l, 0, g2);
+            PCUDA(cudaEventRecord(h->ev_bq[l - 1], g2));
         }
         for (int f = 0; f < 4; f++) {
-            PTRY(interp_launch(h, B, f, 1, nullptr, 0, g));
-            PCUDA(cudaEventRecord(h->ev_knn[f], g));
+            PTRY(interp_launch(h, B, f, 1, nullptr, 0, g2));
+            trace_mark("knn", f, 0, g2);
+            PCUDA(cudaEventRecord(h->ev_knn[f], g2));
         }
     }
     int li = 0;
     for (int l = 1; l <= 4; l++) {
         const int N = h->n[l - 1], S = h->n[l];
-        if (split) PCUDA(cudaStreamWaitEvent(s, h->ev_bq[l - 1], 0));
         if (!split) { StageTimer t(h, s, 1); PTRY(fps_launch(h, B, l, fps_start, s)); }
         if (!split) { StageTimer t(h, s, 2); PTRY(ball_query_launch(h, B, l, s)); }
+        if (l <= h->fused_levels) {
+            // gather + 3 layers + max-pool in one persistent tcgen05 kernel per radius (sa_fused.cuh); level 1 per chunk of
+            // centroids as soon as that chunk's groups exist
+            const int nc = l == 1 ? NC : 1;
+            for (int c = 0; c < nc; c++) {
+                if (split) PCUDA(cudaStreamWaitEvent(s, l == 1 ? h->ev_bc[c] : h->ev_bq[l - 1], 0));
+                for (int sc = 0; sc < 2; sc++) {
+                    StageTimer t(h, s, 4);
+                    const int K = kK[sc];
+                    safused::Args fa;
+                    fa.in6 = h->in6; fa.feat = h->feat[l - 1]; fa.xyz = h->xyz[l - 1]; fa.new_xyz = h->xyz[l]; fa.gidx = h->grp[(l - 1) * 2 + sc];
+                    fa.wimg = h->sa_img[l - 1][sc]; fa.bias = h->sa_bias[l - 1][sc];
+                    fa.out = h->feat[l]; fa.N = N; fa.S = S; fa.B = B; fa.ldo = kC[l]; fa.col_off = sc == 0 ? 0 : h->conv[li + 2].N;
+                    fa.tpc = S * K / 128; fa.chunk_tiles = fa.tpc / nc; fa.chunk_lo = c * fa.chunk_tiles;
+                    if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
+                    const int ntiles = B * fa.chunk_tiles;
+                    const int cps = l == 1 ? 8 : (sc == 0 ? 3 : 2);
+                    const int grid = ntiles < g_num_sms * cps ? ntiles : g_num_sms * cps;
+                    if (l == 1 && sc == 0) safused::k_sa_fused<16, 0, 16, 16, 16, 32><<<grid, 128, safused::Smem<16, 16, 16, 32>::kTotal, s>>>(fa);
+                    else if (l == 1) safused::k_sa_fused<32, 0, 16, 32, 32, 64><<<grid, 128, safused::Smem<16, 32, 32, 64>::kTotal, s>>>(fa);
+                    else if (sc == 0) safused::k_sa_fused<16, 96, 112, 64, 64, 128><<<grid, 128, safused::Smem<112, 64, 64, 128>::kTotal, s>>>(fa);
+                    else safused::k_sa_fused<32, 96, 112, 64, 96, 128><<<grid, 128, safused::Smem<112, 64, 96, 128>::kTotal, s>>>(fa);
+                    PCUDA(cudaGetLastError());
+                    h->launches++;
+                    trace_mark(sc ? "sa_fused1" : "sa_fused0", l, c, s);
+                }
+            }
+            li += 6;
+            continue;
+        }
+        if (split) PCUDA(cudaStreamWaitEvent(s, l == 1 ? h->ev_bc[NC - 1] : h->ev_bq[l - 1], 0));
         for (int sc = 0; sc < 2; sc++) {
             const int K = kK[sc];
             const int rows = B * S * K;
             const Conv &c0 = h->conv[li], &c1 = h->conv[li + 1], &c2 = h->conv[li + 2];
-            if (l <= h->fused_levels) {
-                // gather + 3 layers + max-pool in one persistent tcgen05 kernel (sa_fused.cuh)
-                StageTimer t(h, s, 4);
-                safused::Args fa;
-                fa.in6 = h->in6; fa.feat = h->feat[l - 1]; fa.xyz = h->xyz[l - 1]; fa.new_xyz = h->xyz[l]; fa.gidx = h->grp[(l - 1) * 2 + sc];
-                fa.wimg = h->sa_img[l - 1][sc]; fa.bias = h->sa_bias[l - 1][sc];
-                fa.out = h->feat[l]; fa.N = N; fa.S = S; fa.B = B; fa.ldo = kC[l]; fa.col_off = sc == 0 ? 0 : h->conv[li - 1].N;
-                if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
-                const int ntiles = rows / 128;
-                const int cps = l == 1 ? 8 : (sc == 0 ? 3 : 2);
-                const int grid = ntiles < g_num_sms * cps ? ntiles : g_num_sms * cps;
-                if (l == 1 && sc == 0) safused::k_sa_fused<16, 0, 16, 16, 16, 32><<<grid, 128, safused::Smem<16, 16, 16, 32>::kTotal, s>>>(fa);
-                else if (l == 1) safused::k_sa_fused<32, 0, 16, 32, 32, 64><<<grid, 128, safused::Smem<16, 32, 32, 64>::kTotal, s>>>(fa);
-                else if (sc == 0) safused::k_sa_fused<16, 96, 112, 64, 64, 128><<<grid, 128, safused::Smem<112, 64, 64, 128>::kTotal, s>>>(fa);
-                else safused::k_sa_fused<32, 96, 112, 64, 96, 128><<<grid, 128, safused::Smem<112, 64, 96, 128>::kTotal, s>>>(fa);
-                PCUDA(cudaGetLastError());
-                h->launches++;
-                li += 3;
-                continue;
-            }
             {
                 StageTimer t(h, s, 3);
                 if (l == 1) {
@@ -981,6 +1140,7 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
                 const int off = sc == 0 ? 0 : h->conv[li - 1].N;
                 PTRY(launch_gemm(c2, h->bufA, rows, umma::MODE_POOL, h->feat[l], kC[l], off, K, s));
                 h->launches += 3;
+                trace_mark("sa_gemm", l, sc, s);
             }
             li += 3;
         }
@@ -995,6 +1155,7 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
             StageTimer t(h, s, 5);
             if (split) PCUDA(cudaStreamWaitEvent(s, h->ev_knn[f], 0));
             PTRY(interp_launch(h, B, f, split ? 2 : 0, upf, upC, s));
+            trace_mark("interp", f, 0, s);
         }
         {
             StageTimer t(h, s, 6);
@@ -1009,6 +1170,7 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
                 in = o;
             }
         }
+        trace_mark("fp_gemm", f, 0, s);
         upf = h->up[f];
         upC = kUpC[f];
     }
@@ -1023,7 +1185,9 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
         k_head<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(h->bufA, h->w2, h->b2, total, (long long *)path_pred, path_score, logp);
         PCUDA(cudaGetLastError());
         h->launches++;
+        trace_mark("head", 0, 0, s);
     }
+    trace_dump();
     return NIRRT_OK;
 }
 

@@ -42,6 +42,9 @@ struct Args {
     const float *bias;      // [N1 + N2 + N3]
     __half *out;            // [B][S][ldo]
     int N, S, B, ldo, col_off;
+    // tiles of 128 rows: tpc per cloud (S * G / 128); this launch covers tiles [chunk_lo, chunk_lo + chunk_tiles) of every
+    // cloud (a range of centroids -- level 1 is launched per chunk of FPS selections)
+    int tpc, chunk_lo, chunk_tiles;
 };
 
 __device__ __forceinline__ void split_hi_lo(float x, __half &hi, __half &lo) {
@@ -128,8 +131,7 @@ __global__ void __launch_bounds__(128) k_sa_fused(const Args a) {
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t sa_u = smem_u32(sA), sw1_u = smem_u32(sW1), sw2_u = smem_u32(sW2), sw3_u = smem_u32(sW3);
     uint32_t phase = 0;
-    const long long rows = (long long)a.B * a.S * G;
-    const int ntiles = (int)(rows / 128);
+    const int nvt = a.B * a.chunk_tiles;
 
 #define SA_LAYER_SYNC()                                                   \
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          \
@@ -139,7 +141,8 @@ __global__ void __launch_bounds__(128) k_sa_fused(const Args a) {
     umma::mbar_wait(bar, phase); phase ^= 1u;                             \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x) {
+        const int tile = (vt / a.chunk_tiles) * a.tpc + a.chunk_lo + vt % a.chunk_tiles;
         // ---- grouping: this thread's row (pointnet2_utils.py:246-253)
         {
             const long long r = (long long)tile * 128 + tid;

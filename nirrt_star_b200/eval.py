@@ -87,6 +87,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
         update_seconds, plan_seconds} of this rank's shard.
     """
     import torch
+    t_enter = time.perf_counter()
     args = default_args(dim) if args is None else args
     variant = VARIANTS[planner]
     n_total = len(problems)
@@ -99,6 +100,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
     local, lseeds = problems[b:e], seeds[b:e]
     lists = []
     bp = None
+    engines = []
     if local:
         E = len(local)
         cls = _B.BatchPlanner3D if dim == 3 else _B.BatchPlanner2D
@@ -106,6 +108,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
         bp = cls(local, args.iter_max, step_len=args.step_len, clearance=args.clearance, seeds=lseeds, device=device,
                  record_capacity=args.iter_max + args.iter_after_initial + 8,
                  near_capacity=_B.NEAR_CAPACITY_INFORMED if variant in _B.INFORMED else 0)
+        t_created = time.perf_counter()
         neural = variant in (_B.VARIANT_NIRRT_STAR, _B.VARIANT_NRRT_STAR)
         if neural:
             makers = [_CloudMaker(dim, p, args) for p in local]
@@ -120,6 +123,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                 if state_dict is None:
                     raise ValueError("neural planners need state_dict= or classify=")
                 engine = PointNet2Engine(state_dict, n_points=args.pc_n_points, max_batch=E, device=device)
+                engines.append(engine)
 
                 def classify(items, envs):
                     # torch.randint on each problem's own generator, in problem order (pointnet2_utils.py:77)
@@ -140,6 +144,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                         if preds[k] is None:
                             if "e" not in short_engines:      # one spare engine, re-targeted to each short cloud's size
                                 short_engines["e"] = PointNet2Engine(state_dict, n_points=args.pc_n_points, max_batch=1, device=device)
+                                engines.append(short_engines["e"])
                             short_engines["e"].set_n_points(len(it[0]))
                             pred, _ = short_engines["e"].classify(it[0].astype(np.float32)[None], it[1][None], it[2][None], fps_start=fs[k:k + 1])
                             preds[k] = pred[0]
@@ -275,6 +280,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                         gm = get_mask(pts, makers[env].x_goal[np.newaxis, :], args.step_len).astype(np.float32)
                         if "e" not in short_engines:
                             short_engines["e"] = PointNet2Engine(state_dict, n_points=n_pts, max_batch=1, device=device)
+                            engines.append(short_engines["e"])
                         short_engines["e"].set_n_points(len(pts))
                         pred, _ = short_engines["e"].classify(pts.astype(np.float32)[None], sm[None], gm[None], fps_start=fs[k:k + 1])
                         bp.set_cloud(int(env), pts[pred[0].nonzero()[0]])
@@ -296,9 +302,12 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                 update(list(range(E)), np.full(E, np.inf), np.full(E, np.nan))        # init_pc()
         t_plan = time.perf_counter()
         bp.begin(variant, _B.MODE_PLANNING_RANDOM, args.iter_max, args.iter_after_initial)
+        t_run = 0.0
         while True:
+            tr = time.perf_counter()
             bp.run(chunk)
             running, need = bp.status()
+            t_run += time.perf_counter() - tr
             if need:
                 st, _, _ = bp.env_state()
                 cb, cm = bp.c_best()
@@ -308,17 +317,27 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                 break
         if neural:
             np.random.set_state(keep)
+        t_loop = time.perf_counter() - t_plan
         lists = bp.path_len_lists()
         if stats_out is not None:
             stats_out.update(stats if neural else {})
             stats_out["plan_seconds"] = time.perf_counter() - t_plan
+            stats_out["setup_seconds"] = t_plan - t_enter
+            stats_out["create_seconds"] = t_created - t_enter
+            stats_out["run_seconds"] = t_run            # nirrt_batch_run + the status read that waits for it
+            stats_out["loop_seconds"] = t_loop
             stats_out["iterations"] = int(sum(len(x) for x in lists))
             stats_out["work"] = bp.work_stats()
     out = gather_lists(lists, n_total, device=torch.device("cuda", device)) if distributed else lists
+    t_close = time.perf_counter()
+    for eng in engines:         # the forward engines of this call (device buffers, tensor maps)
+        eng.close()
     if return_planner:
         return out, bp
     if bp is not None:
         bp.close()
+    if stats_out is not None:
+        stats_out["close_seconds"] = time.perf_counter() - t_close
     return out
 
 
