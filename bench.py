@@ -469,7 +469,7 @@ def bench_nirrt(args, world, rank, local, connect="none", dim=3):
             "problems_solved": solved, "problems_total": world * E,
             "cloud_updates": upd, "pointnet2_forward_calls": fwd, "clouds_per_forward": upd / max(1.0, fwd),
             "cloud_update_seconds": upd_s, "cloud_update_share_of_time": upd_s / el, "work_rank0": stats.get("work"),
-            "update_breakdown_rank0": {k: stats.get(k) for k in ("rounds", "t_params", "t_sample", "t_forward", "t_short", "short_clouds")},
+            "update_breakdown_rank0": {k: stats.get(k) for k in ("rounds", "t_params", "t_sample", "t_forward", "t_short", "short_clouds", "t_connect", "heuristic_ties")},
             "time_breakdown_rank0": {k: stats.get(k) for k in ("create_seconds", "setup_seconds", "plan_seconds", "loop_seconds", "run_seconds", "update_seconds", "close_seconds")},
             "what": "wall clock of plan_batch (max over ranks): device-side cloud sampling (MT19937 draws, filters, FPS) + masks + "
                     "ONE PointNet++ forward per lock-step round + commit, interleaved with the lock-step planner iterations"}

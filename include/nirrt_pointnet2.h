@@ -97,6 +97,28 @@ int nirrt_connect_analyse_batch_sync(const float *pc, const int *n_pts, int n_ma
                                      const float *src, const float *dst, float radius, int *has_path,
                                      uint8_t *visited_mask, uint8_t *boundary_mask, void *stream);
 
+/* The masks of the FIRST trial: start_mask[b][i] = |pc[b][i] - src[b]| < radius, goal_mask[b][i] = |pc[b][i] - src[batch + b]|
+ * < radius in float32 (get_point_cloud_mask_around_points on pc.astype(float32), as pointnet2_wrapper_connect_bfs.py sees it).
+ * Device pointers, asynchronous on `stream`. */
+int nirrt_connect_masks_device(const float *pc, int n_points, int dim, int batch, const float *src, float radius,
+                               float *start_mask, float *goal_mask, void *stream);
+/* One Neural Connect trial for `batch` problems whose clouds all hold n_points points, everything in HBM
+ * (generate_connected_path_points, pointnet2_wrapper_connect_bfs.py:76-240, what follows the network call; heuristic
+ * wrapper/utils/bfs_connect_heuristic.py:142-181).  For every problem with active[b] != 0:
+ *   path_mask[b] |= (pred[b] != 0);  the searches src[b] -> dst[b] and src[batch + b] -> dst[batch + b] (callers pass
+ *   starts then goals in src and goals then starts in dst: [2 * batch][3], z ignored in 2D) over the r-disc graph;
+ *   if neither reaches its target: the boundary point with the lowest rank sum (total cost ascending + cost from the
+ *   source descending, first in index order among equals) replaces start_mask[b] (first search) / goal_mask[b] (second)
+ *   by the points closer than radius to it; a search without boundary points leaves its mask as it is.
+ * pc [batch][n_points][dim] f32, path_mask [batch][n_points] u8 (in/out), pred [batch][n_points] int64 (the network's
+ * path_pred), start_mask / goal_mask [batch][n_points] f32 (in/out): device pointers.  Host outputs after the stream
+ * has been synchronised: has_path [2 * batch]; ties [2 * batch] != 0 where two boundary points have EQUAL keys -- numpy's
+ * argsort order among equal keys is an implementation detail, so that search's mask is left untouched and its boundary
+ * mask is copied to tie_boundary [2 * batch][n_points] for the caller to decide with numpy itself. */
+int nirrt_connect_trial_device(const float *pc, int n_points, int dim, int batch, const uint8_t *active, uint8_t *path_mask,
+                               const int64_t *pred, const float *src, const float *dst, float radius, float *start_mask,
+                               float *goal_mask, int32_t *has_path, int32_t *ties, uint8_t *tie_boundary, void *stream);
+
 /* Stand-alone tensor-core GEMM (the kernel the network uses), host buffers, synchronous:
  *   A [m][k] fp16, W [n][k] fp16, bias [n] f32; k, n multiples of 16.
  *   mode 0: out [m][n]        = fp16(relu(A W^T + bias))

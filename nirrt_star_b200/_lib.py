@@ -110,6 +110,8 @@ def lib():
     L.nirrt_pn2_launch_count.restype = C.c_int64
     L.nirrt_pn2_launch_count.argtypes = [V]
     L.nirrt_connect_analyse_batch_sync.argtypes = [c_fp, c_ip, C.c_int, C.c_int, C.c_int, c_u8p, c_fp, c_fp, C.c_float, c_ip, c_u8p, c_u8p, V]
+    L.nirrt_connect_masks_device.argtypes = [V, C.c_int, C.c_int, C.c_int, V, C.c_float, V, V, V]
+    L.nirrt_connect_trial_device.argtypes = [V, C.c_int, C.c_int, C.c_int, V, V, V, V, V, C.c_float, V, V, c_ip, c_ip, c_u8p, V]
     L.nirrt_connect_analyse_sync.argtypes = [c_fp, C.c_int, C.c_int, c_u8p, c_fp, c_fp, C.c_float, c_ip, c_u8p, c_u8p, V]
     L.nirrt_gemm_f16_sync.argtypes = [c_u16p, c_u16p, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_u16p, V]
     _LIB = L

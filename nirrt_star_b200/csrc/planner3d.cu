@@ -56,13 +56,18 @@ static int fail(int code, const std::string &msg) { return nirrt_set_error(code,
 extern "C" const char *nirrt_last_error(void) { return g_err.c_str(); }
 extern "C" int nirrt_version(void) { return 100; }
 extern "C" int nirrt_device_count(void) {
+    // answered once per process: the entry points call this on every invocation, and a full property query costs
+    // milliseconds per device
+    static int cached = -1;
+    if (cached >= 0) return cached;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     int ok = 0;
     for (int i = 0; i < n; i++) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
     }
+    cached = ok;
     return ok;
 }
 

@@ -1298,14 +1298,15 @@ __device__ __forceinline__ float norm_f32(float dx, float dy, float dz, int dim)
     if (dim == 3) s = __fadd_rn(s, __fmul_rn(dz, dz));
     return __fsqrt_rn(s);
 }
-// One CTA per analysis (blockIdx.x): clouds [B][n_max][dim] with n_pts[b] valid points each, masks / outputs [B][n_max],
-// src / dst [B][3].
+// One CTA per analysis (blockIdx.x): clouds [n_clouds][n_max][dim] and masks [n_clouds][n_max], analysis b works on cloud
+// b % n_clouds with n_pts[b] valid points (0: skipped); outputs [B][n_max], src / dst [B][3].
 __global__ void __launch_bounds__(1024) k_connect(const float *pc_all, const int *n_pts, int n_max, int dim, const uint8_t *path_mask_all,
                                                   const float *src_all, const float *dst_all, float radius, int *has_path_all,
-                                                  uint8_t *visited_all, uint8_t *boundary_all) {
+                                                  uint8_t *visited_all, uint8_t *boundary_all, int n_clouds) {
     const int b = blockIdx.x, n = n_pts[b];
-    const float *pc = pc_all + (size_t)b * n_max * dim;
-    const uint8_t *path_mask = path_mask_all + (size_t)b * n_max;
+    if (n == 0) { if (threadIdx.x == 0) has_path_all[b] = 0; return; }
+    const float *pc = pc_all + (size_t)(b % n_clouds) * n_max * dim;
+    const uint8_t *path_mask = path_mask_all + (size_t)(b % n_clouds) * n_max;
     const float *src = src_all + 3 * b, *dst = dst_all + 3 * b;
     int *has_path = has_path_all + b;
     uint8_t *visited_mask = visited_all + (size_t)b * n_max, *boundary_mask = boundary_all + (size_t)b * n_max;
@@ -1427,12 +1428,156 @@ extern "C" int nirrt_connect_analyse_batch_sync(const float *pc, const int *n_pt
     const size_t smem = (size_t)(kConnMax + 2) * (3 * sizeof(float) + 3 * sizeof(int) + 1) + 16;
     static bool attr = false;
     if (!attr) { PCUDA(cudaFuncSetAttribute(k_connect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k_connect<<<batch, 1024, smem, s>>>(d_pc, d_n, n_max, dim, d_mask, d_sd, d_sd + 3 * B, radius, d_hp, d_out, d_out + B * N);
+    k_connect<<<batch, 1024, smem, s>>>(d_pc, d_n, n_max, dim, d_mask, d_sd, d_sd + 3 * B, radius, d_hp, d_out, d_out + B * N, batch);
     PCUDA(cudaGetLastError());
     PCUDA(cudaMemcpyAsync(has_path, d_hp, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     PCUDA(cudaMemcpyAsync(visited_mask, d_out, B * N, cudaMemcpyDeviceToHost, s));
     PCUDA(cudaMemcpyAsync(boundary_mask, d_out + B * N, B * N, cudaMemcpyDeviceToHost, s));
     PCUDA(cudaStreamSynchronize(s));
+    return NIRRT_OK;
+}
+
+// ---- one Neural Connect trial for a batch of problems, device resident (generate_connected_path_points,
+// pointnet2_wrapper_connect_bfs.py:76-240, the part after the network call): path_mask |= prediction, both searches of
+// every active problem, and for the problems still unconnected the boundary-point heuristic and the new start / goal
+// neighbourhood masks (select_heuristic_boundary_point, bfs_connect_heuristic.py:142-181; get_point_cloud_mask_around_points).
+__global__ void __launch_bounds__(256) k_connect_merge(const uint8_t *active, const long long *pred, uint8_t *path_mask, int n, int B, int *n_act) {
+    const int b = blockIdx.x;
+    const bool on = active[b] != 0;
+    if (threadIdx.x == 0) { n_act[b] = on ? n : 0; n_act[b + B] = on ? n : 0; }
+    if (!on) return;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (pred[(size_t)b * n + i] != 0) path_mask[(size_t)b * n + i] = 1;
+}
+// search j of 2B (j < B: start -> goal of problem j; j >= B: goal -> start of problem j - B).  The ranks of the reference
+// come from np.argsort, whose order among EQUAL keys is an implementation detail: a search with equal keys is reported in
+// ties[] and left untouched for the caller to decide with numpy itself.
+__global__ void __launch_bounds__(256) k_connect_pick(const float *pc_all, int n, int dim, int B, const int *n_act, const int *hp,
+                                                      const uint8_t *bnd_all, const float *src_all, const float *dst_all, float radius,
+                                                      float *start_mask, float *goal_mask, int *ties) {
+    const int j = blockIdx.x, b = j % B, dir = j / B, tid = threadIdx.x;
+    if (tid == 0) ties[j] = 0;
+    if (n_act[j] == 0 || hp[b] || hp[b + B]) return;
+    const float *pc = pc_all + (size_t)b * n * dim;
+    const uint8_t *bnd = bnd_all + (size_t)j * n;
+    const float *src = src_all + 3 * j, *dst = dst_all + 3 * j;
+    extern __shared__ unsigned char s_pick[];
+    int *idx = reinterpret_cast<int *>(s_pick);
+    float *fs = reinterpret_cast<float *>(idx + n), *tot = fs + n;
+    __shared__ int s_m, s_w[8], s_tie;
+    __shared__ unsigned s_best;
+    if (tid == 0) { s_m = 0; s_tie = 0; s_best = 0xffffffffu; }
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {       // boundary points in index order
+        const int i = base + tid;
+        const bool p = i < n && bnd[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, p);
+        const int w = tid >> 5, l = tid & 31;
+        if (l == 0) s_w[w] = __popc(bal);
+        __syncthreads();
+        int off = s_m;
+        for (int q = 0; q < w; q++) off += s_w[q];
+        if (p) idx[off + __popc(bal & ((1u << l) - 1u))] = i;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int q = 0; q < 8; q++) t += s_w[q]; s_m += t; }
+        __syncthreads();
+    }
+    const int m = s_m;
+    if (m == 0) return;                                      // no boundary point: the mask stays
+    for (int i = tid; i < m; i += blockDim.x) {
+        const float *p = pc + (size_t)idx[i] * dim;
+        const float pz = dim == 3 ? p[2] : 0.f;
+        const float a = norm_f32(__fsub_rn(p[0], src[0]), __fsub_rn(p[1], src[1]), __fsub_rn(pz, dim == 3 ? src[2] : 0.f), dim);
+        const float g = norm_f32(__fsub_rn(p[0], dst[0]), __fsub_rn(p[1], dst[1]), __fsub_rn(pz, dim == 3 ? dst[2] : 0.f), dim);
+        fs[i] = a; tot[i] = __fadd_rn(a, g);
+    }
+    __syncthreads();
+    // rank of the total cost ascending + rank of the cost from the start descending; lowest sum, first boundary point on ties
+    unsigned best = 0xffffffffu;
+    bool tie = false;
+    for (int i = tid; i < m; i += blockDim.x) {
+        const float ti = tot[i], fi = fs[i];
+        int score = 0;
+        for (int k = 0; k < m; k++) {
+            const float tk = tot[k], fk = fs[k];
+            score += (tk < ti ? 1 : 0) + (fk > fi ? 1 : 0);
+            tie = tie || (k != i && (tk == ti || fk == fi));
+        }
+        best = min(best, ((unsigned)score << 12) | (unsigned)i);
+    }
+    if (tie) s_tie = 1;
+    atomicMin(&s_best, best);
+    __syncthreads();
+    if (s_tie) { if (tid == 0) ties[j] = 1; return; }
+    const float *q = pc + (size_t)idx[s_best & 4095u] * dim;
+    const float qx = q[0], qy = q[1], qz = dim == 3 ? q[2] : 0.f;
+    float *out = (dir == 0 ? start_mask : goal_mask) + (size_t)b * n;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float *p = pc + (size_t)i * dim;
+        out[i] = norm_f32(__fsub_rn(p[0], qx), __fsub_rn(p[1], qy), __fsub_rn(dim == 3 ? p[2] : 0.f, qz), dim) < radius ? 1.f : 0.f;
+    }
+}
+
+// get_point_cloud_mask_around_points(pc, x, radius) of the float32 cloud for x = the problem's start and goal: the masks the
+// first trial's network call sees (pointnet2_wrapper_connect_bfs.py works on pc.astype(float32))
+__global__ void __launch_bounds__(256) k_connect_masks(const float *pc_all, int n, int dim, int B, const float *src, float radius,
+                                                       float *start_mask, float *goal_mask) {
+    const int b = blockIdx.x;
+    const float *pc = pc_all + (size_t)b * n * dim, *a = src + 3 * b, *g = src + 3 * (B + b);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float *p = pc + (size_t)i * dim;
+        const float pz = dim == 3 ? p[2] : 0.f;
+        start_mask[(size_t)b * n + i] = norm_f32(__fsub_rn(p[0], a[0]), __fsub_rn(p[1], a[1]), __fsub_rn(pz, dim == 3 ? a[2] : 0.f), dim) < radius ? 1.f : 0.f;
+        goal_mask[(size_t)b * n + i] = norm_f32(__fsub_rn(p[0], g[0]), __fsub_rn(p[1], g[1]), __fsub_rn(pz, dim == 3 ? g[2] : 0.f), dim) < radius ? 1.f : 0.f;
+    }
+}
+extern "C" int nirrt_connect_masks_device(const float *pc, int n_points, int dim, int batch, const float *src, float radius,
+                                          float *start_mask, float *goal_mask, void *stream) {
+    if (!pc || !src || !start_mask || !goal_mask) return pfail(NIRRT_ERR_INVALID, "nirrt_connect_masks_device: null argument");
+    if (batch < 1 || n_points < 1 || (dim != 2 && dim != 3)) return pfail(NIRRT_ERR_INVALID, "nirrt_connect_masks_device: bad argument");
+    if (nirrt_device_count() <= 0) return pfail(NIRRT_ERR_NO_DEVICE, "no sm_100 device");
+    k_connect_masks<<<batch, 256, 0, (cudaStream_t)stream>>>(pc, n_points, dim, batch, src, radius, start_mask, goal_mask);
+    PCUDA(cudaGetLastError());
+    return NIRRT_OK;
+}
+
+extern "C" int nirrt_connect_trial_device(const float *pc, int n_points, int dim, int batch, const uint8_t *active, uint8_t *path_mask,
+                                          const int64_t *pred, const float *src, const float *dst, float radius, float *start_mask,
+                                          float *goal_mask, int32_t *has_path, int32_t *ties, uint8_t *tie_boundary, void *stream) {
+    if (!pc || !active || !path_mask || !pred || !src || !dst || !start_mask || !goal_mask || !has_path || !ties || !tie_boundary)
+        return pfail(NIRRT_ERR_INVALID, "nirrt_connect_trial_device: null argument");
+    if (batch < 1 || n_points < 1 || n_points > 4095 || (dim != 2 && dim != 3))
+        return pfail(NIRRT_ERR_INVALID, "nirrt_connect_trial_device: batch >= 1, 1 <= n_points <= 4095, dim 2 or 3");
+    if (nirrt_device_count() <= 0) return pfail(NIRRT_ERR_NO_DEVICE, "no sm_100 device");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = (size_t)batch, N = (size_t)n_points;
+    const size_t o_n = 0, o_hp = o_n + sizeof(int) * 2 * B, o_tie = o_hp + sizeof(int) * 2 * B, o_out = o_tie + sizeof(int) * 2 * B,
+                 total = o_out + 4 * B * N;
+    if (g_conn_ws.bytes < total) {
+        if (g_conn_ws.p) cudaFree(g_conn_ws.p);
+        g_conn_ws.p = nullptr; g_conn_ws.bytes = 0;
+        PCUDA(cudaMalloc(&g_conn_ws.p, total + (total >> 2)));
+        g_conn_ws.bytes = total + (total >> 2);
+    }
+    unsigned char *w = (unsigned char *)g_conn_ws.p;
+    int *d_n = (int *)(w + o_n), *d_hp = (int *)(w + o_hp), *d_tie = (int *)(w + o_tie);
+    uint8_t *d_vis = w + o_out, *d_bnd = d_vis + 2 * B * N;
+    k_connect_merge<<<batch, 256, 0, s>>>(active, (const long long *)pred, path_mask, n_points, batch, d_n);
+    PCUDA(cudaGetLastError());
+    const size_t smem = (size_t)(kConnMax + 2) * (3 * sizeof(float) + 3 * sizeof(int) + 1) + 16;
+    static bool attr = false;
+    if (!attr) { PCUDA(cudaFuncSetAttribute(k_connect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_connect<<<2 * batch, 1024, smem, s>>>(pc, d_n, n_points, dim, path_mask, src, dst, radius, d_hp, d_vis, d_bnd, batch);
+    PCUDA(cudaGetLastError());
+    k_connect_pick<<<2 * batch, 256, N * 12, s>>>(pc, n_points, dim, batch, d_n, d_hp, d_bnd, src, dst, radius, start_mask, goal_mask, d_tie);
+    PCUDA(cudaGetLastError());
+    PCUDA(cudaMemcpyAsync(has_path, d_hp, sizeof(int) * 2 * B, cudaMemcpyDeviceToHost, s));
+    PCUDA(cudaMemcpyAsync(ties, d_tie, sizeof(int) * 2 * B, cudaMemcpyDeviceToHost, s));
+    PCUDA(cudaStreamSynchronize(s));
+    bool any = false;
+    for (size_t j = 0; j < 2 * B; j++)
+        if (ties[j]) { any = true; PCUDA(cudaMemcpyAsync(tie_boundary + j * N, d_bnd + j * N, N, cudaMemcpyDeviceToHost, s)); }
+    if (any) PCUDA(cudaStreamSynchronize(s));
     return NIRRT_OK;
 }
 

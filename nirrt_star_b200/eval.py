@@ -193,34 +193,34 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                        "pred": torch.empty((E, n_pts), dtype=torch.int64, device=f"cuda:{device}"),
                        "score": torch.empty((E, n_pts), dtype=torch.float32, device=f"cuda:{device}")}
 
-            def connect_round(envs, pts, counts):
-                """generate_connected_path_points for every listed problem, trial by trial"""
+            def connect_round_host(envs, pts, counts, ks):
+                """generate_connected_path_points for the listed positions of this round, trial by trial, host side of the
+                heuristic (clouds with fewer points than pc_n_points: classified at their own size)"""
                 from wrapper.utils.bfs_connect_heuristic import select_heuristic_boundary_point
                 from .pointnet2 import connect_analyse_batch
                 r = args.step_len
                 st = []
-                for k, env in enumerate(envs):
+                for k in ks:
+                    env = envs[k]
                     pc = pts[k, :counts[k]].astype(np.float32)
                     xs, xg = makers[env].x_start.astype(np.float32), makers[env].x_goal.astype(np.float32)
                     st.append({"pc": pc, "xs": xs, "xg": xg, "sm": get_mask(pc, xs[np.newaxis], r), "gm": get_mask(pc, xg[np.newaxis], r),
-                               "mask": np.zeros(len(pc), dtype=np.float32), "active": True})
+                               "mask": np.zeros(len(pc), dtype=np.float32), "active": True, "env": env})
                 for _ in range(args.connect_max_trial_attempts):
-                    act = [k for k in range(len(envs)) if st[k]["active"]]
+                    act = [q for q in st if q["active"]]
                     if not act:
                         break
-                    preds = classify([(st[k]["pc"], st[k]["sm"].astype(np.float32), st[k]["gm"].astype(np.float32)) for k in act],
-                                     [envs[k] for k in act])
+                    preds = classify([(q["pc"], q["sm"].astype(np.float32), q["gm"].astype(np.float32)) for q in act], [q["env"] for q in act])
                     stats["forward_calls"] += 1; stats["clouds_classified"] += len(act)
-                    for k, pred in zip(act, preds):
-                        st[k]["mask"] = ((st[k]["mask"] + pred) > 0).astype(np.float32)
+                    for q, pred in zip(act, preds):
+                        q["mask"] = ((q["mask"] + pred) > 0).astype(np.float32)
                     # both search directions of every active problem in ONE launch (a path start -> goal exists iff one
                     # goal -> start does, so the second search never depends on the first)
-                    hp, _, bnd = connect_analyse_batch([st[k]["pc"] for k in act] * 2, [st[k]["mask"] for k in act] * 2,
-                                                       [st[k]["xs"] for k in act] + [st[k]["xg"] for k in act],
-                                                       [st[k]["xg"] for k in act] + [st[k]["xs"] for k in act], r)
+                    hp, _, bnd = connect_analyse_batch([q["pc"] for q in act] * 2, [q["mask"] for q in act] * 2,
+                                                       [q["xs"] for q in act] + [q["xg"] for q in act],
+                                                       [q["xg"] for q in act] + [q["xs"] for q in act], r)
                     A = len(act)
-                    for j, k in enumerate(act):
-                        q = st[k]
+                    for j, q in enumerate(act):
                         if hp[j] or hp[A + j]:
                             q["active"] = False
                             continue
@@ -229,8 +229,72 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                         _, bpt, _ = select_heuristic_boundary_point(q["pc"], bnd[A + j], q["xg"], q["xs"])
                         ngm = q["gm"] if bpt is None else get_mask(q["pc"], bpt, r)
                         q["sm"], q["gm"] = nsm, ngm
+                for k, q in zip(ks, st):
+                    bp.set_cloud(int(q["env"]), pts[k, :counts[k]][q["mask"].nonzero()[0]])
+
+            def connect_round(envs, counts):
+                """generate_connected_path_points (pointnet2_wrapper_connect_bfs.py:76-240) for every problem of this round.
+                Full-size clouds never leave HBM: per trial ONE forward over the round's clouds (predictions of problems
+                that are already connected are ignored) and ONE nirrt_connect_trial_device (mask union, both searches,
+                boundary heuristic, new neighbourhood masks); the host sees 2 flags per problem and trial."""
+                from wrapper.utils.bfs_connect_heuristic import select_heuristic_boundary_point
+                from .pointnet2 import connect_masks_device, connect_trial_device
+                n, r, R = args.pc_n_points, args.step_len, len(envs)
+                if engine is None:      # caller-supplied classifier: it wants host arrays
+                    connect_round_host(envs, bp.read_sampled_clouds(0, R, n), counts, list(range(R)))
+                    return
+                ddev = dev["pc"].device
+                full = [k for k in range(R) if counts[k] == n]
+                short = [k for k in range(R) if counts[k] != n]
+                pts = None
+                if short:
+                    pts = bp.read_sampled_clouds(0, R, n)
+                    connect_round_host(envs, pts, counts, short)
+                    stats["short_clouds"] += len(short)
+                if not full:
+                    return
+                src = np.zeros((2 * R, 3), dtype=np.float32); dst = np.zeros((2 * R, 3), dtype=np.float32)
                 for k, env in enumerate(envs):
-                    bp.set_cloud(int(env), pts[k, :counts[k]][st[k]["mask"].nonzero()[0]])
+                    xs, xg = makers[env].x_start.astype(np.float32), makers[env].x_goal.astype(np.float32)
+                    src[k, :dim] = xs; src[R + k, :dim] = xg; dst[k, :dim] = xg; dst[R + k, :dim] = xs
+                d_src, d_dst = torch.from_numpy(src).to(ddev), torch.from_numpy(dst).to(ddev)
+                connect_masks_device(dev["pc"].data_ptr(), n, dim, R, d_src.data_ptr(), r, dev["sm"].data_ptr(), dev["gm"].data_ptr())
+                acc = torch.zeros((R, n), dtype=torch.uint8, device=ddev)
+                active = np.zeros(R, dtype=np.uint8); active[full] = 1
+                fs = np.zeros((R, 4), dtype=np.int32)
+                for _ in range(args.connect_max_trial_attempts):
+                    act = np.nonzero(active)[0]
+                    if len(act) == 0:
+                        break
+                    for k in act:       # torch.randint on each problem's own generator (pointnet2_utils.py:77), active problems only
+                        fs[k] = [int(torch.randint(0, m, (1,), generator=gens[envs[k]], dtype=torch.long)) for m in (n,) + NPOINTS]
+                    d_fs = torch.from_numpy(fs).to(ddev)
+                    t0 = time.perf_counter()
+                    engine.classify_device(R, dim, dev["pc"].data_ptr(), dev["sm"].data_ptr(), dev["gm"].data_ptr(), d_fs.data_ptr(),
+                                           dev["pred"].data_ptr(), dev["score"].data_ptr())
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter()
+                    stats["t_forward"] += t1 - t0
+                    stats["forward_calls"] += 1; stats["clouds_classified"] += len(act)
+                    d_active = torch.from_numpy(active).to(ddev)
+                    hp, ties, tb = connect_trial_device(dev["pc"].data_ptr(), n, dim, R, d_active.data_ptr(), acc.data_ptr(),
+                                                        dev["pred"].data_ptr(), d_src.data_ptr(), d_dst.data_ptr(), r,
+                                                        dev["sm"].data_ptr(), dev["gm"].data_ptr())
+                    stats["t_connect"] = stats.get("t_connect", 0.0) + time.perf_counter() - t1
+                    for k in act:
+                        if hp[k] or hp[R + k]:
+                            active[k] = 0
+                            continue
+                        for j, buf in ((k, dev["sm"]), (R + k, dev["gm"])):
+                            if ties[j]:          # equal keys: numpy's argsort decides, as in the reference
+                                if pts is None:
+                                    pts = bp.read_sampled_clouds(0, R, n)
+                                pc = pts[k].astype(np.float32)
+                                _, bpt, _ = select_heuristic_boundary_point(pc, tb[j].astype(np.float32), src[j, :dim], dst[j, :dim])
+                                buf[k] = torch.from_numpy(get_mask(pc, bpt, r).astype(np.float32)).to(ddev)
+                                stats["heuristic_ties"] = stats.get("heuristic_ties", 0) + 1
+                dev["pred"][:R] = acc.to(torch.int64)
+                bp.commit_clouds(dev["pred"].data_ptr(), None if not short else full)
 
             def update_device(envs, cbest, cmin):
                 n_pts, n_raw = args.pc_n_points, args.pc_n_points * args.pc_over_sample_scale
@@ -247,7 +311,7 @@ def plan_batch(problems, planner, dim, args=None, seeds=None, state_dict=None, c
                 tc = time.perf_counter()
                 stats["rounds"] += 1; stats["t_params"] += tb - ta; stats["t_sample"] += tc - tb
                 if connect == "bfs":
-                    connect_round(envs, bp.read_sampled_clouds(0, len(envs), n_pts), counts)
+                    connect_round(envs, counts)
                     return
                 if engine is None:          # caller-supplied classifier: hand it the clouds, upload what it predicts
                     pts = bp.read_sampled_clouds(0, len(envs), n_pts)

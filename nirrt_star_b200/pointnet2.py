@@ -185,6 +185,28 @@ def connect_analyse_batch(pcs, path_masks, srcs, dsts, radius, stream=None):
     return hp.astype(bool), [vis[b, :n_pts[b]].astype(np.float32) for b in range(B)], [bnd[b, :n_pts[b]].astype(np.float32) for b in range(B)]
 
 
+def connect_masks_device(d_pc, n_points, dim, batch, d_src, radius, d_start_mask, d_goal_mask, stream=None):
+    """float32 start / goal neighbourhood masks of the first Neural Connect trial (nirrt_connect_masks_device)."""
+    _lib.require_device()
+    check(_lib.lib().nirrt_connect_masks_device(C.c_void_p(d_pc), n_points, dim, batch, C.c_void_p(d_src), C.c_float(float(radius)),
+                                                C.c_void_p(d_start_mask), C.c_void_p(d_goal_mask), C.c_void_p(stream) if stream else None))
+
+
+def connect_trial_device(d_pc, n_points, dim, batch, d_active, d_path_mask, d_pred, d_src, d_dst, radius, d_start_mask, d_goal_mask,
+                         stream=None):
+    """One Neural Connect trial on device buffers (nirrt_connect_trial_device; all d_* are device addresses).
+    Returns (has_path int32[2*batch], ties int32[2*batch], tie_boundary u8[2*batch][n_points])."""
+    _lib.require_device()
+    L = _lib.lib()
+    hp = np.zeros(2 * batch, dtype=np.int32); ties = np.zeros(2 * batch, dtype=np.int32)
+    tb = np.zeros((2 * batch, n_points), dtype=np.uint8)
+    check(L.nirrt_connect_trial_device(C.c_void_p(d_pc), n_points, dim, batch, C.c_void_p(d_active), C.c_void_p(d_path_mask),
+                                       C.c_void_p(d_pred), C.c_void_p(d_src), C.c_void_p(d_dst), C.c_float(float(radius)),
+                                       C.c_void_p(d_start_mask), C.c_void_p(d_goal_mask), hp.ctypes.data_as(_lib.c_ip),
+                                       ties.ctypes.data_as(_lib.c_ip), _lib.u8p(tb), C.c_void_p(stream) if stream else None))
+    return hp, ties, tb
+
+
 def connect_analyse(pc, path_mask, src, dst, radius, stream=None):
     """(has_path, visited_mask f32 [n], boundary_mask f32 [n]) of the r-disc graph over
     [src, dst, pc[path_mask]] -- bfs_point_cloud + get_boundary_mask of the reference's Neural Connect

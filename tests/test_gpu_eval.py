@@ -163,27 +163,32 @@ def test_nirrt_batch_of_64_equals_single_problem_dropin(tmp_path):
         assert np.array_equal(np.array(host[k]), np.array(batch[e]))
 
 
-def test_batched_neural_connect_equals_single_problem_dropin(tmp_path):
-    """-c bfs (BASELINE configs[3]): NIRRT* with Neural Connect in a lock-step batch -- the network calls of one trial
-    batched over the waiting problems, the r-disc graph searches on the GPU -- equals the single-problem drop-in
-    NIRRTStarPNGC3D + connect PNGWrapper (reference API: nirrt_star_png_c_3d.py:50-84,
-    pointnet2_wrapper_connect_bfs.py:66-233) bit for bit."""
+@pytest.mark.parametrize("dim", [3, 2])
+def test_batched_neural_connect_equals_single_problem_dropin(dim, tmp_path):
+    """-c bfs (BASELINE configs[3]): NIRRT* with Neural Connect in a lock-step batch -- one network call per trial over the
+    round's clouds, mask union, both r-disc graph searches, the boundary-point heuristic and the new neighbourhood masks on
+    the GPU (nirrt_connect_trial_device) -- equals the single-problem drop-in NIRRTStarPNGC{2,3}D + connect PNGWrapper
+    (reference API: nirrt_star_png_c_3d.py:50-84, pointnet2_wrapper_connect_bfs.py:66-233; host numpy heuristic) bit for bit."""
     import torch
     from nirrt_star_b200 import dropin
     from nirrt_star_b200.eval import default_args, plan_batch
     dropin.install()
-    from path_planning_classes_3d.nirrt_star_png_c_3d import get_path_planner
-    from wrapper_3d.pointnet_pointnet2.pointnet2_wrapper_connect_bfs import PNGWrapper
+    if dim == 3:
+        from path_planning_classes_3d.nirrt_star_png_c_3d import get_path_planner
+        from wrapper_3d.pointnet_pointnet2.pointnet2_wrapper_connect_bfs import PNGWrapper
+    else:
+        from path_planning_classes.nirrt_star_png_c_2d import get_path_planner
+        from wrapper.pointnet_pointnet2.pointnet2_wrapper_connect_bfs import PNGWrapper
     sd = make_pointnet2_state(0)
-    d = tmp_path / "results/model_training/pointnet2_3d/checkpoints"
+    d = tmp_path / f"results/model_training/pointnet2_{dim}d/checkpoints"
     d.mkdir(parents=True)
-    torch.save({"model_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, str(d / "best_pointnet2_3d.pth"))
+    torch.save({"model_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, str(d / f"best_pointnet2_{dim}d.pth"))
     E = 12
-    problems = [make_problem_3d(350 + i) for i in range(E)]
+    problems = [(make_problem_3d if dim == 3 else make_problem_2d)(350 + i) for i in range(E)]
     seeds = [5200 + i for i in range(E)]
-    args = default_args(3, iter_max=900, iter_after_initial=150)
+    args = default_args(dim, iter_max=900, iter_after_initial=150)
     stats = {}
-    batch = plan_batch(problems, "nirrt_star", 3, args, seeds=seeds, state_dict=sd, connect="bfs", stats_out=stats)
+    batch = plan_batch(problems, "nirrt_star", dim, args, seeds=seeds, state_dict=sd, connect="bfs", stats_out=stats)
     assert stats["forward_calls"] >= 2              # several trials happened
     w = PNGWrapper(root_dir=str(tmp_path), device="cuda")
     for e in (0, 3, 5, 8, 11):
