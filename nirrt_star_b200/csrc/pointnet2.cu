@@ -45,13 +45,23 @@ static int pfail(int code, const std::string &msg) { return nirrt_set_error(code
 __global__ void __launch_bounds__(256) k_prep(const float *pc, int dim, const float *sm, const float *gm, int N,
                                               float *xyz0, float *in6) {
     const int b = blockIdx.x;
-    const float *P = pc + (size_t)b * N * dim;
+    // the cloud is staged in shared memory once: the column sums are 3 serial chains of N dependent additions (numpy's
+    // order), which must not wait for a global load per term
+    extern __shared__ float s_pc[];           // [N][dim]
+    {
+        const float *G = pc + (size_t)b * N * dim;
+        for (int i = threadIdx.x; i < N * dim; i += blockDim.x) s_pc[i] = G[i];
+    }
+    const float *P = s_pc;
     __shared__ float s_c[3];
     __shared__ float s_red[8];
+    __syncthreads();
     if (threadIdx.x < 3) {
         float s = 0.f;
-        if ((int)threadIdx.x < dim)
+        if ((int)threadIdx.x < dim) {
+#pragma unroll 8
             for (int i = 0; i < N; i++) s = __fadd_rn(s, P[(size_t)i * dim + threadIdx.x]);
+        }
         s_c[threadIdx.x] = __fdiv_rn(s, (float)N);
     }
     __syncthreads();
@@ -593,6 +603,7 @@ static int gemm_attr() {
     PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PCUDA(cudaFuncSetAttribute(k_ball_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    PCUDA(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     PCUDA(cudaFuncSetAttribute(k_ball_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     PCUDA(cudaFuncSetAttribute(k_fps<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));   // 4096 points x 12 B + static
     g_gemm_attr = true;
@@ -1046,7 +1057,7 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
     if (split) { PCUDA(cudaEventRecord(h->ev_fork, s)); PCUDA(cudaStreamWaitEvent(g, h->ev_fork, 0)); }
     {
         StageTimer t(h, s, 0);
-        k_prep<<<B, 256, 0, g>>>(pc, dim, start_mask, goal_mask, h->N0, h->xyz[0], h->in6);
+        k_prep<<<B, 256, (size_t)h->N0 * dim * sizeof(float), g>>>(pc, dim, start_mask, goal_mask, h->N0, h->xyz[0], h->in6);
         PCUDA(cudaGetLastError());
         h->launches++;
         trace_mark("prep", 0, 0, g);
