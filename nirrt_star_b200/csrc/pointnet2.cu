@@ -332,29 +332,29 @@ __global__ void __launch_bounds__(256) k_group_sa1(const float *in6, const float
 
 // sa2..sa4: feat fp16 [B][N][C] (C % 8 == 0) -> rows of Kpad halves:
 //   [feat(C) | rx ry rz | rx_lo ry_lo rz_lo | 0...]; one thread per 16-byte chunk
+// block = (Kpad / 8 chunks) x (rows): thread (x, y) writes chunk x of row blockIdx.x * blockDim.y + y, so no thread divides
+// (K and S are powers of two: shifts); a warp still writes 32 consecutive chunks
 __global__ void __launch_bounds__(256) k_group(const __half *feat, int C, const float *xyz, int N, const float *new_xyz,
-                                               int S, const int *gidx, int K, int B, int Kpad, __half *out) {
-    const int CH = Kpad >> 3, FC = C >> 3;
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)B * S * K * CH;
-    if (t >= total) return;
-    const size_t r = t / CH;
-    const int ch = (int)(t - r * CH);
-    const size_t bs = r / K;
-    const int b = (int)(bs / S);
+                                               int s_shift, const int *gidx, int k_shift, unsigned rows, int Kpad, __half *out) {
+    const int FC = C >> 3;
+    const unsigned r = blockIdx.x * blockDim.y + threadIdx.y;
+    const int ch = threadIdx.x;
+    if (r >= rows) return;
+    const unsigned bs = r >> k_shift;
+    const int b = (int)(bs >> s_shift);
     const int i = gidx[r];
     uint4 val = make_uint4(0, 0, 0, 0);
     if (ch < FC) {
         val = *reinterpret_cast<const uint4 *>(feat + ((size_t)b * N + i) * C + ch * 8);
     } else if (ch == FC) {
         const float *p = xyz + ((size_t)b * N + i) * 3;
-        const float *c = new_xyz + bs * 3;
+        const float *c = new_xyz + (size_t)bs * 3;
         __half h[8];
         for (int k = 0; k < 3; k++) split_half(__fsub_rn(p[k], c[k]), h[k], h[3 + k]);
         h[6] = h[7] = __float2half_rn(0.f);
         val = *reinterpret_cast<uint4 *>(h);
     }
-    *reinterpret_cast<uint4 *>(out + r * Kpad + ch * 8) = val;
+    *reinterpret_cast<uint4 *>(out + (size_t)r * Kpad + ch * 8) = val;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -506,25 +506,41 @@ __global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const 
     }
     }
     const int cnt = min(32, N - i0);
-    for (int j = 0; j < cnt; j++) {
-        const int n0 = __shfl_sync(0xffffffffu, t.i[0], j), n1 = __shfl_sync(0xffffffffu, t.i[1], j), n2 = __shfl_sync(0xffffffffu, t.i[2], j);
-        const float u0 = __shfl_sync(0xffffffffu, w0, j), u1 = __shfl_sync(0xffffffffu, w1, j), u2 = __shfl_sync(0xffffffffu, w2, j);
+    // LPP lanes share a point, one 16-byte chunk (8 channels) per lane and step; 32 / LPP points per warp step.  Per element
+    // the arithmetic is the reference's (a0 * w0 + a1 * w1) + a2 * w2 in fp32, whatever the vector width.
+    const int chunks2 = C2 >> 3;
+    const int LPP = chunks2 >= 32 ? 32 : (chunks2 >= 16 ? 16 : 8);
+    const int sub = lane / LPP, c = lane % LPP, PPW = 32 / LPP;
+    for (int j0 = 0; j0 < cnt; j0 += PPW) {
+        const int j = j0 + sub, sl = min(j, 31);
+        const int n0 = __shfl_sync(0xffffffffu, t.i[0], sl), n1 = __shfl_sync(0xffffffffu, t.i[1], sl), n2 = __shfl_sync(0xffffffffu, t.i[2], sl);
+        const float u0 = __shfl_sync(0xffffffffu, w0, sl), u1 = __shfl_sync(0xffffffffu, w1, sl), u2 = __shfl_sync(0xffffffffu, w2, sl);
+        if (j >= cnt) continue;
         const size_t p = (size_t)b * N + i0 + j;
         __half *o = out + p * (size_t)(C1 + C2);
         if (C1 > 0) {
             const uint4 *src = reinterpret_cast<const uint4 *>(feat1 + p * (size_t)C1);
             uint4 *dst = reinterpret_cast<uint4 *>(o);
-            for (int k = lane; k < (C1 >> 3); k += 32) dst[k] = src[k];
+            for (int k = c; k < (C1 >> 3); k += LPP) dst[k] = src[k];
         }
-        const __half2 *f0 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + n0) * C2);
-        const __half2 *f1 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + n1) * C2);
-        const __half2 *f2 = reinterpret_cast<const __half2 *>(feat2 + ((size_t)b * S + n2) * C2);
-        __half2 *oi = reinterpret_cast<__half2 *>(o + C1);
-        for (int k = lane; k < (C2 >> 1); k += 32) {
-            const float2 a0 = __half22float2(f0[k]), a1 = __half22float2(f1[k]), a2 = __half22float2(f2[k]);
-            const float x = __fadd_rn(__fadd_rn(__fmul_rn(a0.x, u0), __fmul_rn(a1.x, u1)), __fmul_rn(a2.x, u2));
-            const float y = __fadd_rn(__fadd_rn(__fmul_rn(a0.y, u0), __fmul_rn(a1.y, u1)), __fmul_rn(a2.y, u2));
-            oi[k] = __floats2half2_rn(fminf(x, 65504.f), fminf(y, 65504.f));
+        const uint4 *f0 = reinterpret_cast<const uint4 *>(feat2 + ((size_t)b * S + n0) * C2);
+        const uint4 *f1 = reinterpret_cast<const uint4 *>(feat2 + ((size_t)b * S + n1) * C2);
+        const uint4 *f2 = reinterpret_cast<const uint4 *>(feat2 + ((size_t)b * S + n2) * C2);
+        uint4 *oi = reinterpret_cast<uint4 *>(o + C1);
+        for (int k = c; k < chunks2; k += LPP) {
+            const uint4 q0 = __ldg(f0 + k), q1 = __ldg(f1 + k), q2 = __ldg(f2 + k);
+            const __half2 *h0 = reinterpret_cast<const __half2 *>(&q0), *h1 = reinterpret_cast<const __half2 *>(&q1),
+                          *h2 = reinterpret_cast<const __half2 *>(&q2);
+            uint4 r;
+            __half2 *hr = reinterpret_cast<__half2 *>(&r);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 a0 = __half22float2(h0[e]), a1 = __half22float2(h1[e]), a2 = __half22float2(h2[e]);
+                const float x = __fadd_rn(__fadd_rn(__fmul_rn(a0.x, u0), __fmul_rn(a1.x, u1)), __fmul_rn(a2.x, u2));
+                const float y = __fadd_rn(__fadd_rn(__fmul_rn(a0.y, u0), __fmul_rn(a1.y, u1)), __fmul_rn(a2.y, u2));
+                hr[e] = __floats2half2_rn(fminf(x, 65504.f), fminf(y, 65504.f));
+            }
+            oi[k] = r;
         }
     }
 }
@@ -775,7 +791,7 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
     // any cloud size the reference's forward accepts up to 4096 points: with fewer than 1024 points sa1's farthest point
     // sampling re-selects index 0 once every point is taken (torch.max on all-zero distances), which k_fps reproduces
     if (n_points < 16 || n_points > 4096) return pfail(NIRRT_ERR_INVALID, "n_points must be in [16, 4096]");
-    if (max_batch < 1) return pfail(NIRRT_ERR_INVALID, "max_batch >= 1 required");
+    if (max_batch < 1 || max_batch > 32768) return pfail(NIRRT_ERR_INVALID, "1 <= max_batch <= 32768 required (row indices are 32-bit)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pfail(NIRRT_ERR_NO_DEVICE, "no CUDA device visible");
     if (device < 0 || device >= ndev) return pfail(NIRRT_ERR_INVALID, "bad device ordinal");
@@ -1135,9 +1151,13 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
                 if (l == 1) {
                     k_group_sa1<<<(rows + 255) / 256, 256, 0, s>>>(h->in6, h->xyz[0], N, h->xyz[1], S, h->grp[sc], K, B, h->bufA);
                 } else {
-                    const size_t total = (size_t)rows * (c0.K >> 3);
-                    k_group<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->feat[l - 1], kC[l - 1], h->xyz[l - 1], N, h->xyz[l], S,
-                                                                            h->grp[(l - 1) * 2 + sc], K, B, c0.K, h->bufA);
+                    const int CH = c0.K >> 3;                 // <= 66 chunks per row
+                    const dim3 blk(CH, 256 / CH);
+                    int s_shift = 0, k_shift = 0;
+                    while ((1 << s_shift) < S) s_shift++;
+                    while ((1 << k_shift) < K) k_shift++;
+                    k_group<<<(rows + blk.y - 1) / blk.y, blk, 0, s>>>(h->feat[l - 1], kC[l - 1], h->xyz[l - 1], N, h->xyz[l], s_shift,
+                                                                      h->grp[(l - 1) * 2 + sc], k_shift, (unsigned)rows, c0.K, h->bufA);
                 }
                 PCUDA(cudaGetLastError());
                 h->launches++;

@@ -145,11 +145,12 @@ __global__ void __launch_bounds__(128) k_sa_fused(const Args a) {
         const int tile = (vt / a.chunk_tiles) * a.tpc + a.chunk_lo + vt % a.chunk_tiles;
         // ---- grouping: this thread's row (pointnet2_utils.py:246-253)
         {
-            const long long r = (long long)tile * 128 + tid;
-            const long long bs = r / G;
-            const int b = (int)(bs / a.S);
+            // 32-bit index arithmetic (rows < 2^31 is checked at launch): a 64-bit division per row costs more than the gather
+            const unsigned r = (unsigned)tile * 128u + (unsigned)tid;
+            const unsigned bs = r / G;
+            const int b = tile / a.tpc;
             const int i = a.gidx[r];
-            const float *c = a.new_xyz + bs * 3;
+            const float *c = a.new_xyz + (size_t)bs * 3;
             if (C == 0) {
                 const float *f = a.in6 + ((size_t)b * a.N + i) * 6;
                 __half h[16];
