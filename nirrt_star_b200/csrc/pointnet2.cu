@@ -192,6 +192,121 @@ __global__ void __launch_bounds__(T) k_fps(const float *xyz, int N, int npoint, 
     }
 }
 
+// k_fps_bucket: the same selection with spatial pruning.  The cloud is counting-sorted by 9-bit Morton cell and cut into
+// buckets of 32 consecutive points (one point per lane; 16 buckets per warp, interleaved over the warps); every bucket keeps
+// its bounding box, the largest running distance of its points and the lowest index at that distance.  A selection step
+// evaluates, per bucket, the distance formula on the GAPS between the new centroid and the box: every float32 operation of the
+// formula is monotone, so that value is a lower bound of the computed distance of every point in the bucket, and a bucket whose
+// bound is not below its largest running distance cannot change -- it is skipped.  Late in the selection (most of the steps)
+// a new centroid only touches the few buckets around it.  Same distances, same arg-max with lowest-index ties: the selected
+// indices are those of k_fps whatever the bucket composition (the scatter order inside a cell is arbitrary).
+// Measured (256 clouds x 2048 points, B200): SLOWER than k_fps -- 0.76 vs 0.59 ms for the four levels, 0.70 vs 0.53 ms for one
+// cloud: the selection step stays one dependent chain, and bound + ballot + per-bucket REDUX pairs lengthen it by more than the
+// skipped distance updates shorten it.  Kept as an opt-in (NIRRT_PN2_FPS_BUCKET=1) with its parity test.
+__device__ __forceinline__ int morton_cell(float x, float y, float z) {
+    const int cx = min(7, max(0, (int)((x + 1.f) * 4.f))), cy = min(7, max(0, (int)((y + 1.f) * 4.f))), cz = min(7, max(0, (int)((z + 1.f) * 4.f)));
+    int m = 0;
+#pragma unroll
+    for (int b = 0; b < 3; b++) m |= (((cx >> b) & 1) << (3 * b)) | (((cy >> b) & 1) << (3 * b + 1)) | (((cz >> b) & 1) << (3 * b + 2));
+    return m;
+}
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) k_fps_bucket(const float *xyz, int N, int npoint, const int *start, int level,
+                                                        int *fidx, float *new_xyz) {
+    constexpr int T = 32 * NW, NBW = 16, CAP = T * NBW;
+    extern __shared__ float s_xyz[];          // [N][3] in the caller's order, then perm[CAP] (u16), hist[513]
+    unsigned short *s_perm = reinterpret_cast<unsigned short *>(s_xyz + 3 * N);
+    int *s_hist = reinterpret_cast<int *>(s_perm + CAP + (CAP & 1));
+    __shared__ __align__(16) unsigned s_d[2][NW];
+    __shared__ __align__(16) int s_i[2][NW];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *X = xyz + (size_t)b * N * 3;
+    for (int i = tid; i < N * 3; i += T) s_xyz[i] = X[i];
+    for (int i = tid; i < 513; i += T) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += T) atomicAdd(&s_hist[morton_cell(s_xyz[i * 3], s_xyz[i * 3 + 1], s_xyz[i * 3 + 2])], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int c = 0; c < 512; c++) { const int t = s_hist[c]; s_hist[c] = run; run += t; }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += T)
+        s_perm[atomicAdd(&s_hist[morton_cell(s_xyz[i * 3], s_xyz[i * 3 + 1], s_xyz[i * 3 + 2])], 1)] = (unsigned short)i;
+    __syncthreads();
+    float px[NBW], py[NBW], pz[NBW], dist[NBW];
+    int idx[NBW];
+    float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f;      // lane j < NBW: bounding box of bucket j of this warp
+    unsigned bmax = 0u;                       // ... its largest running distance (bit pattern)
+    int bidx = 0x7fffffff;                    // ... and the lowest index at that distance
+#pragma unroll
+    for (int j = 0; j < NBW; j++) {
+        const int pos = (j * NW + warp) * 32 + lane;
+        const bool in = pos < N;
+        const int i = in ? (int)s_perm[pos] : 0;
+        px[j] = in ? s_xyz[i * 3] : 0.f; py[j] = in ? s_xyz[i * 3 + 1] : 0.f; pz[j] = in ? s_xyz[i * 3 + 2] : 0.f;
+        dist[j] = in ? 1e10f : 0.f;
+        idx[j] = in ? i : 0x7fffffff;
+        float a0 = in ? px[j] : INFINITY, a1 = in ? py[j] : INFINITY, a2 = in ? pz[j] : INFINITY;
+        float b0 = in ? px[j] : -INFINITY, b1 = in ? py[j] : -INFINITY, b2 = in ? pz[j] : -INFINITY;
+        int mi = idx[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a0 = fminf(a0, __shfl_xor_sync(0xffffffffu, a0, off)); a1 = fminf(a1, __shfl_xor_sync(0xffffffffu, a1, off));
+            a2 = fminf(a2, __shfl_xor_sync(0xffffffffu, a2, off));
+            b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, off)); b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, off));
+            b2 = fmaxf(b2, __shfl_xor_sync(0xffffffffu, b2, off));
+            mi = min(mi, __shfl_xor_sync(0xffffffffu, mi, off));
+        }
+        if (lane == j) {
+            lox = a0; loy = a1; loz = a2; hix = b0; hiy = b1; hiz = b2;
+            bmax = mi != 0x7fffffff ? __float_as_uint(1e10f) : 0u;
+            bidx = mi;
+        }
+    }
+    int far = start[b * 4 + level];
+    for (int it = 0; it < npoint; it++) {
+        const float cx = s_xyz[far * 3], cy = s_xyz[far * 3 + 1], cz = s_xyz[far * 3 + 2];
+        if (tid == 0) {
+            fidx[(size_t)b * npoint + it] = far;
+            float *o = new_xyz + ((size_t)b * npoint + it) * 3;
+            o[0] = cx; o[1] = cy; o[2] = cz;
+        }
+        // lower bound of the bucket's distances: the formula on the gaps to the box (monotone operations; an empty bucket has
+        // an infinite bound)
+        const float gx = fmaxf(fmaxf(__fsub_rn(lox, cx), __fsub_rn(cx, hix)), 0.f);
+        const float gy = fmaxf(fmaxf(__fsub_rn(loy, cy), __fsub_rn(cy, hiy)), 0.f);
+        const float gz = fmaxf(fmaxf(__fsub_rn(loz, cz), __fsub_rn(cz, hiz)), 0.f);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+        const unsigned act = __ballot_sync(0xffffffffu, lane < NBW && lb < __uint_as_float(bmax));
+#pragma unroll
+        for (int j = 0; j < NBW; j++) {
+            if ((act >> j) & 1u) {            // warp-uniform
+                const float dx = __fsub_rn(px[j], cx), dy = __fsub_rn(py[j], cy), dz = __fsub_rn(pz[j], cz);
+                const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d < dist[j]) dist[j] = d;
+                const unsigned u = __float_as_uint(dist[j]);          // padding slots hold 0 and index INT_MAX
+                const unsigned bm = __reduce_max_sync(0xffffffffu, u);
+                const int bi = __reduce_min_sync(0xffffffffu, u == bm ? idx[j] : 0x7fffffff);
+                if (lane == j) { bmax = bm; bidx = bi; }
+            }
+        }
+        const unsigned wm = __reduce_max_sync(0xffffffffu, lane < NBW ? bmax : 0u);
+        const int wi = __reduce_min_sync(0xffffffffu, (lane < NBW && bmax == wm) ? bidx : 0x7fffffff);
+        if (NW == 1) { far = wi; continue; }
+        const int slot = it & 1;
+        if (lane == 0) { s_d[slot][warp] = wm; s_i[slot][warp] = wi; }
+        __syncthreads();
+        unsigned gm = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; w++) gm = max(gm, s_d[slot][w]);
+        int gi = 0x7fffffff;
+#pragma unroll
+        for (int w = 0; w < NW; w++) gi = min(gi, s_d[slot][w] == gm ? s_i[slot][w] : 0x7fffffff);
+        far = gi;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_ball_query: query_ball_point (pointnet2_utils.py:89-109) for both radii of an SA level.
 // One warp per centroid scans the cloud in index order (32 points per step, ballot + prefix
@@ -241,8 +356,76 @@ __global__ void __launch_bounds__(256) k_ball_query_warp(const float *xyz, int N
     if (cnt1 < K1) { const int f = cnt1 > 0 ? o1[0] : 0; for (int p = cnt1 + lane; p < K1; p += 32) o1[p] = f; }
 }
 
-__global__ void __launch_bounds__(256) k_ball_query(const float *xyz, int N, const float *new_xyz, int S,
-                                                    float r0sq, int K0, float r1sq, int K1, int *g0, int *g1, int s0, int s1) {
+// Pruned version for radii well below the cloud's extent (levels 1-3): the coordinates are normalised to the unit ball, each
+// axis is cut into kSlabs slabs, and bitmap[axis][slab] marks the points whose coordinate lies within `reach` (>= the large
+// radius plus the rounding slack of the expansion formula) of the slab.  A centroid in slabs (ix, iy, iz) can only have members
+// in bitmap[0][ix] & bitmap[1][iy] & bitmap[2][iz]; the thread walks the set bits in index order and applies the SAME float32
+// test to them, so the groups are those of the exhaustive scan (1-15 % of the points are tested instead of all).
+constexpr int kSlabs = 8;
+constexpr int kSlabWordsMax = 128;        // 4096 points
+__device__ __forceinline__ float slab_lo(int s) { return __fmaf_rn((float)s, 2.f / kSlabs, -1.f); }
+__global__ void __launch_bounds__(1024) k_ball_query(const float *xyz, int N, const float *new_xyz, int S,
+                                                    float r0sq, int K0, float r1sq, int K1, int *g0, int *g1, int s0, int s1, float reach) {
+    extern __shared__ float4 s_p4[];          // [N] (x, y, z, |p|^2), then the bitmaps [3][kSlabs][W]
+    const int Wn = (N + 31) >> 5, W = Wn + 1;   // row stride Wn + 1: the rows of different slabs start in different banks
+    unsigned *bm = reinterpret_cast<unsigned *>(s_p4 + N);
+    const int b = blockIdx.y;
+    const float *X = xyz + (size_t)b * N * 3;
+    for (int i = threadIdx.x; i < 3 * kSlabs * W; i += blockDim.x) bm[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float v[3] = {X[i * 3], X[i * 3 + 1], X[i * 3 + 2]};
+        s_p4[i] = make_float4(v[0], v[1], v[2], __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int sl = 0; sl < kSlabs; sl++) {      // the end slabs are unbounded outwards
+                const bool lo_ok = sl == 0 || v[a] >= slab_lo(sl) - reach;
+                const bool hi_ok = sl == kSlabs - 1 || v[a] <= slab_lo(sl + 1) + reach;
+                if (lo_ok && hi_ok) atomicOr(&bm[(a * kSlabs + sl) * W + (i >> 5)], 1u << (i & 31));
+            }
+    }
+    __syncthreads();
+    const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;      // centroids [s0, s1) of every cloud
+    if (s >= s1) return;
+    const float *c = new_xyz + ((size_t)b * S + s) * 3;
+    const float cx = c[0], cy = c[1], cz = c[2];
+    const float cs = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
+    int *o0 = g0 + ((size_t)b * S + s) * K0, *o1 = g1 + ((size_t)b * S + s) * K1;
+    int cnt0 = 0, cnt1 = 0, f0 = 0, f1 = 0;
+    int ix = 0, iy = 0, iz = 0;               // the slab with slab_lo(s) <= c < slab_lo(s + 1) (clamped at the ends)
+#pragma unroll
+    for (int sl = 1; sl < kSlabs; sl++) {
+        const float lo = slab_lo(sl);
+        ix += cx >= lo ? 1 : 0; iy += cy >= lo ? 1 : 0; iz += cz >= lo ? 1 : 0;
+    }
+    const unsigned *bx = bm + (0 * kSlabs + ix) * W, *by = bm + (1 * kSlabs + iy) * W, *bz = bm + (2 * kSlabs + iz) * W;
+    bool full = false;
+    for (int w = 0; w < Wn && !full; w++) {
+        unsigned m = bx[w] & by[w] & bz[w];
+        while (m && !full) {
+            const int i = (w << 5) + __ffs(m) - 1;
+            m &= m - 1;
+            const float4 p = s_p4[i];
+            const float dot = __fmaf_rn(cz, p.z, __fmaf_rn(cy, p.y, __fmul_rn(cx, p.x)));
+            float d = __fmul_rn(-2.f, dot);
+            d = __fadd_rn(d, cs);
+            d = __fadd_rn(d, p.w);
+            if (!(d > r1sq)) {                       // r0 < r1: members of the small ball are members of the large one
+                if (cnt1 < K1) { if (cnt1 == 0) f1 = i; o1[cnt1++] = i; }
+                if (!(d > r0sq) && cnt0 < K0) { if (cnt0 == 0) f0 = i; o0[cnt0++] = i; }
+                full = cnt1 >= K1 && cnt0 >= K0;
+            }
+        }
+    }
+    // pad with the first member (group_first); an empty ball cannot occur: the centroid is a member
+    for (int p = cnt0; p < K0; p++) o0[p] = f0;
+    for (int p = cnt1; p < K1; p++) o1[p] = f1;
+}
+
+// exhaustive version (large radii)
+__global__ void __launch_bounds__(256) k_ball_query_bf(const float *xyz, int N, const float *new_xyz, int S,
+                                                       float r0sq, int K0, float r1sq, int K1, int *g0, int *g1, int s0, int s1) {
     // points in pairs for the packed fp32 pipe: s_pp[2k] = (x_2k, x_2k+1, y_2k, y_2k+1), s_pp[2k + 1] = (z_2k, z_2k+1, |p|^2_2k,
     // |p|^2_2k+1): two broadcast LDS.128 per two points; an odd cloud is padded with a point far outside every ball
     extern __shared__ float4 s_pp[];
@@ -442,6 +625,70 @@ __global__ void __launch_bounds__(256) k_interp_warp(const float *xyz1, int N, c
     }
 }
 
+// 3-NN search (indices + weights only, what MODE 1 of k_interp produces) with the slab bitmaps of k_ball_query over the
+// COARSE points: the candidates within `reach` of the fine point's slabs are searched first; if the third-nearest of them is
+// closer than every point outside the candidate set can be (squared distance <= ok_d < reach^2 minus the rounding slack of the
+// expansion formula), the result is that of the exhaustive scan -- same distances, same (distance, index) order; otherwise the
+// thread falls back to the exhaustive scan.
+__global__ void __launch_bounds__(512) k_knn_pruned(const float *xyz1, int N, const float *xyz2, int S, int4 *knn_i, float4 *knn_w,
+                                                    float reach, float ok_d) {
+    extern __shared__ float4 s_q4[];          // [S] (x, y, z, |q|^2), then the bitmaps [3][kSlabs][W]
+    const int Wn = (S + 31) >> 5, W = Wn + 1;   // row stride Wn + 1: the rows of different slabs start in different banks
+    unsigned *bm = reinterpret_cast<unsigned *>(s_q4 + S);
+    const int b = blockIdx.y;
+    const float *Q = xyz2 + (size_t)b * S * 3;
+    for (int i = threadIdx.x; i < 3 * kSlabs * W; i += blockDim.x) bm[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const float v[3] = {Q[i * 3], Q[i * 3 + 1], Q[i * 3 + 2]};
+        s_q4[i] = make_float4(v[0], v[1], v[2], __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int sl = 0; sl < kSlabs; sl++) {
+                const bool lo_ok = sl == 0 || v[a] >= slab_lo(sl) - reach;
+                const bool hi_ok = sl == kSlabs - 1 || v[a] <= slab_lo(sl + 1) + reach;
+                if (lo_ok && hi_ok) atomicOr(&bm[(a * kSlabs + sl) * W + (i >> 5)], 1u << (i & 31));
+            }
+    }
+    __syncthreads();
+    const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= N) return;
+    const float *a = xyz1 + ((size_t)b * N + pi) * 3;
+    const float ax = a[0], ay = a[1], az = a[2];
+    const float as = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+    int ix = 0, iy = 0, iz = 0;
+#pragma unroll
+    for (int sl = 1; sl < kSlabs; sl++) {
+        const float lo = slab_lo(sl);
+        ix += ax >= lo ? 1 : 0; iy += ay >= lo ? 1 : 0; iz += az >= lo ? 1 : 0;
+    }
+    const unsigned *bx = bm + (0 * kSlabs + ix) * W, *by = bm + (1 * kSlabs + iy) * W, *bz = bm + (2 * kSlabs + iz) * W;
+    Top3 t;
+    t.d[0] = t.d[1] = t.d[2] = INFINITY; t.i[0] = t.i[1] = t.i[2] = 0;
+    auto visit = [&](int s) {
+        const float4 q = s_q4[s];
+        const float dot = __fmaf_rn(az, q.z, __fmaf_rn(ay, q.y, __fmul_rn(ax, q.x)));
+        float d = __fmul_rn(-2.f, dot);
+        d = __fadd_rn(d, as);
+        d = __fadd_rn(d, q.w);
+        top3_insert(t, d, s);                 // strict <: equal distances keep the lower index first (ascending visits)
+    };
+    for (int w = 0; w < Wn; w++) {
+        unsigned m = bx[w] & by[w] & bz[w];
+        while (m) { visit((w << 5) + __ffs(m) - 1); m &= m - 1; }
+    }
+    if (!(t.d[2] <= ok_d)) {                  // a point outside the candidate set could be among the three: exhaustive scan
+        t.d[0] = t.d[1] = t.d[2] = INFINITY; t.i[0] = t.i[1] = t.i[2] = 0;
+        for (int s = 0; s < S; s++) visit(s);
+    }
+    const float r0 = __fdiv_rn(1.f, __fadd_rn(t.d[0], 1e-8f)), r1 = __fdiv_rn(1.f, __fadd_rn(t.d[1], 1e-8f)),
+                r2 = __fdiv_rn(1.f, __fadd_rn(t.d[2], 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    knn_i[(size_t)b * N + pi] = make_int4(t.i[0], t.i[1], t.i[2], 0);
+    knn_w[(size_t)b * N + pi] = make_float4(__fdiv_rn(r0, norm), __fdiv_rn(r1, norm), __fdiv_rn(r2, norm), 0.f);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_interp(const float *xyz1, int N, const float *xyz2, int S, const __half *feat1, int C1,
                                                 const __half *feat2, int C2, int B, __half *out, int4 *knn_i, float4 *knn_w) {
@@ -618,10 +865,12 @@ static int gemm_attr() {
     if (g_gemm_attr) return NIRRT_OK;
     PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PCUDA(cudaFuncSetAttribute(umma::k_gemm<umma::MODE_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    PCUDA(cudaFuncSetAttribute(k_ball_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    PCUDA(cudaFuncSetAttribute(k_ball_query, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    PCUDA(cudaFuncSetAttribute(k_ball_query_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
     PCUDA(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     PCUDA(cudaFuncSetAttribute(k_ball_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     PCUDA(cudaFuncSetAttribute(k_fps<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));   // 4096 points x 12 B + static
+    PCUDA(cudaFuncSetAttribute(k_fps_bucket<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     g_gemm_attr = true;
     return NIRRT_OK;
 }
@@ -718,6 +967,9 @@ struct nirrt_pn2 {
     cudaStream_t gs = nullptr, gs2 = nullptr;      // FPS chain | ball queries + 3-NN searches
     cudaEvent_t ev_fc[8] = {}, ev_bc[8] = {}, ev_fl[4] = {};      // level-1 FPS chunk / ball-query chunk done; FPS of a level done
     int l1_chunks = 1;
+    bool fps_bucket = false;                       // NIRRT_PN2_FPS_BUCKET = 1: bucket-pruned selection for the larger levels
+    bool bq_pruned = true, knn_pruned = true;     // slab-pruned ball query / 3-NN search (NIRRT_PN2_BQ / NIRRT_PN2_KNN = 0: exhaustive)
+    float knn_reach = 0.3f;                        // NIRRT_PN2_KNN_REACH: candidate radius of the pruned 3-NN search
     cudaEvent_t ev_fork = nullptr, ev_bq[4] = {nullptr, nullptr, nullptr, nullptr}, ev_knn[4] = {nullptr, nullptr, nullptr, nullptr};
     int4 *knn_i[4] = {nullptr, nullptr, nullptr, nullptr};      // per FP level: the three nearest coarse points of every fine point
     float4 *knn_w[4] = {nullptr, nullptr, nullptr, nullptr};    // and their normalised inverse-distance weights
@@ -878,6 +1130,10 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
         if (cudaStreamCreateWithFlags(&h->gs2, cudaStreamNonBlocking) != cudaSuccess) FAILC("nirrt_pn2_create: cudaStreamCreate failed");
         for (int i = 0; i < 8; i++) { cudaEventCreateWithFlags(&h->ev_fc[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_bc[i], cudaEventDisableTiming); }
         for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&h->ev_fl[i], cudaEventDisableTiming);
+        if (getenv("NIRRT_PN2_FPS_BUCKET")) h->fps_bucket = atoi(getenv("NIRRT_PN2_FPS_BUCKET")) != 0;
+        if (getenv("NIRRT_PN2_BQ")) h->bq_pruned = atoi(getenv("NIRRT_PN2_BQ")) != 0;
+        if (getenv("NIRRT_PN2_KNN")) h->knn_pruned = atoi(getenv("NIRRT_PN2_KNN")) != 0;
+        if (getenv("NIRRT_PN2_KNN_REACH")) { const float r = (float)atof(getenv("NIRRT_PN2_KNN_REACH")); if (r > 0.005f && r < 1.f) h->knn_reach = r; }
         const char *ch = getenv("NIRRT_PN2_CHUNKS");
         if (ch) { const int c = atoi(ch); h->l1_chunks = (c == 1 || c == 2 || c == 4 || c == 8) ? c : 1; }
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -971,6 +1227,20 @@ static int fps_launch(nirrt_pn2 *h, int B, int l, const int *start, cudaStream_t
     if (it1 < 0) it1 = np;
     const size_t smem = (size_t)N * 3 * sizeof(float);
     static const int cfg = getenv("NIRRT_FPS_CFG") ? atoi(getenv("NIRRT_FPS_CFG")) : 0;      // development knob: threads per cloud
+    if (h->fps_bucket && it0 == 0 && it1 == np && N > 512 && N <= 4096) {
+        // spatially pruned selection (whole-level launches of the larger levels)
+        const int nw = N > 2048 ? 8 : (N > 1024 ? 4 : 2);
+        const size_t cap = (size_t)32 * nw * 16;
+        const size_t sm = (size_t)N * 12 + (cap + (cap & 1)) * 2 + 513 * 4;
+#define FPSB_ARGS h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l]
+        if (nw == 8) k_fps_bucket<8><<<B, 256, sm, s>>>(FPSB_ARGS);
+        else if (nw == 4) k_fps_bucket<4><<<B, 128, sm, s>>>(FPSB_ARGS);
+        else k_fps_bucket<2><<<B, 64, sm, s>>>(FPSB_ARGS);
+#undef FPSB_ARGS
+        PCUDA(cudaGetLastError());
+        h->launches++;
+        return NIRRT_OK;
+    }
 #define FPS_ARGS h->xyz[l - 1], N, np, start, l - 1, h->fidx[l - 1], h->xyz[l], it0, it1, h->fps_dist, h->fps_far
     // Few fat threads: 16 independent points per thread hide the arithmetic latency, and few warps keep the one barrier
     // per selection step short.
@@ -999,8 +1269,17 @@ static int ball_query_launch(nirrt_pn2 *h, int B, int l, cudaStream_t s, int s0 
     const float r0 = (float)(kRad[l - 1][0] * kRad[l - 1][0]), r1 = (float)(kRad[l - 1][1] * kRad[l - 1][1]);
     if ((long long)B * S >= 65536) {
         const int bt = Sc >= 256 ? 256 : ((Sc + 31) / 32) * 32;
-        k_ball_query<<<dim3((Sc + bt - 1) / bt, B), bt, (size_t)(N + 1) * 4 * sizeof(float), s>>>(
-            h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1], s0, s1);
+        // rounding slack: the float32 expansion -2 a.b + |a|^2 + |b|^2 is within ~1e-6 of the true squared distance for
+        // coordinates in the unit ball, so a member is never farther than sqrt(r1^2 + 1e-5) from the centroid on any axis
+        const float reach = sqrtf(r1 + 1e-5f) * 1.0001f + 1e-6f;
+        if (h->bq_pruned && reach < 0.45f && N <= 32 * kSlabWordsMax) {
+            // one CTA per cloud where possible: every CTA builds the cloud's bitmaps for itself
+            const int pt = Sc >= 1024 ? 1024 : ((Sc + 31) / 32) * 32;
+            k_ball_query<<<dim3((Sc + pt - 1) / pt, B), pt, (size_t)N * 16 + (size_t)3 * kSlabs * ((N + 31) / 32 + 1) * 4, s>>>(
+                h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1], s0, s1, reach);
+        } else
+            k_ball_query_bf<<<dim3((Sc + bt - 1) / bt, B), bt, (size_t)(N + 1) * 4 * sizeof(float), s>>>(
+                h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1], s0, s1);
     } else {
         k_ball_query_warp<<<dim3((Sc + 7) / 8, B), 256, (size_t)N * 4 * sizeof(float), s>>>(
             h->xyz[l - 1], N, h->xyz[l], S, r0, kK[0], r1, kK[1], h->grp[(l - 1) * 2], h->grp[(l - 1) * 2 + 1], s0, s1);
@@ -1024,7 +1303,13 @@ static int interp_launch(nirrt_pn2 *h, int B, int f, int mode, const __half *upf
         const dim3 grid((N + bt - 1) / bt, B);
         const size_t smem = (size_t)S * sizeof(float4);
         if (mode == 0) k_interp<0><<<grid, bt, smem, s>>>(INTERP_ARGS);
-        else if (mode == 1) k_interp<1><<<grid, bt, smem, s>>>(INTERP_ARGS);
+        else if (mode == 1 && h->knn_pruned && S >= 512 && S <= 32 * kSlabWordsMax) {
+            // the coarse level holds S FPS-spread points of the unit ball: the third-nearest is almost always within 0.3
+            const float reach = h->knn_reach, ok_d = reach * reach - 1e-5f;
+            const int pt = N >= 512 ? 512 : ((N + 31) / 32) * 32;
+            k_knn_pruned<<<dim3((N + pt - 1) / pt, B), pt, (size_t)S * 16 + (size_t)3 * kSlabs * ((S + 31) / 32 + 1) * 4, s>>>(
+                h->xyz[lo], N, h->xyz[lo + 1], S, h->knn_i[f], h->knn_w[f], reach, ok_d);
+        } else if (mode == 1) k_interp<1><<<grid, bt, smem, s>>>(INTERP_ARGS);
         else k_interp<2><<<grid, bt, 0, s>>>(INTERP_ARGS);
     } else {
         if (mode == 0) k_interp_warp<0><<<(rows + 7) / 8, 256, 0, s>>>(INTERP_ARGS);

@@ -36,8 +36,9 @@ def test_fps_squares_are_rounded_before_they_are_summed(sass):
 
 
 def test_pair_distance_kernels_use_the_packed_fp32_pipe(sass):
-    """query_ball_point / the 3-NN search evaluate -2 * (a . b) + |a|^2 + |b|^2 two points per instruction."""
-    bq = [b for n, b in sass.items() if n.startswith("_Z12k_ball_queryPKf")]
+    """the exhaustive query_ball_point scan and the 3-NN search evaluate -2 * (a . b) + |a|^2 + |b|^2 two points per
+    instruction."""
+    bq = [b for n, b in sass.items() if n.startswith("_Z15k_ball_query_bfPKf")]
     knn = [b for n, b in sass.items() if n.startswith("_Z8k_interpILi1EE")]
     assert len(bq) == 1 and len(knn) == 1
     for b in bq + knn:

@@ -217,3 +217,38 @@ def test_retargeted_engine_equals_dedicated_engine():
     with pytest.raises(Exception):
         b.set_n_points(4096)
     a.close(); b.close()
+
+
+def test_pruned_geometry_equals_the_exhaustive_scans(monkeypatch):
+    """The bucket-pruned farthest point sampling (selected indices of every level), the slab-pruned ball query and 3-NN search (bitmaps of the points near each coordinate slab, candidates visited in index
+    order, the reference's float32 test on each) must select exactly what the exhaustive scans select: group indices of every
+    level and the network's outputs bit for bit -- also when the 3-NN candidate radius is so small that nearly every query
+    falls back to the exhaustive scan, and on clouds squeezed into a corner of the normalised cube (end slabs)."""
+    from nirrt_star_b200.pointnet2 import PointNet2Engine
+    sd = make_pointnet2_state(0)
+    clouds = [make_cloud_3d(i) for i in range(6)]
+    pc = np.stack([c[0] for c in clouds]); sm = np.stack([c[1] for c in clouds]); gm = np.stack([c[2] for c in clouds])
+    rs = np.random.RandomState(3)
+    pc[4] = pc[4] * np.array([1.0, 0.02, 0.3], dtype=np.float32)             # a thin slab of a cloud
+    pc[5, 1000:] = pc[5, 1000:] * 0.01 + 40.0                                 # two far-apart clusters
+    fs = np.stack([rs.randint(0, n, 6) for n in (2048, 1024, 256, 64)], 1).astype(np.int32)
+
+    def run(env):
+        for k in ("NIRRT_PN2_BQ", "NIRRT_PN2_KNN", "NIRRT_PN2_KNN_REACH", "NIRRT_PN2_FPS_BUCKET"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = PointNet2Engine(sd, n_points=2048, max_batch=6)
+        out = e.classify(pc, sm, gm, fps_start=fs, return_logp=True)
+        groups = [e.read_buffer(f"group{g}", np.int32, (6, (1024, 256, 64, 16)[g // 2], (16, 32)[g & 1])).copy() for g in range(8)]
+        groups += [e.read_buffer(f"fps{l}", np.int32, (6, (1024, 256, 64, 16)[l])).copy() for l in range(4)]
+        e.close()
+        return out, groups
+
+    want, gw = run({"NIRRT_PN2_BQ": "0", "NIRRT_PN2_KNN": "0", "NIRRT_PN2_FPS_BUCKET": "0"})
+    for env in ({}, {"NIRRT_PN2_KNN_REACH": "0.02"}, {"NIRRT_PN2_KNN_REACH": "0.9", "NIRRT_PN2_FPS_BUCKET": "1"}):
+        got, gg = run(env)
+        for a, b in zip(gg, gw):
+            assert np.array_equal(a, b), env
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), env
