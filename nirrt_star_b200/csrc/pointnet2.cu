@@ -948,6 +948,8 @@ struct nirrt_pn2 {
     int *fps_far = nullptr;         // [maxB]
     int *grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     __half *bufA = nullptr, *bufB = nullptr;
+    uint8_t *fp_img = nullptr;      // fused fp1 + conv1 + head kernel: four 128 x 128 weight images (null: layer by layer)
+    float *fp_bias = nullptr;
     uint8_t *sa_img[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // fused sa1 / sa2 kernels: swizzled weight
     float *sa_bias[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};    // images + biases per level and radius
     int fused_levels = 2;                                               // 0: none, 1: sa1, 2: sa1 + sa2
@@ -1170,6 +1172,28 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
                     cudaMemcpy(h->sa_bias[l][sc], bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
                     FAILC("fused SA: weight image upload failed");
             }
+        {
+            const char *ff = getenv("NIRRT_PN2_FP_FUSED");
+            bool ok = !(ff && atoi(ff) == 0);
+            for (int j = 30; j < 34; j++) ok = ok && h->conv[j].K == safused::kFpC && h->conv[j].N == safused::kFpC;
+            if (ok) {
+                std::vector<uint8_t> img((size_t)4 * 32768, 0);
+                std::vector<float> bias;
+                for (int j = 0; j < 4; j++) {
+                    const Conv &c = h->conv[30 + j];
+                    for (int n = 0; n < c.N; n++)
+                        for (int k = 0; k < c.K; k++)
+                            memcpy(&img[(size_t)j * 32768 + safused::w_off(c.N, n, k >> 3) + (k & 7) * 2], &c.hw[(size_t)n * c.K + k], 2);
+                    bias.insert(bias.end(), c.hb.begin(), c.hb.end());
+                }
+                TRYC(palloc(h, &h->fp_img, img.size()));
+                TRYC(palloc(h, &h->fp_bias, bias.size()));
+                if (cudaMemcpy(h->fp_img, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaMemcpy(h->fp_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaFuncSetAttribute(safused::k_fp1_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)safused::kFpSmem) != cudaSuccess)
+                    FAILC("fused fp1: weight image upload failed");
+            }
+        }
         if (h->fused_levels >= 2) {
             if (cudaFuncSetAttribute(safused::k_sa_fused<16, 96, 112, 64, 64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)safused::Smem<112, 64, 64, 128>::kTotal) != cudaSuccess ||
@@ -1467,6 +1491,27 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
     for (int f = 0; f < 4; f++) {
         const int lo = 3 - f;
         const int rows = B * h->n[lo];
+        if (f == 3 && h->fp_img) {
+            // fp1 (3-NN interpolation + three 128-wide layers), conv1 and the head in one kernel (sa_fused.cuh)
+            {
+                StageTimer t(h, s, 5);
+                if (split) PCUDA(cudaStreamWaitEvent(s, h->ev_knn[f], 0));
+                else PTRY(interp_launch(h, B, f, 1, nullptr, 0, s));      // indices / weights only
+            }
+            StageTimer t(h, s, 6);
+            safused::FpArgs fa;
+            fa.feat2 = upf; fa.knn_i = h->knn_i[f]; fa.knn_w = h->knn_w[f]; fa.wimg = h->fp_img; fa.bias = h->fp_bias;
+            fa.w2 = h->w2; fa.b2 = h->b2; fa.pred = (long long *)path_pred; fa.score = path_score; fa.logp = logp;
+            fa.N = h->n[0]; fa.S = h->n[1]; fa.rows = (unsigned)rows;
+            if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
+            const int pairs = (rows + 255) / 256;
+            safused::k_fp1_fused<<<pairs < g_num_sms ? pairs : g_num_sms, 256, safused::kFpSmem, s>>>(fa);
+            PCUDA(cudaGetLastError());
+            h->launches++;
+            trace_mark("fp1_fused", 0, 0, s);
+            trace_dump();
+            return NIRRT_OK;
+        }
         {
             StageTimer t(h, s, 5);
             if (split) PCUDA(cudaStreamWaitEvent(s, h->ev_knn[f], 0));

@@ -55,19 +55,23 @@ __device__ __forceinline__ void split_hi_lo(float x, __half &hi, __half &lo) {
 // accumulator row -> relu(. + bias) -> fp16 -> this thread's row of the next operand tile
 template <int NCOLS>
 __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, uint8_t *sA, int r, const float *bias) {
+    constexpr int W = NCOLS % 32 == 0 ? 32 : 16;          // accumulator columns per TMEM round trip
 #pragma unroll 1
-    for (int h = 0; h < NCOLS; h += 16) {
-        uint32_t u[16];
-        umma::tmem_ld16(taddr + h, u);
-        uint32_t p[8];
+    for (int h = 0; h < NCOLS; h += W) {
+        uint32_t u[W];
+        if (W == 32) umma::tmem_ld32(taddr + h, u);
+        else umma::tmem_ld16(taddr + h, u);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float a = fmaxf(__uint_as_float(u[2 * i]) + bias[h + 2 * i], 0.f);
-            const float b = fmaxf(__uint_as_float(u[2 * i + 1]) + bias[h + 2 * i + 1], 0.f);
-            p[i] = umma::pack_half2_sat(a, b);
+        for (int q = 0; q < W; q += 8) {
+            uint32_t p[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float a = fmaxf(__uint_as_float(u[q + 2 * i]) + bias[h + q + 2 * i], 0.f);
+                const float b = fmaxf(__uint_as_float(u[q + 2 * i + 1]) + bias[h + q + 2 * i + 1], 0.f);
+                p[i] = umma::pack_half2_sat(a, b);
+            }
+            *reinterpret_cast<uint4 *>(sA + a_off(r, (h + q) >> 3)) = make_uint4(p[0], p[1], p[2], p[3]);
         }
-        *reinterpret_cast<uint4 *>(sA + a_off(r, h >> 3)) = make_uint4(p[0], p[1], p[2], p[3]);
-        *reinterpret_cast<uint4 *>(sA + a_off(r, (h >> 3) + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
     }
 }
 
@@ -169,6 +173,9 @@ __global__ void __launch_bounds__(128) k_sa_fused(const Args a) {
                 *reinterpret_cast<uint4 *>(sA + a_off(tid, 0)) = *reinterpret_cast<uint4 *>(h);
                 *reinterpret_cast<uint4 *>(sA + a_off(tid, 1)) = *reinterpret_cast<uint4 *>(h + 8);
             } else {
+                // thread-per-row gather: 12-14 independent 16-byte loads in flight per thread.  (A warp-cooperative walk with
+                // whole rows per load instruction, as in k_fp1_fused, was measured 0.47 ms SLOWER here: with 2-3 CTAs per SM
+                // the memory-level parallelism of the per-thread version matters more than the coalescing.)
                 const uint4 *src = reinterpret_cast<const uint4 *>(a.feat + ((size_t)b * a.N + i) * C);
 #pragma unroll
                 for (int cc = 0; cc < C / 8; cc++) *reinterpret_cast<uint4 *>(sA + a_off(tid, cc)) = __ldg(src + cc);
@@ -239,6 +246,171 @@ __global__ void __launch_bounds__(128) k_sa_fused(const Args a) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp1 + classifier head as ONE persistent kernel (PointNetFeaturePropagation pointnet2_utils.py:278-317 for l0 <- l1, then
+// conv1 + bn1 + relu and conv2 + log_softmax, pointnet2.py:33-41): per tile of 128 fine points the 3-NN interpolation of the
+// level-1 features (indices / weights from the 3-NN search) is the operand producer, four 128 x 128 layers run back to back
+// with the activations in shared memory / TMEM, and the last epilogue applies the 128 -> 2 head.  The four round trips of
+// [rows][128] fp16 activations through HBM of the layer-by-layer path (1.3 GB per forward of 256 clouds) disappear; every
+// rounding point (fp16 operand, fp16 activations, fp32 head in channel order) is the one of the un-fused kernels.
+// 256 threads = two independent halves of 128 (thread = row = TMEM lane; half h owns operand tile h and TMEM columns
+// [128 h, 128 h + 128)) that share the weight images: one half's gather overlaps the other's layers.
+struct FpArgs {
+    const __half *feat2;    // [B][S][128] level-1 features after fp2
+    const int4 *knn_i;      // [B][N] three nearest level-1 points of every level-0 point
+    const float4 *knn_w;    // [B][N] their normalised inverse-distance weights
+    const uint8_t *wimg;    // 4 weight images (fp1 conv 0..2, conv1), 128 rows x 2 blocks x 128 bytes each
+    const float *bias;      // [4][128]
+    const float *w2, *b2;   // head [2][128], [2]
+    long long *pred;        // [B * N]
+    float *score, *logp;    // [B * N], [B * N][2] or null
+    int N, S;
+    unsigned rows;          // B * N
+};
+constexpr int kFpC = 128;
+constexpr size_t kFpSmem = 1024 + 2 * 32768 + 4 * 32768 + (4 * kFpC + 2 * kFpC + 2) * 4 + 64;
+
+__device__ __forceinline__ void half_sync(int half) { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); }
+
+__global__ void __launch_bounds__(256, 1) k_fp1_fused(const FpArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    const int tid = threadIdx.x, half = tid >> 7, t = tid & 127, warp = tid >> 5, lane = tid & 31;
+    uint8_t *sA = smem + half * 32768;                       // this half's operand tile
+    uint8_t *sW = smem + 2 * 32768;                          // 4 x 32 KB
+    float *s_bias = reinterpret_cast<float *>(sW + 4 * 32768);
+    float *s_w2 = s_bias + 4 * kFpC;                         // [2][128] + [2]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_w2 + 2 * kFpC + 2);      // one per half
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bar + 2);
+    if (tid == 0) {
+        umma::mbar_init(bar, 1); umma::mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.wimg);
+        uint4 *dst = reinterpret_cast<uint4 *>(sW);
+        for (int i = tid; i < 4 * 32768 / 16; i += 256) dst[i] = src[i];
+        for (int i = tid; i < 4 * kFpC; i += 256) s_bias[i] = a.bias[i];
+        for (int i = tid; i < 2 * kFpC; i += 256) s_w2[i] = a.w2[i];
+        if (tid < 2) s_w2[2 * kFpC + tid] = a.b2[tid];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr + (uint32_t)half * 128u;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t sa_u = smem_u32(sA), sw_u = smem_u32(sW);
+    uint64_t *mybar = bar + half;
+    uint32_t phase = 0;
+    const unsigned ntiles = (a.rows + 127u) / 128u;
+
+#define FP_LAYER_SYNC()                                                   \
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          \
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      \
+    half_sync(half);
+#define FP_WAIT()                                                         \
+    umma::mbar_wait(mybar, phase); phase ^= 1u;                           \
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    for (unsigned tile = blockIdx.x * 2u + (unsigned)half; tile < ntiles; tile += gridDim.x * 2u) {
+        const unsigned r = tile * 128u + (unsigned)t;
+        const bool valid = r < a.rows;
+        // ---- operand: interpolated level-1 features, (a0 * w0 + a1 * w1) + a2 * w2 in fp32 -> fp16.  Warp-cooperative: the
+        // warp walks its 32 rows two at a time, 16 lanes per row, one 16-byte chunk per lane -- every load instruction reads
+        // whole 256-byte feature rows (a thread-per-row gather touches 32 different rows per instruction).
+        {
+            int4 ki = make_int4(0, 0, 0, 0);
+            float4 kw = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned base = 0u;                 // first feature row of this point's cloud
+            if (valid) { ki = a.knn_i[r]; kw = a.knn_w[r]; base = (r / (unsigned)a.N) * (unsigned)a.S; }
+            const int sub = lane >> 4, cc = lane & 15;
+#pragma unroll 4
+            for (int j = 0; j < 32; j += 2) {
+                const int src = j + sub;
+                const unsigned rb = __shfl_sync(0xffffffffu, base, src);
+                const int n0 = __shfl_sync(0xffffffffu, ki.x, src), n1 = __shfl_sync(0xffffffffu, ki.y, src), n2 = __shfl_sync(0xffffffffu, ki.z, src);
+                const float w0 = __shfl_sync(0xffffffffu, kw.x, src), w1 = __shfl_sync(0xffffffffu, kw.y, src), w2 = __shfl_sync(0xffffffffu, kw.z, src);
+                const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(a.feat2 + ((size_t)rb + n0) * kFpC) + cc);
+                const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(a.feat2 + ((size_t)rb + n1) * kFpC) + cc);
+                const uint4 q2 = __ldg(reinterpret_cast<const uint4 *>(a.feat2 + ((size_t)rb + n2) * kFpC) + cc);
+                const __half2 *h0 = reinterpret_cast<const __half2 *>(&q0), *h1 = reinterpret_cast<const __half2 *>(&q1),
+                              *h2 = reinterpret_cast<const __half2 *>(&q2);
+                uint4 o;
+                __half2 *ho = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float2 a0 = __half22float2(h0[e]), a1 = __half22float2(h1[e]), a2 = __half22float2(h2[e]);
+                    const float x = __fadd_rn(__fadd_rn(__fmul_rn(a0.x, w0), __fmul_rn(a1.x, w1)), __fmul_rn(a2.x, w2));
+                    const float y = __fadd_rn(__fadd_rn(__fmul_rn(a0.y, w0), __fmul_rn(a1.y, w1)), __fmul_rn(a2.y, w2));
+                    ho[e] = __floats2half2_rn(fminf(x, 65504.f), fminf(y, 65504.f));
+                }
+                // rows past the end carry weights 0 and neighbour 0 of cloud 0: finite values that nobody reads
+                *reinterpret_cast<uint4 *>(sA + a_off((warp & 3) * 32 + src, cc)) = o;
+            }
+        }
+        // ---- fp1 conv 0..2
+#pragma unroll 1
+        for (int l = 0; l < 3; l++) {
+            FP_LAYER_SYNC()
+            if (t == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue<kFpC, kFpC>(tmem_base, sa_u, sw_u + l * 32768, mybar);
+            }
+            FP_WAIT()
+            epilogue_to_operand<kFpC>(taddr, sA, t, s_bias + l * kFpC);
+        }
+        // ---- conv1 + bn1 + relu, then the 128 -> 2 head on the fp16-rounded activations in channel order
+        FP_LAYER_SYNC()
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue<kFpC, kFpC>(tmem_base, sa_u, sw_u + 3 * 32768, mybar);
+        }
+        FP_WAIT()
+        float z0 = 0.f, z1 = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < kFpC; h += 32) {
+            uint32_t u[32];
+            umma::tmem_ld32(taddr + h, u);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const float x0 = fmaxf(__uint_as_float(u[i]) + s_bias[3 * kFpC + h + i], 0.f);
+                const float x1 = fmaxf(__uint_as_float(u[i + 1]) + s_bias[3 * kFpC + h + i + 1], 0.f);
+                const uint32_t pk = umma::pack_half2_sat(x0, x1);
+                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&pk));
+                z0 = fmaf(f.x, s_w2[h + i], z0); z0 = fmaf(f.y, s_w2[h + i + 1], z0);
+                z1 = fmaf(f.x, s_w2[kFpC + h + i], z1); z1 = fmaf(f.y, s_w2[kFpC + h + i + 1], z1);
+            }
+        }
+        if (valid) {
+            z0 += s_w2[2 * kFpC]; z1 += s_w2[2 * kFpC + 1];
+            const float m = fmaxf(z0, z1);
+            const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
+            const float l0 = z0 - lse, l1 = z1 - lse;
+            if (a.logp) { a.logp[(size_t)r * 2] = l0; a.logp[(size_t)r * 2 + 1] = l1; }
+            a.pred[r] = (l1 > l0) ? 1 : 0;
+            const float e0 = expf(l0), e1 = expf(l1);
+            a.score[r] = e1 / (e0 + e1);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        half_sync(half);          // every thread of the half has read its accumulator row before the next tile's first MMA
+    }
+#undef FP_LAYER_SYNC
+#undef FP_WAIT
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_ptr), "n"(256) : "memory");
     }
 }
 
