@@ -43,6 +43,11 @@ int nirrt_version(void);
 /* number of visible CUDA devices with compute capability 10.x; <= 0 means the library cannot run */
 int nirrt_device_count(void);
 
+/* Device blocks freed by batches / engines / temporaries are kept in a process-wide cache (exact size match per device,
+ * at most NIRRT_CACHE_GB gigabytes, default 32; 0 disables) and handed out again zero-filled, so that repeated create /
+ * destroy cycles of equal shape cost no driver allocation calls.  This returns the idle blocks to the driver. */
+int nirrt_release_cached_memory(void);
+
 typedef struct nirrt_batch nirrt_batch;
 
 typedef struct nirrt_batch_desc {

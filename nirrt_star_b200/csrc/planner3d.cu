@@ -28,7 +28,11 @@
 #include <stdio.h>
 #include <string.h>
 #include <limits.h>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/nirrt_b200.h"
@@ -43,6 +47,7 @@ using namespace nirrt;
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 #include "errors.h"
+#include "devmem.h"
 static thread_local std::string g_err;
 int nirrt_set_error(int code, const std::string &msg) { g_err = msg; return code; }
 static int fail(int code, const std::string &msg) { return nirrt_set_error(code, msg); }
@@ -69,6 +74,80 @@ extern "C" int nirrt_device_count(void) {
     }
     cached = ok;
     return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device memory cache (devmem.h)
+namespace {
+struct DevCache {
+    std::mutex mu;
+    std::unordered_map<void *, std::pair<size_t, int>> live;                   // block -> (bytes, device)
+    std::multimap<std::pair<int, size_t>, void *> idle;                         // (device, bytes) -> block
+    size_t idle_bytes = 0, cap = (size_t)32 << 30;
+    DevCache() {
+        const char *e = getenv("NIRRT_CACHE_GB");                               // 0 disables the cache
+        if (e) cap = (size_t)(atof(e) * 1073741824.0);
+    }
+    void drop_idle() {                                                          // mu held
+        for (auto &kv : idle) cudaFree(kv.second);
+        idle.clear(); idle_bytes = 0;
+    }
+};
+DevCache &dev_cache() { static DevCache c; return c; }
+}  // namespace
+
+cudaError_t nirrt_dev_malloc(void **p, size_t bytes) {
+    DevCache &c = dev_cache();
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> g(c.mu);
+        auto it = c.idle.find({dev, bytes});
+        if (it != c.idle.end()) {
+            *p = it->second;
+            c.idle.erase(it);
+            c.idle_bytes -= bytes;
+            c.live[*p] = {bytes, dev};
+        } else *p = nullptr;
+    }
+    if (*p) {                                       // a recycled block looks like a fresh one: zero-filled
+        e = cudaMemset(*p, 0, bytes);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        return e;
+    }
+    e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {           // give the cached blocks back and try once more
+        cudaGetLastError();
+        { std::lock_guard<std::mutex> g(c.mu); c.drop_idle(); }
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> g(c.mu); c.live[*p] = {bytes, dev}; }
+    return e;
+}
+
+void nirrt_dev_free(void *p) {
+    if (!p) return;
+    DevCache &c = dev_cache();
+    cudaDeviceSynchronize();                        // cudaFree's contract: nothing in flight uses the block any more
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) { cudaFree(p); return; }
+    const size_t bytes = it->second.first;
+    const int dev = it->second.second;
+    c.live.erase(it);
+    if (c.idle_bytes + bytes > c.cap) { cudaFree(p); return; }
+    c.idle.insert({{dev, bytes}, p});
+    c.idle_bytes += bytes;
+}
+
+extern "C" int nirrt_release_cached_memory(void) {
+    DevCache &c = dev_cache();
+    std::lock_guard<std::mutex> g(c.mu);
+    c.drop_idle();
+    return NIRRT_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2903,19 +2982,19 @@ static int ensure_staging(nirrt_batch *b) {
     if (envs > (size_t)v.E) envs = v.E;
     b->stage_envs = (int)envs;
     for (int i = 0; i < 2; i++) {
-        CUDA_TRY(cudaMalloc(&b->stage[i], envs * per_env));
+        CUDA_TRY(nirrt_dev_malloc(&b->stage[i], envs * per_env));
         b->allocs.push_back(b->stage[i]);
         CUDA_TRY(cudaStreamCreateWithFlags(&b->xs[i], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&b->xe[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&b->xfork, cudaEventDisableTiming));
-    CUDA_TRY(cudaMalloc((void **)&b->stage_n, sizeof(int) * v.E));
+    CUDA_TRY(nirrt_dev_malloc((void **)&b->stage_n, sizeof(int) * v.E));
     b->allocs.push_back(b->stage_n);
     return NIRRT_OK;
 }
 
 static int dalloc(nirrt_batch *b, void **p, size_t bytes) {
-    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    cudaError_t e = nirrt_dev_malloc(p, bytes ? bytes : 16);
     if (e != cudaSuccess) return fail(NIRRT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     b->allocs.push_back(*p);
     return NIRRT_OK;
@@ -2939,7 +3018,7 @@ static int pick_chunks(int E) {
 extern "C" int nirrt_batch_destroy(nirrt_batch *b) {
     if (!b) return NIRRT_OK;
     cudaSetDevice(b->device);
-    for (void *p : b->allocs) cudaFree(p);
+    for (void *p : b->allocs) nirrt_dev_free(p);
     if (b->h_ctl) cudaFreeHost(b->h_ctl);
     free(b->cloud_ws);
     for (int g = 0; g < kMaxGroups; g++) {
@@ -3094,10 +3173,10 @@ static int ensure_goal_lists(nirrt_batch *b) {
 // copies a host array to a temporary device buffer on `s` (freed after the stream is drained by the caller)
 struct TempBufs {
     std::vector<void *> ptrs;
-    ~TempBufs() { for (void *p : ptrs) cudaFree(p); }
+    ~TempBufs() { for (void *p : ptrs) nirrt_dev_free(p); }
     template <typename T> int up(const T *host, size_t count, cudaStream_t s, T **dev) {
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+        cudaError_t e = nirrt_dev_malloc(&p, sizeof(T) * (count ? count : 1));
         if (e != cudaSuccess) return fail(NIRRT_ERR_CUDA, std::string("cudaMalloc(temp): ") + cudaGetErrorString(e));
         ptrs.push_back(p);
         if (count) {
@@ -3109,7 +3188,7 @@ struct TempBufs {
     }
     template <typename T> int make(size_t count, T **dev) {
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+        cudaError_t e = nirrt_dev_malloc(&p, sizeof(T) * (count ? count : 1));
         if (e != cudaSuccess) return fail(NIRRT_ERR_CUDA, std::string("cudaMalloc(temp): ") + cudaGetErrorString(e));
         ptrs.push_back(p);
         *dev = (T *)p;

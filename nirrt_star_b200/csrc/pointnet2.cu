@@ -26,6 +26,7 @@
 #include "../../include/nirrt_b200.h"
 #include "../../include/nirrt_pointnet2.h"
 #include "errors.h"
+#include "devmem.h"
 #include "umma_gemm.cuh"
 #include "sa_fused.cuh"
 
@@ -981,7 +982,7 @@ struct nirrt_pn2 {
 template <typename T>
 static int palloc(nirrt_pn2 *h, T **p, size_t count) {
     void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
+    cudaError_t e = nirrt_dev_malloc(&q, sizeof(T) * (count ? count : 1));
     if (e != cudaSuccess) return pfail(NIRRT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     h->allocs.push_back(q);
     *p = (T *)q;
@@ -1026,7 +1027,7 @@ static std::vector<int> identity_remap(int c_in) {
 extern "C" int nirrt_pn2_destroy(nirrt_pn2 *h) {
     if (!h) return NIRRT_OK;
     cudaSetDevice(h->device);
-    for (void *p : h->allocs) cudaFree(p);
+    for (void *p : h->allocs) nirrt_dev_free(p);
     for (int i = 0; i < 2; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->gs) cudaStreamDestroy(h->gs);
     if (h->gs2) cudaStreamDestroy(h->gs2);
