@@ -1196,10 +1196,10 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
             }
         }
         if (h->fused_levels >= 2) {
-            if (cudaFuncSetAttribute(safused::k_sa_fused<16, 96, 112, 64, 64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)safused::Smem<112, 64, 64, 128>::kTotal) != cudaSuccess ||
-                cudaFuncSetAttribute(safused::k_sa_fused<32, 96, 112, 64, 96, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)safused::Smem<112, 64, 96, 128>::kTotal) != cudaSuccess)
+            if (cudaFuncSetAttribute(safused::k_sa_fused<16, 96, 112, 64, 64, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)safused::Smem<112, 64, 64, 128>::total(4)) != cudaSuccess ||
+                cudaFuncSetAttribute(safused::k_sa_fused<32, 96, 112, 64, 96, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)safused::Smem<112, 64, 96, 128>::total(4)) != cudaSuccess)
                 FAILC("fused SA: cudaFuncSetAttribute failed");
         }
     }
@@ -1437,12 +1437,15 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
                     fa.tpc = S * K / 128; fa.chunk_tiles = fa.tpc / nc; fa.chunk_lo = c * fa.chunk_tiles;
                     if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
                     const int ntiles = B * fa.chunk_tiles;
-                    const int cps = l == 1 ? 8 : (sc == 0 ? 3 : 2);
-                    const int grid = ntiles < g_num_sms * cps ? ntiles : g_num_sms * cps;
-                    if (l == 1 && sc == 0) safused::k_sa_fused<16, 0, 16, 16, 16, 32><<<grid, 128, safused::Smem<16, 16, 16, 32>::kTotal, s>>>(fa);
-                    else if (l == 1) safused::k_sa_fused<32, 0, 16, 32, 32, 64><<<grid, 128, safused::Smem<16, 32, 32, 64>::kTotal, s>>>(fa);
-                    else if (sc == 0) safused::k_sa_fused<16, 96, 112, 64, 64, 128><<<grid, 128, safused::Smem<112, 64, 64, 128>::kTotal, s>>>(fa);
-                    else safused::k_sa_fused<32, 96, 112, 64, 96, 128><<<grid, 128, safused::Smem<112, 64, 96, 128>::kTotal, s>>>(fa);
+                    // sa1: 8 CTAs of one tile per SM (tensor memory is the limit); sa2: one CTA of four tiles per SM (its weight
+                    // images are shared by the four groups)
+                    const int units = l == 1 ? ntiles : (ntiles + 3) / 4;
+                    const int cps = l == 1 ? 8 : 1;
+                    const int grid = units < g_num_sms * cps ? units : g_num_sms * cps;
+                    if (l == 1 && sc == 0) safused::k_sa_fused<16, 0, 16, 16, 16, 32, 1><<<grid, 128, safused::Smem<16, 16, 16, 32>::kTotal, s>>>(fa);
+                    else if (l == 1) safused::k_sa_fused<32, 0, 16, 32, 32, 64, 1><<<grid, 128, safused::Smem<16, 32, 32, 64>::kTotal, s>>>(fa);
+                    else if (sc == 0) safused::k_sa_fused<16, 96, 112, 64, 64, 128, 4><<<grid, 512, safused::Smem<112, 64, 64, 128>::total(4), s>>>(fa);
+                    else safused::k_sa_fused<32, 96, 112, 64, 96, 128, 4><<<grid, 512, safused::Smem<112, 64, 96, 128>::total(4), s>>>(fa);
                     PCUDA(cudaGetLastError());
                     h->launches++;
                     trace_mark(sc ? "sa_fused1" : "sa_fused0", l, c, s);

@@ -95,57 +95,69 @@ struct Smem {
     static constexpr int kW1 = N1 * nblk(K0) * 128, kW2 = N2 * nblk(N1) * 128, kW3 = N3 * nblk(N2) * 128;
     static constexpr int kBias = (N1 + N2 + N3 + 2) * 4;
     static constexpr size_t kTotal = 1024 + (size_t)kABytes + kW1 + kW2 + kW3 + kBias + 64;
+    static constexpr size_t total(int ng) { return kTotal + (size_t)(ng - 1) * kABytes; }      // ng groups per CTA
 };
 
 // C == 0: sa1 (in6 input); C > 0: features [.,C] of the previous level + relative coordinates
-template <int G, int C, int K0, int N1, int N2, int N3>
-__global__ void __launch_bounds__(128) k_sa_fused(const Args a) {
+// NG: independent groups of 128 threads per CTA (thread = row = TMEM lane of its group's tile).  The groups share the weight
+// images and each owns an operand tile, an mbarrier and TCOLS accumulator columns: where the weights are what limits the number
+// of CTAs per SM (sa2: 40-60 KB of weights next to a 32 KB tile), NG = 4 keeps four tiles in flight per SM instead of two or
+// three, so that one group's gather and epilogues overlap the others' round trips.
+template <int G, int C, int K0, int N1, int N2, int N3, int NG>
+__global__ void __launch_bounds__(128 * NG) k_sa_fused(const Args a) {
     typedef Smem<K0, N1, N2, N3> SM;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-    uint8_t *sA = smem;                                   // operand tile (also the pooling scratch)
-    uint8_t *sW1 = sA + SM::kABytes, *sW2 = sW1 + SM::kW1, *sW3 = sW2 + SM::kW2;
+    const int grp = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5, lane = tid & 31;      // within the group
+    uint8_t *sA = smem + grp * SM::kABytes;               // this group's operand tile (also its pooling scratch)
+    uint8_t *sW1 = smem + NG * SM::kABytes, *sW2 = sW1 + SM::kW1, *sW3 = sW2 + SM::kW2;
     float *s_bias = reinterpret_cast<float *>(sW3 + SM::kW3);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_bias) + SM::kBias);
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t *bar0 = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_bias) + SM::kBias);
+    uint64_t *bar = bar0 + grp;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bar0 + NG);
     constexpr int NMAX = imax(imax(N1, N2), N3);
     constexpr int TCOLS = NMAX <= 32 ? 32 : (NMAX <= 64 ? 64 : (NMAX <= 128 ? 128 : 256));
+    static_assert(TCOLS * NG <= 512, "tensor memory holds 512 columns");
 
-    if (tid == 0) {
-        umma::mbar_init(bar, 1);
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < NG; g++) umma::mbar_init(bar0 + g, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (threadIdx.x < 32) {
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TCOLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TCOLS * NG) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.wimg);
         uint4 *dst = reinterpret_cast<uint4 *>(sW1);
-        for (int i = tid; i < (SM::kW1 + SM::kW2 + SM::kW3) / 16; i += 128) dst[i] = src[i];
-        for (int i = tid; i < N1 + N2 + N3; i += 128) s_bias[i] = a.bias[i];
+        for (int i = threadIdx.x; i < (SM::kW1 + SM::kW2 + SM::kW3) / 16; i += 128 * NG) dst[i] = src[i];
+        for (int i = threadIdx.x; i < N1 + N2 + N3; i += 128 * NG) s_bias[i] = a.bias[i];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_all = *tmem_ptr;
+    const uint32_t tmem_base = tmem_all + (uint32_t)(grp * TCOLS);
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t sa_u = smem_u32(sA), sw1_u = smem_u32(sW1), sw2_u = smem_u32(sW2), sw3_u = smem_u32(sW3);
     uint32_t phase = 0;
     const int nvt = a.B * a.chunk_tiles;
+    auto group_sync = [&]() {
+        if (NG == 1) __syncthreads();
+        else asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+    };
 
 #define SA_LAYER_SYNC()                                                   \
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          \
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      \
-    __syncthreads();
+    group_sync();
 #define SA_WAIT()                                                         \
     umma::mbar_wait(bar, phase); phase ^= 1u;                             \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    for (int vt = blockIdx.x; vt < nvt; vt += gridDim.x) {
+    for (int vt = blockIdx.x * NG + grp; vt < nvt; vt += gridDim.x * NG) {
         const int tile = (vt / a.chunk_tiles) * a.tpc + a.chunk_lo + vt % a.chunk_tiles;
         // ---- grouping: this thread's row (pointnet2_utils.py:246-253)
         {
@@ -236,16 +248,16 @@ __global__ void __launch_bounds__(128) k_sa_fused(const Args a) {
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();          // pooling scratch (aliasing the operand tile) is free before the next gather
+        group_sync();             // pooling scratch (aliasing the operand tile) is free before the next gather
     }
 #undef SA_LAYER_SYNC
 #undef SA_WAIT
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
+    if (threadIdx.x < 32) {
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "n"(TCOLS * NG) : "memory");
     }
 }
 
