@@ -876,7 +876,15 @@ static int gemm_attr() {
     return NIRRT_OK;
 }
 
-static int pick_bn(int N) { return N <= 256 ? N : N / 2; }
+// N tile per CTA (multiple of 16).  NIRRT_PN2_BN_MAX (development knob, default 256): narrower tiles need fewer accumulator
+// columns, so more CTAs fit next to each other, at the price of re-reading the A tile once per N tile.
+static int pick_bn(int N) {
+    static const int bn_max = getenv("NIRRT_PN2_BN_MAX") ? atoi(getenv("NIRRT_PN2_BN_MAX")) : 256;
+    if (bn_max >= 256 || bn_max < 32) return N <= 256 ? N : N / 2;
+    if (N <= bn_max) return N;
+    const int parts = (N + bn_max - 1) / bn_max;
+    return (((N + parts - 1) / parts) + 15) & ~15;
+}
 
 struct Conv {
     int K = 0, N = 0, BN = 0;      // padded dims (multiples of 16)
