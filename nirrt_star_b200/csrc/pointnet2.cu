@@ -957,6 +957,8 @@ struct nirrt_pn2 {
     int *fps_far = nullptr;         // [maxB]
     int *grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     __half *bufA = nullptr, *bufB = nullptr;
+    uint8_t *sa3_img[2] = {nullptr, nullptr};      // sa3: gather + first two layers fused (weight images of conv 12,13 / 15,16)
+    float *sa3_bias[2] = {nullptr, nullptr};
     uint8_t *fp_img = nullptr;      // fused fp1 + conv1 + head kernel: four 128 x 128 weight images (null: layer by layer)
     float *fp_bias = nullptr;
     uint8_t *sa_img[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // fused sa1 / sa2 kernels: swizzled weight
@@ -1202,6 +1204,38 @@ extern "C" int nirrt_pn2_create(const nirrt_pn2_layer *layers, int n_layers, int
                     cudaFuncSetAttribute(safused::k_fp1_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)safused::kFpSmem) != cudaSuccess)
                     FAILC("fused fp1: weight image upload failed");
             }
+        }
+        {
+            // sa3: [256 features + xyz -> 128 -> 196 (padded 208)] fused up to the second layer (NIRRT_PN2_SA3_FUSED=0: layer by layer)
+            const char *ff = getenv("NIRRT_PN2_SA3_FUSED");
+            bool ok = !(ff && atoi(ff) == 0) && h->fused_levels >= 2;
+            ok = ok && h->conv[12].K == 272 && h->conv[12].N == 128 && h->conv[13].N == 208 && h->conv[15].K == 272 && h->conv[15].N == 128 &&
+                 h->conv[16].N == 208;
+            for (int sc = 0; sc < 2 && ok; sc++) {
+                size_t bytes = 0;
+                for (int j = 0; j < 2; j++) { const Conv &c = h->conv[12 + sc * 3 + j]; bytes += (size_t)c.N * safused::nblk(c.K) * 128; }
+                std::vector<uint8_t> img(bytes, 0);
+                std::vector<float> bias;
+                size_t base = 0;
+                for (int j = 0; j < 2; j++) {
+                    const Conv &c = h->conv[12 + sc * 3 + j];
+                    for (int n = 0; n < c.N; n++)
+                        for (int k = 0; k < c.K; k++)
+                            memcpy(&img[base + safused::w_off(c.N, n, k >> 3) + (k & 7) * 2], &c.hw[(size_t)n * c.K + k], 2);
+                    bias.insert(bias.end(), c.hb.begin(), c.hb.end());
+                    base += (size_t)c.N * safused::nblk(c.K) * 128;
+                }
+                TRYC(palloc(h, &h->sa3_img[sc], img.size()));
+                TRYC(palloc(h, &h->sa3_bias[sc], bias.size()));
+                if (cudaMemcpy(h->sa3_img[sc], img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaMemcpy(h->sa3_bias[sc], bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+                    FAILC("fused sa3: weight image upload failed");
+            }
+            if (ok && (cudaFuncSetAttribute(safused::k_sa_fused<16, 256, 272, 128, 208, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)safused::Smem<272, 128, 208, 0>::kTotal) != cudaSuccess ||
+                       cudaFuncSetAttribute(safused::k_sa_fused<32, 256, 272, 128, 208, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)safused::Smem<272, 128, 208, 0>::kTotal) != cudaSuccess))
+                FAILC("fused sa3: cudaFuncSetAttribute failed");
         }
         if (h->fused_levels >= 2) {
             if (cudaFuncSetAttribute(safused::k_sa_fused<16, 96, 112, 64, 64, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1467,6 +1501,27 @@ extern "C" int nirrt_pn2_classify_device(nirrt_pn2 *h, int batch, int dim, const
             const int K = kK[sc];
             const int rows = B * S * K;
             const Conv &c0 = h->conv[li], &c1 = h->conv[li + 1], &c2 = h->conv[li + 2];
+            if (l == 3 && h->sa3_img[sc]) {
+                // gather + the first two layers in one kernel, then the last layer with the pooling epilogue
+                StageTimer t(h, s, 4);
+                safused::Args fa;
+                fa.in6 = h->in6; fa.feat = h->feat[l - 1]; fa.xyz = h->xyz[l - 1]; fa.new_xyz = h->xyz[l]; fa.gidx = h->grp[(l - 1) * 2 + sc];
+                fa.wimg = h->sa3_img[sc]; fa.bias = h->sa3_bias[sc];
+                fa.out = h->bufA; fa.N = N; fa.S = S; fa.B = B; fa.ldo = c1.N; fa.col_off = 0;
+                fa.tpc = S * K / 128; fa.chunk_tiles = fa.tpc; fa.chunk_lo = 0;
+                if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
+                const int ntiles = B * fa.tpc;
+                const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
+                if (sc == 0) safused::k_sa_fused<16, 256, 272, 128, 208, 0, 1><<<grid, 128, safused::Smem<272, 128, 208, 0>::kTotal, s>>>(fa);
+                else safused::k_sa_fused<32, 256, 272, 128, 208, 0, 1><<<grid, 128, safused::Smem<272, 128, 208, 0>::kTotal, s>>>(fa);
+                PCUDA(cudaGetLastError());
+                const int off = sc == 0 ? 0 : h->conv[li - 1].N;
+                PTRY(launch_gemm(c2, h->bufA, rows, umma::MODE_POOL, h->feat[l], kC[l], off, K, s));
+                h->launches += 2;
+                trace_mark("sa3_fused", l, sc, s);
+                li += 3;
+                continue;
+            }
             {
                 StageTimer t(h, s, 3);
                 if (l == 1) {

@@ -103,8 +103,11 @@ struct Smem {
 // images and each owns an operand tile, an mbarrier and TCOLS accumulator columns: where the weights are what limits the number
 // of CTAs per SM (sa2: 40-60 KB of weights next to a 32 KB tile), NG = 4 keeps four tiles in flight per SM instead of two or
 // three, so that one group's gather and epilogues overlap the others' round trips.
+// N3 == 0: two layers only -- the fp16 activations of the second layer are written to a.out as rows [row][N2] (ld a.ldo) for a
+// following umma::k_gemm with the pooling epilogue.  Used for sa3, whose first two weight matrices (80 + 52 KB) fit next to the
+// 80 KB operand tile while the third does not: the gathered operand and the first activation never touch HBM.
 template <int G, int C, int K0, int N1, int N2, int N3, int NG>
-__global__ void __launch_bounds__(128 * NG) k_sa_fused(const Args a) {
+__global__ void __launch_bounds__(128 * NG, (N3 == 0 || NG > 1) ? 1 : 8) k_sa_fused(const Args a) {
     typedef Smem<K0, N1, N2, N3> SM;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -214,11 +217,32 @@ __global__ void __launch_bounds__(128 * NG) k_sa_fused(const Args a) {
             issue<N1, N2>(tmem_base, sa_u, sw2_u, bar);
         }
         SA_WAIT()
+        if (N3 == 0) {
+            // ---- two-layer mode: relu(. + bias) -> fp16 -> this thread's row of the activation buffer
+            __half *orow = a.out + (size_t)((unsigned)tile * 128u + (unsigned)tid) * a.ldo;
+#pragma unroll 1
+            for (int h = 0; h < N2; h += 16) {
+                uint32_t u[16];
+                umma::tmem_ld16(taddr + h, u);
+                uint32_t p[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float x0 = fmaxf(__uint_as_float(u[2 * i]) + s_bias[N1 + h + 2 * i], 0.f);
+                    const float x1 = fmaxf(__uint_as_float(u[2 * i + 1]) + s_bias[N1 + h + 2 * i + 1], 0.f);
+                    p[i] = umma::pack_half2_sat(x0, x1);
+                }
+                *reinterpret_cast<uint4 *>(orow + h) = make_uint4(p[0], p[1], p[2], p[3]);
+                *reinterpret_cast<uint4 *>(orow + h + 8) = make_uint4(p[4], p[5], p[6], p[7]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            group_sync();         // every accumulator row has been read before the next tile's first MMA
+            continue;
+        }
         epilogue_to_operand<N2>(taddr, sA, tid, s_bias + N1);
         SA_LAYER_SYNC()
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue<N2, N3>(tmem_base, sa_u, sw3_u, bar);
+            issue<N2, (N3 > 0 ? N3 : 16)>(tmem_base, sa_u, sw3_u, bar);
         }
         SA_WAIT()
         // ---- last layer: max over the G rows of each group, then bias + ReLU (they commute with max)
