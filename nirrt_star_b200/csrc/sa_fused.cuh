@@ -63,11 +63,14 @@ __device__ __forceinline__ void epilogue_to_operand(uint32_t taddr, uint8_t *sA,
         else umma::tmem_ld16(taddr + h, u);
 #pragma unroll
         for (int q = 0; q < W; q += 8) {
+            // the biases of 8 columns as two 16-byte shared-memory loads (layer offsets are multiples of 16 floats)
+            const float4 b0 = *reinterpret_cast<const float4 *>(bias + h + q), b1 = *reinterpret_cast<const float4 *>(bias + h + q + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint32_t p[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float a = fmaxf(__uint_as_float(u[q + 2 * i]) + bias[h + q + 2 * i], 0.f);
-                const float b = fmaxf(__uint_as_float(u[q + 2 * i + 1]) + bias[h + q + 2 * i + 1], 0.f);
+                const float a = fmaxf(__uint_as_float(u[q + 2 * i]) + bb[2 * i], 0.f);
+                const float b = fmaxf(__uint_as_float(u[q + 2 * i + 1]) + bb[2 * i + 1], 0.f);
                 p[i] = umma::pack_half2_sat(a, b);
             }
             *reinterpret_cast<uint4 *>(sA + a_off(r, (h + q) >> 3)) = make_uint4(p[0], p[1], p[2], p[3]);
@@ -226,10 +229,10 @@ __global__ void __launch_bounds__(128 * NG, (N3 == 0 || NG > 1) ? 1 : 8) k_sa_fu
                 umma::tmem_ld16(taddr + h, u);
                 uint32_t p[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float x0 = fmaxf(__uint_as_float(u[2 * i]) + s_bias[N1 + h + 2 * i], 0.f);
-                    const float x1 = fmaxf(__uint_as_float(u[2 * i + 1]) + s_bias[N1 + h + 2 * i + 1], 0.f);
-                    p[i] = umma::pack_half2_sat(x0, x1);
+                for (int i = 0; i < 8; i += 2) {
+                    const float4 bv = *reinterpret_cast<const float4 *>(s_bias + N1 + h + 2 * i);
+                    p[i] = umma::pack_half2_sat(fmaxf(__uint_as_float(u[2 * i]) + bv.x, 0.f), fmaxf(__uint_as_float(u[2 * i + 1]) + bv.y, 0.f));
+                    p[i + 1] = umma::pack_half2_sat(fmaxf(__uint_as_float(u[2 * i + 2]) + bv.z, 0.f), fmaxf(__uint_as_float(u[2 * i + 3]) + bv.w, 0.f));
                 }
                 *reinterpret_cast<uint4 *>(orow + h) = make_uint4(p[0], p[1], p[2], p[3]);
                 *reinterpret_cast<uint4 *>(orow + h + 8) = make_uint4(p[4], p[5], p[6], p[7]);
@@ -417,13 +420,16 @@ __global__ void __launch_bounds__(256, 1) k_fp1_fused(const FpArgs a) {
             uint32_t u[32];
             umma::tmem_ld32(taddr + h, u);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                const float x0 = fmaxf(__uint_as_float(u[i]) + s_bias[3 * kFpC + h + i], 0.f);
-                const float x1 = fmaxf(__uint_as_float(u[i + 1]) + s_bias[3 * kFpC + h + i + 1], 0.f);
-                const uint32_t pk = umma::pack_half2_sat(x0, x1);
-                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&pk));
-                z0 = fmaf(f.x, s_w2[h + i], z0); z0 = fmaf(f.y, s_w2[h + i + 1], z0);
-                z1 = fmaf(f.x, s_w2[kFpC + h + i], z1); z1 = fmaf(f.y, s_w2[kFpC + h + i + 1], z1);
+            for (int i = 0; i < 32; i += 4) {            // bias and head weights of 4 columns per 16-byte shared-memory load
+                const float4 bv = *reinterpret_cast<const float4 *>(s_bias + 3 * kFpC + h + i);
+                const float4 wa = *reinterpret_cast<const float4 *>(s_w2 + h + i), wb = *reinterpret_cast<const float4 *>(s_w2 + kFpC + h + i);
+                const float x0 = fmaxf(__uint_as_float(u[i]) + bv.x, 0.f), x1 = fmaxf(__uint_as_float(u[i + 1]) + bv.y, 0.f);
+                const float x2 = fmaxf(__uint_as_float(u[i + 2]) + bv.z, 0.f), x3 = fmaxf(__uint_as_float(u[i + 3]) + bv.w, 0.f);
+                const uint32_t pk0 = umma::pack_half2_sat(x0, x1), pk1 = umma::pack_half2_sat(x2, x3);
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&pk0));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&pk1));
+                z0 = fmaf(f0.x, wa.x, z0); z0 = fmaf(f0.y, wa.y, z0); z0 = fmaf(f1.x, wa.z, z0); z0 = fmaf(f1.y, wa.w, z0);
+                z1 = fmaf(f0.x, wb.x, z1); z1 = fmaf(f0.y, wb.y, z1); z1 = fmaf(f1.x, wb.z, z1); z1 = fmaf(f1.y, wb.w, z1);
             }
         }
         if (valid) {
