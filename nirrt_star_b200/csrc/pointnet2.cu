@@ -4,12 +4,15 @@
 // Stages of one forward (reference: pointnet_pointnet2/models/pointnet2.py:24-42):
 //   k_prep         pc_normalize + [xyz, start, goal, free] feature build   (pointnet2_wrapper.py:46-59)
 //   per SA level:  k_fps          farthest point sampling, 1 CTA / cloud    (pointnet2_utils.py:65-86)
-//                  k_ball_query   both radii, 1 warp / centroid             (pointnet2_utils.py:89-109)
-//                  k_group*       gather neighbours -> fp16 GEMM operand    (pointnet2_utils.py:246-253)
-//                  umma::k_gemm   3 x (conv1x1 + BN + ReLU) on tcgen05, max over K fused into the last
-//   per FP level:  k_interp       3-NN inverse-distance interpolation + skip concat (:298-311)
-//                  umma::k_gemm   conv1d + BN + ReLU chain
-//   head:          umma::k_gemm (conv1+bn1+relu), k_head (conv2, log_softmax, argmax, softmax[:,1])
+//                  k_ball_query   both radii: slab-pruned candidates, 1 thread / centroid (levels 1-3 of large batches),
+//                                 k_ball_query_bf / _warp exhaustive                       (pointnet2_utils.py:89-109)
+//     sa1, sa2:    safused::k_sa_fused   gather + 3 x (conv1x1 + BN + ReLU) + max over K in one tcgen05 kernel
+//     sa3:         safused::k_sa_fused (two-layer mode) + umma::k_gemm with the pooling epilogue
+//     sa4:         k_group (gather -> fp16 operand, pointnet2_utils.py:246-253) + 3 x umma::k_gemm
+//   fp4..fp2:      k_knn_pruned / k_interp<1>  3-NN search (geometry stream), k_interp<2> interpolation + skip concat
+//                  (:298-311), umma::k_gemm conv1d + BN + ReLU chain
+//   fp1 + head:    safused::k_fp1_fused   interpolation + 3 layers + conv1/bn1/relu + conv2, log_softmax, argmax,
+//                  softmax[:,1] in one kernel (layer by layer with NIRRT_PN2_FP_FUSED=0: umma::k_gemm + k_head)
 //
 // Everything between the input cloud and the per-point outputs stays in HBM/L2; activations and
 // weights are fp16 (K-major rows), accumulation fp32 in TMEM, coordinates enter the first

@@ -4,10 +4,11 @@
 // per tile.  The tile's activations never leave the SM: the gathered operand and every intermediate
 // layer live in one shared-memory tile in the tcgen05 K-major / 128-byte-swizzle layout (one 16 KB
 // block per 64 channels), the accumulators in TMEM; the weights of all three layers are copied into
-// shared memory once per CTA.  Used for sa1 (6 input channels) and sa2 (96); the wider levels keep
-// their weights in L2 and go through umma::k_gemm.
+// shared memory once per CTA.  Used for sa1 (6 input channels) and sa2 (96), for sa3 up to its second
+// layer (N3 = 0), and -- k_fp1_fused below -- for fp1 + conv1 + the classifier head; the remaining
+// layers keep their weights in L2 and go through umma::k_gemm.
 //
-//   128 threads, thread = row = TMEM lane.  Per layer: all threads write their row of the operand,
+//   Groups of 128 threads (NG per CTA), thread = row = TMEM lane of its group's tile.  Per layer: all threads write their row of the operand,
 //   fence.proxy.async + __syncthreads, thread 0 issues the tcgen05.mma instructions (K / 16 of them)
 //   and commits to an mbarrier, all threads wait, tcgen05.ld their accumulator row.  Several CTAs per
 //   SM hide each other's round trips.
