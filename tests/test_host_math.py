@@ -209,3 +209,35 @@ def test_geometry2d_matches_reference_golden(hh, env_idx):
     out = np.zeros(len(pts), dtype=np.uint8)
     hh.hh_inside2(len(pts), dpp(pts), u8(out)); assert np.array_equal(out.astype(bool), g["inside"])
     hh.hh_valid2(len(pts), dpp(pts), u8(out)); assert np.array_equal(out.astype(bool), g["valid"])
+
+
+def test_ellipsoid_parameters_of_the_device_cloud_sampler():
+    """batch.ellipsoid_params_{2d,3d}: the 12 host-side numbers of ellipsoid_point_cloud_sampling{,_3d}
+    (datasets/point_cloud_mask_utils.py:104-133, datasets_3d/point_cloud_mask_utils_3d.py:132-160).  M = C @ L with C a proper
+    rotation whose first column is the start -> goal direction and L = diag(c_max / 2, b, b), b = sqrt(c_max^2 - c_min^2) / 2;
+    the centre is the midpoint (z = 0 in 2D)."""
+    from nirrt_star_b200.batch import ellipsoid_params_2d, ellipsoid_params_3d
+    rs = np.random.RandomState(4)
+    for _ in range(50):
+        a, b = rs.uniform(0, 50, 3), rs.uniform(0, 50, 3)
+        ratio = rs.uniform(1.0005, 3.0)
+        p = ellipsoid_params_3d(a, b, ratio)
+        M, centre = p[:9].reshape(3, 3), p[9:]
+        c_min = np.linalg.norm(b - a); c_max = c_min * ratio
+        semi = np.array([c_max / 2, np.sqrt(c_max ** 2 - c_min ** 2) / 2, np.sqrt(c_max ** 2 - c_min ** 2) / 2])
+        C = M / semi
+        assert np.allclose(C.T @ C, np.eye(3), atol=1e-12) and abs(np.linalg.det(C) - 1) < 1e-12
+        assert np.allclose(C[:, 0], (b - a) / c_min, atol=1e-12)
+        assert np.array_equal(centre, (a + b) / 2.)
+        # the foci are on the boundary's major axis: |x - start| + |x - goal| = c_max at the tip of the first semi-axis
+        tip = centre + M[:, 0]
+        assert abs(np.linalg.norm(tip - a) + np.linalg.norm(tip - b) - c_max) < 1e-9 * c_max
+        a2, b2 = a[:2], b[:2]
+        q = ellipsoid_params_2d(a2, b2, ratio)
+        M2, centre2 = q[:9].reshape(3, 3), q[9:]
+        c_min2 = math.hypot(*(b2 - a2)); c_max2 = c_min2 * ratio
+        semi2 = np.array([c_max2 / 2, math.sqrt(c_max2 ** 2 - c_min2 ** 2) / 2, math.sqrt(c_max2 ** 2 - c_min2 ** 2) / 2])
+        C2 = M2 / semi2
+        assert np.allclose(C2.T @ C2, np.eye(3), atol=1e-12)
+        assert np.allclose(C2[:2, 0], (b2 - a2) / c_min2, atol=1e-12) and abs(C2[2, 0]) < 1e-15
+        assert np.array_equal(centre2, np.concatenate([(a2 + b2) / 2., [0.]]))
